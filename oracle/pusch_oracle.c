@@ -1,0 +1,853 @@
+/* TEST INFRASTRUCTURE - NOT PRODUCT CODE. See pusch_oracle.h for scope, parity status and usage rules.
+ *
+ * Plain-C restatement of the reference algorithm, written from the behaviour of the files cited at each function
+ * (paths relative to /root/reference/srsRAN-5G-ER/). Scalar, single-threaded, no SIMD: the point is clarity.
+ */
+#define _POSIX_C_SOURCE 199309L
+#include "pusch_oracle.h"
+#include "bg_tables.inc"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define MAX_Z 384
+#define MAX_NFULL 68
+#define MAX_M 46
+#define MAX_DEG 19
+#define LLR_MAX 120
+#define LLR_INF 127
+#define MAX_CB_SIZE (66 * MAX_Z)
+#define MAX_CB_BYTES (22 * MAX_Z / 8)
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* LLR algebra - include/srsran/phy/upper/log_likelihood_ratio.h:46-244, lib/phy/upper/log_likelihood_ratio.cpp:40-87. */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+/* isinf: anything outside [-120, 120] (log_likelihood_ratio.h:159-165). */
+static int is_inf(int v)
+{
+  return (v > LLR_MAX) || (v < -LLR_MAX);
+}
+
+/* log_likelihood_ratio::operator+ : opposite values cancel, infinities are sticky, otherwise saturate at +-120.
+ * "a + b" is evaluated by the reference as "b += a" (log_likelihood_ratio.h:103-107), so an infinite b wins over an
+ * infinite a; the negation wraps in int8 like the reference's unary minus. */
+static int8_t llr_add(int a, int b)
+{
+  if (b == (int8_t)(-a)) {
+    return 0;
+  }
+  if (is_inf(b)) {
+    return (int8_t)b;
+  }
+  if (is_inf(a)) {
+    return (int8_t)a;
+  }
+  int s = a + b;
+  if (s > LLR_MAX) {
+    s = LLR_MAX;
+  }
+  if (s < -LLR_MAX) {
+    s = -LLR_MAX;
+  }
+  return (int8_t)s;
+}
+
+/* What the SIMD dematchers do on whole blocks: saturating int8 add, then clamp to +-120, no infinity rules
+ * (ldpc/ldpc_rate_dematcher_avx512_impl.cpp:45-59, ldpc/ldpc_rate_dematcher_avx2_impl.cpp:45-59). */
+static int8_t simd_add(int a, int b)
+{
+  int s = a + b;
+  if (s > 127) {
+    s = 127;
+  }
+  if (s < -128) {
+    s = -128;
+  }
+  if (s > LLR_MAX) {
+    s = LLR_MAX;
+  }
+  if (s < -LLR_MAX) {
+    s = -LLR_MAX;
+  }
+  return (int8_t)s;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* CRC - crc_calculator_generic_impl.cpp:29-57 (polynomials), :111-133 (bitwise remainder).                            */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+static void crc_params(int kind, uint32_t* poly, int* order)
+{
+  switch (kind) {
+    case ORC_CRC16:
+      *poly  = 0x11021;
+      *order = 16;
+      break;
+    case ORC_CRC24A:
+      *poly  = 0x1864CFB;
+      *order = 24;
+      break;
+    default:
+      *poly  = 0x1800063;
+      *order = 24;
+      break;
+  }
+}
+
+static int get_bit(const uint8_t* packed, int i)
+{
+  return (packed[i >> 3] >> (7 - (i & 7))) & 1;
+}
+
+static void put_bit(uint8_t* packed, int i, int b)
+{
+  uint8_t m = (uint8_t)(0x80 >> (i & 7));
+  if (b) {
+    packed[i >> 3] |= m;
+  } else {
+    packed[i >> 3] &= (uint8_t)~m;
+  }
+}
+
+uint32_t orc_crc(int crc_kind, const uint8_t* packed, int nbits)
+{
+  uint32_t poly;
+  int      order;
+  crc_params(crc_kind, &poly, &order);
+  uint32_t top = 1u << order;
+  uint32_t reg = 0;
+  for (int i = 0; i != nbits + order; ++i) {
+    int b = (i < nbits) ? get_bit(packed, i) : 0;
+    reg   = (reg << 1) | (uint32_t)b;
+    if (reg & top) {
+      reg ^= poly;
+    }
+  }
+  return reg & (top - 1);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Rate dematcher.                                                                                                     */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+/* combine_softbits over one chunk: generic ldpc_rate_dematcher_impl.cpp:116-126; SIMD variants process
+ * floor(len/width) blocks with simd_add and the remaining tail with the generic rule. */
+static void combine_chunk(int8_t* out, const int8_t* in, int len, int simd_width)
+{
+  int n_simd = (simd_width > 0) ? (len / simd_width) * simd_width : 0;
+  for (int i = 0; i != n_simd; ++i) {
+    out[i] = simd_add(out[i], in[i]);
+  }
+  for (int i = n_simd; i != len; ++i) {
+    out[i] = llr_add(out[i], in[i]);
+  }
+}
+
+void orc_rate_dematch(int8_t*       out,
+                      int           N,
+                      const int8_t* in,
+                      int           E,
+                      int           new_data,
+                      int           rv,
+                      int           qm,
+                      int           nref,
+                      int           nof_filler,
+                      int           simd_width)
+{
+  static const double sf_bg1[4] = {0, 17, 33, 56};
+  static const double sf_bg2[4] = {0, 13, 25, 43};
+
+  /* ldpc_rate_dematcher_impl.cpp:61-105: circular buffer length, base graph from N, k0. */
+  int           Ncb = (nref > 0) ? ((nref < N) ? nref : N) : N;
+  const double* sf;
+  int           n_short, k_b;
+  if (N % 66 == 0) {
+    sf      = sf_bg1;
+    n_short = 66;
+    k_b     = 22;
+  } else {
+    sf      = sf_bg2;
+    n_short = 50;
+    k_b     = 10;
+  }
+  int Z     = N / n_short;
+  int K_sys = (k_b - 2) * Z;
+  int info  = K_sys - nof_filler;
+  int k0    = (int)((uint16_t)floor((sf[rv] * Ncb) / N)) * Z;
+
+  /* Deinterleaver :203-257: out[(E/Qm) j + i] = in[i Qm + j]. */
+  int8_t* deint = NULL;
+  if (qm > 1) {
+    deint = (int8_t*)malloc((size_t)E);
+    int K = E / qm;
+    for (int i = 0; i != K; ++i) {
+      for (int j = 0; j != qm; ++j) {
+        deint[K * j + i] = in[i * qm + j];
+      }
+    }
+    in = deint;
+  }
+
+  /* allot_llrs :128-201. The walk below keeps the reference's order of side effects, including the ones that look
+   * accidental: in copy mode out[0, idx) is zeroed every time an information chunk is written, out[0, info) is zeroed
+   * when the walk starts beyond the information bits, the final zeroing addresses the LAST (Ncb - idx) entries of the
+   * N-long buffer, and positions in [Ncb, N) or skipped by k0 are otherwise left as they were. */
+  int copy_mode = new_data;
+  int idx       = k0;
+  int left      = E;
+  while (left > 0) {
+    if (idx < info) {
+      int n = info - idx;
+      if (n > left) {
+        n = left;
+      }
+      if (copy_mode) {
+        memset(out, 0, (size_t)idx);
+        memcpy(out + idx, in, (size_t)n);
+      } else {
+        combine_chunk(out + idx, in, n, simd_width);
+      }
+      idx += n;
+      in += n;
+      left -= n;
+    } else if (copy_mode) {
+      memset(out, 0, (size_t)info);
+    }
+    if (copy_mode) {
+      memset(out + info, LLR_INF, (size_t)nof_filler);
+    }
+    if (idx < K_sys) {
+      idx = K_sys;
+    }
+    int n = Ncb - idx;
+    if (n > left) {
+      n = left;
+    }
+    if (copy_mode) {
+      memcpy(out + idx, in, (size_t)n);
+    } else {
+      combine_chunk(out + idx, in, n, simd_width);
+    }
+    idx = (idx + n) % Ncb;
+    in += n;
+    left -= n;
+    if (left > 0) {
+      copy_mode = 0;
+    }
+  }
+  if (copy_mode && (idx != 0)) {
+    memset(out + N - (Ncb - idx), 0, (size_t)(Ncb - idx));
+  }
+  free(deint);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Base graph access.                                                                                                  */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+typedef struct {
+  int n_full, n_short, k_b, m;
+  int deg[MAX_M];
+  int col[MAX_M][MAX_DEG];
+  int shift[MAX_M][MAX_DEG];
+} graph_t;
+
+static int set_index_of(int Z)
+{
+  for (int i = 0; i != NR_LDPC_NOF_LIFTING_SIZES; ++i) {
+    if (NR_LDPC_LIFTING_SIZES[i] == Z) {
+      return NR_LDPC_SET_INDEX[i];
+    }
+  }
+  return -1;
+}
+
+/* ldpc_graph_impl.h:64-78 + ldpc_luts_impl.cpp:4521-4544: shift = V mod Z, edges of a row in ascending column order. */
+static void build_graph(graph_t* g, int bg, int Z)
+{
+  int ls               = set_index_of(Z);
+  int n_edges          = (bg == 1) ? BG1_NOF_EDGES : BG2_NOF_EDGES;
+  const unsigned short(*e)[10] = (bg == 1) ? BG1_EDGES : BG2_EDGES;
+  g->n_full            = (bg == 1) ? 68 : 52;
+  g->n_short           = (bg == 1) ? 66 : 50;
+  g->k_b               = (bg == 1) ? 22 : 10;
+  g->m                 = (bg == 1) ? 46 : 42;
+  memset(g->deg, 0, sizeof(g->deg));
+  for (int i = 0; i != n_edges; ++i) {
+    int m              = e[i][0];
+    int d              = g->deg[m]++;
+    g->col[m][d]       = e[i][1];
+    g->shift[m][d]     = e[i][2 + ls] % Z;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* LDPC decoder.                                                                                                       */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+static int scale_c2v(int x, int mode)
+{
+  switch (mode) {
+    case ORC_SCALE_GENERIC:
+      return (int)roundf((float)x * 0.8f);
+    case ORC_SCALE_NEON:
+      return (x * 204) >> 8;
+    default:
+      return (x * 52428) >> 16;
+  }
+}
+
+int orc_ldpc_decode(int           bg,
+                    int           Z,
+                    const int8_t* in,
+                    int           n_in,
+                    int           nof_filler,
+                    int           crc_kind,
+                    int           max_iter,
+                    int           scale_mode,
+                    uint8_t*      out,
+                    int8_t*       soft_out)
+{
+  graph_t* g = (graph_t*)malloc(sizeof(graph_t));
+  build_graph(g, bg, Z);
+  int K = g->k_b * Z;
+
+  /* ldpc_decoder_impl.cpp:85-94: trim trailing zeros; an all-zero input cannot be decoded. */
+  int trimmed = n_in;
+  while ((trimmed > 0) && (in[trimmed - 1] == 0)) {
+    --trimmed;
+  }
+  if (trimmed == 0) {
+    if (crc_kind == ORC_CRC_NONE) {
+      memset(out, 0xff, (size_t)((K + 7) / 8));
+      if (K % 8) {
+        out[K / 8] = (uint8_t)(0xff << (8 - K % 8));
+      }
+    }
+    free(g);
+    return 0;
+  }
+
+  /* load_soft_bits :149-184: two punctured nodes at zero, full nodes clamped to +-64, a partial last node copied
+   * unclamped (the reference leaves the rest of that node as it was; a fresh decoder has zeros there). */
+  int8_t* soft = (int8_t*)calloc((size_t)(MAX_NFULL * MAX_Z), 1);
+  int     full = (n_in / Z) * Z;
+  for (int i = 0; i != full; ++i) {
+    int v = in[i];
+    if (v > 64) {
+      v = 64;
+    }
+    if (v < -64) {
+      v = -64;
+    }
+    soft[2 * Z + i] = (int8_t)v;
+  }
+  for (int i = full; i != n_in; ++i) {
+    soft[2 * Z + i] = in[i];
+  }
+
+  /* :103-114: number of layers actually processed. */
+  int cb_len = trimmed + 2 * Z;
+  if (cb_len < K + 4 * Z) {
+    cb_len = K + 4 * Z;
+  }
+  if (cb_len % Z != 0) {
+    cb_len = (cb_len / Z + 1) * Z;
+  }
+  int layers = cb_len / Z - g->k_b;
+
+  /* Check-to-variable messages, all zero = "not initialised" (:206-210: the first visit copies the soft bits). */
+  int8_t(*c2v)[MAX_DEG][MAX_Z] = calloc((size_t)MAX_M, sizeof(*c2v));
+  int8_t(*v2c)[MAX_Z]          = calloc((size_t)MAX_DEG, sizeof(*v2c));
+
+  int result = 0;
+  for (int it = 0; it != max_iter; ++it) {
+    for (int m = 0; m != layers; ++m) {
+      int deg = g->deg[m];
+      /* update_variable_to_check_messages :186-229 with compute_var_to_check_msgs (avx512 :81-121). */
+      for (int e = 0; e != deg; ++e) {
+        const int8_t* s = soft + g->col[m][e] * Z;
+        for (int j = 0; j != Z; ++j) {
+          int d = s[j] - c2v[m][e][j];
+          if (d > LLR_MAX) {
+            d = LLR_MAX;
+          }
+          if (d < -LLR_MAX) {
+            d = -LLR_MAX;
+          }
+          if (s[j] >= LLR_INF) {
+            d = LLR_INF;
+          }
+          if (s[j] <= -LLR_INF) {
+            d = -LLR_INF;
+          }
+          v2c[e][j] = (int8_t)d;
+        }
+      }
+      /* update_check_to_variable_messages :246-318: per lifted check j, scan the row in adjacency order. */
+      for (int j = 0; j != Z; ++j) {
+        int min1 = LLR_MAX, min2 = LLR_MAX, arg = 0, par = 0;
+        for (int e = 0; e != deg; ++e) {
+          int x = v2c[e][(j + g->shift[m][e]) % Z];
+          int a = abs(x);
+          if (a < min2) {
+            min2 = (a < min1) ? min1 : a;
+          }
+          if (a < min1) {
+            min1 = a;
+            arg  = e;
+          }
+          par ^= (x < 0);
+        }
+        int s1 = scale_c2v(min1, scale_mode);
+        int s2 = scale_c2v(min2, scale_mode);
+        for (int e = 0; e != deg; ++e) {
+          int pos = (j + g->shift[m][e]) % Z;
+          int x   = v2c[e][pos];
+          int mag = (arg == e) ? s2 : s1;
+          c2v[m][e][pos] = (int8_t)((par ^ (x < 0)) ? -mag : mag);
+        }
+      }
+      /* update_soft_bits :231-244 with compute_soft_bits (avx512 :218-259) = promotion_sum (LLR.cpp:74-87). */
+      for (int e = 0; e != deg; ++e) {
+        int8_t* s = soft + g->col[m][e] * Z;
+        for (int j = 0; j != Z; ++j) {
+          int v = v2c[e][j];
+          int c = c2v[m][e][j];
+          int r;
+          if (is_inf(v)) {
+            r = (v > 0) ? LLR_INF : -LLR_INF;
+          } else {
+            r = v + c;
+            if (r > LLR_MAX) {
+              r = LLR_INF;
+            }
+            if (r < -LLR_MAX) {
+              r = -LLR_INF;
+            }
+          }
+          s[j] = (int8_t)r;
+        }
+      }
+    }
+    /* :125-134: hard decision (bit = soft <= 0, LLR.cpp:313-339), gate on "no zero soft bit", CRC over K - F bits. */
+    if (crc_kind != ORC_CRC_NONE) {
+      int no_zero = 1;
+      for (int i = 0; i != K; ++i) {
+        put_bit(out, i, soft[i] <= 0);
+        no_zero &= (soft[i] != 0);
+      }
+      if (no_zero && (orc_crc(crc_kind, out, K - nof_filler) == 0)) {
+        result = it + 1;
+        break;
+      }
+    }
+  }
+  if (crc_kind == ORC_CRC_NONE) {
+    for (int i = 0; i != K; ++i) {
+      put_bit(out, i, soft[i] <= 0);
+    }
+  }
+  if (soft_out) {
+    memcpy(soft_out, soft, (size_t)(g->n_full * Z));
+  }
+  free(v2c);
+  free(c2v);
+  free(soft);
+  free(g);
+  return result;
+}
+
+/* pusch_codeblock_decoder.cpp:35-71. */
+int orc_cb_decode(int8_t*       rm_buffer,
+                  int           N,
+                  const int8_t* in,
+                  int           E,
+                  int           new_data,
+                  int           rv,
+                  int           qm,
+                  int           nref,
+                  int           nof_filler,
+                  int           crc_kind,
+                  int           use_early_stop,
+                  int           max_iter,
+                  int           scale_mode,
+                  int           simd_width,
+                  uint8_t*      out)
+{
+  int bg = (N % 66 == 0) ? 1 : 2;
+  int Z  = N / ((bg == 1) ? 66 : 50);
+  int K  = ((bg == 1) ? 22 : 10) * Z;
+  orc_rate_dematch(rm_buffer, N, in, E, new_data, rv, qm, nref, nof_filler, simd_width);
+  if (use_early_stop) {
+    return orc_ldpc_decode(bg, Z, rm_buffer, N, nof_filler, crc_kind, max_iter, scale_mode, out, NULL);
+  }
+  orc_ldpc_decode(bg, Z, rm_buffer, N, nof_filler, ORC_CRC_NONE, max_iter, scale_mode, out, NULL);
+  return (orc_crc(crc_kind, out, K - nof_filler) == 0) ? max_iter : 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Segmentation - ldpc.h:128-228, ldpc_segmenter_impl.cpp:58-68, :254-331.                                             */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+static int tb_crc_bits(int tbs)
+{
+  return (tbs <= 3824) ? 16 : 24;
+}
+
+static int nof_codeblocks(int tbs, int bg)
+{
+  int b       = tbs + tb_crc_bits(tbs);
+  int max_seg = (bg == 1) ? 8448 : 3840;
+  return (b <= max_seg) ? 1 : (b + (max_seg - 24) - 1) / (max_seg - 24);
+}
+
+static int lifting_size_for(int tbs, int bg, int C)
+{
+  int b   = tbs + tb_crc_bits(tbs);
+  int ref = 22;
+  if (bg == 2) {
+    ref = (b > 640) ? 10 : (b > 560) ? 9 : (b > 192) ? 8 : 6;
+  }
+  int b_out = b + ((C > 1) ? 24 * C : 0);
+  for (int i = 0; i != NR_LDPC_NOF_LIFTING_SIZES; ++i) {
+    if (NR_LDPC_LIFTING_SIZES[i] * ref * C >= b_out) {
+      return NR_LDPC_LIFTING_SIZES[i];
+    }
+  }
+  return 0;
+}
+
+int orc_segment_rx(int tbs_bits, int bg, int qm, int nof_layers, int n_llr, orc_cb_meta* meta)
+{
+  int C        = nof_codeblocks(tbs_bits, bg);
+  int b_in     = tbs_bits + tb_crc_bits(tbs_bits);
+  int b_out    = b_in + ((C > 1) ? 24 * C : 0);
+  int Z        = lifting_size_for(tbs_bits, bg, C);
+  int K        = ((bg == 1) ? 22 : 10) * Z;
+  int crc_bits = (C > 1) ? 24 : 0;
+  int max_info = (b_out + C - 1) / C - crc_bits;
+  int sym_pl   = (n_llr / qm) / nof_layers;
+  int n_short  = C - (sym_pl % C);
+  int offset   = 0;
+  for (int i = 0; i != C; ++i) {
+    int per_cb           = (i < n_short) ? (sym_pl / C) : ((sym_pl + C - 1) / C);
+    meta[i].Z            = Z;
+    meta[i].full_length  = ((bg == 1) ? 3 : 5) * K;
+    meta[i].rm_length    = per_cb * nof_layers * qm;
+    meta[i].nof_filler   = K - (max_info + crc_bits);
+    meta[i].cw_offset    = offset;
+    meta[i].nof_crc_bits = (C == 1) ? tb_crc_bits(tbs_bits) : 24;
+    offset += meta[i].rm_length;
+  }
+  return C;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Transport-block decoder - pusch_decoder_impl.cpp.                                                                   */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+static void copy_bits(uint8_t* dst, int dst_off, const uint8_t* src, int src_off, int n)
+{
+  for (int i = 0; i != n; ++i) {
+    put_bit(dst, dst_off + i, get_bit(src, src_off + i));
+  }
+}
+
+void orc_pusch_decode(orc_harq*            harq,
+                      const int8_t*        llrs,
+                      int                  n_llr,
+                      int                  tb_bytes,
+                      const orc_pusch_cfg* cfg,
+                      int                  scale_mode,
+                      int                  simd_width,
+                      uint8_t*             tb_out,
+                      int*                 stats)
+{
+  orc_cb_meta meta[256];
+  int         tbs = tb_bytes * 8;
+  int         C   = orc_segment_rx(tbs, cfg->bg, cfg->qm, cfg->nof_layers, n_llr, meta);
+
+  /* select_crc :35-46. */
+  int crc_kind = (C > 1) ? ORC_CRC24B : ((tbs > 3824) ? ORC_CRC24A : ORC_CRC16);
+
+  /* new_data :131-135. */
+  if (cfg->new_data) {
+    memset(harq->crc_ok, 0, (size_t)C);
+  }
+
+  int n_obs = 0, it_min = 0, it_max = 0, it_sum = 0;
+  for (int cb = 0; cb != C; ++cb) {
+    int8_t*  rm  = harq->soft + (size_t)cb * MAX_CB_SIZE;
+    uint8_t* msg = harq->data + (size_t)cb * MAX_CB_BYTES;
+    int      N   = meta[cb].full_length;
+    /* fork_codeblock_task :335-345: codeblocks already decoded keep combining but are not decoded again. */
+    if (harq->crc_ok[cb]) {
+      orc_rate_dematch(rm, N, llrs + meta[cb].cw_offset, meta[cb].rm_length, cfg->new_data, cfg->rv, cfg->qm,
+                       cfg->nref, meta[cb].nof_filler, simd_width);
+      continue;
+    }
+    int it = orc_cb_decode(rm, N, llrs + meta[cb].cw_offset, meta[cb].rm_length, cfg->new_data, cfg->rv, cfg->qm,
+                           cfg->nref, meta[cb].nof_filler, crc_kind, cfg->use_early_stop, cfg->max_iter, scale_mode,
+                           simd_width, msg);
+    /* :357-363. */
+    int obs = it;
+    if (it > 0) {
+      harq->crc_ok[cb] = 1;
+    } else {
+      obs = cfg->max_iter;
+    }
+    it_min = (n_obs == 0 || obs < it_min) ? obs : it_min;
+    it_max = (n_obs == 0 || obs > it_max) ? obs : it_max;
+    it_sum += obs;
+    ++n_obs;
+  }
+
+  /* join_and_notify :384-450. */
+  int tb_ok = 0;
+  if (C == 1) {
+    tb_ok = harq->crc_ok[0];
+    if (tb_ok) {
+      memcpy(tb_out, harq->data, (size_t)tb_bytes);
+    }
+  } else {
+    int all = 1;
+    for (int cb = 0; cb != C; ++cb) {
+      all &= harq->crc_ok[cb];
+    }
+    if (all) {
+      /* concatenate_codeblocks :452-497. */
+      int      tb_off   = 0;
+      uint32_t checksum = 0;
+      for (int cb = 0; cb != C; ++cb) {
+        int            K        = meta[cb].full_length / ((cfg->bg == 1) ? 3 : 5);
+        int            n_data   = K - meta[cb].nof_crc_bits - meta[cb].nof_filler;
+        int            free_bits = tbs - tb_off;
+        int            n_new    = (free_bits < n_data) ? free_bits : n_data;
+        const uint8_t* msg      = harq->data + (size_t)cb * MAX_CB_BYTES;
+        copy_bits(tb_out, tb_off, msg, 0, n_new);
+        if (cb == C - 1) {
+          for (int i = 0; i != 24; ++i) {
+            checksum = (checksum << 1) | (uint32_t)get_bit(msg, n_new + i);
+          }
+        }
+        tb_off += n_new;
+      }
+      if (orc_crc(ORC_CRC24A, tb_out, tbs) == checksum) {
+        tb_ok = 1;
+      } else {
+        memset(harq->crc_ok, 0, (size_t)C);
+      }
+    }
+  }
+  stats[0] = tb_ok;
+  stats[1] = C;
+  stats[2] = n_obs;
+  stats[3] = it_min;
+  stats[4] = it_max;
+  stats[5] = it_sum;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* TX side (input synthesis only): TS 38.212 5.2.2 segmentation, 5.3.2 encoding, 5.4.2 rate matching.                  */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+/* acc[j] ^= v[(j + s) mod Z] */
+static void xor_rot(uint8_t* acc, const uint8_t* v, int s, int Z)
+{
+  for (int j = 0; j != Z; ++j) {
+    acc[j] ^= v[(j + s) % Z];
+  }
+}
+
+void orc_ldpc_encode(int bg, int Z, const uint8_t* msg, uint8_t* cw)
+{
+  graph_t* g = (graph_t*)malloc(sizeof(graph_t));
+  build_graph(g, bg, Z);
+  int      kb = g->k_b;
+  uint8_t* c  = (uint8_t*)calloc((size_t)(g->n_full * Z), 1);
+  memcpy(c, msg, (size_t)(kb * Z));
+
+  /* Core parity: rows 0..3, columns kb..kb+3. lam[i] = sum over information columns of row i. */
+  uint8_t lam[4][MAX_Z];
+  memset(lam, 0, sizeof(lam));
+  for (int i = 0; i != 4; ++i) {
+    for (int e = 0; e != g->deg[i]; ++e) {
+      if (g->col[i][e] < kb) {
+        xor_rot(lam[i], c + g->col[i][e] * Z, g->shift[i][e], Z);
+      }
+    }
+  }
+  /* Column kb appears in three core rows, two of them with the same shift: summing the four rows cancels everything
+   * but one rotated copy of p0. */
+  int sh[4], n_sh = 0;
+  for (int i = 0; i != 4; ++i) {
+    for (int e = 0; e != g->deg[i]; ++e) {
+      if (g->col[i][e] == kb) {
+        sh[n_sh++] = g->shift[i][e];
+      }
+    }
+  }
+  int d = (sh[0] == sh[1]) ? sh[2] : ((sh[0] == sh[2]) ? sh[1] : sh[0]);
+  uint8_t sum[MAX_Z];
+  for (int j = 0; j != Z; ++j) {
+    sum[j] = lam[0][j] ^ lam[1][j] ^ lam[2][j] ^ lam[3][j];
+  }
+  uint8_t* p0 = c + kb * Z;
+  for (int j = 0; j != Z; ++j) {
+    p0[(j + d) % Z] = sum[j];
+  }
+  /* Back-substitution: repeatedly take a core row with exactly one unknown core parity column. */
+  int known[4] = {1, 0, 0, 0};
+  for (int round = 0; round != 3; ++round) {
+    for (int i = 0; i != 4; ++i) {
+      int unknown = -1, n_unknown = 0, unknown_shift = 0;
+      for (int e = 0; e != g->deg[i]; ++e) {
+        int col = g->col[i][e];
+        if ((col >= kb) && (col < kb + 4) && !known[col - kb]) {
+          unknown       = col;
+          unknown_shift = g->shift[i][e];
+          ++n_unknown;
+        }
+      }
+      if (n_unknown != 1) {
+        continue;
+      }
+      uint8_t acc[MAX_Z];
+      memcpy(acc, lam[i], (size_t)Z);
+      for (int e = 0; e != g->deg[i]; ++e) {
+        int col = g->col[i][e];
+        if ((col >= kb) && (col < kb + 4) && known[col - kb]) {
+          xor_rot(acc, c + col * Z, g->shift[i][e], Z);
+        }
+      }
+      uint8_t* p = c + unknown * Z;
+      for (int j = 0; j != Z; ++j) {
+        p[(j + unknown_shift) % Z] = acc[j];
+      }
+      known[unknown - kb] = 1;
+    }
+  }
+  /* Extension parity: row m >= 4 has a single identity column kb + m. */
+  for (int m = 4; m != g->m; ++m) {
+    uint8_t* p = c + (kb + m) * Z;
+    for (int e = 0; e != g->deg[m]; ++e) {
+      if (g->col[m][e] != kb + m) {
+        xor_rot(p, c + g->col[m][e] * Z, g->shift[m][e], Z);
+      }
+    }
+  }
+  memcpy(cw, c + 2 * Z, (size_t)((g->n_full - 2) * Z));
+  free(c);
+  free(g);
+}
+
+void orc_rate_match(const uint8_t* cw, int N, int E, int rv, int qm, int nref, int nof_filler, uint8_t* out)
+{
+  static const double sf_bg1[4] = {0, 17, 33, 56};
+  static const double sf_bg2[4] = {0, 13, 25, 43};
+  int           Ncb  = (nref > 0) ? ((nref < N) ? nref : N) : N;
+  int           bg1  = (N % 66 == 0);
+  const double* sf   = bg1 ? sf_bg1 : sf_bg2;
+  int           Z    = N / (bg1 ? 66 : 50);
+  int           K_sys = ((bg1 ? 22 : 10) - 2) * Z;
+  int           k0   = (int)((uint16_t)floor((sf[rv] * Ncb) / N)) * Z;
+  uint8_t*      sel  = (uint8_t*)malloc((size_t)E);
+  int           idx  = k0 % Ncb;
+  for (int k = 0; k != E;) {
+    if ((idx >= K_sys - nof_filler) && (idx < K_sys)) {
+      idx = K_sys % Ncb;
+      continue;
+    }
+    sel[k++] = cw[idx];
+    idx      = (idx + 1) % Ncb;
+  }
+  int per = E / qm;
+  for (int i = 0; i != per; ++i) {
+    for (int j = 0; j != qm; ++j) {
+      out[i * qm + j] = sel[j * per + i];
+    }
+  }
+  free(sel);
+}
+
+int orc_tb_encode(const uint8_t* tb, int tb_bytes, int bg, int rv, int qm, int nref, int nof_layers, int n_llr,
+                  uint8_t* cw_bits)
+{
+  orc_cb_meta meta[256];
+  int         tbs      = tb_bytes * 8;
+  int         C        = orc_segment_rx(tbs, bg, qm, nof_layers, n_llr, meta);
+  int         tcrc     = tb_crc_bits(tbs);
+  int         b_in     = tbs + tcrc;
+  uint8_t*    tb_crc   = (uint8_t*)calloc((size_t)(b_in / 8 + 8), 1);
+  memcpy(tb_crc, tb, (size_t)tb_bytes);
+  uint32_t chk = orc_crc((tcrc == 16) ? ORC_CRC16 : ORC_CRC24A, tb, tbs);
+  for (int i = 0; i != tcrc; ++i) {
+    put_bit(tb_crc, tbs + i, (chk >> (tcrc - 1 - i)) & 1);
+  }
+  int      Z       = meta[0].Z;
+  int      K       = ((bg == 1) ? 22 : 10) * Z;
+  int      cb_crc  = (C > 1) ? 24 : 0;
+  int      info    = K - meta[0].nof_filler - cb_crc; /* bits taken per CB, incl. TB CRC and zero padding in the last */
+  uint8_t* seg     = (uint8_t*)malloc((size_t)(K / 8 + 8));
+  uint8_t* msg     = (uint8_t*)malloc((size_t)K);
+  uint8_t* cw      = (uint8_t*)malloc((size_t)(66 * MAX_Z));
+  int      tb_off  = 0;
+  for (int cb = 0; cb != C; ++cb) {
+    memset(seg, 0, (size_t)(K / 8 + 8));
+    int take = info;
+    if (tb_off + take > b_in) {
+      take = b_in - tb_off; /* the rest is zero padding */
+    }
+    copy_bits(seg, 0, tb_crc, tb_off, take);
+    tb_off += take;
+    if (cb_crc) {
+      uint32_t c = orc_crc(ORC_CRC24B, seg, info);
+      for (int i = 0; i != 24; ++i) {
+        put_bit(seg, info + i, (c >> (23 - i)) & 1);
+      }
+    }
+    for (int i = 0; i != K; ++i) {
+      msg[i] = (uint8_t)get_bit(seg, i);
+    }
+    orc_ldpc_encode(bg, Z, msg, cw);
+    orc_rate_match(cw, meta[cb].full_length, meta[cb].rm_length, rv, qm, nref, meta[cb].nof_filler,
+                   cw_bits + meta[cb].cw_offset);
+  }
+  free(cw);
+  free(msg);
+  free(seg);
+  free(tb_crc);
+  return C;
+}
+
+double orc_bench_cb_batch(int           n_cb,
+                          const int8_t* llrs,
+                          int           E,
+                          int           N,
+                          int           rv,
+                          int           qm,
+                          int           nref,
+                          int           nof_filler,
+                          int           crc_kind,
+                          int           use_early_stop,
+                          int           max_iter,
+                          int*          iters_out)
+{
+  int8_t*         rm = (int8_t*)malloc((size_t)N);
+  uint8_t         bits[MAX_CB_BYTES + 8];
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int cb = 0; cb != n_cb; ++cb) {
+    int it = orc_cb_decode(rm, N, llrs + (size_t)cb * E, E, 1, rv, qm, nref, nof_filler, crc_kind, use_early_stop,
+                           max_iter, ORC_SCALE_X86, 64, bits);
+    if (iters_out) {
+      iters_out[cb] = it;
+    }
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  free(rm);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
