@@ -1,0 +1,239 @@
+/*
+ * pusch_dec_cuda.h - C ABI of the B200 (sm_100a) uplink PUSCH decode path.
+ *
+ * Rate dematching + HARQ soft combining -> 5G NR LDPC layered normalized min-sum decoding with CRC early stop ->
+ * codeblock / transport-block CRC, batched over every codeblock of a slot. Plain pointers and sizes only; no C++,
+ * CUDA runtime or torch types cross this boundary. Every function returns PDC_OK (0) or a negative error code and never
+ * throws; there is no CPU fallback - if no CUDA device is usable, pdc_create fails.
+ *
+ * Each entry point names the reference interface it stands behind (paths relative to /root/reference/srsRAN-5G-ER/):
+ *
+ *   ldpc_decoder::decode                  include/srsran/phy/upper/channel_coding/ldpc/ldpc_decoder.h:73-74
+ *   ldpc_rate_dematcher::rate_dematch     include/srsran/phy/upper/channel_coding/ldpc/ldpc_rate_dematcher.h:52-55
+ *   crc_calculator::calculate             include/srsran/phy/upper/channel_coding/crc_calculator.h:62-84
+ *   hal::hw_accelerator_pusch_dec         include/srsran/hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec.h:36-115
+ *   hal::hw_accelerator<int8_t,uint8_t>   include/srsran/hal/hw_accelerator.h:35-57
+ *   pusch_decoder (batched)               include/srsran/phy/upper/channel_processors/pusch/pusch_decoder.h:54-99
+ *   rx_buffer (HARQ state)                include/srsran/phy/upper/rx_buffer.h:42-81
+ *
+ * INTEGRATION.md shows the C++ adapter classes that bind these calls behind create_ldpc_decoder_factory_sw("cuda"),
+ * create_ldpc_rate_dematcher_factory_sw("cuda") and the hal::hw_accelerator_pusch_dec factory.
+ */
+#ifndef PUSCH_DEC_CUDA_H
+#define PUSCH_DEC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDC_OK 0
+#define PDC_ERR_INVALID (-1)   /* bad argument or descriptor */
+#define PDC_ERR_CUDA (-2)      /* CUDA runtime error; pdc_last_error() has the text */
+#define PDC_ERR_CAPACITY (-3)  /* batch larger than the context was created for ("queue full": retry after a wait) */
+#define PDC_ERR_NO_DEVICE (-4) /* no usable sm_100 device */
+
+/* Largest lifted codeblock: 66 x 384 soft bits, 22 x 384 message bits. */
+#define PDC_MAX_CB_SOFT 25344
+#define PDC_MAX_CB_BYTES 1056
+
+/* CRC attached to a codeblock (hal::hw_dec_cb_crc_type, hw_accelerator_pusch_dec.h:36). */
+#define PDC_CRC_NONE 0
+#define PDC_CRC16 1
+#define PDC_CRC24A 2
+#define PDC_CRC24B 3
+
+/* Check-to-variable scaling rule = which reference decoder variant is reproduced bit for bit. */
+#define PDC_SCALE_X86 0     /* ldpc_decoder_avx2 / ldpc_decoder_avx512 ("auto" on any x86 host) - default */
+#define PDC_SCALE_GENERIC 1 /* ldpc_decoder_generic */
+#define PDC_SCALE_NEON 2    /* ldpc_decoder_neon */
+
+/* Per-codeblock flags. */
+#define PDC_CB_NEW_DATA 0x01   /* first transmission: copy instead of combine (rate_dematch new_data = true)          */
+#define PDC_CB_EARLY_STOP 0x02 /* check the CRC after every iteration (decode with a crc_calculator)                 */
+#define PDC_CB_DECODE 0x04     /* run the LDPC decoder; clear = dematch/combine only (codeblock already CRC-ok,
+                                  pusch_decoder_impl.cpp:335-345)                                                    */
+#define PDC_CB_DEMATCH 0x08    /* run the rate dematcher; clear = decode the HARQ entry as it is                     */
+
+/*
+ * One codeblock operation. Carries the fields of hal::hw_pusch_decoder_configuration
+ * (hw_accelerator_pusch_dec.h:39-72) / codeblock_metadata (include/srsran/phy/upper/codeblock_metadata.h:42-80).
+ */
+typedef struct {
+  uint32_t llr_offset;   /* first rate-matched LLR of this codeblock inside the batch LLR buffer                      */
+  uint32_t rm_length;    /* E: number of rate-matched LLRs (multiple of qm)                                           */
+  uint32_t harq_id;      /* absolute codeblock id = entry of the device HARQ arena (rx_buffer.h:58-65)                */
+  uint32_t nref;         /* limited-buffer length N_ref, 0 = unlimited                                                */
+  uint16_t lifting_size; /* Z                                                                                         */
+  uint16_t nof_filler;   /* F                                                                                         */
+  uint8_t  base_graph;   /* 1 or 2                                                                                    */
+  uint8_t  qm;           /* bits per symbol: 1, 2, 4, 6, 8                                                            */
+  uint8_t  rv;           /* redundancy version 0..3                                                                   */
+  uint8_t  crc_kind;     /* PDC_CRC16 / PDC_CRC24A / PDC_CRC24B                                                       */
+  uint8_t  max_iter;     /* LDPC iterations (ldpc_decoder::configuration::algorithm_details::max_iterations)          */
+  uint8_t  flags;        /* PDC_CB_*                                                                                  */
+  uint16_t tb_index;     /* transport block this codeblock belongs to (index into the pdc_tb_desc array), or 0xffff   */
+} pdc_cb_desc;
+
+/* Result of one codeblock (hal::hw_pusch_decoder_outputs, hw_accelerator_pusch_dec.h:75-80). */
+typedef struct {
+  uint8_t crc_ok;  /* CRC over the first K - F decoded bits is zero                                                   */
+  uint8_t iters;   /* iterations run: the early-stop iteration, else max_iter                                         */
+  uint8_t status;  /* 0 ok, 1 = all-zero input (not decodable, ldpc_decoder_impl.cpp:88-94), 2 = invalid descriptor   */
+  uint8_t nlayers; /* base-graph rows actually processed (ldpc_decoder_impl.cpp:114)                                  */
+} pdc_cb_result;
+
+/*
+ * One transport block of the batch: codeblocks first_cb .. first_cb + nof_cb - 1 of the descriptor array, in order.
+ * The device concatenates the decoded codeblocks and checks the TB CRC exactly as pusch_decoder_impl::join_and_notify
+ * does (pusch_decoder_impl.cpp:384-450, concatenate_codeblocks :452-497).
+ */
+typedef struct {
+  uint32_t first_cb;
+  uint32_t nof_cb;
+  uint32_t tbs_bits;      /* transport block size without CRC                                                         */
+  uint32_t out_offset;    /* byte offset of this TB inside the batch TB output buffer                                 */
+  uint32_t prev_ok_mask_offset; /* reserved, 0                                                                         */
+} pdc_tb_desc;
+
+typedef struct {
+  uint8_t  tb_crc_ok;
+  uint8_t  all_cb_ok;
+  uint16_t reserved;
+} pdc_tb_result;
+
+typedef struct {
+  int32_t  device;          /* CUDA device ordinal                                                                     */
+  uint32_t max_cbs;         /* largest batch, in codeblocks                                                            */
+  uint32_t max_llrs;        /* largest batch, in rate-matched LLRs                                                     */
+  uint32_t harq_entries;    /* device HARQ arena size in codeblocks (25344 soft bits + 1056 message bytes each)        */
+  uint32_t max_tbs;         /* largest number of transport blocks per batch (0 = codeblock interface only)             */
+  uint32_t max_tb_bytes;    /* bytes of TB output per batch                                                            */
+  int32_t  scale_mode;      /* PDC_SCALE_*                                                                             */
+  int32_t  combine_simd_width; /* 64 / 32 / 0: which reference dematcher's treatment of non-finite stale soft bits is
+                                  reproduced (avx512 / avx2 / generic); irrelevant for finite values                  */
+  uint32_t nof_streams;     /* independent in-flight batches ("hardware queues", reserve_queue/free_queue)             */
+} pdc_config;
+
+typedef struct pdc_ctx pdc_ctx;
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Context                                                                                                             */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+void pdc_default_config(pdc_config* cfg);
+int  pdc_create(const pdc_config* cfg, pdc_ctx** out);
+void pdc_destroy(pdc_ctx* ctx);
+/* Text of the last error on this thread. */
+const char* pdc_last_error(void);
+/* Library and device facts: sm count, sm major/minor, number of kernel launches issued so far by this context. */
+int pdc_device_info(pdc_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
+uint64_t pdc_launch_count(pdc_ctx* ctx);
+
+/* Pinned host memory for zero-copy-staging of LLR batches (the caller may also pass pageable memory, at a price). */
+void* pdc_host_alloc(size_t bytes);
+void  pdc_host_free(void* p);
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Batched codeblock interface = hal::hw_accelerator_pusch_dec (enqueue_operation / dequeue_operation) and the batched */
+/* pusch_decoder. One batch per stream ("queue") at a time.                                                            */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+/*
+ * Enqueues one batch: H2D copy of the descriptors and of n_llrs LLRs, rate dematching into the HARQ arena, LDPC decoding,
+ * CB CRC, optional TB assembly + TB CRC, D2H copy of results, hard bits and TB bytes. Returns as soon as the work is
+ * queued on the stream. Host buffers must stay valid until pdc_wait returns.
+ *   cb_results[n_cb], cb_bits[n_cb * PDC_MAX_CB_BYTES] (may be NULL), tb_results[n_tb], tb_bytes (may be NULL).
+ */
+int pdc_submit(pdc_ctx*           ctx,
+               uint32_t           stream,
+               const pdc_cb_desc* cbs,
+               uint32_t           n_cb,
+               const int8_t*      llrs,
+               size_t             n_llrs,
+               const pdc_tb_desc* tbs,
+               uint32_t           n_tb,
+               pdc_cb_result*     cb_results,
+               uint8_t*           cb_bits,
+               pdc_tb_result*     tb_results,
+               uint8_t*           tb_bytes);
+/* Blocks until the batch on this stream is complete and its outputs are in the host buffers given to pdc_submit. */
+int pdc_wait(pdc_ctx* ctx, uint32_t stream);
+/* Non-blocking: *done = 1 when pdc_wait would not block. */
+int pdc_poll(pdc_ctx* ctx, uint32_t stream, int* done);
+
+/*
+ * Device-resident variant (measurement and pipelines that already hold LLRs in HBM): same work as pdc_submit without
+ * host copies. d_* are device pointers; cuda_stream is a cudaStream_t (0 = default stream); d_tb_* may be 0 when
+ * n_tb == 0. The host does not read the descriptors, so the caller states what the batch contains:
+ * max_lifting_size = largest Z, flags_union = OR of all pdc_cb_desc::flags, any_bg1 = some codeblock uses base graph 1.
+ */
+int pdc_launch_device(pdc_ctx*    ctx,
+                      const void* d_cbs,
+                      uint32_t    n_cb,
+                      const void* d_llrs,
+                      const void* d_tbs,
+                      uint32_t    n_tb,
+                      void*       d_cb_results,
+                      void*       d_cb_bits,
+                      void*       d_tb_results,
+                      void*       d_tb_bytes,
+                      uint32_t    max_lifting_size,
+                      uint32_t    flags_union,
+                      int         any_bg1,
+                      void*       cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* HARQ arena = device-resident rx_buffer soft bits ("external soft bits", rx_buffer_codeblock_pool.h:63-72).          */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+int pdc_harq_read(pdc_ctx* ctx, uint32_t harq_id, int8_t* soft, uint32_t n);
+int pdc_harq_write(pdc_ctx* ctx, uint32_t harq_id, const int8_t* soft, uint32_t n);
+/* free_harq_context_entry: the entry may be reused; contents are left as they are (the reference pool does not clear
+ * soft bits either, include/srsran/phy/upper/rx_buffer_pool.h:62-63). */
+int pdc_harq_free(pdc_ctx* ctx, uint32_t harq_id);
+/* Device address of the arena (harq_entries x PDC_MAX_CB_SOFT int8), for device-resident pipelines. */
+void* pdc_harq_device_ptr(pdc_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Synchronous single-codeblock calls = the "cuda" variants of ldpc_decoder / ldpc_rate_dematcher / crc_calculator.   */
+/* Latency path (one codeblock cannot fill a GPU); used for configs 1-2 parity and by the factory adapters.            */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+/*
+ * ldpc_decoder::decode. llrs[n_llrs] with K + 2Z <= n_llrs <= N; out receives ceil(K/8) bytes (bits MSB first).
+ * crc_kind = PDC_CRC_NONE reproduces decode(..., crc = nullptr, ...). *iters = iteration count when the CRC passed,
+ * 0 otherwise (the reference's empty optional).
+ */
+int pdc_ldpc_decode(pdc_ctx*      ctx,
+                    int           base_graph,
+                    int           lifting_size,
+                    const int8_t* llrs,
+                    uint32_t      n_llrs,
+                    uint32_t      nof_filler,
+                    int           crc_kind,
+                    int           max_iter,
+                    uint8_t*      out,
+                    int*          iters);
+
+/* ldpc_rate_dematcher::rate_dematch. buffer[N] is the in/out soft buffer in host memory, N = 66Z or 50Z. */
+int pdc_rate_dematch(pdc_ctx*      ctx,
+                     int8_t*       buffer,
+                     uint32_t      N,
+                     const int8_t* llrs,
+                     uint32_t      E,
+                     int           new_data,
+                     int           rv,
+                     int           qm,
+                     uint32_t      nref,
+                     uint32_t      nof_filler);
+
+/* crc_calculator::calculate over the first nbits (MSB first) of packed[]. */
+int pdc_crc(pdc_ctx* ctx, int crc_kind, const uint8_t* packed, uint32_t nbits, uint32_t* checksum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PUSCH_DEC_CUDA_H */

@@ -1,0 +1,261 @@
+"""ctypes binding of include/pusch_dec_cuda.h (the C-ABI of the CUDA library).
+
+The library is loaded from the package directory (in-tree build). There is no fallback: a missing library or a missing
+GPU raises.
+"""
+import ctypes
+from pathlib import Path
+
+import numpy as np
+
+from . import build as _build
+
+PDC_OK = 0
+PDC_ERR_INVALID, PDC_ERR_CUDA, PDC_ERR_CAPACITY, PDC_ERR_NO_DEVICE = -1, -2, -3, -4
+PDC_MAX_CB_SOFT = 25344
+PDC_MAX_CB_BYTES = 1056
+CRC_NONE, CRC16, CRC24A, CRC24B = 0, 1, 2, 3
+SCALE_X86, SCALE_GENERIC, SCALE_NEON = 0, 1, 2
+CB_NEW_DATA, CB_EARLY_STOP, CB_DECODE, CB_DEMATCH = 1, 2, 4, 8
+
+_u8, _u16, _u32, _i32 = ctypes.c_uint8, ctypes.c_uint16, ctypes.c_uint32, ctypes.c_int32
+_vp = ctypes.c_void_p
+
+
+class CbDesc(ctypes.Structure):
+    _fields_ = [("llr_offset", _u32), ("rm_length", _u32), ("harq_id", _u32), ("nref", _u32), ("lifting_size", _u16),
+                ("nof_filler", _u16), ("base_graph", _u8), ("qm", _u8), ("rv", _u8), ("crc_kind", _u8),
+                ("max_iter", _u8), ("flags", _u8), ("tb_index", _u16)]
+
+
+class CbResult(ctypes.Structure):
+    _fields_ = [("crc_ok", _u8), ("iters", _u8), ("status", _u8), ("nlayers", _u8)]
+
+
+class TbDesc(ctypes.Structure):
+    _fields_ = [("first_cb", _u32), ("nof_cb", _u32), ("tbs_bits", _u32), ("out_offset", _u32), ("reserved", _u32)]
+
+
+class TbResult(ctypes.Structure):
+    _fields_ = [("tb_crc_ok", _u8), ("all_cb_ok", _u8), ("reserved", _u16)]
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("device", _i32), ("max_cbs", _u32), ("max_llrs", _u32), ("harq_entries", _u32), ("max_tbs", _u32),
+                ("max_tb_bytes", _u32), ("scale_mode", _i32), ("combine_simd_width", _i32), ("nof_streams", _u32)]
+
+
+CB_DESC_DTYPE = np.dtype([("llr_offset", "<u4"), ("rm_length", "<u4"), ("harq_id", "<u4"), ("nref", "<u4"),
+                          ("lifting_size", "<u2"), ("nof_filler", "<u2"), ("base_graph", "u1"), ("qm", "u1"),
+                          ("rv", "u1"), ("crc_kind", "u1"), ("max_iter", "u1"), ("flags", "u1"), ("tb_index", "<u2")])
+CB_RESULT_DTYPE = np.dtype([("crc_ok", "u1"), ("iters", "u1"), ("status", "u1"), ("nlayers", "u1")])
+TB_DESC_DTYPE = np.dtype([("first_cb", "<u4"), ("nof_cb", "<u4"), ("tbs_bits", "<u4"), ("out_offset", "<u4"),
+                          ("reserved", "<u4")])
+TB_RESULT_DTYPE = np.dtype([("tb_crc_ok", "u1"), ("all_cb_ok", "u1"), ("reserved", "<u2")])
+assert CB_DESC_DTYPE.itemsize == ctypes.sizeof(CbDesc) == 28
+assert TB_DESC_DTYPE.itemsize == ctypes.sizeof(TbDesc) == 20
+
+EXPORTS = ["pdc_default_config", "pdc_create", "pdc_destroy", "pdc_last_error", "pdc_device_info", "pdc_launch_count",
+           "pdc_host_alloc", "pdc_host_free", "pdc_submit", "pdc_wait", "pdc_poll", "pdc_launch_device",
+           "pdc_harq_read", "pdc_harq_write", "pdc_harq_free", "pdc_harq_device_ptr", "pdc_ldpc_decode",
+           "pdc_rate_dematch", "pdc_crc"]
+
+_lib = None
+
+
+class PdcError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"pusch_dec_cuda error {code}: {text}")
+        self.code = code
+
+
+def library_path() -> Path:
+    return _build.LIB
+
+
+def load():
+    """Loads (building first if the sources are newer) the in-tree CUDA library. Raises if it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    L = ctypes.CDLL(str(path))
+    L.pdc_default_config.argtypes = [ctypes.POINTER(Config)]
+    L.pdc_default_config.restype = None
+    L.pdc_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(_vp)]
+    L.pdc_destroy.argtypes = [_vp]
+    L.pdc_destroy.restype = None
+    L.pdc_last_error.restype = ctypes.c_char_p
+    L.pdc_device_info.argtypes = [_vp] + [ctypes.POINTER(ctypes.c_int)] * 3
+    L.pdc_launch_count.argtypes = [_vp]
+    L.pdc_launch_count.restype = ctypes.c_uint64
+    L.pdc_host_alloc.argtypes = [ctypes.c_size_t]
+    L.pdc_host_alloc.restype = _vp
+    L.pdc_host_free.argtypes = [_vp]
+    L.pdc_host_free.restype = None
+    L.pdc_submit.argtypes = [_vp, _u32, _vp, _u32, _vp, ctypes.c_size_t, _vp, _u32, _vp, _vp, _vp, _vp]
+    L.pdc_wait.argtypes = [_vp, _u32]
+    L.pdc_poll.argtypes = [_vp, _u32, ctypes.POINTER(ctypes.c_int)]
+    L.pdc_launch_device.argtypes = [_vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _u32, _u32, ctypes.c_int, _vp]
+    L.pdc_harq_read.argtypes = [_vp, _u32, _vp, _u32]
+    L.pdc_harq_write.argtypes = [_vp, _u32, _vp, _u32]
+    L.pdc_harq_free.argtypes = [_vp, _u32]
+    L.pdc_harq_device_ptr.argtypes = [_vp]
+    L.pdc_harq_device_ptr.restype = _vp
+    L.pdc_ldpc_decode.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp, _u32, _u32, ctypes.c_int, ctypes.c_int, _vp,
+                                  ctypes.POINTER(ctypes.c_int)]
+    L.pdc_rate_dematch.argtypes = [_vp, _vp, _u32, _vp, _u32, ctypes.c_int, ctypes.c_int, ctypes.c_int, _u32, _u32]
+    L.pdc_crc.argtypes = [_vp, ctypes.c_int, _vp, _u32, ctypes.POINTER(_u32)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != PDC_OK:
+        raise PdcError(rc, load().pdc_last_error().decode())
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp) if a is not None else None
+
+
+class PinnedBuffer:
+    """Pinned host memory from pdc_host_alloc exposed as a numpy array."""
+
+    def __init__(self, nbytes, dtype=np.int8):
+        self._L = load()
+        self.ptr = self._L.pdc_host_alloc(nbytes)
+        if not self.ptr:
+            raise PdcError(PDC_ERR_CUDA, "pdc_host_alloc failed")
+        n = nbytes // np.dtype(dtype).itemsize
+        self.array = np.ctypeslib.as_array(ctypes.cast(self.ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(nbytes,))
+        self.array = self.array.view(dtype)[:n]
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self._L.pdc_host_free(self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """pdc_ctx: one per GPU. Owns the device HARQ arena, the streams ("queues") and the pinned staging."""
+
+    def __init__(self, device=0, max_cbs=4096, max_llrs=None, harq_entries=4096, max_tbs=256, max_tb_bytes=4 << 20,
+                 scale_mode=SCALE_X86, combine_simd_width=64, nof_streams=2):
+        L = load()
+        cfg = Config()
+        L.pdc_default_config(ctypes.byref(cfg))
+        cfg.device = device
+        cfg.max_cbs = max_cbs
+        cfg.max_llrs = max_llrs if max_llrs is not None else max_cbs * PDC_MAX_CB_SOFT
+        cfg.harq_entries = harq_entries
+        cfg.max_tbs = max_tbs
+        cfg.max_tb_bytes = max_tb_bytes
+        cfg.scale_mode = scale_mode
+        cfg.combine_simd_width = combine_simd_width
+        cfg.nof_streams = nof_streams
+        self.cfg = cfg
+        self._L = L
+        self.h = _vp()
+        check(L.pdc_create(ctypes.byref(cfg), ctypes.byref(self.h)))
+        self._pending = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.pdc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def device_info(self):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(self._L.pdc_device_info(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"sm_count": a.value, "cc": (b.value, c.value)}
+
+    def launch_count(self):
+        return int(self._L.pdc_launch_count(self.h))
+
+    # -- batched interface --------------------------------------------------------------------------------------------
+    def submit(self, cbs, llrs, tbs=None, stream=0, want_bits=True, want_tb=True):
+        """cbs: numpy array of CB_DESC_DTYPE; llrs: int8 array (ideally a PinnedBuffer view); tbs: TB_DESC_DTYPE."""
+        cbs = np.ascontiguousarray(cbs, CB_DESC_DTYPE)
+        assert llrs.dtype == np.int8 and llrs.flags.c_contiguous
+        n_cb = cbs.size
+        n_tb = 0 if tbs is None else tbs.size
+        out = {
+            "cbs": cbs,
+            "llrs": llrs,
+            "cb_results": np.zeros(n_cb, CB_RESULT_DTYPE),
+            "cb_bits": np.zeros((n_cb, PDC_MAX_CB_BYTES), np.uint8) if want_bits else None,
+            "tbs": None,
+            "tb_results": None,
+            "tb_bytes": None,
+        }
+        if n_tb:
+            tbs = np.ascontiguousarray(tbs, TB_DESC_DTYPE)
+            out["tbs"] = tbs
+            out["tb_results"] = np.zeros(n_tb, TB_RESULT_DTYPE)
+            if want_tb:
+                need = int(max(t["out_offset"] + (int(t["tbs_bits"]) + 24 + 31) // 32 * 4 for t in tbs))
+                out["tb_bytes"] = np.zeros(need, np.uint8)
+        check(self._L.pdc_submit(self.h, stream, _ptr(cbs), n_cb, _ptr(llrs), llrs.size, _ptr(out["tbs"]), n_tb,
+                                 _ptr(out["cb_results"]), _ptr(out["cb_bits"]), _ptr(out["tb_results"]),
+                                 _ptr(out["tb_bytes"])))
+        self._pending[stream] = out
+        return out
+
+    def wait(self, stream=0):
+        check(self._L.pdc_wait(self.h, stream))
+        return self._pending.pop(stream, None)
+
+    def poll(self, stream=0):
+        d = ctypes.c_int()
+        check(self._L.pdc_poll(self.h, stream, ctypes.byref(d)))
+        return bool(d.value)
+
+    def launch_device(self, d_cbs, n_cb, d_llrs, d_cb_results, d_cb_bits, max_lifting_size, flags_union, any_bg1,
+                      cuda_stream=0, d_tbs=0, n_tb=0, d_tb_results=0, d_tb_bytes=0):
+        check(self._L.pdc_launch_device(self.h, d_cbs, n_cb, d_llrs, d_tbs or None, n_tb, d_cb_results, d_cb_bits,
+                                        d_tb_results or None, d_tb_bytes or None, max_lifting_size, flags_union,
+                                        int(any_bg1), cuda_stream or None))
+
+    # -- HARQ arena ---------------------------------------------------------------------------------------------------
+    def harq_read(self, harq_id, n=PDC_MAX_CB_SOFT):
+        soft = np.zeros(n, np.int8)
+        check(self._L.pdc_harq_read(self.h, harq_id, _ptr(soft), n))
+        return soft
+
+    def harq_write(self, harq_id, soft):
+        soft = np.ascontiguousarray(soft, np.int8)
+        check(self._L.pdc_harq_write(self.h, harq_id, _ptr(soft), soft.size))
+
+    def harq_free(self, harq_id):
+        check(self._L.pdc_harq_free(self.h, harq_id))
+
+    def harq_device_ptr(self):
+        return self._L.pdc_harq_device_ptr(self.h)
+
+    # -- single-codeblock synchronous calls -----------------------------------------------------------------------------
+    def ldpc_decode(self, bg, Z, llrs, nof_filler=0, crc_kind=CRC_NONE, max_iter=6, out=None):
+        llrs = np.ascontiguousarray(llrs, np.int8)
+        K = (22 if bg == 1 else 10) * Z
+        if out is None:
+            out = np.zeros((K + 7) // 8, np.uint8)
+        it = ctypes.c_int()
+        check(self._L.pdc_ldpc_decode(self.h, bg, Z, _ptr(llrs), llrs.size, nof_filler, crc_kind, max_iter, _ptr(out),
+                                      ctypes.byref(it)))
+        return it.value, out
+
+    def rate_dematch(self, buffer, llrs, new_data, rv, qm, nref=0, nof_filler=0):
+        assert buffer.dtype == np.int8 and buffer.flags.c_contiguous
+        llrs = np.ascontiguousarray(llrs, np.int8)
+        check(self._L.pdc_rate_dematch(self.h, _ptr(buffer), buffer.size, _ptr(llrs), llrs.size, int(new_data), rv, qm,
+                                       nref, nof_filler))
+        return buffer
+
+    def crc(self, crc_kind, packed, nbits):
+        packed = np.ascontiguousarray(packed, np.uint8)
+        c = _u32()
+        check(self._L.pdc_crc(self.h, crc_kind, _ptr(packed), nbits, ctypes.byref(c)))
+        return c.value

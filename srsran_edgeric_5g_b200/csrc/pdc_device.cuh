@@ -1,0 +1,95 @@
+// Shared device-side definitions of the PUSCH decode path (sm_100a).
+#pragma once
+
+#include "../../include/pusch_dec_cuda.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pdc {
+
+constexpr int MAX_Z        = 384;
+constexpr int BG1_EDGES_N  = 316;
+constexpr int BG2_EDGES_N  = 197;
+constexpr int MAX_EDGES    = 316;
+constexpr int MAX_ROWS     = 46;
+constexpr int MAX_DEG      = 19;
+constexpr int LLR_MAX      = 120;
+constexpr int LLR_INF      = 127;
+constexpr int CLAMP_IN     = 64; // ldpc_decoder_impl.h:193-195
+constexpr int XPOW_ENTRIES = 272;
+
+// Base-graph description in constant memory, the standard's sparse form (see bg_tables.inc).
+struct BgTables {
+  uint8_t  row[2][MAX_EDGES];
+  uint8_t  col[2][MAX_EDGES];
+  uint16_t v[2][8][MAX_EDGES];
+  uint16_t row_start[2][MAX_ROWS + 2];
+  uint8_t  set_index[MAX_Z + 1]; // 0xff = not a lifting size
+  // x^(32 k) mod P for the three CRC polynomials (index PDC_CRC16-1 .. PDC_CRC24B-1).
+  uint32_t xpow32[3][XPOW_ENTRIES];
+};
+
+__host__ __device__ inline uint32_t crc_poly(int kind)
+{
+  return (kind == PDC_CRC16) ? 0x11021u : (kind == PDC_CRC24A) ? 0x1864CFBu : 0x1800063u;
+}
+__host__ __device__ inline int crc_order(int kind)
+{
+  return (kind == PDC_CRC16) ? 16 : 24;
+}
+
+// (W(x) * A(x)) mod P, W of degree < 32, A of degree < order.
+__host__ __device__ inline uint32_t gf2_mulmod(uint32_t w, uint32_t a, uint32_t poly, int order)
+{
+  uint32_t top = 1u << order;
+  uint32_t r   = 0;
+#pragma unroll 4
+  for (int i = 31; i >= 0; --i) {
+    r <<= 1;
+    if (r & top) {
+      r ^= poly;
+    }
+    if ((w >> i) & 1u) {
+      r ^= a;
+    }
+  }
+  return r;
+}
+
+// Check-to-variable scaling: the only arithmetic difference between the reference variants.
+__device__ __forceinline__ int scale_c2v(int x, int mode)
+{
+  if (mode == PDC_SCALE_X86) {
+    return (x * 52428) >> 16;
+  }
+  if (mode == PDC_SCALE_GENERIC) {
+    return (int)((float)x * 0.8f + 0.5f);
+  }
+  return (x * 204) >> 8;
+}
+
+// Launch parameters shared by the kernels.
+struct BatchParams {
+  const pdc_cb_desc* cbs;
+  uint32_t           n_cb;
+  const int8_t*      llrs;
+  int8_t*            harq;       // arena: entries x PDC_MAX_CB_SOFT
+  uint32_t           harq_entries;
+  pdc_cb_result*     results;
+  uint8_t*           cb_bits;    // n_cb x PDC_MAX_CB_BYTES (device staging, always present)
+  uint8_t*           harq_data;  // entries x PDC_MAX_CB_BYTES: decoded message bits kept with the HARQ entry
+  int                scale_mode;
+  int                simd_width;
+};
+
+struct TbParams {
+  const pdc_tb_desc* tbs;
+  uint32_t           n_tb;
+  const pdc_cb_desc* cbs;
+  const pdc_cb_result* cb_results;
+  const uint8_t*     cb_bits;
+  pdc_tb_result*     tb_results;
+  uint8_t*           tb_bytes;
+};
+
+} // namespace pdc

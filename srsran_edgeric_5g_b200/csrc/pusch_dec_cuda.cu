@@ -1,0 +1,731 @@
+// C-ABI implementation (include/pusch_dec_cuda.h): context, streams ("queues"), pinned staging, HARQ arena and kernel
+// launches. Single translation unit: the kernels are included so that they share the constant-memory tables.
+#include "pdc_device.cuh"
+#include "tables.cuh"
+#include "rate_dematch.cuh"
+#include "ldpc_decode_scalar.cuh"
+#include "tb_assemble.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess)
+{
+  g_last_error = what;
+  if (e != cudaSuccess) {
+    g_last_error += ": ";
+    g_last_error += cudaGetErrorString(e);
+  }
+  return code;
+}
+
+#define PDC_CUDA(expr)                                                                                                 \
+  do {                                                                                                                 \
+    cudaError_t e__ = (expr);                                                                                          \
+    if (e__ != cudaSuccess) {                                                                                          \
+      return fail(PDC_ERR_CUDA, #expr, e__);                                                                           \
+    }                                                                                                                  \
+  } while (0)
+
+struct Queue {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t  done   = nullptr;
+  // Device staging.
+  pdc_cb_desc*   d_cbs     = nullptr;
+  int8_t*        d_llrs    = nullptr;
+  pdc_tb_desc*   d_tbs     = nullptr;
+  pdc_cb_result* d_cb_res  = nullptr;
+  uint8_t*       d_cb_bits = nullptr;
+  pdc_tb_result* d_tb_res  = nullptr;
+  uint8_t*       d_tb_out  = nullptr;
+  // Pinned host mirrors.
+  pdc_cb_desc*   h_cbs     = nullptr;
+  pdc_tb_desc*   h_tbs     = nullptr;
+  pdc_cb_result* h_cb_res  = nullptr;
+  uint8_t*       h_cb_bits = nullptr;
+  pdc_tb_result* h_tb_res  = nullptr;
+  uint8_t*       h_tb_out  = nullptr;
+  // Pending batch.
+  bool           busy         = false;
+  uint32_t       n_cb         = 0;
+  uint32_t       n_tb         = 0;
+  size_t         tb_out_bytes = 0;
+  pdc_cb_result* u_cb_res     = nullptr;
+  uint8_t*       u_cb_bits    = nullptr;
+  pdc_tb_result* u_tb_res     = nullptr;
+  uint8_t*       u_tb_out     = nullptr;
+};
+
+} // namespace
+
+struct pdc_ctx {
+  pdc_config           cfg;
+  int                  sm_count = 0, cc_major = 0, cc_minor = 0;
+  int8_t*              d_harq      = nullptr; // (harq_entries + 1) x PDC_MAX_CB_SOFT; the extra entry is scratch
+  uint8_t*             d_harq_data = nullptr; // (harq_entries + 1) x PDC_MAX_CB_BYTES
+  int8_t*              d_scratch_llr = nullptr;
+  size_t               scratch_llr_bytes = 0;
+  std::vector<Queue>   queues;
+  std::atomic<uint64_t> launches{0};
+};
+
+namespace {
+
+struct BatchShape {
+  int  max_Z   = 0;
+  bool any_bg1 = false;
+  bool any_decode = false, any_dematch = false;
+};
+
+BatchShape scan_batch(const pdc_cb_desc* cbs, uint32_t n)
+{
+  BatchShape s;
+  for (uint32_t i = 0; i != n; ++i) {
+    if (cbs[i].lifting_size <= pdc::MAX_Z) {
+      s.max_Z = std::max<int>(s.max_Z, cbs[i].lifting_size);
+    }
+    s.any_bg1 |= (cbs[i].base_graph == 1);
+    s.any_decode |= (cbs[i].flags & PDC_CB_DECODE) != 0;
+    s.any_dematch |= (cbs[i].flags & PDC_CB_DEMATCH) != 0;
+  }
+  if (s.max_Z < 2) {
+    s.max_Z = 2;
+  }
+  return s;
+}
+
+// Launches the kernels of one batch on stream s. All pointers are device pointers.
+int launch_batch(pdc_ctx*             ctx,
+                 const pdc_cb_desc*   d_cbs,
+                 uint32_t             n_cb,
+                 const int8_t*        d_llrs,
+                 const pdc_tb_desc*   d_tbs,
+                 uint32_t             n_tb,
+                 pdc_cb_result*       d_cb_res,
+                 uint8_t*             d_cb_bits,
+                 pdc_tb_result*       d_tb_res,
+                 uint8_t*             d_tb_out,
+                 const BatchShape&    shape,
+                 const int8_t*        direct_in,
+                 uint32_t             direct_n,
+                 cudaStream_t         s)
+{
+  pdc::BatchParams p;
+  p.cbs          = d_cbs;
+  p.n_cb         = n_cb;
+  p.llrs         = d_llrs;
+  p.harq         = ctx->d_harq;
+  p.harq_entries = ctx->cfg.harq_entries + 1;
+  p.results      = d_cb_res;
+  p.cb_bits      = d_cb_bits;
+  p.harq_data    = ctx->d_harq_data;
+  p.scale_mode   = ctx->cfg.scale_mode;
+  p.simd_width   = ctx->cfg.combine_simd_width;
+  if (shape.any_dematch) {
+    PDC_CUDA(pdc::launch_rate_dematch(p, s));
+    ctx->launches++;
+  }
+  if (shape.any_decode) {
+    PDC_CUDA(pdc::launch_ldpc_decode(p, shape.max_Z, shape.any_bg1, direct_in, direct_n, s));
+    ctx->launches++;
+  }
+  if (n_tb != 0) {
+    pdc::TbParams t;
+    t.tbs        = d_tbs;
+    t.n_tb       = n_tb;
+    t.cbs        = d_cbs;
+    t.cb_results = d_cb_res;
+    t.cb_bits    = d_cb_bits;
+    t.tb_results = d_tb_res;
+    t.tb_bytes   = d_tb_out;
+    PDC_CUDA(pdc::launch_tb_assemble(t, ctx->d_harq_data, s));
+    ctx->launches++;
+  }
+  return PDC_OK;
+}
+
+template <typename T>
+cudaError_t dev_alloc(T** p, size_t n)
+{
+  return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
+}
+template <typename T>
+cudaError_t host_alloc(T** p, size_t n)
+{
+  return cudaMallocHost(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
+}
+
+// Generic CRC of a packed bit string (compatibility API, not a hot path).
+__constant__ uint32_t c_xpow2[3][24]; // x^(2^i) mod P
+
+__global__ void crc_kernel(const uint8_t* packed, uint32_t nbits, int kind, uint32_t* out)
+{
+  __shared__ uint32_t sh;
+  if (threadIdx.x == 0) {
+    sh = 0;
+  }
+  __syncthreads();
+  const uint32_t poly   = pdc::crc_poly(kind);
+  const int      order  = pdc::crc_order(kind);
+  const uint32_t n_full = nbits / 32u;
+  const uint32_t rem    = nbits & 31u;
+  const uint32_t T      = n_full + (rem ? 1u : 0u);
+  uint32_t       acc    = 0;
+  for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+    uint32_t w = 0;
+    for (int k = 0; k != 4; ++k) {
+      uint32_t byte = 4u * t + k;
+      uint32_t v    = (8u * byte < nbits) ? packed[byte] : 0u;
+      w             = (w << 8) | v;
+    }
+    uint32_t e;
+    if (t < n_full) {
+      e = nbits - 32u * (t + 1u) + order;
+    } else {
+      w >>= (32u - rem);
+      e = order;
+    }
+    uint32_t xp = 1;
+    for (int i = 0; e != 0; ++i, e >>= 1) {
+      if (e & 1u) {
+        xp = pdc::gf2_mulmod(xp, c_xpow2[kind - 1][i], poly, order);
+      }
+    }
+    acc ^= pdc::gf2_mulmod(w, xp, poly, order);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+  }
+  if ((threadIdx.x & 31) == 0 && acc) {
+    atomicXor(&sh, acc);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *out = sh;
+  }
+}
+
+cudaError_t upload_crc_tables()
+{
+  uint32_t h[3][24];
+  for (int k = 0; k != 3; ++k) {
+    uint32_t poly  = pdc::crc_poly(k + 1);
+    int      order = pdc::crc_order(k + 1);
+    uint32_t x     = 2; // x^1
+    for (int i = 0; i != 24; ++i) {
+      h[k][i] = x;
+      x       = pdc::gf2_mulmod(x, x, poly, order);
+    }
+  }
+  return cudaMemcpyToSymbol(c_xpow2, h, sizeof(h));
+}
+
+} // namespace
+
+extern "C" {
+
+void pdc_default_config(pdc_config* cfg)
+{
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->device             = 0;
+  cfg->max_cbs            = 4096;
+  cfg->max_llrs           = 4096u * PDC_MAX_CB_SOFT;
+  cfg->harq_entries       = 4096;
+  cfg->max_tbs            = 256;
+  cfg->max_tb_bytes       = 4u << 20;
+  cfg->scale_mode         = PDC_SCALE_X86;
+  cfg->combine_simd_width = 64;
+  cfg->nof_streams        = 2;
+}
+
+const char* pdc_last_error(void)
+{
+  return g_last_error.c_str();
+}
+
+int pdc_create(const pdc_config* cfg, pdc_ctx** out)
+{
+  if (!cfg || !out || cfg->max_cbs == 0 || cfg->harq_entries == 0 || cfg->nof_streams == 0 ||
+      cfg->scale_mode < PDC_SCALE_X86 || cfg->scale_mode > PDC_SCALE_NEON) {
+    return fail(PDC_ERR_INVALID, "pdc_create: invalid configuration");
+  }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0 || cfg->device >= n_dev) {
+    return fail(PDC_ERR_NO_DEVICE, "pdc_create: no usable CUDA device (this library has no CPU fallback)");
+  }
+  PDC_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  PDC_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    return fail(PDC_ERR_NO_DEVICE, "pdc_create: device is not sm_100 (the kernels are built for sm_100a only)");
+  }
+  pdc_ctx* ctx = new (std::nothrow) pdc_ctx;
+  if (!ctx) {
+    return fail(PDC_ERR_INVALID, "pdc_create: out of host memory");
+  }
+  ctx->cfg      = *cfg;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  *out          = ctx;
+#define PDC_CREATE(expr)                                                                                               \
+  do {                                                                                                                 \
+    cudaError_t e__ = (expr);                                                                                          \
+    if (e__ != cudaSuccess) {                                                                                          \
+      pdc_destroy(ctx);                                                                                                \
+      *out = nullptr;                                                                                                  \
+      return fail(PDC_ERR_CUDA, #expr, e__);                                                                           \
+    }                                                                                                                  \
+  } while (0)
+  PDC_CREATE(pdc::upload_tables());
+  PDC_CREATE(pdc::upload_tb_tables());
+  PDC_CREATE(upload_crc_tables());
+  size_t entries = (size_t)cfg->harq_entries + 1;
+  PDC_CREATE(dev_alloc(&ctx->d_harq, entries * PDC_MAX_CB_SOFT));
+  PDC_CREATE(cudaMemset(ctx->d_harq, 0, entries * PDC_MAX_CB_SOFT));
+  PDC_CREATE(dev_alloc(&ctx->d_harq_data, entries * PDC_MAX_CB_BYTES));
+  PDC_CREATE(cudaMemset(ctx->d_harq_data, 0, entries * PDC_MAX_CB_BYTES));
+  ctx->scratch_llr_bytes = 35u * PDC_MAX_CB_BYTES * 8u; // MAX_CODEBLOCK_RM_SIZE (ldpc.h:122)
+  PDC_CREATE(dev_alloc(&ctx->d_scratch_llr, ctx->scratch_llr_bytes));
+  ctx->queues.resize(cfg->nof_streams);
+  for (Queue& q : ctx->queues) {
+    PDC_CREATE(cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking));
+    PDC_CREATE(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
+    PDC_CREATE(dev_alloc(&q.d_cbs, cfg->max_cbs));
+    PDC_CREATE(dev_alloc(&q.d_llrs, (size_t)cfg->max_llrs + 16));
+    PDC_CREATE(dev_alloc(&q.d_tbs, cfg->max_tbs));
+    PDC_CREATE(dev_alloc(&q.d_cb_res, cfg->max_cbs));
+    PDC_CREATE(dev_alloc(&q.d_cb_bits, (size_t)cfg->max_cbs * PDC_MAX_CB_BYTES));
+    PDC_CREATE(dev_alloc(&q.d_tb_res, cfg->max_tbs));
+    PDC_CREATE(dev_alloc(&q.d_tb_out, (size_t)cfg->max_tb_bytes + 16));
+    PDC_CREATE(host_alloc(&q.h_cbs, cfg->max_cbs));
+    PDC_CREATE(host_alloc(&q.h_tbs, cfg->max_tbs));
+    PDC_CREATE(host_alloc(&q.h_cb_res, cfg->max_cbs));
+    PDC_CREATE(host_alloc(&q.h_cb_bits, (size_t)cfg->max_cbs * PDC_MAX_CB_BYTES));
+    PDC_CREATE(host_alloc(&q.h_tb_res, cfg->max_tbs));
+    PDC_CREATE(host_alloc(&q.h_tb_out, (size_t)cfg->max_tb_bytes + 16));
+  }
+#undef PDC_CREATE
+  return PDC_OK;
+}
+
+void pdc_destroy(pdc_ctx* ctx)
+{
+  if (!ctx) {
+    return;
+  }
+  cudaSetDevice(ctx->cfg.device);
+  for (Queue& q : ctx->queues) {
+    if (q.stream) {
+      cudaStreamSynchronize(q.stream);
+      cudaStreamDestroy(q.stream);
+    }
+    if (q.done) {
+      cudaEventDestroy(q.done);
+    }
+    cudaFree(q.d_cbs);
+    cudaFree(q.d_llrs);
+    cudaFree(q.d_tbs);
+    cudaFree(q.d_cb_res);
+    cudaFree(q.d_cb_bits);
+    cudaFree(q.d_tb_res);
+    cudaFree(q.d_tb_out);
+    cudaFreeHost(q.h_cbs);
+    cudaFreeHost(q.h_tbs);
+    cudaFreeHost(q.h_cb_res);
+    cudaFreeHost(q.h_cb_bits);
+    cudaFreeHost(q.h_tb_res);
+    cudaFreeHost(q.h_tb_out);
+  }
+  cudaFree(ctx->d_harq);
+  cudaFree(ctx->d_harq_data);
+  cudaFree(ctx->d_scratch_llr);
+  delete ctx;
+}
+
+int pdc_device_info(pdc_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor)
+{
+  if (!ctx) {
+    return fail(PDC_ERR_INVALID, "pdc_device_info: null context");
+  }
+  if (sm_count) {
+    *sm_count = ctx->sm_count;
+  }
+  if (cc_major) {
+    *cc_major = ctx->cc_major;
+  }
+  if (cc_minor) {
+    *cc_minor = ctx->cc_minor;
+  }
+  return PDC_OK;
+}
+
+uint64_t pdc_launch_count(pdc_ctx* ctx)
+{
+  return ctx ? ctx->launches.load() : 0;
+}
+
+void* pdc_host_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    return nullptr;
+  }
+  return p;
+}
+
+void pdc_host_free(void* p)
+{
+  if (p) {
+    cudaFreeHost(p);
+  }
+}
+
+int pdc_submit(pdc_ctx*           ctx,
+               uint32_t           stream,
+               const pdc_cb_desc* cbs,
+               uint32_t           n_cb,
+               const int8_t*      llrs,
+               size_t             n_llrs,
+               const pdc_tb_desc* tbs,
+               uint32_t           n_tb,
+               pdc_cb_result*     cb_results,
+               uint8_t*           cb_bits,
+               pdc_tb_result*     tb_results,
+               uint8_t*           tb_bytes)
+{
+  if (!ctx || stream >= ctx->queues.size() || !cbs || n_cb == 0 || !cb_results || (n_tb != 0 && (!tbs || !tb_results))) {
+    return fail(PDC_ERR_INVALID, "pdc_submit: invalid argument");
+  }
+  if (n_cb > ctx->cfg.max_cbs || n_llrs > ctx->cfg.max_llrs || n_tb > ctx->cfg.max_tbs) {
+    return fail(PDC_ERR_CAPACITY, "pdc_submit: batch exceeds the capacity of the context");
+  }
+  Queue& q = ctx->queues[stream];
+  if (q.busy) {
+    return fail(PDC_ERR_CAPACITY, "pdc_submit: queue busy (call pdc_wait first)");
+  }
+  // Validate what the kernels index with before anything is queued.
+  for (uint32_t i = 0; i != n_cb; ++i) {
+    if ((size_t)cbs[i].llr_offset + cbs[i].rm_length > n_llrs && (cbs[i].flags & PDC_CB_DEMATCH)) {
+      return fail(PDC_ERR_INVALID, "pdc_submit: codeblock LLR range outside the batch");
+    }
+    if (cbs[i].harq_id >= ctx->cfg.harq_entries) {
+      return fail(PDC_ERR_INVALID, "pdc_submit: harq_id outside the arena");
+    }
+  }
+  size_t tb_out_bytes = 0;
+  for (uint32_t i = 0; i != n_tb; ++i) {
+    size_t need = ((size_t)tbs[i].tbs_bits + 24 + 31) / 32 * 4;
+    if ((tbs[i].out_offset & 3u) || (size_t)tbs[i].out_offset + need > ctx->cfg.max_tb_bytes ||
+        (size_t)tbs[i].first_cb + tbs[i].nof_cb > n_cb || tbs[i].nof_cb == 0) {
+      return fail(PDC_ERR_INVALID, "pdc_submit: invalid transport block descriptor");
+    }
+    tb_out_bytes = std::max(tb_out_bytes, (size_t)tbs[i].out_offset + need);
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  BatchShape shape = scan_batch(cbs, n_cb);
+  memcpy(q.h_cbs, cbs, sizeof(pdc_cb_desc) * n_cb);
+  PDC_CUDA(cudaMemcpyAsync(q.d_cbs, q.h_cbs, sizeof(pdc_cb_desc) * n_cb, cudaMemcpyHostToDevice, q.stream));
+  if (n_llrs != 0) {
+    PDC_CUDA(cudaMemcpyAsync(q.d_llrs, llrs, n_llrs, cudaMemcpyHostToDevice, q.stream));
+  }
+  if (n_tb != 0) {
+    memcpy(q.h_tbs, tbs, sizeof(pdc_tb_desc) * n_tb);
+    PDC_CUDA(cudaMemcpyAsync(q.d_tbs, q.h_tbs, sizeof(pdc_tb_desc) * n_tb, cudaMemcpyHostToDevice, q.stream));
+  }
+  // Codeblocks that are not decoded report "not run".
+  PDC_CUDA(cudaMemsetAsync(q.d_cb_res, 0, sizeof(pdc_cb_result) * n_cb, q.stream));
+  int rc = launch_batch(ctx, q.d_cbs, n_cb, q.d_llrs, q.d_tbs, n_tb, q.d_cb_res, q.d_cb_bits, q.d_tb_res, q.d_tb_out,
+                        shape, nullptr, 0, q.stream);
+  if (rc != PDC_OK) {
+    return rc;
+  }
+  PDC_CUDA(cudaMemcpyAsync(q.h_cb_res, q.d_cb_res, sizeof(pdc_cb_result) * n_cb, cudaMemcpyDeviceToHost, q.stream));
+  if (cb_bits) {
+    PDC_CUDA(cudaMemcpyAsync(q.h_cb_bits, q.d_cb_bits, (size_t)n_cb * PDC_MAX_CB_BYTES, cudaMemcpyDeviceToHost,
+                             q.stream));
+  }
+  if (n_tb != 0) {
+    PDC_CUDA(cudaMemcpyAsync(q.h_tb_res, q.d_tb_res, sizeof(pdc_tb_result) * n_tb, cudaMemcpyDeviceToHost, q.stream));
+    if (tb_bytes) {
+      PDC_CUDA(cudaMemcpyAsync(q.h_tb_out, q.d_tb_out, tb_out_bytes, cudaMemcpyDeviceToHost, q.stream));
+    }
+  }
+  PDC_CUDA(cudaEventRecord(q.done, q.stream));
+  q.busy         = true;
+  q.n_cb         = n_cb;
+  q.n_tb         = n_tb;
+  q.tb_out_bytes = tb_out_bytes;
+  q.u_cb_res     = cb_results;
+  q.u_cb_bits    = cb_bits;
+  q.u_tb_res     = tb_results;
+  q.u_tb_out     = tb_bytes;
+  return PDC_OK;
+}
+
+int pdc_wait(pdc_ctx* ctx, uint32_t stream)
+{
+  if (!ctx || stream >= ctx->queues.size()) {
+    return fail(PDC_ERR_INVALID, "pdc_wait: invalid argument");
+  }
+  Queue& q = ctx->queues[stream];
+  if (!q.busy) {
+    return PDC_OK;
+  }
+  cudaError_t e = cudaEventSynchronize(q.done);
+  q.busy        = false;
+  if (e != cudaSuccess) {
+    // A failed batch reports CRC failure with the maximum iteration count, like a dropped accelerator operation
+    // (hw_accelerator_pusch_dec_acc100_impl.cpp:233-247).
+    for (uint32_t i = 0; i != q.n_cb; ++i) {
+      q.u_cb_res[i].crc_ok = 0;
+      q.u_cb_res[i].status = 2;
+    }
+    return fail(PDC_ERR_CUDA, "pdc_wait", e);
+  }
+  memcpy(q.u_cb_res, q.h_cb_res, sizeof(pdc_cb_result) * q.n_cb);
+  if (q.u_cb_bits) {
+    memcpy(q.u_cb_bits, q.h_cb_bits, (size_t)q.n_cb * PDC_MAX_CB_BYTES);
+  }
+  if (q.n_tb != 0) {
+    memcpy(q.u_tb_res, q.h_tb_res, sizeof(pdc_tb_result) * q.n_tb);
+    if (q.u_tb_out) {
+      memcpy(q.u_tb_out, q.h_tb_out, q.tb_out_bytes);
+    }
+  }
+  return PDC_OK;
+}
+
+int pdc_poll(pdc_ctx* ctx, uint32_t stream, int* done)
+{
+  if (!ctx || stream >= ctx->queues.size() || !done) {
+    return fail(PDC_ERR_INVALID, "pdc_poll: invalid argument");
+  }
+  Queue& q = ctx->queues[stream];
+  *done    = !q.busy || (cudaEventQuery(q.done) == cudaSuccess);
+  return PDC_OK;
+}
+
+int pdc_launch_device(pdc_ctx*    ctx,
+                      const void* d_cbs,
+                      uint32_t    n_cb,
+                      const void* d_llrs,
+                      const void* d_tbs,
+                      uint32_t    n_tb,
+                      void*       d_cb_results,
+                      void*       d_cb_bits,
+                      void*       d_tb_results,
+                      void*       d_tb_bytes,
+                      uint32_t    max_lifting_size,
+                      uint32_t    flags_union,
+                      int         any_bg1,
+                      void*       cuda_stream)
+{
+  if (!ctx || !d_cbs || n_cb == 0 || !d_cb_results || !d_cb_bits || max_lifting_size < 2 ||
+      max_lifting_size > (uint32_t)pdc::MAX_Z) {
+    return fail(PDC_ERR_INVALID, "pdc_launch_device: invalid argument");
+  }
+  BatchShape shape;
+  shape.max_Z       = (int)max_lifting_size;
+  shape.any_bg1     = any_bg1 != 0;
+  shape.any_decode  = (flags_union & PDC_CB_DECODE) != 0;
+  shape.any_dematch = (flags_union & PDC_CB_DEMATCH) != 0;
+  return launch_batch(ctx, static_cast<const pdc_cb_desc*>(d_cbs), n_cb, static_cast<const int8_t*>(d_llrs),
+                      static_cast<const pdc_tb_desc*>(d_tbs), n_tb, static_cast<pdc_cb_result*>(d_cb_results),
+                      static_cast<uint8_t*>(d_cb_bits), static_cast<pdc_tb_result*>(d_tb_results),
+                      static_cast<uint8_t*>(d_tb_bytes), shape, nullptr, 0, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int pdc_harq_read(pdc_ctx* ctx, uint32_t harq_id, int8_t* soft, uint32_t n)
+{
+  if (!ctx || harq_id >= ctx->cfg.harq_entries || !soft || n > PDC_MAX_CB_SOFT) {
+    return fail(PDC_ERR_INVALID, "pdc_harq_read: invalid argument");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  PDC_CUDA(cudaMemcpy(soft, ctx->d_harq + (size_t)harq_id * PDC_MAX_CB_SOFT, n, cudaMemcpyDeviceToHost));
+  return PDC_OK;
+}
+
+int pdc_harq_write(pdc_ctx* ctx, uint32_t harq_id, const int8_t* soft, uint32_t n)
+{
+  if (!ctx || harq_id >= ctx->cfg.harq_entries || !soft || n > PDC_MAX_CB_SOFT) {
+    return fail(PDC_ERR_INVALID, "pdc_harq_write: invalid argument");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  PDC_CUDA(cudaMemcpy(ctx->d_harq + (size_t)harq_id * PDC_MAX_CB_SOFT, soft, n, cudaMemcpyHostToDevice));
+  return PDC_OK;
+}
+
+int pdc_harq_free(pdc_ctx* ctx, uint32_t harq_id)
+{
+  if (!ctx || harq_id >= ctx->cfg.harq_entries) {
+    return fail(PDC_ERR_INVALID, "pdc_harq_free: invalid argument");
+  }
+  return PDC_OK;
+}
+
+void* pdc_harq_device_ptr(pdc_ctx* ctx)
+{
+  return ctx ? ctx->d_harq : nullptr;
+}
+
+int pdc_ldpc_decode(pdc_ctx*      ctx,
+                    int           base_graph,
+                    int           lifting_size,
+                    const int8_t* llrs,
+                    uint32_t      n_llrs,
+                    uint32_t      nof_filler,
+                    int           crc_kind,
+                    int           max_iter,
+                    uint8_t*      out,
+                    int*          iters)
+{
+  if (!ctx || !llrs || !out || (base_graph != 1 && base_graph != 2) || lifting_size < 2 ||
+      lifting_size > pdc::MAX_Z || max_iter < 1 || max_iter > 255 || crc_kind < PDC_CRC_NONE || crc_kind > PDC_CRC24B) {
+    return fail(PDC_ERR_INVALID, "pdc_ldpc_decode: invalid argument");
+  }
+  const uint32_t Z = (uint32_t)lifting_size;
+  const uint32_t K = ((base_graph == 1) ? 22u : 10u) * Z;
+  const uint32_t N = ((base_graph == 1) ? 66u : 50u) * Z;
+  // Contract of ldpc_decoder_impl::decode (ldpc_decoder_impl.cpp:69-83).
+  if (n_llrs < K + 2 * Z || n_llrs > N || nof_filler >= K) {
+    return fail(PDC_ERR_INVALID, "pdc_ldpc_decode: input length outside [K + 2Z, N]");
+  }
+  Queue& q = ctx->queues[0];
+  if (q.busy) {
+    return fail(PDC_ERR_CAPACITY, "pdc_ldpc_decode: queue 0 busy");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  pdc_cb_desc d;
+  memset(&d, 0, sizeof(d));
+  d.rm_length    = n_llrs;
+  d.harq_id      = ctx->cfg.harq_entries; // scratch entry
+  d.lifting_size = (uint16_t)Z;
+  d.nof_filler   = (uint16_t)nof_filler;
+  d.base_graph   = (uint8_t)base_graph;
+  d.qm           = 1;
+  d.crc_kind     = (uint8_t)crc_kind;
+  d.max_iter     = (uint8_t)max_iter;
+  d.flags        = PDC_CB_DECODE | ((crc_kind != PDC_CRC_NONE) ? PDC_CB_EARLY_STOP : 0);
+  d.tb_index     = 0xffff;
+  q.h_cbs[0]     = d;
+  PDC_CUDA(cudaMemcpyAsync(q.d_cbs, q.h_cbs, sizeof(d), cudaMemcpyHostToDevice, q.stream));
+  PDC_CUDA(cudaMemcpyAsync(ctx->d_scratch_llr, llrs, n_llrs, cudaMemcpyHostToDevice, q.stream));
+  PDC_CUDA(cudaMemsetAsync(q.d_cb_res, 0, sizeof(pdc_cb_result), q.stream));
+  BatchShape shape;
+  shape.max_Z      = (int)Z;
+  shape.any_bg1    = base_graph == 1;
+  shape.any_decode = true;
+  int rc = launch_batch(ctx, q.d_cbs, 1, nullptr, nullptr, 0, q.d_cb_res, q.d_cb_bits, nullptr, nullptr, shape,
+                        ctx->d_scratch_llr, n_llrs, q.stream);
+  if (rc != PDC_OK) {
+    return rc;
+  }
+  PDC_CUDA(cudaMemcpyAsync(q.h_cb_res, q.d_cb_res, sizeof(pdc_cb_result), cudaMemcpyDeviceToHost, q.stream));
+  PDC_CUDA(cudaMemcpyAsync(q.h_cb_bits, q.d_cb_bits, (K + 7) / 8, cudaMemcpyDeviceToHost, q.stream));
+  PDC_CUDA(cudaStreamSynchronize(q.stream));
+  pdc_cb_result r = q.h_cb_res[0];
+  if (r.status == 2) {
+    return fail(PDC_ERR_INVALID, "pdc_ldpc_decode: descriptor rejected by the kernel");
+  }
+  // All-zero input with a CRC calculator: the reference leaves the output untouched (ldpc_decoder_impl.cpp:88-94).
+  if (!(r.status == 1 && crc_kind != PDC_CRC_NONE)) {
+    memcpy(out, q.h_cb_bits, (K + 7) / 8);
+  }
+  if (iters) {
+    *iters = (crc_kind != PDC_CRC_NONE && r.crc_ok) ? r.iters : 0;
+  }
+  return PDC_OK;
+}
+
+int pdc_rate_dematch(pdc_ctx*      ctx,
+                     int8_t*       buffer,
+                     uint32_t      N,
+                     const int8_t* llrs,
+                     uint32_t      E,
+                     int           new_data,
+                     int           rv,
+                     int           qm,
+                     uint32_t      nref,
+                     uint32_t      nof_filler)
+{
+  if (!ctx || !buffer || !llrs || E == 0 || rv < 0 || rv > 3 ||
+      !(qm == 1 || qm == 2 || qm == 4 || qm == 6 || qm == 8) || (E % (uint32_t)qm) != 0) {
+    return fail(PDC_ERR_INVALID, "pdc_rate_dematch: invalid argument");
+  }
+  int bg = (N % 66u == 0) ? 1 : ((N % 50u == 0) ? 2 : 0);
+  if (bg == 0 || N > PDC_MAX_CB_SOFT || E > ctx->scratch_llr_bytes) {
+    return fail(PDC_ERR_INVALID, "pdc_rate_dematch: invalid buffer length");
+  }
+  uint32_t Z = N / ((bg == 1) ? 66u : 50u);
+  Queue&   q = ctx->queues[0];
+  if (q.busy) {
+    return fail(PDC_ERR_CAPACITY, "pdc_rate_dematch: queue 0 busy");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  pdc_cb_desc d;
+  memset(&d, 0, sizeof(d));
+  d.rm_length    = E;
+  d.harq_id      = ctx->cfg.harq_entries;
+  d.nref         = nref;
+  d.lifting_size = (uint16_t)Z;
+  d.nof_filler   = (uint16_t)nof_filler;
+  d.base_graph   = (uint8_t)bg;
+  d.qm           = (uint8_t)qm;
+  d.rv           = (uint8_t)rv;
+  d.flags        = PDC_CB_DEMATCH | (new_data ? PDC_CB_NEW_DATA : 0);
+  d.tb_index     = 0xffff;
+  q.h_cbs[0]     = d;
+  int8_t* entry  = ctx->d_harq + (size_t)ctx->cfg.harq_entries * PDC_MAX_CB_SOFT;
+  PDC_CUDA(cudaMemcpyAsync(q.d_cbs, q.h_cbs, sizeof(d), cudaMemcpyHostToDevice, q.stream));
+  PDC_CUDA(cudaMemcpyAsync(entry, buffer, N, cudaMemcpyHostToDevice, q.stream));
+  PDC_CUDA(cudaMemcpyAsync(ctx->d_scratch_llr, llrs, E, cudaMemcpyHostToDevice, q.stream));
+  BatchShape shape;
+  shape.max_Z       = (int)Z;
+  shape.any_bg1     = bg == 1;
+  shape.any_dematch = true;
+  int rc = launch_batch(ctx, q.d_cbs, 1, ctx->d_scratch_llr, nullptr, 0, q.d_cb_res, q.d_cb_bits, nullptr, nullptr,
+                        shape, nullptr, 0, q.stream);
+  if (rc != PDC_OK) {
+    return rc;
+  }
+  PDC_CUDA(cudaMemcpyAsync(buffer, entry, N, cudaMemcpyDeviceToHost, q.stream));
+  PDC_CUDA(cudaStreamSynchronize(q.stream));
+  return PDC_OK;
+}
+
+int pdc_crc(pdc_ctx* ctx, int crc_kind, const uint8_t* packed, uint32_t nbits, uint32_t* checksum)
+{
+  if (!ctx || !packed || !checksum || crc_kind < PDC_CRC16 || crc_kind > PDC_CRC24B ||
+      (nbits + 7) / 8 > ctx->scratch_llr_bytes) {
+    return fail(PDC_ERR_INVALID, "pdc_crc: invalid argument");
+  }
+  Queue& q = ctx->queues[0];
+  if (q.busy) {
+    return fail(PDC_ERR_CAPACITY, "pdc_crc: queue 0 busy");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  uint8_t*  d_in  = reinterpret_cast<uint8_t*>(ctx->d_scratch_llr);
+  uint32_t* d_out = reinterpret_cast<uint32_t*>(q.d_cb_res);
+  if (nbits != 0) {
+    PDC_CUDA(cudaMemcpyAsync(d_in, packed, (nbits + 7) / 8, cudaMemcpyHostToDevice, q.stream));
+  }
+  crc_kernel<<<1, 256, 0, q.stream>>>(d_in, nbits, crc_kind, d_out);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  PDC_CUDA(cudaMemcpyAsync(q.h_cb_res, d_out, sizeof(uint32_t), cudaMemcpyDeviceToHost, q.stream));
+  PDC_CUDA(cudaStreamSynchronize(q.stream));
+  memcpy(checksum, q.h_cb_res, sizeof(uint32_t));
+  return PDC_OK;
+}
+
+} // extern "C"

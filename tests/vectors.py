@@ -1,0 +1,113 @@
+"""Synthetic test vectors: valid 5G NR codewords through an AWGN channel, quantised like the reference's demodulator.
+
+LLR model: y = +-1 + N(0, sigma^2), LLR = clamp(round(6 * 2y / sigma^2), +-120) - 6 LSB per natural-log unit,
+the scale of log_likelihood_ratio::quantize with range 20 (lib/phy/upper/log_likelihood_ratio.cpp:89-98).
+Uses the oracle's TX chain (checked against the reference's own in tests/test_oracle_vs_reference.py).
+"""
+import numpy as np
+
+from oracle import pyoracle as po
+
+LIFTING_SIZES = [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 22, 24, 26, 28, 30, 32, 36, 40, 44, 48, 52,
+                 56, 60, 64, 72, 80, 88, 96, 104, 112, 120, 128, 144, 160, 176, 192, 208, 224, 240, 256, 288, 320, 352,
+                 384]
+
+
+def awgn_llr(bits, snr_db, rng):
+    sigma2 = 10.0 ** (-snr_db / 10.0)
+    y = (1.0 - 2.0 * bits.astype(np.float64)) + rng.normal(0.0, np.sqrt(sigma2), bits.size)
+    return np.clip(np.round(6.0 * 2.0 * y / sigma2), -120, 120).astype(np.int8)
+
+
+def random_message(orc, bg, Z, nof_filler, crc_kind, rng):
+    """K message bits (one per byte): payload + CRC + zero fillers."""
+    K = (22 if bg == 1 else 10) * Z
+    crc_bits = {po.CRC_NONE: 0, po.CRC16: 16, po.CRC24A: 24, po.CRC24B: 24}[crc_kind]
+    msg = rng.integers(0, 2, K).astype(np.uint8)
+    msg[K - nof_filler:] = 0
+    nb = K - nof_filler - crc_bits
+    assert nb > 0
+    if crc_bits:
+        c = orc.crc(crc_kind, np.packbits(msg[:nb]), nb)
+        msg[nb:nb + crc_bits] = [(c >> (crc_bits - 1 - i)) & 1 for i in range(crc_bits)]
+    return msg
+
+
+class CbBatch:
+    """n_cb codeblocks of one shape: rate-matched LLRs plus everything needed to run them on the GPU or the oracle."""
+
+    def __init__(self, bg, Z, E, qm, rv, nref, nof_filler, crc_kind, llrs, msgs):
+        self.bg, self.Z, self.E, self.qm, self.rv, self.nref = bg, Z, E, qm, rv, nref
+        self.nof_filler, self.crc_kind = nof_filler, crc_kind
+        self.llrs = llrs  # (n_cb, E) int8
+        self.msgs = msgs  # (n_cb, K) bits
+        self.n_cb = llrs.shape[0]
+        self.N = (66 if bg == 1 else 50) * Z
+        self.K = (22 if bg == 1 else 10) * Z
+
+    def descriptors(self, capi, max_iter, early_stop, new_data=True, harq_base=0, decode=True):
+        cbs = np.zeros(self.n_cb, capi.CB_DESC_DTYPE)
+        flags = capi.CB_DEMATCH | (capi.CB_DECODE if decode else 0) | (capi.CB_NEW_DATA if new_data else 0) | (
+            capi.CB_EARLY_STOP if early_stop else 0)
+        for i in range(self.n_cb):
+            cbs[i] = (i * self.E, self.E, harq_base + i, self.nref, self.Z, self.nof_filler, self.bg, self.qm, self.rv,
+                      self.crc_kind, max_iter, flags, 0xffff)
+        return cbs
+
+    def run_gpu(self, ctx, max_iter=6, early_stop=True, new_data=True, harq_base=0, read_harq=True, harq_init=0):
+        """harq_init: value the HARQ entries are filled with before a new transmission (None = leave them as they
+        are); the reference does not clear soft buffers either, so stale regions are part of the comparison."""
+        from srsran_edgeric_5g_b200 import capi
+        cbs = self.descriptors(capi, max_iter, early_stop, new_data, harq_base)
+        if new_data and harq_init is not None:
+            for i in range(self.n_cb):
+                ctx.harq_write(harq_base + i, np.full(self.N, harq_init, np.int8))
+        ctx.submit(cbs, np.ascontiguousarray(self.llrs.reshape(-1)), None, stream=0, want_bits=True)
+        out = ctx.wait(0)
+        kb = (self.K + 7) // 8
+        res = {
+            "crc_ok": out["cb_results"]["crc_ok"].astype(bool),
+            "iters": out["cb_results"]["iters"].astype(np.int32),
+            "status": out["cb_results"]["status"].astype(np.int32),
+            "nlayers": out["cb_results"]["nlayers"].astype(np.int32),
+            "bits": out["cb_bits"][:, :kb].copy(),
+        }
+        if read_harq:
+            res["harq"] = np.stack([ctx.harq_read(harq_base + i, self.N) for i in range(self.n_cb)])
+        return res
+
+    def run_oracle(self, orc, max_iter=6, early_stop=True, new_data=True, harq=None, scale=po.SCALE_X86,
+                   simd_width=64):
+        kb = (self.K + 7) // 8
+        harq = np.zeros((self.n_cb, self.N), np.int8) if harq is None else harq
+        crc_ok = np.zeros(self.n_cb, bool)
+        iters = np.zeros(self.n_cb, np.int32)
+        bits = np.zeros((self.n_cb, kb), np.uint8)
+        for i in range(self.n_cb):
+            it, b = orc.cb_decode(harq[i], self.llrs[i], new_data, self.rv, self.qm, self.nref, self.nof_filler,
+                                  self.crc_kind, early_stop, max_iter, scale, simd_width)
+            crc_ok[i] = it > 0
+            iters[i] = it if it > 0 else max_iter
+            bits[i] = b
+        return {"crc_ok": crc_ok, "iters": iters, "bits": bits, "harq": harq}
+
+
+def make_cb_batch(orc, bg, Z, n_cb, E, qm, rv, snr_db, seed, crc_kind=po.CRC24B, nof_filler=0, nref=0):
+    rng = np.random.default_rng(seed)
+    N = (66 if bg == 1 else 50) * Z
+    K = (22 if bg == 1 else 10) * Z
+    llrs = np.zeros((n_cb, E), np.int8)
+    msgs = np.zeros((n_cb, K), np.uint8)
+    for i in range(n_cb):
+        msg = random_message(orc, bg, Z, nof_filler, crc_kind, rng)
+        cw = orc.ldpc_encode(bg, Z, msg)
+        tx = orc.rate_match(cw, E, rv, qm, nref, nof_filler)
+        llrs[i] = awgn_llr(tx, snr_db, rng)
+        msgs[i] = msg
+    assert N == cw.size
+    return CbBatch(bg, Z, E, qm, rv, nref, nof_filler, crc_kind, llrs, msgs)
+
+
+def make_tb_llrs(orc, tb, bg, rv, qm, nref, nof_layers, n_llr, snr_db, rng):
+    cw, n_cb = orc.tb_encode(tb, bg, rv, qm, nref, nof_layers, n_llr)
+    return awgn_llr(cw, snr_db, rng), n_cb
