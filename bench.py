@@ -1,0 +1,366 @@
+#!/usr/bin/env python3
+"""bench.py - decoded info Gbit/s of the uplink PUSCH decode hot path (BG1, Z=384, 6 iterations) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one pass of the hot path (rate dematch + HARQ combine -> LDPC decode -> CB CRC) over one batch of synthetic
+codeblocks per GPU. Workload at N=1 (BASELINE.json metric shape): BG1, Z=384, rate 1/3 (E = N = 25344, 46 layers), QPSK,
+rv0, 6 LDPC iterations with early stop OFF - the worst case the metric names - n_cb codeblocks per GPU per step.
+Inputs are AWGN LLRs of valid codewords; the timed batch reads more than the 126 MB L2 per step (LLR batch + HARQ arena),
+so no explicit L2 flush is needed.
+
+  value : whole-job decoded information Gbit/s with the LLR batch resident in HBM (CUDA events, max over ranks).
+  e2e   : the same metric through the C-ABI with host buffers (pdc_submit/pdc_wait: pinned H2D of the LLRs and D2H of
+          results + decoded bits inside the timed region, two batches in flight).
+  roofline      : dominant kernel (LDPC decoder) against the integer-issue peak measured on the same device.
+  roofline_hbm  : rate-dematch kernel against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  : the reference's own AVX2/AVX512 code (oracle/_ref/libsrsref.so) on all host cores, bounded sample.
+
+Multi-GPU: one process per GPU (torchrun), codeblock batches are independent (cells/UEs are sharded, HARQ state is
+sticky per GPU), no data-path collective: "scaling": "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "decoded_info_gbps_bg1_z384_6it"
+UNIT = "Gbit/s"
+BG, Z, QM, RV, MAX_ITER = 1, 384, 2, 0, 6
+N_SOFT = 66 * Z
+K_BITS = 22 * Z
+INFO_BITS = K_BITS - 24  # payload delivered per codeblock (K - F - CB CRC)
+EDGES_46 = 316
+WORKLOAD = "bg1_z384_rate1/3_E25344_qpsk_rv0_6it_fixed"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_batch(orc, n_distinct, n_cb, snr_db, seed):
+    """n_cb x E int8 LLRs: n_distinct different noisy codewords tiled (distinct addresses, inputs larger than L2)."""
+    from tests.vectors import make_cb_batch
+    from oracle.pyoracle import CRC24B
+    b = make_cb_batch(orc, BG, Z, n_distinct, N_SOFT, QM, RV, snr_db, seed, CRC24B)
+    reps = -(-n_cb // n_distinct)
+    return np.tile(b.llrs, (reps, 1))[:n_cb].copy(), b
+
+
+def cpu_reference_rate(llrs, early_stop, target_seconds, threads):
+    """Reference CPU arm: Gbit/s of info bits on `threads` host threads over a bounded sample of the same workload."""
+    from oracle.pyoracle import Reference, Oracle, CRC24B
+    if Reference.available():
+        ref = Reference("auto")
+        kind, variant = "reference", ref.auto_variant()
+        n0 = min(llrs.shape[0], threads * 4)
+        sec, _ = ref.bench_cb_batch(llrs[:n0], N_SOFT, N_SOFT, RV, QM, 0, 0, CRC24B, early_stop, MAX_ITER, threads, 1)
+        per_pass = max(sec, 1e-6)
+        n = min(llrs.shape[0], max(threads, int(n0 * min(4.0, target_seconds / 2 / per_pass))))
+        sec1, _ = ref.bench_cb_batch(llrs[:n], N_SOFT, N_SOFT, RV, QM, 0, 0, CRC24B, early_stop, MAX_ITER, threads, 1)
+        repeats = max(1, int(target_seconds / max(sec1, 1e-6)))
+        sec, _ = ref.bench_cb_batch(llrs[:n], N_SOFT, N_SOFT, RV, QM, 0, 0, CRC24B, early_stop, MAX_ITER, threads,
+                                    repeats)
+        n_total = n * repeats
+    else:
+        orc = Oracle()
+        kind, variant, threads = "port", "oracle/pusch_oracle.c (scalar)", 1
+        n = max(1, min(llrs.shape[0], int(target_seconds / 0.03)))
+        sec, _ = orc.bench_cb_batch(llrs[:n], N_SOFT, N_SOFT, RV, QM, 0, 0, CRC24B, early_stop, MAX_ITER)
+        n_total = n
+    gbps = n_total * INFO_BITS / sec / 1e9
+    return {"value": gbps, "unit": UNIT, "cores": threads, "kind": kind, "variant": variant,
+            "sample": f"{n_total} codeblocks of the bench workload ({WORKLOAD}), {sec:.1f} s wall",
+            "us_per_cb_per_core": sec / n_total * threads * 1e6}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from oracle.pyoracle import Oracle
+    orc = Oracle()
+    llrs, _ = synth_batch(orc, 64, 1024, args.snr, 1234)
+    threads = os.cpu_count() or 1
+    per_step = 4.0  # seconds of CPU work per step: (steps + warmup) x 4 s stays within a few minutes
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_rate(llrs, False, per_step, threads)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    n_cb_step = v * 1e9 / INFO_BITS * per_step
+    line = {
+        "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8", "data": "synthetic", "impl": "reference",
+        "config": {"workload": WORKLOAD, "codeblocks_per_step": int(n_cb_step), "early_stop": False,
+                   "host_threads": threads, "variant": vals[-1]["variant"]},
+        "cpu_baseline": {**vals[-1], "value": v},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--n-cb", type=int, default=8192, help="codeblocks per GPU per step")
+    ap.add_argument("--snr", type=float, default=-1.0, help="AWGN SNR (dB) of the synthetic LLRs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the early-stop / config-3 / cpu legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl cuda needs a GPU (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from oracle.pyoracle import Oracle
+    from srsran_edgeric_5g_b200 import capi
+
+    orc = Oracle()
+    n_cb = args.n_cb
+    ctx = capi.Context(device=local_rank, max_cbs=n_cb, max_llrs=n_cb * N_SOFT, harq_entries=n_cb, max_tbs=1,
+                       max_tb_bytes=4096, nof_streams=2)
+    llrs_np, small = synth_batch(orc, 64, n_cb, args.snr, 1234 + rank)
+    pinned = [capi.PinnedBuffer(n_cb * N_SOFT), capi.PinnedBuffer(n_cb * N_SOFT)]
+    for p in pinned:
+        p.array[:] = llrs_np.reshape(-1)
+
+    def descs(early_stop, E=N_SOFT, qm=QM, nref=0, F=0):
+        d = np.zeros(n_cb, capi.CB_DESC_DTYPE)
+        flags = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA | (capi.CB_EARLY_STOP if early_stop else 0)
+        d["llr_offset"] = np.arange(n_cb, dtype=np.uint64) * E
+        d["rm_length"], d["harq_id"], d["nref"] = E, np.arange(n_cb), nref
+        d["lifting_size"], d["nof_filler"], d["base_graph"], d["qm"], d["rv"] = Z, F, BG, qm, RV
+        d["crc_kind"], d["max_iter"], d["flags"], d["tb_index"] = capi.CRC24B, MAX_ITER, flags, 0xffff
+        return d
+
+    stream = torch.cuda.current_stream()
+    d_llrs = torch.from_numpy(llrs_np.reshape(-1)).cuda()
+    d_res = torch.zeros(n_cb * 4, dtype=torch.uint8, device="cuda")
+    d_bits = torch.zeros(n_cb * capi.PDC_MAX_CB_BYTES, dtype=torch.uint8, device="cuda")
+    flags_union = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA | capi.CB_EARLY_STOP
+
+    def resident_step(d_cbs):
+        ctx.launch_device(d_cbs.data_ptr(), n_cb, d_llrs.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), Z, flags_union,
+                          True, cuda_stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def time_resident(d_cbs, steps, warmup):
+        for _ in range(warmup):
+            resident_step(d_cbs)
+        barrier()
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            resident_step(d_cbs)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.launch_count() - l0
+
+    def time_kernels_separately(d_cbs, steps):
+        """Average device time of each kernel of the step (dematch-only and decode-only launches)."""
+        out = {}
+        for name, fl in (("rate_dematch", capi.CB_DEMATCH), ("ldpc_decode", capi.CB_DECODE)):
+            for _ in range(2):
+                ctx.launch_device(d_cbs.data_ptr(), n_cb, d_llrs.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), Z, fl,
+                                  True, cuda_stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                ctx.launch_device(d_cbs.data_ptr(), n_cb, d_llrs.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), Z, fl,
+                                  True, cuda_stream=stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            out[name] = e0.elapsed_time(e1) / steps
+        return out
+
+    # ---- headline: fixed 6 iterations, resident -------------------------------------------------------------------------
+    d_fixed = torch.from_numpy(descs(False).view(np.uint8)).cuda()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, launches = time_resident(d_fixed, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_per_step = ms / args.steps
+    value = world * n_cb * INFO_BITS / (ms_per_step * 1e-3) / 1e9
+
+    # Parity spot check on the timed configuration: first codeblocks of this rank against the oracle.
+    res = d_res.cpu().numpy().view(capi.CB_RESULT_DTYPE)
+    bits = d_bits.cpu().numpy().reshape(n_cb, capi.PDC_MAX_CB_BYTES)
+    ref = small.run_oracle(orc, MAX_ITER, False)
+    n_chk = 8
+    parity_ok = bool((res["crc_ok"][:n_chk].astype(bool) == ref["crc_ok"][:n_chk]).all() and
+                     (bits[:n_chk, :K_BITS // 8] == ref["bits"][:n_chk]).all())
+
+    # ---- e2e: host buffers through pdc_submit / pdc_wait, two batches in flight -----------------------------------------
+    cb_fixed = descs(False)
+
+    def e2e_run(steps):
+        ctx.submit(cb_fixed, pinned[0].array, None, stream=0)
+        for i in range(1, steps):
+            ctx.submit(cb_fixed, pinned[i & 1].array, None, stream=i & 1)
+            ctx.wait((i - 1) & 1)
+        return ctx.wait((steps - 1) & 1)
+
+    e2e_run(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_out = e2e_run(args.steps)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e2e_s = t1 - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * n_cb * INFO_BITS * args.steps / e2e_s / 1e9
+    h2d = n_cb * N_SOFT + n_cb * capi.CB_DESC_DTYPE.itemsize
+    d2h = n_cb * capi.PDC_MAX_CB_BYTES + n_cb * 4
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "codeblocks_per_gpu_per_step": n_cb, "layers": 46, "early_stop": False,
+                   "info_bits_per_cb": INFO_BITS, "k_bits_per_cb": K_BITS, "snr_db": args.snr,
+                   "l2": "no flush: each step streams %d MB of LLRs + %d MB of HARQ soft bits (> 126 MB L2)" %
+                         (n_cb * N_SOFT >> 20, n_cb * N_SOFT >> 20),
+                   "parity_spot_check_vs_oracle": parity_ok, "us_per_slot_equiv_152cb": ms_per_step * 1e3 * 152 / n_cb},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": launches,
+    }
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel + HBM roofline of the dematcher (rank 0, kernels timed alone) -----------------
+        kt = time_kernels_separately(d_fixed, max(3, args.steps // 2))
+        pk, pk_src = peaks()
+        int_peak_alu = ctx.measure_int_peak(0)
+        int_peak_both = ctx.measure_int_peak(1)
+        edge_updates = EDGES_46 * Z * MAX_ITER * n_cb
+        ops = edge_updates * 22.0  # ~22 int8 lane-operations per edge update (algorithmic figure)
+        dec_s = kt["ldpc_decode"] * 1e-3
+        # Peak in int8 lane-operations: measured 32-bit integer issue rate (both pipes) x 4 packed int8 lanes.
+        peak_i8 = int_peak_both * 4.0
+        line["roofline"] = {
+            "kernel": "ldpc_decode", "bound": "int_issue", "achieved": ops / dec_s / 1e12, "peak": peak_i8 / 1e12,
+            "unit": "Tera int8-lane-op/s", "frac": ops / dec_s / peak_i8, "traffic": None,
+            "edge_updates_per_s": edge_updates / dec_s, "ms_per_launch": kt["ldpc_decode"],
+            "share_of_step": kt["ldpc_decode"] / (kt["ldpc_decode"] + kt["rate_dematch"]),
+            "peak_source": "pdc_measure_int_peak on this device: %.1f (ALU pipe) / %.1f (ALU+FMA pipes) Tera 32-bit "
+                           "lane-op/s; x4 int8 lanes" % (int_peak_alu / 1e12, int_peak_both / 1e12),
+        }
+        dm_bytes = n_cb * (N_SOFT + N_SOFT)  # new data: read E, write N
+        dm_s = kt["rate_dematch"] * 1e-3
+        line["roofline_hbm"] = {
+            "kernel": "rate_dematch", "bound": "hbm", "achieved": dm_bytes / dm_s / 1e9, "peak": pk["hbm_gbs"],
+            "unit": "GB/s", "frac": dm_bytes / dm_s / 1e9 / pk["hbm_gbs"], "traffic": None,
+            "ms_per_launch": kt["rate_dematch"], "peak_source": pk_src,
+        }
+        if not args.no_extras:
+            # ---- the same workload with CRC early stop on (operating point), and the config-3 shape -------------------------
+            d_es = torch.from_numpy(descs(True).view(np.uint8)).cuda()
+            llrs_hi, _ = synth_batch(orc, 64, n_cb, args.snr + 2.0, 99)
+            d_llrs.copy_(torch.from_numpy(llrs_hi.reshape(-1)))
+            ms_es, _ = time_resident(d_es, max(3, args.steps // 2), 2) if world == 1 else (None, 0)
+            if ms_es:
+                res = d_res.cpu().numpy().view(capi.CB_RESULT_DTYPE)
+                line["extra"] = {"early_stop_on": {
+                    "value": n_cb * INFO_BITS / (ms_es / max(3, args.steps // 2) * 1e-3) / 1e9, "unit": UNIT,
+                    "snr_db": args.snr + 2.0, "mean_iters": float(res["iters"].mean()),
+                    "crc_ok_frac": float(res["crc_ok"].mean())}}
+            # ---- CPU baseline: the reference's own SIMD code on the host cores, bounded sample ---------------------------
+            line["cpu_baseline"] = cpu_reference_rate(llrs_np[:2048], False, 12.0, os.cpu_count() or 1)
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

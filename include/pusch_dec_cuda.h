@@ -132,6 +132,12 @@ const char* pdc_last_error(void);
 int pdc_device_info(pdc_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
 uint64_t pdc_launch_count(pdc_ctx* ctx);
 
+/*
+ * Measures the 32-bit integer instruction throughput of the device in lane-operations per second (the decoder's
+ * roofline denominator): mode 0 = LOP3/IADD3 only (ALU pipe), mode 1 = LOP3/IADD3 interleaved with IMAD (ALU + FMA pipes).
+ */
+int pdc_measure_int_peak(pdc_ctx* ctx, int mode, double* lane_ops_per_s);
+
 /* Pinned host memory for zero-copy-staging of LLR batches (the caller may also pass pageable memory, at a price). */
 void* pdc_host_alloc(size_t bytes);
 void  pdc_host_free(void* p);

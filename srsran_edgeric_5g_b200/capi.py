@@ -56,7 +56,7 @@ assert CB_DESC_DTYPE.itemsize == ctypes.sizeof(CbDesc) == 28
 assert TB_DESC_DTYPE.itemsize == ctypes.sizeof(TbDesc) == 20
 
 EXPORTS = ["pdc_default_config", "pdc_create", "pdc_destroy", "pdc_last_error", "pdc_device_info", "pdc_launch_count",
-           "pdc_host_alloc", "pdc_host_free", "pdc_submit", "pdc_wait", "pdc_poll", "pdc_launch_device",
+           "pdc_measure_int_peak", "pdc_host_alloc", "pdc_host_free", "pdc_submit", "pdc_wait", "pdc_poll", "pdc_launch_device",
            "pdc_harq_read", "pdc_harq_write", "pdc_harq_free", "pdc_harq_device_ptr", "pdc_ldpc_decode",
            "pdc_rate_dematch", "pdc_crc"]
 
@@ -89,6 +89,7 @@ def load():
     L.pdc_device_info.argtypes = [_vp] + [ctypes.POINTER(ctypes.c_int)] * 3
     L.pdc_launch_count.argtypes = [_vp]
     L.pdc_launch_count.restype = ctypes.c_uint64
+    L.pdc_measure_int_peak.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     L.pdc_host_alloc.argtypes = [ctypes.c_size_t]
     L.pdc_host_alloc.restype = _vp
     L.pdc_host_free.argtypes = [_vp]
@@ -175,6 +176,12 @@ class Context:
 
     def launch_count(self):
         return int(self._L.pdc_launch_count(self.h))
+
+    def measure_int_peak(self, mode=0):
+        """32-bit integer lane-operations per second (mode 0: ALU pipe only, 1: ALU + FMA pipes)."""
+        v = ctypes.c_double()
+        check(self._L.pdc_measure_int_peak(self.h, mode, ctypes.byref(v)))
+        return v.value
 
     # -- batched interface --------------------------------------------------------------------------------------------
     def submit(self, cbs, llrs, tbs=None, stream=0, want_bits=True, want_tb=True):

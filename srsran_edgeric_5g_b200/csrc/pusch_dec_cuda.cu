@@ -1,14 +1,16 @@
 // C-ABI implementation (include/pusch_dec_cuda.h): context, streams ("queues"), pinned staging, HARQ arena and kernel
 // launches. Single translation unit: the kernels are included so that they share the constant-memory tables.
+#include <algorithm>
 #include "pdc_device.cuh"
 #include "tables.cuh"
 #include "rate_dematch.cuh"
 #include "ldpc_decode_scalar.cuh"
+#include "ldpc_decode_h2.cuh"
 #include "tb_assemble.cuh"
 
-#include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -76,6 +78,9 @@ struct pdc_ctx {
   size_t               scratch_llr_bytes = 0;
   std::vector<Queue>   queues;
   std::atomic<uint64_t> launches{0};
+  bool                 force_scalar = false;      // PDC_FORCE_SCALAR=1: use the general kernel for every batch
+  uint32_t*            d_state_scratch = nullptr; // compressed check-to-variable messages of the resident CTAs
+  size_t               state_scratch_words = 0;
 };
 
 namespace {
@@ -135,7 +140,25 @@ int launch_batch(pdc_ctx*             ctx,
     ctx->launches++;
   }
   if (shape.any_decode) {
-    PDC_CUDA(pdc::launch_ldpc_decode(p, shape.max_Z, shape.any_bg1, direct_in, direct_n, s));
+    if (direct_in == nullptr && ctx->cfg.scale_mode != PDC_SCALE_NEON && !ctx->force_scalar) {
+      // Throughput kernel: two codeblocks per CTA, half-precision packed arithmetic.
+      pdc::H2Plan plan;
+      PDC_CUDA(pdc::h2_plan(shape.max_Z, shape.any_bg1, n_cb, ctx->sm_count, plan));
+      size_t need = plan.scratch_words_per_cta * (size_t)plan.grid;
+      if (need > ctx->state_scratch_words) {
+        // Grow-only; sized once per (largest lifting size) in practice. cudaMalloc synchronises the device.
+        size_t want = plan.scratch_words_per_cta * (size_t)ctx->sm_count * 8;
+        want        = std::max(need, std::min(want, (size_t)1 << 27));
+        PDC_CUDA(cudaFree(ctx->d_state_scratch));
+        ctx->d_state_scratch     = nullptr;
+        ctx->state_scratch_words = 0;
+        PDC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->d_state_scratch), want * sizeof(uint32_t)));
+        ctx->state_scratch_words = want;
+      }
+      PDC_CUDA(pdc::launch_ldpc_decode_h2(p, plan, ctx->d_state_scratch, s));
+    } else {
+      PDC_CUDA(pdc::launch_ldpc_decode(p, shape.max_Z, shape.any_bg1, direct_in, direct_n, s));
+    }
     ctx->launches++;
   }
   if (n_tb != 0) {
@@ -214,6 +237,40 @@ __global__ void crc_kernel(const uint8_t* packed, uint32_t nbits, int kind, uint
   }
 }
 
+// Integer-pipe throughput probe: the decoder is bound by 32-bit integer/logic instruction issue (no tensor cores, no
+// HBM), so the roofline denominator is measured on the device it runs on. mode 0: LOP3 + IADD3 only (ALU pipe);
+// mode 1: LOP3/IADD3 interleaved with IMAD (ALU + FMA pipes).
+template <int MODE>
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters)
+{
+  uint32_t a[8];
+  uint32_t b = threadIdx.x * 2654435761u + 1u, c = blockIdx.x * 40503u + 7u;
+#pragma unroll
+  for (int k = 0; k != 8; ++k) {
+    a[k] = b + k;
+  }
+  for (int i = 0; i != iters; ++i) {
+#pragma unroll
+    for (int r = 0; r != 8; ++r) {
+#pragma unroll
+      for (int k = 0; k != 8; ++k) {
+        if (MODE == 0 || (k & 1)) {
+          a[k] = (a[k] ^ b) + c; // LOP3 + IADD3
+        } else {
+          a[k] = a[k] * 5u + b;  // IMAD
+          a[k] = a[k] * 3u + c;  // IMAD
+        }
+      }
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k != 8; ++k) {
+    r ^= a[k];
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 cudaError_t upload_crc_tables()
 {
   uint32_t h[3][24];
@@ -273,6 +330,10 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
     return fail(PDC_ERR_INVALID, "pdc_create: out of host memory");
   }
   ctx->cfg      = *cfg;
+  {
+    const char* fs    = getenv("PDC_FORCE_SCALAR");
+    ctx->force_scalar = fs && fs[0] == '1';
+  }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
@@ -349,6 +410,7 @@ void pdc_destroy(pdc_ctx* ctx)
   cudaFree(ctx->d_harq);
   cudaFree(ctx->d_harq_data);
   cudaFree(ctx->d_scratch_llr);
+  cudaFree(ctx->d_state_scratch);
   delete ctx;
 }
 
@@ -700,6 +762,44 @@ int pdc_rate_dematch(pdc_ctx*      ctx,
   }
   PDC_CUDA(cudaMemcpyAsync(buffer, entry, N, cudaMemcpyDeviceToHost, q.stream));
   PDC_CUDA(cudaStreamSynchronize(q.stream));
+  return PDC_OK;
+}
+
+int pdc_measure_int_peak(pdc_ctx* ctx, int mode, double* lane_ops_per_s)
+{
+  if (!ctx || !lane_ops_per_s || mode < 0 || mode > 1) {
+    return fail(PDC_ERR_INVALID, "pdc_measure_int_peak: invalid argument");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  Queue&    q      = ctx->queues[0];
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 2000;
+  uint32_t* d_out  = nullptr;
+  PDC_CUDA(dev_alloc(&d_out, (size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  PDC_CUDA(cudaEventCreate(&e0));
+  PDC_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep != 4; ++rep) {
+    PDC_CUDA(cudaEventRecord(e0, q.stream));
+    if (mode == 0) {
+      int_peak_kernel<0><<<blocks, threads, 0, q.stream>>>(d_out, iters);
+    } else {
+      int_peak_kernel<1><<<blocks, threads, 0, q.stream>>>(d_out, iters);
+    }
+    PDC_CUDA(cudaEventRecord(e1, q.stream));
+    PDC_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    PDC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) {
+      best = ms;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  // 64 statements per inner iteration, 2 integer instructions each.
+  double ops      = (double)blocks * threads * (double)iters * 64.0 * 2.0;
+  *lane_ops_per_s = ops / (best * 1e-3);
   return PDC_OK;
 }
 
