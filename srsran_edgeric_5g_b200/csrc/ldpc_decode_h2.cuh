@@ -9,7 +9,8 @@
 //   * packed add/fma/relu on the FMA pipe (HADD2/HFMA2), leaving the ALU pipe (LOP3/PRMT/HMNMX2, 64 lanes/clk/SM on
 //     B200 - the bound of this kernel) for sign logic and min/second-min only; both pipes issue in parallel.
 // Check-to-variable messages are kept compressed per (row, check) as {scaled min1, scaled min2} bytes plus one
-// "is the minimum" and one "sign" bit per edge, from which every message is exactly reconstructible.
+// "is the minimum" and one "sign" bit per edge, from which every message is exactly reconstructible; they live in a
+// per-CTA scratch that stays L2-resident (persistent CTAs) and are prefetched one row ahead.
 //
 // Bit-exact target: ldpc_decoder_impl::decode (lib/phy/upper/channel_coding/ldpc/ldpc_decoder_impl.cpp:60-318) with the
 // AVX2/AVX512 or generic node kernels (ldpc_decoder_avx512.cpp:81-290, ldpc_decoder_generic.cpp:30-128); see SURVEY 8a
@@ -24,33 +25,13 @@ namespace h2 {
 
 typedef uint32_t hh; // two halves: low = codeblock A, high = codeblock B
 
-__device__ __forceinline__ __half2 as_h2(hh x)
+__device__ __forceinline__ __half2 H(hh x)
 {
   return *reinterpret_cast<__half2*>(&x);
 }
-__device__ __forceinline__ hh as_u(__half2 x)
+__device__ __forceinline__ hh U(__half2 x)
 {
   return *reinterpret_cast<hh*>(&x);
-}
-__device__ __forceinline__ hh hfma(hh a, hh b, hh c)
-{
-  return as_u(__hfma2(as_h2(a), as_h2(b), as_h2(c)));
-}
-__device__ __forceinline__ hh hfma_relu(hh a, hh b, hh c)
-{
-  return as_u(__hfma2_relu(as_h2(a), as_h2(b), as_h2(c)));
-}
-__device__ __forceinline__ hh hadd(hh a, hh b)
-{
-  return as_u(__hadd2(as_h2(a), as_h2(b)));
-}
-__device__ __forceinline__ hh hmin(hh a, hh b)
-{
-  return as_u(__hmin2(as_h2(a), as_h2(b)));
-}
-__device__ __forceinline__ hh hmax(hh a, hh b)
-{
-  return as_u(__hmax2(as_h2(a), as_h2(b)));
 }
 __device__ __forceinline__ hh lop_and_or(hh a, hh b, hh c) // (a & b) | c
 {
@@ -64,47 +45,27 @@ __device__ __forceinline__ hh lop_xor_and(hh a, hh b, hh c) // a ^ (b & c)
   asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
   return r;
 }
-__device__ __forceinline__ hh lop_sel(hh a, hh b, hh m) // (a & m) | (b & ~m)
-{
-  hh r;
-  asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(m), "r"(a), "r"(b));
-  return r;
-}
 
 // Half-precision constants, both halves.
-constexpr hh H_ZERO   = 0x00000000u;
-constexpr hh H_ONE    = 0x3C003C00u;
-constexpr hh H_NEG1   = 0xBC00BC00u;
-constexpr hh H_TWO    = 0x40004000u;
-constexpr hh H_HALF   = 0x38003800u;
-constexpr hh H_120    = 0x57805780u;
-constexpr hh H_N120   = 0xD780D780u;
-constexpr hh H_230    = 0x5B305B30u;
-constexpr hh H_N230   = 0xDB30DB30u;
-constexpr hh H_128    = 0x58005800u;
-constexpr hh H_N128   = 0xD800D800u;
-constexpr hh H_1024   = 0x64006400u;
-constexpr hh H_N1024  = 0xE400E400u;
-constexpr hh H_BIG    = 0x7BFF7BFFu; // 65504
-constexpr hh H_NBIG   = 0xFBFFFBFFu;
-constexpr hh H_INF    = 0x7C007C00u;
-constexpr hh H_SIGN   = 0x80008000u;
-constexpr hh H_ABS    = 0x7FFF7FFFu;
-constexpr hh H_0P8    = 0x3A663A66u; // 0.7998046875
-constexpr hh H_N0P6   = 0xB8CDB8CDu; // -0.60009765625
-constexpr hh H_256    = 0x5C005C00u;
-
-// Where the compressed check-to-variable state of a row lives.
-enum StateSpace { STATE_SMEM = 0, STATE_GLOBAL = 1 };
+constexpr hh H_ZERO  = 0x00000000u;
+constexpr hh H_ONE   = 0x3C003C00u;
+constexpr hh H_NEG1  = 0xBC00BC00u;
+constexpr hh H_TWO   = 0x40004000u;
+constexpr hh H_HALF  = 0x38003800u;
+constexpr hh H_120   = 0x57805780u;
+constexpr hh H_N120  = 0xD780D780u;
+constexpr hh H_N230  = 0xDB30DB30u;
+constexpr hh H_N128  = 0xD800D800u;
+constexpr hh H_1024  = 0x64006400u;
+constexpr hh H_N1024 = 0xE400E400u;
+constexpr hh H_BIG   = 0x7BFF7BFFu; // 65504: one excess unit times BIG overflows to infinity
+constexpr hh H_NBIG  = 0xFBFFFBFFu;
+constexpr hh H_SIGN  = 0x80008000u;
+constexpr hh H_0P8   = 0x3A663A66u; // 0.7998046875
+constexpr hh H_N0P6  = 0xB8CDB8CDu; // -0.60009765625
 
 struct RowState {
-  hh w[4]; // w[0]: scaled minima as bytes {m1 A, m1 B, m2 A, m2 B}; w[1..3]: flag groups of 8 edges
-};
-
-// Per-CTA view of the state storage: word k of row m of thread j is at base[(off[m] + k) * stride + j].
-struct StateView {
-  hh*      base;
-  uint32_t stride;
+  hh w[4]; // w[0]: scaled minima as bytes {m1 A, m1 B, m2 A, m2 B}; w[1..3]: flag groups of 8 edges {M B, S B, M A, S A}
 };
 
 __device__ __forceinline__ int flag_groups(int deg)
@@ -114,158 +75,141 @@ __device__ __forceinline__ int flag_groups(int deg)
 
 // The lifted graph of this (base graph, Z) in shared memory.
 struct GraphSmem {
-  uint16_t shift[MAX_EDGES];
-  uint8_t  col[MAX_EDGES];
+  uint16_t shift[MAX_EDGES];      // circulant shift of the edge
+  uint16_t base[MAX_EDGES];       // col * Z: first soft word of the edge's variable node
   uint16_t row_start[MAX_ROWS + 2];
-  uint16_t st_off[MAX_ROWS + 2]; // state word offset of each row
+  uint16_t st_off[MAX_ROWS + 2];  // state word offset of each row
 };
 
 // One base-graph row (layer) of degree DEG for check j of both codeblocks.
 //   soft     : variable-node soft bits, soft[col * Z + pos], fp16x2
 //   st/st_out: compressed messages of this row from the previous iteration / for the next one
-//   lane_mask: 0xffff per half that takes part (a half whose codeblock uses fewer rows is frozen on the extra rows)
-template <int DEG, bool MASKED>
-__device__ __forceinline__ void process_row(hh* __restrict__ soft, const GraphSmem& g, int e0, int j, int Z,
-                                            const RowState& st, RowState& st_out, int scale_mode, hh lane_mask)
+template <int DEG>
+__device__ __forceinline__ void process_row(hh* __restrict__ soft, const uint16_t* __restrict__ e_shift,
+                                            const uint16_t* __restrict__ e_base, int j, int Z, const RowState& st,
+                                            RowState& st_out, int scale_mode)
 {
-  hh  vu[DEG]; // soft - c2v_old, unclamped: |.| <= 222 or +-INF
-  int idx[DEG];
+  __half2  vc[DEG]; // soft - c2v_old clamped to +-120, infinite if the soft bit was infinite
+  uint32_t idx[DEG];
 
-  // Old scaled minima: bytes -> halves.
-  hh m1 = hadd(__byte_perm(st.w[0], 0x64646464u, 0x4140), H_N1024);
-  hh m2 = hadd(__byte_perm(st.w[0], 0x64646464u, 0x4342), H_N1024);
-  // -mag_old = z * hd - mid with z = -1 for the edge holding the minimum (gets min2), +1 otherwise (gets min1).
-  hh mid = hfma(hadd(m1, m2), H_HALF, H_ZERO);
-  hh hd  = hfma(hadd(m2, m1 ^ H_SIGN), H_HALF, H_ZERO);
-  hh nmid = mid ^ H_SIGN;
+  const __half2 one = H(H_ONE), neg1 = H(H_NEG1), h120 = H(H_120), hn120 = H(H_N120), hn230 = H(H_N230);
 
-  hh min1 = H_120, min2 = H_120, par = 0;
-  hh ps = 0, pm = 0;
+  // Old scaled minima: bytes -> halves. -mag_old = z * hd - mid with z = -1 for the edge that held the minimum (its
+  // message was min2), +1 otherwise (min1).
+  const __half2 m1  = __hadd2(H(__byte_perm(st.w[0], 0x64646464u, 0x4140)), H(H_N1024));
+  const __half2 m2  = __hadd2(H(__byte_perm(st.w[0], 0x64646464u, 0x4342)), H(H_N1024));
+  const __half2 mid = __hmul2(__hadd2(m1, m2), H(H_HALF));
+  const __half2 hd  = __hmul2(__hsub2(m2, m1), H(H_HALF));
+
+  __half2 min1 = h120, min2 = h120;
+  hh      par = 0, ps = 0, pm = 0;
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
     if ((e & 7) == 0) {
       hh f = st.w[1 + (e >> 3)];
-      pm   = f;      // "is minimum" flags: bit 15 of each half = edge e, then e+1, ...
+      pm   = f;      // "held the minimum" flags: bit 15 of each half = edge e, then e+1, ... after each doubling
       ps   = f << 8; // sign flags
     }
-    int pos = j + g.shift[e0 + e];
-    pos     = (pos >= Z) ? pos - Z : pos;
-    idx[e]  = g.col[e0 + e] * Z + pos;
-    hh s    = soft[idx[e]];
-    hh z    = lop_and_or(pm, H_SIGN, H_ONE);
-    hh sg   = lop_and_or(ps, H_SIGN, H_ONE);
-    hh nmag = hfma(z, hd, nmid);
-    hh v    = hfma(sg, nmag, s); // s - sg * mag_old
-    vu[e]   = v;
-    hh a    = hmin(v & H_ABS, H_120);
-    min2    = hmin(min2, hmax(min1, a));
-    min1    = hmin(min1, a);
-    par ^= v;
-    pm += pm;
-    ps += ps;
+    uint32_t pos = (uint32_t)j + e_shift[e];
+    pos          = min(pos, pos - (uint32_t)Z); // wrap: pos - Z underflows to a huge value when pos < Z
+    idx[e]       = e_base[e] + pos;
+    const __half2 s    = H(soft[idx[e]]);
+    const __half2 z    = H(lop_and_or(pm, H_SIGN, H_ONE));
+    const __half2 sg   = H(lop_and_or(ps, H_SIGN, H_ONE));
+    const __half2 nmag = __hfma2(z, hd, __hneg2(mid));
+    const __half2 v    = __hfma2(sg, nmag, s); // s - c2v_old; |v| <= 222, or infinite with s
+    // Clamp to +-120 but keep infinity: relu(|v| - 230) is 0 for every finite v.
+    __half2       c   = __hmax2(__hmin2(v, h120), hn120);
+    const __half2 ehi = __hfma2_relu(v, one, hn230);
+    const __half2 elo = __hfma2_relu(v, neg1, hn230);
+    c                 = __hadd2(c, __hsub2(ehi, elo));
+    vc[e]             = c;
+    par ^= U(c);
+    const __half2 a = __habs2(c);
+    min2            = __hmin2(min2, __hmax2(min1, a));
+    min1            = __hmin2(min1, a);
+    pm <<= 1;
+    ps <<= 1;
   }
 
   // Scaled minima. x86: (x * 52428) >> 16 == ceil(0.8 x) - 1 for x >= 1, 0 for x = 0;
-  // generic: round(0.8 x). Both are computed exactly through round-to-nearest at the 1024 binade.
-  hh s1, s2;
+  // generic: round(0.8 x). Both are computed exactly through round-to-nearest in the [1024, 2048) binade.
+  __half2 s1, s2;
   if (scale_mode == PDC_SCALE_X86) {
-    s1 = hfma_relu(hadd(hfma(min1, H_0P8, H_N0P6), H_1024), H_ONE, H_N1024);
-    s2 = hfma_relu(hadd(hfma(min2, H_0P8, H_N0P6), H_1024), H_ONE, H_N1024);
+    s1 = __hfma2_relu(__hadd2(__hfma2(min1, H(H_0P8), H(H_N0P6)), H(H_1024)), one, H(H_N1024));
+    s2 = __hfma2_relu(__hadd2(__hfma2(min2, H(H_0P8), H(H_N0P6)), H(H_1024)), one, H(H_N1024));
   } else {
-    s1 = hadd(hfma(min1, H_0P8, H_1024), H_N1024);
-    s2 = hadd(hfma(min2, H_0P8, H_1024), H_N1024);
+    s1 = __hadd2(__hfma2(min1, H(H_0P8), H(H_1024)), H(H_N1024));
+    s2 = __hadd2(__hfma2(min2, H(H_0P8), H(H_1024)), H(H_N1024));
   }
-  const hh ds     = hadd(s2, s1 ^ H_SIGN);
-  const hh nmin1s = hfma(min1, H_N128, H_ZERO); // -128 * min1
-  const hh par_s  = lop_and_or(par, H_SIGN, H_ONE);
+  const __half2 ds    = __hsub2(s2, s1);
+  const hh      par_s = lop_and_or(par, H_SIGN, H_ONE);
 
-  hh acc_s = 0, acc_m = 0;
+  __half2 acc_s = H(H_ZERO), acc_m = H(H_ZERO);
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
-    hh v   = vu[e];
-    hh vc  = hmax(hmin(v, H_120), H_N120);
-    hh a   = vc & H_ABS;
-    hh u   = hfma(a, H_128, nmin1s);       // 128 * (a - min1) >= 0
-    hh ism = hfma_relu(u, H_NEG1, H_ONE);  // 1 if this edge holds the minimum
-    hh mag = hfma(ism, ds, s1);
-    hh sgn = lop_xor_and(par_s, v, H_SIGN); // +-1: row parity without this edge
-    hh x   = hfma(sgn, mag, vc);
-    // Promotion: |x| > 120 -> +-INF; a soft bit that was infinite stays infinite (|v| > 230 only if infinite).
-    hh ehi = hfma_relu(x, H_ONE, H_N120);
-    hh elo = hfma_relu(x, H_NEG1, H_N120);
-    hh r   = hfma(ehi, H_BIG, x);
-    r      = hfma(elo, H_NBIG, r);
-    hh ihi = hfma_relu(v, H_ONE, H_N230);
-    hh ilo = hfma_relu(v, H_NEG1, H_N230);
-    r      = hadd(r, hadd(ihi, ilo ^ H_SIGN));
-    if (MASKED) {
-      r = lop_sel(r, soft[idx[e]], lane_mask);
-    }
-    soft[idx[e]] = r;
-    acc_s = hfma(acc_s, H_TWO, hfma_relu(sgn, H_NEG1, H_ZERO));
-    acc_m = hfma(acc_m, H_TWO, ism);
+    const __half2 c   = vc[e];
+    const __half2 d   = __hsub2(__habs2(c), min1);            // |c| - min1 >= 0 (infinite for a fixed bit)
+    const __half2 ism = __hfma2_relu(d, H(H_N128), one);      // 1 if this edge holds the minimum, else 0
+    const __half2 mag = __hfma2(ism, ds, s1);                 // min2 for the minimum edge, min1 otherwise (scaled)
+    const __half2 sgn = H(lop_xor_and(par_s, U(c), H_SIGN));  // +-1: sign parity of the row without this edge
+    const __half2 x   = __hfma2(sgn, mag, c);
+    // Promotion (LLR.cpp:74-87): |x| > 120 -> +-infinity; an infinite c stays infinite.
+    const __half2 ehi = __hfma2_relu(x, one, hn120);
+    const __half2 elo = __hfma2_relu(x, neg1, hn120);
+    __half2       r   = __hfma2(ehi, H(H_BIG), x);
+    r                 = __hfma2(elo, H(H_NBIG), r);
+    soft[idx[e]]      = U(r);
+    acc_s             = __hfma2(acc_s, H(H_TWO), __hfma2_relu(sgn, neg1, H(H_ZERO)));
+    acc_m             = __hfma2(acc_m, H(H_TWO), ism);
     if ((e & 7) == 7 || e == DEG - 1) {
       // Left-align a partial group, convert to integer bytes and pack {M B, S B, M A, S A}.
       const int fill = 7 - (e & 7);
       if (fill) {
-        hh sc = 0x3C003C00u + (uint32_t)fill * 0x04000400u; // 2^fill
-        acc_s = hfma(acc_s, sc, H_ZERO);
-        acc_m = hfma(acc_m, sc, H_ZERO);
+        const __half2 sc = H(0x3C003C00u + (uint32_t)fill * 0x04000400u); // 2^fill
+        acc_s            = __hmul2(acc_s, sc);
+        acc_m            = __hmul2(acc_m, sc);
       }
-      st_out.w[1 + (e >> 3)] = __byte_perm(hadd(acc_s, H_1024), hadd(acc_m, H_1024), 0x6240);
-      acc_s = 0;
-      acc_m = 0;
+      st_out.w[1 + (e >> 3)] = __byte_perm(U(__hadd2(acc_s, H(H_1024))), U(__hadd2(acc_m, H(H_1024))), 0x6240);
+      acc_s                  = H(H_ZERO);
+      acc_m                  = H(H_ZERO);
     }
   }
-  st_out.w[0] = __byte_perm(hadd(s1, H_1024), hadd(s2, H_1024), 0x6420);
-  if (MASKED) {
-#pragma unroll
-    for (int k = 0; k != 4; ++k) {
-      // Bytes of a frozen half keep their old value: mask bytes {A: 0,2 | B: 1,3} for w[0], halves for the flags.
-      hh bm       = (k == 0) ? (((lane_mask & 0xffffu) ? 0x00ff00ffu : 0u) | ((lane_mask >> 16) ? 0xff00ff00u : 0u))
-                             : lane_mask;
-      st_out.w[k] = lop_sel(st_out.w[k], st.w[k], bm);
-    }
-  }
+  st_out.w[0] = __byte_perm(U(__hadd2(s1, H(H_1024))), U(__hadd2(s2, H(H_1024))), 0x6420);
 }
 
-template <bool MASKED>
-__device__ __forceinline__ void dispatch_row(int deg, hh* soft, const GraphSmem& g, int e0, int j, int Z,
-                                             const RowState& st, RowState& st_out, int scale_mode, hh lane_mask)
+__device__ __forceinline__ void dispatch_row(int deg, hh* soft, const uint16_t* e_shift, const uint16_t* e_base, int j,
+                                             int Z, const RowState& st, RowState& st_out, int scale_mode)
 {
   switch (deg) {
-    case 3: process_row<3, MASKED>(soft, g, e0, j, Z, st, st_out, scale_mode, lane_mask); break;
-    case 4: process_row<4, MASKED>(soft, g, e0, j, Z, st, st_out, scale_mode, lane_mask); break;
-    case 5: process_row<5, MASKED>(soft, g, e0, j, Z, st, st_out, scale_mode, lane_mask); break;
-    case 6: process_row<6, MASKED>(soft, g, e0, j, Z, st, st_out, scale_mode, lane_mask); break;
-    case 7: process_row<7, MASKED>(soft, g, e0, j, Z, st, st_out, scale_mode, lane_mask); break;
-    case 8: process_row<8, MASKED>(soft, g, e0, j, Z, st, st_out, scale_mode, lane_mask); break;
-    case 9: process_row<9, MASKED>(soft, g, e0, j, Z, st, st_out, scale_mode, lane_mask); break;
-    case 10: process_row<10, MASKED>(soft, g, e0, j, Z, st, st_out, scale_mode, lane_mask); break;
-    default: process_row<19, MASKED>(soft, g, e0, j, Z, st, st_out, scale_mode, lane_mask); break;
+    case 3: process_row<3>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 4: process_row<4>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 5: process_row<5>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 6: process_row<6>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 7: process_row<7>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 8: process_row<8>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 9: process_row<9>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 10: process_row<10>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    default: process_row<19>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
   }
 }
 
 // Per-codeblock bookkeeping of the pair.
 struct LaneInfo {
-  int  valid;     // a codeblock is decoded in this half
-  int  cb;        // index in the batch
-  int  layers;
-  int  trimmed;
-  int  F, crc_kind, early, max_iter;
-  int  done;      // early stop reached
-  int  iters, crc_ok;
+  int valid; // a codeblock is decoded in this half during the current pass
+  int cb;    // index in the batch
+  int layers;
+  int F, crc_kind, early, max_iter;
+  int done;  // 1: early stop reached, 2: all-zero input
 };
 
-__host__ __device__ inline size_t h2_smem_bytes(int bg, int Z, bool state_in_smem)
+__host__ __device__ inline size_t h2_smem_bytes(int bg, int Z)
 {
   int    n_full = (bg == 1) ? 68 : 52;
   int    kb     = (bg == 1) ? 22 : 10;
-  int    words  = (bg == 1) ? 103 : 86;
   size_t soft   = (size_t)n_full * Z * 4;
   size_t bits   = 2 * ((size_t)((kb * Z + 31) / 32) * 4 + 16);
-  size_t state  = state_in_smem ? (size_t)words * Z * 4 : 0;
-  return soft + bits + state + sizeof(GraphSmem) + 256;
+  return soft + bits + sizeof(GraphSmem) + 64;
 }
 
 // Hard decision of one half of the soft words + "any zero" flag, MSB-first packed into bits[].
@@ -306,318 +250,320 @@ __device__ __forceinline__ uint32_t crc_partial(const uint32_t* bits, int nb, in
   return acc;
 }
 
-template <int SPACE>
-__global__ void ldpc_decode_h2_kernel(BatchParams prm, hh* state_scratch, uint32_t scratch_stride_words)
+template <int MAX_THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
+    ldpc_decode_h2_kernel(BatchParams prm, hh* state_scratch, uint32_t scratch_stride_words)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ LaneInfo lane[2];
   __shared__ int      sh_last[2];
   __shared__ uint32_t sh_crc[2];
   __shared__ int      sh_any_zero[2];
+  __shared__ int      sh_defer_b; // codeblock B could not be decoded together with A: it gets its own pass
 
   const int tid  = threadIdx.x;
   const int nthr = blockDim.x;
 
   // Persistent CTAs: pair p = codeblocks 2p and 2p+1 of the batch. They are decoded together when they share the lifted
-  // graph and the iteration policy, otherwise one after the other.
+  // graph, the iteration count and the number of rows in use; otherwise one after the other.
   const uint32_t n_pairs = (prm.n_cb + 1) / 2;
-  for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-  for (int pass = 0; pass != 2; ++pass) {
-    const uint32_t cb0 = 2 * pair;
-    __syncthreads();
-    if (tid == 0) {
-      const pdc_cb_desc* d[2];
-      bool               ok[2];
-      for (int h = 0; h != 2; ++h) {
-        uint32_t cb = cb0 + h;
-        ok[h]       = false;
-        d[h]        = nullptr;
-        if (cb < prm.n_cb) {
-          d[h]  = &prm.cbs[cb];
-          ok[h] = (d[h]->flags & PDC_CB_DECODE) != 0;
-          if (ok[h]) {
-            const int bg = d[h]->base_graph, Z = d[h]->lifting_size;
-            if ((bg != 1 && bg != 2) || Z < 2 || Z > MAX_Z || c_tab.set_index[Z] == 0xff || d[h]->max_iter == 0 ||
-                d[h]->harq_id >= prm.harq_entries || d[h]->crc_kind > PDC_CRC24B) {
-              pdc_cb_result r;
-              r.crc_ok = 0, r.iters = d[h]->max_iter, r.status = 2, r.nlayers = 0;
-              prm.results[cb] = r;
-              ok[h]           = false;
-            }
-          }
-        }
-      }
-      bool together = ok[0] && ok[1] && d[0]->base_graph == d[1]->base_graph &&
-                      d[0]->lifting_size == d[1]->lifting_size && d[0]->max_iter == d[1]->max_iter;
-      for (int h = 0; h != 2; ++h) {
-        bool take     = together ? (pass == 0) : (ok[h] && pass == h);
-        lane[h].valid = take;
-        lane[h].cb    = cb0 + h;
-        if (take) {
-          lane[h].F        = d[h]->nof_filler;
-          lane[h].crc_kind = d[h]->crc_kind;
-          lane[h].early    = ((d[h]->flags & PDC_CB_EARLY_STOP) && d[h]->crc_kind != PDC_CRC_NONE) ? 1 : 0;
-          lane[h].max_iter = d[h]->max_iter;
-          lane[h].done     = 0;
-          lane[h].iters    = d[h]->max_iter;
-          lane[h].crc_ok   = 0;
-        }
-        sh_last[h] = 0;
-      }
-    }
-    __syncthreads();
-    if (!lane[0].valid && !lane[1].valid) {
-      continue;
-    }
-    const int          lead = lane[0].valid ? 0 : 1;
-    const pdc_cb_desc& dl   = prm.cbs[lane[lead].cb];
-    const int          bg   = dl.base_graph;
-    const int          Z    = dl.lifting_size;
-    const int          b    = bg - 1;
-    const int          kb   = (bg == 1) ? 22 : 10;
-    const int          n_full  = (bg == 1) ? 68 : 52;
-    const int          rows    = (bg == 1) ? 46 : 42;
-    const int          n_edges = (bg == 1) ? BG1_EDGES_N : BG2_EDGES_N;
-    const int          K       = kb * Z;
-    const int          N       = (n_full - 2) * Z;
-    const int          set     = c_tab.set_index[Z];
-    const int          n_words = (K + 31) / 32;
-
-    // Carve shared memory.
-    size_t off  = 0;
-    hh*    soft = reinterpret_cast<hh*>(smem_raw);
-    off += (size_t)n_full * Z * 4;
-    uint32_t* bits[2];
-    bits[0] = reinterpret_cast<uint32_t*>(smem_raw + off);
-    off += (size_t)n_words * 4 + 16;
-    bits[1] = reinterpret_cast<uint32_t*>(smem_raw + off);
-    off += (size_t)n_words * 4 + 16;
-    GraphSmem& g = *reinterpret_cast<GraphSmem*>(smem_raw + off);
-    off += (sizeof(GraphSmem) + 15) & ~(size_t)15;
-    StateView sv;
-    if (SPACE == STATE_SMEM) {
-      sv.base   = reinterpret_cast<hh*>(smem_raw + off);
-      sv.stride = Z;
-    } else {
-      sv.base   = state_scratch + (size_t)blockIdx.x * scratch_stride_words;
-      sv.stride = (Z + 31) & ~31;
-    }
-
-    for (int i = tid; i < n_edges; i += nthr) {
-      g.shift[i] = (uint16_t)(c_tab.v[b][set][i] % Z);
-      g.col[i]   = c_tab.col[b][i];
-    }
-    if (tid == 0) {
-      int o = 0;
-      for (int m = 0; m <= rows; ++m) {
-        g.row_start[m] = c_tab.row_start[b][m];
-        g.st_off[m]    = (uint16_t)o;
-        if (m < rows) {
-          o += 1 + flag_groups(c_tab.row_start[b][m + 1] - c_tab.row_start[b][m]);
-        }
-      }
-    }
-    // load_soft_bits (ldpc_decoder_impl.cpp:149-184): two punctured nodes at zero, whole nodes clamped to +-64; values
-    // of +-127 (reachable only in an unclamped tail) are infinite. Also the last non-zero input of each codeblock.
-    {
-      const int8_t* in[2];
-      for (int h = 0; h != 2; ++h) {
-        in[h] = lane[h].valid ? prm.harq + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_SOFT : nullptr;
-      }
-      int last[2] = {0, 0};
-      for (int i = tid; i < n_full * Z; i += nthr) {
-        int k = i - 2 * Z;
-        hh  w = 0;
+  for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int pass = 0; pass != 2; ++pass) {
+      const uint32_t cb0 = 2 * pair;
+      __syncthreads();
+      if (tid == 0) {
+        const pdc_cb_desc* d[2];
+        bool               ok[2];
         for (int h = 0; h != 2; ++h) {
-          int v = 0;
-          if (in[h] && k >= 0 && k < N) {
-            v = in[h][k];
-            if (v != 0) {
-              last[h] = k + 1;
-            }
-            v = max(-CLAMP_IN, min(CLAMP_IN, v));
-          }
-          w |= (hh)__half_as_ushort(__int2half_rn(v)) << (16 * h);
-        }
-        soft[i] = w;
-      }
-      for (int h = 0; h != 2; ++h) {
-        int l = last[h];
-        for (int o = 16; o > 0; o >>= 1) {
-          l = max(l, __shfl_xor_sync(0xffffffffu, l, o));
-        }
-        if ((tid & 31) == 0 && l > 0) {
-          atomicMax(&sh_last[h], l);
-        }
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      for (int h = 0; h != 2; ++h) {
-        if (!lane[h].valid) {
-          lane[h].layers = 0;
-          continue;
-        }
-        lane[h].trimmed = sh_last[h];
-        if (sh_last[h] == 0) {
-          // All-zero input: not decodable (ldpc_decoder_impl.cpp:88-94).
-          pdc_cb_result r;
-          r.crc_ok = 0, r.iters = (uint8_t)lane[h].max_iter, r.status = 1, r.nlayers = 0;
-          prm.results[lane[h].cb] = r;
-          lane[h].valid           = 0;
-          lane[h].layers          = 0;
-          lane[h].done            = 2; // handled
-          continue;
-        }
-        int cb_len     = max(sh_last[h] + 2 * Z, K + 4 * Z);
-        cb_len         = ((cb_len + Z - 1) / Z) * Z;
-        lane[h].layers = cb_len / Z - kb;
-      }
-    }
-    __syncthreads();
-    // All-zero codeblocks without a CRC calculator output all ones.
-    for (int h = 0; h != 2; ++h) {
-      if (lane[h].done == 2 && lane[h].crc_kind == PDC_CRC_NONE) {
-        uint8_t* out = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
-        for (int i = tid; i < (K + 7) / 8; i += nthr) {
-          int rem = K - 8 * i;
-          out[i]  = (rem >= 8) ? 0xff : (uint8_t)(0xff << (8 - rem));
-        }
-      }
-    }
-    if (!lane[0].valid && !lane[1].valid) {
-      continue;
-    }
-    const int layers_a   = lane[0].layers, layers_b = lane[1].layers;
-    const int layers_max = max(layers_a, layers_b);
-    const int layers_min = (lane[0].valid && lane[1].valid) ? min(layers_a, layers_b) : layers_max;
-    const int max_iter   = lane[lead].max_iter;
-    const int scale_mode = prm.scale_mode;
-    const int j          = tid;
-    const bool active    = j < Z;
-
-    // Compressed messages of the next row are fetched while the current row is processed (they are private to thread j:
-    // word k of row m of check j is only ever touched by thread j).
-    RowState st_next;
-#pragma unroll
-    for (int k = 0; k != 4; ++k) {
-      st_next.w[k] = 0;
-    }
-    for (int it = 0; it < max_iter; ++it) {
-      for (int m = 0; m < layers_max; ++m) {
-        if (active) {
-          const int e0  = g.row_start[m];
-          const int deg = g.row_start[m + 1] - e0;
-          const int ng  = flag_groups(deg);
-          hh*       sp  = sv.base + (size_t)g.st_off[m] * sv.stride + j;
-          RowState  st  = st_next, st_out;
-#pragma unroll
-          for (int k = 0; k != 4; ++k) {
-            st_out.w[k] = 0;
-          }
-          // Prefetch: next row of this iteration, or row 0 of the next iteration.
-          {
-            const int  mn   = (m + 1 < layers_max) ? m + 1 : 0;
-            const bool have = (m + 1 < layers_max) ? (it != 0) : (it + 1 < max_iter);
-            const int  ngn  = flag_groups(g.row_start[mn + 1] - g.row_start[mn]);
-            const hh*  spn  = sv.base + (size_t)g.st_off[mn] * sv.stride + j;
-#pragma unroll
-            for (int k = 0; k != 4; ++k) {
-              st_next.w[k] = (have && k <= ngn && mn != m) ? spn[(size_t)k * sv.stride] : 0u;
-            }
-          }
-          if (m < layers_min) {
-            dispatch_row<false>(deg, soft, g, e0, j, Z, st, st_out, scale_mode, 0xffffffffu);
-          } else {
-            hh lm = ((m < layers_a) ? 0x0000ffffu : 0u) | ((m < layers_b) ? 0xffff0000u : 0u);
-            dispatch_row<true>(deg, soft, g, e0, j, Z, st, st_out, scale_mode, lm);
-          }
-#pragma unroll
-          for (int k = 0; k != 4; ++k) {
-            if (k <= ng) {
-              sp[(size_t)k * sv.stride] = st_out.w[k];
-            }
-          }
-        }
-        __syncthreads();
-      }
-
-      const bool last_it = (it + 1 == max_iter);
-      bool       any_early = (lane[0].valid && lane[0].early && !lane[0].done) ||
-                       (lane[1].valid && lane[1].early && !lane[1].done);
-      if (any_early || last_it) {
-        if (tid < 2) {
-          sh_crc[tid]      = 0;
-          sh_any_zero[tid] = 0;
-        }
-        __syncthreads();
-        for (int h = 0; h != 2; ++h) {
-          if (!lane[h].valid || lane[h].done) {
-            continue;
-          }
-          if (!(lane[h].early || last_it)) {
-            continue;
-          }
-          int az = hard_bits(soft, h, K, bits[h], tid, nthr);
-          if (az) {
-            sh_any_zero[h] = 1;
-          }
-        }
-        __syncthreads();
-        for (int h = 0; h != 2; ++h) {
-          if (!lane[h].valid || lane[h].done || !(lane[h].early || last_it) || lane[h].crc_kind == PDC_CRC_NONE) {
-            continue;
-          }
-          uint32_t acc = crc_partial(bits[h], K - lane[h].F, lane[h].crc_kind, tid, nthr);
-          if ((tid & 31) == 0 && acc) {
-            atomicXor(&sh_crc[h], acc);
-          }
-        }
-        __syncthreads();
-        // Publish finished codeblocks (bits are written while they are still in shared memory).
-        for (int h = 0; h != 2; ++h) {
-          if (!lane[h].valid || lane[h].done || !(lane[h].early || last_it)) {
-            continue;
-          }
-          bool pass_crc = (lane[h].crc_kind != PDC_CRC_NONE) && (sh_crc[h] == 0);
-          bool stop     = lane[h].early ? (pass_crc && !sh_any_zero[h]) : false;
-          if (stop || last_it) {
-            uint8_t* out   = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
-            uint8_t* out_h = prm.harq_data + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_BYTES;
-            const int nbytes = (K + 7) / 8;
-            for (int w = tid; w < n_words; w += nthr) {
-              uint32_t v = bits[h][w];
-#pragma unroll
-              for (int k = 0; k != 4; ++k) {
-                if (4 * w + k < nbytes) {
-                  out[4 * w + k]   = (uint8_t)(v >> (24 - 8 * k));
-                  out_h[4 * w + k] = (uint8_t)(v >> (24 - 8 * k));
+          uint32_t cb = cb0 + h;
+          ok[h]       = false;
+          d[h]        = nullptr;
+          if (cb < prm.n_cb) {
+            d[h]  = &prm.cbs[cb];
+            ok[h] = (d[h]->flags & PDC_CB_DECODE) != 0;
+            if (ok[h]) {
+              const int bg = d[h]->base_graph, Z = d[h]->lifting_size;
+              if ((bg != 1 && bg != 2) || Z < 2 || Z > MAX_Z || c_tab.set_index[Z] == 0xff || d[h]->max_iter == 0 ||
+                  d[h]->harq_id >= prm.harq_entries || d[h]->crc_kind > PDC_CRC24B) {
+                if (pass == 0) {
+                  pdc_cb_result r;
+                  r.crc_ok = 0, r.iters = d[h]->max_iter, r.status = 2, r.nlayers = 0;
+                  prm.results[cb] = r;
                 }
+                ok[h] = false;
               }
             }
-            if (tid == 0) {
-              pdc_cb_result r;
-              r.crc_ok  = lane[h].early ? (stop ? 1 : 0) : (pass_crc ? 1 : 0);
-              r.iters   = (uint8_t)(stop ? it + 1 : lane[h].max_iter);
-              r.status  = 0;
-              r.nlayers = (uint8_t)lane[h].layers;
-              prm.results[lane[h].cb] = r;
-            }
           }
         }
-        __syncthreads();
-        if (tid == 0) {
+        bool compatible = ok[0] && ok[1] && d[0]->base_graph == d[1]->base_graph &&
+                          d[0]->lifting_size == d[1]->lifting_size && d[0]->max_iter == d[1]->max_iter;
+        if (pass == 0) {
+          sh_defer_b = (ok[1] && !compatible) ? 1 : 0;
+        }
+        for (int h = 0; h != 2; ++h) {
+          bool take = (pass == 0) ? (h == 0 ? ok[0] : (ok[1] && compatible)) : (h == 1 && ok[1] && sh_defer_b);
+          lane[h].valid  = take;
+          lane[h].cb     = cb0 + h;
+          lane[h].layers = 0;
+          lane[h].done   = 0;
+          if (take) {
+            lane[h].F        = d[h]->nof_filler;
+            lane[h].crc_kind = d[h]->crc_kind;
+            lane[h].early    = ((d[h]->flags & PDC_CB_EARLY_STOP) && d[h]->crc_kind != PDC_CRC_NONE) ? 1 : 0;
+            lane[h].max_iter = d[h]->max_iter;
+          }
+          sh_last[h] = 0;
+        }
+      }
+      __syncthreads();
+      if (!lane[0].valid && !lane[1].valid) {
+        continue;
+      }
+      const int          lead    = lane[0].valid ? 0 : 1;
+      const pdc_cb_desc& dl      = prm.cbs[lane[lead].cb];
+      const int          bg      = dl.base_graph;
+      const int          Z       = dl.lifting_size;
+      const int          b       = bg - 1;
+      const int          kb      = (bg == 1) ? 22 : 10;
+      const int          n_full  = (bg == 1) ? 68 : 52;
+      const int          rows    = (bg == 1) ? 46 : 42;
+      const int          n_edges = (bg == 1) ? BG1_EDGES_N : BG2_EDGES_N;
+      const int          K       = kb * Z;
+      const int          N       = (n_full - 2) * Z;
+      const int          set     = c_tab.set_index[Z];
+      const int          n_words = (K + 31) / 32;
+
+      // Carve shared memory.
+      size_t off  = 0;
+      hh*    soft = reinterpret_cast<hh*>(smem_raw);
+      off += (size_t)n_full * Z * 4;
+      uint32_t* bits[2];
+      bits[0] = reinterpret_cast<uint32_t*>(smem_raw + off);
+      off += (size_t)n_words * 4 + 16;
+      bits[1] = reinterpret_cast<uint32_t*>(smem_raw + off);
+      off += (size_t)n_words * 4 + 16;
+      GraphSmem& g = *reinterpret_cast<GraphSmem*>(smem_raw + off);
+
+      hh*            st_base   = state_scratch + (size_t)blockIdx.x * scratch_stride_words;
+      const uint32_t st_stride = (uint32_t)((Z + 31) & ~31);
+
+      for (int i = tid; i < n_edges; i += nthr) {
+        g.shift[i] = (uint16_t)(c_tab.v[b][set][i] % Z); // ldpc_luts_impl.cpp:4536-4541
+        g.base[i]  = (uint16_t)(c_tab.col[b][i] * Z);
+      }
+      if (tid == 0) {
+        int o = 0;
+        for (int m = 0; m <= rows; ++m) {
+          g.row_start[m] = c_tab.row_start[b][m];
+          g.st_off[m]    = (uint16_t)o;
+          if (m < rows) {
+            o += 1 + flag_groups(c_tab.row_start[b][m + 1] - c_tab.row_start[b][m]);
+          }
+        }
+      }
+      // load_soft_bits (ldpc_decoder_impl.cpp:149-184): two punctured nodes at zero, whole nodes clamped to +-64.
+      // Also finds the last non-zero input of each codeblock (:86-99).
+      {
+        const int8_t* in[2];
+        for (int h = 0; h != 2; ++h) {
+          in[h] = lane[h].valid ? prm.harq + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_SOFT : nullptr;
+        }
+        int last[2] = {0, 0};
+        for (int i = tid; i < n_full * Z; i += nthr) {
+          int k = i - 2 * Z;
+          hh  w = 0;
+#pragma unroll
           for (int h = 0; h != 2; ++h) {
-            if (lane[h].valid && !lane[h].done && lane[h].early && lane[h].crc_kind != PDC_CRC_NONE &&
-                sh_crc[h] == 0 && !sh_any_zero[h]) {
-              lane[h].done = 1;
+            int v = 0;
+            if (in[h] && k >= 0 && k < N) {
+              v = in[h][k];
+              if (v != 0) {
+                last[h] = k + 1;
+              }
+              v = max(-CLAMP_IN, min(CLAMP_IN, v));
             }
+            w |= (hh)__half_as_ushort(__int2half_rn(v)) << (16 * h);
+          }
+          soft[i] = w;
+        }
+#pragma unroll
+        for (int h = 0; h != 2; ++h) {
+          int l = last[h];
+          for (int o = 16; o > 0; o >>= 1) {
+            l = max(l, __shfl_xor_sync(0xffffffffu, l, o));
+          }
+          if ((tid & 31) == 0 && l > 0) {
+            atomicMax(&sh_last[h], l);
           }
         }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int h = 0; h != 2; ++h) {
+          if (!lane[h].valid) {
+            continue;
+          }
+          if (sh_last[h] == 0) {
+            // All-zero input: not decodable (ldpc_decoder_impl.cpp:88-94).
+            pdc_cb_result r;
+            r.crc_ok = 0, r.iters = (uint8_t)lane[h].max_iter, r.status = 1, r.nlayers = 0;
+            prm.results[lane[h].cb] = r;
+            lane[h].valid           = 0;
+            lane[h].done            = 2;
+            continue;
+          }
+          int cb_len     = max(sh_last[h] + 2 * Z, K + 4 * Z);
+          cb_len         = ((cb_len + Z - 1) / Z) * Z;
+          lane[h].layers = cb_len / Z - kb;
+        }
+        // Different numbers of rows in use: B is decoded alone in the second pass.
+        if (lane[0].valid && lane[1].valid && lane[0].layers != lane[1].layers) {
+          lane[1].valid = 0;
+          sh_defer_b    = 2;
+        }
+      }
+      __syncthreads();
+      // All-zero codeblocks without a CRC calculator output all ones.
+      for (int h = 0; h != 2; ++h) {
+        if (lane[h].done == 2 && lane[h].crc_kind == PDC_CRC_NONE) {
+          uint8_t* out = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
+          for (int i = tid; i < (K + 7) / 8; i += nthr) {
+            int rem = K - 8 * i;
+            out[i]  = (rem >= 8) ? 0xff : (uint8_t)(0xff << (8 - rem));
+          }
+        }
+      }
+      if (!lane[0].valid && !lane[1].valid) {
+        continue;
+      }
+      if (pass == 0 && sh_defer_b == 2) {
+        // B's half holds its inputs but B is not decoded in this pass: clear it so that A computes next to zeros.
+        for (int i = tid; i < n_full * Z; i += nthr) {
+          soft[i] &= 0x0000ffffu;
+        }
         __syncthreads();
-        bool all_done = (!lane[0].valid || lane[0].done) && (!lane[1].valid || lane[1].done);
-        if (all_done) {
-          break;
+      }
+      const int  layers     = lane[lane[0].valid ? 0 : 1].layers;
+      const int  max_iter   = lane[lead].max_iter;
+      const int  scale_mode = prm.scale_mode;
+      const int  j          = tid;
+      const bool active     = j < Z;
+
+      // Compressed messages of the next row are fetched while the current row is processed (they are private to
+      // thread j: word k of row m of check j is only ever touched by thread j).
+      RowState st_next;
+#pragma unroll
+      for (int k = 0; k != 4; ++k) {
+        st_next.w[k] = 0;
+      }
+      for (int it = 0; it < max_iter; ++it) {
+        for (int m = 0; m < layers; ++m) {
+          if (active) {
+            const int e0  = g.row_start[m];
+            const int deg = g.row_start[m + 1] - e0;
+            const int ng  = flag_groups(deg);
+            hh*       sp  = st_base + (uint32_t)g.st_off[m] * st_stride + j;
+            RowState  st  = st_next, st_out;
+#pragma unroll
+            for (int k = 0; k != 4; ++k) {
+              st_out.w[k] = 0;
+            }
+            {
+              // Prefetch: next row of this iteration, or row 0 of the next iteration.
+              const int  mn   = (m + 1 < layers) ? m + 1 : 0;
+              const bool have = (m + 1 < layers) ? (it != 0) : (it + 1 < max_iter);
+              const int  ngn  = flag_groups(g.row_start[mn + 1] - g.row_start[mn]);
+              const hh*  spn  = st_base + (uint32_t)g.st_off[mn] * st_stride + j;
+#pragma unroll
+              for (int k = 0; k != 4; ++k) {
+                st_next.w[k] = (have && k <= ngn) ? spn[k * st_stride] : 0u;
+              }
+            }
+            dispatch_row(deg, soft, g.shift + e0, g.base + e0, j, Z, st, st_out, scale_mode);
+#pragma unroll
+            for (int k = 0; k != 4; ++k) {
+              if (k <= ng) {
+                sp[k * st_stride] = st_out.w[k];
+              }
+            }
+          }
+          __syncthreads();
+        }
+
+        const bool last_it   = (it + 1 == max_iter);
+        const bool any_early = (lane[0].valid && lane[0].early && !lane[0].done) ||
+                               (lane[1].valid && lane[1].early && !lane[1].done);
+        if (any_early || last_it) {
+          if (tid < 2) {
+            sh_crc[tid]      = 0;
+            sh_any_zero[tid] = 0;
+          }
+          __syncthreads();
+          for (int h = 0; h != 2; ++h) {
+            if (!lane[h].valid || lane[h].done || !(lane[h].early || last_it)) {
+              continue;
+            }
+            // get_hard_bits (:126-134): bit = soft <= 0, MSB first; a zero among the K message soft bits blocks the
+            // early stop.
+            if (hard_bits(soft, h, K, bits[h], tid, nthr)) {
+              sh_any_zero[h] = 1;
+            }
+          }
+          __syncthreads();
+          for (int h = 0; h != 2; ++h) {
+            if (!lane[h].valid || lane[h].done || !(lane[h].early || last_it) || lane[h].crc_kind == PDC_CRC_NONE) {
+              continue;
+            }
+            uint32_t acc = crc_partial(bits[h], K - lane[h].F, lane[h].crc_kind, tid, nthr);
+            if ((tid & 31) == 0 && acc) {
+              atomicXor(&sh_crc[h], acc);
+            }
+          }
+          __syncthreads();
+          // Publish finished codeblocks while their bits are in shared memory.
+          for (int h = 0; h != 2; ++h) {
+            if (!lane[h].valid || lane[h].done || !(lane[h].early || last_it)) {
+              continue;
+            }
+            const bool pass_crc = (lane[h].crc_kind != PDC_CRC_NONE) && (sh_crc[h] == 0);
+            const bool stop     = lane[h].early && pass_crc && !sh_any_zero[h];
+            if (stop || last_it) {
+              uint8_t*  out    = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
+              uint8_t*  out_h  = prm.harq_data + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_BYTES;
+              const int nbytes = (K + 7) / 8;
+              for (int w = tid; w < n_words; w += nthr) {
+                uint32_t v = bits[h][w];
+#pragma unroll
+                for (int k = 0; k != 4; ++k) {
+                  if (4 * w + k < nbytes) {
+                    out[4 * w + k]   = (uint8_t)(v >> (24 - 8 * k));
+                    out_h[4 * w + k] = (uint8_t)(v >> (24 - 8 * k));
+                  }
+                }
+              }
+              if (tid == 0) {
+                pdc_cb_result r;
+                r.crc_ok  = lane[h].early ? (stop ? 1 : 0) : (pass_crc ? 1 : 0);
+                r.iters   = (uint8_t)(stop ? it + 1 : lane[h].max_iter);
+                r.status  = 0;
+                r.nlayers = (uint8_t)lane[h].layers;
+                prm.results[lane[h].cb] = r;
+              }
+            }
+          }
+          __syncthreads();
+          if (tid == 0) {
+            for (int h = 0; h != 2; ++h) {
+              if (lane[h].valid && !lane[h].done && lane[h].early && sh_crc[h] == 0 && !sh_any_zero[h]) {
+                lane[h].done = 1;
+              }
+            }
+          }
+          __syncthreads();
+          const bool all_done = (!lane[0].valid || lane[0].done) && (!lane[1].valid || lane[1].done);
+          if (all_done) {
+            break;
+          }
         }
       }
     }
@@ -625,9 +571,6 @@ __global__ void ldpc_decode_h2_kernel(BatchParams prm, hh* state_scratch, uint32
 }
 
 } // namespace h2
-} // namespace pdc
-
-namespace pdc {
 
 // Launch plan of the throughput kernel for a batch whose largest lifting size is max_Z.
 struct H2Plan {
@@ -635,27 +578,31 @@ struct H2Plan {
   int    grid;
   size_t smem;
   size_t scratch_words_per_cta;
+  bool   big; // the 384-thread instantiation (two CTAs per SM)
 };
+
+typedef void (*h2_kernel_t)(BatchParams, uint32_t*, uint32_t);
 
 inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count, H2Plan& plan)
 {
-  const int bg     = any_bg1 ? 1 : 2;
-  plan.threads     = ((max_Z + 31) / 32) * 32;
-  plan.smem        = h2::h2_smem_bytes(bg, max_Z, false);
-  const int words  = (bg == 1) ? 103 : 86;
+  const int bg               = any_bg1 ? 1 : 2;
+  plan.threads               = ((max_Z + 31) / 32) * 32;
+  plan.smem                  = h2::h2_smem_bytes(bg, max_Z);
+  const int words            = (bg == 1) ? 103 : 86;
   plan.scratch_words_per_cta = (size_t)words * ((max_Z + 31) & ~31);
-  static size_t configured = 0;
-  if (plan.smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(h2::ldpc_decode_h2_kernel<h2::STATE_GLOBAL>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+  plan.big                   = plan.threads > 192;
+  h2_kernel_t   k            = plan.big ? (h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2>
+                                        : (h2_kernel_t)h2::ldpc_decode_h2_kernel<192, 4>;
+  static size_t configured[2] = {0, 0};
+  if (plan.smem > configured[plan.big]) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) {
       return e;
     }
-    configured = plan.smem;
+    configured[plan.big] = plan.smem;
   }
   int         per_sm = 0;
-  cudaError_t e      = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &per_sm, h2::ldpc_decode_h2_kernel<h2::STATE_GLOBAL>, plan.threads, plan.smem);
+  cudaError_t e      = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, plan.threads, plan.smem);
   if (e != cudaSuccess) {
     return e;
   }
@@ -669,8 +616,13 @@ inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count,
 
 inline cudaError_t launch_ldpc_decode_h2(const BatchParams& p, const H2Plan& plan, uint32_t* scratch, cudaStream_t s)
 {
-  h2::ldpc_decode_h2_kernel<h2::STATE_GLOBAL>
-      <<<plan.grid, plan.threads, plan.smem, s>>>(p, scratch, (uint32_t)plan.scratch_words_per_cta);
+  if (plan.big) {
+    h2::ldpc_decode_h2_kernel<384, 2>
+        <<<plan.grid, plan.threads, plan.smem, s>>>(p, scratch, (uint32_t)plan.scratch_words_per_cta);
+  } else {
+    h2::ldpc_decode_h2_kernel<192, 4>
+        <<<plan.grid, plan.threads, plan.smem, s>>>(p, scratch, (uint32_t)plan.scratch_words_per_cta);
+  }
   return cudaGetLastError();
 }
 
