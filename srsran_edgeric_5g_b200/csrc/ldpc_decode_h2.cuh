@@ -64,40 +64,55 @@ constexpr hh H_SIGN  = 0x80008000u;
 constexpr hh H_0P8   = 0x3A663A66u; // 0.7998046875
 constexpr hh H_N0P6  = 0xB8CDB8CDu; // -0.60009765625
 
-struct RowState {
-  hh w[4]; // w[0]: scaled minima as bytes {m1 A, m1 B, m2 A, m2 B}; w[1..3]: flag groups of 8 edges {M B, S B, M A, S A}
-};
+// Compressed check-to-variable messages of one (row, check), both codeblocks: one 128-bit word.
+//   rows of degree <= 16: {scaled min1 (half2), scaled min2 (half2), flags of edges 0-7, flags of edges 8-15}
+//   rows of degree 19   : {scaled minima as bytes {m1 A, m1 B, m2 A, m2 B}, flags 0-7, flags 8-15, flags 16-18}
+// A flag word holds, per codeblock half, {"held the minimum" : 8 | "negative" : 8}, first edge of the group in the MSB.
+typedef uint4 RowState;
 
-__device__ __forceinline__ int flag_groups(int deg)
+__device__ __forceinline__ hh& st_word(RowState& s, int k)
 {
-  return (deg + 7) >> 3;
+  return (k == 0) ? s.x : (k == 1) ? s.y : (k == 2) ? s.z : s.w;
+}
+__device__ __forceinline__ hh st_word(const RowState& s, int k)
+{
+  return (k == 0) ? s.x : (k == 1) ? s.y : (k == 2) ? s.z : s.w;
 }
 
 // The lifted graph of this (base graph, Z) in shared memory.
 struct GraphSmem {
-  uint16_t shift[MAX_EDGES];      // circulant shift of the edge
-  uint16_t base[MAX_EDGES];       // col * Z: first soft word of the edge's variable node
-  uint16_t row_start[MAX_ROWS + 2];
-  uint16_t st_off[MAX_ROWS + 2];  // state word offset of each row
+  uint16_t shift[MAX_EDGES];     // circulant shift of the edge
+  uint16_t base[MAX_EDGES];      // col * Z: first soft word of the edge's variable node
+  uint32_t row_info[MAX_ROWS];   // first edge | degree << 16
 };
 
+
 // One base-graph row (layer) of degree DEG for check j of both codeblocks.
-//   soft     : variable-node soft bits, soft[col * Z + pos], fp16x2
+//   soft     : shared-memory soft words, soft[col * Z + pos] as fp16x2 (addressed by byte offset)
 //   st/st_out: compressed messages of this row from the previous iteration / for the next one
 template <int DEG>
-__device__ __forceinline__ void process_row(hh* __restrict__ soft, const uint16_t* __restrict__ e_shift,
+__device__ __forceinline__ void process_row(unsigned char* soft, const uint16_t* __restrict__ e_shift,
                                             const uint16_t* __restrict__ e_base, int j, int Z, const RowState& st,
                                             RowState& st_out, int scale_mode)
 {
+  constexpr bool PACKED_MIN = DEG > 16;
+  constexpr int  F0         = PACKED_MIN ? 1 : 2; // index of the first flag word
+
   __half2  vc[DEG]; // soft - c2v_old clamped to +-120, infinite if the soft bit was infinite
-  uint32_t idx[DEG];
+  uint32_t addr[DEG];
 
   const __half2 one = H(H_ONE), neg1 = H(H_NEG1), h120 = H(H_120), hn120 = H(H_N120), hn230 = H(H_N230);
 
-  // Old scaled minima: bytes -> halves. -mag_old = z * hd - mid with z = -1 for the edge that held the minimum (its
-  // message was min2), +1 otherwise (min1).
-  const __half2 m1  = __hadd2(H(__byte_perm(st.w[0], 0x64646464u, 0x4140)), H(H_N1024));
-  const __half2 m2  = __hadd2(H(__byte_perm(st.w[0], 0x64646464u, 0x4342)), H(H_N1024));
+  // Old scaled minima. -mag_old = z * hd - mid with z = -1 for the edge that held the minimum (its message was min2),
+  // +1 otherwise (min1).
+  __half2 m1, m2;
+  if (PACKED_MIN) {
+    m1 = __hadd2(H(__byte_perm(st.x, 0x64646464u, 0x4140)), H(H_N1024));
+    m2 = __hadd2(H(__byte_perm(st.x, 0x64646464u, 0x4342)), H(H_N1024));
+  } else {
+    m1 = H(st.x);
+    m2 = H(st.y);
+  }
   const __half2 mid = __hmul2(__hadd2(m1, m2), H(H_HALF));
   const __half2 hd  = __hmul2(__hsub2(m2, m1), H(H_HALF));
 
@@ -106,23 +121,22 @@ __device__ __forceinline__ void process_row(hh* __restrict__ soft, const uint16_
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
     if ((e & 7) == 0) {
-      hh f = st.w[1 + (e >> 3)];
-      pm   = f;      // "held the minimum" flags: bit 15 of each half = edge e, then e+1, ... after each doubling
+      hh f = st_word(st, F0 + (e >> 3));
+      pm   = f;      // "held the minimum" flags: bit 15 of each half = edge e, then e+1, ... after each shift
       ps   = f << 8; // sign flags
     }
     uint32_t pos = (uint32_t)j + e_shift[e];
     pos          = min(pos, pos - (uint32_t)Z); // wrap: pos - Z underflows to a huge value when pos < Z
-    idx[e]       = e_base[e] + pos;
-    const __half2 s    = H(soft[idx[e]]);
+    addr[e]      = (e_base[e] + pos) * 4u;
+    const __half2 s    = H(*reinterpret_cast<const hh*>(soft + addr[e]));
     const __half2 z    = H(lop_and_or(pm, H_SIGN, H_ONE));
     const __half2 sg   = H(lop_and_or(ps, H_SIGN, H_ONE));
     const __half2 nmag = __hfma2(z, hd, __hneg2(mid));
     const __half2 v    = __hfma2(sg, nmag, s); // s - c2v_old; |v| <= 222, or infinite with s
-    // Clamp to +-120 but keep infinity: relu(|v| - 230) is 0 for every finite v.
+    // Clamp to +-120 but keep infinity: relu(|v| - 230) is 0 for every finite v and infinite otherwise.
+    const __half2 inf = __hfma2_relu(__habs2(v), one, hn230);
     __half2       c   = __hmax2(__hmin2(v, h120), hn120);
-    const __half2 ehi = __hfma2_relu(v, one, hn230);
-    const __half2 elo = __hfma2_relu(v, neg1, hn230);
-    c                 = __hadd2(c, __hsub2(ehi, elo));
+    c                 = __hfma2(c, inf, c);
     vc[e]             = c;
     par ^= U(c);
     const __half2 a = __habs2(c);
@@ -149,19 +163,16 @@ __device__ __forceinline__ void process_row(hh* __restrict__ soft, const uint16_
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
     const __half2 c   = vc[e];
-    const __half2 d   = __hsub2(__habs2(c), min1);            // |c| - min1 >= 0 (infinite for a fixed bit)
-    const __half2 ism = __hfma2_relu(d, H(H_N128), one);      // 1 if this edge holds the minimum, else 0
+    const __half2 ism = __heq2(__habs2(c), min1);             // 1.0 if this edge holds the minimum, else 0.0
     const __half2 mag = __hfma2(ism, ds, s1);                 // min2 for the minimum edge, min1 otherwise (scaled)
     const __half2 sgn = H(lop_xor_and(par_s, U(c), H_SIGN));  // +-1: sign parity of the row without this edge
     const __half2 x   = __hfma2(sgn, mag, c);
-    // Promotion (LLR.cpp:74-87): |x| > 120 -> +-infinity; an infinite c stays infinite.
-    const __half2 ehi = __hfma2_relu(x, one, hn120);
-    const __half2 elo = __hfma2_relu(x, neg1, hn120);
-    __half2       r   = __hfma2(ehi, H(H_BIG), x);
-    r                 = __hfma2(elo, H(H_NBIG), r);
-    soft[idx[e]]      = U(r);
-    acc_s             = __hfma2(acc_s, H(H_TWO), __hfma2_relu(sgn, neg1, H(H_ZERO)));
-    acc_m             = __hfma2(acc_m, H(H_TWO), ism);
+    // Promotion (LLR.cpp:74-87): |x| > 120 -> +-infinity (excess * x * 65504 overflows); infinite stays infinite.
+    const __half2 ex = __hmul2(__hfma2_relu(__habs2(x), one, hn120), x);
+    const __half2 r  = __hfma2(ex, H(H_BIG), x);
+    *reinterpret_cast<hh*>(soft + addr[e]) = U(r);
+    acc_s = __hfma2(acc_s, H(H_TWO), __hfma2_relu(sgn, neg1, H(H_ZERO)));
+    acc_m = __hfma2(acc_m, H(H_TWO), ism);
     if ((e & 7) == 7 || e == DEG - 1) {
       // Left-align a partial group, convert to integer bytes and pack {M B, S B, M A, S A}.
       const int fill = 7 - (e & 7);
@@ -170,27 +181,34 @@ __device__ __forceinline__ void process_row(hh* __restrict__ soft, const uint16_
         acc_s            = __hmul2(acc_s, sc);
         acc_m            = __hmul2(acc_m, sc);
       }
-      st_out.w[1 + (e >> 3)] = __byte_perm(U(__hadd2(acc_s, H(H_1024))), U(__hadd2(acc_m, H(H_1024))), 0x6240);
-      acc_s                  = H(H_ZERO);
-      acc_m                  = H(H_ZERO);
+      st_word(st_out, F0 + (e >> 3)) =
+          __byte_perm(U(__hadd2(acc_s, H(H_1024))), U(__hadd2(acc_m, H(H_1024))), 0x6240);
+      acc_s = H(H_ZERO);
+      acc_m = H(H_ZERO);
     }
   }
-  st_out.w[0] = __byte_perm(U(__hadd2(s1, H(H_1024))), U(__hadd2(s2, H(H_1024))), 0x6420);
+  if (PACKED_MIN) {
+    st_out.x = __byte_perm(U(__hadd2(s1, H(H_1024))), U(__hadd2(s2, H(H_1024))), 0x6420);
+  } else {
+    st_out.x = U(s1);
+    st_out.y = U(s2);
+  }
 }
 
-__device__ __forceinline__ void dispatch_row(int deg, hh* soft, const uint16_t* e_shift, const uint16_t* e_base, int j,
-                                             int Z, const RowState& st, RowState& st_out, int scale_mode)
+__device__ __forceinline__ void dispatch_row(int deg, unsigned char* soft_addr, const uint16_t* e_shift,
+                                             const uint16_t* e_base, int j, int Z, const RowState& st, RowState& st_out,
+                                             int scale_mode)
 {
   switch (deg) {
-    case 3: process_row<3>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 4: process_row<4>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 5: process_row<5>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 6: process_row<6>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 7: process_row<7>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 8: process_row<8>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 9: process_row<9>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 10: process_row<10>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    default: process_row<19>(soft, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 3: process_row<3>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 4: process_row<4>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 5: process_row<5>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 6: process_row<6>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 7: process_row<7>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 8: process_row<8>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 9: process_row<9>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    case 10: process_row<10>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+    default: process_row<19>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
   }
 }
 
@@ -344,22 +362,18 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       off += (size_t)n_words * 4 + 16;
       GraphSmem& g = *reinterpret_cast<GraphSmem*>(smem_raw + off);
 
-      hh*            st_base   = state_scratch + (size_t)blockIdx.x * scratch_stride_words;
+      // Compressed messages: one uint4 per (row, check), private to thread j.
+      uint4*         st_base   = reinterpret_cast<uint4*>(state_scratch + (size_t)blockIdx.x * scratch_stride_words);
       const uint32_t st_stride = (uint32_t)((Z + 31) & ~31);
+      unsigned char* soft_addr = smem_raw;
 
       for (int i = tid; i < n_edges; i += nthr) {
         g.shift[i] = (uint16_t)(c_tab.v[b][set][i] % Z); // ldpc_luts_impl.cpp:4536-4541
         g.base[i]  = (uint16_t)(c_tab.col[b][i] * Z);
       }
-      if (tid == 0) {
-        int o = 0;
-        for (int m = 0; m <= rows; ++m) {
-          g.row_start[m] = c_tab.row_start[b][m];
-          g.st_off[m]    = (uint16_t)o;
-          if (m < rows) {
-            o += 1 + flag_groups(c_tab.row_start[b][m + 1] - c_tab.row_start[b][m]);
-          }
-        }
+      for (int m = tid; m < rows; m += nthr) {
+        g.row_info[m] = (uint32_t)c_tab.row_start[b][m] |
+                        ((uint32_t)(c_tab.row_start[b][m + 1] - c_tab.row_start[b][m]) << 16);
       }
       // load_soft_bits (ldpc_decoder_impl.cpp:149-184): two punctured nodes at zero, whole nodes clamped to +-64.
       // Also finds the last non-zero input of each codeblock (:86-99).
@@ -450,42 +464,25 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       const bool active     = j < Z;
 
       // Compressed messages of the next row are fetched while the current row is processed (they are private to
-      // thread j: word k of row m of check j is only ever touched by thread j).
-      RowState st_next;
-#pragma unroll
-      for (int k = 0; k != 4; ++k) {
-        st_next.w[k] = 0;
-      }
+      // thread j: the uint4 of row m of check j is only ever touched by thread j).
+      RowState st_next = make_uint4(0, 0, 0, 0);
       for (int it = 0; it < max_iter; ++it) {
         for (int m = 0; m < layers; ++m) {
           if (active) {
-            const int e0  = g.row_start[m];
-            const int deg = g.row_start[m + 1] - e0;
-            const int ng  = flag_groups(deg);
-            hh*       sp  = st_base + (uint32_t)g.st_off[m] * st_stride + j;
-            RowState  st  = st_next, st_out;
-#pragma unroll
-            for (int k = 0; k != 4; ++k) {
-              st_out.w[k] = 0;
+            const uint32_t info = g.row_info[m];
+            const int      e0   = info & 0xffffu;
+            const int      deg  = info >> 16;
+            const RowState st   = st_next;
+            RowState       st_out = make_uint4(0, 0, 0, 0);
+            // Prefetch: next row of this iteration (written one iteration ago), or row 0 of the next iteration.
+            const int mn = (m + 1 < layers) ? m + 1 : 0;
+            if ((m + 1 < layers) ? (it != 0) : (it + 1 < max_iter)) {
+              st_next = st_base[(uint32_t)mn * st_stride + j];
+            } else {
+              st_next = make_uint4(0, 0, 0, 0);
             }
-            {
-              // Prefetch: next row of this iteration, or row 0 of the next iteration.
-              const int  mn   = (m + 1 < layers) ? m + 1 : 0;
-              const bool have = (m + 1 < layers) ? (it != 0) : (it + 1 < max_iter);
-              const int  ngn  = flag_groups(g.row_start[mn + 1] - g.row_start[mn]);
-              const hh*  spn  = st_base + (uint32_t)g.st_off[mn] * st_stride + j;
-#pragma unroll
-              for (int k = 0; k != 4; ++k) {
-                st_next.w[k] = (have && k <= ngn) ? spn[k * st_stride] : 0u;
-              }
-            }
-            dispatch_row(deg, soft, g.shift + e0, g.base + e0, j, Z, st, st_out, scale_mode);
-#pragma unroll
-            for (int k = 0; k != 4; ++k) {
-              if (k <= ng) {
-                sp[k * st_stride] = st_out.w[k];
-              }
-            }
+            dispatch_row(deg, soft_addr, g.shift + e0, g.base + e0, j, Z, st, st_out, scale_mode);
+            st_base[(uint32_t)m * st_stride + j] = st_out;
           }
           __syncthreads();
         }
@@ -588,8 +585,8 @@ inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count,
   const int bg               = any_bg1 ? 1 : 2;
   plan.threads               = ((max_Z + 31) / 32) * 32;
   plan.smem                  = h2::h2_smem_bytes(bg, max_Z);
-  const int words            = (bg == 1) ? 103 : 86;
-  plan.scratch_words_per_cta = (size_t)words * ((max_Z + 31) & ~31);
+  const int rows             = (bg == 1) ? 46 : 42;
+  plan.scratch_words_per_cta = (size_t)rows * 4 * ((max_Z + 31) & ~31);
   plan.big                   = plan.threads > 192;
   h2_kernel_t   k            = plan.big ? (h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2>
                                         : (h2_kernel_t)h2::ldpc_decode_h2_kernel<192, 4>;
