@@ -199,16 +199,25 @@ __device__ __forceinline__ void dispatch_row(int deg, unsigned char* soft_addr, 
                                              const uint16_t* e_base, int j, int Z, const RowState& st, RowState& st_out,
                                              int scale_mode)
 {
-  switch (deg) {
-    case 3: process_row<3>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 4: process_row<4>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 5: process_row<5>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 6: process_row<6>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 7: process_row<7>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 8: process_row<8>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 9: process_row<9>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    case 10: process_row<10>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
-    default: process_row<19>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode); break;
+  // Most frequent degrees first (BG1: 18 rows of degree 5, 8 of degree 6, ...).
+  if (deg == 5) {
+    process_row<5>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+  } else if (deg == 6) {
+    process_row<6>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+  } else if (deg == 4) {
+    process_row<4>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+  } else if (deg == 7) {
+    process_row<7>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+  } else if (deg == 19) {
+    process_row<19>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+  } else if (deg == 3) {
+    process_row<3>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+  } else if (deg == 8) {
+    process_row<8>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+  } else if (deg == 9) {
+    process_row<9>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+  } else {
+    process_row<10>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
   }
 }
 
@@ -383,22 +392,35 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           in[h] = lane[h].valid ? prm.harq + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_SOFT : nullptr;
         }
         int last[2] = {0, 0};
-        for (int i = tid; i < n_full * Z; i += nthr) {
-          int k = i - 2 * Z;
-          hh  w = 0;
+        // Punctured nodes.
+        for (int i = tid; i < 2 * Z; i += nthr) {
+          soft[i] = 0;
+        }
+        // Four soft bits of each codeblock per thread and step (the HARQ entries are 16-byte aligned).
+        const int n4 = (N + 3) >> 2;
+        for (int q = tid; q < n4; q += nthr) {
+          uint32_t w4[2];
 #pragma unroll
           for (int h = 0; h != 2; ++h) {
-            int v = 0;
-            if (in[h] && k >= 0 && k < N) {
-              v = in[h][k];
-              if (v != 0) {
-                last[h] = k + 1;
+            w4[h] = in[h] ? __ldg(reinterpret_cast<const uint32_t*>(in[h]) + q) : 0u;
+          }
+#pragma unroll
+          for (int k = 0; k != 4; ++k) {
+            const int pos = 4 * q + k;
+            hh        w   = 0;
+#pragma unroll
+            for (int h = 0; h != 2; ++h) {
+              int v = (int)(int8_t)(w4[h] >> (8 * k));
+              if (v != 0 && pos < N) {
+                last[h] = pos + 1;
               }
               v = max(-CLAMP_IN, min(CLAMP_IN, v));
+              w |= (hh)__half_as_ushort(__int2half_rn(v)) << (16 * h);
             }
-            w |= (hh)__half_as_ushort(__int2half_rn(v)) << (16 * h);
+            if (pos < N) {
+              soft[2 * Z + pos] = w;
+            }
           }
-          soft[i] = w;
         }
 #pragma unroll
         for (int h = 0; h != 2; ++h) {
@@ -463,26 +485,27 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       const int  j          = tid;
       const bool active     = j < Z;
 
-      // Compressed messages of the next row are fetched while the current row is processed (they are private to
-      // thread j: the uint4 of row m of check j is only ever touched by thread j).
+      // Compressed messages: one uint4 per (row, check), only ever touched by thread j. They start at zero ("no message
+      // yet") and the next row is fetched while the current one is processed.
+      uint4* const st_thread = st_base + j;
+      if (active) {
+        for (int m = 0; m < layers; ++m) {
+          st_thread[(uint32_t)m * st_stride] = make_uint4(0, 0, 0, 0);
+        }
+      }
       RowState st_next = make_uint4(0, 0, 0, 0);
       for (int it = 0; it < max_iter; ++it) {
         for (int m = 0; m < layers; ++m) {
           if (active) {
-            const uint32_t info = g.row_info[m];
-            const int      e0   = info & 0xffffu;
-            const int      deg  = info >> 16;
-            const RowState st   = st_next;
+            const uint32_t info   = g.row_info[m];
+            const int      e0     = info & 0xffffu;
+            const int      deg    = info >> 16;
+            const RowState st     = st_next;
             RowState       st_out = make_uint4(0, 0, 0, 0);
-            // Prefetch: next row of this iteration (written one iteration ago), or row 0 of the next iteration.
-            const int mn = (m + 1 < layers) ? m + 1 : 0;
-            if ((m + 1 < layers) ? (it != 0) : (it + 1 < max_iter)) {
-              st_next = st_base[(uint32_t)mn * st_stride + j];
-            } else {
-              st_next = make_uint4(0, 0, 0, 0);
-            }
+            uint4* const   sp     = st_thread + (uint32_t)m * st_stride;
+            st_next               = (m + 1 < layers) ? sp[st_stride] : st_thread[0];
             dispatch_row(deg, soft_addr, g.shift + e0, g.base + e0, j, Z, st, st_out, scale_mode);
-            st_base[(uint32_t)m * st_stride + j] = st_out;
+            *sp = st_out;
           }
           __syncthreads();
         }
