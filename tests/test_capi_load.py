@@ -1,0 +1,56 @@
+"""CPU tests: the C-ABI library builds, loads and exports every symbol include/pusch_dec_cuda.h declares.
+No compute call is made (there may be no GPU); creating a context without a GPU must fail loudly, not fall back."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+from srsran_edgeric_5g_b200 import build, capi
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "pusch_dec_cuda.h"
+
+
+def declared_functions():
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pdc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_the_abi():
+    lib = build.build()
+    assert lib.exists()
+    L = ctypes.CDLL(str(lib))
+    decl = declared_functions()
+    assert len(decl) >= 18
+    for name in decl:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert sorted(capi.EXPORTS) == decl, "capi.EXPORTS and the header disagree"
+
+
+def test_struct_layouts_match_the_header():
+    assert ctypes.sizeof(capi.CbDesc) == 28 and capi.CB_DESC_DTYPE.itemsize == 28
+    assert ctypes.sizeof(capi.CbResult) == 4 and capi.CB_RESULT_DTYPE.itemsize == 4
+    assert ctypes.sizeof(capi.TbDesc) == 20 and capi.TB_DESC_DTYPE.itemsize == 20
+    assert ctypes.sizeof(capi.TbResult) == 4 and capi.TB_RESULT_DTYPE.itemsize == 4
+    assert ctypes.sizeof(capi.Config) == 36
+    for f, _ in capi.CbDesc._fields_:
+        assert capi.CB_DESC_DTYPE.fields[f][1] == getattr(capi.CbDesc, f).offset
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.PdcError) as e:
+        capi.Context(max_cbs=4, harq_entries=4)
+    assert e.value.code == capi.PDC_ERR_NO_DEVICE
+
+
+def test_sm100a_code_only():
+    # The library carries sm_100a SASS and nothing else (no multi-arch fatbin, no PTX JIT fallback).
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", str(build.LIB)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs

@@ -1,0 +1,105 @@
+"""CPU tests of the host-side logic: segmentation arithmetic, HARQ buffer pool, decoder state machine, sharding."""
+import numpy as np
+import pytest
+
+from srsran_edgeric_5g_b200 import ldpc, sharding
+from srsran_edgeric_5g_b200.channel_coding import (create_crc_calculator_factory_sw, create_ldpc_decoder_factory_sw,
+                                                   create_ldpc_rate_dematcher_factory_sw)
+from srsran_edgeric_5g_b200.pusch_decoder import PuschDecoderBatch, pusch_decoder_configuration, rx_buffer_pool
+
+
+def test_segmentation_matches_oracle(orc):
+    rng = np.random.default_rng(7)
+    for trial in range(300):
+        bg = int(rng.integers(1, 3))
+        tb_bytes = int(rng.integers(1, 3000 if bg == 2 else 20000)) if rng.random() < 0.9 else int(
+            rng.integers(100000, 159749))
+        if bg == 2 and tb_bytes * 8 > 30000:
+            tb_bytes = 3000
+        qm = int(rng.choice([1, 2, 4, 6, 8]))
+        nl = int(rng.integers(1, 5))
+        nsym = int(np.ceil(tb_bytes * 8 / rng.uniform(0.15, 0.92) / qm / nl)) * nl
+        n_llr = nsym * qm
+        a = ldpc.segment_rx(tb_bytes * 8, bg, 0, qm, 0, nl, n_llr)
+        b = orc.segment_rx(tb_bytes * 8, bg, qm, nl, n_llr)
+        assert len(a) == len(b) == ldpc.compute_nof_codeblocks(tb_bytes * 8, bg)
+        for x, y in zip(a, b):
+            assert (x.lifting_size, x.full_length, x.rm_length, x.nof_filler_bits, x.cw_offset, x.nof_crc_bits) == (
+                y.Z, y.full_length, y.rm_length, y.nof_filler, y.cw_offset, y.nof_crc_bits)
+
+
+def test_config3_numbers():
+    # 273 PRB x 13 symbols x 12 x 4 layers x 256QAM.
+    tbs, n_llr = 1277992, 1362816
+    metas = ldpc.segment_rx(tbs, ldpc.BG1, 0, 8, 0, 4, n_llr)
+    assert len(metas) == 152 and metas[0].lifting_size == 384 and metas[0].nof_filler_bits == 16
+    assert sorted({m.rm_length for m in metas}) == [8960, 8992]
+    assert sum(m.rm_length == 8960 for m in metas) == 124
+    assert ldpc.compute_N_ref(tbs // 8, 152) == 12611
+
+
+def test_unknown_factory_types_return_none():
+    # The reference returns nullptr for unknown types (channel_coding_factories.cpp:100-124, :166-192).
+    assert create_ldpc_decoder_factory_sw("avx2") is None
+    assert create_ldpc_rate_dematcher_factory_sw("generic") is None
+    assert create_crc_calculator_factory_sw("lut") is None
+
+
+class _FakeCtx:
+    class cfg:
+        harq_entries = 8
+
+    def harq_free(self, i):
+        pass
+
+
+def test_rx_buffer_pool_semantics():
+    pool = rx_buffer_pool(_FakeCtx())
+    a = pool.reserve(None, (1, 0), 3, True)
+    assert a is not None and a.get_nof_codeblocks() == 3 and a.locked
+    assert pool.reserve(None, (1, 0), 3, False) is None  # locked
+    a.unlock()
+    assert pool.reserve(None, (2, 0), 6, True) is None  # not enough codeblocks left
+    b = pool.reserve(None, (1, 0), 3, False)
+    assert b is a  # retransmission gets the same entries: HARQ state is sticky
+    ids = [b.get_absolute_codeblock_id(k) for k in range(3)]
+    b.unlock()
+    assert pool.reserve(None, (1, 0), 2, False) is None  # different number of codeblocks on a retransmission
+    c = pool.reserve(None, (1, 0), 2, True)  # new data may change the size
+    assert c is not None and c.get_nof_codeblocks() == 2
+    c.release()
+    assert pool.reserve(None, (1, 0), 2, False) is None  # released buffers are gone
+    d = pool.reserve(None, (3, 1), 8, True)
+    assert d is not None and sorted(d.get_absolute_codeblock_id(k) for k in range(8)) == list(range(8))
+    assert len(set(ids)) == 3
+
+
+def test_pusch_decoder_state_machine():
+    batch = PuschDecoderBatch(ctx=None)
+    dec = batch.create()
+    pool = rx_buffer_pool(_FakeCtx())
+    buf = pool.reserve(None, (1, 0), 1, True)
+    cfg = pusch_decoder_configuration(ldpc.BG2, 0, 2, 0, 1)
+    with pytest.raises(RuntimeError):
+        dec.on_new_softbits(np.zeros(4, np.int8))  # not configured yet
+    with pytest.raises(ValueError):
+        dec.new_data(np.zeros(1000, np.uint8), buf, None, cfg)  # 3 codeblocks needed, buffer has 1
+    b = dec.new_data(np.zeros(20, np.uint8), buf, None, cfg)
+    with pytest.raises(RuntimeError):
+        dec.new_data(np.zeros(20, np.uint8), buf, None, cfg)  # already collecting
+    b.on_new_softbits(np.zeros(300, np.int8))
+    dec.set_nof_softbits(400)
+    with pytest.raises(ValueError):
+        b.on_end_softbits()  # 300 != 400
+    b.on_new_softbits(np.zeros(100, np.int8))
+    b.on_end_softbits()
+    assert batch.pending() == 1
+
+
+def test_sharding_is_a_sticky_partition():
+    tbs = [dict(cell=c, rnti=0x4601 + u) for c in range(16) for u in range(5)]
+    for world in (1, 2, 4, 8):
+        sharding.check_partition(tbs, world)
+        parts = [sharding.shard_transport_blocks(tbs, world, r) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(len(tbs)))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 5  # 16 cells -> 2 per GPU at 8
