@@ -1,0 +1,318 @@
+#include "pusch_dec_cuda_adapters.h"
+#include "srsran/ran/sch/modulation_scheme.h"
+#include "srsran/support/error_handling.h"
+#include "srsran/support/srsran_assert.h"
+#include <atomic>
+#include <cstring>
+
+using namespace srsran;
+using namespace srsran::cuda;
+
+static int to_crc_kind(crc_generator_poly poly)
+{
+  switch (poly) {
+    case crc_generator_poly::CRC16:
+      return PDC_CRC16;
+    case crc_generator_poly::CRC24A:
+      return PDC_CRC24A;
+    case crc_generator_poly::CRC24B:
+      return PDC_CRC24B;
+    default:
+      return -1;
+  }
+}
+
+std::shared_ptr<context> context::create(const config& cfg)
+{
+  pdc_config c;
+  pdc_default_config(&c);
+  c.device       = cfg.device;
+  c.max_cbs      = cfg.max_cbs;
+  c.max_llrs     = cfg.max_cbs * 12288u;
+  c.harq_entries = cfg.harq_entries;
+  c.scale_mode   = cfg.scale_mode;
+  pdc_ctx* h     = nullptr;
+  if (pdc_create(&c, &h) != PDC_OK) {
+    return nullptr;
+  }
+  return std::shared_ptr<context>(new context(h));
+}
+
+context::~context()
+{
+  pdc_destroy(ctx);
+}
+
+std::optional<unsigned> ldpc_decoder_cuda::decode(bit_buffer&                      output,
+                                                  span<const log_likelihood_ratio> input,
+                                                  crc_calculator*                  crc,
+                                                  const configuration&             cfg)
+{
+  const auto& tb = cfg.block_conf.tb_common;
+  int         bg = (tb.base_graph == ldpc_base_graph_type::BG1) ? 1 : 2;
+  unsigned    Z  = static_cast<unsigned>(tb.lifting_size);
+  unsigned    K  = ((bg == 1) ? 22 : 10) * Z;
+  // Same contract as ldpc_decoder_impl::decode (ldpc_decoder_impl.cpp:69-83).
+  srsran_assert(output.size() == K, "The output size {} is not equal to the message length {}.", output.size(), K);
+  int kind = PDC_CRC_NONE;
+  if (crc != nullptr) {
+    kind = to_crc_kind(crc->get_generator_poly());
+    srsran_assert(kind > 0, "Invalid CRC calculator.");
+  }
+  int iters = 0;
+  int rc    = pdc_ldpc_decode(ctx->get(),
+                           bg,
+                           static_cast<int>(Z),
+                           reinterpret_cast<const int8_t*>(input.data()),
+                           input.size(),
+                           cfg.block_conf.cb_specific.nof_filler_bits,
+                           kind,
+                           static_cast<int>(cfg.algorithm_conf.max_iterations),
+                           output.get_buffer().data(),
+                           &iters);
+  report_fatal_error_if_not(rc == PDC_OK, "pdc_ldpc_decode failed: {}", pdc_last_error());
+  if (iters > 0) {
+    return static_cast<unsigned>(iters);
+  }
+  return std::nullopt;
+}
+
+void ldpc_rate_dematcher_cuda::rate_dematch(span<log_likelihood_ratio>       output,
+                                            span<const log_likelihood_ratio> input,
+                                            bool                             new_data,
+                                            const codeblock_metadata&        cfg)
+{
+  int rc = pdc_rate_dematch(ctx->get(),
+                            reinterpret_cast<int8_t*>(output.data()),
+                            output.size(),
+                            reinterpret_cast<const int8_t*>(input.data()),
+                            input.size(),
+                            new_data,
+                            static_cast<int>(cfg.tb_common.rv),
+                            static_cast<int>(get_bits_per_symbol(cfg.tb_common.mod)),
+                            cfg.tb_common.Nref,
+                            cfg.cb_specific.nof_filler_bits);
+  report_fatal_error_if_not(rc == PDC_OK, "pdc_rate_dematch failed: {}", pdc_last_error());
+}
+
+crc_calculator_checksum_t crc_calculator_cuda::calculate_byte(span<const uint8_t> data)
+{
+  uint32_t c  = 0;
+  int      rc = pdc_crc(ctx->get(), to_crc_kind(poly), data.data(), data.size() * 8, &c);
+  report_fatal_error_if_not(rc == PDC_OK, "pdc_crc failed: {}", pdc_last_error());
+  return c;
+}
+
+crc_calculator_checksum_t crc_calculator_cuda::calculate_bit(span<const uint8_t> data)
+{
+  std::vector<uint8_t> packed((data.size() + 7) / 8, 0);
+  for (size_t i = 0; i != data.size(); ++i) {
+    packed[i / 8] |= static_cast<uint8_t>((data[i] & 1U) << (7 - (i % 8)));
+  }
+  uint32_t c  = 0;
+  int      rc = pdc_crc(ctx->get(), to_crc_kind(poly), packed.data(), data.size(), &c);
+  report_fatal_error_if_not(rc == PDC_OK, "pdc_crc failed: {}", pdc_last_error());
+  return c;
+}
+
+crc_calculator_checksum_t crc_calculator_cuda::calculate(const bit_buffer& data)
+{
+  uint32_t c  = 0;
+  int      rc = pdc_crc(ctx->get(), to_crc_kind(poly), data.get_buffer().data(), data.size(), &c);
+  report_fatal_error_if_not(rc == PDC_OK, "pdc_crc failed: {}", pdc_last_error());
+  return c;
+}
+
+hw_accelerator_pusch_dec_cuda::hw_accelerator_pusch_dec_cuda(std::shared_ptr<context> c, unsigned q) :
+  ctx(std::move(c)), queue(q), pending_cfg(MAX_NOF_SEGMENTS), slot_of_cb(MAX_NOF_SEGMENTS, -1)
+{
+  llr_capacity = static_cast<size_t>(MAX_NOF_SEGMENTS) * 12288u;
+  llr_staging  = static_cast<int8_t*>(pdc_host_alloc(llr_capacity));
+  report_fatal_error_if_not(llr_staging != nullptr, "pdc_host_alloc failed");
+  results.resize(MAX_NOF_SEGMENTS);
+  bits.resize(static_cast<size_t>(MAX_NOF_SEGMENTS) * PDC_MAX_CB_BYTES);
+}
+
+hw_accelerator_pusch_dec_cuda::~hw_accelerator_pusch_dec_cuda()
+{
+  pdc_host_free(llr_staging);
+}
+
+void hw_accelerator_pusch_dec_cuda::reserve_queue()
+{
+  batch.clear();
+  std::fill(slot_of_cb.begin(), slot_of_cb.end(), -1);
+  llr_used  = 0;
+  submitted = false;
+}
+
+void hw_accelerator_pusch_dec_cuda::free_queue()
+{
+  batch.clear();
+  submitted = false;
+}
+
+void hw_accelerator_pusch_dec_cuda::configure_operation(const hal::hw_pusch_decoder_configuration& cfg,
+                                                        unsigned                                   cb_index)
+{
+  pdc_cb_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.rm_length    = cfg.cw_length;
+  d.harq_id      = cfg.absolute_cb_id;
+  d.nref         = cfg.Nref;
+  d.lifting_size = static_cast<uint16_t>(cfg.lifting_size);
+  d.nof_filler   = static_cast<uint16_t>(cfg.nof_filler_bits);
+  d.base_graph   = (cfg.base_graph_index == ldpc_base_graph_type::BG1) ? 1 : 2;
+  d.qm           = static_cast<uint8_t>(get_bits_per_symbol(cfg.modulation));
+  d.rv           = static_cast<uint8_t>(cfg.rv);
+  d.crc_kind     = (cfg.cb_crc_type == hal::hw_dec_cb_crc_type::CRC16)    ? PDC_CRC16
+                   : (cfg.cb_crc_type == hal::hw_dec_cb_crc_type::CRC24A) ? PDC_CRC24A
+                                                                          : PDC_CRC24B;
+  d.max_iter     = static_cast<uint8_t>(cfg.max_nof_ldpc_iterations);
+  d.flags        = PDC_CB_DEMATCH | PDC_CB_DECODE | (cfg.new_data ? PDC_CB_NEW_DATA : 0) |
+            (cfg.use_early_stop ? PDC_CB_EARLY_STOP : 0);
+  d.tb_index            = 0xffff;
+  pending_cfg[cb_index] = d;
+}
+
+bool hw_accelerator_pusch_dec_cuda::enqueue_operation(span<const int8_t> data,
+                                                      span<const int8_t> /*soft_data*/,
+                                                      unsigned cb_index)
+{
+  // "Queue full": the caller retries after dequeuing (pusch_decoder_hw_impl.cpp:237-241).
+  if (submitted || llr_used + data.size() > llr_capacity || batch.size() >= MAX_NOF_SEGMENTS) {
+    return false;
+  }
+  pdc_cb_desc d = pending_cfg[cb_index];
+  d.llr_offset  = static_cast<uint32_t>(llr_used);
+  std::memcpy(llr_staging + llr_used, data.data(), data.size());
+  llr_used += (data.size() + 15) & ~static_cast<size_t>(15);
+  slot_of_cb[cb_index] = static_cast<int>(batch.size());
+  batch.push_back(d);
+  return true;
+}
+
+void hw_accelerator_pusch_dec_cuda::flush()
+{
+  int rc = pdc_submit(ctx->get(), queue, batch.data(), batch.size(), llr_staging, llr_used, nullptr, 0, results.data(),
+                      bits.data(), nullptr, nullptr);
+  if (rc == PDC_OK) {
+    rc = pdc_wait(ctx->get(), queue);
+  }
+  if (rc != PDC_OK) {
+    // A failed batch reports CRC failure with the maximum number of iterations, like a dropped accelerator operation
+    // (hw_accelerator_pusch_dec_acc100_impl.cpp:233-247).
+    for (size_t i = 0; i != batch.size(); ++i) {
+      results[i].crc_ok = 0;
+      results[i].iters  = batch[i].max_iter;
+    }
+  }
+  submitted = true;
+}
+
+bool hw_accelerator_pusch_dec_cuda::dequeue_operation(span<uint8_t> data,
+                                                      span<int8_t> /*soft_data*/,
+                                                      unsigned segment_index)
+{
+  int slot = slot_of_cb[segment_index];
+  if (slot < 0) {
+    return false;
+  }
+  if (!submitted) {
+    flush();
+  }
+  std::memcpy(data.data(), bits.data() + static_cast<size_t>(slot) * PDC_MAX_CB_BYTES, data.size());
+  return true;
+}
+
+void hw_accelerator_pusch_dec_cuda::read_operation_outputs(hal::hw_pusch_decoder_outputs& out,
+                                                           unsigned                       cb_index,
+                                                           unsigned /*absolute_cb_id*/)
+{
+  int slot = slot_of_cb[cb_index];
+  srsran_assert(slot >= 0 && submitted, "No completed operation for this codeblock.");
+  out.CRC_pass            = results[slot].crc_ok != 0;
+  out.nof_ldpc_iterations = results[slot].iters;
+}
+
+void hw_accelerator_pusch_dec_cuda::free_harq_context_entry(unsigned absolute_cb_id)
+{
+  pdc_harq_free(ctx->get(), absolute_cb_id);
+}
+
+namespace {
+
+class ldpc_decoder_factory_cuda : public ldpc_decoder_factory
+{
+public:
+  explicit ldpc_decoder_factory_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  std::unique_ptr<ldpc_decoder> create() override { return std::make_unique<ldpc_decoder_cuda>(ctx); }
+
+private:
+  std::shared_ptr<context> ctx;
+};
+
+class ldpc_rate_dematcher_factory_cuda : public ldpc_rate_dematcher_factory
+{
+public:
+  explicit ldpc_rate_dematcher_factory_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  std::unique_ptr<ldpc_rate_dematcher> create() override { return std::make_unique<ldpc_rate_dematcher_cuda>(ctx); }
+
+private:
+  std::shared_ptr<context> ctx;
+};
+
+class crc_calculator_factory_cuda : public crc_calculator_factory
+{
+public:
+  explicit crc_calculator_factory_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  std::unique_ptr<crc_calculator> create(crc_generator_poly poly) override
+  {
+    if (to_crc_kind(poly) < 0) {
+      return nullptr;
+    }
+    return std::make_unique<crc_calculator_cuda>(ctx, poly);
+  }
+
+private:
+  std::shared_ptr<context> ctx;
+};
+
+class hw_accelerator_pusch_dec_factory_cuda : public hal::hw_accelerator_pusch_dec_factory
+{
+public:
+  explicit hw_accelerator_pusch_dec_factory_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  std::unique_ptr<hal::hw_accelerator_pusch_dec> create() override
+  {
+    // One stream ("hardware queue") per accelerator instance, round robin over the context's streams.
+    return std::make_unique<hw_accelerator_pusch_dec_cuda>(ctx, next_queue++ % 2);
+  }
+
+private:
+  std::shared_ptr<context> ctx;
+  std::atomic<unsigned>    next_queue{0};
+};
+
+} // namespace
+
+std::shared_ptr<ldpc_decoder_factory> srsran::cuda::create_ldpc_decoder_factory_cuda(std::shared_ptr<context> ctx)
+{
+  return ctx ? std::make_shared<ldpc_decoder_factory_cuda>(std::move(ctx)) : nullptr;
+}
+
+std::shared_ptr<ldpc_rate_dematcher_factory>
+srsran::cuda::create_ldpc_rate_dematcher_factory_cuda(std::shared_ptr<context> ctx)
+{
+  return ctx ? std::make_shared<ldpc_rate_dematcher_factory_cuda>(std::move(ctx)) : nullptr;
+}
+
+std::shared_ptr<crc_calculator_factory> srsran::cuda::create_crc_calculator_factory_cuda(std::shared_ptr<context> ctx)
+{
+  return ctx ? std::make_shared<crc_calculator_factory_cuda>(std::move(ctx)) : nullptr;
+}
+
+std::shared_ptr<hal::hw_accelerator_pusch_dec_factory>
+srsran::cuda::create_hw_accelerator_pusch_dec_factory_cuda(std::shared_ptr<context> ctx)
+{
+  return ctx ? std::make_shared<hw_accelerator_pusch_dec_factory_cuda>(std::move(ctx)) : nullptr;
+}

@@ -1,0 +1,133 @@
+/// \file
+/// \brief "cuda" variants of the reference's plug-in interfaces, implemented on top of the C ABI
+///        (include/pusch_dec_cuda.h). This translation unit sees the reference's headers and the C header only; no CUDA.
+///
+///   ldpc_decoder_cuda             : srsran::ldpc_decoder            (phy/upper/channel_coding/ldpc/ldpc_decoder.h:37-75)
+///   ldpc_rate_dematcher_cuda      : srsran::ldpc_rate_dematcher     (.../ldpc/ldpc_rate_dematcher.h:35-56)
+///   crc_calculator_cuda           : srsran::crc_calculator          (.../crc_calculator.h:62-84)
+///   hw_accelerator_pusch_dec_cuda : srsran::hal::hw_accelerator_pusch_dec
+///                                   (hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec.h:83-115),
+///                                   driven unchanged by pusch_decoder_hw_impl (pusch_decoder_hw_impl.cpp:132-342).
+/// and the factories a "cuda" branch of create_ldpc_decoder_factory_sw / create_ldpc_rate_dematcher_factory_sw /
+/// create_crc_calculator_factory_sw / create_hw_accelerator_pusch_dec_factory returns.
+#pragma once
+
+#include "pusch_dec_cuda.h"
+#include "srsran/hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec.h"
+#include "srsran/hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec_factory.h"
+#include "srsran/phy/upper/channel_coding/channel_coding_factories.h"
+#include <memory>
+#include <vector>
+
+namespace srsran {
+namespace cuda {
+
+/// Shared, reference-counted GPU context (one per device; owns the HARQ arena, streams and pinned staging).
+class context
+{
+public:
+  /// Configuration of the device context.
+  struct config {
+    int      device       = 0;
+    unsigned max_cbs      = 4096;
+    unsigned harq_entries = 4096;
+    /// Which reference decoder is reproduced bit for bit: PDC_SCALE_X86 (avx2/avx512, "auto" on x86) or generic.
+    int scale_mode = PDC_SCALE_X86;
+  };
+
+  /// Returns nullptr if no usable GPU is present (there is no software fallback).
+  static std::shared_ptr<context> create(const config& cfg);
+  ~context();
+  pdc_ctx* get() const { return ctx; }
+
+private:
+  explicit context(pdc_ctx* c) : ctx(c) {}
+  pdc_ctx* ctx;
+};
+
+/// LDPC decoder, single-codeblock synchronous call (latency path).
+class ldpc_decoder_cuda : public ldpc_decoder
+{
+public:
+  explicit ldpc_decoder_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  std::optional<unsigned>
+  decode(bit_buffer& output, span<const log_likelihood_ratio> input, crc_calculator* crc, const configuration& cfg) override;
+
+private:
+  std::shared_ptr<context> ctx;
+};
+
+/// LDPC rate dematcher, single-codeblock synchronous call.
+class ldpc_rate_dematcher_cuda : public ldpc_rate_dematcher
+{
+public:
+  explicit ldpc_rate_dematcher_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  void rate_dematch(span<log_likelihood_ratio>       output,
+                    span<const log_likelihood_ratio> input,
+                    bool                             new_data,
+                    const codeblock_metadata&        cfg) override;
+
+private:
+  std::shared_ptr<context> ctx;
+};
+
+/// CRC calculator (CRC16 / CRC24A / CRC24B).
+class crc_calculator_cuda : public crc_calculator
+{
+public:
+  crc_calculator_cuda(std::shared_ptr<context> c, crc_generator_poly p) : ctx(std::move(c)), poly(p) {}
+  crc_calculator_checksum_t calculate_byte(span<const uint8_t> data) override;
+  crc_calculator_checksum_t calculate_bit(span<const uint8_t> data) override;
+  crc_calculator_checksum_t calculate(const bit_buffer& data) override;
+  crc_generator_poly        get_generator_poly() const override { return poly; }
+
+private:
+  std::shared_ptr<context> ctx;
+  crc_generator_poly       poly;
+};
+
+/// \brief PUSCH decoder accelerator in the hal::hw_accelerator_pusch_dec slot.
+///
+/// External HARQ: soft bits live in the device arena, indexed by the absolute codeblock id of the rx_buffer pool
+/// (rx_buffer.h:58-65), so pusch_decoder_hw_impl enqueues every codeblock of the transport block before the first
+/// dequeue (pusch_decoder_hw_impl.cpp:246-262). The first dequeue submits all of them as ONE GPU batch.
+class hw_accelerator_pusch_dec_cuda : public hal::hw_accelerator_pusch_dec
+{
+public:
+  hw_accelerator_pusch_dec_cuda(std::shared_ptr<context> c, unsigned queue);
+  ~hw_accelerator_pusch_dec_cuda() override;
+
+  void reserve_queue() override;
+  void free_queue() override;
+  bool enqueue_operation(span<const int8_t> data, span<const int8_t> soft_data = {}, unsigned cb_index = 0) override;
+  bool dequeue_operation(span<uint8_t> data, span<int8_t> soft_data = {}, unsigned segment_index = 0) override;
+  void configure_operation(const hal::hw_pusch_decoder_configuration& config, unsigned cb_index = 0) override;
+  void read_operation_outputs(hal::hw_pusch_decoder_outputs& out,
+                              unsigned                       cb_index       = 0,
+                              unsigned                       absolute_cb_id = 0) override;
+  void free_harq_context_entry(unsigned absolute_cb_id) override;
+  bool is_external_harq_supported() const override { return true; }
+
+private:
+  void flush();
+
+  std::shared_ptr<context>   ctx;
+  unsigned                   queue;
+  std::vector<pdc_cb_desc>   pending_cfg;   // by codeblock index within the TB
+  std::vector<int>           slot_of_cb;    // position in the submitted batch, -1 if not enqueued
+  std::vector<pdc_cb_desc>   batch;
+  std::vector<pdc_cb_result> results;
+  std::vector<uint8_t>       bits;
+  int8_t*                    llr_staging = nullptr; // pinned
+  size_t                     llr_capacity = 0, llr_used = 0;
+  bool                       submitted = false;
+};
+
+std::shared_ptr<ldpc_decoder_factory>        create_ldpc_decoder_factory_cuda(std::shared_ptr<context> ctx);
+std::shared_ptr<ldpc_rate_dematcher_factory> create_ldpc_rate_dematcher_factory_cuda(std::shared_ptr<context> ctx);
+std::shared_ptr<crc_calculator_factory>      create_crc_calculator_factory_cuda(std::shared_ptr<context> ctx);
+std::shared_ptr<hal::hw_accelerator_pusch_dec_factory>
+create_hw_accelerator_pusch_dec_factory_cuda(std::shared_ptr<context> ctx);
+
+} // namespace cuda
+} // namespace srsran
