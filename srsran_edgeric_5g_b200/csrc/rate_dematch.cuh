@@ -17,6 +17,7 @@ namespace pdc {
 
 struct DematchGeom {
   int N, Ncb, Z, K_sys, F, info, k0, d0, Dn, E, qm, Kq;
+  float inv_Kq;
   int new_data;
   int first_pass_len; // data positions from the start of the walk to the end of the circular buffer
   int wrapped;        // the walk went past the end of the circular buffer at least once
@@ -53,6 +54,7 @@ __device__ __forceinline__ bool dm_geometry(const pdc_cb_desc& d, int simd_width
   g.E              = d.rm_length;
   g.qm             = d.qm;
   g.Kq             = g.E / g.qm;
+  g.inv_Kq         = 1.0f / (float)g.Kq;
   g.new_data       = (d.flags & PDC_CB_NEW_DATA) ? 1 : 0;
   g.first_pass_len = g.Dn - g.d0;
   g.wrapped        = g.E > g.first_pass_len;
@@ -159,6 +161,101 @@ __device__ __forceinline__ int dm_position(const DematchGeom& g, const int8_t* _
   return val;
 }
 
+// True if any of the four packed int8 is outside [-120, 120] (|u - 0x80| < 8 for the unsigned byte u).
+__device__ __forceinline__ bool dm_any_nonfinite(uint32_t x)
+{
+  uint32_t v = __vabsdiffu4(x, 0x80808080u);
+  return ((v - 0x08080808u) & ~v & 0x80808080u) != 0;
+}
+
+// Four saturating LLR sums at once for finite operands: clamp(a + b, +-120) per int8, computed in 16-bit lanes.
+__device__ __forceinline__ uint32_t dm_combine4_finite(uint32_t a, uint32_t b)
+{
+  // Sign-extend even / odd bytes to 16-bit lanes (PRMT selector bit 3 replicates the sign of the selected byte; the
+  // __byte_perm intrinsic only defines selector values 0-7, hence the explicit PTX).
+  uint32_t ae, ao, be, bo;
+  asm("prmt.b32 %0, %1, 0, 0xA280;" : "=r"(ae) : "r"(a));
+  asm("prmt.b32 %0, %1, 0, 0xB391;" : "=r"(ao) : "r"(a));
+  asm("prmt.b32 %0, %1, 0, 0xA280;" : "=r"(be) : "r"(b));
+  asm("prmt.b32 %0, %1, 0, 0xB391;" : "=r"(bo) : "r"(b));
+  uint32_t se = __vmaxs2(__vmins2(__vadd2(ae, be), 0x00780078u), 0xff88ff88u);
+  uint32_t so = __vmaxs2(__vmins2(__vadd2(ao, bo), 0x00780078u), 0xff88ff88u);
+  return __byte_perm(se, so, 0x6240);
+}
+
+// Word fast path: the four positions 4w..4w+3 lie in one region of the circular buffer, are fed by four consecutive
+// deinterleaved inputs of one bit plane (or by none) and the transmission makes a single lap. Returns false if the
+// word needs the general per-position path.
+__device__ __forceinline__ bool dm_word_fast(const DematchGeom& g, const int8_t* __restrict__ llr, int p0, uint32_t old,
+                                             uint32_t& res)
+{
+  if (p0 + 3 >= g.Ncb) {
+    return false;
+  }
+  const bool in_info = p0 + 3 < g.info;
+  if (!in_info && p0 < g.K_sys) {
+    return false;
+  }
+  int  i         = (in_info ? p0 : p0 - g.F) - g.d0;
+  bool first_lap = i >= 0;
+  if (!first_lap) {
+    if (i + 3 >= 0) {
+      return false;
+    }
+    i += g.Dn;
+  }
+  // Base value of the four positions (what the sequential walk leaves there before combining).
+  uint32_t base = old;
+  if (g.new_data) {
+    const bool z0 = (p0 < g.zlo) || (p0 >= g.zf_lo);
+    const bool z3 = (p0 + 3 < g.zlo) || (p0 + 3 >= g.zf_lo);
+    if (z0 != z3) {
+      return false;
+    }
+    if (z0) {
+      base = 0;
+    }
+  }
+  if (i >= g.E) {
+    res = base;
+    return true;
+  }
+  if (i + 3 >= g.E) {
+    return false;
+  }
+  // Four consecutive inputs of one bit plane.
+  uint32_t in;
+  if (g.qm == 1) {
+    in = (uint32_t)(uint8_t)__ldg(llr + i) | ((uint32_t)(uint8_t)__ldg(llr + i + 1) << 8) |
+         ((uint32_t)(uint8_t)__ldg(llr + i + 2) << 16) | ((uint32_t)(uint8_t)__ldg(llr + i + 3) << 24);
+  } else {
+    int j = __float2int_rz(__fmul_rz((float)i, g.inv_Kq));
+    int sym = i - j * g.Kq;
+    if (sym < 0) {
+      --j;
+      sym += g.Kq;
+    } else if (sym >= g.Kq) {
+      ++j;
+      sym -= g.Kq;
+    }
+    if (sym + 3 >= g.Kq) {
+      return false;
+    }
+    const int8_t* src = llr + sym * g.qm + j;
+    in = (uint32_t)(uint8_t)__ldg(src) | ((uint32_t)(uint8_t)__ldg(src + g.qm) << 8) |
+         ((uint32_t)(uint8_t)__ldg(src + 2 * g.qm) << 16) | ((uint32_t)(uint8_t)__ldg(src + 3 * g.qm) << 24);
+  }
+  if (g.new_data && first_lap) {
+    res = in; // copy
+    return true;
+  }
+  if (dm_any_nonfinite(base) || dm_any_nonfinite(in)) {
+    return false;
+  }
+  res = dm_combine4_finite(base, in);
+  return true;
+}
+
 // One CTA per codeblock; each thread owns 4 consecutive soft bits (one 32-bit read-modify-write of the HARQ entry).
 __global__ void __launch_bounds__(256) rate_dematch_kernel(BatchParams prm)
 {
@@ -176,17 +273,21 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(BatchParams prm)
   if (!ok) {
     return; // the decode kernel reports the invalid descriptor
   }
-  const int8_t* llr  = prm.llrs + d.llr_offset;
-  uint32_t*     out  = reinterpret_cast<uint32_t*>(prm.harq + (size_t)d.harq_id * PDC_MAX_CB_SOFT);
-  int           nw   = (g.N + 3) >> 2;
+  const int8_t* llr        = prm.llrs + d.llr_offset;
+  uint32_t*     out        = reinterpret_cast<uint32_t*>(prm.harq + (size_t)d.harq_id * PDC_MAX_CB_SOFT);
+  const int     nw         = (g.N + 3) >> 2;
+  const bool    single_lap = g.E <= g.Dn;
   for (int w = threadIdx.x; w < nw; w += blockDim.x) {
-    uint32_t old = out[w];
-    uint32_t res = 0;
+    const uint32_t old = out[w];
+    uint32_t       res = 0;
+    if (!(single_lap && dm_word_fast(g, llr, 4 * w, old, res))) {
+      res = 0;
 #pragma unroll
-    for (int k = 0; k != 4; ++k) {
-      int o = (int)(int8_t)(old >> (8 * k));
-      int v = dm_position(g, llr, 4 * w + k, o);
-      res |= (uint32_t)(uint8_t)(int8_t)v << (8 * k);
+      for (int k = 0; k != 4; ++k) {
+        int o = (int)(int8_t)(old >> (8 * k));
+        int v = dm_position(g, llr, 4 * w + k, o);
+        res |= (uint32_t)(uint8_t)(int8_t)v << (8 * k);
+      }
     }
     if (res != old) {
       out[w] = res;
