@@ -61,6 +61,8 @@ constexpr hh H_N1024 = 0xE400E400u;
 constexpr hh H_BIG   = 0x7BFF7BFFu; // 65504: one excess unit times BIG overflows to infinity
 constexpr hh H_NBIG  = 0xFBFFFBFFu;
 constexpr hh H_SIGN  = 0x80008000u;
+constexpr hh H_544   = 0x60406040u; // promotion slope: 121 * 544 overflows, 120 * 544 = 65280 does not
+constexpr hh H_N65280 = 0xFBF8FBF8u;
 constexpr hh H_0P8   = 0x3A663A66u; // 0.7998046875
 constexpr hh H_N0P6  = 0xB8CDB8CDu; // -0.60009765625
 
@@ -81,8 +83,8 @@ __device__ __forceinline__ hh st_word(const RowState& s, int k)
 
 // The lifted graph of this (base graph, Z) in shared memory.
 struct GraphSmem {
-  uint16_t shift[MAX_EDGES];     // circulant shift of the edge
-  uint16_t base[MAX_EDGES];      // col * Z: first soft word of the edge's variable node
+  uint32_t base4[MAX_EDGES];     // byte offset of the first soft word of the edge's variable node (col * Z * 4)
+  uint16_t shift4[MAX_EDGES];    // circulant shift of the edge, in bytes
   uint32_t row_info[MAX_ROWS];   // first edge | degree << 16
 };
 
@@ -92,8 +94,8 @@ struct GraphSmem {
 //   st/st_out: compressed messages of this row from the previous iteration / for the next one
 template <int DEG>
 __device__ __forceinline__ void process_row(unsigned char* soft, const uint16_t* __restrict__ e_shift,
-                                            const uint16_t* __restrict__ e_base, int j, int Z, const RowState& st,
-                                            RowState& st_out, int scale_mode)
+                                            const uint32_t* __restrict__ e_base, uint32_t j4, uint32_t Z4,
+                                            const RowState& st, RowState& st_out, int scale_mode)
 {
   constexpr bool PACKED_MIN = DEG > 16;
   constexpr int  F0         = PACKED_MIN ? 1 : 2; // index of the first flag word
@@ -116,7 +118,7 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint16_t*
   const __half2 mid = __hmul2(__hadd2(m1, m2), H(H_HALF));
   const __half2 hd  = __hmul2(__hsub2(m2, m1), H(H_HALF));
 
-  __half2 min1 = h120, min2 = h120;
+  __half2 min1 = h120, min2 = h120, a_prev = h120;
   hh      par = 0, ps = 0, pm = 0;
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
@@ -125,9 +127,9 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint16_t*
       pm   = f;      // "held the minimum" flags: bit 15 of each half = edge e, then e+1, ... after each shift
       ps   = f << 8; // sign flags
     }
-    uint32_t pos = (uint32_t)j + e_shift[e];
-    pos          = min(pos, pos - (uint32_t)Z); // wrap: pos - Z underflows to a huge value when pos < Z
-    addr[e]      = (e_base[e] + pos) * 4u;
+    uint32_t pos = j4 + e_shift[e];
+    pos          = min(pos, pos - Z4); // wrap: pos - Z underflows to a huge value when pos < Z
+    addr[e]      = e_base[e] + pos;
     const __half2 s    = H(*reinterpret_cast<const hh*>(soft + addr[e]));
     const __half2 z    = H(lop_and_or(pm, H_SIGN, H_ONE));
     const __half2 sg   = H(lop_and_or(ps, H_SIGN, H_ONE));
@@ -139,9 +141,18 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint16_t*
     c                 = __hfma2(c, inf, c);
     vc[e]             = c;
     par ^= U(c);
+    // Two smallest magnitudes of the row, edges taken in pairs (shorter dependency chain, three-input minimum).
     const __half2 a = __habs2(c);
-    min2            = __hmin2(min2, __hmax2(min1, a));
-    min1            = __hmin2(min1, a);
+    if ((e & 1) == 0 && e != DEG - 1) {
+      a_prev = a;
+    } else if (e & 1) {
+      const __half2 lo = __hmin2(a_prev, a), hi = __hmax2(a_prev, a);
+      min2             = __hmin2(__hmin2(min2, hi), __hmax2(min1, lo));
+      min1             = __hmin2(min1, lo);
+    } else {
+      min2 = __hmin2(min2, __hmax2(min1, a));
+      min1 = __hmin2(min1, a);
+    }
     pm <<= 1;
     ps <<= 1;
   }
@@ -167,18 +178,25 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint16_t*
     const __half2 mag = __hfma2(ism, ds, s1);                 // min2 for the minimum edge, min1 otherwise (scaled)
     const __half2 sgn = H(lop_xor_and(par_s, U(c), H_SIGN));  // +-1: sign parity of the row without this edge
     const __half2 x   = __hfma2(sgn, mag, c);
-    // Promotion (LLR.cpp:74-87): |x| > 120 -> +-infinity (excess * x * 65504 overflows); infinite stays infinite.
-    const __half2 ex = __hmul2(__hfma2_relu(__habs2(x), one, hn120), x);
-    const __half2 r  = __hfma2(ex, H(H_BIG), x);
+    // Promotion (LLR.cpp:74-87): |x| > 120 -> +-infinity. pe = relu(544 |x| - 65280) is 0 up to |x| = 120 and at
+    // least 544 from 121 on, where x * pe + x exceeds the half-precision range; an infinite x stays infinite.
+    const __half2 pe = __hfma2_relu(__habs2(x), H(H_544), H(H_N65280));
+    const __half2 r  = __hfma2(x, pe, x);
     *reinterpret_cast<hh*>(soft + addr[e]) = U(r);
-    acc_s = __hfma2(acc_s, H(H_TWO), __hfma2_relu(sgn, neg1, H(H_ZERO)));
+    acc_s = __hfma2(acc_s, H(H_TWO), sgn); // sum of +-2^k; turned into "negative" bits when the group is packed
     acc_m = __hfma2(acc_m, H(H_TWO), ism);
     if ((e & 7) == 7 || e == DEG - 1) {
+      // acc_s = sum over the n edges of the group of sgn * 2^(n-1-k): negative-edge bits = ((2^n - 1) - acc_s) / 2.
       // Left-align a partial group, convert to integer bytes and pack {M B, S B, M A, S A}.
-      const int fill = 7 - (e & 7);
+      const int n_in_group = (e & 7) + 1;
+      const int fill       = 8 - n_in_group;
+      {
+        const float   full = (float)((1 << n_in_group) - 1) * 0.5f * (float)(1 << fill);
+        const __half2 sc   = H(0x38003800u + (uint32_t)fill * 0x04000400u); // 0.5 * 2^fill
+        acc_s              = __hfma2(acc_s, __hneg2(sc), __float2half2_rn(full));
+      }
       if (fill) {
         const __half2 sc = H(0x3C003C00u + (uint32_t)fill * 0x04000400u); // 2^fill
-        acc_s            = __hmul2(acc_s, sc);
         acc_m            = __hmul2(acc_m, sc);
       }
       st_word(st_out, F0 + (e >> 3)) =
@@ -196,8 +214,8 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint16_t*
 }
 
 __device__ __forceinline__ void dispatch_row(int deg, unsigned char* soft_addr, const uint16_t* e_shift,
-                                             const uint16_t* e_base, int j, int Z, const RowState& st, RowState& st_out,
-                                             int scale_mode)
+                                             const uint32_t* e_base, uint32_t j, uint32_t Z, const RowState& st,
+                                             RowState& st_out, int scale_mode)
 {
   // Most frequent degrees first (BG1: 18 rows of degree 5, 8 of degree 6, ...).
   if (deg == 5) {
@@ -377,8 +395,8 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       unsigned char* soft_addr = smem_raw;
 
       for (int i = tid; i < n_edges; i += nthr) {
-        g.shift[i] = (uint16_t)(c_tab.v[b][set][i] % Z); // ldpc_luts_impl.cpp:4536-4541
-        g.base[i]  = (uint16_t)(c_tab.col[b][i] * Z);
+        g.shift4[i] = (uint16_t)(4 * (c_tab.v[b][set][i] % Z)); // ldpc_luts_impl.cpp:4536-4541
+        g.base4[i]  = (uint32_t)(c_tab.col[b][i] * Z * 4);
       }
       for (int m = tid; m < rows; m += nthr) {
         g.row_info[m] = (uint32_t)c_tab.row_start[b][m] |
@@ -493,8 +511,10 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           st_thread[(uint32_t)m * st_stride] = make_uint4(0, 0, 0, 0);
         }
       }
-      RowState st_next = make_uint4(0, 0, 0, 0);
+      const uint32_t j4 = 4u * (uint32_t)j, Z4 = 4u * (uint32_t)Z;
+      RowState       st_next = make_uint4(0, 0, 0, 0);
       for (int it = 0; it < max_iter; ++it) {
+        uint4* sp = st_thread;
         for (int m = 0; m < layers; ++m) {
           if (active) {
             const uint32_t info   = g.row_info[m];
@@ -502,10 +522,11 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
             const int      deg    = info >> 16;
             const RowState st     = st_next;
             RowState       st_out = make_uint4(0, 0, 0, 0);
-            uint4* const   sp     = st_thread + (uint32_t)m * st_stride;
-            st_next               = (m + 1 < layers) ? sp[st_stride] : st_thread[0];
-            dispatch_row(deg, soft_addr, g.shift + e0, g.base + e0, j, Z, st, st_out, scale_mode);
+            uint4* const   spn    = (m + 1 < layers) ? sp + st_stride : st_thread;
+            st_next               = *spn;
+            dispatch_row(deg, soft_addr, g.shift4 + e0, g.base4 + e0, j4, Z4, st, st_out, scale_mode);
             *sp = st_out;
+            sp  = spn;
           }
           __syncthreads();
         }
