@@ -43,6 +43,14 @@ EDGES_46 = 316
 WORKLOAD = "bg1_z384_rate1/3_E25344_qpsk_rv0_6it_fixed"
 
 
+def profiled_traffic(kernel):
+    """DRAM bytes per launch of the named kernel from the committed ncu --set full capture (profiles/r1_traffic.json)."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    if p.exists():
+        return json.loads(p.read_text()).get(kernel)
+    return None
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -155,6 +163,68 @@ def run_reference_arm(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def slot_legs(ctx, orc, capi, torch, stream, args):
+    """Config 3 (one 100 MHz 273-PRB 256QAM 4-layer slot: TBS 1 277 992 bits, 152 codeblocks, E = 8960/8992, gNB-style
+    Nref) and config 4 (16 such cells in one batch), resident, including TB concatenation and TB CRC on the device."""
+    from srsran_edgeric_5g_b200 import ldpc
+    from tests.vectors import make_tb_llrs
+    rng = np.random.default_rng(3)
+    tbs_bits, n_llr, qm, nl = 1277992, 1362816, 8, 4
+    C = ldpc.compute_nof_codeblocks(tbs_bits, 1)
+    nref = ldpc.compute_N_ref(tbs_bits // 8, C)
+    tb = rng.integers(0, 256, tbs_bits // 8).astype(np.uint8)
+    llrs, _ = make_tb_llrs(orc, tb, 1, 0, qm, nref, nl, n_llr, 8.4, rng)
+    metas = ldpc.segment_rx(tbs_bits, 1, 0, qm, nref, nl, n_llr)
+    out = {}
+    for name, cells in (("config3_slot_1cell", 1), ("config4_slot_16cells", 16)):
+        n_cb = C * cells
+        if n_cb > ctx.cfg.max_cbs:
+            continue
+        for early in (True, False):
+            cbs = np.zeros(n_cb, capi.CB_DESC_DTYPE)
+            tbd = np.zeros(cells, capi.TB_DESC_DTYPE)
+            flags = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA | (capi.CB_EARLY_STOP if early else 0)
+            tb_stride = (tbs_bits + 24 + 31) // 32 * 4
+            for c in range(cells):
+                tbd[c] = (c * C, C, tbs_bits, c * tb_stride, 0)
+                for k, m in enumerate(metas):
+                    cbs[c * C + k] = (c * n_llr + m.cw_offset, m.rm_length, c * C + k, nref, m.lifting_size,
+                                      m.nof_filler_bits, 1, qm, 0, capi.CRC24B, MAX_ITER, flags, c)
+            d_cbs = torch.from_numpy(cbs.view(np.uint8)).cuda()
+            d_tbs = torch.from_numpy(tbd.view(np.uint8)).cuda()
+            d_llr = torch.from_numpy(np.tile(llrs, cells)).cuda()
+            d_res = torch.zeros(n_cb * 4, dtype=torch.uint8, device="cuda")
+            d_bits = torch.zeros(n_cb * capi.PDC_MAX_CB_BYTES, dtype=torch.uint8, device="cuda")
+            d_tres = torch.zeros(cells * 4, dtype=torch.uint8, device="cuda")
+            d_tb = torch.zeros(cells * tb_stride + 16, dtype=torch.uint8, device="cuda")
+
+            def step():
+                ctx.launch_device(d_cbs.data_ptr(), n_cb, d_llr.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), 384,
+                                  flags, True, cuda_stream=stream.cuda_stream, d_tbs=d_tbs.data_ptr(), n_tb=cells,
+                                  d_tb_results=d_tres.data_ptr(), d_tb_bytes=d_tb.data_ptr())
+
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            reps = 20
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                step()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / reps * 1e3
+            res = d_res.cpu().numpy().view(capi.CB_RESULT_DTYPE)
+            tres = d_tres.cpu().numpy().view(capi.TB_RESULT_DTYPE)
+            tb_ok = bool(tres["tb_crc_ok"].all())
+            tb_match = bool((d_tb.cpu().numpy()[:tbs_bits // 8] == tb).all()) if tb_ok else False
+            out[f"{name}_{'early_stop' if early else 'fixed6'}"] = {
+                "us_per_slot": us, "value": cells * tbs_bits / (us * 1e-6) / 1e9, "unit": UNIT, "codeblocks": n_cb,
+                "rows_per_cb": int(res["nlayers"].max()), "mean_iters": float(res["iters"].mean()),
+                "tb_crc_ok": tb_ok, "tb_bytes_match": tb_match, "snr_db": 8.4}
+    return out
 
 
 def main():
@@ -328,7 +398,7 @@ def main():
         peak_i8 = int_peak_both * 4.0
         line["roofline"] = {
             "kernel": "ldpc_decode", "bound": "int_issue", "achieved": ops / dec_s / 1e12, "peak": peak_i8 / 1e12,
-            "unit": "Tera int8-lane-op/s", "frac": ops / dec_s / peak_i8, "traffic": None,
+            "unit": "Tera int8-lane-op/s", "frac": ops / dec_s / peak_i8, "traffic": profiled_traffic("ldpc_decode"),
             "edge_updates_per_s": edge_updates / dec_s, "ms_per_launch": kt["ldpc_decode"],
             "share_of_step": kt["ldpc_decode"] / (kt["ldpc_decode"] + kt["rate_dematch"]),
             "peak_source": "pdc_measure_int_peak on this device: %.1f (ALU pipe) / %.1f (ALU+FMA pipes) Tera 32-bit "
@@ -338,7 +408,7 @@ def main():
         dm_s = kt["rate_dematch"] * 1e-3
         line["roofline_hbm"] = {
             "kernel": "rate_dematch", "bound": "hbm", "achieved": dm_bytes / dm_s / 1e9, "peak": pk["hbm_gbs"],
-            "unit": "GB/s", "frac": dm_bytes / dm_s / 1e9 / pk["hbm_gbs"], "traffic": None,
+            "unit": "GB/s", "frac": dm_bytes / dm_s / 1e9 / pk["hbm_gbs"], "traffic": profiled_traffic("rate_dematch"),
             "ms_per_launch": kt["rate_dematch"], "peak_source": pk_src,
         }
         if not args.no_extras:
@@ -347,12 +417,19 @@ def main():
             llrs_hi, _ = synth_batch(orc, 64, n_cb, args.snr + 2.0, 99)
             d_llrs.copy_(torch.from_numpy(llrs_hi.reshape(-1)))
             ms_es, _ = time_resident(d_es, max(3, args.steps // 2), 2) if world == 1 else (None, 0)
+            line["extra"] = {}
             if ms_es:
                 res = d_res.cpu().numpy().view(capi.CB_RESULT_DTYPE)
                 line["extra"] = {"early_stop_on": {
                     "value": n_cb * INFO_BITS / (ms_es / max(3, args.steps // 2) * 1e-3) / 1e9, "unit": UNIT,
                     "snr_db": args.snr + 2.0, "mean_iters": float(res["iters"].mean()),
                     "crc_ok_frac": float(res["crc_ok"].mean())}}
+            # ---- config 3 / config 4 of BASELINE.json: 273-PRB 4-layer 256QAM slots (152 codeblocks, 4 rows each) -----------
+            # (a fresh context: the reference semantics leave regions of a reused HARQ entry stale)
+            ctx2 = capi.Context(device=local_rank, max_cbs=2432, max_llrs=1 << 20, harq_entries=2432, max_tbs=16,
+                                max_tb_bytes=16 * 160000, nof_streams=1)
+            line["extra"].update(slot_legs(ctx2, orc, capi, torch, stream, args))
+            ctx2.close()
             # ---- CPU baseline: the reference's own SIMD code on the host cores, bounded sample ---------------------------
             line["cpu_baseline"] = cpu_reference_rate(llrs_np[:2048], False, 12.0, os.cpu_count() or 1)
         print(json.dumps(line))

@@ -81,6 +81,41 @@ __device__ __forceinline__ hh st_word(const RowState& s, int k)
   return (k == 0) ? s.x : (k == 1) ? s.y : (k == 2) ? s.z : s.w;
 }
 
+// The row state is re-read every iteration and must stay in L2 while LLR batches stream through it: its accesses carry
+// an evict-last policy, the soft-bit input an evict-first one.
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ld_state(const uint4* p, uint64_t pol)
+{
+  uint4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_state(uint4* p, const uint4& v, uint64_t pol)
+{
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p, uint64_t pol)
+{
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 // The lifted graph of this (base graph, Z) in shared memory.
 struct GraphSmem {
   uint32_t base4[MAX_EDGES];     // byte offset of the first soft word of the edge's variable node (col * Z * 4)
@@ -409,7 +444,8 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         for (int h = 0; h != 2; ++h) {
           in[h] = lane[h].valid ? prm.harq + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_SOFT : nullptr;
         }
-        int last[2] = {0, 0};
+        int            last[2]    = {0, 0};
+        const uint64_t pol_stream = l2_policy_evict_first();
         // Punctured nodes.
         for (int i = tid; i < 2 * Z; i += nthr) {
           soft[i] = 0;
@@ -420,7 +456,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           uint32_t w4[2];
 #pragma unroll
           for (int h = 0; h != 2; ++h) {
-            w4[h] = in[h] ? __ldg(reinterpret_cast<const uint32_t*>(in[h]) + q) : 0u;
+            w4[h] = in[h] ? ld_stream_u32(reinterpret_cast<const uint32_t*>(in[h]) + q, pol_stream) : 0u;
           }
 #pragma unroll
           for (int k = 0; k != 4; ++k) {
@@ -505,10 +541,11 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
 
       // Compressed messages: one uint4 per (row, check), only ever touched by thread j. They start at zero ("no message
       // yet") and the next row is fetched while the current one is processed.
-      uint4* const st_thread = st_base + j;
+      uint4* const   st_thread = st_base + j;
+      const uint64_t pol_keep  = l2_policy_evict_last();
       if (active) {
         for (int m = 0; m < layers; ++m) {
-          st_thread[(uint32_t)m * st_stride] = make_uint4(0, 0, 0, 0);
+          st_state(st_thread + (uint32_t)m * st_stride, make_uint4(0, 0, 0, 0), pol_keep);
         }
       }
       const uint32_t j4 = 4u * (uint32_t)j, Z4 = 4u * (uint32_t)Z;
@@ -523,10 +560,10 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
             const RowState st     = st_next;
             RowState       st_out = make_uint4(0, 0, 0, 0);
             uint4* const   spn    = (m + 1 < layers) ? sp + st_stride : st_thread;
-            st_next               = *spn;
+            st_next               = ld_state(spn, pol_keep);
             dispatch_row(deg, soft_addr, g.shift4 + e0, g.base4 + e0, j4, Z4, st, st_out, scale_mode);
-            *sp = st_out;
-            sp  = spn;
+            st_state(sp, st_out, pol_keep);
+            sp = spn;
           }
           __syncthreads();
         }

@@ -152,3 +152,75 @@ def test_harq_retransmissions_cb_level(ctx, orc):
         out = b.run_gpu(ctx, 6, True, new_data=(t == 0), harq_base=300, harq_init=None)
         ref = b.run_oracle(orc, 6, True, new_data=(t == 0), harq=harq_o)
         _assert_same(out, ref, f"retx {t}")
+
+
+def test_mixed_batch_pairs_and_lone_codeblocks(ctx, orc):
+    # One batch mixing lifting sizes, base graphs, iteration counts and an odd number of codeblocks: consecutive
+    # codeblocks that cannot share a CTA pair are decoded one after the other; results must not depend on the pairing.
+    from srsran_edgeric_5g_b200 import capi
+    rng = np.random.default_rng(31)
+    shapes = [(1, 384, 30 * 384, 6), (1, 384, 30 * 384, 6), (1, 384, 30 * 384, 4), (2, 384, 20 * 384, 6),
+              (1, 96, 40 * 96, 6), (1, 96, 26 * 96, 6), (2, 15, 30 * 15 + 2, 5), (1, 384, 66 * 384, 6),
+              (1, 384, 66 * 384, 6), (2, 7, 30 * 7 + 4, 6), (1, 208, 33 * 208, 6)]
+    batches = [make_cb_batch(orc, bg, Z, 1, E - E % 2, 2, 0, float(rng.uniform(1, 6)), 500 + i, nof_filler=i % 3)
+               for i, (bg, Z, E, mi) in enumerate(shapes)]
+    n = len(batches)
+    cbs = np.zeros(n, capi.CB_DESC_DTYPE)
+    off = 0
+    llrs = []
+    for i, (b, (bg, Z, E, mi)) in enumerate(zip(batches, shapes)):
+        flags = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA | (capi.CB_EARLY_STOP if i % 2 == 0 else 0)
+        cbs[i] = (off, b.E, 700 + i, 0, Z, b.nof_filler, bg, 2, 0, b.crc_kind, mi, flags, 0xffff)
+        ctx.harq_write(700 + i, np.zeros(b.N, np.int8))
+        llrs.append(b.llrs[0])
+        off += b.E
+    ctx.submit(cbs, np.concatenate(llrs), None, stream=0, want_bits=True)
+    out = ctx.wait(0)
+    for i, (b, (bg, Z, E, mi)) in enumerate(zip(batches, shapes)):
+        ref = b.run_oracle(orc, mi, i % 2 == 0)
+        r = out["cb_results"][i]
+        assert bool(r["crc_ok"]) == bool(ref["crc_ok"][0]) and r["iters"] == ref["iters"][0], (i, r, ref["iters"])
+        assert (out["cb_bits"][i, :(b.K + 7) // 8] == ref["bits"][0]).all(), i
+        assert (ctx.harq_read(700 + i, b.N) == ref["harq"][0]).all(), i
+
+
+def test_pair_with_different_rows_in_use(ctx, orc):
+    # Same shape, but the second codeblock ends in zero LLRs that span a whole node: the reference trims them and uses
+    # fewer base-graph rows (ldpc_decoder_impl.cpp:86-114), so the pair cannot be decoded in lock step.
+    b = make_cb_batch(orc, 1, 64, n_cb=4, E=40 * 64, qm=2, rv=0, snr_db=2.5, seed=77)
+    b.llrs[1, -130:] = 0
+    b.llrs[2, -1:] = 0
+    out = b.run_gpu(ctx, 6, True, harq_base=800)
+    ref = b.run_oracle(orc, 6, True)
+    _assert_same(out, ref, "unequal rows")
+    assert out["nlayers"][0] != out["nlayers"][1]
+
+
+def test_all_zero_and_dematch_only(ctx, orc):
+    from srsran_edgeric_5g_b200 import capi
+    b = make_cb_batch(orc, 2, 32, n_cb=3, E=20 * 32, qm=2, rv=0, snr_db=3.0, seed=5, crc_kind=po.CRC16)
+    b.llrs[1] = 0  # all-zero input: not decodable
+    cbs = b.descriptors(capi, 6, True, True, harq_base=900)
+    cbs["flags"][2] = int(cbs["flags"][2]) & (0xff ^ capi.CB_DECODE)  # dematch / combine only
+    for i in range(3):
+        ctx.harq_write(900 + i, np.zeros(b.N, np.int8))
+    ctx.submit(cbs, np.ascontiguousarray(b.llrs.reshape(-1)), None, stream=0, want_bits=True)
+    out = ctx.wait(0)
+    ref = b.run_oracle(orc, 6, True)
+    r = out["cb_results"]
+    assert r["status"][1] == 1 and r["crc_ok"][1] == 0 and r["iters"][1] == 6
+    assert bool(r["crc_ok"][0]) == bool(ref["crc_ok"][0]) and r["iters"][0] == ref["iters"][0]
+    assert r["iters"][2] == 0 and r["crc_ok"][2] == 0  # not decoded
+    assert (ctx.harq_read(902, b.N) == ref["harq"][2]).all()
+
+
+def test_general_kernel_forced(orc, monkeypatch):
+    # PDC_FORCE_SCALAR=1 routes every batch through the general kernel: both kernels must agree with the oracle.
+    from srsran_edgeric_5g_b200 import capi
+    monkeypatch.setenv("PDC_FORCE_SCALAR", "1")
+    c = capi.Context(device=0, max_cbs=64, harq_entries=64, max_tbs=1, max_tb_bytes=4096)
+    monkeypatch.delenv("PDC_FORCE_SCALAR")
+    for bg, Z, E in ((1, 384, 30 * 384), (2, 36, 40 * 36), (1, 11, 50 * 11 + 1)):
+        b = make_cb_batch(orc, bg, Z, n_cb=5, E=E - E % 2, qm=2, rv=0, snr_db=3.0, seed=Z)
+        _assert_same(b.run_gpu(c, 6, True), b.run_oracle(orc, 6, True), f"general kernel BG{bg} Z={Z}")
+    c.close()
