@@ -4,34 +4,39 @@
 // (lib/phy/upper/channel_processors/pusch/pusch_decoder_impl.cpp:384-450, :452-497): with one codeblock the TB CRC is the
 // codeblock CRC; with several, and only if every codeblock CRC passed, the payloads (without CB CRC, filler and zero
 // padding) are concatenated and CRC24A over the TB must equal the 24 bits that follow the payload of the last codeblock.
+//
+// One CTA per transport block. The concatenated stream (payload + TB checksum) is produced 32 bits per thread with a
+// funnel shift from at most two codeblocks; each thread then runs a table-driven CRC24A over its run of consecutive words
+// and weights it by x^(32 * words after the run) mod P; the XOR of all weighted remainders is zero iff the CRC matches.
 #pragma once
 
 #include "pdc_device.cuh"
 
 namespace pdc {
 
-// x^(32 * 2^i) mod CRC24A, i = 0..19, filled at start-up.
-__constant__ uint32_t c_xpow_crc24a_pow2[20];
+constexpr int TB_THREADS = 1024;
 
-__device__ __forceinline__ uint32_t tb_stream_byte(const uint8_t* __restrict__ data, const pdc_cb_desc* cbs,
-                                                   uint32_t first_cb, uint32_t n_data, uint32_t q)
+// x^(32 * 2^i) mod CRC24A, i = 0..19, and the byte table T[b] = (b * x^24) mod P; filled at start-up.
+__constant__ uint32_t c_xpow_crc24a_pow2[20];
+__constant__ uint32_t c_crc24a_table[256];
+
+// 32 bits of a codeblock's decoded message starting at bit `off` (MSB first), zero beyond the buffer.
+__device__ __forceinline__ uint32_t cb_bits32(const uint8_t* __restrict__ src, uint32_t off)
 {
-  // 8 bits of the concatenated stream starting at bit q.
-  uint32_t v = 0;
-#pragma unroll
-  for (int k = 0; k != 8; ++k) {
-    uint32_t        qq  = q + k;
-    uint32_t        cb  = qq / n_data;
-    uint32_t        off = qq - cb * n_data;
-    const uint8_t*  src = data + (size_t)cbs[first_cb + cb].harq_id * PDC_MAX_CB_BYTES;
-    v                   = (v << 1) | ((src[off >> 3] >> (7 - (off & 7))) & 1u);
+  const uint32_t* w  = reinterpret_cast<const uint32_t*>(src);
+  uint32_t        i  = off >> 5, sh = off & 31u;
+  uint32_t        hi = __byte_perm(w[i], 0, 0x0123); // bytes in memory are MSB first
+  if (sh == 0) {
+    return hi;
   }
-  return v;
+  uint32_t lo = (i + 1 < PDC_MAX_CB_BYTES / 4) ? __byte_perm(w[i + 1], 0, 0x0123) : 0u;
+  return __funnelshift_l(lo, hi, sh);
 }
 
-__global__ void __launch_bounds__(256) tb_assemble_kernel(TbParams prm, const uint8_t* harq_data)
+__global__ void __launch_bounds__(TB_THREADS) tb_assemble_kernel(TbParams prm, const uint8_t* harq_data)
 {
   __shared__ uint32_t sh_crc;
+  __shared__ uint32_t sh_table[256];
   const pdc_tb_desc&  tb  = prm.tbs[blockIdx.x];
   const int           tid = threadIdx.x;
   int                 ok  = 1;
@@ -41,14 +46,17 @@ __global__ void __launch_bounds__(256) tb_assemble_kernel(TbParams prm, const ui
       ok = 0;
     }
   }
+  if (tid < 256) {
+    sh_table[tid] = c_crc24a_table[tid];
+  }
   if (tid == 0) {
     sh_crc = 0;
   }
   ok = __syncthreads_and(ok);
   pdc_tb_result r;
-  r.tb_crc_ok = 0;
-  r.all_cb_ok = (uint8_t)ok;
-  r.reserved  = 0;
+  r.tb_crc_ok  = 0;
+  r.all_cb_ok  = (uint8_t)ok;
+  r.reserved   = 0;
   uint8_t* out = prm.tb_bytes + tb.out_offset;
   if (ok && tb.nof_cb == 1) {
     const uint8_t* src = harq_data + (size_t)prm.cbs[tb.first_cb].harq_id * PDC_MAX_CB_BYTES;
@@ -64,34 +72,60 @@ __global__ void __launch_bounds__(256) tb_assemble_kernel(TbParams prm, const ui
     const uint32_t     T      = (total + 31u) / 32u;
     uint32_t*          out_w  = reinterpret_cast<uint32_t*>(out);
     const uint32_t     poly   = crc_poly(PDC_CRC24A);
-    uint32_t           acc    = 0;
-    for (uint32_t t = tid; t < T; t += blockDim.x) {
-      uint32_t w = 0;
+    // Thread t owns words [t * per, min(T, (t + 1) * per)).
+    const uint32_t per   = (T + blockDim.x - 1) / blockDim.x;
+    const uint32_t first = tid * per;
+    const uint32_t last  = min(T, first + per);
+    uint32_t       crc   = 0;
+    if (first < T) {
+      uint32_t q   = 32u * first;
+      uint32_t cb  = q / n_data;
+      uint32_t off = q - cb * n_data;
+      for (uint32_t t = first; t < last; ++t) {
+        const uint8_t* src = harq_data + (size_t)prm.cbs[tb.first_cb + cb].harq_id * PDC_MAX_CB_BYTES;
+        uint32_t       w   = cb_bits32(src, off);
+        uint32_t       rem = n_data - off; // bits left in this codeblock
+        if (rem < 32u) {
+          // The word continues in the next codeblock (the last codeblock never runs out before `total`).
+          w &= 0xffffffffu << (32u - rem);
+          if (cb + 1 < tb.nof_cb) {
+            const uint8_t* nxt = harq_data + (size_t)prm.cbs[tb.first_cb + cb + 1].harq_id * PDC_MAX_CB_BYTES;
+            w |= cb_bits32(nxt, 0) >> rem;
+          }
+          cb += 1;
+          off = 32u - rem;
+        } else {
+          off += 32u;
+          if (off == n_data) {
+            cb += 1;
+            off = 0;
+          }
+        }
+        if (t == T - 1 && (total & 31u)) {
+          w &= 0xffffffffu << (32u - (total & 31u));
+        }
+        out_w[t] = __byte_perm(w, 0, 0x0123); // big-endian bit order -> byte order in memory
 #pragma unroll
-      for (int k = 0; k != 4; ++k) {
-        uint32_t q = 32u * t + 8u * k;
-        uint32_t b = (q < total) ? tb_stream_byte(harq_data, prm.cbs, tb.first_cb, n_data, q) : 0u;
-        w          = (w << 8) | b;
+        for (int k = 3; k >= 0; --k) {
+          uint32_t byte = (w >> (8 * k)) & 0xffu;
+          crc           = ((crc << 8) ^ sh_table[((crc >> 16) ^ byte) & 0xffu]) & 0xffffffu;
+        }
       }
-      if (t == T - 1 && (total & 31u)) {
-        w &= 0xffffffffu << (32u - (total & 31u));
-      }
-      out_w[t] = __byte_perm(w, 0, 0x0123); // big-endian bit order -> byte order in memory
-      // x^(32 (T-1-t)) mod P by square-and-multiply over the precomputed x^(32 2^i).
-      uint32_t e  = T - 1 - t;
+      // Weight by x^(32 * words after this run) mod P (square-and-multiply over the precomputed x^(32 2^i)).
+      uint32_t e  = T - last;
       uint32_t xp = 1;
       for (int i = 0; e != 0; ++i, e >>= 1) {
         if (e & 1u) {
           xp = gf2_mulmod(xp, c_xpow_crc24a_pow2[i], poly, 24);
         }
       }
-      acc ^= gf2_mulmod(w, xp, poly, 24);
+      crc = gf2_mulmod(crc, xp, poly, 24);
     }
     for (int o = 16; o > 0; o >>= 1) {
-      acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+      crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
     }
-    if ((tid & 31) == 0 && acc) {
-      atomicXor(&sh_crc, acc);
+    if ((tid & 31) == 0 && crc) {
+      atomicXor(&sh_crc, crc);
     }
     __syncthreads();
     r.tb_crc_ok = (sh_crc == 0) ? 1 : 0;
@@ -116,7 +150,22 @@ inline cudaError_t upload_tb_tables()
     h[i] = x;
     x    = gf2_mulmod(x, x, poly, 24);
   }
-  return cudaMemcpyToSymbol(c_xpow_crc24a_pow2, h, sizeof(h));
+  cudaError_t e = cudaMemcpyToSymbol(c_xpow_crc24a_pow2, h, sizeof(h));
+  if (e != cudaSuccess) {
+    return e;
+  }
+  uint32_t table[256];
+  for (uint32_t b = 0; b != 256; ++b) {
+    uint32_t v = b << 16;
+    for (int k = 0; k != 8; ++k) {
+      v <<= 1;
+      if (v & (1u << 24)) {
+        v ^= poly;
+      }
+    }
+    table[b] = v & 0xffffffu;
+  }
+  return cudaMemcpyToSymbol(c_crc24a_table, table, sizeof(table));
 }
 
 inline cudaError_t launch_tb_assemble(const TbParams& p, const uint8_t* harq_data, cudaStream_t s)
@@ -124,7 +173,7 @@ inline cudaError_t launch_tb_assemble(const TbParams& p, const uint8_t* harq_dat
   if (p.n_tb == 0) {
     return cudaSuccess;
   }
-  tb_assemble_kernel<<<p.n_tb, 256, 0, s>>>(p, harq_data);
+  tb_assemble_kernel<<<p.n_tb, TB_THREADS, 0, s>>>(p, harq_data);
   return cudaGetLastError();
 }
 
