@@ -236,6 +236,7 @@ def main():
     ap.add_argument("--n-cb", type=int, default=8192, help="codeblocks per GPU per step")
     ap.add_argument("--snr", type=float, default=-1.0, help="AWGN SNR (dB) of the synthetic LLRs")
     ap.add_argument("--no-extras", action="store_true", help="skip the early-stop / config-3 / cpu legs")
+    ap.add_argument("--only-slots", action="store_true", help="profiling aid: run only the config-3/4 slot legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
 
@@ -259,6 +260,12 @@ def main():
     from srsran_edgeric_5g_b200 import capi
 
     orc = Oracle()
+    if args.only_slots:
+        ctx2 = capi.Context(device=local_rank, max_cbs=2432, max_llrs=1 << 20, harq_entries=2432, max_tbs=16,
+                            max_tb_bytes=16 * 160000, nof_streams=1)
+        print(json.dumps(slot_legs(ctx2, orc, capi, torch, torch.cuda.current_stream(), args)))
+        ctx2.close()
+        return
     n_cb = args.n_cb
     ctx = capi.Context(device=local_rank, max_cbs=n_cb, max_llrs=n_cb * N_SOFT, harq_entries=n_cb, max_tbs=1,
                        max_tb_bytes=4096, nof_streams=2)

@@ -288,7 +288,7 @@ __host__ __device__ inline size_t h2_smem_bytes(int bg, int Z)
   int    n_full = (bg == 1) ? 68 : 52;
   int    kb     = (bg == 1) ? 22 : 10;
   size_t soft   = (size_t)n_full * Z * 4;
-  size_t bits   = 2 * ((size_t)((kb * Z + 31) / 32) * 4 + 16);
+  size_t bits   = 4 * ((size_t)((kb * Z + 31) / 32) * 4 + 16); // hard bits + CRC weights of both codeblocks
   return soft + bits + sizeof(GraphSmem) + 64;
 }
 
@@ -311,7 +311,9 @@ __device__ __forceinline__ int hard_bits(const hh* soft, int half, int K, uint32
   return any_zero;
 }
 
-__device__ __forceinline__ uint32_t crc_partial(const uint32_t* bits, int nb, int crc_kind, int tid, int nthr)
+// wgt[t] = x^(32 (T-1-t)) mod P, staged in shared memory (a divergent constant-memory index would serialise the warp).
+__device__ __forceinline__ uint32_t crc_partial(const uint32_t* bits, const uint32_t* wgt, int nb, int crc_kind, int tid,
+                                                int nthr)
 {
   const int      T     = (nb + 31) / 32;
   const uint32_t poly  = crc_poly(crc_kind);
@@ -322,7 +324,7 @@ __device__ __forceinline__ uint32_t crc_partial(const uint32_t* bits, int nb, in
     if (t == T - 1 && (nb & 31)) {
       w &= 0xffffffffu << (32 - (nb & 31));
     }
-    acc ^= gf2_mulmod(w, c_tab.xpow32[crc_kind - 1][T - 1 - t], poly, order);
+    acc ^= gf2_mulmod(w, wgt[t], poly, order);
   }
   for (int o = 16; o > 0; o >>= 1) {
     acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
@@ -337,7 +339,8 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ LaneInfo lane[2];
   __shared__ int      sh_last[2];
-  __shared__ uint32_t sh_crc[2];
+  __shared__ uint32_t           sh_crc[2];
+  __shared__ unsigned long long sh_acc[2];
   __shared__ int      sh_any_zero[2];
   __shared__ int      sh_defer_b; // codeblock B could not be decoded together with A: it gets its own pass
 
@@ -422,6 +425,11 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       off += (size_t)n_words * 4 + 16;
       bits[1] = reinterpret_cast<uint32_t*>(smem_raw + off);
       off += (size_t)n_words * 4 + 16;
+      uint32_t* wgt[2]; // CRC word weights of each codeblock
+      wgt[0] = reinterpret_cast<uint32_t*>(smem_raw + off);
+      off += (size_t)n_words * 4 + 16;
+      wgt[1] = reinterpret_cast<uint32_t*>(smem_raw + off);
+      off += (size_t)n_words * 4 + 16;
       GraphSmem& g = *reinterpret_cast<GraphSmem*>(smem_raw + off);
 
       // Compressed messages: one uint4 per (row, check), private to thread j.
@@ -433,58 +441,52 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         g.shift4[i] = (uint16_t)(4 * (c_tab.v[b][set][i] % Z)); // ldpc_luts_impl.cpp:4536-4541
         g.base4[i]  = (uint32_t)(c_tab.col[b][i] * Z * 4);
       }
+      for (int h = 0; h != 2; ++h) {
+        if (lane[h].valid && lane[h].crc_kind != PDC_CRC_NONE) {
+          const int T = (K - lane[h].F + 31) / 32;
+          for (int t = tid; t < T; t += nthr) {
+            wgt[h][t] = c_tab.xpow32[lane[h].crc_kind - 1][T - 1 - t];
+          }
+        }
+      }
       for (int m = tid; m < rows; m += nthr) {
         g.row_info[m] = (uint32_t)c_tab.row_start[b][m] |
                         ((uint32_t)(c_tab.row_start[b][m + 1] - c_tab.row_start[b][m]) << 16);
       }
-      // load_soft_bits (ldpc_decoder_impl.cpp:149-184): two punctured nodes at zero, whole nodes clamped to +-64.
-      // Also finds the last non-zero input of each codeblock (:86-99).
-      {
-        const int8_t* in[2];
-        for (int h = 0; h != 2; ++h) {
-          in[h] = lane[h].valid ? prm.harq + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_SOFT : nullptr;
-        }
-        int            last[2]    = {0, 0};
-        const uint64_t pol_stream = l2_policy_evict_first();
-        // Punctured nodes.
-        for (int i = tid; i < 2 * Z; i += nthr) {
-          soft[i] = 0;
-        }
-        // Four soft bits of each codeblock per thread and step (the HARQ entries are 16-byte aligned).
-        const int n4 = (N + 3) >> 2;
-        for (int q = tid; q < n4; q += nthr) {
-          uint32_t w4[2];
+      // Last non-zero input of each codeblock (ldpc_decoder_impl.cpp:86-99): recorded by the rate dematcher for the
+      // entries it wrote; entries of unknown content are scanned.
+      const int8_t* in[2];
+      for (int h = 0; h != 2; ++h) {
+        in[h] = lane[h].valid ? prm.harq + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_SOFT : nullptr;
+      }
+      const uint64_t pol_stream = l2_policy_evict_first();
 #pragma unroll
-          for (int h = 0; h != 2; ++h) {
-            w4[h] = in[h] ? ld_stream_u32(reinterpret_cast<const uint32_t*>(in[h]) + q, pol_stream) : 0u;
+      for (int h = 0; h != 2; ++h) {
+        if (in[h] == nullptr) {
+          continue;
+        }
+        const int known = prm.harq_last[prm.cbs[lane[h].cb].harq_id];
+        if (known >= 0) {
+          if (tid == 0) {
+            sh_last[h] = min(known, N);
           }
+          continue;
+        }
+        int last = 0;
+        for (int q = tid; q < ((N + 3) >> 2); q += nthr) {
+          const uint32_t w4 = ld_stream_u32(reinterpret_cast<const uint32_t*>(in[h]) + q, pol_stream);
 #pragma unroll
           for (int k = 0; k != 4; ++k) {
-            const int pos = 4 * q + k;
-            hh        w   = 0;
-#pragma unroll
-            for (int h = 0; h != 2; ++h) {
-              int v = (int)(int8_t)(w4[h] >> (8 * k));
-              if (v != 0 && pos < N) {
-                last[h] = pos + 1;
-              }
-              v = max(-CLAMP_IN, min(CLAMP_IN, v));
-              w |= (hh)__half_as_ushort(__int2half_rn(v)) << (16 * h);
-            }
-            if (pos < N) {
-              soft[2 * Z + pos] = w;
+            if (((w4 >> (8 * k)) & 0xffu) != 0 && 4 * q + k < N) {
+              last = max(last, 4 * q + k + 1);
             }
           }
         }
-#pragma unroll
-        for (int h = 0; h != 2; ++h) {
-          int l = last[h];
-          for (int o = 16; o > 0; o >>= 1) {
-            l = max(l, __shfl_xor_sync(0xffffffffu, l, o));
-          }
-          if ((tid & 31) == 0 && l > 0) {
-            atomicMax(&sh_last[h], l);
-          }
+        for (int o = 16; o > 0; o >>= 1) {
+          last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        }
+        if ((tid & 31) == 0 && last > 0) {
+          atomicMax(&sh_last[h], last);
         }
       }
       __syncthreads();
@@ -513,6 +515,39 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         }
       }
       __syncthreads();
+      // load_soft_bits (ldpc_decoder_impl.cpp:149-184): two punctured nodes at zero, whole nodes clamped to +-64; only
+      // the variable nodes of the rows in use are needed. int8 -> half through the 1024 binade: 0x6400 | (v + 128) is
+      // the half 1024 + v + 128.
+      {
+        const int n_rows = max(lane[0].valid ? lane[0].layers : 0, lane[1].valid ? lane[1].layers : 0);
+        const int n_load = min(N, (kb + n_rows - 2) * Z);
+        for (int i = tid; i < 2 * Z; i += nthr) {
+          soft[i] = 0;
+        }
+        const uint32_t* src[2];
+        for (int h = 0; h != 2; ++h) {
+          src[h] = lane[h].valid ? reinterpret_cast<const uint32_t*>(in[h]) : nullptr;
+        }
+        const __half2 h64 = H(0x54005400u), hn64 = H(0xD400D400u), hn1152 = H(0xE480E480u);
+#pragma unroll 2
+        for (int q = tid; q < ((n_load + 3) >> 2); q += nthr) {
+          const uint32_t wa = src[0] ? ld_stream_u32(src[0] + q, pol_stream) : 0u;
+          const uint32_t wb = src[1] ? ld_stream_u32(src[1] + q, pol_stream) : 0u;
+#pragma unroll
+          for (int k = 0; k != 4; ++k) {
+            // bytes {A_k, A_k, B_k, B_k} -> halves {0x64 : A_k ^ 0x80, 0x64 : B_k ^ 0x80}
+            uint32_t t = __byte_perm(wa, wb, (uint32_t)(k | (k << 4) | ((4 + k) << 8) | ((4 + k) << 12)));
+            uint32_t u;
+            asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(u) : "r"(t), "r"(0x00ff00ffu), "r"(0x64806480u));
+            __half2 v = __hadd2(H(u), hn1152);
+            v         = __hmax2(__hmin2(v, h64), hn64);
+            if (4 * q + k < n_load) {
+              soft[2 * Z + 4 * q + k] = U(v);
+            }
+          }
+        }
+      }
+      __syncthreads();
       // All-zero codeblocks without a CRC calculator output all ones.
       for (int h = 0; h != 2; ++h) {
         if (lane[h].done == 2 && lane[h].crc_kind == PDC_CRC_NONE) {
@@ -525,13 +560,6 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       }
       if (!lane[0].valid && !lane[1].valid) {
         continue;
-      }
-      if (pass == 0 && sh_defer_b == 2) {
-        // B's half holds its inputs but B is not decoded in this pass: clear it so that A computes next to zeros.
-        for (int i = tid; i < n_full * Z; i += nthr) {
-          soft[i] &= 0x0000ffffu;
-        }
-        __syncthreads();
       }
       const int  layers     = lane[lane[0].valid ? 0 : 1].layers;
       const int  max_iter   = lane[lead].max_iter;
@@ -573,29 +601,74 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
                                (lane[1].valid && lane[1].early && !lane[1].done);
         if (any_early || last_it) {
           if (tid < 2) {
-            sh_crc[tid]      = 0;
+            sh_acc[tid]      = 0ull;
             sh_any_zero[tid] = 0;
           }
-          __syncthreads();
-          for (int h = 0; h != 2; ++h) {
-            if (!lane[h].valid || lane[h].done || !(lane[h].early || last_it)) {
-              continue;
+          // get_hard_bits (:126-134) of both codeblocks in one sweep: bit = soft <= 0, MSB first; a zero among the K
+          // message soft bits blocks the early stop.
+          {
+            int za = 0, zb = 0;
+#pragma unroll 4
+            for (int w = tid >> 5; w < n_words; w += nthr >> 5) {
+              const int      i  = 32 * w + (tid & 31);
+              const uint32_t sw = (i < K) ? soft[i] : 0x3C003C00u;
+              const bool     z0 = (sw & 0x7fffu) == 0, z1 = (sw & 0x7fff0000u) == 0;
+              const uint32_t b0 = __brev(__ballot_sync(0xffffffffu, z0 || (sw & 0x8000u)));
+              const uint32_t b1 = __brev(__ballot_sync(0xffffffffu, z1 || (sw & 0x80000000u)));
+              za |= z0;
+              zb |= z1;
+              if ((tid & 31) == 0) {
+                bits[0][w] = b0;
+                bits[1][w] = b1;
+              }
             }
-            // get_hard_bits (:126-134): bit = soft <= 0, MSB first; a zero among the K message soft bits blocks the
-            // early stop.
-            if (hard_bits(soft, h, K, bits[h], tid, nthr)) {
-              sh_any_zero[h] = 1;
+            if (za) {
+              sh_any_zero[0] = 1;
+            }
+            if (zb) {
+              sh_any_zero[1] = 1;
             }
           }
           __syncthreads();
+          // CRC as M(x) mod P == 0 with M(x) = sum_t W_t(x) x^(32 (T-1-t)): every thread forms the UNREDUCED carry-less
+          // product of its word with its weight (independent steps), the products are XOR-reduced, and only the sum is
+          // reduced modulo P.
           for (int h = 0; h != 2; ++h) {
             if (!lane[h].valid || lane[h].done || !(lane[h].early || last_it) || lane[h].crc_kind == PDC_CRC_NONE) {
               continue;
             }
-            uint32_t acc = crc_partial(bits[h], K - lane[h].F, lane[h].crc_kind, tid, nthr);
-            if ((tid & 31) == 0 && acc) {
-              atomicXor(&sh_crc[h], acc);
+            const int nb = K - lane[h].F;
+            const int T  = (nb + 31) / 32;
+            uint64_t  acc = 0;
+            for (int t = tid; t < T; t += nthr) {
+              uint32_t w = bits[h][t];
+              if (t == T - 1 && (nb & 31)) {
+                w &= 0xffffffffu << (32 - (nb & 31));
+              }
+              const uint64_t a = wgt[h][t];
+#pragma unroll
+              for (int i = 0; i != 32; ++i) {
+                acc ^= (a << i) & (0ull - (uint64_t)((w >> i) & 1u));
+              }
             }
+            for (int o = 16; o > 0; o >>= 1) {
+              acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+            }
+            if ((tid & 31) == 0 && acc) {
+              atomicXor(&sh_acc[h], (unsigned long long)acc);
+            }
+          }
+          __syncthreads();
+          if (tid < 2 && lane[tid].valid && lane[tid].crc_kind != PDC_CRC_NONE) {
+            const uint64_t poly  = crc_poly(lane[tid].crc_kind);
+            const int      order = crc_order(lane[tid].crc_kind);
+            uint64_t       v     = sh_acc[tid];
+            for (int bit = 55; bit >= order; --bit) {
+              if ((v >> bit) & 1ull) {
+                v ^= poly << (bit - order);
+              }
+            }
+            sh_crc[tid] = (uint32_t)v;
           }
           __syncthreads();
           // Publish finished codeblocks while their bits are in shared memory.

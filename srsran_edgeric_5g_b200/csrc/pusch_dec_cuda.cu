@@ -49,6 +49,7 @@ struct Queue {
   uint8_t*       d_cb_bits = nullptr;
   pdc_tb_result* d_tb_res  = nullptr;
   uint8_t*       d_tb_out  = nullptr;
+  uint32_t*      d_tb_sync = nullptr; // {CRC accumulator, arrival counter} per TB for the TB assembly kernel
   // Pinned host mirrors.
   pdc_cb_desc*   h_cbs     = nullptr;
   pdc_tb_desc*   h_tbs     = nullptr;
@@ -74,6 +75,9 @@ struct pdc_ctx {
   int                  sm_count = 0, cc_major = 0, cc_minor = 0;
   int8_t*              d_harq      = nullptr; // (harq_entries + 1) x PDC_MAX_CB_SOFT; the extra entry is scratch
   uint8_t*             d_harq_data = nullptr; // (harq_entries + 1) x PDC_MAX_CB_BYTES
+  uint32_t*            d_tb_sync = nullptr;   // per TB {CRC accumulator, arrival counter} of the TB assembly kernel
+  uint32_t             tb_sync_entries = 0;
+  int32_t*             d_harq_last = nullptr; // (harq_entries + 1): last non-zero soft bit of each entry (+1), -1 unknown
   int8_t*              d_scratch_llr = nullptr;
   size_t               scratch_llr_bytes = 0;
   std::vector<Queue>   queues;
@@ -122,7 +126,8 @@ int launch_batch(pdc_ctx*             ctx,
                  const BatchShape&    shape,
                  const int8_t*        direct_in,
                  uint32_t             direct_n,
-                 cudaStream_t         s)
+                 cudaStream_t         s,
+                 uint32_t*            tb_sync = nullptr)
 {
   pdc::BatchParams p;
   p.cbs          = d_cbs;
@@ -133,6 +138,7 @@ int launch_batch(pdc_ctx*             ctx,
   p.results      = d_cb_res;
   p.cb_bits      = d_cb_bits;
   p.harq_data    = ctx->d_harq_data;
+  p.harq_last    = ctx->d_harq_last;
   p.scale_mode   = ctx->cfg.scale_mode;
   p.simd_width   = ctx->cfg.combine_simd_width;
   if (shape.any_dematch) {
@@ -170,7 +176,10 @@ int launch_batch(pdc_ctx*             ctx,
     t.cb_bits    = d_cb_bits;
     t.tb_results = d_tb_res;
     t.tb_bytes   = d_tb_out;
-    PDC_CUDA(pdc::launch_tb_assemble(t, ctx->d_harq_data, s));
+    if (n_tb > ctx->tb_sync_entries) {
+      return fail(PDC_ERR_CAPACITY, "launch_batch: more transport blocks than the context was created for");
+    }
+    PDC_CUDA(pdc::launch_tb_assemble(t, ctx->d_harq_data, tb_sync ? tb_sync : ctx->d_tb_sync, s));
     ctx->launches++;
   }
   return PDC_OK;
@@ -355,6 +364,11 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
   PDC_CREATE(cudaMemset(ctx->d_harq, 0, entries * PDC_MAX_CB_SOFT));
   PDC_CREATE(dev_alloc(&ctx->d_harq_data, entries * PDC_MAX_CB_BYTES));
   PDC_CREATE(cudaMemset(ctx->d_harq_data, 0, entries * PDC_MAX_CB_BYTES));
+  ctx->tb_sync_entries = std::max<uint32_t>(cfg->max_tbs, 1);
+  PDC_CREATE(dev_alloc(&ctx->d_tb_sync, 2 * (size_t)ctx->tb_sync_entries));
+  PDC_CREATE(cudaMemset(ctx->d_tb_sync, 0, 2 * (size_t)ctx->tb_sync_entries * sizeof(uint32_t)));
+  PDC_CREATE(dev_alloc(&ctx->d_harq_last, entries));
+  PDC_CREATE(cudaMemset(ctx->d_harq_last, 0, entries * sizeof(int32_t))); // all-zero entries
   ctx->scratch_llr_bytes = 35u * PDC_MAX_CB_BYTES * 8u; // MAX_CODEBLOCK_RM_SIZE (ldpc.h:122)
   PDC_CREATE(dev_alloc(&ctx->d_scratch_llr, ctx->scratch_llr_bytes));
   ctx->queues.resize(cfg->nof_streams);
@@ -368,6 +382,8 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
     PDC_CREATE(dev_alloc(&q.d_cb_bits, (size_t)cfg->max_cbs * PDC_MAX_CB_BYTES));
     PDC_CREATE(dev_alloc(&q.d_tb_res, cfg->max_tbs));
     PDC_CREATE(dev_alloc(&q.d_tb_out, (size_t)cfg->max_tb_bytes + 16));
+    PDC_CREATE(dev_alloc(&q.d_tb_sync, 2 * (size_t)ctx->tb_sync_entries));
+    PDC_CREATE(cudaMemset(q.d_tb_sync, 0, 2 * (size_t)ctx->tb_sync_entries * sizeof(uint32_t)));
     PDC_CREATE(host_alloc(&q.h_cbs, cfg->max_cbs));
     PDC_CREATE(host_alloc(&q.h_tbs, cfg->max_tbs));
     PDC_CREATE(host_alloc(&q.h_cb_res, cfg->max_cbs));
@@ -400,6 +416,7 @@ void pdc_destroy(pdc_ctx* ctx)
     cudaFree(q.d_cb_bits);
     cudaFree(q.d_tb_res);
     cudaFree(q.d_tb_out);
+    cudaFree(q.d_tb_sync);
     cudaFreeHost(q.h_cbs);
     cudaFreeHost(q.h_tbs);
     cudaFreeHost(q.h_cb_res);
@@ -409,6 +426,8 @@ void pdc_destroy(pdc_ctx* ctx)
   }
   cudaFree(ctx->d_harq);
   cudaFree(ctx->d_harq_data);
+  cudaFree(ctx->d_harq_last);
+  cudaFree(ctx->d_tb_sync);
   cudaFree(ctx->d_scratch_llr);
   cudaFree(ctx->d_state_scratch);
   delete ctx;
@@ -507,7 +526,7 @@ int pdc_submit(pdc_ctx*           ctx,
   // Codeblocks that are not decoded report "not run".
   PDC_CUDA(cudaMemsetAsync(q.d_cb_res, 0, sizeof(pdc_cb_result) * n_cb, q.stream));
   int rc = launch_batch(ctx, q.d_cbs, n_cb, q.d_llrs, q.d_tbs, n_tb, q.d_cb_res, q.d_cb_bits, q.d_tb_res, q.d_tb_out,
-                        shape, nullptr, 0, q.stream);
+                        shape, nullptr, 0, q.stream, q.d_tb_sync);
   if (rc != PDC_OK) {
     return rc;
   }
@@ -624,6 +643,7 @@ int pdc_harq_write(pdc_ctx* ctx, uint32_t harq_id, const int8_t* soft, uint32_t 
   }
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   PDC_CUDA(cudaMemcpy(ctx->d_harq + (size_t)harq_id * PDC_MAX_CB_SOFT, soft, n, cudaMemcpyHostToDevice));
+  PDC_CUDA(cudaMemset(ctx->d_harq_last + harq_id, 0xff, sizeof(int32_t))); // contents changed behind the kernels: unknown
   return PDC_OK;
 }
 

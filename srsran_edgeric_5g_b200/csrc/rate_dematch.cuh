@@ -261,13 +261,15 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(BatchParams prm)
 {
   __shared__ DematchGeom g;
   __shared__ int         ok;
+  __shared__ int         sh_last;
   uint32_t               cb = blockIdx.x;
   const pdc_cb_desc&     d  = prm.cbs[cb];
   if (!(d.flags & PDC_CB_DEMATCH)) {
     return;
   }
   if (threadIdx.x == 0) {
-    ok = dm_geometry(d, prm.simd_width, g) && (d.harq_id < prm.harq_entries);
+    ok      = dm_geometry(d, prm.simd_width, g) && (d.harq_id < prm.harq_entries);
+    sh_last = 0;
   }
   __syncthreads();
   if (!ok) {
@@ -277,6 +279,7 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(BatchParams prm)
   uint32_t*     out        = reinterpret_cast<uint32_t*>(prm.harq + (size_t)d.harq_id * PDC_MAX_CB_SOFT);
   const int     nw         = (g.N + 3) >> 2;
   const bool    single_lap = g.E <= g.Dn;
+  int           last       = 0;
   for (int w = threadIdx.x; w < nw; w += blockDim.x) {
     const uint32_t old = out[w];
     uint32_t       res = 0;
@@ -292,6 +295,26 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(BatchParams prm)
     if (res != old) {
       out[w] = res;
     }
+    if (res != 0) {
+      // Highest non-zero position of this word (bytes beyond N keep their old value and do not count).
+#pragma unroll
+      for (int k = 0; k != 4; ++k) {
+        if (((res >> (8 * k)) & 0xffu) != 0 && 4 * w + k < g.N) {
+          last = max(last, 4 * w + k + 1);
+        }
+      }
+    }
+  }
+  // The decoder trims trailing zeros (ldpc_decoder_impl.cpp:86-99): hand it the position of the last non-zero soft bit.
+  for (int o = 16; o > 0; o >>= 1) {
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  }
+  if ((threadIdx.x & 31) == 0 && last > 0) {
+    atomicMax(&sh_last, last);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    prm.harq_last[d.harq_id] = sh_last;
   }
 }
 

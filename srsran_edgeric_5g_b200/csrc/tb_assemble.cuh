@@ -5,16 +5,18 @@
 // codeblock CRC; with several, and only if every codeblock CRC passed, the payloads (without CB CRC, filler and zero
 // padding) are concatenated and CRC24A over the TB must equal the 24 bits that follow the payload of the last codeblock.
 //
-// One CTA per transport block. The concatenated stream (payload + TB checksum) is produced 32 bits per thread with a
-// funnel shift from at most two codeblocks; each thread then runs a table-driven CRC24A over its run of consecutive words
-// and weights it by x^(32 * words after the run) mod P; the XOR of all weighted remainders is zero iff the CRC matches.
+// TB_SPLIT CTAs per transport block. The concatenated stream (payload + TB checksum) is produced 32 bits per thread
+// with a funnel shift from at most two codeblocks; each thread then runs a table-driven CRC24A over its run of
+// consecutive words and weights it by x^(32 * words after the run) mod P; the XOR of all weighted remainders (across the
+// CTAs of the TB through a global accumulator, last CTA publishes) is zero iff the CRC matches.
 #pragma once
 
 #include "pdc_device.cuh"
 
 namespace pdc {
 
-constexpr int TB_THREADS = 1024;
+constexpr int TB_THREADS = 512;
+constexpr int TB_SPLIT   = 16;
 
 // x^(32 * 2^i) mod CRC24A, i = 0..19, and the byte table T[b] = (b * x^24) mod P; filled at start-up.
 __constant__ uint32_t c_xpow_crc24a_pow2[20];
@@ -33,7 +35,8 @@ __device__ __forceinline__ uint32_t cb_bits32(const uint8_t* __restrict__ src, u
   return __funnelshift_l(lo, hi, sh);
 }
 
-__global__ void __launch_bounds__(TB_THREADS) tb_assemble_kernel(TbParams prm, const uint8_t* harq_data)
+// sync: per TB {XOR accumulator, arrival counter}, zero between launches (the last CTA of a TB resets them).
+__global__ void __launch_bounds__(TB_THREADS) tb_assemble_kernel(TbParams prm, const uint8_t* harq_data, uint32_t* sync)
 {
   __shared__ uint32_t sh_crc;
   __shared__ uint32_t sh_table[256];
@@ -58,10 +61,13 @@ __global__ void __launch_bounds__(TB_THREADS) tb_assemble_kernel(TbParams prm, c
   r.all_cb_ok  = (uint8_t)ok;
   r.reserved   = 0;
   uint8_t* out = prm.tb_bytes + tb.out_offset;
+  const uint32_t part = blockIdx.y, n_parts = gridDim.y;
   if (ok && tb.nof_cb == 1) {
-    const uint8_t* src = harq_data + (size_t)prm.cbs[tb.first_cb].harq_id * PDC_MAX_CB_BYTES;
-    for (uint32_t i = tid; i < tb.tbs_bits / 8; i += blockDim.x) {
-      out[i] = src[i];
+    if (part == 0) {
+      const uint8_t* src = harq_data + (size_t)prm.cbs[tb.first_cb].harq_id * PDC_MAX_CB_BYTES;
+      for (uint32_t i = tid; i < tb.tbs_bits / 8; i += blockDim.x) {
+        out[i] = src[i];
+      }
     }
     r.tb_crc_ok = 1;
   } else if (ok) {
@@ -72,9 +78,10 @@ __global__ void __launch_bounds__(TB_THREADS) tb_assemble_kernel(TbParams prm, c
     const uint32_t     T      = (total + 31u) / 32u;
     uint32_t*          out_w  = reinterpret_cast<uint32_t*>(out);
     const uint32_t     poly   = crc_poly(PDC_CRC24A);
-    // Thread t owns words [t * per, min(T, (t + 1) * per)).
-    const uint32_t per   = (T + blockDim.x - 1) / blockDim.x;
-    const uint32_t first = tid * per;
+    // Thread t of part p owns words [(p * blockDim + t) * per, ...).
+    const uint32_t n_thr = blockDim.x * n_parts;
+    const uint32_t per   = (T + n_thr - 1) / n_thr;
+    const uint32_t first = (part * blockDim.x + tid) * per;
     const uint32_t last  = min(T, first + per);
     uint32_t       crc   = 0;
     if (first < T) {
@@ -128,10 +135,23 @@ __global__ void __launch_bounds__(TB_THREADS) tb_assemble_kernel(TbParams prm, c
       atomicXor(&sh_crc, crc);
     }
     __syncthreads();
-    r.tb_crc_ok = (sh_crc == 0) ? 1 : 0;
   }
+  // Combine the parts: XOR the CTA's remainder into the TB accumulator; the last CTA to arrive publishes and resets.
   if (tid == 0) {
-    prm.tb_results[blockIdx.x] = r;
+    uint32_t* acc = sync + 2 * blockIdx.x;
+    if (sh_crc) {
+      atomicXor(acc, sh_crc);
+    }
+    __threadfence();
+    if (atomicAdd(acc + 1, 1u) == n_parts - 1) {
+      __threadfence();
+      const uint32_t total_crc = atomicExch(acc, 0u);
+      acc[1]                   = 0;
+      if (ok && tb.nof_cb > 1) {
+        r.tb_crc_ok = (total_crc == 0) ? 1 : 0;
+      }
+      prm.tb_results[blockIdx.x] = r;
+    }
   }
 }
 
@@ -168,12 +188,12 @@ inline cudaError_t upload_tb_tables()
   return cudaMemcpyToSymbol(c_crc24a_table, table, sizeof(table));
 }
 
-inline cudaError_t launch_tb_assemble(const TbParams& p, const uint8_t* harq_data, cudaStream_t s)
+inline cudaError_t launch_tb_assemble(const TbParams& p, const uint8_t* harq_data, uint32_t* sync, cudaStream_t s)
 {
   if (p.n_tb == 0) {
     return cudaSuccess;
   }
-  tb_assemble_kernel<<<p.n_tb, TB_THREADS, 0, s>>>(p, harq_data);
+  tb_assemble_kernel<<<dim3(p.n_tb, TB_SPLIT), TB_THREADS, 0, s>>>(p, harq_data, sync);
   return cudaGetLastError();
 }
 
