@@ -465,8 +465,9 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         if (in[h] == nullptr) {
           continue;
         }
-        const int known = prm.harq_last[prm.cbs[lane[h].cb].harq_id];
-        if (known >= 0) {
+        const int4 slots = reinterpret_cast<const int4*>(prm.harq_last)[prm.cbs[lane[h].cb].harq_id];
+        const int  known = max(max(slots.x, slots.y), max(slots.z, slots.w));
+        if (min(min(slots.x, slots.y), min(slots.z, slots.w)) >= 0) {
           if (tid == 0) {
             sh_last[h] = min(known, N);
           }

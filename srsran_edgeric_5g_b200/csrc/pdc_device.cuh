@@ -78,7 +78,8 @@ struct BatchParams {
   pdc_cb_result*     results;
   uint8_t*           cb_bits;    // n_cb x PDC_MAX_CB_BYTES (device staging, always present)
   uint8_t*           harq_data;  // entries x PDC_MAX_CB_BYTES: decoded message bits kept with the HARQ entry
-  int32_t*           harq_last;  // per entry: 1 + index of the last non-zero soft bit, -1 = unknown (scan the entry)
+  int32_t*           harq_last;  // per entry, 4 slots (one per dematcher part; take the maximum): 1 + index of the last
+                                 // non-zero soft bit, -1 = unknown (scan the entry)
   int                scale_mode;
   int                simd_width;
 };

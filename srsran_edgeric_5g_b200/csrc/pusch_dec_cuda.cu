@@ -77,7 +77,7 @@ struct pdc_ctx {
   uint8_t*             d_harq_data = nullptr; // (harq_entries + 1) x PDC_MAX_CB_BYTES
   uint32_t*            d_tb_sync = nullptr;   // per TB {CRC accumulator, arrival counter} of the TB assembly kernel
   uint32_t             tb_sync_entries = 0;
-  int32_t*             d_harq_last = nullptr; // (harq_entries + 1): last non-zero soft bit of each entry (+1), -1 unknown
+  int32_t*             d_harq_last = nullptr; // (harq_entries + 1) x DM_MAX_PARTS: last non-zero soft bit (+1), -1 unknown
   int8_t*              d_scratch_llr = nullptr;
   size_t               scratch_llr_bytes = 0;
   std::vector<Queue>   queues;
@@ -142,7 +142,7 @@ int launch_batch(pdc_ctx*             ctx,
   p.scale_mode   = ctx->cfg.scale_mode;
   p.simd_width   = ctx->cfg.combine_simd_width;
   if (shape.any_dematch) {
-    PDC_CUDA(pdc::launch_rate_dematch(p, s));
+    PDC_CUDA(pdc::launch_rate_dematch(p, ctx->sm_count, s));
     ctx->launches++;
   }
   if (shape.any_decode) {
@@ -367,8 +367,8 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
   ctx->tb_sync_entries = std::max<uint32_t>(cfg->max_tbs, 1);
   PDC_CREATE(dev_alloc(&ctx->d_tb_sync, 2 * (size_t)ctx->tb_sync_entries));
   PDC_CREATE(cudaMemset(ctx->d_tb_sync, 0, 2 * (size_t)ctx->tb_sync_entries * sizeof(uint32_t)));
-  PDC_CREATE(dev_alloc(&ctx->d_harq_last, entries));
-  PDC_CREATE(cudaMemset(ctx->d_harq_last, 0, entries * sizeof(int32_t))); // all-zero entries
+  PDC_CREATE(dev_alloc(&ctx->d_harq_last, entries * pdc::DM_MAX_PARTS));
+  PDC_CREATE(cudaMemset(ctx->d_harq_last, 0, entries * pdc::DM_MAX_PARTS * sizeof(int32_t))); // all-zero entries
   ctx->scratch_llr_bytes = 35u * PDC_MAX_CB_BYTES * 8u; // MAX_CODEBLOCK_RM_SIZE (ldpc.h:122)
   PDC_CREATE(dev_alloc(&ctx->d_scratch_llr, ctx->scratch_llr_bytes));
   ctx->queues.resize(cfg->nof_streams);
@@ -643,7 +643,8 @@ int pdc_harq_write(pdc_ctx* ctx, uint32_t harq_id, const int8_t* soft, uint32_t 
   }
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   PDC_CUDA(cudaMemcpy(ctx->d_harq + (size_t)harq_id * PDC_MAX_CB_SOFT, soft, n, cudaMemcpyHostToDevice));
-  PDC_CUDA(cudaMemset(ctx->d_harq_last + harq_id, 0xff, sizeof(int32_t))); // contents changed behind the kernels: unknown
+  // Contents changed behind the kernels: position of the last non-zero soft bit unknown.
+  PDC_CUDA(cudaMemset(ctx->d_harq_last + (size_t)harq_id * pdc::DM_MAX_PARTS, 0xff, pdc::DM_MAX_PARTS * sizeof(int32_t)));
   return PDC_OK;
 }
 

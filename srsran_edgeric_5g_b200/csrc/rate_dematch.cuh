@@ -15,6 +15,13 @@
 
 namespace pdc {
 
+// Kernel geometry. The rate-matched input of a codeblock is first staged in shared memory in DEINTERLEAVED order
+// (coalesced 64/128-bit global loads, bit planes separated with byte permutes), so the gather that follows reads
+// consecutive bytes. Inputs longer than the staging buffer are gathered from global memory instead.
+constexpr int DM_THREADS     = 512;
+constexpr int DM_STAGE_BYTES = 40960;
+constexpr int DM_MAX_PARTS   = 4; // CTAs per codeblock (small batches are latency bound: split the N positions)
+
 struct DematchGeom {
   int N, Ncb, Z, K_sys, F, info, k0, d0, Dn, E, qm, Kq;
   float inv_Kq;
@@ -24,6 +31,7 @@ struct DematchGeom {
   int zlo;            // new data: [0, zlo) is zeroed
   int zf_lo;          // new data, not wrapped: [zf_lo, N) is zeroed at the end; N if not applicable
   int simd_width;
+  int staged;         // the deinterleaved input is staged in shared memory
 };
 
 __device__ __forceinline__ bool dm_geometry(const pdc_cb_desc& d, int simd_width, DematchGeom& g)
@@ -61,6 +69,7 @@ __device__ __forceinline__ bool dm_geometry(const pdc_cb_desc& d, int simd_width
   g.zlo            = (g.k0 < g.info) ? g.k0 : g.info;
   g.zf_lo          = g.N;
   g.simd_width     = simd_width;
+  g.staged = (g.qm == 1 || g.qm == 2 || g.qm == 4 || g.qm == 6 || g.qm == 8) && (g.E <= DM_STAGE_BYTES);
   if (g.new_data && !g.wrapped) {
     int de      = g.d0 + g.E;
     int idx_end = (g.K_sys + max(0, de - g.info)) % g.Ncb;
@@ -113,17 +122,24 @@ __device__ __forceinline__ int dm_combine(const DematchGeom& g, int p, int i, in
   return a; // a is the non-finite one
 }
 
-__device__ __forceinline__ int dm_fetch(const DematchGeom& g, const int8_t* __restrict__ llr, int i)
+// Deinterleaved input element i (ldpc_rate_dematcher_impl.cpp:203-257). STAGED: the deinterleaved sequence is in sh[].
+template <bool STAGED>
+__device__ __forceinline__ int dm_fetch(const DematchGeom& g, const int8_t* __restrict__ llr, const uint8_t* sh, int i)
 {
+  if (STAGED) {
+    return (int)(int8_t)sh[i];
+  }
   if (g.qm == 1) {
-    return __ldg(llr + i);
+    return (int)__ldg(llr + i);
   }
   int j   = i / g.Kq; // bit plane
   int sym = i - j * g.Kq;
-  return __ldg(llr + sym * g.qm + j);
+  return (int)__ldg(llr + sym * g.qm + j);
 }
 
-__device__ __forceinline__ int dm_position(const DematchGeom& g, const int8_t* __restrict__ llr, int p, int old)
+template <bool STAGED>
+__device__ __forceinline__ int dm_position(const DematchGeom& g, const int8_t* __restrict__ llr, const uint8_t* sh,
+                                           int p, int old)
 {
   if (p >= g.N) {
     return old;
@@ -152,13 +168,53 @@ __device__ __forceinline__ int dm_position(const DematchGeom& g, const int8_t* _
     return val;
   }
   if (g.new_data && first_lap) {
-    val = dm_fetch(g, llr, i);
+    val = dm_fetch<STAGED>(g, llr, sh, i);
     i += g.Dn;
   }
   for (; i < g.E; i += g.Dn) {
-    val = dm_combine(g, p, i, val, dm_fetch(g, llr, i));
+    val = dm_combine(g, p, i, val, dm_fetch<STAGED>(g, llr, sh, i));
   }
   return val;
+}
+
+// Position of the last non-zero soft bit seen by a thread: the word with the highest index and its value.
+struct DmLast {
+  int      w   = -1;
+  uint32_t val = 0;
+  __device__ __forceinline__ void note(int word, uint32_t v)
+  {
+    if (v != 0 && word > w) {
+      w   = word;
+      val = v;
+    }
+  }
+  __device__ __forceinline__ int position() const // 1 + index of the last non-zero byte, 0 if none
+  {
+    return (w < 0) ? 0 : 4 * w + 4 - (__clz((int)val) >> 3);
+  }
+};
+
+// General path: the four positions of word w one by one.
+template <bool STAGED>
+__device__ __noinline__ uint32_t dm_word_general(const DematchGeom& g, const int8_t* __restrict__ llr, const uint8_t* sh,
+                                                 uint32_t* out, int w)
+{
+  const uint32_t old = out[w];
+  uint32_t       res = 0;
+#pragma unroll
+  for (int k = 0; k != 4; ++k) {
+    int o = (int)(int8_t)(old >> (8 * k));
+    int v = dm_position<STAGED>(g, llr, sh, 4 * w + k, o);
+    res |= (uint32_t)(uint8_t)(int8_t)v << (8 * k);
+  }
+  if (res != old) {
+    out[w] = res;
+  }
+  // Bytes beyond N keep their old value and do not count as soft bits.
+  if (4 * w + 3 >= g.N) {
+    res &= 0xffffffffu >> (8 * (4 * w + 4 - g.N));
+  }
+  return res;
 }
 
 // True if any of the four packed int8 is outside [-120, 120] (|u - 0x80| < 8 for the unsigned byte u).
@@ -183,91 +239,276 @@ __device__ __forceinline__ uint32_t dm_combine4_finite(uint32_t a, uint32_t b)
   return __byte_perm(se, so, 0x6240);
 }
 
-// Word fast path: the four positions 4w..4w+3 lie in one region of the circular buffer, are fed by four consecutive
-// deinterleaved inputs of one bit plane (or by none) and the transmission makes a single lap. Returns false if the
-// word needs the general per-position path.
-__device__ __forceinline__ bool dm_word_fast(const DematchGeom& g, const int8_t* __restrict__ llr, int p0, uint32_t old,
-                                             uint32_t& res)
+// ---- single-lap transmissions: the N positions fall into a few segments of uniform behaviour ------------------------
+//
+// Between two consecutive breakpoints (region limits of the circular buffer, start and end of the walk) every position
+// is treated alike and is fed by the deinterleaved input at a constant distance, i = p + ioff.
+enum DmAction : int {
+  DM_KEEP = 0,  // stale: the walk does not touch the position
+  DM_ZERO,      // zeroed by a new transmission
+  DM_FILL,      // filler bits of a new transmission: +infinity
+  DM_COPY,      // first lap of a new transmission
+  DM_COMB_ZERO, // combined with a zeroed position
+  DM_COMB       // combined with the stored soft bit
+};
+struct DmSeg {
+  int p0, p1, action, ioff;
+};
+constexpr int DM_MAX_BP = 12;
+
+__device__ __forceinline__ int dm_classify(const DematchGeom& g, int p, int& ioff)
 {
-  if (p0 + 3 >= g.Ncb) {
-    return false;
+  ioff = 0;
+  if (p >= g.info && p < g.K_sys) {
+    return g.new_data ? DM_FILL : DM_KEEP;
   }
-  const bool in_info = p0 + 3 < g.info;
-  if (!in_info && p0 < g.K_sys) {
-    return false;
+  const bool base_zero = g.new_data && (p < g.zlo || p >= g.zf_lo);
+  const int  idle      = base_zero ? DM_ZERO : DM_KEEP;
+  if (p >= g.Ncb) {
+    return idle;
   }
-  int  i         = (in_info ? p0 : p0 - g.F) - g.d0;
-  bool first_lap = i >= 0;
+  int        d         = (p < g.info) ? p : p - g.F;
+  int        i         = d - g.d0;
+  const bool first_lap = i >= 0;
   if (!first_lap) {
-    if (i + 3 >= 0) {
-      return false;
-    }
     i += g.Dn;
   }
-  // Base value of the four positions (what the sequential walk leaves there before combining).
-  uint32_t base = old;
-  if (g.new_data) {
-    const bool z0 = (p0 < g.zlo) || (p0 >= g.zf_lo);
-    const bool z3 = (p0 + 3 < g.zlo) || (p0 + 3 >= g.zf_lo);
-    if (z0 != z3) {
-      return false;
-    }
-    if (z0) {
-      base = 0;
-    }
-  }
   if (i >= g.E) {
-    res = base;
-    return true;
+    return idle;
   }
-  if (i + 3 >= g.E) {
-    return false;
-  }
-  // Four consecutive inputs of one bit plane.
-  uint32_t in;
-  if (g.qm == 1) {
-    in = (uint32_t)(uint8_t)__ldg(llr + i) | ((uint32_t)(uint8_t)__ldg(llr + i + 1) << 8) |
-         ((uint32_t)(uint8_t)__ldg(llr + i + 2) << 16) | ((uint32_t)(uint8_t)__ldg(llr + i + 3) << 24);
-  } else {
-    int j = __float2int_rz(__fmul_rz((float)i, g.inv_Kq));
-    int sym = i - j * g.Kq;
-    if (sym < 0) {
-      --j;
-      sym += g.Kq;
-    } else if (sym >= g.Kq) {
-      ++j;
-      sym -= g.Kq;
-    }
-    if (sym + 3 >= g.Kq) {
-      return false;
-    }
-    const int8_t* src = llr + sym * g.qm + j;
-    in = (uint32_t)(uint8_t)__ldg(src) | ((uint32_t)(uint8_t)__ldg(src + g.qm) << 8) |
-         ((uint32_t)(uint8_t)__ldg(src + 2 * g.qm) << 16) | ((uint32_t)(uint8_t)__ldg(src + 3 * g.qm) << 24);
-  }
+  ioff = i - p;
   if (g.new_data && first_lap) {
-    res = in; // copy
-    return true;
+    return DM_COPY;
   }
-  if (dm_any_nonfinite(base) || dm_any_nonfinite(in)) {
-    return false;
-  }
-  res = dm_combine4_finite(base, in);
-  return true;
+  return base_zero ? DM_COMB_ZERO : DM_COMB;
 }
 
-// One CTA per codeblock; each thread owns 4 consecutive soft bits (one 32-bit read-modify-write of the HARQ entry).
-__global__ void __launch_bounds__(256) rate_dematch_kernel(BatchParams prm)
+__device__ __forceinline__ int dm_breakpoint(const DematchGeom& g, int k)
 {
-  __shared__ DematchGeom g;
-  __shared__ int         ok;
-  __shared__ int         sh_last;
-  uint32_t               cb = blockIdx.x;
-  const pdc_cb_desc&     d  = prm.cbs[cb];
+  auto pos_of = [&](int d) { return (d < g.info) ? d : d + g.F; };
+  int  v;
+  switch (k) {
+    case 0:
+      v = 0;
+      break;
+    case 1:
+      v = g.zlo;
+      break;
+    case 2:
+      v = g.zf_lo;
+      break;
+    case 3:
+      v = g.info;
+      break;
+    case 4:
+      v = g.K_sys;
+      break;
+    case 5:
+      v = g.Ncb;
+      break;
+    case 6:
+      v = pos_of(g.d0);
+      break;
+    case 7:
+      v = g.wrapped ? pos_of(g.E - g.first_pass_len) : pos_of(g.d0 + g.E);
+      break;
+    default:
+      v = g.N;
+      break;
+  }
+  return max(0, min(v, g.N));
+}
+
+__device__ __forceinline__ uint32_t dm_lds_u32_unaligned(const uint8_t* sh, int a)
+{
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(sh + (a & ~3));
+  return __funnelshift_r(w[0], w[1], 8 * (a & 3));
+}
+
+// Words [wa, wb) of one segment, all four positions of each inside the segment.
+__device__ __forceinline__ void dm_segment_words(const DematchGeom& g, const int8_t* __restrict__ llr, const uint8_t* sh,
+                                                 uint32_t* out, int action, int ioff, int wa, int wb, DmLast& last)
+{
+  const int tid = threadIdx.x, T = blockDim.x;
+  switch (action) {
+    case DM_ZERO:
+      for (int w = wa + tid; w < wb; w += T) {
+        out[w] = 0u;
+      }
+      break;
+    case DM_FILL:
+      for (int w = wa + tid; w < wb; w += T) {
+        out[w] = 0x7f7f7f7fu;
+        last.note(w, 0x7f7f7f7fu);
+      }
+      break;
+    case DM_COPY:
+#pragma unroll 2
+      for (int w = wa + tid; w < wb; w += T) {
+        const uint32_t r = dm_lds_u32_unaligned(sh, 4 * w + ioff);
+        out[w]           = r;
+        last.note(w, r);
+      }
+      break;
+    case DM_COMB_ZERO:
+      for (int w = wa + tid; w < wb; w += T) {
+        const uint32_t in = dm_lds_u32_unaligned(sh, 4 * w + ioff);
+        uint32_t       r  = in; // clamp(0 + in) for finite soft bits
+        if (dm_any_nonfinite(in)) {
+          r = dm_word_general<true>(g, llr, sh, out, w);
+        } else {
+          out[w] = r;
+        }
+        last.note(w, r);
+      }
+      break;
+    case DM_COMB:
+      for (int w = wa + tid; w < wb; w += 2 * T) {
+        const int      w2   = w + T;
+        const bool     has2 = w2 < wb;
+        const uint32_t o1   = out[w];
+        const uint32_t o2   = has2 ? out[w2] : 0u;
+        const uint32_t i1   = dm_lds_u32_unaligned(sh, 4 * w + ioff);
+        const uint32_t i2   = has2 ? dm_lds_u32_unaligned(sh, 4 * w2 + ioff) : 0u;
+        uint32_t       r1, r2 = 0;
+        if (dm_any_nonfinite(o1) || dm_any_nonfinite(i1)) {
+          r1 = dm_word_general<true>(g, llr, sh, out, w);
+        } else {
+          r1 = dm_combine4_finite(o1, i1);
+          if (r1 != o1) {
+            out[w] = r1;
+          }
+        }
+        last.note(w, r1);
+        if (has2) {
+          if (dm_any_nonfinite(o2) || dm_any_nonfinite(i2)) {
+            r2 = dm_word_general<true>(g, llr, sh, out, w2);
+          } else {
+            r2 = dm_combine4_finite(o2, i2);
+            if (r2 != o2) {
+              out[w2] = r2;
+            }
+          }
+          last.note(w2, r2);
+        }
+      }
+      break;
+    default: // DM_KEEP: only the position of the last non-zero soft bit is needed
+      for (int w = wa + tid; w < wb; w += 2 * T) {
+        const int      w2 = w + T;
+        const uint32_t o1 = out[w];
+        const uint32_t o2 = (w2 < wb) ? out[w2] : 0u;
+        last.note(w, o1);
+        last.note(w2, o2);
+      }
+      break;
+  }
+}
+
+// Stage the rate-matched input in shared memory in deinterleaved order: sh[j * Kq + sym] = llr[sym * QM + j].
+// Four symbols per thread step: coalesced vector loads, bit planes separated with byte permutes.
+template <int QM>
+__device__ __forceinline__ void dm_stage_planes(const DematchGeom& g, const int8_t* __restrict__ llr, uint8_t* sh)
+{
+  const uint8_t*  src      = reinterpret_cast<const uint8_t*>(llr);
+  const int       n_groups = g.Kq >> 2;
+  constexpr int   VEC      = (QM % 4 == 0) ? 16 : 8; // bytes per vector load (a group is 4 * QM bytes)
+  const bool      aligned  = (reinterpret_cast<uintptr_t>(src) % VEC) == 0;
+  const bool      word_st  = (g.Kq & 3) == 0;        // plane starts are word aligned
+  for (int grp = threadIdx.x; grp < n_groups; grp += blockDim.x) {
+    uint32_t       w[QM];
+    const uint8_t* p = src + (size_t)grp * 4 * QM;
+    if (aligned) {
+      if (VEC == 16) {
+#pragma unroll
+        for (int r = 0; r != QM / 4; ++r) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + r);
+          w[4 * r] = v.x, w[4 * r + 1] = v.y, w[4 * r + 2] = v.z, w[4 * r + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r != QM / 2; ++r) {
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(p) + r);
+          w[2 * r] = v.x, w[2 * r + 1] = v.y;
+        }
+      }
+    } else {
+      const uint32_t  sh8 = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+      const uint32_t* a   = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+      uint32_t        cur = __ldg(a);
+#pragma unroll
+      for (int r = 0; r != QM; ++r) {
+        // The next aligned word holds at least one byte of this group whenever the pointer is misaligned.
+        const uint32_t nxt = (sh8 != 0 || r + 1 != QM) ? __ldg(a + r + 1) : 0u;
+        w[r]               = __funnelshift_r(cur, nxt, sh8);
+        cur                = nxt;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j != QM; ++j) {
+      uint32_t o = 0;
+#pragma unroll
+      for (int s4 = 0; s4 != 4; ++s4) {
+        const int off = s4 * QM + j;
+        o |= ((w[off >> 2] >> (8 * (off & 3))) & 0xffu) << (8 * s4);
+      }
+      uint8_t* dst = sh + j * g.Kq + 4 * grp;
+      if (word_st) {
+        *reinterpret_cast<uint32_t*>(dst) = o;
+      } else {
+        dst[0] = (uint8_t)o, dst[1] = (uint8_t)(o >> 8), dst[2] = (uint8_t)(o >> 16), dst[3] = (uint8_t)(o >> 24);
+      }
+    }
+  }
+  // Symbols after the last complete group.
+  const int sym0 = 4 * n_groups;
+  for (int idx = threadIdx.x; idx < (g.Kq - sym0) * QM; idx += blockDim.x) {
+    const int s4 = idx / QM, j = idx - s4 * QM;
+    sh[j * g.Kq + sym0 + s4] = src[(size_t)(sym0 + s4) * QM + j];
+  }
+}
+
+__device__ __forceinline__ void dm_stage(const DematchGeom& g, const int8_t* __restrict__ llr, uint8_t* sh)
+{
+  switch (g.qm) {
+    case 2:
+      dm_stage_planes<2>(g, llr, sh);
+      break;
+    case 4:
+      dm_stage_planes<4>(g, llr, sh);
+      break;
+    case 6:
+      dm_stage_planes<6>(g, llr, sh);
+      break;
+    case 8:
+      dm_stage_planes<8>(g, llr, sh);
+      break;
+    default:
+      // One bit per symbol: the stream is already in order. (Other modulation orders are never staged.)
+      for (int i = threadIdx.x; i < g.E; i += blockDim.x) {
+        sh[i] = (uint8_t)__ldg(llr + i);
+      }
+      break;
+  }
+}
+
+// gridDim = (codeblocks, parts). Each CTA owns a contiguous range of the 32-bit words of the HARQ entry.
+__global__ void __launch_bounds__(DM_THREADS, 3) rate_dematch_kernel(BatchParams prm)
+{
+  __shared__ __align__(16) uint8_t sh_in[DM_STAGE_BYTES + 16];
+  __shared__ DematchGeom           g;
+  __shared__ int                   ok;
+  __shared__ int                   sh_last;
+  __shared__ int                   sh_cand[DM_MAX_BP];
+  __shared__ int                   sh_bp[DM_MAX_BP];
+  __shared__ DmSeg                 sh_seg[DM_MAX_BP];
+  const int                        tid = threadIdx.x;
+  uint32_t                         cb  = blockIdx.x;
+  const pdc_cb_desc&               d   = prm.cbs[cb];
   if (!(d.flags & PDC_CB_DEMATCH)) {
     return;
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     ok      = dm_geometry(d, prm.simd_width, g) && (d.harq_id < prm.harq_entries);
     sh_last = 0;
   }
@@ -275,55 +516,107 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(BatchParams prm)
   if (!ok) {
     return; // the decode kernel reports the invalid descriptor
   }
-  const int8_t* llr        = prm.llrs + d.llr_offset;
-  uint32_t*     out        = reinterpret_cast<uint32_t*>(prm.harq + (size_t)d.harq_id * PDC_MAX_CB_SOFT);
-  const int     nw         = (g.N + 3) >> 2;
-  const bool    single_lap = g.E <= g.Dn;
-  int           last       = 0;
-  for (int w = threadIdx.x; w < nw; w += blockDim.x) {
-    const uint32_t old = out[w];
-    uint32_t       res = 0;
-    if (!(single_lap && dm_word_fast(g, llr, 4 * w, old, res))) {
-      res = 0;
-#pragma unroll
-      for (int k = 0; k != 4; ++k) {
-        int o = (int)(int8_t)(old >> (8 * k));
-        int v = dm_position(g, llr, 4 * w + k, o);
-        res |= (uint32_t)(uint8_t)(int8_t)v << (8 * k);
-      }
-    }
-    if (res != old) {
-      out[w] = res;
-    }
-    if (res != 0) {
-      // Highest non-zero position of this word (bytes beyond N keep their old value and do not count).
-#pragma unroll
-      for (int k = 0; k != 4; ++k) {
-        if (((res >> (8 * k)) & 0xffu) != 0 && 4 * w + k < g.N) {
-          last = max(last, 4 * w + k + 1);
-        }
-      }
-    }
+  const int8_t* llr    = prm.llrs + d.llr_offset;
+  uint32_t*     out    = reinterpret_cast<uint32_t*>(prm.harq + (size_t)d.harq_id * PDC_MAX_CB_SOFT);
+  const int     nw     = (g.N + 3) >> 2;
+  const bool    staged = g.staged != 0;
+  const bool    fast   = staged && g.E <= g.Dn; // single lap
+  const int     per    = (nw + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int     w_lo   = (int)blockIdx.y * per;
+  const int     w_hi   = min(nw, w_lo + per);
+  if (fast && tid < DM_MAX_BP) {
+    sh_cand[tid] = dm_breakpoint(g, tid);
   }
-  // The decoder trims trailing zeros (ldpc_decoder_impl.cpp:86-99): hand it the position of the last non-zero soft bit.
-  for (int o = 16; o > 0; o >>= 1) {
-    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-  }
-  if ((threadIdx.x & 31) == 0 && last > 0) {
-    atomicMax(&sh_last, last);
+  if (staged) {
+    dm_stage(g, llr, sh_in);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    prm.harq_last[d.harq_id] = sh_last;
+  DmLast last;
+  if (fast) {
+    if (tid < DM_MAX_BP) {
+      const int mine = sh_cand[tid];
+      int       rank = 0;
+      for (int k = 0; k != DM_MAX_BP; ++k) {
+        const int c = sh_cand[k];
+        rank += (c < mine || (c == mine && k < tid)) ? 1 : 0;
+      }
+      sh_bp[rank] = mine;
+    }
+    __syncthreads();
+    if (tid < DM_MAX_BP - 1) {
+      DmSeg sg;
+      sg.p0     = sh_bp[tid];
+      sg.p1     = sh_bp[tid + 1];
+      sg.ioff   = 0;
+      sg.action = DM_KEEP;
+      if (sg.p0 < sg.p1) {
+        sg.action = dm_classify(g, sg.p0, sg.ioff);
+      }
+      sh_seg[tid] = sg;
+    }
+    __syncthreads();
+    for (int s = 0; s != DM_MAX_BP - 1; ++s) {
+      const DmSeg sg = sh_seg[s];
+      const int   wa = max((sg.p0 + 3) >> 2, w_lo);
+      const int   wb = min(sg.p1 >> 2, w_hi);
+      if (wa < wb) {
+        dm_segment_words(g, llr, sh_in, out, sg.action, sg.ioff, wa, wb, last);
+      }
+    }
+    // Words cut by a breakpoint (and the incomplete last word).
+    if (tid < DM_MAX_BP) {
+      const int b = sh_bp[tid];
+      const int w = b >> 2;
+      bool      mine = (b & 3) != 0 && w >= w_lo && w < w_hi;
+      if (mine && tid > 0) {
+        const int prev = sh_bp[tid - 1];
+        mine           = !((prev & 3) != 0 && (prev >> 2) == w);
+      }
+      if (mine) {
+        last.note(w, dm_word_general<true>(g, llr, sh_in, out, w));
+      }
+    }
+  } else if (staged) {
+    for (int w = w_lo + tid; w < w_hi; w += blockDim.x) {
+      last.note(w, dm_word_general<true>(g, llr, sh_in, out, w));
+    }
+  } else {
+    for (int w = w_lo + tid; w < w_hi; w += blockDim.x) {
+      last.note(w, dm_word_general<false>(g, llr, sh_in, out, w));
+    }
+  }
+  // The decoder trims trailing zeros (ldpc_decoder_impl.cpp:86-99): hand it the position of the last non-zero soft
+  // bit, one slot per part (the decoder takes the maximum).
+  int pos = last.position();
+  for (int o = 16; o > 0; o >>= 1) {
+    pos = max(pos, __shfl_xor_sync(0xffffffffu, pos, o));
+  }
+  if ((tid & 31) == 0 && pos > 0) {
+    atomicMax(&sh_last, pos);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int32_t* slot    = prm.harq_last + (size_t)d.harq_id * DM_MAX_PARTS;
+    slot[blockIdx.y] = sh_last;
+    if (blockIdx.y == 0) {
+      for (int k = (int)gridDim.y; k < DM_MAX_PARTS; ++k) {
+        slot[k] = 0;
+      }
+    }
   }
 }
 
-inline cudaError_t launch_rate_dematch(const BatchParams& p, cudaStream_t s)
+inline cudaError_t launch_rate_dematch(const BatchParams& p, int sm_count, cudaStream_t s)
 {
   if (p.n_cb == 0) {
     return cudaSuccess;
   }
-  rate_dematch_kernel<<<p.n_cb, 256, 0, s>>>(p);
+  // Small batches are latency bound: up to DM_MAX_PARTS CTAs per codeblock until the GPU is filled a few times over.
+  int parts = 1;
+  while (parts < DM_MAX_PARTS && (size_t)p.n_cb * parts < (size_t)4 * sm_count) {
+    parts *= 2;
+  }
+  rate_dematch_kernel<<<dim3(p.n_cb, parts), DM_THREADS, 0, s>>>(p);
   return cudaGetLastError();
 }
 
