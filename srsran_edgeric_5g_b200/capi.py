@@ -4,6 +4,7 @@ The library is loaded from the package directory (in-tree build). There is no fa
 GPU raises.
 """
 import ctypes
+import os
 from pathlib import Path
 
 import numpy as np
@@ -78,7 +79,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    # PDC_LIBRARY: load a prebuilt library from elsewhere (deployment, A/B measurements) instead of the in-tree build.
+    path = os.environ.get("PDC_LIBRARY") or _build.build()
     L = ctypes.CDLL(str(path))
     L.pdc_default_config.argtypes = [ctypes.POINTER(Config)]
     L.pdc_default_config.restype = None

@@ -118,9 +118,10 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p, uint64_t po
 
 // The lifted graph of this (base graph, Z) in shared memory.
 struct GraphSmem {
-  uint32_t base4[MAX_EDGES];     // byte offset of the first soft word of the edge's variable node (col * Z * 4)
-  uint16_t shift4[MAX_EDGES];    // circulant shift of the edge, in bytes
-  uint32_t row_info[MAX_ROWS];   // first edge | degree << 16
+  // Per edge {circulant shift in bytes, byte offset of the first soft word of its variable node (col * Z * 4)}; every
+  // row starts on a 16-byte boundary so that one 128-bit load brings two edges.
+  uint2    einfo[MAX_EDGES + MAX_ROWS];
+  uint32_t row_info[MAX_ROWS]; // first einfo entry | degree << 16
 };
 
 
@@ -128,9 +129,8 @@ struct GraphSmem {
 //   soft     : shared-memory soft words, soft[col * Z + pos] as fp16x2 (addressed by byte offset)
 //   st/st_out: compressed messages of this row from the previous iteration / for the next one
 template <int DEG>
-__device__ __forceinline__ void process_row(unsigned char* soft, const uint16_t* __restrict__ e_shift,
-                                            const uint32_t* __restrict__ e_base, uint32_t j4, uint32_t Z4,
-                                            const RowState& st, RowState& st_out, int scale_mode)
+__device__ __forceinline__ void process_row(unsigned char* soft, const uint4* __restrict__ e_info, uint32_t j4,
+                                            uint32_t neg_Z4, const RowState& st, RowState& st_out, int scale_mode)
 {
   constexpr bool PACKED_MIN = DEG > 16;
   constexpr int  F0         = PACKED_MIN ? 1 : 2; // index of the first flag word
@@ -155,16 +155,20 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint16_t*
 
   __half2 min1 = h120, min2 = h120, a_prev = h120;
   hh      par = 0, ps = 0, pm = 0;
+  uint4   ei  = make_uint4(0, 0, 0, 0);
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
+    if ((e & 1) == 0) {
+      ei = e_info[e >> 1];
+    }
     if ((e & 7) == 0) {
       hh f = st_word(st, F0 + (e >> 3));
       pm   = f;      // "held the minimum" flags: bit 15 of each half = edge e, then e+1, ... after each shift
       ps   = f << 8; // sign flags
     }
-    uint32_t pos = j4 + e_shift[e];
-    pos          = min(pos, pos - Z4); // wrap: pos - Z underflows to a huge value when pos < Z
-    addr[e]      = e_base[e] + pos;
+    const uint32_t t = j4 + ((e & 1) ? ei.z : ei.x);
+    // wrap: t - Z underflows to a huge value when t < Z (one fused add + unsigned minimum)
+    addr[e] = ((e & 1) ? ei.w : ei.y) + __viaddmin_u32(t, neg_Z4, t);
     const __half2 s    = H(*reinterpret_cast<const hh*>(soft + addr[e]));
     const __half2 z    = H(lop_and_or(pm, H_SIGN, H_ONE));
     const __half2 sg   = H(lop_and_or(ps, H_SIGN, H_ONE));
@@ -248,29 +252,28 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint16_t*
   }
 }
 
-__device__ __forceinline__ void dispatch_row(int deg, unsigned char* soft_addr, const uint16_t* e_shift,
-                                             const uint32_t* e_base, uint32_t j, uint32_t Z, const RowState& st,
-                                             RowState& st_out, int scale_mode)
+__device__ __forceinline__ void dispatch_row(int deg, unsigned char* soft_addr, const uint4* e_info, uint32_t j,
+                                             uint32_t Z, const RowState& st, RowState& st_out, int scale_mode)
 {
   // Most frequent degrees first (BG1: 18 rows of degree 5, 8 of degree 6, ...).
   if (deg == 5) {
-    process_row<5>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+    process_row<5>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
   } else if (deg == 6) {
-    process_row<6>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+    process_row<6>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
   } else if (deg == 4) {
-    process_row<4>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+    process_row<4>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
   } else if (deg == 7) {
-    process_row<7>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+    process_row<7>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
   } else if (deg == 19) {
-    process_row<19>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+    process_row<19>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
   } else if (deg == 3) {
-    process_row<3>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+    process_row<3>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
   } else if (deg == 8) {
-    process_row<8>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+    process_row<8>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
   } else if (deg == 9) {
-    process_row<9>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+    process_row<9>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
   } else {
-    process_row<10>(soft_addr, e_shift, e_base, j, Z, st, st_out, scale_mode);
+    process_row<10>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
   }
 }
 
@@ -430,6 +433,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       off += (size_t)n_words * 4 + 16;
       wgt[1] = reinterpret_cast<uint32_t*>(smem_raw + off);
       off += (size_t)n_words * 4 + 16;
+      off          = (off + 15) & ~(size_t)15;
       GraphSmem& g = *reinterpret_cast<GraphSmem*>(smem_raw + off);
 
       // Compressed messages: one uint4 per (row, check), private to thread j.
@@ -438,8 +442,10 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       unsigned char* soft_addr = smem_raw;
 
       for (int i = tid; i < n_edges; i += nthr) {
-        g.shift4[i] = (uint16_t)(4 * (c_tab.v[b][set][i] % Z)); // ldpc_luts_impl.cpp:4536-4541
-        g.base4[i]  = (uint32_t)(c_tab.col[b][i] * Z * 4);
+        const int m  = c_tab.row[b][i];
+        const int pi = c_tab.row_pstart[b][m] + (i - c_tab.row_start[b][m]);
+        g.einfo[pi]  = make_uint2((uint32_t)(4 * (c_tab.v[b][set][i] % Z)), // ldpc_luts_impl.cpp:4536-4541
+                                  (uint32_t)(c_tab.col[b][i] * Z * 4));
       }
       for (int h = 0; h != 2; ++h) {
         if (lane[h].valid && lane[h].crc_kind != PDC_CRC_NONE) {
@@ -450,7 +456,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         }
       }
       for (int m = tid; m < rows; m += nthr) {
-        g.row_info[m] = (uint32_t)c_tab.row_start[b][m] |
+        g.row_info[m] = (uint32_t)c_tab.row_pstart[b][m] |
                         ((uint32_t)(c_tab.row_start[b][m + 1] - c_tab.row_start[b][m]) << 16);
       }
       // Last non-zero input of each codeblock (ldpc_decoder_impl.cpp:86-99): recorded by the rate dematcher for the
@@ -577,7 +583,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           st_state(st_thread + (uint32_t)m * st_stride, make_uint4(0, 0, 0, 0), pol_keep);
         }
       }
-      const uint32_t j4 = 4u * (uint32_t)j, Z4 = 4u * (uint32_t)Z;
+      const uint32_t j4 = 4u * (uint32_t)j, neg_Z4 = 0u - 4u * (uint32_t)Z;
       RowState       st_next = make_uint4(0, 0, 0, 0);
       for (int it = 0; it < max_iter; ++it) {
         uint4* sp = st_thread;
@@ -590,7 +596,8 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
             RowState       st_out = make_uint4(0, 0, 0, 0);
             uint4* const   spn    = (m + 1 < layers) ? sp + st_stride : st_thread;
             st_next               = ld_state(spn, pol_keep);
-            dispatch_row(deg, soft_addr, g.shift4 + e0, g.base4 + e0, j4, Z4, st, st_out, scale_mode);
+            dispatch_row(deg, soft_addr, reinterpret_cast<const uint4*>(g.einfo + e0), j4, neg_Z4, st, st_out,
+                         scale_mode);
             st_state(sp, st_out, pol_keep);
             sp = spn;
           }

@@ -33,6 +33,11 @@ inline cudaError_t upload_tables()
     while (r < rows) {
       h.row_start[bg][++r] = (uint16_t)n;
     }
+    h.row_pstart[bg][0] = 0;
+    for (int m = 0; m != rows; ++m) {
+      int deg                 = h.row_start[bg][m + 1] - h.row_start[bg][m];
+      h.row_pstart[bg][m + 1] = (uint16_t)(h.row_pstart[bg][m] + ((deg + 1) & ~1));
+    }
   }
   memset(h.set_index, 0xff, sizeof(h.set_index));
   for (int i = 0; i != NR_LDPC_NOF_LIFTING_SIZES; ++i) {
