@@ -206,42 +206,39 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint4* __
     s1 = __hadd2(__hfma2(min1, H(H_0P8), H(H_1024)), H(H_N1024));
     s2 = __hadd2(__hfma2(min2, H(H_0P8), H(H_1024)), H(H_N1024));
   }
-  const __half2 ds    = __hsub2(s2, s1);
   const hh      par_s = lop_and_or(par, H_SIGN, H_ONE);
 
-  __half2 acc_s = H(H_ZERO), acc_m = H(H_ZERO);
+  // Pass 2 is balanced between the two math pipes: the magnitude select and the "held the minimum" flags are bit
+  // operations on the comparison mask (ALU pipe), the message sum, the promotion and the sign flags are packed
+  // half-precision arithmetic (FMA pipe).
+  const hh s_diff = U(s1) ^ U(s2);
+  __half2  acc_s  = H(H_ZERO);
+  hh       acc_m  = 0;
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
-    const __half2 c   = vc[e];
-    const __half2 ism = __heq2(__habs2(c), min1);             // 1.0 if this edge holds the minimum, else 0.0
-    const __half2 mag = __hfma2(ism, ds, s1);                 // min2 for the minimum edge, min1 otherwise (scaled)
-    const __half2 sgn = H(lop_xor_and(par_s, U(c), H_SIGN));  // +-1: sign parity of the row without this edge
-    const __half2 x   = __hfma2(sgn, mag, c);
+    const __half2 c    = vc[e];
+    const hh      ism  = __heq2_mask(__habs2(c), min1);       // 0xffff per half if this edge holds the minimum
+    const __half2 mag  = H(lop_xor_and(U(s1), ism, s_diff));  // min2 for the minimum edge, min1 otherwise (scaled)
+    const __half2 sgn  = H(lop_xor_and(par_s, U(c), H_SIGN)); // +-1: sign parity of the row without this edge
+    const __half2 x    = __hfma2(sgn, mag, c);
     // Promotion (LLR.cpp:74-87): |x| > 120 -> +-infinity. pe = relu(544 |x| - 65280) is 0 up to |x| = 120 and at
     // least 544 from 121 on, where x * pe + x exceeds the half-precision range; an infinite x stays infinite.
     const __half2 pe = __hfma2_relu(__habs2(x), H(H_544), H(H_N65280));
     const __half2 r  = __hfma2(x, pe, x);
     *reinterpret_cast<hh*>(soft + addr[e]) = U(r);
-    acc_s = __hfma2(acc_s, H(H_TWO), sgn); // sum of +-2^k; turned into "negative" bits when the group is packed
-    acc_m = __hfma2(acc_m, H(H_TWO), ism);
+    acc_s = __hfma2(acc_s, H(H_TWO), sgn);                    // sum of +-2^k; turned into "negative" bits below
+    acc_m = lop_and_or(ism, H_SIGN >> (e & 7), acc_m);        // flag of the first edge of a group in the MSB
     if ((e & 7) == 7 || e == DEG - 1) {
-      // acc_s = sum over the n edges of the group of sgn * 2^(n-1-k): negative-edge bits = ((2^n - 1) - acc_s) / 2.
-      // Left-align a partial group, convert to integer bytes and pack {M B, S B, M A, S A}.
-      const int n_in_group = (e & 7) + 1;
-      const int fill       = 8 - n_in_group;
-      {
-        const float   full = (float)((1 << n_in_group) - 1) * 0.5f * (float)(1 << fill);
-        const __half2 sc   = H(0x38003800u + (uint32_t)fill * 0x04000400u); // 0.5 * 2^fill
-        acc_s              = __hfma2(acc_s, __hneg2(sc), __float2half2_rn(full));
-      }
-      if (fill) {
-        const __half2 sc = H(0x3C003C00u + (uint32_t)fill * 0x04000400u); // 2^fill
-        acc_m            = __hmul2(acc_m, sc);
-      }
-      st_word(st_out, F0 + (e >> 3)) =
-          __byte_perm(U(__hadd2(acc_s, H(H_1024))), U(__hadd2(acc_m, H(H_1024))), 0x6240);
+      // acc_s = sum over the n edges of the group of sgn * 2^(n-1-k): negative-edge bits = ((2^n - 1) - acc_s) / 2,
+      // left-aligned for a partial group and converted to an integer byte through the 1024 binade.
+      const int     n_in_group = (e & 7) + 1;
+      const int     fill       = 8 - n_in_group;
+      const float   full       = (float)((1 << n_in_group) - 1) * 0.5f * (float)(1 << fill);
+      const __half2 sc         = H(0x38003800u + (uint32_t)fill * 0x04000400u); // 0.5 * 2^fill
+      acc_s                    = __hadd2(__hfma2(acc_s, __hneg2(sc), __float2half2_rn(full)), H(H_1024));
+      st_word(st_out, F0 + (e >> 3)) = lop_and_or(U(acc_s), 0x00ff00ffu, acc_m);
       acc_s = H(H_ZERO);
-      acc_m = H(H_ZERO);
+      acc_m = 0;
     }
   }
   if (PACKED_MIN) {
