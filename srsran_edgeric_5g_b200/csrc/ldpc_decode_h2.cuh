@@ -292,46 +292,6 @@ __host__ __device__ inline size_t h2_smem_bytes(int bg, int Z)
   return soft + bits + sizeof(GraphSmem) + 64;
 }
 
-// Hard decision of one half of the soft words + "any zero" flag, MSB-first packed into bits[].
-__device__ __forceinline__ int hard_bits(const hh* soft, int half, int K, uint32_t* bits, int tid, int nthr)
-{
-  int       any_zero = 0;
-  const int n_words  = (K + 31) / 32;
-  for (int w = tid >> 5; w < n_words; w += nthr >> 5) {
-    int      i  = 32 * w + (tid & 31);
-    uint32_t h  = (i < K) ? ((soft[i] >> (16 * half)) & 0xffffu) : 0x3C00u;
-    bool     z  = (h & 0x7fffu) == 0;
-    bool     ng = (h & 0x8000u) != 0;
-    uint32_t bw = __brev(__ballot_sync(0xffffffffu, z || ng));
-    any_zero |= z;
-    if ((tid & 31) == 0) {
-      bits[w] = bw;
-    }
-  }
-  return any_zero;
-}
-
-// wgt[t] = x^(32 (T-1-t)) mod P, staged in shared memory (a divergent constant-memory index would serialise the warp).
-__device__ __forceinline__ uint32_t crc_partial(const uint32_t* bits, const uint32_t* wgt, int nb, int crc_kind, int tid,
-                                                int nthr)
-{
-  const int      T     = (nb + 31) / 32;
-  const uint32_t poly  = crc_poly(crc_kind);
-  const int      order = crc_order(crc_kind);
-  uint32_t       acc   = 0;
-  for (int t = tid; t < T; t += nthr) {
-    uint32_t w = bits[t];
-    if (t == T - 1 && (nb & 31)) {
-      w &= 0xffffffffu << (32 - (nb & 31));
-    }
-    acc ^= gf2_mulmod(w, wgt[t], poly, order);
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
-  }
-  return acc;
-}
-
 template <int MAX_THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
     ldpc_decode_h2_kernel(BatchParams prm, hh* state_scratch, uint32_t scratch_stride_words)
@@ -339,9 +299,11 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ LaneInfo lane[2];
   __shared__ int      sh_last[2];
-  __shared__ uint32_t           sh_crc[2];
-  __shared__ unsigned long long sh_acc[2];
-  __shared__ int      sh_any_zero[2];
+  __shared__ unsigned long long sh_part[2][MAX_THREADS / 32]; // per-warp unreduced CRC remainders
+  __shared__ int                sh_zpart[MAX_THREADS / 32];   // per-warp "a message soft bit is zero" flags
+  __shared__ uint32_t           sh_red[2][32];                // x^(order + k) mod P of each codeblock's CRC
+  __shared__ int                sh_publish[2];
+  __shared__ pdc_cb_result      sh_result[2];
   __shared__ int      sh_defer_b; // codeblock B could not be decoded together with A: it gets its own pass
 
   const int tid  = threadIdx.x;
@@ -444,13 +406,28 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         g.einfo[pi]  = make_uint2((uint32_t)(4 * (c_tab.v[b][set][i] % Z)), // ldpc_luts_impl.cpp:4536-4541
                                   (uint32_t)(c_tab.col[b][i] * Z * 4));
       }
+      // CRC word weights: wgt[t] = x^(32 (T-1-t)) mod P for the T words of the K - F checked bits, zero beyond.
       for (int h = 0; h != 2; ++h) {
+        const bool with_crc = lane[h].valid && lane[h].crc_kind != PDC_CRC_NONE;
+        const int  T        = with_crc ? (K - lane[h].F + 31) / 32 : 0;
+        for (int t = tid; t < n_words; t += nthr) {
+          wgt[h][t] = (t < T) ? c_tab.xpow32[lane[h].crc_kind - 1][T - 1 - t] : 0u;
+        }
+      }
+      for (int idx = tid; idx < 64; idx += nthr) {
+        const int h = idx >> 5, k = idx & 31;
+        uint32_t  r = 0;
         if (lane[h].valid && lane[h].crc_kind != PDC_CRC_NONE) {
-          const int T = (K - lane[h].F + 31) / 32;
-          for (int t = tid; t < T; t += nthr) {
-            wgt[h][t] = c_tab.xpow32[lane[h].crc_kind - 1][T - 1 - t];
+          const uint32_t poly = crc_poly(lane[h].crc_kind), top = 1u << crc_order(lane[h].crc_kind);
+          r = poly ^ top; // x^order mod P
+          for (int i = 0; i != k; ++i) {
+            r <<= 1;
+            if (r & top) {
+              r ^= poly;
+            }
           }
         }
+        sh_red[h][k] = r;
       }
       for (int m = tid; m < rows; m += nthr) {
         g.row_info[m] = (uint32_t)c_tab.row_pstart[b][m] |
@@ -605,117 +582,109 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         const bool any_early = (lane[0].valid && lane[0].early && !lane[0].done) ||
                                (lane[1].valid && lane[1].early && !lane[1].done);
         if (any_early || last_it) {
-          if (tid < 2) {
-            sh_acc[tid]      = 0ull;
-            sh_any_zero[tid] = 0;
-          }
           // get_hard_bits (:126-134) of both codeblocks in one sweep: bit = soft <= 0, MSB first; a zero among the K
-          // message soft bits blocks the early stop.
+          // message soft bits blocks the early stop. The CRC is folded into the same sweep as M(x) mod P == 0 with
+          // M(x) = sum_t W_t(x) x^(32 (T-1-t)): the lane holding bit b of word t adds the UNREDUCED product
+          // wgt[t] x^(31-b); the sum is reduced modulo P once, one bit per lane, by the first warp.
           {
-            int za = 0, zb = 0;
-#pragma unroll 4
-            for (int w = tid >> 5; w < n_words; w += nthr >> 5) {
-              const int      i  = 32 * w + (tid & 31);
-              const uint32_t sw = (i < K) ? soft[i] : 0x3C003C00u;
-              const bool     z0 = (sw & 0x7fffu) == 0, z1 = (sw & 0x7fff0000u) == 0;
-              const uint32_t b0 = __brev(__ballot_sync(0xffffffffu, z0 || (sw & 0x8000u)));
-              const uint32_t b1 = __brev(__ballot_sync(0xffffffffu, z1 || (sw & 0x80000000u)));
-              za |= z0;
-              zb |= z1;
-              if ((tid & 31) == 0) {
+            const int      lane_id = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
+            const int      nb0 = lane[0].valid ? K - lane[0].F : 0, nb1 = lane[1].valid ? K - lane[1].F : 0;
+            const int      shl = 31 - lane_id;
+            uint64_t       acc0 = 0, acc1 = 0;
+            uint32_t       zacc = 0;
+#pragma unroll 2
+            for (int w = warp; w < n_words; w += n_warps) {
+              const int      i  = 32 * w + lane_id;
+              const __half2  sw = H((i < K) ? soft[i] : H_ONE);
+              const uint32_t zm = __heq2_mask(sw, H(H_ZERO)); // 0xffff per half: the soft bit is zero
+              const uint32_t hm = __hle2_mask(sw, H(H_ZERO)); // 0xffff per half: hard bit 1 (soft <= 0)
+              const bool     h0 = (hm & 0xffffu) != 0, h1 = (hm >> 16) != 0;
+              const uint32_t b0 = __brev(__ballot_sync(0xffffffffu, h0));
+              const uint32_t b1 = __brev(__ballot_sync(0xffffffffu, h1));
+              zacc |= zm;
+              if (lane_id == 0) {
                 bits[0][w] = b0;
                 bits[1][w] = b1;
               }
+              const uint64_t w0 = (uint64_t)wgt[0][w] << shl, w1 = (uint64_t)wgt[1][w] << shl;
+              acc0 ^= (h0 && i < nb0) ? w0 : 0ull;
+              acc1 ^= (h1 && i < nb1) ? w1 : 0ull;
             }
-            if (za) {
-              sh_any_zero[0] = 1;
-            }
-            if (zb) {
-              sh_any_zero[1] = 1;
-            }
-          }
-          __syncthreads();
-          // CRC as M(x) mod P == 0 with M(x) = sum_t W_t(x) x^(32 (T-1-t)): every thread forms the UNREDUCED carry-less
-          // product of its word with its weight (independent steps), the products are XOR-reduced, and only the sum is
-          // reduced modulo P.
-          for (int h = 0; h != 2; ++h) {
-            if (!lane[h].valid || lane[h].done || !(lane[h].early || last_it) || lane[h].crc_kind == PDC_CRC_NONE) {
-              continue;
-            }
-            const int nb = K - lane[h].F;
-            const int T  = (nb + 31) / 32;
-            uint64_t  acc = 0;
-            for (int t = tid; t < T; t += nthr) {
-              uint32_t w = bits[h][t];
-              if (t == T - 1 && (nb & 31)) {
-                w &= 0xffffffffu << (32 - (nb & 31));
-              }
-              const uint64_t a = wgt[h][t];
-#pragma unroll
-              for (int i = 0; i != 32; ++i) {
-                acc ^= (a << i) & (0ull - (uint64_t)((w >> i) & 1u));
-              }
-            }
+            const int za = __any_sync(0xffffffffu, (zacc & 0xffffu) != 0);
+            const int zb = __any_sync(0xffffffffu, (zacc >> 16) != 0);
             for (int o = 16; o > 0; o >>= 1) {
-              acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+              acc0 ^= __shfl_xor_sync(0xffffffffu, acc0, o);
+              acc1 ^= __shfl_xor_sync(0xffffffffu, acc1, o);
             }
-            if ((tid & 31) == 0 && acc) {
-              atomicXor(&sh_acc[h], (unsigned long long)acc);
+            if (lane_id == 0) {
+              sh_part[0][warp] = acc0;
+              sh_part[1][warp] = acc1;
+              sh_zpart[warp]   = (za ? 1 : 0) | (zb ? 2 : 0);
             }
-          }
-          __syncthreads();
-          if (tid < 2 && lane[tid].valid && lane[tid].crc_kind != PDC_CRC_NONE) {
-            const uint64_t poly  = crc_poly(lane[tid].crc_kind);
-            const int      order = crc_order(lane[tid].crc_kind);
-            uint64_t       v     = sh_acc[tid];
-            for (int bit = 55; bit >= order; --bit) {
-              if ((v >> bit) & 1ull) {
-                v ^= poly << (bit - order);
+            __syncthreads();
+            if (warp == 0) {
+              uint64_t v0 = (lane_id < n_warps) ? sh_part[0][lane_id] : 0ull;
+              uint64_t v1 = (lane_id < n_warps) ? sh_part[1][lane_id] : 0ull;
+              int      zz = (lane_id < n_warps) ? sh_zpart[lane_id] : 0;
+              for (int o = 16; o > 0; o >>= 1) {
+                v0 ^= __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 ^= __shfl_xor_sync(0xffffffffu, v1, o);
+                zz |= __shfl_xor_sync(0xffffffffu, zz, o);
               }
-            }
-            sh_crc[tid] = (uint32_t)v;
-          }
-          __syncthreads();
-          // Publish finished codeblocks while their bits are in shared memory.
-          for (int h = 0; h != 2; ++h) {
-            if (!lane[h].valid || lane[h].done || !(lane[h].early || last_it)) {
-              continue;
-            }
-            const bool pass_crc = (lane[h].crc_kind != PDC_CRC_NONE) && (sh_crc[h] == 0);
-            const bool stop     = lane[h].early && pass_crc && !sh_any_zero[h];
-            if (stop || last_it) {
-              uint8_t*  out    = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
-              uint8_t*  out_h  = prm.harq_data + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_BYTES;
-              const int nbytes = (K + 7) / 8;
-              for (int w = tid; w < n_words; w += nthr) {
-                uint32_t v = bits[h][w];
-#pragma unroll
-                for (int k = 0; k != 4; ++k) {
-                  if (4 * w + k < nbytes) {
-                    out[4 * w + k]   = (uint8_t)(v >> (24 - 8 * k));
-                    out_h[4 * w + k] = (uint8_t)(v >> (24 - 8 * k));
+              for (int h = 0; h != 2; ++h) {
+                const uint64_t v     = h ? v1 : v0;
+                const int      kind  = lane[h].crc_kind;
+                const int      order = crc_order(kind);
+                uint32_t       part  = ((v >> (order + lane_id)) & 1ull) ? sh_red[h][lane_id] : 0u;
+                for (int o = 16; o > 0; o >>= 1) {
+                  part ^= __shfl_xor_sync(0xffffffffu, part, o);
+                }
+                const uint32_t crc = part ^ ((uint32_t)v & ((1u << order) - 1u));
+                if (lane_id == 0) {
+                  const bool active   = lane[h].valid && !lane[h].done && (lane[h].early || last_it);
+                  const bool pass_crc = (kind != PDC_CRC_NONE) && (crc == 0);
+                  const bool stop     = lane[h].early && pass_crc && !((zz >> h) & 1);
+                  sh_publish[h]       = (active && (stop || last_it)) ? 1 : 0;
+                  pdc_cb_result r;
+                  r.crc_ok     = lane[h].early ? (stop ? 1 : 0) : (pass_crc ? 1 : 0);
+                  r.iters      = (uint8_t)(stop ? it + 1 : lane[h].max_iter);
+                  r.status     = 0;
+                  r.nlayers    = (uint8_t)lane[h].layers;
+                  sh_result[h] = r;
+                  if (active && stop) {
+                    lane[h].done = 1;
                   }
                 }
               }
-              if (tid == 0) {
-                pdc_cb_result r;
-                r.crc_ok  = lane[h].early ? (stop ? 1 : 0) : (pass_crc ? 1 : 0);
-                r.iters   = (uint8_t)(stop ? it + 1 : lane[h].max_iter);
-                r.status  = 0;
-                r.nlayers = (uint8_t)lane[h].layers;
-                prm.results[lane[h].cb] = r;
+            }
+            __syncthreads();
+          }
+          // Publish finished codeblocks while their bits are in shared memory (the bits of a word are MSB first, the
+          // output is a byte string: byte-reverse and store whole words, single bytes at the tail).
+          for (int h = 0; h != 2; ++h) {
+            if (!sh_publish[h]) {
+              continue;
+            }
+            uint8_t*  out    = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
+            uint8_t*  out_h  = prm.harq_data + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_BYTES;
+            const int nbytes = (K + 7) / 8;
+            for (int w = tid; w < n_words; w += nthr) {
+              const uint32_t v = bits[h][w];
+              if (4 * w + 4 <= nbytes) {
+                const uint32_t le = __byte_perm(v, 0, 0x0123);
+                reinterpret_cast<uint32_t*>(out)[w]   = le;
+                reinterpret_cast<uint32_t*>(out_h)[w] = le;
+              } else {
+                for (int k = 0; 4 * w + k < nbytes; ++k) {
+                  out[4 * w + k]   = (uint8_t)(v >> (24 - 8 * k));
+                  out_h[4 * w + k] = (uint8_t)(v >> (24 - 8 * k));
+                }
               }
             }
-          }
-          __syncthreads();
-          if (tid == 0) {
-            for (int h = 0; h != 2; ++h) {
-              if (lane[h].valid && !lane[h].done && lane[h].early && sh_crc[h] == 0 && !sh_any_zero[h]) {
-                lane[h].done = 1;
-              }
+            if (tid == 0) {
+              prm.results[lane[h].cb] = sh_result[h];
             }
           }
-          __syncthreads();
           const bool all_done = (!lane[0].valid || lane[0].done) && (!lane[1].valid || lane[1].done);
           if (all_done) {
             break;
