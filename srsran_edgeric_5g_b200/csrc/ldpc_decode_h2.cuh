@@ -288,7 +288,7 @@ __host__ __device__ inline size_t h2_smem_bytes(int bg, int Z)
   int    n_full = (bg == 1) ? 68 : 52;
   int    kb     = (bg == 1) ? 22 : 10;
   size_t soft   = (size_t)n_full * Z * 4;
-  size_t bits   = 4 * ((size_t)((kb * Z + 31) / 32) * 4 + 16); // hard bits + CRC weights of both codeblocks
+  size_t bits   = (size_t)((kb * Z + 31) / 32) * 8 + 16; // CRC word weights of both codeblocks
   return soft + bits + sizeof(GraphSmem) + 64;
 }
 
@@ -382,16 +382,8 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       size_t off  = 0;
       hh*    soft = reinterpret_cast<hh*>(smem_raw);
       off += (size_t)n_full * Z * 4;
-      uint32_t* bits[2];
-      bits[0] = reinterpret_cast<uint32_t*>(smem_raw + off);
-      off += (size_t)n_words * 4 + 16;
-      bits[1] = reinterpret_cast<uint32_t*>(smem_raw + off);
-      off += (size_t)n_words * 4 + 16;
-      uint32_t* wgt[2]; // CRC word weights of each codeblock
-      wgt[0] = reinterpret_cast<uint32_t*>(smem_raw + off);
-      off += (size_t)n_words * 4 + 16;
-      wgt[1] = reinterpret_cast<uint32_t*>(smem_raw + off);
-      off += (size_t)n_words * 4 + 16;
+      uint2* wgt = reinterpret_cast<uint2*>(smem_raw + off); // CRC word weights {codeblock A, codeblock B}
+      off += (size_t)n_words * 8;
       off          = (off + 15) & ~(size_t)15;
       GraphSmem& g = *reinterpret_cast<GraphSmem*>(smem_raw + off);
 
@@ -406,12 +398,17 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         g.einfo[pi]  = make_uint2((uint32_t)(4 * (c_tab.v[b][set][i] % Z)), // ldpc_luts_impl.cpp:4536-4541
                                   (uint32_t)(c_tab.col[b][i] * Z * 4));
       }
-      // CRC word weights: wgt[t] = x^(32 (T-1-t)) mod P for the T words of the K - F checked bits, zero beyond.
-      for (int h = 0; h != 2; ++h) {
-        const bool with_crc = lane[h].valid && lane[h].crc_kind != PDC_CRC_NONE;
-        const int  T        = with_crc ? (K - lane[h].F + 31) / 32 : 0;
+      // CRC word weights: x^(32 (T-1-t)) mod P for the T words of the K - F checked bits, zero beyond.
+      {
+        int kind[2], T[2];
+        for (int h = 0; h != 2; ++h) {
+          const bool with_crc = lane[h].valid && lane[h].crc_kind != PDC_CRC_NONE;
+          kind[h]             = with_crc ? lane[h].crc_kind - 1 : 0;
+          T[h]                = with_crc ? (K - lane[h].F + 31) / 32 : 0;
+        }
         for (int t = tid; t < n_words; t += nthr) {
-          wgt[h][t] = (t < T) ? c_tab.xpow32[lane[h].crc_kind - 1][T - 1 - t] : 0u;
+          wgt[t] = make_uint2((t < T[0]) ? c_tab.xpow32[kind[0]][T[0] - 1 - t] : 0u,
+                              (t < T[1]) ? c_tab.xpow32[kind[1]][T[1] - 1 - t] : 0u);
         }
       }
       for (int idx = tid; idx < 64; idx += nthr) {
@@ -582,34 +579,43 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         const bool any_early = (lane[0].valid && lane[0].early && !lane[0].done) ||
                                (lane[1].valid && lane[1].early && !lane[1].done);
         if (any_early || last_it) {
-          // get_hard_bits (:126-134) of both codeblocks in one sweep: bit = soft <= 0, MSB first; a zero among the K
-          // message soft bits blocks the early stop. The CRC is folded into the same sweep as M(x) mod P == 0 with
+          // get_hard_bits (:126-134) of both codeblocks in one sweep: bit = soft <= 0; a zero among the K message soft
+          // bits blocks the early stop. The CRC is computed in the same sweep as M(x) mod P == 0 with
           // M(x) = sum_t W_t(x) x^(32 (T-1-t)): the lane holding bit b of word t adds the UNREDUCED product
           // wgt[t] x^(31-b); the sum is reduced modulo P once, one bit per lane, by the first warp.
           {
-            const int      lane_id = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
-            const int      nb0 = lane[0].valid ? K - lane[0].F : 0, nb1 = lane[1].valid ? K - lane[1].F : 0;
-            const int      shl = 31 - lane_id;
-            uint64_t       acc0 = 0, acc1 = 0;
-            uint32_t       zacc = 0;
-#pragma unroll 2
-            for (int w = warp; w < n_words; w += n_warps) {
+            const int lane_id = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
+            const int nb0 = lane[0].valid ? K - lane[0].F : 0, nb1 = lane[1].valid ? K - lane[1].F : 0;
+            const int shl = 31 - lane_id;
+            // Words entirely inside the checked bits of both codeblocks need no bound test.
+            const int w_safe = min(nb0, nb1) >> 5;
+            uint32_t  a0l = 0, a0h = 0, a1l = 0, a1h = 0, zacc = 0;
+            auto      sweep = [&](int w, bool bounded) {
               const int      i  = 32 * w + lane_id;
               const __half2  sw = H((i < K) ? soft[i] : H_ONE);
               const uint32_t zm = __heq2_mask(sw, H(H_ZERO)); // 0xffff per half: the soft bit is zero
               const uint32_t hm = __hle2_mask(sw, H(H_ZERO)); // 0xffff per half: hard bit 1 (soft <= 0)
-              const bool     h0 = (hm & 0xffffu) != 0, h1 = (hm >> 16) != 0;
-              const uint32_t b0 = __brev(__ballot_sync(0xffffffffu, h0));
-              const uint32_t b1 = __brev(__ballot_sync(0xffffffffu, h1));
-              zacc |= zm;
-              if (lane_id == 0) {
-                bits[0][w] = b0;
-                bits[1][w] = b1;
+              uint32_t       m0 = __byte_perm(hm, 0, 0x1010), m1 = __byte_perm(hm, 0, 0x3232);
+              if (bounded) {
+                m0 = (i < nb0) ? m0 : 0u;
+                m1 = (i < nb1) ? m1 : 0u;
               }
-              const uint64_t w0 = (uint64_t)wgt[0][w] << shl, w1 = (uint64_t)wgt[1][w] << shl;
-              acc0 ^= (h0 && i < nb0) ? w0 : 0ull;
-              acc1 ^= (h1 && i < nb1) ? w1 : 0ull;
+              const uint2 wg = wgt[w];
+              zacc |= zm;
+              a0l = lop_xor_and(a0l, wg.x << shl, m0);
+              a0h = lop_xor_and(a0h, __funnelshift_l(wg.x, 0u, shl), m0);
+              a1l = lop_xor_and(a1l, wg.y << shl, m1);
+              a1h = lop_xor_and(a1h, __funnelshift_l(wg.y, 0u, shl), m1);
+            };
+            int w = warp;
+#pragma unroll 2
+            for (; w < w_safe; w += n_warps) {
+              sweep(w, false);
             }
+            for (; w < n_words; w += n_warps) {
+              sweep(w, true);
+            }
+            uint64_t acc0 = ((uint64_t)a0h << 32) | a0l, acc1 = ((uint64_t)a1h << 32) | a1l;
             const int za = __any_sync(0xffffffffu, (zacc & 0xffffu) != 0);
             const int zb = __any_sync(0xffffffffu, (zacc >> 16) != 0);
             for (int o = 16; o > 0; o >>= 1) {
@@ -659,30 +665,38 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
             }
             __syncthreads();
           }
-          // Publish finished codeblocks while their bits are in shared memory (the bits of a word are MSB first, the
-          // output is a byte string: byte-reverse and store whole words, single bytes at the tail).
-          for (int h = 0; h != 2; ++h) {
-            if (!sh_publish[h]) {
-              continue;
+          // Publish finished codeblocks: hard decisions packed MSB first, one 32-bit word per warp step.
+          if (sh_publish[0] || sh_publish[1]) {
+            const int lane_id = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
+            const int nbytes  = (K + 7) / 8;
+            uint8_t*  out[2];
+            uint8_t*  out_h[2];
+            for (int h = 0; h != 2; ++h) {
+              out[h]   = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
+              out_h[h] = sh_publish[h] ? prm.harq_data + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_BYTES : nullptr;
             }
-            uint8_t*  out    = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
-            uint8_t*  out_h  = prm.harq_data + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_BYTES;
-            const int nbytes = (K + 7) / 8;
-            for (int w = tid; w < n_words; w += nthr) {
-              const uint32_t v = bits[h][w];
-              if (4 * w + 4 <= nbytes) {
-                const uint32_t le = __byte_perm(v, 0, 0x0123);
-                reinterpret_cast<uint32_t*>(out)[w]   = le;
-                reinterpret_cast<uint32_t*>(out_h)[w] = le;
-              } else {
-                for (int k = 0; 4 * w + k < nbytes; ++k) {
-                  out[4 * w + k]   = (uint8_t)(v >> (24 - 8 * k));
-                  out_h[4 * w + k] = (uint8_t)(v >> (24 - 8 * k));
+            for (int w = warp; w < n_words; w += n_warps) {
+              const int      i  = 32 * w + lane_id;
+              const uint32_t hm = __hle2_mask(H((i < K) ? soft[i] : H_ONE), H(H_ZERO));
+              const uint32_t b0 = __ballot_sync(0xffffffffu, (hm & 0xffffu) != 0);
+              const uint32_t b1 = __ballot_sync(0xffffffffu, (hm >> 16) != 0);
+              if (lane_id < 2 && sh_publish[lane_id]) {
+                // Lane k holds bit k of the ballot = bit 31-k of the MSB-first word: reversing the bits of each byte
+                // gives the byte string in memory order.
+                const uint32_t le = __byte_perm(__brev(lane_id ? b1 : b0), 0, 0x0123);
+                if (4 * w + 4 <= nbytes) {
+                  reinterpret_cast<uint32_t*>(out[lane_id])[w]   = le;
+                  reinterpret_cast<uint32_t*>(out_h[lane_id])[w] = le;
+                } else {
+                  for (int k = 0; 4 * w + k < nbytes; ++k) {
+                    out[lane_id][4 * w + k]   = (uint8_t)(le >> (8 * k));
+                    out_h[lane_id][4 * w + k] = (uint8_t)(le >> (8 * k));
+                  }
                 }
               }
             }
-            if (tid == 0) {
-              prm.results[lane[h].cb] = sh_result[h];
+            if (tid < 2 && sh_publish[tid]) {
+              prm.results[lane[tid].cb] = sh_result[tid];
             }
           }
           const bool all_done = (!lane[0].valid || lane[0].done) && (!lane[1].valid || lane[1].done);
