@@ -93,7 +93,7 @@ typedef struct {
 typedef struct {
   uint32_t first_cb;
   uint32_t nof_cb;
-  uint32_t tbs_bits;      /* transport block size without CRC                                                         */
+  uint32_t tbs_bits;      /* transport block size without CRC (at most 2 097 088 bits; the largest NR TBS is 1 277 992) */
   uint32_t out_offset;    /* byte offset of this TB inside the batch TB output buffer                                 */
   uint32_t prev_ok_mask_offset; /* reserved, 0                                                                         */
 } pdc_tb_desc;

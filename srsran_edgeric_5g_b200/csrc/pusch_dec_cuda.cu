@@ -507,7 +507,7 @@ int pdc_submit(pdc_ctx*           ctx,
   for (uint32_t i = 0; i != n_tb; ++i) {
     size_t need = ((size_t)tbs[i].tbs_bits + 24 + 31) / 32 * 4;
     if ((tbs[i].out_offset & 3u) || (size_t)tbs[i].out_offset + need > ctx->cfg.max_tb_bytes ||
-        (size_t)tbs[i].first_cb + tbs[i].nof_cb > n_cb || tbs[i].nof_cb == 0) {
+        (size_t)tbs[i].first_cb + tbs[i].nof_cb > n_cb || tbs[i].nof_cb == 0 || need > 4u * 65535u) {
       return fail(PDC_ERR_INVALID, "pdc_submit: invalid transport block descriptor");
     }
     tb_out_bytes = std::max(tb_out_bytes, (size_t)tbs[i].out_offset + need);

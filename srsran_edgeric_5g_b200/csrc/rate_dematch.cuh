@@ -408,14 +408,15 @@ __device__ __forceinline__ void dm_segment_words(const DematchGeom& g, const int
 // Stage the rate-matched input in shared memory in deinterleaved order: sh[j * Kq + sym] = llr[sym * QM + j].
 // Four symbols per thread step: coalesced vector loads, bit planes separated with byte permutes.
 template <int QM>
-__device__ __forceinline__ void dm_stage_planes(const DematchGeom& g, const int8_t* __restrict__ llr, uint8_t* sh)
+__device__ __forceinline__ void dm_stage_planes(const DematchGeom& g, const int8_t* __restrict__ llr, uint8_t* sh,
+                                                int t0, int nt)
 {
   const uint8_t*  src      = reinterpret_cast<const uint8_t*>(llr);
   const int       n_groups = g.Kq >> 2;
   constexpr int   VEC      = (QM % 4 == 0) ? 16 : 8; // bytes per vector load (a group is 4 * QM bytes)
   const bool      aligned  = (reinterpret_cast<uintptr_t>(src) % VEC) == 0;
   const bool      word_st  = (g.Kq & 3) == 0;        // plane starts are word aligned
-  for (int grp = threadIdx.x; grp < n_groups; grp += blockDim.x) {
+  for (int grp = t0; grp < n_groups; grp += nt) {
     uint32_t       w[QM];
     const uint8_t* p = src + (size_t)grp * 4 * QM;
     if (aligned) {
@@ -462,30 +463,31 @@ __device__ __forceinline__ void dm_stage_planes(const DematchGeom& g, const int8
   }
   // Symbols after the last complete group.
   const int sym0 = 4 * n_groups;
-  for (int idx = threadIdx.x; idx < (g.Kq - sym0) * QM; idx += blockDim.x) {
+  for (int idx = t0; idx < (g.Kq - sym0) * QM; idx += nt) {
     const int s4 = idx / QM, j = idx - s4 * QM;
     sh[j * g.Kq + sym0 + s4] = src[(size_t)(sym0 + s4) * QM + j];
   }
 }
 
-__device__ __forceinline__ void dm_stage(const DematchGeom& g, const int8_t* __restrict__ llr, uint8_t* sh)
+// Thread t0 of the nt staging threads.
+__device__ __forceinline__ void dm_stage(const DematchGeom& g, const int8_t* __restrict__ llr, uint8_t* sh, int t0, int nt)
 {
   switch (g.qm) {
     case 2:
-      dm_stage_planes<2>(g, llr, sh);
+      dm_stage_planes<2>(g, llr, sh, t0, nt);
       break;
     case 4:
-      dm_stage_planes<4>(g, llr, sh);
+      dm_stage_planes<4>(g, llr, sh, t0, nt);
       break;
     case 6:
-      dm_stage_planes<6>(g, llr, sh);
+      dm_stage_planes<6>(g, llr, sh, t0, nt);
       break;
     case 8:
-      dm_stage_planes<8>(g, llr, sh);
+      dm_stage_planes<8>(g, llr, sh, t0, nt);
       break;
     default:
       // One bit per symbol: the stream is already in order. (Other modulation orders are never staged.)
-      for (int i = threadIdx.x; i < g.E; i += blockDim.x) {
+      for (int i = t0; i < g.E; i += nt) {
         sh[i] = (uint8_t)__ldg(llr + i);
       }
       break;
@@ -496,71 +498,78 @@ __device__ __forceinline__ void dm_stage(const DematchGeom& g, const int8_t* __r
 __global__ void __launch_bounds__(DM_THREADS, 3) rate_dematch_kernel(BatchParams prm)
 {
   __shared__ __align__(16) uint8_t sh_in[DM_STAGE_BYTES + 16];
-  __shared__ DematchGeom           g;
+  __shared__ DematchGeom           g_sh;
   __shared__ int                   ok;
   __shared__ int                   sh_last;
-  __shared__ int                   sh_cand[DM_MAX_BP];
   __shared__ int                   sh_bp[DM_MAX_BP];
   __shared__ DmSeg                 sh_seg[DM_MAX_BP];
   const int                        tid = threadIdx.x;
   uint32_t                         cb  = blockIdx.x;
-  const pdc_cb_desc&               d   = prm.cbs[cb];
+  const pdc_cb_desc                d   = prm.cbs[cb];
   if (!(d.flags & PDC_CB_DEMATCH)) {
     return;
   }
-  if (tid == 0) {
-    ok      = dm_geometry(d, prm.simd_width, g) && (d.harq_id < prm.harq_entries);
-    sh_last = 0;
+  // The first warp derives the geometry and the segments while the others stage the input, for which the modulation
+  // order and the length are enough.
+  const int8_t* llr = prm.llrs + d.llr_offset;
+  uint32_t*     out = reinterpret_cast<uint32_t*>(prm.harq + (size_t)min(d.harq_id, prm.harq_entries - 1) * PDC_MAX_CB_SOFT);
+  const int     qm = d.qm, E = d.rm_length;
+  const bool    staged = (qm == 1 || qm == 2 || qm == 4 || qm == 6 || qm == 8) && E > 0 && (E % qm) == 0 &&
+                      E <= DM_STAGE_BYTES;
+  if (tid < 32) {
+    if (tid == 0) {
+      ok      = dm_geometry(d, prm.simd_width, g_sh) && (d.harq_id < prm.harq_entries);
+      sh_last = 0;
+    }
+    __syncwarp();
+    if (ok && g_sh.staged && g_sh.E <= g_sh.Dn) {
+      // Sort the breakpoints (rank by counting) and classify the segments between them.
+      const int mine = dm_breakpoint(g_sh, min(tid, DM_MAX_BP - 1));
+      int       rank = 0;
+      for (int k = 0; k != DM_MAX_BP; ++k) {
+        const int c = __shfl_sync(0xffffffffu, mine, k);
+        rank += (c < mine || (c == mine && k < tid)) ? 1 : 0;
+      }
+      if (tid < DM_MAX_BP) {
+        sh_bp[rank] = mine;
+      }
+      __syncwarp();
+      if (tid < DM_MAX_BP - 1) {
+        DmSeg sg;
+        sg.p0     = sh_bp[tid];
+        sg.p1     = sh_bp[tid + 1];
+        sg.ioff   = 0;
+        sg.action = DM_KEEP;
+        if (sg.p0 < sg.p1) {
+          sg.action = dm_classify(g_sh, sg.p0, sg.ioff);
+        }
+        sh_seg[tid] = sg;
+      }
+    }
+  }
+  if (staged && tid >= 32) {
+    DematchGeom gs; // the fields staging needs
+    gs.qm = qm, gs.E = E, gs.Kq = E / qm;
+    dm_stage(gs, llr, sh_in, tid - 32, (int)blockDim.x - 32);
   }
   __syncthreads();
   if (!ok) {
     return; // the decode kernel reports the invalid descriptor
   }
-  const int8_t* llr    = prm.llrs + d.llr_offset;
-  uint32_t*     out    = reinterpret_cast<uint32_t*>(prm.harq + (size_t)d.harq_id * PDC_MAX_CB_SOFT);
-  const int     nw     = (g.N + 3) >> 2;
-  const bool    staged = g.staged != 0;
-  const bool    fast   = staged && g.E <= g.Dn; // single lap
-  const int     per    = (nw + (int)gridDim.y - 1) / (int)gridDim.y;
-  const int     w_lo   = (int)blockIdx.y * per;
-  const int     w_hi   = min(nw, w_lo + per);
-  if (fast && tid < DM_MAX_BP) {
-    sh_cand[tid] = dm_breakpoint(g, tid);
-  }
-  if (staged) {
-    dm_stage(g, llr, sh_in);
-  }
-  __syncthreads();
+  const int  N    = g_sh.N;
+  const int  nw   = (N + 3) >> 2;
+  const bool fast = staged && g_sh.E <= g_sh.Dn; // single lap
+  const int  per  = (nw + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int  w_lo = (int)blockIdx.y * per;
+  const int  w_hi = min(nw, w_lo + per);
   DmLast last;
   if (fast) {
-    if (tid < DM_MAX_BP) {
-      const int mine = sh_cand[tid];
-      int       rank = 0;
-      for (int k = 0; k != DM_MAX_BP; ++k) {
-        const int c = sh_cand[k];
-        rank += (c < mine || (c == mine && k < tid)) ? 1 : 0;
-      }
-      sh_bp[rank] = mine;
-    }
-    __syncthreads();
-    if (tid < DM_MAX_BP - 1) {
-      DmSeg sg;
-      sg.p0     = sh_bp[tid];
-      sg.p1     = sh_bp[tid + 1];
-      sg.ioff   = 0;
-      sg.action = DM_KEEP;
-      if (sg.p0 < sg.p1) {
-        sg.action = dm_classify(g, sg.p0, sg.ioff);
-      }
-      sh_seg[tid] = sg;
-    }
-    __syncthreads();
     for (int s = 0; s != DM_MAX_BP - 1; ++s) {
       const DmSeg sg = sh_seg[s];
       const int   wa = max((sg.p0 + 3) >> 2, w_lo);
       const int   wb = min(sg.p1 >> 2, w_hi);
       if (wa < wb) {
-        dm_segment_words(g, llr, sh_in, out, sg.action, sg.ioff, wa, wb, last);
+        dm_segment_words(g_sh, llr, sh_in, out, sg.action, sg.ioff, wa, wb, last);
       }
     }
     // Words cut by a breakpoint (and the incomplete last word).
@@ -573,16 +582,16 @@ __global__ void __launch_bounds__(DM_THREADS, 3) rate_dematch_kernel(BatchParams
         mine           = !((prev & 3) != 0 && (prev >> 2) == w);
       }
       if (mine) {
-        last.note(w, dm_word_general<true>(g, llr, sh_in, out, w));
+        last.note(w, dm_word_general<true>(g_sh, llr, sh_in, out, w));
       }
     }
   } else if (staged) {
     for (int w = w_lo + tid; w < w_hi; w += blockDim.x) {
-      last.note(w, dm_word_general<true>(g, llr, sh_in, out, w));
+      last.note(w, dm_word_general<true>(g_sh, llr, sh_in, out, w));
     }
   } else {
     for (int w = w_lo + tid; w < w_hi; w += blockDim.x) {
-      last.note(w, dm_word_general<false>(g, llr, sh_in, out, w));
+      last.note(w, dm_word_general<false>(g_sh, llr, sh_in, out, w));
     }
   }
   // The decoder trims trailing zeros (ldpc_decoder_impl.cpp:86-99): hand it the position of the last non-zero soft

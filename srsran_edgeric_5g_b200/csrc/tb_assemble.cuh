@@ -18,8 +18,10 @@ namespace pdc {
 constexpr int TB_THREADS = 512;
 constexpr int TB_SPLIT   = 16;
 
-// x^(32 * 2^i) mod CRC24A, i = 0..19, and the byte table T[b] = (b * x^24) mod P; filled at start-up.
-__constant__ uint32_t c_xpow_crc24a_pow2[20];
+// Two-level table of x^(32 e) mod CRC24A, e = 256 hi + lo (transport blocks of up to 65536 words), and the byte table
+// T[b] = (b * x^24) mod P; filled at start-up.
+__device__ uint32_t   g_xpow_crc24a_hi[256]; // x^(32 * 256 * i)
+__device__ uint32_t   g_xpow_crc24a_lo[256]; // x^(32 * i)
 __constant__ uint32_t c_crc24a_table[256];
 
 // 32 bits of a codeblock's decoded message starting at bit `off` (MSB first), zero beyond the buffer.
@@ -118,15 +120,10 @@ __global__ void __launch_bounds__(TB_THREADS) tb_assemble_kernel(TbParams prm, c
           crc           = ((crc << 8) ^ sh_table[((crc >> 16) ^ byte) & 0xffu]) & 0xffffffu;
         }
       }
-      // Weight by x^(32 * words after this run) mod P (square-and-multiply over the precomputed x^(32 2^i)).
-      uint32_t e  = T - last;
-      uint32_t xp = 1;
-      for (int i = 0; e != 0; ++i, e >>= 1) {
-        if (e & 1u) {
-          xp = gf2_mulmod(xp, c_xpow_crc24a_pow2[i], poly, 24);
-        }
-      }
-      crc = gf2_mulmod(crc, xp, poly, 24);
+      // Weight by x^(32 * words after this run) mod P.
+      const uint32_t e = T - last;
+      crc              = gf2_mulmod(crc, __ldg(&g_xpow_crc24a_hi[(e >> 8) & 255u]), poly, 24);
+      crc              = gf2_mulmod(crc, __ldg(&g_xpow_crc24a_lo[e & 255u]), poly, 24);
     }
     for (int o = 16; o > 0; o >>= 1) {
       crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
@@ -157,20 +154,29 @@ __global__ void __launch_bounds__(TB_THREADS) tb_assemble_kernel(TbParams prm, c
 
 inline cudaError_t upload_tb_tables()
 {
-  uint32_t h[20];
-  uint32_t poly = crc_poly(PDC_CRC24A);
-  uint32_t x    = 1;
+  static uint32_t lo[256], hi[256];
+  uint32_t        poly = crc_poly(PDC_CRC24A);
+  uint32_t        x32  = 1; // x^32 mod P
   for (int b = 0; b != 32; ++b) {
-    x <<= 1;
-    if (x & (1u << 24)) {
-      x ^= poly;
+    x32 <<= 1;
+    if (x32 & (1u << 24)) {
+      x32 ^= poly;
     }
   }
-  for (int i = 0; i != 20; ++i) {
-    h[i] = x;
-    x    = gf2_mulmod(x, x, poly, 24);
+  lo[0] = 1;
+  for (int i = 1; i != 256; ++i) {
+    lo[i] = gf2_mulmod(lo[i - 1], x32, poly, 24);
   }
-  cudaError_t e = cudaMemcpyToSymbol(c_xpow_crc24a_pow2, h, sizeof(h));
+  const uint32_t x8192 = gf2_mulmod(lo[255], x32, poly, 24); // x^(32 * 256)
+  hi[0]                = 1;
+  for (int i = 1; i != 256; ++i) {
+    hi[i] = gf2_mulmod(hi[i - 1], x8192, poly, 24);
+  }
+  cudaError_t e = cudaMemcpyToSymbol(g_xpow_crc24a_lo, lo, sizeof(lo));
+  if (e != cudaSuccess) {
+    return e;
+  }
+  e = cudaMemcpyToSymbol(g_xpow_crc24a_hi, hi, sizeof(hi));
   if (e != cudaSuccess) {
     return e;
   }
