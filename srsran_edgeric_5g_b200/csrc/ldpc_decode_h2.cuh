@@ -125,7 +125,15 @@ struct GraphSmem {
 };
 
 
-// One base-graph row (layer) of degree DEG for check j of both codeblocks.
+// CTA barrier that threads of one warp may reach from different places (partial last warp of a lifting size that is not
+// a multiple of 32): the non-aligned form.
+__device__ __forceinline__ void row_barrier()
+{
+  asm volatile("barrier.sync 0;" ::: "memory");
+}
+
+// One base-graph row (layer) of degree DEG for check j of both codeblocks. Contains the barrier that orders the row after
+// the previous one.
 //   soft     : shared-memory soft words, soft[col * Z + pos] as fp16x2 (addressed by byte offset)
 //   st/st_out: compressed messages of this row from the previous iteration / for the next one
 template <int DEG>
@@ -153,22 +161,31 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint4* __
   const __half2 mid = __hmul2(__hadd2(m1, m2), H(H_HALF));
   const __half2 hd  = __hmul2(__hsub2(m2, m1), H(H_HALF));
 
+  // Soft-word addresses of the row's edges: independent of the previous row, so they are formed BEFORE the barrier that
+  // orders this row after the previous one (the wait then overlaps useful work).
+  {
+    uint4 ei = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int e = 0; e != DEG; ++e) {
+      if ((e & 1) == 0) {
+        ei = e_info[e >> 1];
+      }
+      const uint32_t t = j4 + ((e & 1) ? ei.z : ei.x);
+      // wrap: t - Z underflows to a huge value when t < Z (one fused add + unsigned minimum)
+      addr[e] = ((e & 1) ? ei.w : ei.y) + __viaddmin_u32(t, neg_Z4, t);
+    }
+  }
+  row_barrier();
+
   __half2 min1 = h120, min2 = h120, a_prev = h120;
   hh      par = 0, ps = 0, pm = 0;
-  uint4   ei  = make_uint4(0, 0, 0, 0);
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
-    if ((e & 1) == 0) {
-      ei = e_info[e >> 1];
-    }
     if ((e & 7) == 0) {
       hh f = st_word(st, F0 + (e >> 3));
       pm   = f;      // "held the minimum" flags: bit 15 of each half = edge e, then e+1, ... after each shift
       ps   = f << 8; // sign flags
     }
-    const uint32_t t = j4 + ((e & 1) ? ei.z : ei.x);
-    // wrap: t - Z underflows to a huge value when t < Z (one fused add + unsigned minimum)
-    addr[e] = ((e & 1) ? ei.w : ei.y) + __viaddmin_u32(t, neg_Z4, t);
     const __half2 s    = H(*reinterpret_cast<const hh*>(soft + addr[e]));
     const __half2 z    = H(lop_and_or(pm, H_SIGN, H_ONE));
     const __half2 sg   = H(lop_and_or(ps, H_SIGN, H_ONE));
@@ -571,14 +588,16 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
                          scale_mode);
             st_state(sp, st_out, pol_keep);
             sp = spn;
+          } else {
+            row_barrier();
           }
-          __syncthreads();
         }
 
         const bool last_it   = (it + 1 == max_iter);
         const bool any_early = (lane[0].valid && lane[0].early && !lane[0].done) ||
                                (lane[1].valid && lane[1].early && !lane[1].done);
         if (any_early || last_it) {
+          row_barrier(); // the last row is complete
           // get_hard_bits (:126-134) of both codeblocks in one sweep: bit = soft <= 0; a zero among the K message soft
           // bits blocks the early stop. The CRC is computed in the same sweep as M(x) mod P == 0 with
           // M(x) = sum_t W_t(x) x^(32 (T-1-t)): the lane holding bit b of word t adds the UNREDUCED product
