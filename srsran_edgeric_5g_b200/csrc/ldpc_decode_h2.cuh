@@ -116,10 +116,29 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p, uint64_t po
   return v;
 }
 
+// Shared memory through explicit 32-bit shared-window addresses (a generic pointer makes the compiler rebuild the window
+// base from a special register in every row).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v)
+{
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v));
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t a)
+{
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+
 // The lifted graph of this (base graph, Z) in shared memory.
 struct GraphSmem {
-  // Per edge {circulant shift in bytes, byte offset of the first soft word of its variable node (col * Z * 4)}; every
-  // row starts on a 16-byte boundary so that one 128-bit load brings two edges.
+  // Per edge {circulant shift in bytes, shared-window address of the first soft word of its variable node}; every row
+  // starts on a 16-byte boundary so that one 128-bit load brings two edges.
   uint2    einfo[MAX_EDGES + MAX_ROWS];
   uint32_t row_info[MAX_ROWS]; // first einfo entry | degree << 16
 };
@@ -134,12 +153,14 @@ __device__ __forceinline__ void row_barrier()
 
 // One base-graph row (layer) of degree DEG for check j of both codeblocks. Contains the barrier that orders the row after
 // the previous one.
-//   soft     : shared-memory soft words, soft[col * Z + pos] as fp16x2 (addressed by byte offset)
-//   st/st_out: compressed messages of this row from the previous iteration / for the next one
+//   e_info : shared-window address of the row's edge table
+//   st     : in: compressed messages of this row from the previous iteration; out: those of the NEXT row (fetched from
+//            sp_next as soon as this row's are consumed). This row's new messages are stored to sp.
 template <int DEG>
-__device__ __forceinline__ void process_row(unsigned char* soft, const uint4* __restrict__ e_info, uint32_t j4,
-                                            uint32_t neg_Z4, const RowState& st, RowState& st_out, int scale_mode)
+__device__ __forceinline__ void process_row(uint32_t e_info, uint32_t j4, uint32_t neg_Z4, RowState& st, uint4* sp,
+                                            const uint4* sp_next, uint64_t pol, int scale_mode)
 {
+  RowState st_out = make_uint4(0, 0, 0, 0);
   constexpr bool PACKED_MIN = DEG > 16;
   constexpr int  F0         = PACKED_MIN ? 1 : 2; // index of the first flag word
 
@@ -168,7 +189,7 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint4* __
 #pragma unroll
     for (int e = 0; e != DEG; ++e) {
       if ((e & 1) == 0) {
-        ei = e_info[e >> 1];
+        ei = lds_u128(e_info + 8 * e);
       }
       const uint32_t t = j4 + ((e & 1) ? ei.z : ei.x);
       // wrap: t - Z underflows to a huge value when t < Z (one fused add + unsigned minimum)
@@ -186,7 +207,7 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint4* __
       pm   = f;      // "held the minimum" flags: bit 15 of each half = edge e, then e+1, ... after each shift
       ps   = f << 8; // sign flags
     }
-    const __half2 s    = H(*reinterpret_cast<const hh*>(soft + addr[e]));
+    const __half2 s    = H(lds_u32(addr[e]));
     const __half2 z    = H(lop_and_or(pm, H_SIGN, H_ONE));
     const __half2 sg   = H(lop_and_or(ps, H_SIGN, H_ONE));
     const __half2 nmag = __hfma2(z, hd, __hneg2(mid));
@@ -212,6 +233,9 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint4* __
     pm <<= 1;
     ps <<= 1;
   }
+
+  // This row's old messages are consumed: fetch those of the next row into the same registers.
+  st = ld_state(sp_next, pol);
 
   // Scaled minima. x86: (x * 52428) >> 16 == ceil(0.8 x) - 1 for x >= 1, 0 for x = 0;
   // generic: round(0.8 x). Both are computed exactly through round-to-nearest in the [1024, 2048) binade.
@@ -242,7 +266,7 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint4* __
     // least 544 from 121 on, where x * pe + x exceeds the half-precision range; an infinite x stays infinite.
     const __half2 pe = __hfma2_relu(__habs2(x), H(H_544), H(H_N65280));
     const __half2 r  = __hfma2(x, pe, x);
-    *reinterpret_cast<hh*>(soft + addr[e]) = U(r);
+    sts_u32(addr[e], U(r));
     acc_s = __hfma2(acc_s, H(H_TWO), sgn);                    // sum of +-2^k; turned into "negative" bits below
     acc_m = lop_and_or(ism, H_SIGN >> (e & 7), acc_m);        // flag of the first edge of a group in the MSB
     if ((e & 7) == 7 || e == DEG - 1) {
@@ -264,30 +288,31 @@ __device__ __forceinline__ void process_row(unsigned char* soft, const uint4* __
     st_out.x = U(s1);
     st_out.y = U(s2);
   }
+  st_state(sp, st_out, pol);
 }
 
-__device__ __forceinline__ void dispatch_row(int deg, unsigned char* soft_addr, const uint4* e_info, uint32_t j,
-                                             uint32_t Z, const RowState& st, RowState& st_out, int scale_mode)
+__device__ __forceinline__ void dispatch_row(int deg, uint32_t e_info, uint32_t j4, uint32_t neg_Z4, RowState& st,
+                                             uint4* sp, const uint4* sp_next, uint64_t pol, int scale_mode)
 {
   // Most frequent degrees first (BG1: 18 rows of degree 5, 8 of degree 6, ...).
   if (deg == 5) {
-    process_row<5>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
+    process_row<5>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
   } else if (deg == 6) {
-    process_row<6>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
+    process_row<6>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
   } else if (deg == 4) {
-    process_row<4>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
+    process_row<4>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
   } else if (deg == 7) {
-    process_row<7>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
+    process_row<7>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
   } else if (deg == 19) {
-    process_row<19>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
+    process_row<19>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
   } else if (deg == 3) {
-    process_row<3>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
+    process_row<3>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
   } else if (deg == 8) {
-    process_row<8>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
+    process_row<8>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
   } else if (deg == 9) {
-    process_row<9>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
+    process_row<9>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
   } else {
-    process_row<10>(soft_addr, e_info, j, Z, st, st_out, scale_mode);
+    process_row<10>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
   }
 }
 
@@ -407,13 +432,13 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       // Compressed messages: one uint4 per (row, check), private to thread j.
       uint4*         st_base   = reinterpret_cast<uint4*>(state_scratch + (size_t)blockIdx.x * scratch_stride_words);
       const uint32_t st_stride = (uint32_t)((Z + 31) & ~31);
-      unsigned char* soft_addr = smem_raw;
+      const uint32_t soft_s    = (uint32_t)__cvta_generic_to_shared(smem_raw);
 
       for (int i = tid; i < n_edges; i += nthr) {
         const int m  = c_tab.row[b][i];
         const int pi = c_tab.row_pstart[b][m] + (i - c_tab.row_start[b][m]);
         g.einfo[pi]  = make_uint2((uint32_t)(4 * (c_tab.v[b][set][i] % Z)), // ldpc_luts_impl.cpp:4536-4541
-                                  (uint32_t)(c_tab.col[b][i] * Z * 4));
+                                  soft_s + (uint32_t)(c_tab.col[b][i] * Z * 4));
       }
       // CRC word weights: x^(32 (T-1-t)) mod P for the T words of the K - F checked bits, zero beyond.
       {
@@ -572,21 +597,18 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         }
       }
       const uint32_t j4 = 4u * (uint32_t)j, neg_Z4 = 0u - 4u * (uint32_t)Z;
-      RowState       st_next = make_uint4(0, 0, 0, 0);
+      const uint32_t einfo_s    = (uint32_t)__cvta_generic_to_shared(g.einfo);
+      const uint32_t row_info_s = (uint32_t)__cvta_generic_to_shared(g.row_info);
+      RowState       st         = make_uint4(0, 0, 0, 0);
       for (int it = 0; it < max_iter; ++it) {
         uint4* sp = st_thread;
         for (int m = 0; m < layers; ++m) {
           if (active) {
-            const uint32_t info   = g.row_info[m];
-            const int      e0     = info & 0xffffu;
-            const int      deg    = info >> 16;
-            const RowState st     = st_next;
-            RowState       st_out = make_uint4(0, 0, 0, 0);
-            uint4* const   spn    = (m + 1 < layers) ? sp + st_stride : st_thread;
-            st_next               = ld_state(spn, pol_keep);
-            dispatch_row(deg, soft_addr, reinterpret_cast<const uint4*>(g.einfo + e0), j4, neg_Z4, st, st_out,
-                         scale_mode);
-            st_state(sp, st_out, pol_keep);
+            const uint32_t info = lds_u32(row_info_s + 4u * (uint32_t)m);
+            const int      e0   = info & 0xffffu;
+            const int      deg  = info >> 16;
+            uint4* const   spn  = (m + 1 < layers) ? sp + st_stride : st_thread;
+            dispatch_row(deg, einfo_s + 8u * (uint32_t)e0, j4, neg_Z4, st, sp, spn, pol_keep, scale_mode);
             sp = spn;
           } else {
             row_barrier();
