@@ -144,7 +144,8 @@ def run_reference_arm(args, rank, world):
     orc = Oracle()
     llrs, _ = synth_batch(orc, 64, 1024, args.snr, 1234)
     threads = os.cpu_count() or 1
-    per_step = 4.0  # seconds of CPU work per step: (steps + warmup) x 4 s stays within a few minutes
+    # Seconds of CPU work per step, sized so that the whole run stays within a few minutes.
+    per_step = max(0.25, min(4.0, 150.0 / max(1, args.steps + args.warmup)))
     vals = []
     for i in range(args.warmup + args.steps):
         r = cpu_reference_rate(llrs, False, per_step, threads)
@@ -230,7 +231,7 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--n-cb", type=int, default=8192, help="codeblocks per GPU per step")
@@ -355,10 +356,13 @@ def main():
     # ---- e2e: host buffers through pdc_submit / pdc_wait, two batches in flight -----------------------------------------
     cb_fixed = descs(False)
 
+    # Page-locked output buffers, one per queue: the hard bits of every step are written there by the GPU.
+    pinned_out = [capi.PinnedBuffer(n_cb * capi.PDC_MAX_CB_BYTES, np.uint8) for _ in range(2)]
+
     def e2e_run(steps):
-        ctx.submit(cb_fixed, pinned[0].array, None, stream=0)
+        ctx.submit(cb_fixed, pinned[0].array, None, stream=0, out_bits=pinned_out[0].array)
         for i in range(1, steps):
-            ctx.submit(cb_fixed, pinned[i & 1].array, None, stream=i & 1)
+            ctx.submit(cb_fixed, pinned[i & 1].array, None, stream=i & 1, out_bits=pinned_out[i & 1].array)
             ctx.wait((i - 1) & 1)
         return ctx.wait((steps - 1) & 1)
 
@@ -376,6 +380,19 @@ def main():
     e2e_value = world * n_cb * INFO_BITS * args.steps / e2e_s / 1e9
     h2d = n_cb * N_SOFT + n_cb * capi.CB_DESC_DTYPE.itemsize
     d2h = n_cb * capi.PDC_MAX_CB_BYTES + n_cb * 4
+    # The host link under the e2e number: a plain pinned-host -> device copy of one step's LLR bytes.
+    probe_src = torch.empty(n_cb * N_SOFT, dtype=torch.uint8).pin_memory()
+    probe_dst = torch.empty(n_cb * N_SOFT, dtype=torch.uint8, device="cuda")
+    probe_dst.copy_(probe_src, non_blocking=True)
+    torch.cuda.synchronize()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(4):
+        probe_dst.copy_(probe_src, non_blocking=True)
+    pe1.record()
+    torch.cuda.synchronize()
+    link_gbs = 4 * n_cb * N_SOFT / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
+    del probe_src, probe_dst
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -388,7 +405,8 @@ def main():
                    "parity_spot_check_vs_oracle": parity_ok, "us_per_slot_equiv_152cb": ms_per_step * 1e3 * 152 / n_cb},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s / args.steps * 1e3},
+                "ms_per_step": e2e_s / args.steps * 1e3,
+                "h2d_gbs_achieved": h2d * args.steps / e2e_s / 1e9, "h2d_gbs_plain_copy": link_gbs},
         "gpu_launches": launches,
     }
 

@@ -152,6 +152,8 @@ void  pdc_host_free(void* p);
  * CB CRC, optional TB assembly + TB CRC, D2H copy of results, hard bits and TB bytes. Returns as soon as the work is
  * queued on the stream. Host buffers must stay valid until pdc_wait returns.
  *   cb_results[n_cb], cb_bits[n_cb * PDC_MAX_CB_BYTES] (may be NULL), tb_results[n_tb], tb_bytes (may be NULL).
+ * llrs, cb_bits and tb_bytes in page-locked memory (pdc_host_alloc) are copied from / to directly; pageable buffers go
+ * through the context's pinned staging at the price of one host memcpy.
  */
 int pdc_submit(pdc_ctx*           ctx,
                uint32_t           stream,

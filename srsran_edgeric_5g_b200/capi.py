@@ -186,8 +186,9 @@ class Context:
         return v.value
 
     # -- batched interface --------------------------------------------------------------------------------------------
-    def submit(self, cbs, llrs, tbs=None, stream=0, want_bits=True, want_tb=True):
-        """cbs: numpy array of CB_DESC_DTYPE; llrs: int8 array (ideally a PinnedBuffer view); tbs: TB_DESC_DTYPE."""
+    def submit(self, cbs, llrs, tbs=None, stream=0, want_bits=True, want_tb=True, out_bits=None, out_tb=None):
+        """cbs: numpy array of CB_DESC_DTYPE; llrs: int8 array (ideally a PinnedBuffer view); tbs: TB_DESC_DTYPE.
+        out_bits / out_tb: caller-owned uint8 output arrays (PinnedBuffer views are written by the GPU directly)."""
         cbs = np.ascontiguousarray(cbs, CB_DESC_DTYPE)
         assert llrs.dtype == np.int8 and llrs.flags.c_contiguous
         n_cb = cbs.size
@@ -196,7 +197,8 @@ class Context:
             "cbs": cbs,
             "llrs": llrs,
             "cb_results": np.zeros(n_cb, CB_RESULT_DTYPE),
-            "cb_bits": np.zeros((n_cb, PDC_MAX_CB_BYTES), np.uint8) if want_bits else None,
+            "cb_bits": (out_bits[:n_cb * PDC_MAX_CB_BYTES].reshape(n_cb, PDC_MAX_CB_BYTES) if out_bits is not None else
+                        np.zeros((n_cb, PDC_MAX_CB_BYTES), np.uint8)) if want_bits else None,
             "tbs": None,
             "tb_results": None,
             "tb_bytes": None,
@@ -207,7 +209,7 @@ class Context:
             out["tb_results"] = np.zeros(n_tb, TB_RESULT_DTYPE)
             if want_tb:
                 need = int(max(t["out_offset"] + (int(t["tbs_bits"]) + 24 + 31) // 32 * 4 for t in tbs))
-                out["tb_bytes"] = np.zeros(need, np.uint8)
+                out["tb_bytes"] = out_tb[:need] if out_tb is not None else np.zeros(need, np.uint8)
         check(self._L.pdc_submit(self.h, stream, _ptr(cbs), n_cb, _ptr(llrs), llrs.size, _ptr(out["tbs"]), n_tb,
                                  _ptr(out["cb_results"]), _ptr(out["cb_bits"]), _ptr(out["tb_results"]),
                                  _ptr(out["tb_bytes"])))

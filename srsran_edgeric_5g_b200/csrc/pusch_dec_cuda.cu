@@ -471,6 +471,17 @@ void pdc_host_free(void* p)
   }
 }
 
+// Page-locked host memory (pdc_host_alloc, cudaHostAlloc, cudaHostRegister) can be the target of an asynchronous copy.
+static bool is_pinned_host(const void* p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int pdc_submit(pdc_ctx*           ctx,
                uint32_t           stream,
                const pdc_cb_desc* cbs,
@@ -531,14 +542,18 @@ int pdc_submit(pdc_ctx*           ctx,
     return rc;
   }
   PDC_CUDA(cudaMemcpyAsync(q.h_cb_res, q.d_cb_res, sizeof(pdc_cb_result) * n_cb, cudaMemcpyDeviceToHost, q.stream));
+  // Outputs go straight to page-locked caller buffers; pageable ones are filled from the pinned staging in pdc_wait.
+  const bool direct_bits = cb_bits && is_pinned_host(cb_bits);
+  const bool direct_tb   = tb_bytes && n_tb != 0 && is_pinned_host(tb_bytes);
   if (cb_bits) {
-    PDC_CUDA(cudaMemcpyAsync(q.h_cb_bits, q.d_cb_bits, (size_t)n_cb * PDC_MAX_CB_BYTES, cudaMemcpyDeviceToHost,
-                             q.stream));
+    PDC_CUDA(cudaMemcpyAsync(direct_bits ? cb_bits : q.h_cb_bits, q.d_cb_bits, (size_t)n_cb * PDC_MAX_CB_BYTES,
+                             cudaMemcpyDeviceToHost, q.stream));
   }
   if (n_tb != 0) {
     PDC_CUDA(cudaMemcpyAsync(q.h_tb_res, q.d_tb_res, sizeof(pdc_tb_result) * n_tb, cudaMemcpyDeviceToHost, q.stream));
     if (tb_bytes) {
-      PDC_CUDA(cudaMemcpyAsync(q.h_tb_out, q.d_tb_out, tb_out_bytes, cudaMemcpyDeviceToHost, q.stream));
+      PDC_CUDA(cudaMemcpyAsync(direct_tb ? tb_bytes : q.h_tb_out, q.d_tb_out, tb_out_bytes, cudaMemcpyDeviceToHost,
+                               q.stream));
     }
   }
   PDC_CUDA(cudaEventRecord(q.done, q.stream));
@@ -547,9 +562,9 @@ int pdc_submit(pdc_ctx*           ctx,
   q.n_tb         = n_tb;
   q.tb_out_bytes = tb_out_bytes;
   q.u_cb_res     = cb_results;
-  q.u_cb_bits    = cb_bits;
+  q.u_cb_bits    = direct_bits ? nullptr : cb_bits;
   q.u_tb_res     = tb_results;
-  q.u_tb_out     = tb_bytes;
+  q.u_tb_out     = direct_tb ? nullptr : tb_bytes;
   return PDC_OK;
 }
 
