@@ -851,3 +851,336 @@ double orc_bench_cb_batch(int           n_cb,
   free(rm);
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ---- codeword front end ------------------------------------------------------------------------------------------------ */
+
+/* TS 38.211 5.2.1: x1(n+31) = x1(n+3) + x1(n), x2(n+31) = x2(n+3) + x2(n+2) + x2(n+1) + x2(n), x1(0) = 1,
+ * x2 = c_init, c(n) = x1(n + 1600) + x2(n + 1600). Bit-serial; state bit j = x(n + j). */
+void orc_prg_bits(uint32_t c_init, uint32_t offset, uint32_t n, uint8_t* bits)
+{
+  uint32_t x1 = 1u, x2 = c_init & 0x7fffffffu;
+  uint32_t skip = 1600u + offset;
+  for (uint32_t i = 0; i != skip + n; ++i) {
+    if (i >= skip) {
+      bits[i - skip] = (uint8_t)((x1 ^ x2) & 1u);
+    }
+    uint32_t f1 = ((x1 >> 3) ^ x1) & 1u;
+    uint32_t f2 = ((x2 >> 3) ^ (x2 >> 2) ^ (x2 >> 1) ^ x2) & 1u;
+    x1          = (x1 >> 1) | (f1 << 30);
+    x2          = (x2 >> 1) | (f2 << 30);
+  }
+}
+
+void orc_revert_scrambling(int8_t* out, const int8_t* in, const uint8_t* seq_bits, uint32_t n)
+{
+  for (uint32_t i = 0; i != n; ++i) {
+    out[i] = seq_bits[i] ? (int8_t)(uint8_t)(0u - (uint8_t)in[i]) : in[i];
+  }
+}
+
+#define ORC_MAX_RE (275 * 12)
+
+typedef struct {
+  uint8_t v[ORC_MAX_RE];
+  int     size;
+} re_set;
+
+static void re_fill(re_set* s, int size, int value)
+{
+  s->size = size;
+  memset(s->v, value ? 1 : 0, (size_t)size);
+}
+static int re_count(const re_set* s)
+{
+  int c = 0;
+  for (int i = 0; i != s->size; ++i) {
+    c += s->v[i];
+  }
+  return c;
+}
+/* First m_re_count elements of src taking one out of d (re_set_select, ulsch_demultiplex_impl.cpp:78-102). */
+static void re_select(re_set* dst, const re_set* src, int d, int m_re_count)
+{
+  re_fill(dst, src->size, 0);
+  int count = 0, d_count = 0;
+  for (int i = 0; i != src->size && count != m_re_count; ++i) {
+    if (!src->v[i]) {
+      continue;
+    }
+    if (d_count % d == 0) {
+      dst->v[i] = 1;
+      ++count;
+    }
+    ++d_count;
+  }
+}
+
+static int ulsch_l1(int mask)
+{
+  int first = -1;
+  for (int l = 0; l != 14; ++l) {
+    if ((mask >> l) & 1) {
+      first = l;
+      break;
+    }
+  }
+  if (first < 0) {
+    return -1;
+  }
+  for (int l = first; l != 14; ++l) {
+    if (!((mask >> l) & 1)) {
+      return l;
+    }
+  }
+  return -1;
+}
+static int ulsch_l1_csi(int mask)
+{
+  for (int l = 0; l != 14; ++l) {
+    if (!((mask >> l) & 1)) {
+      return l;
+    }
+  }
+  return -1;
+}
+static int ulsch_re_dmrs_symbol(const orc_ulsch_cfg* c)
+{
+  int per_prb = c->nof_cdm_groups_without_data * (c->dmrs_type == 1 ? 6 : 4);
+  return (12 - per_prb) * c->nof_prb;
+}
+
+uint32_t orc_ulsch_codeword_length(const orc_ulsch_cfg* c)
+{
+  uint32_t total = 0;
+  for (int l = c->start_symbol_index; l != c->start_symbol_index + c->nof_symbols; ++l) {
+    int m = ((c->dmrs_symbol_mask >> l) & 1) ? ulsch_re_dmrs_symbol(c) : c->nof_prb * 12;
+    total += (uint32_t)(m * c->qm * c->nof_layers);
+  }
+  return total;
+}
+
+/* on_uci_placeholder_1bit / _2bit (ulsch_demultiplex_impl.cpp:111-198): x placeholders get their scrambling undone, the
+ * y placeholder of the 1-bit case takes the scrambling of the first bit. */
+static void uci_placeholder(int8_t* out, const int8_t* data, const uint8_t* seq, int qm, int nbits, int nof_uci_bits)
+{
+  if (qm == 1) {
+    memcpy(out, data, (size_t)nbits);
+    return;
+  }
+  for (int s = 0; s != nbits / qm; ++s) {
+    const int8_t*  d = data + s * qm;
+    const uint8_t* m = seq + s * qm;
+    int8_t*        o = out + s * qm;
+    o[0]             = d[0];
+    if (nof_uci_bits == 1) {
+      o[1] = ((m[0] ^ m[1]) == 1) ? (int8_t)-d[1] : d[1];
+    } else {
+      o[1] = d[1];
+    }
+    for (int b = 2; b != qm; ++b) {
+      o[b] = (m[b] == 1) ? (int8_t)-d[b] : d[b];
+    }
+  }
+}
+
+int orc_ulsch_demux(const orc_ulsch_cfg* c,
+                    const int8_t*        in,
+                    const uint8_t*       seq_bits,
+                    uint32_t             n_in,
+                    int8_t*              sch,
+                    int8_t*              harq_ack,
+                    int8_t*              csi_part1,
+                    int8_t*              csi_part2,
+                    uint32_t*            n_out)
+{
+  static re_set ulsch, uci, rvd, hack, csi1, csi2, tmp;
+  static int8_t sym[ORC_MAX_RE * 8 * 4];
+  const int     bpre   = c->qm * c->nof_layers;
+  const int     l1     = ulsch_l1(c->dmrs_symbol_mask);
+  const int     l1_csi = ulsch_l1_csi(c->dmrs_symbol_mask);
+  if (l1 < 0 || l1_csi < 0 || bpre <= 0 || n_in != orc_ulsch_codeword_length(c)) {
+    return -1;
+  }
+  int m_rvd = 0, m_hack = 0, m_csi1 = 0, m_csi2 = 0;
+  int hack_open = c->nof_harq_ack_bits != 0, csi1_open = c->nof_csi_part1_bits != 0, csi2_open = 0;
+  int csi2_bits = 0, csi2_enc = 0; /* configured when CSI Part 1 ends (set_csi_part2) */
+  uint32_t pos = 0;
+  n_out[0] = n_out[1] = n_out[2] = n_out[3] = 0;
+
+  for (int l = c->start_symbol_index; l != c->start_symbol_index + c->nof_symbols; ++l) {
+    /* configure_current_ofdm_symbol (:371-473) */
+    const int dmrs    = (c->dmrs_symbol_mask >> l) & 1;
+    const int M_ulsch = dmrs ? ulsch_re_dmrs_symbol(c) : c->nof_prb * 12;
+    const int nsoft   = M_ulsch * bpre;
+    if (nsoft == 0) {
+      continue;
+    }
+    re_fill(&ulsch, M_ulsch, 1);
+    re_fill(&uci, M_ulsch, !dmrs);
+    re_fill(&rvd, M_ulsch, 0);
+    re_fill(&hack, M_ulsch, 0);
+    re_fill(&csi1, M_ulsch, 0);
+    re_fill(&csi2, M_ulsch, 0);
+    int M_uci    = re_count(&uci);
+    int rem_rvd  = (int)((unsigned)(c->nof_harq_ack_rvd - m_rvd) / (unsigned)bpre);
+    if (l >= l1 && M_uci > 0 && rem_rvd > 0) {
+      int d = 1, m = M_uci;
+      if (rem_rvd < M_uci) {
+        d = M_uci / rem_rvd;
+        m = rem_rvd;
+      }
+      re_select(&rvd, &ulsch, d, m);
+      m_rvd += m * bpre;
+    }
+    const int rem_hack = (int)((unsigned)(c->nof_enc_harq_ack_bits - m_hack) / (unsigned)bpre);
+    if (l >= l1 && M_uci > 0 && c->nof_harq_ack_bits > 2 && rem_hack > 0) {
+      int d = 1, m = M_uci;
+      if (rem_hack < M_uci) {
+        d = M_uci / rem_hack;
+        m = rem_hack;
+      }
+      re_select(&hack, &uci, d, m);
+      for (int i = 0; i != M_ulsch; ++i) {
+        if (hack.v[i]) {
+          ulsch.v[i] = 0;
+          uci.v[i]   = 0;
+        }
+      }
+      M_uci = re_count(&uci);
+      m_hack += m * bpre;
+    }
+    const int rem_csi1 = (int)((unsigned)(c->nof_enc_csi_part1_bits - m_csi1) / (unsigned)bpre);
+    const int M_rvd    = re_count(&rvd);
+    if (l >= l1_csi && (M_uci - M_rvd) > 0 && rem_csi1 > 0) {
+      int d = 1, m = M_uci - M_rvd;
+      if (rem_csi1 < M_uci - M_rvd) {
+        d = (M_uci - M_rvd) / rem_csi1;
+        m = rem_csi1;
+      }
+      re_fill(&tmp, M_ulsch, 0);
+      for (int i = 0; i != M_ulsch; ++i) {
+        tmp.v[i] = (uint8_t)(!rvd.v[i] && uci.v[i]);
+      }
+      re_select(&csi1, &tmp, d, m);
+      for (int i = 0; i != M_ulsch; ++i) {
+        if (csi1.v[i]) {
+          ulsch.v[i] = 0;
+          uci.v[i]   = 0;
+        }
+      }
+      m_csi1 += m * bpre;
+    }
+    /* configure_csi_part2_current_ofdm_symbol (:475-499); also run when CSI Part 2 is set in the middle of the symbol. */
+#define CONFIGURE_CSI2()                                                                                               \
+  do {                                                                                                                 \
+    int M_uci2   = re_count(&uci);                                                                                     \
+    int rem_csi2 = (int)((unsigned)(csi2_enc - m_csi2) / (unsigned)bpre);                                              \
+    if (l >= l1_csi && M_uci2 > 0 && rem_csi2 > 0) {                                                                   \
+      int d2 = 1, m2 = M_uci2;                                                                                         \
+      if (rem_csi2 < M_uci2) {                                                                                         \
+        d2 = M_uci2 / rem_csi2;                                                                                        \
+        m2 = rem_csi2;                                                                                                 \
+      }                                                                                                                \
+      re_select(&csi2, &uci, d2, m2);                                                                                  \
+      for (int i = 0; i != M_ulsch; ++i) {                                                                             \
+        if (csi2.v[i]) {                                                                                               \
+          ulsch.v[i] = 0;                                                                                              \
+          uci.v[i]   = 0;                                                                                              \
+        }                                                                                                              \
+      }                                                                                                                \
+      m_csi2 += m2 * bpre;                                                                                             \
+    }                                                                                                                  \
+  } while (0)
+    CONFIGURE_CSI2();
+    if (M_rvd > 0 && c->nof_harq_ack_bits <= 2 && rem_hack > 0) {
+      int d = 1, m = M_rvd;
+      if (rem_hack < M_rvd) {
+        d = M_rvd / rem_hack;
+        m = rem_hack;
+      }
+      re_select(&hack, &rvd, d, m);
+      m_hack += m * bpre;
+    }
+
+    /* demux_current_ofdm_symbol (:501-589) on a copy of the symbol (HARQ-ACK placeholders are zeroed in place). */
+    memcpy(sym, in + pos, (size_t)nsoft);
+    const uint8_t* seq = seq_bits + pos;
+    if (re_count(&hack) != 0) {
+      if (!hack_open) {
+        return -1;
+      }
+      for (int i = 0; i != M_ulsch; ++i) {
+        if (!hack.v[i]) {
+          continue;
+        }
+        int8_t* re = sym + i * bpre;
+        if (c->nof_harq_ack_bits == 1 || c->nof_harq_ack_bits == 2) {
+          uci_placeholder(harq_ack + n_out[1], re, seq + i * bpre, c->qm, bpre, c->nof_harq_ack_bits);
+          memset(re, 0, (size_t)bpre);
+        } else {
+          memcpy(harq_ack + n_out[1], re, (size_t)bpre);
+        }
+        n_out[1] += (uint32_t)bpre;
+      }
+      if (m_hack == c->nof_enc_harq_ack_bits) {
+        hack_open = 0;
+      }
+    }
+    if (re_count(&csi1) != 0) {
+      if (!csi1_open) {
+        return -1;
+      }
+      for (int i = 0; i != M_ulsch; ++i) {
+        if (!csi1.v[i]) {
+          continue;
+        }
+        const int8_t* re = sym + i * bpre;
+        if (c->nof_csi_part1_bits == 1 || c->nof_csi_part1_bits == 2) {
+          uci_placeholder(csi_part1 + n_out[2], re, seq + i * bpre, c->qm, bpre, c->nof_csi_part1_bits);
+        } else {
+          memcpy(csi_part1 + n_out[2], re, (size_t)bpre);
+        }
+        n_out[2] += (uint32_t)bpre;
+      }
+      if (m_csi1 == c->nof_enc_csi_part1_bits) {
+        csi1_open = 0;
+        /* CSI Part 1 decoded: the processor configures CSI Part 2 now, for the symbol being demultiplexed. */
+        if (c->nof_enc_csi_part2_bits != 0) {
+          csi2_open = 1;
+          csi2_bits = c->nof_csi_part2_bits;
+          csi2_enc  = c->nof_enc_csi_part2_bits;
+          CONFIGURE_CSI2();
+        }
+      }
+    }
+    if (re_count(&csi2) != 0) {
+      if (!csi2_open) {
+        return -1;
+      }
+      for (int i = 0; i != M_ulsch; ++i) {
+        if (!csi2.v[i]) {
+          continue;
+        }
+        const int8_t* re = sym + i * bpre;
+        if (csi2_bits == 1 || csi2_bits == 2) {
+          uci_placeholder(csi_part2 + n_out[3], re, seq + i * bpre, c->qm, bpre, csi2_bits);
+        } else {
+          memcpy(csi_part2 + n_out[3], re, (size_t)bpre);
+        }
+        n_out[3] += (uint32_t)bpre;
+      }
+      if (m_csi2 == csi2_enc) {
+        csi2_open = 0;
+      }
+    }
+    for (int i = 0; i != M_ulsch; ++i) {
+      if (ulsch.v[i]) {
+        memcpy(sch + n_out[0], sym + i * bpre, (size_t)bpre);
+        n_out[0] += (uint32_t)bpre;
+      }
+    }
+    pos += (uint32_t)nsoft;
+  }
+#undef CONFIGURE_CSI2
+  return (hack_open || csi1_open || csi2_open) ? -1 : 0;
+}

@@ -150,6 +150,56 @@ double orc_bench_cb_batch(int           n_cb,
                           int           max_iter,
                           int*          iters_out);
 
+
+/* ---- codeword front end: scrambling sequence, descrambling, UL-SCH demultiplexing ---------------- */
+
+/* TS 38.211 5.2.1 pseudo-random sequence c(offset .. offset+n-1) for c_init, one bit per byte
+ * (lib/phy/upper/sequence_generators/pseudo_random_generator_impl.cpp:47-68 init/advance, generate). */
+void orc_prg_bits(uint32_t c_init, uint32_t offset, uint32_t n, uint8_t* bits);
+
+/* out[i] = seq[i] ? -in[i] : in[i] with two's-complement wrap of -128
+ * (revert_scrambling, lib/phy/upper/channel_processors/pusch/pusch_demodulator_impl.cpp:38-128). */
+void orc_revert_scrambling(int8_t* out, const int8_t* in, const uint8_t* seq_bits, uint32_t n);
+
+/* ulsch_demultiplex::configuration (include/srsran/phy/upper/channel_processors/pusch/ulsch_demultiplex.h:46-76) plus
+ * the CSI Part 2 sizes the PUSCH processor hands over when CSI Part 1 has been decoded (pusch_processor_impl.cpp:61-82;
+ * 0 = no CSI Part 2). */
+typedef struct {
+  int qm;                          /* bits per symbol of the modulation                          */
+  int nof_layers;
+  int nof_prb;
+  int start_symbol_index;
+  int nof_symbols;
+  int nof_harq_ack_rvd;
+  int dmrs_type;                   /* 1 or 2                                                     */
+  int dmrs_symbol_mask;            /* bit l set: OFDM symbol l of the slot carries DM-RS         */
+  int nof_cdm_groups_without_data;
+  int nof_harq_ack_bits;
+  int nof_enc_harq_ack_bits;
+  int nof_csi_part1_bits;
+  int nof_enc_csi_part1_bits;
+  int nof_csi_part2_bits;
+  int nof_enc_csi_part2_bits;
+} orc_ulsch_cfg;
+
+/* Number of soft bits of the codeword (all OFDM symbols of the allocation). */
+uint32_t orc_ulsch_codeword_length(const orc_ulsch_cfg* cfg);
+
+/* ulsch_demultiplex_impl (lib/phy/upper/channel_processors/pusch/ulsch_demultiplex_impl.cpp:200-589): in[] are the
+ * descrambled soft bits of the codeword in resource-element order, seq_bits[] the scrambling sequence applied to them
+ * (needed to undo the scrambling of the UCI placeholders). Outputs are the soft-bit streams handed to the four decoder
+ * buffers; n_out[0..3] = lengths of sch, harq_ack, csi_part1, csi_part2. Returns 0, or -1 on an inconsistent
+ * configuration (where the reference asserts). */
+int orc_ulsch_demux(const orc_ulsch_cfg* cfg,
+                    const int8_t*        in,
+                    const uint8_t*       seq_bits,
+                    uint32_t             n_in,
+                    int8_t*              sch,
+                    int8_t*              harq_ack,
+                    int8_t*              csi_part1,
+                    int8_t*              csi_part2,
+                    uint32_t*            n_out);
+
 #ifdef __cplusplus
 }
 #endif

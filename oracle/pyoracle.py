@@ -66,6 +66,16 @@ class Harq:
         return _Harq(self.nof_cb, _ptr(self.soft), _ptr(self.data), _ptr(self.crc_ok))
 
 
+ULSCH_CFG_FIELDS = ("qm", "nof_layers", "nof_prb", "start_symbol_index", "nof_symbols", "nof_harq_ack_rvd", "dmrs_type",
+                    "dmrs_symbol_mask", "nof_cdm_groups_without_data", "nof_harq_ack_bits", "nof_enc_harq_ack_bits",
+                    "nof_csi_part1_bits", "nof_enc_csi_part1_bits", "nof_csi_part2_bits", "nof_enc_csi_part2_bits")
+
+
+def ulsch_cfg_array(cfg):
+    """orc_ulsch_cfg as an int32 array (the struct is 15 ints)."""
+    return np.array([int(cfg.get(k, 0)) for k in ULSCH_CFG_FIELDS], np.int32)
+
+
 class Oracle:
     def __init__(self):
         if not ORACLE_SO.exists():
@@ -91,7 +101,43 @@ class Oracle:
         L.orc_tb_encode.argtypes = [_vp] + [_c_int] * 7 + [_vp]
         L.orc_bench_cb_batch.restype = ctypes.c_double
         L.orc_bench_cb_batch.argtypes = [_c_int, _vp] + [_c_int] * 9 + [_vp]
+        L.orc_prg_bits.restype = None
+        L.orc_prg_bits.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _vp]
+        L.orc_revert_scrambling.restype = None
+        L.orc_revert_scrambling.argtypes = [_vp, _vp, _vp, ctypes.c_uint32]
+        L.orc_ulsch_codeword_length.restype = ctypes.c_uint32
+        L.orc_ulsch_codeword_length.argtypes = [_vp]
+        L.orc_ulsch_demux.restype = _c_int
+        L.orc_ulsch_demux.argtypes = [_vp, _vp, _vp, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp]
         self.L = L
+
+    # -- codeword front end ---------------------------------------------------------------------------------------------
+    def prg_bits(self, c_init, offset, n):
+        bits = np.zeros(n, np.uint8)
+        self.L.orc_prg_bits(c_init, offset, n, _ptr(bits))
+        return bits
+
+    def revert_scrambling(self, llrs, seq_bits):
+        llrs = np.ascontiguousarray(llrs, np.int8)
+        seq_bits = np.ascontiguousarray(seq_bits, np.uint8)
+        out = np.zeros_like(llrs)
+        self.L.orc_revert_scrambling(_ptr(out), _ptr(llrs), _ptr(seq_bits), llrs.size)
+        return out
+
+    def ulsch_codeword_length(self, cfg):
+        c = ulsch_cfg_array(cfg)
+        return int(self.L.orc_ulsch_codeword_length(_ptr(c)))
+
+    def ulsch_demux(self, cfg, llrs, seq_bits):
+        """cfg: dict with the fields of orc_ulsch_cfg. Returns (status, [sch, harq_ack, csi_part1, csi_part2])."""
+        c = ulsch_cfg_array(cfg)
+        llrs = np.ascontiguousarray(llrs, np.int8)
+        seq_bits = np.ascontiguousarray(seq_bits, np.uint8)
+        outs = [np.zeros(llrs.size, np.int8) for _ in range(4)]
+        n_out = np.zeros(4, np.uint32)
+        rc = self.L.orc_ulsch_demux(_ptr(c), _ptr(llrs), _ptr(seq_bits), llrs.size, _ptr(outs[0]), _ptr(outs[1]),
+                                    _ptr(outs[2]), _ptr(outs[3]), _ptr(n_out))
+        return rc, [o[:n] for o, n in zip(outs, n_out)]
 
     def crc(self, kind, packed, nbits):
         packed = np.ascontiguousarray(packed, np.uint8)
@@ -192,6 +238,10 @@ class Reference:
         L.ref_ldpc_encode.argtypes = [_c_int, _c_int, _vp, _vp, _c_int]
         L.ref_segment_rx.restype = _c_int
         L.ref_segment_rx.argtypes = [_c_int] * 7 + [_vp]
+        L.ref_prg_bits.restype = None
+        L.ref_prg_bits.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, _vp]
+        L.ref_ulsch_demux.restype = _c_int
+        L.ref_ulsch_demux.argtypes = [_vp, _vp, _vp, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _vp, _vp]
         L.ref_pusch_create.restype = _vp
         L.ref_pusch_create.argtypes = [ctypes.c_char_p, _c_int]
         L.ref_pusch_destroy.argtypes = [_vp]
@@ -259,6 +309,22 @@ class Reference:
         meta = np.zeros(256 * 6, np.int32)
         n = self.L.ref_segment_rx(tbs_bits, bg, rv, qm, nref, nof_layers, n_llr, _ptr(meta))
         return meta[:n * 6].reshape(n, 6)
+
+    def prg_bits(self, c_init, offset, n):
+        bits = np.zeros(n, np.uint8)
+        self.L.ref_prg_bits(c_init, offset, n, _ptr(bits))
+        return bits
+
+    def ulsch_demux(self, cfg, llrs, seq_bits, max_block_re=0):
+        """ulsch_demultiplex_impl fed like pusch_demodulator_impl does. Returns (status, [sch, ack, csi1, csi2])."""
+        c = ulsch_cfg_array(cfg)
+        llrs = np.ascontiguousarray(llrs, np.int8)
+        seq_bits = np.ascontiguousarray(seq_bits, np.uint8)
+        outs = [np.zeros(llrs.size, np.int8) for _ in range(4)]
+        n_out = np.zeros(4, np.uint32)
+        rc = self.L.ref_ulsch_demux(_ptr(c), _ptr(llrs), _ptr(seq_bits), llrs.size, max_block_re, _ptr(outs[0]),
+                                    _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), _ptr(n_out))
+        return rc, [o[:n] for o, n in zip(outs, n_out)]
 
     def bench_cb_batch(self, llrs, E, N, rv, qm, nref, nof_filler, crc_kind, early_stop, max_iter, threads=1,
                        repeats=1, want_bits=False):

@@ -13,6 +13,10 @@
 
 #include "lib/phy/upper/channel_processors/pusch/pusch_codeblock_decoder.h"
 #include "lib/phy/upper/channel_processors/pusch/pusch_decoder_impl.h"
+#include "lib/phy/upper/channel_processors/pusch/ulsch_demultiplex_impl.h"
+#include "lib/phy/upper/sequence_generators/pseudo_random_generator_impl.h"
+#include "srsran/phy/upper/channel_processors/pusch/pusch_codeword_buffer.h"
+#include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_buffer.h"
 #include "srsran/phy/upper/channel_coding/channel_coding_factories.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_notifier.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_result.h"
@@ -20,6 +24,7 @@
 #include "srsran/srsvec/bit.h"
 #include "srsran/support/cpu_features.h"
 #include <atomic>
+#include <functional>
 #include <chrono>
 #include <cstring>
 #include <memory>
@@ -536,6 +541,145 @@ double ref_bench_cb_batch(const char*   type,
   }
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+
+// ---- codeword front end: pseudo-random sequence and UL-SCH demultiplexer of the reference ----------------------------
+
+/// c(offset .. offset + n - 1) of pseudo_random_generator_impl, one bit per byte.
+void ref_prg_bits(unsigned c_init, unsigned offset, unsigned n, uint8_t* bits)
+{
+  pseudo_random_generator_impl prg;
+  prg.init(c_init);
+  prg.advance(offset);
+  dynamic_bit_buffer seq(n);
+  prg.generate(seq);
+  for (unsigned i = 0; i != n; ++i) {
+    bits[i] = seq.extract(i, 1);
+  }
+}
+
+namespace {
+/// Decoder buffer that records the soft bits it is given.
+class spy_decoder_buffer : public pusch_decoder_buffer
+{
+public:
+  std::vector<log_likelihood_ratio> data;
+  std::vector<log_likelihood_ratio> scratch;
+  bool                              ended = false;
+  std::function<void()>             on_end;
+
+  span<log_likelihood_ratio> get_next_block_view(unsigned block_size) override
+  {
+    scratch.resize(block_size);
+    return scratch;
+  }
+  void on_new_softbits(span<const log_likelihood_ratio> softbits) override
+  {
+    data.insert(data.end(), softbits.begin(), softbits.end());
+  }
+  void on_end_softbits() override
+  {
+    ended = true;
+    if (on_end) {
+      on_end();
+    }
+  }
+};
+} // namespace
+
+/// Drives ulsch_demultiplex_impl the way pusch_demodulator_impl does (pusch_demodulator_impl.cpp:160-283): per OFDM
+/// symbol, blocks as large as get_next_block_view grants. cfg[15]: the fields of orc_ulsch_cfg in order.
+/// max_block (> 0) additionally caps the block size in resource elements. Returns 0.
+int ref_ulsch_demux(const int*     cfg,
+                    const int8_t*  in,
+                    const uint8_t* seq_bits,
+                    unsigned       n_in,
+                    unsigned       max_block_re,
+                    int8_t*        sch,
+                    int8_t*        harq_ack,
+                    int8_t*        csi_part1,
+                    int8_t*        csi_part2,
+                    unsigned*      n_out)
+{
+  ulsch_demultiplex::configuration c;
+  const int                        qm = cfg[0];
+  c.modulation  = (qm == 1)   ? modulation_scheme::PI_2_BPSK
+                  : (qm == 2) ? modulation_scheme::QPSK
+                  : (qm == 4) ? modulation_scheme::QAM16
+                  : (qm == 6) ? modulation_scheme::QAM64
+                              : modulation_scheme::QAM256;
+  c.nof_layers                  = cfg[1];
+  c.nof_prb                     = cfg[2];
+  c.start_symbol_index          = cfg[3];
+  c.nof_symbols                 = cfg[4];
+  c.nof_harq_ack_rvd            = cfg[5];
+  c.dmrs                        = (cfg[6] == 1) ? dmrs_type::TYPE1 : dmrs_type::TYPE2;
+  c.dmrs_symbol_mask            = symbol_slot_mask(14);
+  for (unsigned l = 0; l != 14; ++l) {
+    if ((cfg[7] >> l) & 1) {
+      c.dmrs_symbol_mask.set(l);
+    }
+  }
+  c.nof_cdm_groups_without_data = cfg[8];
+  c.nof_harq_ack_bits           = cfg[9];
+  c.nof_enc_harq_ack_bits       = cfg[10];
+  c.nof_csi_part1_bits          = cfg[11];
+  c.nof_enc_csi_part1_bits      = cfg[12];
+  const unsigned csi2_bits = cfg[13], csi2_enc = cfg[14];
+
+  auto               demux = std::make_unique<ulsch_demultiplex_impl>();
+  spy_decoder_buffer b_sch, b_ack, b_csi1, b_csi2;
+  b_csi1.on_end = [&]() {
+    if (csi2_enc != 0) {
+      demux->set_csi_part2(b_csi2, csi2_bits, csi2_enc);
+    }
+  };
+  pusch_codeword_buffer& cw = demux->demultiplex(b_sch, b_ack, b_csi1, c);
+
+  const unsigned bpre        = qm * c.nof_layers;
+  const unsigned per_prb_dm  = c.nof_cdm_groups_without_data * ((cfg[6] == 1) ? 6 : 4);
+  unsigned       pos         = 0;
+  for (unsigned l = c.start_symbol_index; l != c.start_symbol_index + c.nof_symbols; ++l) {
+    unsigned nof_re = c.dmrs_symbol_mask.test(l) ? (12 - per_prb_dm) * c.nof_prb : 12 * c.nof_prb;
+    unsigned count  = 0;
+    while (count != nof_re) {
+      unsigned want = nof_re - count;
+      if (max_block_re != 0) {
+        want = std::min(want, max_block_re);
+      }
+      span<log_likelihood_ratio> view = cw.get_next_block_view(want * bpre);
+      unsigned                   n    = view.size();
+      if (n == 0) {
+        // The reference's demodulator would spin here (an allocation whose FIRST symbol carries no data together with
+        // UCI): not a case the reference supports.
+        return -3;
+      }
+      for (unsigned i = 0; i != n; ++i) {
+        view[i] = log_likelihood_ratio(in[pos + i]);
+      }
+      dynamic_bit_buffer seq(n);
+      for (unsigned i = 0; i != n; ++i) {
+        seq.insert(seq_bits[pos + i], i, 1);
+      }
+      cw.on_new_block(view, seq);
+      pos += n;
+      count += n / bpre;
+    }
+  }
+  if (pos != n_in) {
+    return -2;
+  }
+  cw.on_end_codeword();
+  spy_decoder_buffer* bufs[4] = {&b_sch, &b_ack, &b_csi1, &b_csi2};
+  int8_t*             outs[4] = {sch, harq_ack, csi_part1, csi_part2};
+  for (int k = 0; k != 4; ++k) {
+    n_out[k] = bufs[k]->data.size();
+    for (unsigned i = 0; i != n_out[k]; ++i) {
+      outs[k][i] = bufs[k]->data[i].to_value_type();
+    }
+  }
+  return 0;
 }
 
 } // extern "C"

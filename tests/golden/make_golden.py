@@ -7,6 +7,9 @@
   ref_decoder.npz       - LLR inputs and the outputs (bits, iterations) of the compiled reference's ldpc_decoder
                           ("auto" = avx512/avx2, and "generic"), produced through oracle/_ref/libsrsref.so.
   ref_dematcher.npz     - HARQ buffer before/after the compiled reference's ldpc_rate_dematcher.
+  ref_frontend.npz      - codeword front end: pseudo-random sequences of the compiled reference's
+                          pseudo_random_generator_impl and inputs/outputs of its ulsch_demultiplex_impl (fed block by
+                          block like pusch_demodulator_impl does) for 40 random configurations.
   ref_pusch.npz         - transport-block level: LLRs of 4 HARQ transmissions, expected TB bytes/CRC/statistics and
                           CRC32 of every codeblock soft buffer after each transmission (reference pusch_decoder_impl).
 """
@@ -173,9 +176,36 @@ def gen_pusch(orc):
                         soft_crc32=np.array(crcs, np.uint32))
 
 
+def gen_frontend(orc):
+    from tests.vectors import ulsch_case
+    ref = po.Reference("auto")
+    rng = np.random.default_rng(2024)
+    prg_cases = [(0, 0, 256), (1, 0, 300), (12345, 0, 2000), (0x7FFFFFFF, 777, 1000), (1 << 30, 100000, 500),
+                 (4660 * 32768 + 321, 1362816 - 640, 640)]
+    prg = [np.packbits(ref.prg_bits(c, o, n)) for c, o, n in prg_cases]
+    cfgs, llrs, seqs, outs, lens = [], [], [], [], []
+    while len(cfgs) < 40:
+        cfg, llr, seq, _ = ulsch_case(orc, rng, max_prb=12)
+        rc, ro = ref.ulsch_demux(cfg, llr, seq, int(rng.choice([0, 0, 7, 50])))
+        if rc != 0:
+            continue
+        cfgs.append(po.ulsch_cfg_array(cfg))
+        llrs.append(llr)
+        seqs.append(np.packbits(seq))
+        outs.extend(ro)
+        lens.append([llr.size] + [o.size for o in ro])
+    np.savez_compressed(OUT / "ref_frontend.npz", prg_cases=np.array(prg_cases, np.int64), prg_bits=np.concatenate(prg),
+                        cfgs=np.array(cfgs, np.int32), llrs=np.concatenate(llrs), seq_bits=np.concatenate(seqs),
+                        outs=np.concatenate(outs), lens=np.array(lens, np.int64))
+
+
 if __name__ == "__main__":
     orc = po.Oracle()
+    if "--frontend-only" in sys.argv:
+        gen_frontend(orc)
+        sys.exit(0)
     gen_examples()
+    gen_frontend(orc)
     gen_decoder(orc)
     gen_dematcher()
     gen_pusch(orc)

@@ -111,3 +111,53 @@ def make_cb_batch(orc, bg, Z, n_cb, E, qm, rv, snr_db, seed, crc_kind=po.CRC24B,
 def make_tb_llrs(orc, tb, bg, rv, qm, nref, nof_layers, n_llr, snr_db, rng):
     cw, n_cb = orc.tb_encode(tb, bg, rv, qm, nref, nof_layers, n_llr)
     return awgn_llr(cw, snr_db, rng), n_cb
+
+
+# ---- codeword front end (UL-SCH demultiplexing) -------------------------------------------------------------------------
+
+def random_ulsch_cfg(rng, max_prb=40):
+    """A random, self-consistent ulsch_demultiplex configuration (dict with the fields of orc_ulsch_cfg): every
+    modulation, 1-4 layers, both DM-RS types, HARQ-ACK with 0 / 1 / 2 / more bits, CSI Part 1 and Part 2. The first OFDM
+    symbol of the allocation always carries data (the reference's demodulator cannot start on an empty symbol)."""
+    qm = int(rng.choice([1, 2, 4, 6, 8]))
+    nl = int(rng.integers(1, 5)) if qm > 1 else 1
+    nprb = int(rng.integers(1, max_prb))
+    start = int(rng.integers(0, 4))
+    nsym = int(rng.integers(4, 15 - start))
+    dt = int(rng.integers(1, 3))
+    cdm = int(rng.integers(1, 3 if dt == 1 else 4))
+    full_dmrs = cdm * (6 if dt == 1 else 4) == 12
+    lo = start + 1 if full_dmrs else start
+    mask = 0
+    for p in set(int(x) for x in rng.integers(lo, start + nsym - 1, size=int(rng.integers(1, 4)))):
+        mask |= 1 << p
+    cfg = dict(qm=qm, nof_layers=nl, nof_prb=nprb, start_symbol_index=start, nof_symbols=nsym, dmrs_type=dt,
+               dmrs_symbol_mask=mask, nof_cdm_groups_without_data=cdm)
+    bpre = qm * nl
+    per_dmrs = (12 - cdm * (6 if dt == 1 else 4)) * nprb
+    nre = sum(per_dmrs if (mask >> l) & 1 else 12 * nprb for l in range(start, start + nsym))
+    ack_bits = int(rng.choice([0, 0, 1, 2, 3, 7, 20]))
+    cfg["nof_harq_ack_bits"] = ack_bits
+    if ack_bits > 0:
+        cfg["nof_enc_harq_ack_bits"] = int(rng.integers(1, max(2, nre // 6))) * bpre
+    if ack_bits <= 2:
+        cfg["nof_harq_ack_rvd"] = max(cfg.get("nof_enc_harq_ack_bits", 0), int(rng.integers(0, max(1, nre // 5))) * bpre)
+    if rng.random() < 0.5:
+        cfg["nof_csi_part1_bits"] = int(rng.choice([1, 2, 5, 30]))
+        cfg["nof_enc_csi_part1_bits"] = int(rng.integers(1, max(2, nre // 6))) * bpre
+        if rng.random() < 0.5:
+            cfg["nof_csi_part2_bits"] = int(rng.choice([1, 2, 9]))
+            cfg["nof_enc_csi_part2_bits"] = int(rng.integers(1, max(2, nre // 6))) * bpre
+    return cfg
+
+
+def ulsch_case(orc, rng, max_prb=40):
+    """(cfg, descrambled LLRs, scrambling bits) of a configuration the oracle accepts (all UCI fits)."""
+    while True:
+        cfg = random_ulsch_cfg(rng, max_prb)
+        n = orc.ulsch_codeword_length(cfg)
+        llr = rng.integers(-120, 121, n).astype(np.int8)
+        seq = rng.integers(0, 2, n).astype(np.uint8)
+        rc, outs = orc.ulsch_demux(cfg, llr, seq)
+        if rc == 0:
+            return cfg, llr, seq, outs
