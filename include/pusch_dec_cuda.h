@@ -104,6 +104,49 @@ typedef struct {
   uint16_t reserved;
 } pdc_tb_result;
 
+/*
+ * One PUSCH codeword of the front end: the soft bits of one UE in one slot as the soft demapper
+ * emits them, in resource-element order over the OFDM symbols of the allocation. Carries the fields of
+ * ulsch_demultiplex::configuration (include/srsran/phy/upper/channel_processors/pusch/ulsch_demultiplex.h:46-76), the
+ * scrambling seed of pusch_demodulator_impl::demodulate (c_init = rnti * 2^15 + n_id, pusch_demodulator_impl.cpp:139-140)
+ * and the CSI Part 2 sizes the PUSCH processor passes to set_csi_part2 once CSI Part 1 is decoded
+ * (pusch_processor_impl.cpp:61-82; both 0 = no CSI Part 2).
+ */
+#define PDC_CW_SCRAMBLED 1u /* the input still carries the scrambling sequence: descramble on the device             */
+
+typedef struct {
+  uint32_t in_offset;   /* first soft bit of the codeword in the input buffer                                         */
+  uint32_t sch_offset;  /* where its UL-SCH soft bits start in the UL-SCH space (multiple of 4); pdc_cb_desc::llr_offset
+                           of the transport block's codeblocks refers to that space                                   */
+  uint32_t uci_offset;  /* where its UCI soft bits go in the UCI output: HARQ-ACK, CSI Part 1, CSI Part 2 back to back  */
+  uint32_t c_init;
+  uint32_t flags;       /* PDC_CW_*                                                                                    */
+  uint8_t  qm;          /* bits per symbol of the modulation: 1, 2, 4, 6, 8                                            */
+  uint8_t  nof_layers;  /* 1..4                                                                                        */
+  uint8_t  start_symbol_index;
+  uint8_t  nof_symbols;
+  uint8_t  dmrs_type;   /* 1 or 2                                                                                      */
+  uint8_t  nof_cdm_groups_without_data;
+  uint16_t nof_prb;
+  uint16_t dmrs_symbol_mask; /* bit l: OFDM symbol l of the slot carries DM-RS                                        */
+  uint16_t reserved;
+  uint32_t nof_harq_ack_rvd;
+  uint32_t nof_harq_ack_bits;
+  uint32_t nof_enc_harq_ack_bits;
+  uint32_t nof_csi_part1_bits;
+  uint32_t nof_enc_csi_part1_bits;
+  uint32_t nof_csi_part2_bits;
+  uint32_t nof_enc_csi_part2_bits;
+} pdc_cw_desc;
+
+/* Soft bits delivered to each of the four decoder buffers of ulsch_demultiplex::demultiplex / set_csi_part2. */
+typedef struct {
+  uint32_t n_sch;
+  uint32_t n_harq_ack;
+  uint32_t n_csi_part1;
+  uint32_t n_csi_part2;
+} pdc_cw_result;
+
 typedef struct {
   int32_t  device;          /* CUDA device ordinal                                                                     */
   uint32_t max_cbs;         /* largest batch, in codeblocks                                                            */
@@ -169,6 +212,25 @@ int pdc_submit(pdc_ctx*           ctx,
                uint8_t*           tb_bytes);
 /* Blocks until the batch on this stream is complete and its outputs are in the host buffers given to pdc_submit. */
 int pdc_wait(pdc_ctx* ctx, uint32_t stream);
+
+/*
+ * Codeword front end of a batch = pusch_demodulator_impl's descrambling (pusch_demodulator_impl.cpp:254-259) +
+ * ulsch_demultiplex_impl (lib/phy/upper/channel_processors/pusch/ulsch_demultiplex_impl.cpp:200-589), on the device:
+ * H2D copy of the n_raw soft bits of all codewords, scrambling sequences, descrambling, demultiplexing into the UL-SCH
+ * soft bits of the batch (which stay on the device, where the rate dematcher reads them) and into the UCI soft bits
+ * (copied to uci_out). Call it before pdc_submit on the same stream and pass llrs = NULL, n_llrs = 0 to pdc_submit:
+ * the codeblock descriptors then address the demultiplexed UL-SCH space. results[n_cw] and uci_out are valid after
+ * pdc_wait (results also right away: the lengths are known from the plan).
+ */
+int pdc_submit_codewords(pdc_ctx*           ctx,
+                         uint32_t           stream,
+                         const pdc_cw_desc* cws,
+                         uint32_t           n_cw,
+                         const int8_t*      raw_llrs,
+                         size_t             n_raw,
+                         int8_t*            uci_out,
+                         size_t             uci_capacity,
+                         pdc_cw_result*     results);
 /* Non-blocking: *done = 1 when pdc_wait would not block. */
 int pdc_poll(pdc_ctx* ctx, uint32_t stream, int* done);
 
@@ -239,6 +301,26 @@ int pdc_rate_dematch(pdc_ctx*      ctx,
                      uint32_t      nof_filler);
 
 /* crc_calculator::calculate over the first nbits (MSB first) of packed[]. */
+/*
+ * ulsch_demultiplex::demultiplex for n_cw codewords, synchronous, host buffers. seq_bits: the scrambling sequence of
+ * the input, packed MSB first and indexed like llrs (bit in_offset + i belongs to soft bit i of the codeword), as
+ * pusch_codeword_buffer::on_new_block receives it; NULL = generated on the device from c_init. sch_out receives the
+ * UL-SCH soft bits at sch_offset, uci_out the UCI soft bits at uci_offset.
+ */
+int pdc_ulsch_demux(pdc_ctx*           ctx,
+                    const pdc_cw_desc* cws,
+                    uint32_t           n_cw,
+                    const int8_t*      llrs,
+                    size_t             n_llrs,
+                    const uint8_t*     seq_bits,
+                    int8_t*            sch_out,
+                    size_t             sch_capacity,
+                    int8_t*            uci_out,
+                    size_t             uci_capacity,
+                    pdc_cw_result*     results);
+/* TS 38.211 5.2.1 pseudo-random sequence c(offset .. offset + n - 1), packed MSB first (pseudo_random_generator::generate). */
+int pdc_scrambling_sequence(pdc_ctx* ctx, uint32_t c_init, uint32_t offset, uint32_t n, uint8_t* packed);
+
 int pdc_crc(pdc_ctx* ctx, int crc_kind, const uint8_t* packed, uint32_t nbits, uint32_t* checksum);
 
 #ifdef __cplusplus

@@ -53,13 +53,24 @@ CB_RESULT_DTYPE = np.dtype([("crc_ok", "u1"), ("iters", "u1"), ("status", "u1"),
 TB_DESC_DTYPE = np.dtype([("first_cb", "<u4"), ("nof_cb", "<u4"), ("tbs_bits", "<u4"), ("out_offset", "<u4"),
                           ("reserved", "<u4")])
 TB_RESULT_DTYPE = np.dtype([("tb_crc_ok", "u1"), ("all_cb_ok", "u1"), ("reserved", "<u2")])
+CW_SCRAMBLED = 1
+# pdc_cw_desc / pdc_cw_result (codeword front end)
+CW_DESC_DTYPE = np.dtype([("in_offset", "<u4"), ("sch_offset", "<u4"), ("uci_offset", "<u4"), ("c_init", "<u4"),
+                          ("flags", "<u4"), ("qm", "u1"), ("nof_layers", "u1"), ("start_symbol_index", "u1"),
+                          ("nof_symbols", "u1"), ("dmrs_type", "u1"), ("nof_cdm_groups_without_data", "u1"),
+                          ("nof_prb", "<u2"), ("dmrs_symbol_mask", "<u2"), ("reserved", "<u2"),
+                          ("nof_harq_ack_rvd", "<u4"), ("nof_harq_ack_bits", "<u4"), ("nof_enc_harq_ack_bits", "<u4"),
+                          ("nof_csi_part1_bits", "<u4"), ("nof_enc_csi_part1_bits", "<u4"),
+                          ("nof_csi_part2_bits", "<u4"), ("nof_enc_csi_part2_bits", "<u4")])
+CW_RESULT_DTYPE = np.dtype([("n_sch", "<u4"), ("n_harq_ack", "<u4"), ("n_csi_part1", "<u4"), ("n_csi_part2", "<u4")])
+assert CW_DESC_DTYPE.itemsize == 60 and CW_RESULT_DTYPE.itemsize == 16
 assert CB_DESC_DTYPE.itemsize == ctypes.sizeof(CbDesc) == 28
 assert TB_DESC_DTYPE.itemsize == ctypes.sizeof(TbDesc) == 20
 
 EXPORTS = ["pdc_default_config", "pdc_create", "pdc_destroy", "pdc_last_error", "pdc_device_info", "pdc_launch_count",
            "pdc_measure_int_peak", "pdc_host_alloc", "pdc_host_free", "pdc_submit", "pdc_wait", "pdc_poll", "pdc_launch_device",
            "pdc_harq_read", "pdc_harq_write", "pdc_harq_free", "pdc_harq_device_ptr", "pdc_ldpc_decode",
-           "pdc_rate_dematch", "pdc_crc"]
+           "pdc_rate_dematch", "pdc_crc", "pdc_submit_codewords", "pdc_ulsch_demux", "pdc_scrambling_sequence"]
 
 _lib = None
 
@@ -109,6 +120,10 @@ def load():
                                   ctypes.POINTER(ctypes.c_int)]
     L.pdc_rate_dematch.argtypes = [_vp, _vp, _u32, _vp, _u32, ctypes.c_int, ctypes.c_int, ctypes.c_int, _u32, _u32]
     L.pdc_crc.argtypes = [_vp, ctypes.c_int, _vp, _u32, ctypes.POINTER(_u32)]
+    L.pdc_submit_codewords.argtypes = [_vp, _u32, _vp, _u32, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp]
+    L.pdc_ulsch_demux.argtypes = [_vp, _vp, _u32, _vp, ctypes.c_size_t, _vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t,
+                                  _vp]
+    L.pdc_scrambling_sequence.argtypes = [_vp, _u32, _u32, _u32, _vp]
     _lib = L
     return L
 
@@ -162,6 +177,7 @@ class Context:
         self.h = _vp()
         check(L.pdc_create(ctypes.byref(cfg), ctypes.byref(self.h)))
         self._pending = {}
+        self._pending_fe = {}
 
     def close(self):
         if getattr(self, "h", None):
@@ -190,7 +206,8 @@ class Context:
         """cbs: numpy array of CB_DESC_DTYPE; llrs: int8 array (ideally a PinnedBuffer view); tbs: TB_DESC_DTYPE.
         out_bits / out_tb: caller-owned uint8 output arrays (PinnedBuffer views are written by the GPU directly)."""
         cbs = np.ascontiguousarray(cbs, CB_DESC_DTYPE)
-        assert llrs.dtype == np.int8 and llrs.flags.c_contiguous
+        # llrs = None: the LLRs are the UL-SCH soft bits submit_codewords() left on the device.
+        assert llrs is None or (llrs.dtype == np.int8 and llrs.flags.c_contiguous)
         n_cb = cbs.size
         n_tb = 0 if tbs is None else tbs.size
         out = {
@@ -210,7 +227,8 @@ class Context:
             if want_tb:
                 need = int(max(t["out_offset"] + (int(t["tbs_bits"]) + 24 + 31) // 32 * 4 for t in tbs))
                 out["tb_bytes"] = out_tb[:need] if out_tb is not None else np.zeros(need, np.uint8)
-        check(self._L.pdc_submit(self.h, stream, _ptr(cbs), n_cb, _ptr(llrs), llrs.size, _ptr(out["tbs"]), n_tb,
+        check(self._L.pdc_submit(self.h, stream, _ptr(cbs), n_cb, _ptr(llrs), 0 if llrs is None else llrs.size,
+                                 _ptr(out["tbs"]), n_tb,
                                  _ptr(out["cb_results"]), _ptr(out["cb_bits"]), _ptr(out["tb_results"]),
                                  _ptr(out["tb_bytes"])))
         self._pending[stream] = out
@@ -218,7 +236,46 @@ class Context:
 
     def wait(self, stream=0):
         check(self._L.pdc_wait(self.h, stream))
-        return self._pending.pop(stream, None)
+        out = self._pending.pop(stream, None)
+        fe = self._pending_fe.pop(stream, None)
+        if fe is not None:
+            if out is None:
+                return fe
+            out["codewords"] = fe
+        return out
+
+    # -- codeword front end ---------------------------------------------------------------------------------------------
+    def submit_codewords(self, cws, raw_llrs, stream=0, out_uci=None):
+        """pdc_submit_codewords: descrambling + UL-SCH demultiplexing of the batch's codewords on the device; follow it
+        with submit(cbs, None, ...) on the same stream. cws: CW_DESC_DTYPE array; raw_llrs: int8 (ideally pinned)."""
+        cws = np.ascontiguousarray(cws, CW_DESC_DTYPE)
+        assert raw_llrs.dtype == np.int8 and raw_llrs.flags.c_contiguous
+        res = np.zeros(cws.size, CW_RESULT_DTYPE)
+        uci = out_uci if out_uci is not None else np.zeros(max(1, raw_llrs.size), np.int8)
+        check(self._L.pdc_submit_codewords(self.h, stream, _ptr(cws), cws.size, _ptr(raw_llrs), raw_llrs.size, _ptr(uci),
+                                           uci.size, _ptr(res)))
+        fe = {"cws": cws, "raw_llrs": raw_llrs, "cw_results": res, "uci": uci}
+        self._pending_fe[stream] = fe
+        return fe
+
+    def ulsch_demux(self, cws, llrs, seq_bits_packed=None, sch_capacity=None, uci_capacity=None):
+        """pdc_ulsch_demux (synchronous). Returns (cw_results, sch, uci)."""
+        cws = np.ascontiguousarray(cws, CW_DESC_DTYPE)
+        llrs = np.ascontiguousarray(llrs, np.int8)
+        sch = np.zeros(sch_capacity if sch_capacity is not None else llrs.size + 4 * cws.size, np.int8)
+        uci = np.zeros(uci_capacity if uci_capacity is not None else max(1, llrs.size), np.int8)
+        res = np.zeros(cws.size, CW_RESULT_DTYPE)
+        if seq_bits_packed is not None:
+            seq_bits_packed = np.ascontiguousarray(seq_bits_packed, np.uint8)
+        check(self._L.pdc_ulsch_demux(self.h, _ptr(cws), cws.size, _ptr(llrs), llrs.size, _ptr(seq_bits_packed), _ptr(sch),
+                                      sch.size, _ptr(uci), uci.size, _ptr(res)))
+        return res, sch, uci
+
+    def scrambling_sequence(self, c_init, offset, n):
+        """TS 38.211 5.2.1 sequence c(offset .. offset + n - 1), one bit per element."""
+        packed = np.zeros((n + 7) // 8, np.uint8)
+        check(self._L.pdc_scrambling_sequence(self.h, c_init, offset, n, _ptr(packed)))
+        return np.unpackbits(packed)[:n]
 
     def poll(self, stream=0):
         d = ctypes.c_int()

@@ -7,6 +7,7 @@
 #include "ldpc_decode_scalar.cuh"
 #include "ldpc_decode_h2.cuh"
 #include "tb_assemble.cuh"
+#include "ulsch_demux.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -38,7 +39,28 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess)
     }                                                                                                                  \
   } while (0)
 
+// Buffers of the codeword front end (grow-only; the plan is staged in pinned memory).
+struct FrontEnd {
+  pdc::UlschPlan       plan;
+  int8_t*              d_raw = nullptr;
+  size_t               raw_cap = 0;
+  uint32_t*            d_seq = nullptr;
+  size_t               seq_cap = 0;
+  int8_t*              d_uci = nullptr;
+  int8_t*              h_uci = nullptr;
+  size_t               uci_cap = 0;
+  unsigned char*       d_plan = nullptr;
+  unsigned char*       h_plan = nullptr;
+  size_t               plan_cap = 0;
+  // Pending results of the queue.
+  int8_t*              u_uci = nullptr;
+  size_t               uci_bytes = 0;
+  uint32_t             sch_len = 0; // soft bits of the demultiplexed UL-SCH space waiting for pdc_submit
+  bool                 pending = false;
+};
+
 struct Queue {
+  FrontEnd     fe;
   cudaStream_t stream = nullptr;
   cudaEvent_t  done   = nullptr;
   // Device staging.
@@ -85,6 +107,9 @@ struct pdc_ctx {
   bool                 force_scalar = false;      // PDC_FORCE_SCALAR=1: use the general kernel for every batch
   uint32_t*            d_state_scratch = nullptr; // compressed check-to-variable messages of the resident CTAs
   size_t               state_scratch_words = 0;
+  FrontEnd             fe_sync;                   // buffers of the synchronous front-end calls
+  int8_t*              d_sch_sync = nullptr;
+  size_t               sch_sync_cap = 0;
 };
 
 namespace {
@@ -190,6 +215,23 @@ cudaError_t dev_alloc(T** p, size_t n)
 {
   return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
 }
+template <typename T>
+static cudaError_t grow_device(T** p, size_t* cap, size_t need)
+{
+  if (need <= *cap) {
+    return cudaSuccess;
+  }
+  cudaFree(*p);
+  *p   = nullptr;
+  *cap = 0;
+  size_t      want = need + need / 4 + 64;
+  cudaError_t e    = cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T));
+  if (e == cudaSuccess) {
+    *cap = want;
+  }
+  return e;
+}
+
 template <typename T>
 cudaError_t host_alloc(T** p, size_t n)
 {
@@ -358,6 +400,7 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
   } while (0)
   PDC_CREATE(pdc::upload_tables());
   PDC_CREATE(pdc::upload_tb_tables());
+  PDC_CREATE(pdc::upload_prg_tables());
   PDC_CREATE(upload_crc_tables());
   size_t entries = (size_t)cfg->harq_entries + 1;
   PDC_CREATE(dev_alloc(&ctx->d_harq, entries * PDC_MAX_CB_SOFT));
@@ -395,12 +438,25 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
   return PDC_OK;
 }
 
+static void free_front_end(FrontEnd& fe)
+{
+  cudaFree(fe.d_raw);
+  cudaFree(fe.d_seq);
+  cudaFree(fe.d_uci);
+  cudaFree(fe.d_plan);
+  cudaFreeHost(fe.h_uci);
+  cudaFreeHost(fe.h_plan);
+  fe = FrontEnd();
+}
+
 void pdc_destroy(pdc_ctx* ctx)
 {
   if (!ctx) {
     return;
   }
   cudaSetDevice(ctx->cfg.device);
+  free_front_end(ctx->fe_sync);
+  cudaFree(ctx->d_sch_sync);
   for (Queue& q : ctx->queues) {
     if (q.stream) {
       cudaStreamSynchronize(q.stream);
@@ -417,6 +473,7 @@ void pdc_destroy(pdc_ctx* ctx)
     cudaFree(q.d_tb_res);
     cudaFree(q.d_tb_out);
     cudaFree(q.d_tb_sync);
+    free_front_end(q.fe);
     cudaFreeHost(q.h_cbs);
     cudaFreeHost(q.h_tbs);
     cudaFreeHost(q.h_cb_res);
@@ -505,6 +562,12 @@ int pdc_submit(pdc_ctx*           ctx,
   if (q.busy) {
     return fail(PDC_ERR_CAPACITY, "pdc_submit: queue busy (call pdc_wait first)");
   }
+  if (llrs == nullptr && n_llrs == 0 && q.fe.pending) {
+    // The rate-matched LLRs are the UL-SCH soft bits pdc_submit_codewords left on the device.
+    n_llrs = q.fe.sch_len;
+  } else if (llrs == nullptr && n_llrs != 0) {
+    return fail(PDC_ERR_INVALID, "pdc_submit: no LLR buffer");
+  }
   // Validate what the kernels index with before anything is queued.
   for (uint32_t i = 0; i != n_cb; ++i) {
     if ((size_t)cbs[i].llr_offset + cbs[i].rm_length > n_llrs && (cbs[i].flags & PDC_CB_DEMATCH)) {
@@ -527,7 +590,7 @@ int pdc_submit(pdc_ctx*           ctx,
   BatchShape shape = scan_batch(cbs, n_cb);
   memcpy(q.h_cbs, cbs, sizeof(pdc_cb_desc) * n_cb);
   PDC_CUDA(cudaMemcpyAsync(q.d_cbs, q.h_cbs, sizeof(pdc_cb_desc) * n_cb, cudaMemcpyHostToDevice, q.stream));
-  if (n_llrs != 0) {
+  if (n_llrs != 0 && llrs != nullptr) {
     PDC_CUDA(cudaMemcpyAsync(q.d_llrs, llrs, n_llrs, cudaMemcpyHostToDevice, q.stream));
   }
   if (n_tb != 0) {
@@ -568,16 +631,177 @@ int pdc_submit(pdc_ctx*           ctx,
   return PDC_OK;
 }
 
+
+// ---- codeword front end ------------------------------------------------------------------------------------------------
+
+// Plans the codewords, uploads the plan and queues the kernels on stream s:
+//   d_in (raw soft bits, already on the device) -> d_sch (UL-SCH space) and fe.d_uci (UCI area of n_uci bytes).
+// seq_words != nullptr: caller-supplied scrambling sequence (fe.plan layout), else generated from c_init.
+static int front_end_launch(pdc_ctx*           ctx,
+                            FrontEnd&          fe,
+                            const pdc_cw_desc* cws,
+                            uint32_t           n_cw,
+                            size_t             n_in,
+                            const int8_t*      d_in,
+                            int8_t*            d_sch,
+                            size_t             sch_capacity,
+                            size_t             uci_capacity,
+                            const uint8_t*     seq_bits_packed,
+                            pdc_cw_result*     results,
+                            cudaStream_t       s)
+{
+  pdc::UlschPlan& plan = fe.plan;
+  plan.clear();
+  size_t sch_end = 0, uci_end = 0;
+  for (uint32_t i = 0; i != n_cw; ++i) {
+    if (!pdc::ulsch_plan_codeword(cws[i], plan)) {
+      return fail(PDC_ERR_INVALID, "codeword front end: inconsistent codeword description");
+    }
+    const pdc::UlschCodeword& cw = plan.cws.back();
+    if ((cws[i].sch_offset & 3u) || (size_t)cw.in_off + cw.n_in > n_in) {
+      return fail(PDC_ERR_INVALID, "codeword front end: codeword outside the input or misaligned UL-SCH offset");
+    }
+    results[i].n_sch       = cw.n_out[0];
+    results[i].n_harq_ack  = cw.n_out[1];
+    results[i].n_csi_part1 = cw.n_out[2];
+    results[i].n_csi_part2 = cw.n_out[3];
+    sch_end = std::max(sch_end, (size_t)cw.sch_off + cw.n_out[0]);
+    uci_end = std::max(uci_end, (size_t)cw.uci_off + cw.n_out[1] + cw.n_out[2] + cw.n_out[3]);
+  }
+  if (sch_end > sch_capacity || uci_end > uci_capacity) {
+    return fail(PDC_ERR_CAPACITY, "codeword front end: output buffer too small");
+  }
+  // Plan image: codewords | symbols | element lists.
+  const size_t b_cws  = plan.cws.size() * sizeof(pdc::UlschCodeword);
+  const size_t b_syms = plan.syms.size() * sizeof(pdc::UlschSymbol);
+  const size_t b_list = ((plan.lists.size() * sizeof(uint16_t)) + 15) & ~(size_t)15;
+  const size_t bytes  = b_cws + b_syms + b_list;
+  if (bytes > fe.plan_cap) {
+    cudaFreeHost(fe.h_plan);
+    fe.h_plan = nullptr;
+    PDC_CUDA(grow_device(&fe.d_plan, &fe.plan_cap, bytes));
+    PDC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&fe.h_plan), fe.plan_cap));
+  }
+  memcpy(fe.h_plan, plan.cws.data(), b_cws);
+  memcpy(fe.h_plan + b_cws, plan.syms.data(), b_syms);
+  memcpy(fe.h_plan + b_cws + b_syms, plan.lists.data(), plan.lists.size() * sizeof(uint16_t));
+  PDC_CUDA(cudaMemcpyAsync(fe.d_plan, fe.h_plan, bytes, cudaMemcpyHostToDevice, s));
+  PDC_CUDA(grow_device(&fe.d_seq, &fe.seq_cap, (size_t)plan.seq_words + 8));
+  if (uci_end > fe.uci_cap) {
+    cudaFreeHost(fe.h_uci);
+    fe.h_uci = nullptr;
+    PDC_CUDA(grow_device(&fe.d_uci, &fe.uci_cap, uci_end));
+    PDC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&fe.h_uci), fe.uci_cap));
+  }
+  pdc::UlschArgs a;
+  a.cws   = reinterpret_cast<const pdc::UlschCodeword*>(fe.d_plan);
+  a.syms  = reinterpret_cast<const pdc::UlschSymbol*>(fe.d_plan + b_cws);
+  a.lists = reinterpret_cast<const uint16_t*>(fe.d_plan + b_cws + b_syms);
+  a.seq   = fe.d_seq;
+  a.in    = d_in;
+  a.sch   = d_sch;
+  a.uci   = fe.d_uci;
+  uint32_t max_in = 0, max_sch = 0, max_uci = 0;
+  for (const pdc::UlschCodeword& cw : plan.cws) {
+    max_in  = std::max(max_in, cw.n_in);
+    max_sch = std::max(max_sch, cw.n_out[0]);
+    max_uci = std::max(max_uci, cw.n_out[1] + cw.n_out[2] + cw.n_out[3]);
+  }
+  if (seq_bits_packed != nullptr) {
+    // Caller-supplied sequence (MSB-first bit string indexed like the input): repack per codeword, element k in bit k.
+    std::vector<uint32_t> words(plan.seq_words + 8, 0u);
+    for (const pdc::UlschCodeword& cw : plan.cws) {
+      for (uint32_t i = 0; i != cw.n_in; ++i) {
+        const size_t b = (size_t)cw.in_off + i;
+        if ((seq_bits_packed[b >> 3] >> (7u - (b & 7u))) & 1u) {
+          words[cw.seq_word_off + (i >> 5)] |= 1u << (i & 31u);
+        }
+      }
+    }
+    PDC_CUDA(cudaMemcpyAsync(fe.d_seq, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    PDC_CUDA(cudaStreamSynchronize(s)); // `words` goes out of scope
+  } else {
+    const uint32_t per_cta = 128 * pdc::PRG_WORDS_PER_THREAD;
+    dim3           grid(((max_in + 31) / 32 + per_cta - 1) / per_cta, n_cw);
+    pdc::prg_kernel<<<grid, 128, 0, s>>>(a.cws, fe.d_seq);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  {
+    // Enough CTAs to fill the GPU a few times over; each thread steps through the words of its codeword.
+    const uint32_t words = (max_sch + 3) / 4;
+    uint32_t       gx    = std::max(1u, std::min((words + 255) / 256, (uint32_t)(8 * ctx->sm_count + n_cw - 1) / n_cw));
+    pdc::ulsch_sch_kernel<<<dim3(gx, n_cw), 256, 0, s>>>(a);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (max_uci != 0) {
+    pdc::ulsch_uci_kernel<<<dim3((max_uci + 255) / 256, n_cw), 256, 0, s>>>(a);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  fe.uci_bytes = uci_end;
+  fe.sch_len   = (uint32_t)sch_end;
+  return PDC_OK;
+}
+
+int pdc_submit_codewords(pdc_ctx*           ctx,
+                         uint32_t           stream,
+                         const pdc_cw_desc* cws,
+                         uint32_t           n_cw,
+                         const int8_t*      raw_llrs,
+                         size_t             n_raw,
+                         int8_t*            uci_out,
+                         size_t             uci_capacity,
+                         pdc_cw_result*     results)
+{
+  if (!ctx || stream >= ctx->queues.size() || !cws || n_cw == 0 || !raw_llrs || !results || n_cw > 65535u) {
+    return fail(PDC_ERR_INVALID, "pdc_submit_codewords: invalid argument");
+  }
+  Queue& q = ctx->queues[stream];
+  if (q.busy || q.fe.pending) {
+    return fail(PDC_ERR_CAPACITY, "pdc_submit_codewords: queue busy (call pdc_wait first)");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  PDC_CUDA(grow_device(&q.fe.d_raw, &q.fe.raw_cap, n_raw + 16));
+  PDC_CUDA(cudaMemcpyAsync(q.fe.d_raw, raw_llrs, n_raw, cudaMemcpyHostToDevice, q.stream));
+  int rc = front_end_launch(ctx, q.fe, cws, n_cw, n_raw, q.fe.d_raw, q.d_llrs, ctx->cfg.max_llrs,
+                            uci_out ? uci_capacity : (size_t)-1, nullptr, results, q.stream);
+  if (rc != PDC_OK) {
+    return rc;
+  }
+  q.fe.u_uci = nullptr;
+  if (uci_out && q.fe.uci_bytes != 0) {
+    const bool direct = is_pinned_host(uci_out);
+    PDC_CUDA(cudaMemcpyAsync(direct ? uci_out : q.fe.h_uci, q.fe.d_uci, q.fe.uci_bytes, cudaMemcpyDeviceToHost,
+                             q.stream));
+    q.fe.u_uci = direct ? nullptr : uci_out;
+  }
+  q.fe.pending = true;
+  return PDC_OK;
+}
+
 int pdc_wait(pdc_ctx* ctx, uint32_t stream)
 {
   if (!ctx || stream >= ctx->queues.size()) {
     return fail(PDC_ERR_INVALID, "pdc_wait: invalid argument");
   }
   Queue& q = ctx->queues[stream];
-  if (!q.busy) {
+  if (!q.busy && !q.fe.pending) {
     return PDC_OK;
   }
-  cudaError_t e = cudaEventSynchronize(q.done);
+  // A front end without a decode batch behind it has no event: wait for the stream.
+  cudaError_t e = q.busy ? cudaEventSynchronize(q.done) : cudaStreamSynchronize(q.stream);
+  if (q.fe.pending) {
+    q.fe.pending = false;
+    if (e == cudaSuccess && q.fe.u_uci != nullptr) {
+      memcpy(q.fe.u_uci, q.fe.h_uci, q.fe.uci_bytes);
+    }
+    q.fe.u_uci = nullptr;
+    if (!q.busy) {
+      return (e == cudaSuccess) ? PDC_OK : fail(PDC_ERR_CUDA, "pdc_wait", e);
+    }
+  }
   q.busy        = false;
   if (e != cudaSuccess) {
     // A failed batch reports CRC failure with the maximum iteration count, like a dropped accelerator operation
@@ -836,6 +1060,79 @@ int pdc_measure_int_peak(pdc_ctx* ctx, int mode, double* lane_ops_per_s)
   // 64 statements per inner iteration, 2 integer instructions each.
   double ops      = (double)blocks * threads * (double)iters * 64.0 * 2.0;
   *lane_ops_per_s = ops / (best * 1e-3);
+  return PDC_OK;
+}
+
+
+int pdc_ulsch_demux(pdc_ctx*           ctx,
+                    const pdc_cw_desc* cws,
+                    uint32_t           n_cw,
+                    const int8_t*      llrs,
+                    size_t             n_llrs,
+                    const uint8_t*     seq_bits,
+                    int8_t*            sch_out,
+                    size_t             sch_capacity,
+                    int8_t*            uci_out,
+                    size_t             uci_capacity,
+                    pdc_cw_result*     results)
+{
+  if (!ctx || !cws || n_cw == 0 || n_cw > 65535u || !llrs || !sch_out || !results) {
+    return fail(PDC_ERR_INVALID, "pdc_ulsch_demux: invalid argument");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  FrontEnd& fe = ctx->fe_sync;
+  PDC_CUDA(grow_device(&fe.d_raw, &fe.raw_cap, n_llrs + 16));
+  PDC_CUDA(grow_device(&ctx->d_sch_sync, &ctx->sch_sync_cap, sch_capacity + 16));
+  PDC_CUDA(cudaMemcpyAsync(fe.d_raw, llrs, n_llrs, cudaMemcpyHostToDevice, nullptr));
+  int rc = front_end_launch(ctx, fe, cws, n_cw, n_llrs, fe.d_raw, ctx->d_sch_sync, sch_capacity,
+                            uci_out ? uci_capacity : (size_t)-1, seq_bits, results, nullptr);
+  if (rc != PDC_OK) {
+    cudaStreamSynchronize(nullptr);
+    return rc;
+  }
+  // Only the codewords' own ranges are written back: the caller's buffer may hold other data in between.
+  for (const pdc::UlschCodeword& cw : fe.plan.cws) {
+    if (cw.n_out[0] != 0) {
+      PDC_CUDA(cudaMemcpyAsync(sch_out + cw.sch_off, ctx->d_sch_sync + cw.sch_off, cw.n_out[0], cudaMemcpyDeviceToHost,
+                               nullptr));
+    }
+    const uint32_t n_uci = cw.n_out[1] + cw.n_out[2] + cw.n_out[3];
+    if (uci_out && n_uci != 0) {
+      PDC_CUDA(cudaMemcpyAsync(uci_out + cw.uci_off, fe.d_uci + cw.uci_off, n_uci, cudaMemcpyDeviceToHost, nullptr));
+    }
+  }
+  PDC_CUDA(cudaStreamSynchronize(nullptr));
+  return PDC_OK;
+}
+
+int pdc_scrambling_sequence(pdc_ctx* ctx, uint32_t c_init, uint32_t offset, uint32_t n, uint8_t* packed)
+{
+  if (!ctx || !packed || n == 0 || (uint64_t)offset + n + pdc::PRG_NC >= (1ull << 21)) {
+    return fail(PDC_ERR_INVALID, "pdc_scrambling_sequence: invalid argument (sequence positions below 2^21 - 1600)");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  FrontEnd&          fe = ctx->fe_sync;
+  pdc::UlschCodeword cw = {};
+  cw.c_init             = c_init;
+  cw.n_in               = n;
+  cw.prg_offset         = offset;
+  const uint32_t n_words = (n + 31) / 32 + 8;
+  PDC_CUDA(grow_device(&fe.d_seq, &fe.seq_cap, (size_t)n_words));
+  PDC_CUDA(grow_device(&fe.d_plan, &fe.plan_cap, sizeof(cw)));
+  PDC_CUDA(cudaMemcpyAsync(fe.d_plan, &cw, sizeof(cw), cudaMemcpyHostToDevice, nullptr));
+  const uint32_t per_cta = 128 * pdc::PRG_WORDS_PER_THREAD;
+  pdc::prg_kernel<<<dim3(((n + 31) / 32 + per_cta - 1) / per_cta, 1), 128>>>(
+      reinterpret_cast<const pdc::UlschCodeword*>(fe.d_plan), fe.d_seq);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  std::vector<uint32_t> words(n_words);
+  PDC_CUDA(cudaMemcpy(words.data(), fe.d_seq, (size_t)((n + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  memset(packed, 0, (n + 7) / 8);
+  for (uint32_t i = 0; i != n; ++i) {
+    if ((words[i >> 5] >> (i & 31u)) & 1u) {
+      packed[i >> 3] |= (uint8_t)(0x80u >> (i & 7u));
+    }
+  }
   return PDC_OK;
 }
 

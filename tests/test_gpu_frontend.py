@@ -1,0 +1,173 @@
+"""GPU parity of the codeword front end (scrambling sequence, descrambling, UL-SCH demultiplexing) through the C ABI
+(pdc_scrambling_sequence, pdc_ulsch_demux, pdc_submit_codewords + pdc_submit) against the oracle restatement of
+pseudo_random_generator_impl / pusch_demodulator_impl::revert_scrambling / ulsch_demultiplex_impl."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from srsran_edgeric_5g_b200 import capi, ldpc
+from tests.vectors import make_tb_llrs, ulsch_case
+
+pytestmark = pytest.mark.gpu
+
+
+def cw_desc(cfg, in_offset=0, sch_offset=0, uci_offset=0, c_init=0, flags=0):
+    d = np.zeros(1, capi.CW_DESC_DTYPE)[0]
+    d["in_offset"], d["sch_offset"], d["uci_offset"], d["c_init"], d["flags"] = in_offset, sch_offset, uci_offset, c_init, flags
+    for k in po.ULSCH_CFG_FIELDS:
+        d[k] = cfg.get(k, 0)
+    return d
+
+
+def test_scrambling_sequence(ctx, orc):
+    for c_init, offset, n in [(0, 0, 64), (1, 0, 1), (12345, 0, 4000), (0x7FFFFFFF, 777, 3001), (1 << 30, 100000, 2000),
+                              (4660 * 32768 + 321, 0, 1362816), (99 << 15, 2000000, 90000)]:
+        got = ctx.scrambling_sequence(c_init, offset, n)
+        assert (got == orc.prg_bits(c_init, offset, n)).all(), (c_init, offset, n)
+
+
+def check_streams(res, sch, uci, d, outs):
+    assert [int(res["n_sch"]), int(res["n_harq_ack"]), int(res["n_csi_part1"]), int(res["n_csi_part2"])] == \
+           [o.size for o in outs]
+    so, uo = int(d["sch_offset"]), int(d["uci_offset"])
+    assert (sch[so:so + outs[0].size] == outs[0]).all()
+    want_uci = np.concatenate(outs[1:])
+    assert (uci[uo:uo + want_uci.size] == want_uci).all()
+
+
+def test_ulsch_demux_random_configurations(ctx, orc):
+    """Both entry conditions: descrambled input with the sequence supplied (what ulsch_demultiplex::on_new_block
+    receives), and scrambled input with the sequence generated on the device from c_init."""
+    rng = np.random.default_rng(5)
+    for trial in range(120):
+        cfg, llr, _, _ = ulsch_case(orc, rng)
+        c_init = int(rng.integers(0, 1 << 31))
+        seq = orc.prg_bits(c_init, 0, llr.size)
+        rc, outs = orc.ulsch_demux(cfg, llr, seq)
+        assert rc == 0
+        # (a) descrambled input + caller-supplied sequence
+        res, sch, uci = ctx.ulsch_demux(np.array([cw_desc(cfg)]), llr, np.packbits(seq))
+        check_streams(res[0], sch, uci, cw_desc(cfg), outs)
+        # (b) scrambled input, sequence from c_init
+        raw = orc.revert_scrambling(llr, seq)
+        d = cw_desc(cfg, c_init=c_init, flags=capi.CW_SCRAMBLED)
+        res, sch, uci = ctx.ulsch_demux(np.array([d]), raw)
+        check_streams(res[0], sch, uci, d, outs)
+
+
+def test_ulsch_demux_batch_of_codewords(ctx, orc):
+    """Several codewords in one call, each at its own offsets; bytes between the codewords' outputs stay untouched."""
+    rng = np.random.default_rng(6)
+    descs, raws, wants = [], [], []
+    in_off = sch_off = uci_off = 0
+    for k in range(12):
+        cfg, llr, _, _ = ulsch_case(orc, rng, max_prb=30)
+        c_init = int(rng.integers(0, 1 << 31))
+        seq = orc.prg_bits(c_init, 0, llr.size)
+        rc, outs = orc.ulsch_demux(cfg, llr, seq)
+        d = cw_desc(cfg, in_off, sch_off, uci_off, c_init, capi.CW_SCRAMBLED)
+        descs.append(d)
+        raws.append(orc.revert_scrambling(llr, seq))
+        wants.append(outs)
+        in_off += llr.size
+        sch_off += (outs[0].size + 3) // 4 * 4 + 8
+        uci_off += sum(o.size for o in outs[1:]) + 3
+    res, sch, uci = ctx.ulsch_demux(np.array(descs), np.concatenate(raws), sch_capacity=sch_off, uci_capacity=uci_off + 1)
+    for d, r, outs in zip(descs, res, wants):
+        check_streams(r, sch, uci, d, outs)
+    # gaps were not written
+    for d, outs in zip(descs, wants):
+        end = int(d["sch_offset"]) + outs[0].size
+        assert (sch[end:(end + 3) // 4 * 4 + 8][:8] == 0).all()
+
+
+def test_ulsch_demux_golden_vectors(ctx):
+    gold = np.load(Path(__file__).parent / "golden" / "ref_frontend.npz")
+    p_llr = p_seq = p_out = 0
+    for cfg_arr, lens in zip(gold["cfgs"], gold["lens"]):
+        cfg = dict(zip(po.ULSCH_CFG_FIELDS, (int(v) for v in cfg_arr)))
+        n = int(lens[0])
+        llr = gold["llrs"][p_llr:p_llr + n]
+        nb = (n + 7) // 8
+        seq_packed = gold["seq_bits"][p_seq:p_seq + nb]
+        p_llr += n
+        p_seq += nb
+        outs = []
+        for k in range(4):
+            outs.append(gold["outs"][p_out:p_out + int(lens[1 + k])])
+            p_out += int(lens[1 + k])
+        res, sch, uci = ctx.ulsch_demux(np.array([cw_desc(cfg)]), llr, seq_packed)
+        check_streams(res[0], sch, uci, cw_desc(cfg), outs)
+
+
+def source_index_of_sch(orc, cfg, n):
+    """For every UL-SCH output soft bit, the input soft bit it comes from (-1 = punctured), found by pushing the digits
+    of the input index through the oracle demultiplexer."""
+    idx = np.arange(n)
+    src = np.zeros(0, np.int64)
+    digits = []
+    for k in range(4):
+        d = ((idx >> (6 * k)) & 63).astype(np.int8) + 1  # 1..64, never 0 (punctured elements read 0)
+        rc, outs = orc.ulsch_demux(cfg, d, np.zeros(n, np.uint8))
+        assert rc == 0
+        digits.append(outs[0].astype(np.int64))
+    punct = digits[0] == 0
+    src = sum((dg - 1) << (6 * k) for k, dg in enumerate(digits))
+    src[punct] = -1
+    return src
+
+
+@pytest.mark.parametrize("ack_bits", [0, 2, 7])
+def test_front_end_feeds_the_decoder(ctx, orc, ack_bits):
+    """pdc_submit_codewords + pdc_submit(llrs = NULL): a 4-layer 256QAM slot with HARQ-ACK (punctured or rate matched
+    around) and CSI Part 1 multiplexed in, scrambled; the transport block must come out of the device chain and every
+    stream must equal the oracle's."""
+    rng = np.random.default_rng(40 + ack_bits)
+    qm, nl, nprb = 8, 4, 60
+    cfg = dict(qm=qm, nof_layers=nl, nof_prb=nprb, start_symbol_index=0, nof_symbols=14, dmrs_type=1,
+               dmrs_symbol_mask=1 << 2, nof_cdm_groups_without_data=2, nof_harq_ack_bits=ack_bits,
+               nof_enc_harq_ack_bits=(40 * qm * nl if ack_bits else 0),
+               nof_harq_ack_rvd=(60 * qm * nl if ack_bits <= 2 else 0), nof_csi_part1_bits=11,
+               nof_enc_csi_part1_bits=90 * qm * nl)
+    n = orc.ulsch_codeword_length(cfg)
+    src = source_index_of_sch(orc, cfg, n)
+    n_sch = src.size
+    tbs_bits = int(n_sch * 0.8) // 8 * 8
+    C = ldpc.compute_nof_codeblocks(tbs_bits, 1)
+    nref = ldpc.compute_N_ref(tbs_bits // 8, C)
+    tb = rng.integers(0, 256, tbs_bits // 8).astype(np.uint8)
+    sch_llr, _ = make_tb_llrs(orc, tb, 1, 0, qm, nref, nl, n_sch, 9.5, rng)
+    llr = rng.integers(-100, 101, n).astype(np.int8)  # UCI elements carry arbitrary soft bits
+    llr[src[src >= 0]] = sch_llr[src >= 0]
+    c_init = 0x4601 * 32768 + 77
+    seq = orc.prg_bits(c_init, 0, n)
+    rc, outs = orc.ulsch_demux(cfg, llr, seq)
+    assert rc == 0 and outs[0].size == n_sch
+    raw = capi.PinnedBuffer(n)
+    raw.array[:] = orc.revert_scrambling(llr, seq)
+
+    metas = ldpc.segment_rx(tbs_bits, 1, 0, qm, nref, nl, n_sch)
+    cbs = np.zeros(C, capi.CB_DESC_DTYPE)
+    flags = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA | capi.CB_EARLY_STOP
+    for k, m in enumerate(metas):
+        cbs[k] = (m.cw_offset, m.rm_length, 100 + k, nref, m.lifting_size, m.nof_filler_bits, 1, qm, 0, capi.CRC24B, 6,
+                  flags, 0)
+    tbd = np.zeros(1, capi.TB_DESC_DTYPE)
+    tbd[0] = (0, C, tbs_bits, 0, 0)
+    d = cw_desc(cfg, c_init=c_init, flags=capi.CW_SCRAMBLED)
+    ctx.submit_codewords(np.array([d]), raw.array, stream=0)
+    ctx.submit(cbs, None, tbd, stream=0)
+    out = ctx.wait(0)
+    fe = out["codewords"]
+    want_uci = np.concatenate(outs[1:])
+    assert int(fe["cw_results"][0]["n_sch"]) == n_sch
+    assert (fe["uci"][:want_uci.size] == want_uci).all()
+    # the decoder saw exactly the oracle's UL-SCH stream: same codeblock results as decoding that stream directly
+    ctx.submit(cbs, outs[0], tbd, stream=1)
+    direct = ctx.wait(1)
+    assert (out["cb_results"] == direct["cb_results"]).all()
+    assert (out["cb_bits"] == direct["cb_bits"]).all()
+    assert out["tb_results"][0]["tb_crc_ok"] == 1
+    assert (out["tb_bytes"][:tbs_bits // 8] == tb).all()

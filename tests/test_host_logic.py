@@ -103,3 +103,60 @@ def test_sharding_is_a_sticky_partition():
         parts = [sharding.shard_transport_blocks(tbs, world, r) for r in range(world)]
         assert sorted(i for p in parts for i in p) == list(range(len(tbs)))
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 5  # 16 cells -> 2 per GPU at 8
+
+
+# ---- host-side plan of the UL-SCH demultiplexing (csrc/ulsch_plan.h) -------------------------------------------------
+
+def _plan_check_lib():
+    """tests/host/ulsch_plan_check.cpp: the plan executed on the CPU with the index arithmetic of the device gathers."""
+    import ctypes
+    import subprocess
+    from pathlib import Path
+    here = Path(__file__).resolve().parent
+    out = here / "_build" / "libulsch_plan_check.so"
+    src = here / "host" / "ulsch_plan_check.cpp"
+    hdr = here.parent / "srsran_edgeric_5g_b200" / "csrc" / "ulsch_plan.h"
+    if not out.exists() or out.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+        out.parent.mkdir(exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(out), str(src)], check=True)
+    return ctypes.CDLL(str(out))
+
+
+def test_ulsch_plan_matches_oracle(orc):
+    import ctypes
+    from srsran_edgeric_5g_b200 import capi
+    from oracle import pyoracle as po
+    from tests.vectors import ulsch_case
+    L = _plan_check_lib()
+    rng = np.random.default_rng(8)
+    vp = ctypes.c_void_p
+    for _ in range(400):
+        cfg, llr, seq, outs = ulsch_case(orc, rng)
+        d = np.zeros(1, capi.CW_DESC_DTYPE)
+        for k in po.ULSCH_CFG_FIELDS:
+            d[0][k] = cfg.get(k, 0)
+        sch, uci, n = np.zeros(llr.size, np.int8), np.zeros(llr.size, np.int8), np.zeros(4, np.uint32)
+        rc = L.plan_demux_cpu(d.ctypes.data_as(vp), llr.ctypes.data_as(vp), seq.ctypes.data_as(vp), sch.ctypes.data_as(vp),
+                              uci.ctypes.data_as(vp), n.ctypes.data_as(vp))
+        assert rc == 0 and list(n) == [o.size for o in outs], cfg
+        want = np.concatenate(outs[1:])
+        assert (sch[:n[0]] == outs[0]).all() and (uci[:want.size] == want).all(), cfg
+
+
+def test_ulsch_plan_rejects_inconsistent_descriptions():
+    import ctypes
+    from srsran_edgeric_5g_b200 import capi
+    L = _plan_check_lib()
+    d = np.zeros(1, capi.CW_DESC_DTYPE)
+    d[0]["qm"], d[0]["nof_layers"], d[0]["nof_prb"], d[0]["nof_symbols"], d[0]["dmrs_type"] = 2, 1, 4, 14, 1
+    d[0]["nof_cdm_groups_without_data"] = 2
+    buf = np.zeros(4096, np.int8)
+    n = np.zeros(4, np.uint32)
+    vp = ctypes.c_void_p
+    args = [buf.ctypes.data_as(vp)] * 4 + [n.ctypes.data_as(vp)]
+    assert L.plan_demux_cpu(d.ctypes.data_as(vp), *args) == -1            # no DM-RS symbol
+    d[0]["dmrs_symbol_mask"] = 1 << 2
+    d[0]["nof_harq_ack_bits"], d[0]["nof_enc_harq_ack_bits"] = 4, 1 << 20  # HARQ-ACK that cannot fit
+    assert L.plan_demux_cpu(d.ctypes.data_as(vp), *args) == -1
+    d[0]["qm"] = 3                                                          # not a modulation order
+    assert L.plan_demux_cpu(d.ctypes.data_as(vp), *args) == -1
