@@ -302,6 +302,24 @@ int pdc_rate_dematch(pdc_ctx*      ctx,
 
 /* crc_calculator::calculate over the first nbits (MSB first) of packed[]. */
 /*
+ * The front end on buffers that are already on the device (descriptors on the host: the plan is made there), queued on
+ * the caller's CUDA stream: d_raw_llrs -> d_sch (UL-SCH space, feed it to pdc_launch_device as d_llrs) and d_uci
+ * (may be NULL when no codeword carries UCI). One call at a time per context: the plan buffers are shared with the
+ * synchronous calls below.
+ */
+int pdc_launch_codewords_device(pdc_ctx*           ctx,
+                                const pdc_cw_desc* cws,
+                                uint32_t           n_cw,
+                                const void*        d_raw_llrs,
+                                size_t             n_raw,
+                                void*              d_sch,
+                                size_t             sch_capacity,
+                                void*              d_uci,
+                                size_t             uci_capacity,
+                                pdc_cw_result*     results,
+                                void*              cuda_stream);
+
+/*
  * ulsch_demultiplex::demultiplex for n_cw codewords, synchronous, host buffers. seq_bits: the scrambling sequence of
  * the input, packed MSB first and indexed like llrs (bit in_offset + i belongs to soft bit i of the codeword), as
  * pusch_codeword_buffer::on_new_block receives it; NULL = generated on the device from c_init. sch_out receives the

@@ -70,7 +70,8 @@ assert TB_DESC_DTYPE.itemsize == ctypes.sizeof(TbDesc) == 20
 EXPORTS = ["pdc_default_config", "pdc_create", "pdc_destroy", "pdc_last_error", "pdc_device_info", "pdc_launch_count",
            "pdc_measure_int_peak", "pdc_host_alloc", "pdc_host_free", "pdc_submit", "pdc_wait", "pdc_poll", "pdc_launch_device",
            "pdc_harq_read", "pdc_harq_write", "pdc_harq_free", "pdc_harq_device_ptr", "pdc_ldpc_decode",
-           "pdc_rate_dematch", "pdc_crc", "pdc_submit_codewords", "pdc_ulsch_demux", "pdc_scrambling_sequence"]
+           "pdc_rate_dematch", "pdc_crc", "pdc_submit_codewords", "pdc_ulsch_demux", "pdc_scrambling_sequence",
+           "pdc_launch_codewords_device"]
 
 _lib = None
 
@@ -124,6 +125,8 @@ def load():
     L.pdc_ulsch_demux.argtypes = [_vp, _vp, _u32, _vp, ctypes.c_size_t, _vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t,
                                   _vp]
     L.pdc_scrambling_sequence.argtypes = [_vp, _u32, _u32, _u32, _vp]
+    L.pdc_launch_codewords_device.argtypes = [_vp, _vp, _u32, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp,
+                                              ctypes.c_size_t, _vp, _vp]
     _lib = L
     return L
 
@@ -257,6 +260,14 @@ class Context:
         fe = {"cws": cws, "raw_llrs": raw_llrs, "cw_results": res, "uci": uci}
         self._pending_fe[stream] = fe
         return fe
+
+    def launch_codewords_device(self, cws, d_raw, n_raw, d_sch, sch_capacity, d_uci=0, uci_capacity=0, cuda_stream=0):
+        """pdc_launch_codewords_device: the front end on device buffers, queued on the caller's stream."""
+        cws = np.ascontiguousarray(cws, CW_DESC_DTYPE)
+        res = np.zeros(cws.size, CW_RESULT_DTYPE)
+        check(self._L.pdc_launch_codewords_device(self.h, _ptr(cws), cws.size, d_raw, n_raw, d_sch, sch_capacity,
+                                                  d_uci or None, uci_capacity, _ptr(res), cuda_stream or None))
+        return res
 
     def ulsch_demux(self, cws, llrs, seq_bits_packed=None, sch_capacity=None, uci_capacity=None):
         """pdc_ulsch_demux (synchronous). Returns (cw_results, sch, uci)."""

@@ -50,8 +50,14 @@ struct FrontEnd {
   int8_t*              h_uci = nullptr;
   size_t               uci_cap = 0;
   unsigned char*       d_plan = nullptr;
-  unsigned char*       h_plan = nullptr;
   size_t               plan_cap = 0;
+  // The plan is staged in a ring of pinned buffers: a slot is reused once its upload (an event) has completed, so
+  // back-to-back launches on one stream do not overwrite a plan that is still waiting to be copied.
+  static constexpr int RING = 4;
+  unsigned char*       h_plan[RING]   = {nullptr, nullptr, nullptr, nullptr};
+  size_t               h_plan_cap[RING] = {0, 0, 0, 0};
+  cudaEvent_t          plan_ev[RING]  = {nullptr, nullptr, nullptr, nullptr};
+  int                  ring_pos = 0;
   // Pending results of the queue.
   int8_t*              u_uci = nullptr;
   size_t               uci_bytes = 0;
@@ -445,7 +451,12 @@ static void free_front_end(FrontEnd& fe)
   cudaFree(fe.d_uci);
   cudaFree(fe.d_plan);
   cudaFreeHost(fe.h_uci);
-  cudaFreeHost(fe.h_plan);
+  for (int k = 0; k != FrontEnd::RING; ++k) {
+    cudaFreeHost(fe.h_plan[k]);
+    if (fe.plan_ev[k]) {
+      cudaEventDestroy(fe.plan_ev[k]);
+    }
+  }
   fe = FrontEnd();
 }
 
@@ -648,7 +659,8 @@ static int front_end_launch(pdc_ctx*           ctx,
                             size_t             uci_capacity,
                             const uint8_t*     seq_bits_packed,
                             pdc_cw_result*     results,
-                            cudaStream_t       s)
+                            cudaStream_t       s,
+                            int8_t*            d_uci_user = nullptr)
 {
   pdc::UlschPlan& plan = fe.plan;
   plan.clear();
@@ -676,18 +688,29 @@ static int front_end_launch(pdc_ctx*           ctx,
   const size_t b_syms = plan.syms.size() * sizeof(pdc::UlschSymbol);
   const size_t b_list = ((plan.lists.size() * sizeof(uint16_t)) + 15) & ~(size_t)15;
   const size_t bytes  = b_cws + b_syms + b_list;
-  if (bytes > fe.plan_cap) {
-    cudaFreeHost(fe.h_plan);
-    fe.h_plan = nullptr;
-    PDC_CUDA(grow_device(&fe.d_plan, &fe.plan_cap, bytes));
-    PDC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&fe.h_plan), fe.plan_cap));
+  PDC_CUDA(grow_device(&fe.d_plan, &fe.plan_cap, bytes));
+  const int slot = fe.ring_pos;
+  fe.ring_pos    = (fe.ring_pos + 1) % FrontEnd::RING;
+  if (fe.plan_ev[slot] == nullptr) {
+    PDC_CUDA(cudaEventCreateWithFlags(&fe.plan_ev[slot], cudaEventDisableTiming));
+  } else {
+    PDC_CUDA(cudaEventSynchronize(fe.plan_ev[slot]));
   }
-  memcpy(fe.h_plan, plan.cws.data(), b_cws);
-  memcpy(fe.h_plan + b_cws, plan.syms.data(), b_syms);
-  memcpy(fe.h_plan + b_cws + b_syms, plan.lists.data(), plan.lists.size() * sizeof(uint16_t));
-  PDC_CUDA(cudaMemcpyAsync(fe.d_plan, fe.h_plan, bytes, cudaMemcpyHostToDevice, s));
-  PDC_CUDA(grow_device(&fe.d_seq, &fe.seq_cap, (size_t)plan.seq_words + 8));
-  if (uci_end > fe.uci_cap) {
+  if (bytes > fe.h_plan_cap[slot]) {
+    cudaFreeHost(fe.h_plan[slot]);
+    fe.h_plan[slot]     = nullptr;
+    fe.h_plan_cap[slot] = 0;
+    PDC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&fe.h_plan[slot]), bytes + bytes / 4 + 64));
+    fe.h_plan_cap[slot] = bytes + bytes / 4 + 64;
+  }
+  unsigned char* h_plan = fe.h_plan[slot];
+  memcpy(h_plan, plan.cws.data(), b_cws);
+  memcpy(h_plan + b_cws, plan.syms.data(), b_syms);
+  memcpy(h_plan + b_cws + b_syms, plan.lists.data(), plan.lists.size() * sizeof(uint16_t));
+  PDC_CUDA(cudaMemcpyAsync(fe.d_plan, h_plan, bytes, cudaMemcpyHostToDevice, s));
+  PDC_CUDA(cudaEventRecord(fe.plan_ev[slot], s));
+  PDC_CUDA(grow_device(&fe.d_seq, &fe.seq_cap, (size_t)plan.seq_words + 2 * pdc::PRG_WORDS_PER_THREAD));
+  if (d_uci_user == nullptr && uci_end > fe.uci_cap) {
     cudaFreeHost(fe.h_uci);
     fe.h_uci = nullptr;
     PDC_CUDA(grow_device(&fe.d_uci, &fe.uci_cap, uci_end));
@@ -700,7 +723,7 @@ static int front_end_launch(pdc_ctx*           ctx,
   a.seq   = fe.d_seq;
   a.in    = d_in;
   a.sch   = d_sch;
-  a.uci   = fe.d_uci;
+  a.uci   = d_uci_user ? d_uci_user : fe.d_uci;
   uint32_t max_in = 0, max_sch = 0, max_uci = 0;
   for (const pdc::UlschCodeword& cw : plan.cws) {
     max_in  = std::max(max_in, cw.n_in);
@@ -709,7 +732,7 @@ static int front_end_launch(pdc_ctx*           ctx,
   }
   if (seq_bits_packed != nullptr) {
     // Caller-supplied sequence (MSB-first bit string indexed like the input): repack per codeword, element k in bit k.
-    std::vector<uint32_t> words(plan.seq_words + 8, 0u);
+    std::vector<uint32_t> words(plan.seq_words + 2 * pdc::PRG_WORDS_PER_THREAD, 0u);
     for (const pdc::UlschCodeword& cw : plan.cws) {
       for (uint32_t i = 0; i != cw.n_in; ++i) {
         const size_t b = (size_t)cw.in_off + i;
@@ -729,8 +752,8 @@ static int front_end_launch(pdc_ctx*           ctx,
   }
   {
     // Enough CTAs to fill the GPU a few times over; each thread steps through the words of its codeword.
-    const uint32_t words = (max_sch + 3) / 4;
-    uint32_t       gx    = std::max(1u, std::min((words + 255) / 256, (uint32_t)(8 * ctx->sm_count + n_cw - 1) / n_cw));
+    const uint32_t chunks = (max_sch + 15) / 16;
+    uint32_t       gx = std::max(1u, std::min((chunks + 255) / 256, (uint32_t)(8 * ctx->sm_count + n_cw - 1) / n_cw));
     pdc::ulsch_sch_kernel<<<dim3(gx, n_cw), 256, 0, s>>>(a);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -1064,6 +1087,27 @@ int pdc_measure_int_peak(pdc_ctx* ctx, int mode, double* lane_ops_per_s)
 }
 
 
+int pdc_launch_codewords_device(pdc_ctx*           ctx,
+                                const pdc_cw_desc* cws,
+                                uint32_t           n_cw,
+                                const void*        d_raw_llrs,
+                                size_t             n_raw,
+                                void*              d_sch,
+                                size_t             sch_capacity,
+                                void*              d_uci,
+                                size_t             uci_capacity,
+                                pdc_cw_result*     results,
+                                void*              cuda_stream)
+{
+  if (!ctx || !cws || n_cw == 0 || n_cw > 65535u || !d_raw_llrs || !d_sch || !results) {
+    return fail(PDC_ERR_INVALID, "pdc_launch_codewords_device: invalid argument");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  return front_end_launch(ctx, ctx->fe_sync, cws, n_cw, n_raw, static_cast<const int8_t*>(d_raw_llrs),
+                          static_cast<int8_t*>(d_sch), sch_capacity, d_uci ? uci_capacity : (size_t)-1, nullptr, results,
+                          static_cast<cudaStream_t>(cuda_stream), d_uci ? static_cast<int8_t*>(d_uci) : nullptr);
+}
+
 int pdc_ulsch_demux(pdc_ctx*           ctx,
                     const pdc_cw_desc* cws,
                     uint32_t           n_cw,
@@ -1116,7 +1160,7 @@ int pdc_scrambling_sequence(pdc_ctx* ctx, uint32_t c_init, uint32_t offset, uint
   cw.c_init             = c_init;
   cw.n_in               = n;
   cw.prg_offset         = offset;
-  const uint32_t n_words = (n + 31) / 32 + 8;
+  const uint32_t n_words = (n + 31) / 32 + 2 * pdc::PRG_WORDS_PER_THREAD;
   PDC_CUDA(grow_device(&fe.d_seq, &fe.seq_cap, (size_t)n_words));
   PDC_CUDA(grow_device(&fe.d_plan, &fe.plan_cap, sizeof(cw)));
   PDC_CUDA(cudaMemcpyAsync(fe.d_plan, &cw, sizeof(cw), cudaMemcpyHostToDevice, nullptr));

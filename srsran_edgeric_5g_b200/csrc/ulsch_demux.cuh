@@ -23,7 +23,7 @@ namespace pdc {
 constexpr uint32_t PRG_NC    = 1600;
 constexpr uint32_t PRG_TAPS1 = 0x9u; // x1: x^31 + x^3 + 1
 constexpr uint32_t PRG_TAPS2 = 0xfu; // x2: x^31 + x^3 + x^2 + x + 1
-constexpr int      PRG_WORDS_PER_THREAD = 4;
+constexpr int      PRG_WORDS_PER_THREAD = 16;
 
 // x^(c * 128^level) mod g of both generators, c < 128, level < 3 (sequence positions below 2^21).
 __device__ uint32_t g_prg_jump[2][3][128];
@@ -112,12 +112,6 @@ __global__ void __launch_bounds__(128) prg_kernel(const UlschCodeword* __restric
   }
 }
 
-// Four scrambling bits starting at element i of the codeword (bit k of the result = element i + k).
-__device__ __forceinline__ uint32_t seq_bits4(const uint32_t* __restrict__ seq, uint32_t i)
-{
-  const uint32_t* w = seq + (i >> 5);
-  return __funnelshift_r(__ldg(w), __ldg(w + 1), i & 31u) & 0xfu;
-}
 __device__ __forceinline__ uint32_t seq_bit(const uint32_t* __restrict__ seq, uint32_t i)
 {
   return (__ldg(seq + (i >> 5)) >> (i & 31u)) & 1u;
@@ -130,16 +124,6 @@ __device__ __forceinline__ uint32_t negate4(uint32_t v, uint32_t bits)
   const uint32_t m   = one * 0xffu;
   const uint32_t t   = v ^ m;
   return ((t & 0x7f7f7f7fu) + one) ^ (t & 0x80808080u);
-}
-
-__device__ __forceinline__ uint32_t ldg_u32_unaligned(const int8_t* p)
-{
-  const uintptr_t a  = reinterpret_cast<uintptr_t>(p);
-  const uint32_t* w  = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  const uint32_t  sh = (uint32_t)(a & 3u) * 8u;
-  const uint32_t  lo = __ldg(w);
-  const uint32_t  hi = sh ? __ldg(w + 1) : 0u;
-  return __funnelshift_r(lo, hi, sh);
 }
 
 struct UlschArgs {
@@ -190,6 +174,31 @@ __device__ __forceinline__ int ulsch_sch_byte(const UlschArgs& a, const UlschCod
   return v;
 }
 
+// Sixteen scrambling bits starting at element i of the codeword.
+__device__ __forceinline__ uint32_t seq_bits16(const uint32_t* __restrict__ seq, uint32_t i)
+{
+  const uint32_t* w = seq + (i >> 5);
+  return __funnelshift_r(__ldg(w), __ldg(w + 1), i & 31u) & 0xffffu;
+}
+
+// Sixteen input bytes from any address: one 128-bit load when aligned, else five aligned words and funnel shifts.
+__device__ __forceinline__ uint4 ldg_u128_unaligned(const int8_t* p)
+{
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  if ((a & 15u) == 0) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+  }
+  const uint32_t* w  = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t  sh = (uint32_t)(a & 3u) * 8u;
+  const uint32_t  w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+  const uint32_t  w4 = sh ? __ldg(w + 4) : 0u;
+  return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                    __funnelshift_r(w3, w4, sh));
+}
+
+// UL-SCH stream: every thread step produces sixteen consecutive output soft bits (one 128-bit store) when they come
+// from sixteen consecutive inputs of one symbol; runs that touch a symbol with UCI or a symbol boundary go soft bit by
+// soft bit.
 __global__ void __launch_bounds__(256) ulsch_sch_kernel(UlschArgs a)
 {
   __shared__ UlschCodeword cw;
@@ -203,25 +212,29 @@ __global__ void __launch_bounds__(256) ulsch_sch_kernel(UlschArgs a)
   }
   __syncthreads();
   const uint32_t  n_sch     = cw.n_out[0];
-  const uint32_t  n_words   = (n_sch + 3u) / 4u;
+  const uint32_t  n_chunks  = (n_sch + 15u) / 16u;
   const bool      scrambled = (cw.flags & PDC_CW_SCRAMBLED) != 0;
   const uint32_t* seq       = a.seq + cw.seq_word_off;
   int8_t*         out       = a.sch + cw.sch_off;
-  // Consecutive threads take consecutive words; the symbol of a word rarely changes from one step to the next.
-  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
-    const uint32_t     o   = 4u * w;
+  const bool      out_al16  = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
+    const uint32_t     o   = 16u * c;
     const int          s   = ulsch_find_symbol(S, (int)cw.n_sym, 0, o, cw.bpre);
     const UlschSymbol& sym = S[s];
     const uint32_t     rel = o - sym.out_off[0];
-    if (sym.list_off[0] == ULSCH_IDENTITY && rel + 4u <= sym.n_out_re[0] * cw.bpre && o + 4u <= n_sch) {
+    if (out_al16 && sym.list_off[0] == ULSCH_IDENTITY && rel + 16u <= sym.n_out_re[0] * cw.bpre && o + 16u <= n_sch) {
       const uint32_t i = sym.in_off + rel;
-      uint32_t       v = ldg_u32_unaligned(a.in + cw.in_off + i);
+      uint4          v = ldg_u128_unaligned(a.in + cw.in_off + i);
       if (scrambled) {
-        v = negate4(v, seq_bits4(seq, i));
+        const uint32_t bits = seq_bits16(seq, i);
+        v.x                 = negate4(v.x, bits & 0xfu);
+        v.y                 = negate4(v.y, (bits >> 4) & 0xfu);
+        v.z                 = negate4(v.z, (bits >> 8) & 0xfu);
+        v.w                 = negate4(v.w, bits >> 12);
       }
-      *reinterpret_cast<uint32_t*>(out + o) = v;
+      *reinterpret_cast<uint4*>(out + o) = v;
     } else {
-      for (uint32_t b = 0; b != 4u && o + b < n_sch; ++b) {
+      for (uint32_t b = 0; b != 16u && o + b < n_sch; ++b) {
         out[o + b] = (int8_t)ulsch_sch_byte(a, cw, S, o + b);
       }
     }

@@ -165,6 +165,25 @@ inline bool ulsch_plan_codeword(const pdc_cw_desc& d, UlschPlan& plan)
     if (n_re == 0) {
       continue;
     }
+    // Once every UCI stream has been placed, the remaining symbols are plain UL-SCH (the reserved elements alone do
+    // not change any stream): no element sets needed.
+    const bool ack_left  = m_ack < d.nof_enc_harq_ack_bits;
+    const bool csi1_left = m_csi1 < d.nof_enc_csi_part1_bits;
+    const bool csi2_left = csi2_open ? (m_csi2 < csi2_enc) : (csi1_left && d.nof_enc_csi_part2_bits != 0);
+    if (!ack_left && !csi1_left && !csi2_left) {
+      UlschSymbol s = {};
+      s.in_off      = in_pos;
+      s.n_re        = (uint32_t)n_re;
+      for (int k = 0; k != ULSCH_STREAMS; ++k) {
+        s.out_off[k]  = out_pos[k];
+        s.list_off[k] = ULSCH_IDENTITY;
+      }
+      s.n_out_re[0] = (uint32_t)n_re;
+      out_pos[0] += (uint32_t)(n_re * bpre);
+      plan.syms.push_back(s);
+      in_pos += (uint32_t)(n_re * bpre);
+      continue;
+    }
     ulsch.assign((size_t)n_re, 1);
     uci.assign((size_t)n_re, dmrs ? 0 : 1);
     rvd.assign((size_t)n_re, 0);
@@ -306,7 +325,7 @@ inline bool ulsch_plan_codeword(const pdc_cw_desc& d, UlschPlan& plan)
     }
   }
   cw.seq_word_off = plan.seq_words;
-  plan.seq_words += (in_pos + 31) / 32 + 4; // generated four words at a time
+  plan.seq_words += (in_pos + 31) / 32 + 16; // generated sixteen words at a time
   plan.seq_words = (plan.seq_words + 3) & ~3u;
   plan.cws.push_back(cw);
   return true;
