@@ -1,4 +1,8 @@
 #include "pusch_dec_cuda_adapters.h"
+#include "srsran/ran/dmrs.h"
+#include "srsran/ran/pusch/pusch_constants.h"
+#include "srsran/support/srsran_assert.h"
+#include <algorithm>
 #include "srsran/ran/sch/modulation_scheme.h"
 #include "srsran/support/error_handling.h"
 #include "srsran/support/srsran_assert.h"
@@ -315,4 +319,126 @@ std::shared_ptr<hal::hw_accelerator_pusch_dec_factory>
 srsran::cuda::create_hw_accelerator_pusch_dec_factory_cuda(std::shared_ptr<context> ctx)
 {
   return ctx ? std::make_shared<hw_accelerator_pusch_dec_factory_cuda>(std::move(ctx)) : nullptr;
+}
+
+// ---- ulsch_demultiplex_cuda ---------------------------------------------------------------------------------------------
+
+pusch_codeword_buffer& ulsch_demultiplex_cuda::demultiplex(pusch_decoder_buffer& sch_data,
+                                                           pusch_decoder_buffer& harq_ack,
+                                                           pusch_decoder_buffer& csi_part1,
+                                                           const configuration&  config)
+{
+  cfg       = config;
+  sch       = &sch_data;
+  ack       = (config.nof_harq_ack_bits != 0) ? &harq_ack : nullptr;
+  csi1      = (config.nof_csi_part1_bits != 0) ? &csi_part1 : nullptr;
+  csi2      = nullptr;
+  csi2_bits = csi2_enc = 0;
+  count     = 0;
+  // Size of the codeword: every OFDM symbol of the allocation (ulsch_demultiplex_impl.cpp:371-382).
+  const unsigned bpre    = get_bits_per_symbol(cfg.modulation) * cfg.nof_layers;
+  const unsigned re_dmrs = (NRE - cfg.nof_cdm_groups_without_data * (cfg.dmrs == dmrs_type::TYPE1 ? 6 : 4)) * cfg.nof_prb;
+  size_t         total   = 0;
+  for (unsigned l = cfg.start_symbol_index; l != cfg.start_symbol_index + cfg.nof_symbols; ++l) {
+    total += (cfg.dmrs_symbol_mask.test(l) ? re_dmrs : NRE * cfg.nof_prb) * bpre;
+  }
+  codeword.resize(total);
+  seq.assign((total + 7) / 8, 0);
+  return *this;
+}
+
+void ulsch_demultiplex_cuda::set_csi_part2(pusch_decoder_buffer& csi_part2, unsigned nof_bits, unsigned nof_enc_bits)
+{
+  csi2      = &csi_part2;
+  csi2_bits = nof_bits;
+  csi2_enc  = nof_enc_bits;
+}
+
+span<log_likelihood_ratio> ulsch_demultiplex_cuda::get_next_block_view(unsigned block_size)
+{
+  block_size = static_cast<unsigned>(std::min<size_t>(block_size, codeword.size() - count));
+  return span<log_likelihood_ratio>(codeword).subspan(count, block_size);
+}
+
+void ulsch_demultiplex_cuda::on_new_block(span<const log_likelihood_ratio> data, const bit_buffer& scrambling_seq)
+{
+  srsran_assert(count + data.size() <= codeword.size(), "More soft bits than the allocation holds.");
+  if (data.data() != codeword.data() + count) {
+    std::copy(data.begin(), data.end(), codeword.begin() + count);
+  }
+  // Append the scrambling sequence at bit position `count` (MSB first).
+  for (size_t i = 0, n = data.size(); i != n;) {
+    const size_t   pos  = count + i;
+    const unsigned room = 8 - static_cast<unsigned>(pos & 7);
+    const unsigned take = static_cast<unsigned>(std::min<size_t>(room, n - i));
+    const unsigned bits = scrambling_seq.extract(i, take); // first bit in the most significant position
+    seq[pos >> 3] |= static_cast<uint8_t>(bits << (room - take));
+    i += take;
+  }
+  count += data.size();
+}
+
+bool ulsch_demultiplex_cuda::run(pdc_cw_result& res)
+{
+  pdc_cw_desc d                 = {};
+  d.qm                          = get_bits_per_symbol(cfg.modulation);
+  d.nof_layers                  = cfg.nof_layers;
+  d.start_symbol_index          = cfg.start_symbol_index;
+  d.nof_symbols                 = cfg.nof_symbols;
+  d.dmrs_type                   = (cfg.dmrs == dmrs_type::TYPE1) ? 1 : 2;
+  d.nof_cdm_groups_without_data = cfg.nof_cdm_groups_without_data;
+  d.nof_prb                     = cfg.nof_prb;
+  for (unsigned l = 0; l != 14; ++l) {
+    if (l < cfg.dmrs_symbol_mask.size() && cfg.dmrs_symbol_mask.test(l)) {
+      d.dmrs_symbol_mask |= static_cast<uint16_t>(1u << l);
+    }
+  }
+  d.nof_harq_ack_rvd       = cfg.nof_harq_ack_rvd;
+  d.nof_harq_ack_bits      = cfg.nof_harq_ack_bits;
+  d.nof_enc_harq_ack_bits  = cfg.nof_enc_harq_ack_bits;
+  d.nof_csi_part1_bits     = cfg.nof_csi_part1_bits;
+  d.nof_enc_csi_part1_bits = cfg.nof_enc_csi_part1_bits;
+  d.nof_csi_part2_bits     = csi2_bits;
+  d.nof_enc_csi_part2_bits = csi2_enc;
+  out_sch.resize(codeword.size() + 16);
+  out_uci.resize(codeword.size() + 16);
+  return pdc_ulsch_demux(ctx->get(), &d, 1, reinterpret_cast<const int8_t*>(codeword.data()), codeword.size(),
+                         seq.data(), out_sch.data(), out_sch.size(), out_uci.data(), out_uci.size(), &res) == PDC_OK;
+}
+
+void ulsch_demultiplex_cuda::on_end_codeword()
+{
+  auto deliver = [](pusch_decoder_buffer* b, const int8_t* p, size_t n) {
+    if (b != nullptr && n != 0) {
+      b->on_new_softbits(span<const log_likelihood_ratio>(reinterpret_cast<const log_likelihood_ratio*>(p), n));
+    }
+  };
+  pdc_cw_result res = {};
+  bool          ok  = run(res);
+  srsran_assert(ok, "UL-SCH demultiplexing failed: {}", pdc_last_error());
+  if (ack != nullptr) {
+    deliver(ack, out_uci.data(), res.n_harq_ack);
+    ack->on_end_softbits();
+  }
+  if (csi1 != nullptr) {
+    deliver(csi1, out_uci.data() + res.n_harq_ack, res.n_csi_part1);
+    csi1->on_end_softbits(); // the CSI Part 1 decoder may answer with set_csi_part2
+  }
+  if (csi2 != nullptr && csi2_enc != 0) {
+    ok = run(res); // same HARQ-ACK and CSI Part 1; CSI Part 2 taken out of the UL-SCH elements
+    srsran_assert(ok, "UL-SCH demultiplexing failed: {}", pdc_last_error());
+    deliver(csi2, out_uci.data() + res.n_harq_ack + res.n_csi_part1, res.n_csi_part2);
+    csi2->on_end_softbits();
+  }
+  deliver(sch, out_sch.data(), res.n_sch);
+  sch->on_end_softbits();
+  sch = ack = csi1 = csi2 = nullptr;
+}
+
+std::unique_ptr<ulsch_demultiplex> srsran::cuda::create_ulsch_demultiplex_cuda(std::shared_ptr<context> ctx)
+{
+  if (!ctx) {
+    return nullptr;
+  }
+  return std::make_unique<ulsch_demultiplex_cuda>(std::move(ctx));
 }

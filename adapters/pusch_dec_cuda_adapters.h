@@ -8,6 +8,9 @@
 ///   hw_accelerator_pusch_dec_cuda : srsran::hal::hw_accelerator_pusch_dec
 ///                                   (hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec.h:83-115),
 ///                                   driven unchanged by pusch_decoder_hw_impl (pusch_decoder_hw_impl.cpp:132-342).
+///   ulsch_demultiplex_cuda        : srsran::ulsch_demultiplex + pusch_codeword_buffer
+///                                   (phy/upper/channel_processors/pusch/ulsch_demultiplex.h:41-103,
+///                                   pusch_codeword_buffer.h), the step that feeds pusch_decoder_buffer::on_new_softbits.
 /// and the factories a "cuda" branch of create_ldpc_decoder_factory_sw / create_ldpc_rate_dematcher_factory_sw /
 /// create_crc_calculator_factory_sw / create_hw_accelerator_pusch_dec_factory returns.
 #pragma once
@@ -16,6 +19,9 @@
 #include "srsran/hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec.h"
 #include "srsran/hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec_factory.h"
 #include "srsran/phy/upper/channel_coding/channel_coding_factories.h"
+#include "srsran/phy/upper/channel_processors/pusch/pusch_codeword_buffer.h"
+#include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_buffer.h"
+#include "srsran/phy/upper/channel_processors/pusch/ulsch_demultiplex.h"
 #include <memory>
 #include <vector>
 
@@ -123,11 +129,50 @@ private:
   bool                       submitted = false;
 };
 
+/// \brief UL-SCH demultiplexer in the ulsch_demultiplex slot (created per PUSCH processor, like ulsch_demultiplex_impl).
+///
+/// The demodulator writes the descrambled soft bits of the whole codeword into the staging buffer this object hands out
+/// (get_next_block_view never limits a block to the current OFDM symbol) and passes the scrambling sequence of every
+/// block; on_end_codeword runs the demultiplexing of the whole codeword on the GPU (pdc_ulsch_demux) and feeds the four
+/// decoder buffers. CSI Part 2: the CSI Part 1 buffer is completed first; if its decoder answers with set_csi_part2 the
+/// codeword is demultiplexed a second time with the CSI Part 2 sizes (HARQ-ACK and CSI Part 1 do not depend on them).
+class ulsch_demultiplex_cuda : public ulsch_demultiplex, private pusch_codeword_buffer
+{
+public:
+  explicit ulsch_demultiplex_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  void set_csi_part2(pusch_decoder_buffer& csi_part2, unsigned nof_csi_part2_bits, unsigned nof_csi_part2_enc_bits) override;
+  pusch_codeword_buffer& demultiplex(pusch_decoder_buffer& sch_data,
+                                     pusch_decoder_buffer& harq_ack,
+                                     pusch_decoder_buffer& csi_part1,
+                                     const configuration&  config) override;
+
+private:
+  span<log_likelihood_ratio> get_next_block_view(unsigned block_size) override;
+  void on_new_block(span<const log_likelihood_ratio> data, const bit_buffer& scrambling_seq) override;
+  void on_end_codeword() override;
+  bool run(pdc_cw_result& res);
+
+  std::shared_ptr<context>          ctx;
+  configuration                     cfg;
+  pusch_decoder_buffer*             sch = nullptr;
+  pusch_decoder_buffer*             ack = nullptr;
+  pusch_decoder_buffer*             csi1 = nullptr;
+  pusch_decoder_buffer*             csi2 = nullptr;
+  unsigned                          csi2_bits = 0, csi2_enc = 0;
+  std::vector<log_likelihood_ratio> codeword; // descrambled soft bits, resource-element order
+  std::vector<uint8_t>              seq;      // scrambling sequence, packed MSB first
+  std::vector<int8_t>               out_sch, out_uci;
+  size_t                            count = 0;
+};
+
 std::shared_ptr<ldpc_decoder_factory>        create_ldpc_decoder_factory_cuda(std::shared_ptr<context> ctx);
 std::shared_ptr<ldpc_rate_dematcher_factory> create_ldpc_rate_dematcher_factory_cuda(std::shared_ptr<context> ctx);
 std::shared_ptr<crc_calculator_factory>      create_crc_calculator_factory_cuda(std::shared_ptr<context> ctx);
 std::shared_ptr<hal::hw_accelerator_pusch_dec_factory>
 create_hw_accelerator_pusch_dec_factory_cuda(std::shared_ptr<context> ctx);
+/// What a "cuda" branch of create_ulsch_demultiplex_factory_sw (phy/upper/channel_processors/pusch/factories.h:161)
+/// creates for every PUSCH processor.
+std::unique_ptr<ulsch_demultiplex> create_ulsch_demultiplex_cuda(std::shared_ptr<context> ctx);
 
 } // namespace cuda
 } // namespace srsran

@@ -5,11 +5,13 @@
 #include "lib/phy/upper/channel_processors/pusch/pusch_codeblock_decoder.h"
 #include "lib/phy/upper/channel_processors/pusch/pusch_decoder_hw_impl.h"
 #include "lib/phy/upper/channel_processors/pusch/pusch_decoder_impl.h"
+#include "lib/phy/upper/channel_processors/pusch/ulsch_demultiplex_impl.h"
 #include "pusch_dec_cuda_adapters.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_notifier.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_result.h"
 #include "srsran/phy/upper/unique_rx_buffer.h"
 #include <cmath>
+#include <functional>
 #include <cstdio>
 #include <random>
 
@@ -75,6 +77,69 @@ modulation_scheme to_mod(int qm)
          : qm == 6 ? modulation_scheme::QAM64
                    : modulation_scheme::QAM256;
 }
+
+
+/// Decoder buffer that records what it is given; the CSI Part 1 one answers with set_csi_part2 like the PUSCH processor.
+class recording_buffer : public pusch_decoder_buffer
+{
+public:
+  std::vector<log_likelihood_ratio> data, scratch;
+  bool                              ended = false;
+  std::function<void()>             on_end;
+  span<log_likelihood_ratio>        get_next_block_view(unsigned n) override
+  {
+    scratch.resize(n);
+    return scratch;
+  }
+  void on_new_softbits(span<const log_likelihood_ratio> s) override { data.insert(data.end(), s.begin(), s.end()); }
+  void on_end_softbits() override
+  {
+    ended = true;
+    if (on_end) {
+      on_end();
+    }
+  }
+};
+
+/// Feeds one codeword into a demultiplexer the way pusch_demodulator_impl does (:160-283) and records the four streams.
+struct demux_run {
+  recording_buffer sch, ack, csi1, csi2;
+  void             run(ulsch_demultiplex&                      demux,
+                       const ulsch_demultiplex::configuration& cfg,
+                       unsigned                                csi2_bits,
+                       unsigned                                csi2_enc,
+                       const std::vector<int8_t>&              llr,
+                       const std::vector<uint8_t>&             seq_bits)
+  {
+    csi1.on_end = [&]() {
+      if (csi2_enc != 0) {
+        demux.set_csi_part2(csi2, csi2_bits, csi2_enc);
+      }
+    };
+    pusch_codeword_buffer& cw   = demux.demultiplex(sch, ack, csi1, cfg);
+    const unsigned         bpre = get_bits_per_symbol(cfg.modulation) * cfg.nof_layers;
+    const unsigned         re_dmrs =
+        (12 - cfg.nof_cdm_groups_without_data * (cfg.dmrs == dmrs_type::TYPE1 ? 6 : 4)) * cfg.nof_prb;
+    size_t pos = 0;
+    for (unsigned l = cfg.start_symbol_index; l != cfg.start_symbol_index + cfg.nof_symbols; ++l) {
+      unsigned nof_re = cfg.dmrs_symbol_mask.test(l) ? re_dmrs : 12 * cfg.nof_prb;
+      unsigned done   = 0;
+      while (done != nof_re) {
+        span<log_likelihood_ratio> view = cw.get_next_block_view((nof_re - done) * bpre);
+        unsigned                   n    = view.size();
+        dynamic_bit_buffer         seq(n);
+        for (unsigned i = 0; i != n; ++i) {
+          view[i] = log_likelihood_ratio(llr[pos + i]);
+          seq.insert(seq_bits[pos + i], i, 1);
+        }
+        cw.on_new_block(view, seq);
+        pos += n;
+        done += n / bpre;
+      }
+    }
+    cw.on_end_codeword();
+  }
+};
 
 int failures = 0;
 #define CHECK(cond, ...)                                                                                               \
@@ -260,6 +325,97 @@ int main()
                   b.tb_crc_ok,
                   b.ldpc_decoder_stats.get_nof_observations());
     }
+  }
+
+  // ---- ulsch_demultiplex_cuda vs the reference's ulsch_demultiplex_impl ---------------------------------------------------
+  {
+    auto     demux_gpu = cuda::create_ulsch_demultiplex_cuda(ctx);
+    unsigned checked   = 0;
+    for (int trial = 0; trial != 400 && checked != 60; ++trial) {
+      const unsigned qms[] = {2, 4, 6, 8};
+      const unsigned qm = qms[rng() % 4], nl = 1 + rng() % 4, nprb = 1 + rng() % 30;
+      ulsch_demultiplex::configuration cfg;
+      cfg.modulation                  = to_mod(qm);
+      cfg.nof_layers                  = nl;
+      cfg.nof_prb                     = nprb;
+      cfg.start_symbol_index          = rng() % 3;
+      cfg.nof_symbols                 = 6 + rng() % (9 - cfg.start_symbol_index);
+      cfg.dmrs                        = (rng() % 2) ? dmrs_type::TYPE1 : dmrs_type::TYPE2;
+      cfg.nof_cdm_groups_without_data = 1 + rng() % 2;
+      cfg.dmrs_symbol_mask            = symbol_slot_mask(14);
+      cfg.dmrs_symbol_mask.set(cfg.start_symbol_index + 1 + rng() % 3); // never the first symbol of the allocation
+      const unsigned bpre   = qm * nl;
+      const unsigned nre    = cfg.nof_prb * 12 * (cfg.nof_symbols - 1);
+      const unsigned acks[] = {0, 1, 2, 5, 20};
+      cfg.nof_harq_ack_bits = acks[rng() % 5];
+      cfg.nof_enc_harq_ack_bits = cfg.nof_harq_ack_bits ? (1 + rng() % (nre / 8 + 1)) * bpre : 0;
+      cfg.nof_harq_ack_rvd      = (cfg.nof_harq_ack_bits <= 2) ? cfg.nof_enc_harq_ack_bits + (rng() % 4) * bpre : 0;
+      cfg.nof_csi_part1_bits    = (rng() % 2) ? 1 + rng() % 20 : 0;
+      cfg.nof_enc_csi_part1_bits = cfg.nof_csi_part1_bits ? (1 + rng() % (nre / 8 + 1)) * bpre : 0;
+      unsigned csi2_bits = 0, csi2_enc = 0;
+      if (cfg.nof_csi_part1_bits != 0 && rng() % 2) {
+        csi2_bits = 1 + rng() % 9;
+        csi2_enc  = (1 + rng() % (nre / 8 + 1)) * bpre;
+      }
+      // Codeword length.
+      const unsigned re_dmrs =
+          (12 - cfg.nof_cdm_groups_without_data * (cfg.dmrs == dmrs_type::TYPE1 ? 6 : 4)) * cfg.nof_prb;
+      size_t total = 0;
+      for (unsigned l = cfg.start_symbol_index; l != cfg.start_symbol_index + cfg.nof_symbols; ++l) {
+        total += (cfg.dmrs_symbol_mask.test(l) ? re_dmrs : 12 * cfg.nof_prb) * bpre;
+      }
+      std::vector<int8_t>  llr(total);
+      std::vector<uint8_t> seq(total);
+      for (size_t i = 0; i != total; ++i) {
+        llr[i] = static_cast<int8_t>(static_cast<int>(rng() % 241) - 120);
+        seq[i] = rng() & 1;
+      }
+      // Only descriptions in which all UCI fits (the reference asserts otherwise; the GPU path reports an error).
+      {
+        pdc_cw_desc d                 = {};
+        d.qm                          = qm;
+        d.nof_layers                  = nl;
+        d.start_symbol_index          = cfg.start_symbol_index;
+        d.nof_symbols                 = cfg.nof_symbols;
+        d.dmrs_type                   = (cfg.dmrs == dmrs_type::TYPE1) ? 1 : 2;
+        d.nof_cdm_groups_without_data = cfg.nof_cdm_groups_without_data;
+        d.nof_prb                     = cfg.nof_prb;
+        for (unsigned l = 0; l != 14; ++l) {
+          d.dmrs_symbol_mask |= cfg.dmrs_symbol_mask.test(l) ? (1u << l) : 0u;
+        }
+        d.nof_harq_ack_rvd       = cfg.nof_harq_ack_rvd;
+        d.nof_harq_ack_bits      = cfg.nof_harq_ack_bits;
+        d.nof_enc_harq_ack_bits  = cfg.nof_enc_harq_ack_bits;
+        d.nof_csi_part1_bits     = cfg.nof_csi_part1_bits;
+        d.nof_enc_csi_part1_bits = cfg.nof_enc_csi_part1_bits;
+        d.nof_csi_part2_bits     = csi2_bits;
+        d.nof_enc_csi_part2_bits = csi2_enc;
+        std::vector<int8_t> o1(total + 16), o2(total + 16);
+        pdc_cw_result       r;
+        if (pdc_ulsch_demux(ctx->get(), &d, 1, llr.data(), total, nullptr, o1.data(), o1.size(), o2.data(), o2.size(),
+                            &r) != PDC_OK) {
+          continue;
+        }
+      }
+      // Value-initialised like the reference's factory does (std::make_unique): the class leaves softbit_count
+      // without an initialiser.
+      auto      demux_sw = std::make_unique<ulsch_demultiplex_impl>();
+      demux_run a, b;
+      a.run(*demux_sw, cfg, csi2_bits, csi2_enc, llr, seq);
+      b.run(*demux_gpu, cfg, csi2_bits, csi2_enc, llr, seq);
+      auto same = [](const recording_buffer& x, const recording_buffer& y) {
+        return x.data.size() == y.data.size() && x.ended == y.ended &&
+               std::equal(x.data.begin(), x.data.end(), y.data.begin());
+      };
+      CHECK(same(a.sch, b.sch), "ulsch demux: SCH stream differs (trial %d, %zu vs %zu)", trial, a.sch.data.size(),
+            b.sch.data.size());
+      CHECK(same(a.ack, b.ack), "ulsch demux: HARQ-ACK stream differs (trial %d)", trial);
+      CHECK(same(a.csi1, b.csi1), "ulsch demux: CSI Part 1 stream differs (trial %d)", trial);
+      CHECK(same(a.csi2, b.csi2), "ulsch demux: CSI Part 2 stream differs (trial %d)", trial);
+      ++checked;
+    }
+    std::printf("ulsch_demultiplex_cuda: %u configurations compared with ulsch_demultiplex_impl\n", checked);
+    CHECK(checked >= 30, "too few UL-SCH demultiplexing configurations were checked");
   }
   std::printf(failures ? "FAILED: %d checks\n" : "PASS (%d failures)\n", failures);
   return failures ? 1 : 0;
