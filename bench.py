@@ -388,7 +388,6 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms, launches = time_resident(d_fixed, args.steps, args.warmup)
-    clocks = sampler.stop()
     ms_per_step = ms / args.steps
     value = world * n_cb * INFO_BITS / (ms_per_step * 1e-3) / 1e9
 
@@ -419,6 +418,7 @@ def main():
     e2e_out = e2e_run(args.steps)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    clocks = sampler.stop()  # sampled over both timed regions (resident and e2e)
     e2e_s = t1 - t0
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda")
