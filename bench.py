@@ -253,8 +253,21 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
                                   flags, True, cuda_stream=stream.cuda_stream, d_tbs=d_tbs.data_ptr(), n_tb=cells,
                                   d_tb_results=d_tres.data_ptr(), d_tb_bytes=d_tb.data_ptr())
 
+            # Deferred variant: no UCI in these codewords, so the UL-SCH soft bits are not materialised at all; the rate
+            # dematcher descrambles while it stages the codeblocks (one pass less over the soft bits).
+            cws_def = cws.copy()
+            cws_def["flags"] = capi.CW_SCRAMBLED | capi.CW_DEFER_DESCRAMBLING
+            d_sch2 = torch.zeros(cells * n_llr + 16, dtype=torch.int8, device="cuda")
+
+            def chain_deferred():
+                ctx.launch_codewords_device(cws_def, d_raw.data_ptr(), cells * n_llr, d_sch2.data_ptr(), cells * n_llr,
+                                            cuda_stream=stream.cuda_stream)
+                ctx.launch_device(d_cbs.data_ptr(), n_cb, d_sch2.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), 384,
+                                  flags, True, cuda_stream=stream.cuda_stream, d_tbs=d_tbs.data_ptr(), n_tb=cells,
+                                  d_tb_results=d_tres.data_ptr(), d_tb_bytes=d_tb.data_ptr())
+
             times = {}
-            for label, fn in (("front_end", front), ("chain", chain)):
+            for label, fn in (("front_end", front), ("chain", chain), ("chain_deferred", chain_deferred)):
                 for _ in range(3):
                     fn()
                 torch.cuda.synchronize()
@@ -265,11 +278,14 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
                 torch.cuda.synchronize()
                 times[label] = e0.elapsed_time(e1) / reps * 1e3
             same = bool((d_sch[:cells * n_llr].cpu().numpy() == np.tile(llrs, cells)).all())
-            tres = d_tres.cpu().numpy().view(capi.TB_RESULT_DTYPE)
+            tres = d_tres.cpu().numpy().view(capi.TB_RESULT_DTYPE)  # results of the deferred chain (ran last)
+            deferred_ok = bool(tres["tb_crc_ok"].all()) and bool((d_tb.cpu().numpy()[:tbs_bits // 8] == tb).all()) and \
+                not bool(d_sch2.any().item())  # the UL-SCH space was never written
             fe_bytes = 2 * cells * n_llr + cells * n_llr // 8 * 2  # soft bits in + out, sequence written + read
             out[f"{name}_front_end"] = {
                 "us_front_end": times["front_end"], "us_per_slot_with_front_end": times["chain"],
                 "front_end_gbs": fe_bytes / (times["front_end"] * 1e-6) / 1e9, "front_end_bytes": fe_bytes,
+                "us_per_slot_with_deferred_descrambling": times["chain_deferred"], "deferred_chain_ok": deferred_ok,
                 "descrambled_equals_input": same, "tb_crc_ok": bool(tres["tb_crc_ok"].all()),
                 "kernels": "prg_kernel + ulsch_sch_kernel (no UCI in this slot)"}
     return out

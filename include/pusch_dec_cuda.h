@@ -113,6 +113,11 @@ typedef struct {
  * (pusch_processor_impl.cpp:61-82; both 0 = no CSI Part 2).
  */
 #define PDC_CW_SCRAMBLED 1u /* the input still carries the scrambling sequence: descramble on the device             */
+#define PDC_CW_DEFER_DESCRAMBLING 2u /* with PDC_CW_SCRAMBLED, for a codeword without UCI: do not materialise its UL-SCH
+                                        soft bits; the rate dematcher of the NEXT batch that reads its LLRs from that
+                                        UL-SCH space (pdc_submit after pdc_submit_codewords; pdc_launch_device with
+                                        d_llrs = the d_sch of pdc_launch_codewords_device) descrambles while it stages
+                                        the codeblocks. The UL-SCH space itself is then left unwritten.              */
 
 typedef struct {
   uint32_t in_offset;   /* first soft bit of the codeword in the input buffer                                         */

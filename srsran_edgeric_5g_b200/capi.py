@@ -54,6 +54,7 @@ TB_DESC_DTYPE = np.dtype([("first_cb", "<u4"), ("nof_cb", "<u4"), ("tbs_bits", "
                           ("reserved", "<u4")])
 TB_RESULT_DTYPE = np.dtype([("tb_crc_ok", "u1"), ("all_cb_ok", "u1"), ("reserved", "<u2")])
 CW_SCRAMBLED = 1
+CW_DEFER_DESCRAMBLING = 2
 # pdc_cw_desc / pdc_cw_result (codeword front end)
 CW_DESC_DTYPE = np.dtype([("in_offset", "<u4"), ("sch_offset", "<u4"), ("uci_offset", "<u4"), ("c_init", "<u4"),
                           ("flags", "<u4"), ("qm", "u1"), ("nof_layers", "u1"), ("start_symbol_index", "u1"),

@@ -69,6 +69,31 @@ __device__ __forceinline__ int scale_c2v(int x, int mode)
   return (x * 204) >> 8;
 }
 
+// ---- scrambling-sequence helpers shared by the front end and the rate dematcher ---------------------------------------
+// Sequences are stored one element per bit, element k of a codeword in bit (k & 31) of word (k >> 5).
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t seq_bit(const uint32_t* __restrict__ seq, uint32_t i)
+{
+  return (__ldg(seq + (i >> 5)) >> (i & 31u)) & 1u;
+}
+// Up to 32 elements starting at element i (element i + k in bit k).
+__device__ __forceinline__ uint32_t seq_bits32(const uint32_t* __restrict__ seq, uint32_t i)
+{
+  const uint32_t* w = seq + (i >> 5);
+  return __funnelshift_r(__ldg(w), __ldg(w + 1), i & 31u);
+}
+// Per byte: -v where the bit of `bits` is set (two's complement, -128 stays -128), v otherwise.
+__device__ __forceinline__ uint32_t negate4(uint32_t v, uint32_t bits)
+{
+  const uint32_t one = (bits * 0x00204081u) & 0x01010101u; // bit k -> byte k
+  const uint32_t m   = one * 0xffu;
+  const uint32_t t   = v ^ m;
+  return ((t & 0x7f7f7f7fu) + one) ^ (t & 0x80808080u);
+}
+#endif
+
+constexpr uint32_t CB_NOT_SCRAMBLED = 0xffffffffu;
+
 // Launch parameters shared by the kernels.
 struct BatchParams {
   const pdc_cb_desc* cbs;
@@ -83,6 +108,12 @@ struct BatchParams {
                                  // non-zero soft bit, -1 = unknown (scan the entry)
   int                scale_mode;
   int                simd_width;
+  // Deferred descrambling (codewords without UCI whose UL-SCH soft bits were not materialised): per codeblock
+  // {first word of the codeword's sequence, sequence element of the codeblock's first soft bit, offset of that soft bit
+  // in `raw`, -}; x = CB_NOT_SCRAMBLED: read `llrs` as usual. nullptr: no codeblock is affected.
+  const uint4*       cb_scr;
+  const uint32_t*    seq;
+  const int8_t*      raw;
 };
 
 struct TbParams {

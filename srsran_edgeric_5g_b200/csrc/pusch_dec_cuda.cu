@@ -58,6 +58,14 @@ struct FrontEnd {
   size_t               h_plan_cap[RING] = {0, 0, 0, 0};
   cudaEvent_t          plan_ev[RING]  = {nullptr, nullptr, nullptr, nullptr};
   int                  ring_pos = 0;
+  // Deferred descrambling: the last front end left codewords without UCI scrambled in d_in for the rate dematcher of
+  // the next batch that reads its LLRs from d_sch.
+  bool                 deferred = false;
+  uint32_t             deferred_n_cw = 0;
+  const int8_t*        deferred_in = nullptr;
+  const int8_t*        deferred_sch = nullptr;
+  uint4*               d_cb_scr = nullptr;
+  size_t               cb_scr_cap = 0;
   // Pending results of the queue.
   int8_t*              u_uci = nullptr;
   size_t               uci_bytes = 0;
@@ -143,6 +151,23 @@ BatchShape scan_batch(const pdc_cb_desc* cbs, uint32_t n)
   return s;
 }
 
+template <typename T>
+static cudaError_t grow_device(T** p, size_t* cap, size_t need)
+{
+  if (need <= *cap) {
+    return cudaSuccess;
+  }
+  cudaFree(*p);
+  *p   = nullptr;
+  *cap = 0;
+  size_t      want = need + need / 4 + 64;
+  cudaError_t e    = cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T));
+  if (e == cudaSuccess) {
+    *cap = want;
+  }
+  return e;
+}
+
 // Launches the kernels of one batch on stream s. All pointers are device pointers.
 int launch_batch(pdc_ctx*             ctx,
                  const pdc_cb_desc*   d_cbs,
@@ -158,9 +183,25 @@ int launch_batch(pdc_ctx*             ctx,
                  const int8_t*        direct_in,
                  uint32_t             direct_n,
                  cudaStream_t         s,
-                 uint32_t*            tb_sync = nullptr)
+                 uint32_t*            tb_sync = nullptr,
+                 FrontEnd*            fe      = nullptr)
 {
   pdc::BatchParams p;
+  p.cb_scr = nullptr;
+  p.seq    = nullptr;
+  p.raw    = nullptr;
+  if (fe != nullptr && fe->deferred && shape.any_dematch && d_llrs == fe->deferred_sch) {
+    // Codewords whose descrambling was deferred to this batch: map every codeblock to its codeword (one-shot).
+    PDC_CUDA(grow_device(&fe->d_cb_scr, &fe->cb_scr_cap, (size_t)n_cb));
+    pdc::cb_descramble_map_kernel<<<(n_cb + 255) / 256, 256, 0, s>>>(
+        d_cbs, n_cb, reinterpret_cast<const pdc::UlschCodeword*>(fe->d_plan), fe->deferred_n_cw, fe->d_cb_scr);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+    p.cb_scr     = fe->d_cb_scr;
+    p.seq        = fe->d_seq;
+    p.raw        = fe->deferred_in;
+    fe->deferred = false;
+  }
   p.cbs          = d_cbs;
   p.n_cb         = n_cb;
   p.llrs         = d_llrs;
@@ -221,23 +262,6 @@ cudaError_t dev_alloc(T** p, size_t n)
 {
   return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
 }
-template <typename T>
-static cudaError_t grow_device(T** p, size_t* cap, size_t need)
-{
-  if (need <= *cap) {
-    return cudaSuccess;
-  }
-  cudaFree(*p);
-  *p   = nullptr;
-  *cap = 0;
-  size_t      want = need + need / 4 + 64;
-  cudaError_t e    = cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T));
-  if (e == cudaSuccess) {
-    *cap = want;
-  }
-  return e;
-}
-
 template <typename T>
 cudaError_t host_alloc(T** p, size_t n)
 {
@@ -450,6 +474,7 @@ static void free_front_end(FrontEnd& fe)
   cudaFree(fe.d_seq);
   cudaFree(fe.d_uci);
   cudaFree(fe.d_plan);
+  cudaFree(fe.d_cb_scr);
   cudaFreeHost(fe.h_uci);
   for (int k = 0; k != FrontEnd::RING; ++k) {
     cudaFreeHost(fe.h_plan[k]);
@@ -611,7 +636,7 @@ int pdc_submit(pdc_ctx*           ctx,
   // Codeblocks that are not decoded report "not run".
   PDC_CUDA(cudaMemsetAsync(q.d_cb_res, 0, sizeof(pdc_cb_result) * n_cb, q.stream));
   int rc = launch_batch(ctx, q.d_cbs, n_cb, q.d_llrs, q.d_tbs, n_tb, q.d_cb_res, q.d_cb_bits, q.d_tb_res, q.d_tb_out,
-                        shape, nullptr, 0, q.stream, q.d_tb_sync);
+                        shape, nullptr, 0, q.stream, q.d_tb_sync, q.fe.pending ? &q.fe : nullptr);
   if (rc != PDC_OK) {
     return rc;
   }
@@ -665,11 +690,19 @@ static int front_end_launch(pdc_ctx*           ctx,
   pdc::UlschPlan& plan = fe.plan;
   plan.clear();
   size_t sch_end = 0, uci_end = 0;
+  bool   any_deferred = false, all_deferred = true;
   for (uint32_t i = 0; i != n_cw; ++i) {
     if (!pdc::ulsch_plan_codeword(cws[i], plan)) {
       return fail(PDC_ERR_INVALID, "codeword front end: inconsistent codeword description");
     }
-    const pdc::UlschCodeword& cw = plan.cws.back();
+    pdc::UlschCodeword& cw = plan.cws.back();
+    if ((cws[i].flags & PDC_CW_DEFER_DESCRAMBLING) && (cws[i].flags & PDC_CW_SCRAMBLED) && cw.n_out[0] == cw.n_in) {
+      // No UCI: the UL-SCH stream is the input itself; leave it scrambled for the rate dematcher.
+      cw.flags |= pdc::ULSCH_CW_DEFERRED;
+      any_deferred = true;
+    } else {
+      all_deferred = false;
+    }
     if ((cws[i].sch_offset & 3u) || (size_t)cw.in_off + cw.n_in > n_in) {
       return fail(PDC_ERR_INVALID, "codeword front end: codeword outside the input or misaligned UL-SCH offset");
     }
@@ -750,7 +783,7 @@ static int front_end_launch(pdc_ctx*           ctx,
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
-  {
+  if (!all_deferred) {
     // Enough CTAs to fill the GPU a few times over; each thread steps through the words of its codeword.
     const uint32_t chunks = (max_sch + 15) / 16;
     uint32_t       gx = std::max(1u, std::min((chunks + 255) / 256, (uint32_t)(8 * ctx->sm_count + n_cw - 1) / n_cw));
@@ -763,8 +796,12 @@ static int front_end_launch(pdc_ctx*           ctx,
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
-  fe.uci_bytes = uci_end;
-  fe.sch_len   = (uint32_t)sch_end;
+  fe.uci_bytes     = uci_end;
+  fe.sch_len       = (uint32_t)sch_end;
+  fe.deferred      = any_deferred;
+  fe.deferred_n_cw = n_cw;
+  fe.deferred_in   = d_in;
+  fe.deferred_sch  = d_sch;
   return PDC_OK;
 }
 
@@ -885,7 +922,8 @@ int pdc_launch_device(pdc_ctx*    ctx,
   return launch_batch(ctx, static_cast<const pdc_cb_desc*>(d_cbs), n_cb, static_cast<const int8_t*>(d_llrs),
                       static_cast<const pdc_tb_desc*>(d_tbs), n_tb, static_cast<pdc_cb_result*>(d_cb_results),
                       static_cast<uint8_t*>(d_cb_bits), static_cast<pdc_tb_result*>(d_tb_results),
-                      static_cast<uint8_t*>(d_tb_bytes), shape, nullptr, 0, static_cast<cudaStream_t>(cuda_stream));
+                      static_cast<uint8_t*>(d_tb_bytes), shape, nullptr, 0, static_cast<cudaStream_t>(cuda_stream), nullptr,
+                      &ctx->fe_sync);
 }
 
 int pdc_harq_read(pdc_ctx* ctx, uint32_t harq_id, int8_t* soft, uint32_t n)

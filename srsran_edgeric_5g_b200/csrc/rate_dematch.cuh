@@ -32,6 +32,8 @@ struct DematchGeom {
   int zf_lo;          // new data, not wrapped: [zf_lo, N) is zeroed at the end; N if not applicable
   int simd_width;
   int staged;         // the deinterleaved input is staged in shared memory
+  const uint32_t* seq; // deferred descrambling: scrambling sequence of the codeword (nullptr: the input is descrambled)
+  uint32_t seq_base;  // sequence element of the codeblock's first rate-matched soft bit
 };
 
 __device__ __forceinline__ bool dm_geometry(const pdc_cb_desc& d, int simd_width, DematchGeom& g)
@@ -129,12 +131,17 @@ __device__ __forceinline__ int dm_fetch(const DematchGeom& g, const int8_t* __re
   if (STAGED) {
     return (int)(int8_t)sh[i];
   }
-  if (g.qm == 1) {
-    return (int)__ldg(llr + i);
+  int k = i;
+  if (g.qm != 1) {
+    int j   = i / g.Kq; // bit plane
+    int sym = i - j * g.Kq;
+    k       = sym * g.qm + j;
   }
-  int j   = i / g.Kq; // bit plane
-  int sym = i - j * g.Kq;
-  return (int)__ldg(llr + sym * g.qm + j);
+  int v = (int)__ldg(llr + k);
+  if (g.seq != nullptr && seq_bit(g.seq, g.seq_base + (uint32_t)k)) {
+    v = (int)(int8_t)(uint8_t)(0u - (uint32_t)v);
+  }
+  return v;
 }
 
 template <bool STAGED>
@@ -445,6 +452,14 @@ __device__ __forceinline__ void dm_stage_planes(const DematchGeom& g, const int8
         cur                = nxt;
       }
     }
+    if (g.seq != nullptr) {
+      // Deferred descrambling: the 4 * QM soft bits of the group against their sequence elements.
+      const uint32_t bits = seq_bits32(g.seq, g.seq_base + (uint32_t)grp * 4u * QM);
+#pragma unroll
+      for (int r = 0; r != QM; ++r) {
+        w[r] = negate4(w[r], (bits >> (4 * r)) & 0xfu);
+      }
+    }
 #pragma unroll
     for (int j = 0; j != QM; ++j) {
       uint32_t o = 0;
@@ -465,7 +480,12 @@ __device__ __forceinline__ void dm_stage_planes(const DematchGeom& g, const int8
   const int sym0 = 4 * n_groups;
   for (int idx = t0; idx < (g.Kq - sym0) * QM; idx += nt) {
     const int s4 = idx / QM, j = idx - s4 * QM;
-    sh[j * g.Kq + sym0 + s4] = src[(size_t)(sym0 + s4) * QM + j];
+    const int k  = (sym0 + s4) * QM + j;
+    uint8_t   v  = src[(size_t)k];
+    if (g.seq != nullptr && seq_bit(g.seq, g.seq_base + (uint32_t)k)) {
+      v = (uint8_t)(0u - v);
+    }
+    sh[j * g.Kq + sym0 + s4] = v;
   }
 }
 
@@ -488,7 +508,11 @@ __device__ __forceinline__ void dm_stage(const DematchGeom& g, const int8_t* __r
     default:
       // One bit per symbol: the stream is already in order. (Other modulation orders are never staged.)
       for (int i = t0; i < g.E; i += nt) {
-        sh[i] = (uint8_t)__ldg(llr + i);
+        uint8_t v = (uint8_t)__ldg(llr + i);
+        if (g.seq != nullptr && seq_bit(g.seq, g.seq_base + (uint32_t)i)) {
+          v = (uint8_t)(0u - v);
+        }
+        sh[i] = v;
       }
       break;
   }
@@ -511,15 +535,28 @@ __global__ void __launch_bounds__(DM_THREADS, 3) rate_dematch_kernel(BatchParams
   }
   // The first warp derives the geometry and the segments while the others stage the input, for which the modulation
   // order and the length are enough.
-  const int8_t* llr = prm.llrs + d.llr_offset;
-  uint32_t*     out = reinterpret_cast<uint32_t*>(prm.harq + (size_t)min(d.harq_id, prm.harq_entries - 1) * PDC_MAX_CB_SOFT);
+  const int8_t*   llr      = prm.llrs + d.llr_offset;
+  const uint32_t* seq      = nullptr;
+  uint32_t        seq_base = 0;
+  if (prm.cb_scr != nullptr) {
+    const uint4 e = prm.cb_scr[cb];
+    if (e.x != CB_NOT_SCRAMBLED) {
+      // The codeblock's soft bits were left scrambled in the raw codeword: descramble while staging.
+      llr      = prm.raw + e.z;
+      seq      = prm.seq + e.x;
+      seq_base = e.y;
+    }
+  }
+  uint32_t* out = reinterpret_cast<uint32_t*>(prm.harq + (size_t)min(d.harq_id, prm.harq_entries - 1) * PDC_MAX_CB_SOFT);
   const int     qm = d.qm, E = d.rm_length;
   const bool    staged = (qm == 1 || qm == 2 || qm == 4 || qm == 6 || qm == 8) && E > 0 && (E % qm) == 0 &&
                       E <= DM_STAGE_BYTES;
   if (tid < 32) {
     if (tid == 0) {
-      ok      = dm_geometry(d, prm.simd_width, g_sh) && (d.harq_id < prm.harq_entries);
-      sh_last = 0;
+      ok            = dm_geometry(d, prm.simd_width, g_sh) && (d.harq_id < prm.harq_entries);
+      g_sh.seq      = seq;
+      g_sh.seq_base = seq_base;
+      sh_last       = 0;
     }
     __syncwarp();
     if (ok && g_sh.staged && g_sh.E <= g_sh.Dn) {
@@ -549,7 +586,7 @@ __global__ void __launch_bounds__(DM_THREADS, 3) rate_dematch_kernel(BatchParams
   }
   if (staged && tid >= 32) {
     DematchGeom gs; // the fields staging needs
-    gs.qm = qm, gs.E = E, gs.Kq = E / qm;
+    gs.qm = qm, gs.E = E, gs.Kq = E / qm, gs.seq = seq, gs.seq_base = seq_base;
     dm_stage(gs, llr, sh_in, tid - 32, (int)blockDim.x - 32);
   }
   __syncthreads();

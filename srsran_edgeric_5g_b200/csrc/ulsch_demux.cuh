@@ -112,20 +112,6 @@ __global__ void __launch_bounds__(128) prg_kernel(const UlschCodeword* __restric
   }
 }
 
-__device__ __forceinline__ uint32_t seq_bit(const uint32_t* __restrict__ seq, uint32_t i)
-{
-  return (__ldg(seq + (i >> 5)) >> (i & 31u)) & 1u;
-}
-
-// Per byte: -v where the bit of `bits` is set (two's complement, -128 stays -128), v otherwise.
-__device__ __forceinline__ uint32_t negate4(uint32_t v, uint32_t bits)
-{
-  const uint32_t one = (bits * 0x00204081u) & 0x01010101u; // bit k -> byte k
-  const uint32_t m   = one * 0xffu;
-  const uint32_t t   = v ^ m;
-  return ((t & 0x7f7f7f7fu) + one) ^ (t & 0x80808080u);
-}
-
 struct UlschArgs {
   const UlschCodeword* cws;
   const UlschSymbol*   syms;
@@ -177,8 +163,7 @@ __device__ __forceinline__ int ulsch_sch_byte(const UlschArgs& a, const UlschCod
 // Sixteen scrambling bits starting at element i of the codeword.
 __device__ __forceinline__ uint32_t seq_bits16(const uint32_t* __restrict__ seq, uint32_t i)
 {
-  const uint32_t* w = seq + (i >> 5);
-  return __funnelshift_r(__ldg(w), __ldg(w + 1), i & 31u) & 0xffffu;
+  return seq_bits32(seq, i) & 0xffffu;
 }
 
 // Sixteen input bytes from any address: one 128-bit load when aligned, else five aligned words and funnel shifts.
@@ -211,6 +196,9 @@ __global__ void __launch_bounds__(256) ulsch_sch_kernel(UlschArgs a)
     reinterpret_cast<uint32_t*>(S)[i] = reinterpret_cast<const uint32_t*>(a.syms + cw.sym_first)[i];
   }
   __syncthreads();
+  if (cw.flags & ULSCH_CW_DEFERRED) {
+    return; // descrambled by the rate dematcher while it stages the codeblocks
+  }
   const uint32_t  n_sch     = cw.n_out[0];
   const uint32_t  n_chunks  = (n_sch + 15u) / 16u;
   const bool      scrambled = (cw.flags & PDC_CW_SCRAMBLED) != 0;
@@ -288,6 +276,27 @@ __global__ void __launch_bounds__(256) ulsch_uci_kernel(UlschArgs a)
     }
     a.uci[cw.uci_off + t] = (int8_t)v;
   }
+}
+
+// For every codeblock of the batch: the deferred codeword (if any) whose UL-SCH space holds its rate-matched soft bits.
+__global__ void cb_descramble_map_kernel(const pdc_cb_desc* __restrict__ cbs, uint32_t n_cb,
+                                         const UlschCodeword* __restrict__ cws, uint32_t n_cw, uint4* __restrict__ out)
+{
+  const uint32_t cb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cb >= n_cb) {
+    return;
+  }
+  const uint32_t off = cbs[cb].llr_offset;
+  uint4          e   = make_uint4(CB_NOT_SCRAMBLED, 0, 0, 0);
+  for (uint32_t c = 0; c != n_cw; ++c) {
+    const UlschCodeword& cw = cws[c];
+    if ((cw.flags & ULSCH_CW_DEFERRED) && off >= cw.sch_off && off - cw.sch_off < cw.n_out[0]) {
+      const uint32_t s = off - cw.sch_off;
+      e                = make_uint4(cw.seq_word_off, s, cw.in_off + s, 0);
+      break;
+    }
+  }
+  out[cb] = e;
 }
 
 inline cudaError_t upload_prg_tables()

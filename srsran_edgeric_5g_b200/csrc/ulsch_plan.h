@@ -18,6 +18,7 @@ namespace pdc {
 constexpr uint32_t ULSCH_IDENTITY  = 0xffffffffu; // list offset: every resource element of the symbol, in order
 constexpr uint16_t ULSCH_PUNCTURED = 0x8000u;     // list entry: the soft bits of this element read as zero (taken by HARQ-ACK)
 constexpr int      ULSCH_STREAMS   = 4;           // UL-SCH, HARQ-ACK, CSI Part 1, CSI Part 2
+constexpr uint32_t ULSCH_CW_DEFERRED = 0x100u;    // internal codeword flag: UL-SCH not materialised, the dematcher descrambles
 
 // One OFDM symbol that carries soft bits. Offsets are in soft bits relative to the codeword / to each output stream.
 struct UlschSymbol {

@@ -171,3 +171,75 @@ def test_front_end_feeds_the_decoder(ctx, orc, ack_bits):
     assert (out["cb_bits"] == direct["cb_bits"]).all()
     assert out["tb_results"][0]["tb_crc_ok"] == 1
     assert (out["tb_bytes"][:tbs_bits // 8] == tb).all()
+
+
+@pytest.mark.parametrize("qm,nl,nprb,rate", [(1, 1, 30, 0.3), (2, 1, 25, 0.2), (2, 2, 50, 0.1), (4, 2, 40, 0.5),
+                                             (6, 3, 33, 0.7), (8, 4, 60, 0.85)])
+def test_deferred_descrambling_in_the_dematcher(ctx, orc, qm, nl, nprb, rate):
+    """PDC_CW_DEFER_DESCRAMBLING: codewords without UCI stay scrambled and the rate dematcher descrambles while it
+    stages the codeblocks. Two transmissions (new data, then a retransmission that combines) of two codewords in one
+    batch - one without UCI (deferred), one with CSI Part 1 (materialised) - must leave exactly the codeblock results and
+    HARQ soft bits of decoding the descrambled UL-SCH streams directly."""
+    rng = np.random.default_rng(qm * 10 + nl)
+    base = dict(qm=qm, nof_layers=nl, nof_prb=nprb, start_symbol_index=0, nof_symbols=14, dmrs_type=1,
+                dmrs_symbol_mask=1 << 2, nof_cdm_groups_without_data=2)
+    cfgs = [dict(base), dict(base, nof_csi_part1_bits=7, nof_enc_csi_part1_bits=30 * qm * nl)]
+    bg = 1 if rate > 0.3 else 2
+    state = []
+    for k, cfg in enumerate(cfgs):
+        n = orc.ulsch_codeword_length(cfg)
+        src = source_index_of_sch(orc, cfg, n)
+        n_sch = src.size
+        tbs_bits = max(24, int(n_sch * rate) // 8 * 8)
+        if bg == 2:
+            tbs_bits = min(tbs_bits, 3824)
+        C = ldpc.compute_nof_codeblocks(tbs_bits, bg)
+        tb = rng.integers(0, 256, tbs_bits // 8).astype(np.uint8)
+        state.append(dict(cfg=cfg, n=n, src=src, n_sch=n_sch, tbs_bits=tbs_bits, C=C, tb=tb,
+                          c_init=int(rng.integers(0, 1 << 31))))
+    first_id = {0: 300, 1: 700}  # HARQ entries of the chain / of the direct decode
+    for tx, rv in enumerate([0, 2]):
+        raws, schs, cws, cb_chain, cb_direct = [], [], [], [], []
+        in_off = sch_off = uci_off = cb_pos = 0
+        for k, st in enumerate(state):
+            sch_llr, _ = make_tb_llrs(orc, st["tb"], bg, rv, qm, 0, nl, st["n_sch"], 2.0 + 6 * rate, rng)
+            llr = rng.integers(-100, 101, st["n"]).astype(np.int8)
+            llr[st["src"]] = sch_llr
+            seq = orc.prg_bits(st["c_init"], 0, st["n"])
+            rc, outs = orc.ulsch_demux(st["cfg"], llr, seq)
+            assert rc == 0 and (outs[0] == sch_llr).all()
+            raws.append(orc.revert_scrambling(llr, seq))
+            schs.append((sch_off, sch_llr))
+            cws.append(cw_desc(st["cfg"], in_off, sch_off, uci_off, st["c_init"],
+                               capi.CW_SCRAMBLED | capi.CW_DEFER_DESCRAMBLING))
+            flags = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_EARLY_STOP | (capi.CB_NEW_DATA if tx == 0 else 0)
+            for i, m in enumerate(ldpc.segment_rx(st["tbs_bits"], bg, rv, qm, 0, nl, st["n_sch"])):
+                crc = capi.CRC24B if st["C"] > 1 else (capi.CRC24A if st["tbs_bits"] > 3824 else capi.CRC16)
+                row = (sch_off + m.cw_offset, m.rm_length, 0, 0, m.lifting_size, m.nof_filler_bits, bg, qm, rv, crc, 6,
+                       flags, 0xffff)
+                cb_chain.append((row, first_id[0] + cb_pos))
+                cb_direct.append((row, first_id[1] + cb_pos))
+                cb_pos += 1
+            in_off += st["n"]
+            sch_off += (st["n_sch"] + 15) // 16 * 16
+            uci_off += 4096
+        def descs(rows):
+            a = np.zeros(len(rows), capi.CB_DESC_DTYPE)
+            for i, (row, hid) in enumerate(rows):
+                a[i] = row
+                a[i]["harq_id"] = hid
+            return a
+        raw = np.concatenate(raws)
+        ctx.submit_codewords(np.array(cws), raw, stream=0)
+        ctx.submit(descs(cb_chain), None, stream=0)
+        chain = ctx.wait(0)
+        sch_space = np.zeros(sch_off, np.int8)
+        for off, v in schs:
+            sch_space[off:off + v.size] = v
+        ctx.submit(descs(cb_direct), sch_space, stream=1)
+        direct = ctx.wait(1)
+        assert (chain["cb_results"] == direct["cb_results"]).all(), (tx, chain["cb_results"], direct["cb_results"])
+        assert (chain["cb_bits"] == direct["cb_bits"]).all()
+        for i in range(cb_pos):
+            assert (ctx.harq_read(first_id[0] + i) == ctx.harq_read(first_id[1] + i)).all(), (tx, i)
+    assert chain["cb_results"]["crc_ok"].all()
