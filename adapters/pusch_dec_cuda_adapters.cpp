@@ -21,6 +21,12 @@ static int to_crc_kind(crc_generator_poly poly)
       return PDC_CRC24A;
     case crc_generator_poly::CRC24B:
       return PDC_CRC24B;
+    case crc_generator_poly::CRC24C:
+      return PDC_CRC24C;
+    case crc_generator_poly::CRC11:
+      return PDC_CRC11;
+    case crc_generator_poly::CRC6:
+      return PDC_CRC6;
     default:
       return -1;
   }

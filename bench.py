@@ -101,6 +101,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pin_to_gpu_numa_node(torch, device):
+    """One process per GPU: run on the CPUs next to the GPU (and, by first touch, allocate the pinned LLR buffers in that
+    NUMA node's memory) so that the H2D streams of the ranks do not all cross the same socket link. Best effort."""
+    try:
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = torch.cuda.get_device_properties(device).pci_domain_id
+        dev = torch.cuda.get_device_properties(device).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus near %s" % (len(cpus), path.split("/")[5])
+    except (OSError, ValueError, AttributeError):
+        pass
+    return None
+
+
 def synth_batch(orc, n_distinct, n_cb, snr_db, seed):
     """n_cb x E int8 LLRs: n_distinct different noisy codewords tiled (distinct addresses, inputs larger than L2)."""
     from tests.vectors import make_cb_batch
@@ -317,6 +338,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl cuda needs a GPU (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -469,7 +491,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3,
-                "h2d_gbs_achieved": h2d * args.steps / e2e_s / 1e9, "h2d_gbs_plain_copy": link_gbs},
+                "h2d_gbs_achieved": h2d * args.steps / e2e_s / 1e9, "h2d_gbs_plain_copy": link_gbs,
+                "host_affinity": numa},
         "gpu_launches": launches,
     }
 

@@ -44,6 +44,10 @@ extern "C" {
 #define PDC_CRC16 1
 #define PDC_CRC24A 2
 #define PDC_CRC24B 3
+/* The remaining NR polynomials, accepted by pdc_crc only (crc_calculator.h:35-48). */
+#define PDC_CRC24C 4
+#define PDC_CRC11 5
+#define PDC_CRC6 6
 
 /* Check-to-variable scaling rule = which reference decoder variant is reproduced bit for bit. */
 #define PDC_SCALE_X86 0     /* ldpc_decoder_avx2 / ldpc_decoder_avx512 ("auto" on any x86 host) - default */

@@ -89,6 +89,18 @@ static void crc_params(int kind, uint32_t* poly, int* order)
       *poly  = 0x1864CFB;
       *order = 24;
       break;
+    case ORC_CRC24C:
+      *poly  = 0x1B2B117;
+      *order = 24;
+      break;
+    case ORC_CRC11:
+      *poly  = 0xE21;
+      *order = 11;
+      break;
+    case ORC_CRC6:
+      *poly  = 0x61;
+      *order = 6;
+      break;
     default:
       *poly  = 0x1800063;
       *order = 24;

@@ -30,6 +30,9 @@ extern "C" {
 #define ORC_CRC16 1
 #define ORC_CRC24A 2
 #define ORC_CRC24B 3
+#define ORC_CRC24C 4 /* the remaining polynomials of crc_calculator.h:35-48, for the stand-alone CRC only */
+#define ORC_CRC11 5
+#define ORC_CRC6 6
 
 /* crc_calculator::calculate - lib/phy/upper/channel_coding/crc_calculator_generic_impl.cpp:111-133.
  * Remainder of the first nbits (MSB first) of packed[] followed by `order` zero bits. */

@@ -19,6 +19,7 @@ ORACLE_SO = REF_DIR / "liboracle.so"
 REFERENCE_SO = REF_DIR / "libsrsref.so"
 
 CRC_NONE, CRC16, CRC24A, CRC24B = 0, 1, 2, 3
+CRC24C, CRC11, CRC6 = 4, 5, 6
 SCALE_X86, SCALE_GENERIC, SCALE_NEON = 0, 1, 2
 MAX_CB_SIZE = 66 * 384
 MAX_CB_BYTES = 22 * 384 // 8
@@ -76,9 +77,17 @@ def ulsch_cfg_array(cfg):
     return np.array([int(cfg.get(k, 0)) for k in ULSCH_CFG_FIELDS], np.int32)
 
 
+def _oracle_stale():
+    """The shared object is missing or older than the C source it is compiled from."""
+    if not ORACLE_SO.exists():
+        return True
+    t = ORACLE_SO.stat().st_mtime
+    return any((HERE / f).stat().st_mtime > t for f in ("pusch_oracle.c", "pusch_oracle.h", "bg_tables.inc"))
+
+
 class Oracle:
     def __init__(self):
-        if not ORACLE_SO.exists():
+        if _oracle_stale():
             build_oracle()
         L = ctypes.CDLL(str(ORACLE_SO))
         L.orc_crc.restype = ctypes.c_uint32

@@ -37,12 +37,18 @@ namespace {
 
 crc_generator_poly to_poly(int crc_kind)
 {
-  // 1 = CRC16, 2 = CRC24A, 3 = CRC24B.
+  // 1 = CRC16, 2 = CRC24A, 3 = CRC24B, 4 = CRC24C, 5 = CRC11, 6 = CRC6.
   switch (crc_kind) {
     case 1:
       return crc_generator_poly::CRC16;
     case 2:
       return crc_generator_poly::CRC24A;
+    case 4:
+      return crc_generator_poly::CRC24C;
+    case 5:
+      return crc_generator_poly::CRC11;
+    case 6:
+      return crc_generator_poly::CRC6;
     default:
       return crc_generator_poly::CRC24B;
   }
@@ -73,7 +79,7 @@ bit_buffer view_bits(uint8_t* ptr, unsigned nbits)
 struct cb_tools {
   std::unique_ptr<ldpc_decoder>        dec;
   std::unique_ptr<ldpc_rate_dematcher> dem;
-  std::unique_ptr<crc_calculator>      crc[4];
+  std::unique_ptr<crc_calculator>      crc[7];
 };
 
 std::unique_ptr<cb_tools> make_tools(const char* type)
@@ -87,7 +93,7 @@ std::unique_ptr<cb_tools> make_tools(const char* type)
   }
   t->dec = dec_f->create();
   t->dem = dem_f->create();
-  for (int k = 1; k <= 3; ++k) {
+  for (int k = 1; k <= 6; ++k) {
     t->crc[k] = crc_f->create(to_poly(k));
   }
   return t;

@@ -16,6 +16,7 @@ PDC_ERR_INVALID, PDC_ERR_CUDA, PDC_ERR_CAPACITY, PDC_ERR_NO_DEVICE = -1, -2, -3,
 PDC_MAX_CB_SOFT = 25344
 PDC_MAX_CB_BYTES = 1056
 CRC_NONE, CRC16, CRC24A, CRC24B = 0, 1, 2, 3
+CRC24C, CRC11, CRC6 = 4, 5, 6  # pdc_crc only
 SCALE_X86, SCALE_GENERIC, SCALE_NEON = 0, 1, 2
 CB_NEW_DATA, CB_EARLY_STOP, CB_DECODE, CB_DEMATCH = 1, 2, 4, 8
 

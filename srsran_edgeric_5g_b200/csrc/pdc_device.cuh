@@ -39,6 +39,18 @@ __host__ __device__ inline int crc_order(int kind)
   return (kind == PDC_CRC16) ? 16 : 24;
 }
 
+// All six NR generator polynomials (crc_calculator.h:35-48) for the stand-alone CRC call; codeblocks and transport blocks
+// only use the first three.
+constexpr int CRC_KINDS = 6;
+__host__ __device__ inline uint32_t crc_poly_any(int kind)
+{
+  return (kind == PDC_CRC24C) ? 0x1B2B117u : (kind == PDC_CRC11) ? 0xE21u : (kind == PDC_CRC6) ? 0x61u : crc_poly(kind);
+}
+__host__ __device__ inline int crc_order_any(int kind)
+{
+  return (kind == PDC_CRC24C) ? 24 : (kind == PDC_CRC11) ? 11 : (kind == PDC_CRC6) ? 6 : crc_order(kind);
+}
+
 // (W(x) * A(x)) mod P, W of degree < 32, A of degree < order.
 __host__ __device__ inline uint32_t gf2_mulmod(uint32_t w, uint32_t a, uint32_t poly, int order)
 {

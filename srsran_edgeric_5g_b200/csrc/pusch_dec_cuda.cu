@@ -269,7 +269,7 @@ cudaError_t host_alloc(T** p, size_t n)
 }
 
 // Generic CRC of a packed bit string (compatibility API, not a hot path).
-__constant__ uint32_t c_xpow2[3][24]; // x^(2^i) mod P
+__constant__ uint32_t c_xpow2[pdc::CRC_KINDS][24]; // x^(2^i) mod P
 
 __global__ void crc_kernel(const uint8_t* packed, uint32_t nbits, int kind, uint32_t* out)
 {
@@ -278,8 +278,8 @@ __global__ void crc_kernel(const uint8_t* packed, uint32_t nbits, int kind, uint
     sh = 0;
   }
   __syncthreads();
-  const uint32_t poly   = pdc::crc_poly(kind);
-  const int      order  = pdc::crc_order(kind);
+  const uint32_t poly   = pdc::crc_poly_any(kind);
+  const int      order  = pdc::crc_order_any(kind);
   const uint32_t n_full = nbits / 32u;
   const uint32_t rem    = nbits & 31u;
   const uint32_t T      = n_full + (rem ? 1u : 0u);
@@ -354,10 +354,10 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters)
 
 cudaError_t upload_crc_tables()
 {
-  uint32_t h[3][24];
-  for (int k = 0; k != 3; ++k) {
-    uint32_t poly  = pdc::crc_poly(k + 1);
-    int      order = pdc::crc_order(k + 1);
+  uint32_t h[pdc::CRC_KINDS][24];
+  for (int k = 0; k != pdc::CRC_KINDS; ++k) {
+    uint32_t poly  = pdc::crc_poly_any(k + 1);
+    int      order = pdc::crc_order_any(k + 1);
     uint32_t x     = 2; // x^1
     for (int i = 0; i != 24; ++i) {
       h[k][i] = x;
@@ -1220,7 +1220,7 @@ int pdc_scrambling_sequence(pdc_ctx* ctx, uint32_t c_init, uint32_t offset, uint
 
 int pdc_crc(pdc_ctx* ctx, int crc_kind, const uint8_t* packed, uint32_t nbits, uint32_t* checksum)
 {
-  if (!ctx || !packed || !checksum || crc_kind < PDC_CRC16 || crc_kind > PDC_CRC24B ||
+  if (!ctx || !packed || !checksum || crc_kind < PDC_CRC16 || crc_kind > PDC_CRC6 ||
       (nbits + 7) / 8 > ctx->scratch_llr_bytes) {
     return fail(PDC_ERR_INVALID, "pdc_crc: invalid argument");
   }

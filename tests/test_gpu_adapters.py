@@ -20,3 +20,30 @@ def test_reference_hw_decoder_front_end_on_cuda_accelerator():
     print(out.stdout[-3000:])
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "PASS" in out.stdout
+
+
+# ---- the reference's OWN harnesses on the "cuda" variants (integration/Makefile) ------------------------------------------
+HARNESS = Path(__file__).resolve().parent.parent / "integration" / "_build"
+
+
+def test_reference_crc_calculator_test_with_cuda_factory():
+    """tests/unittests/phy/upper/channel_coding/crc_calculator_test.cpp of the reference, unmodified, `-F cuda`: all six
+    generator polynomials, byte / bit / bit-buffer interfaces, against its own bit-serial model."""
+    exe = HARNESS / "crc_calculator_test"
+    if not exe.exists():
+        pytest.skip("integration/_build not built (needs /root/reference at build time)")
+    out = subprocess.run([str(exe), "-F", "cuda"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_reference_ldpc_decoder_benchmark_with_cuda_factory():
+    """tests/benchmarks/phy/upper/channel_coding/ldpc/ldpc_decoder_benchmark.cpp of the reference, unmodified,
+    `-T cuda`: create_ldpc_decoder_factory_sw("cuda") hands out the GPU decoder and the benchmark runs to completion
+    (encoded codeblocks with CRC16, both base graphs)."""
+    exe = HARNESS / "ldpc_decoder_benchmark"
+    if not exe.exists():
+        pytest.skip("integration/_build not built (needs /root/reference at build time)")
+    out = subprocess.run([str(exe), "-T", "cuda", "-L", "96", "-I", "6", "-C", "-R", "20"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "LDPC decoder cuda" in out.stdout and "BG=2 LS=96" in out.stdout

@@ -112,7 +112,7 @@ def test_rate_dematcher_random(ctx, orc):
 
 def test_crc(ctx, orc):
     rng = np.random.default_rng(6)
-    for kind in (po.CRC16, po.CRC24A, po.CRC24B):
+    for kind in (po.CRC16, po.CRC24A, po.CRC24B, po.CRC24C, po.CRC11, po.CRC6):
         for n in (1, 7, 8, 24, 31, 32, 33, 100, 1000, 8448, 30000, 1277992):
             d = rng.integers(0, 256, (n + 7) // 8 + 1).astype(np.uint8)
             assert ctx.crc(kind, d, n) == orc.crc(kind, d, n), (kind, n)

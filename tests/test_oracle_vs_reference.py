@@ -13,7 +13,7 @@ pytestmark = pytest.mark.skipif(not po.Reference.available(), reason="oracle/_re
 def test_crc(orc):
     ref = po.Reference("auto")
     rng = np.random.default_rng(1)
-    for kind in (po.CRC16, po.CRC24A, po.CRC24B):
+    for kind in (po.CRC16, po.CRC24A, po.CRC24B, po.CRC24C, po.CRC11, po.CRC6):
         for n in (1, 7, 8, 24, 25, 100, 1000, 8448, 30000):
             d = rng.integers(0, 256, (n + 7) // 8 + 1).astype(np.uint8)
             assert orc.crc(kind, d, n) == ref.crc(kind, d, n)
