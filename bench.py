@@ -303,12 +303,59 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
             deferred_ok = bool(tres["tb_crc_ok"].all()) and bool((d_tb.cpu().numpy()[:tbs_bits // 8] == tb).all()) and \
                 not bool(d_sch2.any().item())  # the UL-SCH space was never written
             fe_bytes = 2 * cells * n_llr + cells * n_llr // 8 * 2  # soft bits in + out, sequence written + read
+            # ---- the same slot end to end through the C ABI with HOST buffers: scrambled codewords in page-locked memory
+            # -> pdc_submit_codewords + pdc_submit (two slots in flight) -> TB bytes back in page-locked memory.
+            e2e = None
+            if cells > 1 or True:
+                NQ = 3  # slots in flight: the copy in of slot k+1/k+2 hides behind the kernels of slot k
+                ctx3 = capi.Context(device=torch.cuda.current_device(), max_cbs=n_cb, max_llrs=cells * n_llr + 64,
+                                    harq_entries=NQ * n_cb, max_tbs=cells, max_tb_bytes=cells * tb_stride + 64,
+                                    nof_streams=NQ)
+                raw_pin = [capi.PinnedBuffer(cells * n_llr) for _ in range(NQ)]
+                bits_pin = [capi.PinnedBuffer(n_cb * capi.PDC_MAX_CB_BYTES, np.uint8) for _ in range(NQ)]
+                tb_pin = [capi.PinnedBuffer(cells * tb_stride + 64, np.uint8) for _ in range(NQ)]
+                for b in raw_pin:
+                    b.array[:] = np.concatenate(raws)
+                cbs_q = []
+                for q in range(NQ):
+                    c2 = cbs.copy()
+                    c2["harq_id"] += q * n_cb
+                    cbs_q.append(c2)
+
+                def slot(i):
+                    q = i % NQ
+                    ctx3.submit_codewords(cws_def, raw_pin[q].array, stream=q)
+                    return ctx3.submit(cbs_q[q], None, tbd, stream=q, out_bits=bits_pin[q].array, out_tb=tb_pin[q].array)
+
+                def run(n):
+                    last = None
+                    for i in range(n):
+                        if i >= NQ:
+                            ctx3.wait(i % NQ)
+                        slot(i)
+                    for i in range(n, n + NQ):
+                        r = ctx3.wait(i % NQ)
+                        last = r if r is not None else last
+                    return last
+
+                run(2 * NQ + 4)
+                n_slots = 40
+                t0 = time.perf_counter()
+                last = run(n_slots)
+                t1 = time.perf_counter()
+                us_e2e = (t1 - t0) / n_slots * 1e6
+                e2e = {"us_per_slot": us_e2e, "value": cells * tbs_bits / (us_e2e * 1e-6) / 1e9, "unit": UNIT,
+                       "h2d_bytes_per_slot": cells * n_llr + n_cb * 28 + cells * 60,
+                       "d2h_bytes_per_slot": n_cb * (capi.PDC_MAX_CB_BYTES + 4) + cells * tb_stride,
+                       "slots_in_flight": NQ, "tb_crc_ok": bool(last["tb_results"]["tb_crc_ok"].all()),
+                       "tb_bytes_match": bool((last["tb_bytes"][:tbs_bits // 8] == tb).all())}
+                ctx3.close()
             out[f"{name}_front_end"] = {
                 "us_front_end": times["front_end"], "us_per_slot_with_front_end": times["chain"],
                 "front_end_gbs": fe_bytes / (times["front_end"] * 1e-6) / 1e9, "front_end_bytes": fe_bytes,
                 "us_per_slot_with_deferred_descrambling": times["chain_deferred"], "deferred_chain_ok": deferred_ok,
                 "descrambled_equals_input": same, "tb_crc_ok": bool(tres["tb_crc_ok"].all()),
-                "kernels": "prg_kernel + ulsch_sch_kernel (no UCI in this slot)"}
+                "kernels": "prg_kernel + ulsch_sch_kernel (no UCI in this slot)", "e2e_host_buffers": e2e}
     return out
 
 

@@ -256,7 +256,12 @@ class Context:
         cws = np.ascontiguousarray(cws, CW_DESC_DTYPE)
         assert raw_llrs.dtype == np.int8 and raw_llrs.flags.c_contiguous
         res = np.zeros(cws.size, CW_RESULT_DTYPE)
-        uci = out_uci if out_uci is not None else np.zeros(max(1, raw_llrs.size), np.int8)
+        if out_uci is None:
+            # UCI area: the codewords' UCI soft bits back to back from their uci_offset.
+            need = int((cws["uci_offset"].astype(np.int64) + cws["nof_enc_harq_ack_bits"] + cws["nof_enc_csi_part1_bits"] +
+                        cws["nof_enc_csi_part2_bits"]).max()) if cws.size else 0
+            out_uci = np.zeros(max(1, need), np.int8)
+        uci = out_uci
         check(self._L.pdc_submit_codewords(self.h, stream, _ptr(cws), cws.size, _ptr(raw_llrs), raw_llrs.size, _ptr(uci),
                                            uci.size, _ptr(res)))
         fe = {"cws": cws, "raw_llrs": raw_llrs, "cw_results": res, "uci": uci}

@@ -66,6 +66,12 @@ struct FrontEnd {
   const int8_t*        deferred_sch = nullptr;
   uint4*               d_cb_scr = nullptr;
   size_t               cb_scr_cap = 0;
+  // Kernels of the last plan (launched right away, or - for the queued interface - after the descriptor uploads of the
+  // decode batch so that all host-to-device copies of a slot are issued back to back).
+  pdc::UlschArgs       args = {};
+  uint32_t             k_n_cw = 0, k_max_in = 0, k_max_sch = 0, k_max_uci = 0;
+  bool                 k_all_deferred = false, k_generate_seq = false, kernels_pending = false;
+  int8_t*              uci_copy_dst = nullptr; // host destination of the UCI soft bits once the kernels are queued
   // Pending results of the queue.
   int8_t*              u_uci = nullptr;
   size_t               uci_bytes = 0;
@@ -564,6 +570,8 @@ void pdc_host_free(void* p)
   }
 }
 
+static int front_end_kernels(pdc_ctx* ctx, FrontEnd& fe, cudaStream_t s);
+
 // Page-locked host memory (pdc_host_alloc, cudaHostAlloc, cudaHostRegister) can be the target of an asynchronous copy.
 static bool is_pinned_host(const void* p)
 {
@@ -635,6 +643,12 @@ int pdc_submit(pdc_ctx*           ctx,
   }
   // Codeblocks that are not decoded report "not run".
   PDC_CUDA(cudaMemsetAsync(q.d_cb_res, 0, sizeof(pdc_cb_result) * n_cb, q.stream));
+  if (q.fe.pending) {
+    int rc_fe = front_end_kernels(ctx, q.fe, q.stream);
+    if (rc_fe != PDC_OK) {
+      return rc_fe;
+    }
+  }
   int rc = launch_batch(ctx, q.d_cbs, n_cb, q.d_llrs, q.d_tbs, n_tb, q.d_cb_res, q.d_cb_bits, q.d_tb_res, q.d_tb_out,
                         shape, nullptr, 0, q.stream, q.d_tb_sync, q.fe.pending ? &q.fe : nullptr);
   if (rc != PDC_OK) {
@@ -670,6 +684,42 @@ int pdc_submit(pdc_ctx*           ctx,
 
 // ---- codeword front end ------------------------------------------------------------------------------------------------
 
+// Queues the kernels of the plan front_end_launch prepared (and the copy of the UCI soft bits to the host).
+static int front_end_kernels(pdc_ctx* ctx, FrontEnd& fe, cudaStream_t s)
+{
+  if (!fe.kernels_pending) {
+    return PDC_OK;
+  }
+  fe.kernels_pending       = false;
+  const pdc::UlschArgs& a  = fe.args;
+  const uint32_t        n_cw = fe.k_n_cw;
+  if (fe.k_generate_seq) {
+    const uint32_t per_cta = 128 * pdc::PRG_WORDS_PER_THREAD;
+    dim3           grid(((fe.k_max_in + 31) / 32 + per_cta - 1) / per_cta, n_cw);
+    pdc::prg_kernel<<<grid, 128, 0, s>>>(a.cws, fe.d_seq);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (!fe.k_all_deferred) {
+    // Enough CTAs to fill the GPU a few times over; each thread steps through the chunks of its codeword.
+    const uint32_t chunks = (fe.k_max_sch + 15) / 16;
+    uint32_t       gx = std::max(1u, std::min((chunks + 255) / 256, (uint32_t)(8 * ctx->sm_count + n_cw - 1) / n_cw));
+    pdc::ulsch_sch_kernel<<<dim3(gx, n_cw), 256, 0, s>>>(a);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (fe.k_max_uci != 0) {
+    pdc::ulsch_uci_kernel<<<dim3((fe.k_max_uci + 255) / 256, n_cw), 256, 0, s>>>(a);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (fe.uci_copy_dst != nullptr && fe.uci_bytes != 0) {
+    PDC_CUDA(cudaMemcpyAsync(fe.uci_copy_dst, fe.d_uci, fe.uci_bytes, cudaMemcpyDeviceToHost, s));
+  }
+  fe.uci_copy_dst = nullptr;
+  return PDC_OK;
+}
+
 // Plans the codewords, uploads the plan and queues the kernels on stream s:
 //   d_in (raw soft bits, already on the device) -> d_sch (UL-SCH space) and fe.d_uci (UCI area of n_uci bytes).
 // seq_words != nullptr: caller-supplied scrambling sequence (fe.plan layout), else generated from c_init.
@@ -685,7 +735,8 @@ static int front_end_launch(pdc_ctx*           ctx,
                             const uint8_t*     seq_bits_packed,
                             pdc_cw_result*     results,
                             cudaStream_t       s,
-                            int8_t*            d_uci_user = nullptr)
+                            int8_t*            d_uci_user = nullptr,
+                            bool               launch_now = true)
 {
   pdc::UlschPlan& plan = fe.plan;
   plan.clear();
@@ -749,7 +800,7 @@ static int front_end_launch(pdc_ctx*           ctx,
     PDC_CUDA(grow_device(&fe.d_uci, &fe.uci_cap, uci_end));
     PDC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&fe.h_uci), fe.uci_cap));
   }
-  pdc::UlschArgs a;
+  pdc::UlschArgs& a = fe.args;
   a.cws   = reinterpret_cast<const pdc::UlschCodeword*>(fe.d_plan);
   a.syms  = reinterpret_cast<const pdc::UlschSymbol*>(fe.d_plan + b_cws);
   a.lists = reinterpret_cast<const uint16_t*>(fe.d_plan + b_cws + b_syms);
@@ -776,32 +827,23 @@ static int front_end_launch(pdc_ctx*           ctx,
     }
     PDC_CUDA(cudaMemcpyAsync(fe.d_seq, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     PDC_CUDA(cudaStreamSynchronize(s)); // `words` goes out of scope
-  } else {
-    const uint32_t per_cta = 128 * pdc::PRG_WORDS_PER_THREAD;
-    dim3           grid(((max_in + 31) / 32 + per_cta - 1) / per_cta, n_cw);
-    pdc::prg_kernel<<<grid, 128, 0, s>>>(a.cws, fe.d_seq);
-    PDC_CUDA(cudaGetLastError());
-    ctx->launches++;
   }
-  if (!all_deferred) {
-    // Enough CTAs to fill the GPU a few times over; each thread steps through the words of its codeword.
-    const uint32_t chunks = (max_sch + 15) / 16;
-    uint32_t       gx = std::max(1u, std::min((chunks + 255) / 256, (uint32_t)(8 * ctx->sm_count + n_cw - 1) / n_cw));
-    pdc::ulsch_sch_kernel<<<dim3(gx, n_cw), 256, 0, s>>>(a);
-    PDC_CUDA(cudaGetLastError());
-    ctx->launches++;
-  }
-  if (max_uci != 0) {
-    pdc::ulsch_uci_kernel<<<dim3((max_uci + 255) / 256, n_cw), 256, 0, s>>>(a);
-    PDC_CUDA(cudaGetLastError());
-    ctx->launches++;
-  }
+  fe.k_n_cw          = n_cw;
+  fe.k_max_in        = max_in;
+  fe.k_max_sch       = max_sch;
+  fe.k_max_uci       = max_uci;
+  fe.k_all_deferred  = all_deferred;
+  fe.k_generate_seq  = seq_bits_packed == nullptr;
+  fe.kernels_pending = true;
   fe.uci_bytes     = uci_end;
   fe.sch_len       = (uint32_t)sch_end;
   fe.deferred      = any_deferred;
   fe.deferred_n_cw = n_cw;
   fe.deferred_in   = d_in;
   fe.deferred_sch  = d_sch;
+  if (launch_now) {
+    return front_end_kernels(ctx, fe, s);
+  }
   return PDC_OK;
 }
 
@@ -825,17 +867,19 @@ int pdc_submit_codewords(pdc_ctx*           ctx,
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   PDC_CUDA(grow_device(&q.fe.d_raw, &q.fe.raw_cap, n_raw + 16));
   PDC_CUDA(cudaMemcpyAsync(q.fe.d_raw, raw_llrs, n_raw, cudaMemcpyHostToDevice, q.stream));
+  // The kernels are queued by the pdc_submit that follows (after its descriptor uploads) or, failing that, by pdc_wait:
+  // a kernel between two host-to-device copies of one stream would hold back the copies of the next slot.
   int rc = front_end_launch(ctx, q.fe, cws, n_cw, n_raw, q.fe.d_raw, q.d_llrs, ctx->cfg.max_llrs,
-                            uci_out ? uci_capacity : (size_t)-1, nullptr, results, q.stream);
+                            uci_out ? uci_capacity : (size_t)-1, nullptr, results, q.stream, nullptr, false);
   if (rc != PDC_OK) {
     return rc;
   }
-  q.fe.u_uci = nullptr;
+  q.fe.u_uci        = nullptr;
+  q.fe.uci_copy_dst = nullptr;
   if (uci_out && q.fe.uci_bytes != 0) {
     const bool direct = is_pinned_host(uci_out);
-    PDC_CUDA(cudaMemcpyAsync(direct ? uci_out : q.fe.h_uci, q.fe.d_uci, q.fe.uci_bytes, cudaMemcpyDeviceToHost,
-                             q.stream));
-    q.fe.u_uci = direct ? nullptr : uci_out;
+    q.fe.uci_copy_dst = direct ? uci_out : q.fe.h_uci;
+    q.fe.u_uci        = direct ? nullptr : uci_out;
   }
   q.fe.pending = true;
   return PDC_OK;
@@ -850,7 +894,11 @@ int pdc_wait(pdc_ctx* ctx, uint32_t stream)
   if (!q.busy && !q.fe.pending) {
     return PDC_OK;
   }
-  // A front end without a decode batch behind it has no event: wait for the stream.
+  // A front end without a decode batch behind it: its kernels are still to be queued, and there is no event.
+  if (q.fe.pending && q.fe.kernels_pending) {
+    cudaSetDevice(ctx->cfg.device);
+    front_end_kernels(ctx, q.fe, q.stream);
+  }
   cudaError_t e = q.busy ? cudaEventSynchronize(q.done) : cudaStreamSynchronize(q.stream);
   if (q.fe.pending) {
     q.fe.pending = false;
