@@ -15,6 +15,14 @@
  *   hal::hw_accelerator<int8_t,uint8_t>   include/srsran/hal/hw_accelerator.h:35-57
  *   pusch_decoder (batched)               include/srsran/phy/upper/channel_processors/pusch/pusch_decoder.h:54-99
  *   rx_buffer (HARQ state)                include/srsran/phy/upper/rx_buffer.h:42-81
+ *   ulsch_demultiplex / pusch_codeword_buffer (codeword front end)
+ *                                         include/srsran/phy/upper/channel_processors/pusch/ulsch_demultiplex.h:41-103,
+ *                                         include/srsran/phy/upper/channel_processors/pusch/pusch_codeword_buffer.h
+ *   pseudo_random_generator::generate     include/srsran/phy/upper/sequence_generators/pseudo_random_generator.h
+ *
+ * Threading: a context serialises nothing itself. Each queue ("stream") may be driven by one thread at a time; the
+ * synchronous single-object calls (pdc_ldpc_decode, pdc_rate_dematch, pdc_crc, pdc_ulsch_demux, pdc_scrambling_sequence,
+ * pdc_launch_codewords_device) share queue 0 / one set of scratch buffers and must not run concurrently with each other.
  *
  * INTEGRATION.md shows the C++ adapter classes that bind these calls behind create_ldpc_decoder_factory_sw("cuda"),
  * create_ldpc_rate_dematcher_factory_sw("cuda") and the hal::hw_accelerator_pusch_dec factory.
