@@ -336,7 +336,7 @@ __host__ __device__ inline size_t h2_smem_bytes(int bg, int Z)
 
 template <int MAX_THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
-    ldpc_decode_h2_kernel(BatchParams prm, hh* state_scratch, uint32_t scratch_stride_words)
+    ldpc_decode_h2_kernel(BatchParams prm, hh* state_scratch, uint32_t scratch_stride_words, uint32_t* work_counter)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ LaneInfo lane[2];
@@ -347,14 +347,17 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
   __shared__ int                sh_publish[2];
   __shared__ pdc_cb_result      sh_result[2];
   __shared__ int      sh_defer_b; // codeblock B could not be decoded together with A: it gets its own pass
+  __shared__ uint32_t sh_next_pair;
 
   const int tid  = threadIdx.x;
   const int nthr = blockDim.x;
 
   // Persistent CTAs: pair p = codeblocks 2p and 2p+1 of the batch. They are decoded together when they share the lifted
   // graph, the iteration count and the number of rows in use; otherwise one after the other.
+  // The first pair of a CTA is its index; further pairs come from a counter, so that CTAs whose codeblocks stopped early
+  // take over work from those still iterating.
   const uint32_t n_pairs = (prm.n_cb + 1) / 2;
-  for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+  for (uint32_t pair = blockIdx.x; pair < n_pairs;) {
     for (int pass = 0; pass != 2; ++pass) {
       const uint32_t cb0 = 2 * pair;
       __syncthreads();
@@ -747,6 +750,12 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         }
       }
     }
+    __syncthreads();
+    if (tid == 0) {
+      sh_next_pair = gridDim.x + atomicAdd(work_counter, 1u);
+    }
+    __syncthreads();
+    pair = sh_next_pair;
   }
 }
 
@@ -761,7 +770,7 @@ struct H2Plan {
   bool   big; // the 384-thread instantiation (two CTAs per SM)
 };
 
-typedef void (*h2_kernel_t)(BatchParams, uint32_t*, uint32_t);
+typedef void (*h2_kernel_t)(BatchParams, uint32_t*, uint32_t, uint32_t*);
 
 inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count, H2Plan& plan)
 {
@@ -794,14 +803,16 @@ inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count,
   return cudaSuccess;
 }
 
-inline cudaError_t launch_ldpc_decode_h2(const BatchParams& p, const H2Plan& plan, uint32_t* scratch, cudaStream_t s)
+// work_counter: one zeroed uint32 per launch (pairs beyond the first of every CTA are handed out through it).
+inline cudaError_t launch_ldpc_decode_h2(const BatchParams& p, const H2Plan& plan, uint32_t* scratch,
+                                         uint32_t* work_counter, cudaStream_t s)
 {
   if (plan.big) {
     h2::ldpc_decode_h2_kernel<384, 2>
-        <<<plan.grid, plan.threads, plan.smem, s>>>(p, scratch, (uint32_t)plan.scratch_words_per_cta);
+        <<<plan.grid, plan.threads, plan.smem, s>>>(p, scratch, (uint32_t)plan.scratch_words_per_cta, work_counter);
   } else {
     h2::ldpc_decode_h2_kernel<192, 4>
-        <<<plan.grid, plan.threads, plan.smem, s>>>(p, scratch, (uint32_t)plan.scratch_words_per_cta);
+        <<<plan.grid, plan.threads, plan.smem, s>>>(p, scratch, (uint32_t)plan.scratch_words_per_cta, work_counter);
   }
   return cudaGetLastError();
 }

@@ -125,8 +125,15 @@ struct pdc_ctx {
   std::vector<Queue>   queues;
   std::atomic<uint64_t> launches{0};
   bool                 force_scalar = false;      // PDC_FORCE_SCALAR=1: use the general kernel for every batch
-  uint32_t*            d_state_scratch = nullptr; // compressed check-to-variable messages of the resident CTAs
-  size_t               state_scratch_words = 0;
+  // Compressed check-to-variable messages of the resident CTAs + the work counter of the persistent decoder, ONE SET
+  // PER CUDA STREAM: decoder launches of different streams may overlap at their tails and must not share scratch.
+  struct DecodeScratch {
+    cudaStream_t stream  = nullptr;
+    uint32_t*    d_state = nullptr;
+    size_t       words   = 0;
+    uint32_t*    d_counter = nullptr;
+  };
+  std::vector<DecodeScratch> decode_scratch;
   FrontEnd             fe_sync;                   // buffers of the synchronous front-end calls
   int8_t*              d_sch_sync = nullptr;
   size_t               sch_sync_cap = 0;
@@ -229,17 +236,31 @@ int launch_batch(pdc_ctx*             ctx,
       pdc::H2Plan plan;
       PDC_CUDA(pdc::h2_plan(shape.max_Z, shape.any_bg1, n_cb, ctx->sm_count, plan));
       size_t need = plan.scratch_words_per_cta * (size_t)plan.grid;
-      if (need > ctx->state_scratch_words) {
+      pdc_ctx::DecodeScratch* sc = nullptr;
+      for (pdc_ctx::DecodeScratch& c : ctx->decode_scratch) {
+        if (c.stream == s) {
+          sc = &c;
+        }
+      }
+      if (sc == nullptr) {
+        ctx->decode_scratch.emplace_back();
+        sc         = &ctx->decode_scratch.back();
+        sc->stream = s;
+        PDC_CUDA(cudaMalloc(reinterpret_cast<void**>(&sc->d_counter), sizeof(uint32_t)));
+      }
+      if (need > sc->words) {
         // Grow-only; sized once per (largest lifting size) in practice. cudaMalloc synchronises the device.
         size_t want = plan.scratch_words_per_cta * (size_t)ctx->sm_count * 8;
         want        = std::max(need, std::min(want, (size_t)1 << 27));
-        PDC_CUDA(cudaFree(ctx->d_state_scratch));
-        ctx->d_state_scratch     = nullptr;
-        ctx->state_scratch_words = 0;
-        PDC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->d_state_scratch), want * sizeof(uint32_t)));
-        ctx->state_scratch_words = want;
+        PDC_CUDA(cudaFree(sc->d_state));
+        sc->d_state = nullptr;
+        sc->words   = 0;
+        PDC_CUDA(cudaMalloc(reinterpret_cast<void**>(&sc->d_state), want * sizeof(uint32_t)));
+        sc->words = want;
       }
-      PDC_CUDA(pdc::launch_ldpc_decode_h2(p, plan, ctx->d_state_scratch, s));
+      // Pairs are handed out dynamically (codeblocks that stop early free their CTA for the next pair).
+      PDC_CUDA(cudaMemsetAsync(sc->d_counter, 0, sizeof(uint32_t), s));
+      PDC_CUDA(pdc::launch_ldpc_decode_h2(p, plan, sc->d_state, sc->d_counter, s));
     } else {
       PDC_CUDA(pdc::launch_ldpc_decode(p, shape.max_Z, shape.any_bg1, direct_in, direct_n, s));
     }
@@ -528,7 +549,10 @@ void pdc_destroy(pdc_ctx* ctx)
   cudaFree(ctx->d_harq_last);
   cudaFree(ctx->d_tb_sync);
   cudaFree(ctx->d_scratch_llr);
-  cudaFree(ctx->d_state_scratch);
+  for (pdc_ctx::DecodeScratch& c : ctx->decode_scratch) {
+    cudaFree(c.d_state);
+    cudaFree(c.d_counter);
+  }
   delete ctx;
 }
 
