@@ -140,7 +140,7 @@ struct GraphSmem {
   // Per edge {circulant shift in bytes, shared-window address of the first soft word of its variable node}; every row
   // starts on a 16-byte boundary so that one 128-bit load brings two edges.
   uint2    einfo[MAX_EDGES + MAX_ROWS];
-  uint32_t row_info[MAX_ROWS]; // first einfo entry | degree << 16
+  uint32_t row_info[MAX_ROWS]; // first einfo entry | degree << 16 | "no barrier needed" << 31
 };
 
 
@@ -158,7 +158,7 @@ __device__ __forceinline__ void row_barrier()
 //            sp_next as soon as this row's are consumed). This row's new messages are stored to sp.
 template <int DEG>
 __device__ __forceinline__ void process_row(uint32_t e_info, uint32_t j4, uint32_t neg_Z4, RowState& st, uint4* sp,
-                                            const uint4* sp_next, uint64_t pol, int scale_mode)
+                                            const uint4* sp_next, uint64_t pol, int scale_mode, bool need_barrier)
 {
   RowState st_out = make_uint4(0, 0, 0, 0);
   constexpr bool PACKED_MIN = DEG > 16;
@@ -196,7 +196,9 @@ __device__ __forceinline__ void process_row(uint32_t e_info, uint32_t j4, uint32
       addr[e] = ((e & 1) ? ei.w : ei.y) + __viaddmin_u32(t, neg_Z4, t);
     }
   }
-  row_barrier();
+  if (need_barrier) {
+    row_barrier();
+  }
 
   __half2 min1 = h120, min2 = h120, a_prev = h120;
   hh      par = 0, ps = 0, pm = 0;
@@ -292,27 +294,28 @@ __device__ __forceinline__ void process_row(uint32_t e_info, uint32_t j4, uint32
 }
 
 __device__ __forceinline__ void dispatch_row(int deg, uint32_t e_info, uint32_t j4, uint32_t neg_Z4, RowState& st,
-                                             uint4* sp, const uint4* sp_next, uint64_t pol, int scale_mode)
+                                             uint4* sp, const uint4* sp_next, uint64_t pol, int scale_mode,
+                                             bool need_barrier)
 {
   // Most frequent degrees first (BG1: 18 rows of degree 5, 8 of degree 6, ...).
   if (deg == 5) {
-    process_row<5>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
+    process_row<5>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode, need_barrier);
   } else if (deg == 6) {
-    process_row<6>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
+    process_row<6>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode, need_barrier);
   } else if (deg == 4) {
-    process_row<4>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
+    process_row<4>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode, need_barrier);
   } else if (deg == 7) {
-    process_row<7>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
+    process_row<7>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode, need_barrier);
   } else if (deg == 19) {
-    process_row<19>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
+    process_row<19>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode, need_barrier);
   } else if (deg == 3) {
-    process_row<3>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
+    process_row<3>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode, need_barrier);
   } else if (deg == 8) {
-    process_row<8>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
+    process_row<8>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode, need_barrier);
   } else if (deg == 9) {
-    process_row<9>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
+    process_row<9>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode, need_barrier);
   } else {
-    process_row<10>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode);
+    process_row<10>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode, need_barrier);
   }
 }
 
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         sh_red[h][k] = r;
       }
       for (int m = tid; m < rows; m += nthr) {
-        g.row_info[m] = (uint32_t)c_tab.row_pstart[b][m] |
+        g.row_info[m] = ((uint32_t)c_tab.row_free[b][m] << 31) | (uint32_t)c_tab.row_pstart[b][m] |
                         ((uint32_t)(c_tab.row_start[b][m + 1] - c_tab.row_start[b][m]) << 16);
       }
       // Last non-zero input of each codeblock (ldpc_decoder_impl.cpp:86-99): recorded by the rate dematcher for the
@@ -609,11 +612,12 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           if (active) {
             const uint32_t info = lds_u32(row_info_s + 4u * (uint32_t)m);
             const int      e0   = info & 0xffffu;
-            const int      deg  = info >> 16;
+            const int      deg  = (info >> 16) & 0x7fff;
             uint4* const   spn  = (m + 1 < layers) ? sp + st_stride : st_thread;
-            dispatch_row(deg, einfo_s + 8u * (uint32_t)e0, j4, neg_Z4, st, sp, spn, pol_keep, scale_mode);
+            dispatch_row(deg, einfo_s + 8u * (uint32_t)e0, j4, neg_Z4, st, sp, spn, pol_keep, scale_mode,
+                         (info >> 31) == 0);
             sp = spn;
-          } else {
+          } else if ((g.row_info[m] >> 31) == 0) {
             row_barrier();
           }
         }

@@ -25,6 +25,7 @@ struct BgTables {
   uint16_t v[2][8][MAX_EDGES];
   uint16_t row_start[2][MAX_ROWS + 2];
   uint16_t row_pstart[2][MAX_ROWS + 2]; // row starts when every row is padded to an even number of edges
+  uint8_t  row_free[2][MAX_ROWS + 2];   // 1: the row shares no variable node with the rows since the last barrier
   uint8_t  set_index[MAX_Z + 1]; // 0xff = not a lifting size
   // x^(32 k) mod P for the three CRC polynomials (index PDC_CRC16-1 .. PDC_CRC24B-1).
   uint32_t xpow32[3][XPOW_ENTRIES];

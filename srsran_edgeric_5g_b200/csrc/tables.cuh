@@ -33,6 +33,26 @@ inline cudaError_t upload_tables()
     while (r < rows) {
       h.row_start[bg][++r] = (uint16_t)n;
     }
+    // Rows that touch none of the variable nodes of the rows processed since the last barrier need no barrier of their
+    // own (the extension rows of both base graphs are pairwise column-disjoint in consecutive pairs).
+    {
+      bool used[MAX_EDGES] = {false}; // indexed by column (< 68)
+      for (int m = 0; m != rows; ++m) {
+        bool clash = (m == 0);
+        for (int i = h.row_start[bg][m]; i != h.row_start[bg][m + 1]; ++i) {
+          clash = clash || used[h.col[bg][i]];
+        }
+        if (clash) {
+          for (bool& u : used) {
+            u = false;
+          }
+        }
+        for (int i = h.row_start[bg][m]; i != h.row_start[bg][m + 1]; ++i) {
+          used[h.col[bg][i]] = true;
+        }
+        h.row_free[bg][m] = clash ? 0 : 1;
+      }
+    }
     h.row_pstart[bg][0] = 0;
     for (int m = 0; m != rows; ++m) {
       int deg                 = h.row_start[bg][m + 1] - h.row_start[bg][m];
