@@ -1196,3 +1196,281 @@ int orc_ulsch_demux(const orc_ulsch_cfg* c,
 #undef CONFIGURE_CSI2
   return (hack_open || csi1_open || csi2_open) ? -1 : 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Soft demapper - lib/phy/upper/channel_modulation/demodulation_mapper_*.cpp.                      */
+/*                                                                                                                    */
+/* The reference chooses its kernels at COMPILE time: on an x86 build (-mavx2 -mfma, what oracle/Makefile and the       */
+/* reference's AUTO_DETECT_ISA build use) whole blocks of 16/8/16/4 symbols (QPSK/16QAM/64QAM/256QAM) of every          */
+/* demodulate_soft call take the AVX2 kernel and the remainder a scalar loop whose arithmetic differs (division instead */
+/* of reciprocal multiplication, round-half-away instead of round-half-even, near-zero test on |z|^2 instead of per     */
+/* component). An AVX512 build adds wider blocks with the same per-element arithmetic, hence the same output.           */
+/* GCC contracts "slope * value + intercept" into one fused multiply-add in both paths (checked in the object code of   */
+/* oracle/_ref); fmaf() below is that contraction, every other operation is a separate single-precision operation       */
+/* (this file is compiled with -ffp-contract=off).                                                                     */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+/* cvttss2si / cvtps2dq of an integer-valued float: out-of-range and NaN give the "integer indefinite" 0x80000000. */
+static int32_t x86_f2i(float v)
+{
+  if (!(v >= -2147483648.0f && v < 2147483648.0f)) {
+    return INT32_MIN;
+  }
+  return (int32_t)v;
+}
+
+/* log_likelihood_ratio::quantize (lib/phy/upper/log_likelihood_ratio.cpp:89-98); the cast of the rounded value goes
+ * through cvttss2si and keeps the low byte, so a NaN becomes 0. */
+static int8_t quantize_scalar(float value, float range_limit)
+{
+  float clipped = value;
+  if (fabsf(value) > range_limit) {
+    clipped = copysignf(range_limit, value);
+  }
+  float q = clipped / range_limit;
+  q       = q * (float)LLR_MAX;
+  return (int8_t)(uint8_t)(uint32_t)x86_f2i(roundf(q));
+}
+
+/* mm256::quantize_ps (lib/phy/upper/channel_modulation/avx2_helpers.h:121-166), one element. */
+static int8_t quantize_simd(float value, float range_limit)
+{
+  float scale = (float)LLR_MAX / range_limit;
+  float v     = value * scale;
+  /* clip_ps: ordered compares, a NaN passes through. */
+  if (v > (float)LLR_MAX) {
+    v = (float)LLR_MAX;
+  }
+  if (v < (float)-LLR_MAX) {
+    v = (float)-LLR_MAX;
+  }
+  v         = nearbyintf(v); /* _MM_FROUND_NINT: to nearest, ties to even (default rounding mode) */
+  int32_t i = x86_f2i(v);
+  if (i > LLR_MAX || i < -LLR_MAX) { /* check_bounds_epi32: NaN (integer indefinite) -> 0 */
+    i = 0;
+  }
+  return (int8_t)i;
+}
+
+typedef struct {
+  float width;
+  int   n;
+  float slope[16];
+  float icpt[16];
+} itab_t;
+
+/* Tables of demodulation_mapper_qam64.cpp:43-80 and demodulation_mapper_qam256.cpp:43-165: slopes are small integers
+ * times 1/sqrt(42) or 1/sqrt(170) (single-precision product), intercepts integers over 21 or 85. */
+static void make_itab(itab_t* t, float unit, int width_units, int n, const int* slope_k, const int* icpt_num, float den)
+{
+  t->width = (float)width_units * unit;
+  t->n     = n;
+  for (int i = 0; i != n; ++i) {
+    t->slope[i] = (float)slope_k[i] * unit;
+    t->icpt[i]  = (float)icpt_num[i] / den;
+  }
+}
+
+static itab_t g_q64[3], g_q256[4];
+static int    g_itab_ready;
+
+static void init_itabs(void)
+{
+  if (g_itab_ready) {
+    return;
+  }
+  const float u42 = 1.0f / sqrtf(42.0f), u170 = 1.0f / sqrtf(170.0f);
+  static const int s64_01[8] = {16, 12, 8, 4, 4, 8, 12, 16}, i64_01[8] = {24, 12, 4, 0, 0, -4, -12, -24};
+  static const int s64_23[8] = {8, 4, 4, 8, -8, -4, -4, -8}, i64_23[8] = {20, 8, 8, 12, 12, 8, 8, 20};
+  static const int s64_45[4] = {4, -4, 4, -4}, i64_45[4] = {12, -4, -4, 12};
+  make_itab(&g_q64[0], u42, 2, 8, s64_01, i64_01, 21.0f);
+  make_itab(&g_q64[1], u42, 2, 8, s64_23, i64_23, 21.0f);
+  make_itab(&g_q64[2], u42, 4, 4, s64_45, i64_45, 21.0f);
+  static const int s256_01[16] = {32, 28, 24, 20, 16, 12, 8, 4, 4, 8, 12, 16, 20, 24, 28, 32};
+  static const int i256_01[16] = {112, 84, 60, 40, 24, 12, 4, 0, 0, -4, -12, -24, -40, -60, -84, -112};
+  static const int s256_23[16] = {16, 12, 8, 4, 4, 8, 12, 16, -16, -12, -8, -4, -4, -8, -12, -16};
+  static const int i256_23[16] = {88, 60, 36, 16, 16, 28, 36, 40, 40, 36, 28, 16, 16, 36, 60, 88};
+  static const int s256_45[16] = {8, 4, 4, 8, -8, -4, -4, -8, 8, 4, 4, 8, -8, -4, -4, -8};
+  static const int i256_45[16] = {52, 24, 24, 44, -20, -8, -8, -12, -12, -8, -8, -20, 44, 24, 24, 52};
+  static const int s256_67[8]  = {4, -4, 4, -4, 4, -4, 4, -4};
+  static const int i256_67[8]  = {28, -20, 12, -4, -4, 12, -20, 28};
+  make_itab(&g_q256[0], u170, 2, 16, s256_01, i256_01, 85.0f);
+  make_itab(&g_q256[1], u170, 2, 16, s256_23, i256_23, 85.0f);
+  make_itab(&g_q256[2], u170, 2, 16, s256_45, i256_45, 85.0f);
+  make_itab(&g_q256[3], u170, 4, 8, s256_67, i256_67, 85.0f);
+  g_itab_ready = 1;
+}
+
+static int clamp_idx(int32_t idx, int n)
+{
+  return (idx < 0) ? 0 : (idx > n - 1) ? n - 1 : idx;
+}
+
+/* interval_function (demodulation_mapper_intervals.h:31-63): index from a DIVISION by the interval width. */
+static float interval_scalar(float value, float rcp_noise, const itab_t* t)
+{
+  float   q   = value / t->width;
+  int32_t idx = (int32_t)((uint32_t)x86_f2i(floorf(q)) + (uint32_t)(t->n / 2));
+  int     k   = clamp_idx(idx, t->n);
+  float   l   = fmaf(t->slope[k], value, t->icpt[k]);
+  return l * rcp_noise;
+}
+
+/* mm256::interval_function (avx2_helpers.h:234-254): index from a MULTIPLICATION by 1 / width, result forced to zero for
+ * |value| <= 1e-9 (ordered compare). */
+static float interval_simd(float value, float rcp_noise, const itab_t* t)
+{
+  float   inv = 1.0f / t->width;
+  float   q   = value * inv;
+  int32_t idx = (int32_t)((uint32_t)x86_f2i(floorf(q)) + (uint32_t)(t->n / 2));
+  int     k   = clamp_idx(idx, t->n);
+  float   l   = fmaf(t->slope[k], value, t->icpt[k]);
+  l           = l * rcp_noise;
+  if (fabsf(value) <= 1e-9f) {
+    l = 0.0f;
+  }
+  return l;
+}
+
+/* safe_div(1, noise) (avx2_helpers.h:259-271) and the scalar "if (noise > 0) rcp = 1 / noise". */
+static float rcp_noise_of(float nv)
+{
+  return (nv > 0.0f) ? 1.0f / nv : 0.0f;
+}
+
+/* is_near_zero(cf_t) (include/srsran/support/math_utils.h:91-94): |z|^2 < 1e-9, |z|^2 evaluated as fma(re, re, im * im). */
+static int near_zero_cf(float re, float im)
+{
+  float t = im * im;
+  t       = fmaf(re, re, t);
+  return 1e-9f > t;
+}
+
+static void demod_symbol_simd(int8_t* out, float re, float im, float nv, int mod)
+{
+  const float rcp = rcp_noise_of(nv);
+  const float c[2] = {re, im};
+  if (mod == 2) {
+    /* demod_QPSK_avx2 (demodulation_mapper_qpsk.cpp:39-78). */
+    const float gain = 2.0f * 1.41421356237309504880f;
+    for (int k = 0; k != 2; ++k) {
+      float l = gain * c[k];
+      out[k]  = quantize_simd(l * rcp, 24.0f);
+    }
+  } else if (mod == 4) {
+    /* demod_QAM16_avx2 (demodulation_mapper_qam16.cpp:41-116). */
+    const float u10 = 1.0f / sqrtf(10.0f), gain = 4.0f * u10, thr = 2.0f * u10;
+    for (int k = 0; k != 2; ++k) {
+      float first  = gain * c[k];
+      float second = 2.0f * first - copysignf(0.8f, c[k]);
+      float l01    = (fabsf(c[k]) > thr) ? second : first;
+      float l23    = 0.8f - fabsf(first);
+      l01 *= rcp;
+      l23 *= rcp;
+      if (fabsf(c[k]) <= 1e-9f) {
+        l01 = 0.0f;
+        l23 = 0.0f;
+      }
+      out[k]     = quantize_simd(l01, 20.0f);
+      out[2 + k] = quantize_simd(l23, 20.0f);
+    }
+  } else if (mod == 6) {
+    for (int g = 0; g != 3; ++g) {
+      for (int k = 0; k != 2; ++k) {
+        out[2 * g + k] = quantize_simd(interval_simd(c[k], rcp, &g_q64[g]), 20.0f);
+      }
+    }
+  } else {
+    for (int g = 0; g != 4; ++g) {
+      for (int k = 0; k != 2; ++k) {
+        out[2 * g + k] = quantize_simd(interval_simd(c[k], rcp, &g_q256[g]), 20.0f);
+      }
+    }
+  }
+}
+
+static void demod_symbol_scalar(int8_t* out, float re, float im, float nv, int mod)
+{
+  const float c[2] = {re, im};
+  if (mod == 2) {
+    /* demod_QPSK_symbol (demodulation_mapper_qpsk.cpp:121-129). */
+    const float gain = 2.0f * 1.41421356237309504880f;
+    for (int k = 0; k != 2; ++k) {
+      if (!(nv > 0.0f)) {
+        out[k] = 0;
+      } else {
+        float l = gain * c[k];
+        out[k]  = quantize_scalar(l / nv, 24.0f);
+      }
+    }
+    return;
+  }
+  if (near_zero_cf(re, im)) {
+    memset(out, 0, (size_t)mod);
+    return;
+  }
+  if (mod == 4) {
+    /* demod_16QAM_symbol_01/_23 (demodulation_mapper_qam16.cpp:192-222): "0.8 - gain * |x|" is one fused operation. */
+    const float u10 = 1.0f / sqrtf(10.0f), gain = 4.0f * u10, thr = 2.0f * u10;
+    for (int k = 0; k != 2; ++k) {
+      if (!(nv > 0.0f)) {
+        out[k] = out[2 + k] = 0;
+        continue;
+      }
+      float l01 = gain * c[k];
+      if (fabsf(c[k]) > thr) {
+        l01 = 2.0f * l01 - copysignf(0.8f, c[k]);
+      }
+      float l23  = fmaf(-gain, fabsf(c[k]), 0.8f);
+      out[k]     = quantize_scalar(l01 / nv, 20.0f);
+      out[2 + k] = quantize_scalar(l23 / nv, 20.0f);
+    }
+    return;
+  }
+  const float   rcp = rcp_noise_of(nv);
+  const itab_t* t   = (mod == 6) ? g_q64 : g_q256;
+  for (int g = 0; g != mod / 2; ++g) {
+    for (int k = 0; k != 2; ++k) {
+      out[2 * g + k] = quantize_scalar(interval_scalar(c[k], rcp, &t[g]), 20.0f);
+    }
+  }
+}
+
+/* demod_BPSK_symbol (demodulation_mapper_impl.cpp:34-42). */
+static int8_t demod_bpsk(float re, float im, float nv)
+{
+  if (!(nv > 0.0f)) {
+    return 0;
+  }
+  float l = re + im;
+  l       = l * (2.0f * 1.41421356237309504880f);
+  return quantize_scalar(l / nv, 24.0f);
+}
+
+void orc_demodulate_soft(int8_t* llr, const float* symbols, const float* noise_vars, uint32_t n, int mod, int simd)
+{
+  init_itabs();
+  if (mod == ORC_MOD_BPSK || mod == ORC_MOD_PI_2_BPSK) {
+    /* demodulate_soft_BPSK / _PI_2_BPSK (demodulation_mapper_impl.cpp:44-76): odd symbols of pi/2-BPSK are rotated by
+     * -90 degrees, i.e. re + im becomes im - re. */
+    for (uint32_t i = 0; i != n; ++i) {
+      float re = symbols[2 * i], im = symbols[2 * i + 1];
+      if (mod == ORC_MOD_PI_2_BPSK && (i & 1)) {
+        float t = re;
+        re      = im;
+        im      = -t;
+      }
+      llr[i] = demod_bpsk(re, im, noise_vars[i]);
+    }
+    return;
+  }
+  const uint32_t block  = (mod == 2) ? 16 : (mod == 4) ? 8 : (mod == 6) ? 16 : 4;
+  const uint32_t n_simd = simd ? (n / block) * block : 0;
+  for (uint32_t i = 0; i != n; ++i) {
+    if (i < n_simd) {
+      demod_symbol_simd(llr + (size_t)i * mod, symbols[2 * i], symbols[2 * i + 1], noise_vars[i], mod);
+    } else {
+      demod_symbol_scalar(llr + (size_t)i * mod, symbols[2 * i], symbols[2 * i + 1], noise_vars[i], mod);
+    }
+  }
+}

@@ -203,6 +203,17 @@ int orc_ulsch_demux(const orc_ulsch_cfg* cfg,
                     int8_t*              csi_part2,
                     uint32_t*            n_out);
 
+/* ---- soft demapper ------------------------------------------------------------------------------ */
+
+#define ORC_MOD_PI_2_BPSK 0
+#define ORC_MOD_BPSK 1 /* 2, 4, 6, 8: QPSK, 16QAM, 64QAM, 256QAM (bits per symbol) */
+
+/* One demodulation_mapper::demodulate_soft call (lib/phy/upper/channel_modulation/demodulation_mapper_impl.cpp:78-106):
+ * symbols = n interleaved {re, im} pairs (equaliser output), noise_vars = n post-equalisation noise variances,
+ * llr = n * bits-per-symbol soft bits. simd != 0: the x86 build of the reference (AVX2 kernels on whole blocks of the
+ * call, scalar remainder); simd == 0: the portable build (scalar loop only). */
+void orc_demodulate_soft(int8_t* llr, const float* symbols, const float* noise_vars, uint32_t n, int mod, int simd);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,7 +118,18 @@ class Oracle:
         L.orc_ulsch_codeword_length.argtypes = [_vp]
         L.orc_ulsch_demux.restype = _c_int
         L.orc_ulsch_demux.argtypes = [_vp, _vp, _vp, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp]
+        L.orc_demodulate_soft.restype = None
+        L.orc_demodulate_soft.argtypes = [_vp, _vp, _vp, ctypes.c_uint32, _c_int, _c_int]
         self.L = L
+
+    # -- soft demapper --------------------------------------------------------------------------------------------------
+    def demodulate_soft(self, symbols, noise_vars, mod, simd=True):
+        """One demodulate_soft call. symbols: complex64[n]; noise_vars: float32[n]; mod: 0 (pi/2-BPSK), 1, 2, 4, 6, 8."""
+        symbols = np.ascontiguousarray(symbols, np.complex64)
+        noise_vars = np.ascontiguousarray(noise_vars, np.float32)
+        out = np.zeros(symbols.size * max(mod, 1), np.int8)
+        self.L.orc_demodulate_soft(_ptr(out), _ptr(symbols), _ptr(noise_vars), symbols.size, mod, 1 if simd else 0)
+        return out
 
     # -- codeword front end ---------------------------------------------------------------------------------------------
     def prg_bits(self, c_init, offset, n):
@@ -251,6 +262,8 @@ class Reference:
         L.ref_prg_bits.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, _vp]
         L.ref_ulsch_demux.restype = _c_int
         L.ref_ulsch_demux.argtypes = [_vp, _vp, _vp, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _vp, _vp]
+        L.ref_demodulate_soft.restype = None
+        L.ref_demodulate_soft.argtypes = [_vp, _vp, _vp, ctypes.c_uint, _c_int]
         L.ref_pusch_create.restype = _vp
         L.ref_pusch_create.argtypes = [ctypes.c_char_p, _c_int]
         L.ref_pusch_destroy.argtypes = [_vp]
@@ -323,6 +336,14 @@ class Reference:
         bits = np.zeros(n, np.uint8)
         self.L.ref_prg_bits(c_init, offset, n, _ptr(bits))
         return bits
+
+    def demodulate_soft(self, symbols, noise_vars, mod):
+        """demodulation_mapper_impl::demodulate_soft of the compiled reference (one call)."""
+        symbols = np.ascontiguousarray(symbols, np.complex64)
+        noise_vars = np.ascontiguousarray(noise_vars, np.float32)
+        out = np.zeros(symbols.size * max(mod, 1), np.int8)
+        self.L.ref_demodulate_soft(_ptr(out), _ptr(symbols), _ptr(noise_vars), symbols.size, mod)
+        return out
 
     def ulsch_demux(self, cfg, llrs, seq_bits, max_block_re=0):
         """ulsch_demultiplex_impl fed like pusch_demodulator_impl does. Returns (status, [sch, ack, csi1, csi2])."""

@@ -18,6 +18,7 @@
 #include "srsran/phy/upper/channel_processors/pusch/pusch_codeword_buffer.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_buffer.h"
 #include "srsran/phy/upper/channel_coding/channel_coding_factories.h"
+#include "srsran/phy/upper/channel_modulation/channel_modulation_factories.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_notifier.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_result.h"
 #include "srsran/phy/upper/unique_rx_buffer.h"
@@ -562,6 +563,23 @@ void ref_prg_bits(unsigned c_init, unsigned offset, unsigned n, uint8_t* bits)
   prg.generate(seq);
   for (unsigned i = 0; i != n; ++i) {
     bits[i] = seq.extract(i, 1);
+  }
+}
+
+/// One demodulation_mapper::demodulate_soft call (include/srsran/phy/upper/channel_modulation/demodulation_mapper.h:62)
+/// on the mapper of create_channel_modulation_sw_factory(). symbols: n interleaved {re, im} pairs.
+/// mod: 0 = pi/2-BPSK, 1 = BPSK, 2 = QPSK, 4 = 16QAM, 6 = 64QAM, 8 = 256QAM.
+void ref_demodulate_soft(int8_t* llr, const float* symbols, const float* noise_vars, unsigned n, int mod)
+{
+  static std::unique_ptr<demodulation_mapper> demapper =
+      create_channel_modulation_sw_factory()->create_demodulation_mapper();
+  modulation_scheme scheme = (mod == 0) ? modulation_scheme::PI_2_BPSK : to_mod(mod);
+  unsigned          qm     = (mod == 0) ? 1 : mod;
+  std::vector<log_likelihood_ratio> out(static_cast<size_t>(n) * qm);
+  demapper->demodulate_soft(
+      out, span<const cf_t>(reinterpret_cast<const cf_t*>(symbols), n), span<const float>(noise_vars, n), scheme);
+  for (size_t i = 0; i != out.size(); ++i) {
+    llr[i] = out[i].to_value_type();
   }
 }
 
