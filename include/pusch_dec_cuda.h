@@ -19,10 +19,12 @@
  *                                         include/srsran/phy/upper/channel_processors/pusch/ulsch_demultiplex.h:41-103,
  *                                         include/srsran/phy/upper/channel_processors/pusch/pusch_codeword_buffer.h
  *   pseudo_random_generator::generate     include/srsran/phy/upper/sequence_generators/pseudo_random_generator.h
+ *   demodulation_mapper::demodulate_soft  include/srsran/phy/upper/channel_modulation/demodulation_mapper.h:62-65
+ *                                         (factory: channel_modulation_factories.h:32-41)
  *
  * Threading: a context serialises nothing itself. Each queue ("stream") may be driven by one thread at a time; the
  * synchronous single-object calls (pdc_ldpc_decode, pdc_rate_dematch, pdc_crc, pdc_ulsch_demux, pdc_scrambling_sequence,
- * pdc_launch_codewords_device) share queue 0 / one set of scratch buffers and must not run concurrently with each other.
+ * pdc_launch_codewords_device, pdc_demodulate_soft, pdc_launch_demod_device) share queue 0 / one set of scratch buffers and must not run concurrently with each other.
  *
  * INTEGRATION.md shows the C++ adapter classes that bind these calls behind create_ldpc_decoder_factory_sw("cuda"),
  * create_ldpc_rate_dematcher_factory_sw("cuda") and the hal::hw_accelerator_pusch_dec factory.
@@ -164,6 +166,31 @@ typedef struct {
   uint32_t n_csi_part2;
 } pdc_cw_result;
 
+/*
+ * Soft demapper. Modulation codes = bits per symbol, 0 for pi/2-BPSK
+ * (modulation_scheme, include/srsran/ran/sch/modulation_scheme.h).
+ */
+#define PDC_MOD_PI_2_BPSK 0
+#define PDC_MOD_BPSK 1
+#define PDC_MOD_QPSK 2
+#define PDC_MOD_QAM16 4
+#define PDC_MOD_QAM64 6
+#define PDC_MOD_QAM256 8
+
+/* Which build of the reference's demapper is reproduced bit for bit (its SIMD path is chosen at compile time). */
+#define PDC_DEMOD_X86 0    /* x86 build (AVX2 / AVX512 kernels on whole blocks of a call, scalar remainder) - default */
+#define PDC_DEMOD_SCALAR 1 /* portable build: the scalar loop for every symbol                                        */
+
+#define PDC_CW_PLAIN_BPSK 16u /* pdc_submit_symbols, qm = 1: BPSK instead of the pi/2-BPSK that PUSCH uses            */
+
+/* One demodulation_mapper::demodulate_soft call: n_sym symbols -> n_sym * bits-per-symbol soft bits. */
+typedef struct {
+  uint32_t sym_offset; /* first symbol of the call in the symbol / noise-variance arrays                               */
+  uint32_t n_sym;
+  uint32_t llr_offset; /* first soft bit of the call in the output                                                     */
+  uint32_t modulation; /* PDC_MOD_*                                                                                    */
+} pdc_demod_call;
+
 typedef struct {
   int32_t  device;          /* CUDA device ordinal                                                                     */
   uint32_t max_cbs;         /* largest batch, in codeblocks                                                            */
@@ -175,6 +202,7 @@ typedef struct {
   int32_t  combine_simd_width; /* 64 / 32 / 0: which reference dematcher's treatment of non-finite stale soft bits is
                                   reproduced (avx512 / avx2 / generic); irrelevant for finite values                  */
   uint32_t nof_streams;     /* independent in-flight batches ("hardware queues", reserve_queue/free_queue)             */
+  int32_t  demod_mode;      /* PDC_DEMOD_*                                                                             */
 } pdc_config;
 
 typedef struct pdc_ctx pdc_ctx;
@@ -248,6 +276,27 @@ int pdc_submit_codewords(pdc_ctx*           ctx,
                          int8_t*            uci_out,
                          size_t             uci_capacity,
                          pdc_cw_result*     results);
+/*
+ * The same front end fed one step earlier, by the channel equaliser's output instead of soft bits
+ * (pusch_demodulator_impl.cpp:231-259: demodulate_soft, then descrambling, per OFDM symbol): H2D copy of n_sym equalised
+ * symbols ({re, im} float pairs) and their noise variances, soft demapping on the device with one demodulate_soft call
+ * per OFDM symbol of each codeword (the blocks pusch_demodulator_impl hands to the demapper), then exactly what
+ * pdc_submit_codewords does with the resulting soft bits - which never exist in host memory. cws[i].in_offset places
+ * the codeword's soft bits in a device-internal space; sym_offsets[i] is its first symbol in symbols[] / noise_vars[]
+ * (symbol k of the codeword yields soft bits k * qm .. k * qm + qm - 1 of it). Every codeword must carry
+ * PDC_CW_SCRAMBLED: the demapper's output is scrambled.
+ */
+int pdc_submit_symbols(pdc_ctx*           ctx,
+                       uint32_t           stream,
+                       const pdc_cw_desc* cws,
+                       uint32_t           n_cw,
+                       const uint32_t*    sym_offsets,
+                       const float*       symbols,
+                       const float*       noise_vars,
+                       size_t             n_sym,
+                       int8_t*            uci_out,
+                       size_t             uci_capacity,
+                       pdc_cw_result*     results);
 /* Non-blocking: *done = 1 when pdc_wait would not block. */
 int pdc_poll(pdc_ctx* ctx, uint32_t stream, int* done);
 
@@ -353,6 +402,30 @@ int pdc_ulsch_demux(pdc_ctx*           ctx,
                     int8_t*            uci_out,
                     size_t             uci_capacity,
                     pdc_cw_result*     results);
+/*
+ * demodulation_mapper::demodulate_soft, synchronous, host buffers: symbols = n {re, im} pairs, noise_vars[n],
+ * llrs[n * bits per symbol]. One call = one call of the reference (block / remainder split of its SIMD build).
+ */
+int pdc_demodulate_soft(pdc_ctx*     ctx,
+                        int8_t*      llrs,
+                        const float* symbols,
+                        const float* noise_vars,
+                        uint32_t     n,
+                        int          modulation);
+/*
+ * Batched, device-resident: n_calls demodulate_soft calls over d_symbols / d_noise_vars into d_llrs, queued on the
+ * caller's CUDA stream (call table on the host). One call at a time per context.
+ */
+int pdc_launch_demod_device(pdc_ctx*              ctx,
+                            const pdc_demod_call* calls,
+                            uint32_t              n_calls,
+                            const void*           d_symbols,
+                            const void*           d_noise_vars,
+                            size_t                n_sym,
+                            void*                 d_llrs,
+                            size_t                llr_capacity,
+                            void*                 cuda_stream);
+
 /* TS 38.211 5.2.1 pseudo-random sequence c(offset .. offset + n - 1), packed MSB first (pseudo_random_generator::generate). */
 int pdc_scrambling_sequence(pdc_ctx* ctx, uint32_t c_init, uint32_t offset, uint32_t n, uint8_t* packed);
 

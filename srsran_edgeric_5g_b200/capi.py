@@ -44,7 +44,8 @@ class TbResult(ctypes.Structure):
 
 class Config(ctypes.Structure):
     _fields_ = [("device", _i32), ("max_cbs", _u32), ("max_llrs", _u32), ("harq_entries", _u32), ("max_tbs", _u32),
-                ("max_tb_bytes", _u32), ("scale_mode", _i32), ("combine_simd_width", _i32), ("nof_streams", _u32)]
+                ("max_tb_bytes", _u32), ("scale_mode", _i32), ("combine_simd_width", _i32), ("nof_streams", _u32),
+                ("demod_mode", _i32)]
 
 
 CB_DESC_DTYPE = np.dtype([("llr_offset", "<u4"), ("rm_length", "<u4"), ("harq_id", "<u4"), ("nref", "<u4"),
@@ -56,6 +57,11 @@ TB_DESC_DTYPE = np.dtype([("first_cb", "<u4"), ("nof_cb", "<u4"), ("tbs_bits", "
 TB_RESULT_DTYPE = np.dtype([("tb_crc_ok", "u1"), ("all_cb_ok", "u1"), ("reserved", "<u2")])
 CW_SCRAMBLED = 1
 CW_DEFER_DESCRAMBLING = 2
+CW_PLAIN_BPSK = 16
+# soft demapper: modulation codes (bits per symbol, 0 = pi/2-BPSK), reference build reproduced, pdc_demod_call
+MOD_PI_2_BPSK, MOD_BPSK, MOD_QPSK, MOD_QAM16, MOD_QAM64, MOD_QAM256 = 0, 1, 2, 4, 6, 8
+DEMOD_X86, DEMOD_SCALAR = 0, 1
+DEMOD_CALL_DTYPE = np.dtype([("sym_offset", "<u4"), ("n_sym", "<u4"), ("llr_offset", "<u4"), ("modulation", "<u4")])
 # pdc_cw_desc / pdc_cw_result (codeword front end)
 CW_DESC_DTYPE = np.dtype([("in_offset", "<u4"), ("sch_offset", "<u4"), ("uci_offset", "<u4"), ("c_init", "<u4"),
                           ("flags", "<u4"), ("qm", "u1"), ("nof_layers", "u1"), ("start_symbol_index", "u1"),
@@ -73,7 +79,7 @@ EXPORTS = ["pdc_default_config", "pdc_create", "pdc_destroy", "pdc_last_error", 
            "pdc_measure_int_peak", "pdc_host_alloc", "pdc_host_free", "pdc_submit", "pdc_wait", "pdc_poll", "pdc_launch_device",
            "pdc_harq_read", "pdc_harq_write", "pdc_harq_free", "pdc_harq_device_ptr", "pdc_ldpc_decode",
            "pdc_rate_dematch", "pdc_crc", "pdc_submit_codewords", "pdc_ulsch_demux", "pdc_scrambling_sequence",
-           "pdc_launch_codewords_device"]
+           "pdc_launch_codewords_device", "pdc_submit_symbols", "pdc_demodulate_soft", "pdc_launch_demod_device"]
 
 _lib = None
 
@@ -129,6 +135,9 @@ def load():
     L.pdc_scrambling_sequence.argtypes = [_vp, _u32, _u32, _u32, _vp]
     L.pdc_launch_codewords_device.argtypes = [_vp, _vp, _u32, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp,
                                               ctypes.c_size_t, _vp, _vp]
+    L.pdc_submit_symbols.argtypes = [_vp, _u32, _vp, _u32, _vp, _vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp]
+    L.pdc_demodulate_soft.argtypes = [_vp, _vp, _vp, _vp, _u32, ctypes.c_int]
+    L.pdc_launch_demod_device.argtypes = [_vp, _vp, _u32, _vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp]
     _lib = L
     return L
 
@@ -164,7 +173,7 @@ class Context:
     """pdc_ctx: one per GPU. Owns the device HARQ arena, the streams ("queues") and the pinned staging."""
 
     def __init__(self, device=0, max_cbs=4096, max_llrs=None, harq_entries=4096, max_tbs=256, max_tb_bytes=4 << 20,
-                 scale_mode=SCALE_X86, combine_simd_width=64, nof_streams=2):
+                 scale_mode=SCALE_X86, combine_simd_width=64, nof_streams=2, demod_mode=DEMOD_X86):
         L = load()
         cfg = Config()
         L.pdc_default_config(ctypes.byref(cfg))
@@ -177,6 +186,7 @@ class Context:
         cfg.scale_mode = scale_mode
         cfg.combine_simd_width = combine_simd_width
         cfg.nof_streams = nof_streams
+        cfg.demod_mode = demod_mode
         self.cfg = cfg
         self._L = L
         self.h = _vp()
@@ -267,6 +277,42 @@ class Context:
         fe = {"cws": cws, "raw_llrs": raw_llrs, "cw_results": res, "uci": uci}
         self._pending_fe[stream] = fe
         return fe
+
+    def submit_symbols(self, cws, sym_offsets, symbols, noise_vars, stream=0, out_uci=None):
+        """pdc_submit_symbols: the front end fed by the equaliser's output - soft demapping (one demodulate_soft call per
+        OFDM symbol of each codeword), descrambling and UL-SCH demultiplexing on the device; follow it with
+        submit(cbs, None, ...) on the same stream. symbols: complex64 (ideally pinned); noise_vars: float32."""
+        cws = np.ascontiguousarray(cws, CW_DESC_DTYPE)
+        sym_offsets = np.ascontiguousarray(sym_offsets, np.uint32)
+        assert symbols.dtype == np.complex64 and symbols.flags.c_contiguous
+        assert noise_vars.dtype == np.float32 and noise_vars.flags.c_contiguous and noise_vars.size == symbols.size
+        res = np.zeros(cws.size, CW_RESULT_DTYPE)
+        if out_uci is None:
+            need = int((cws["uci_offset"].astype(np.int64) + cws["nof_enc_harq_ack_bits"] + cws["nof_enc_csi_part1_bits"] +
+                        cws["nof_enc_csi_part2_bits"]).max()) if cws.size else 0
+            out_uci = np.zeros(max(1, need), np.int8)
+        check(self._L.pdc_submit_symbols(self.h, stream, _ptr(cws), cws.size, _ptr(sym_offsets), _ptr(symbols),
+                                         _ptr(noise_vars), symbols.size, _ptr(out_uci), out_uci.size, _ptr(res)))
+        fe = {"cws": cws, "sym_offsets": sym_offsets, "symbols": symbols, "noise_vars": noise_vars, "cw_results": res,
+              "uci": out_uci}
+        self._pending_fe[stream] = fe
+        return fe
+
+    def demodulate_soft(self, symbols, noise_vars, modulation):
+        """pdc_demodulate_soft: one demodulation_mapper::demodulate_soft call (synchronous, host buffers)."""
+        symbols = np.ascontiguousarray(symbols, np.complex64)
+        noise_vars = np.ascontiguousarray(noise_vars, np.float32)
+        assert symbols.size == noise_vars.size
+        out = np.zeros(symbols.size * max(int(modulation), 1), np.int8)
+        check(self._L.pdc_demodulate_soft(self.h, _ptr(out), _ptr(symbols), _ptr(noise_vars), symbols.size,
+                                          int(modulation)))
+        return out
+
+    def launch_demod_device(self, calls, d_symbols, d_noise_vars, n_sym, d_llrs, llr_capacity, cuda_stream=0):
+        """pdc_launch_demod_device: a batch of demodulate_soft calls on device buffers, queued on the caller's stream."""
+        calls = np.ascontiguousarray(calls, DEMOD_CALL_DTYPE)
+        check(self._L.pdc_launch_demod_device(self.h, _ptr(calls), calls.size, d_symbols, d_noise_vars, n_sym, d_llrs,
+                                              llr_capacity, cuda_stream or None))
 
     def launch_codewords_device(self, cws, d_raw, n_raw, d_sch, sch_capacity, d_uci=0, uci_capacity=0, cuda_stream=0):
         """pdc_launch_codewords_device: the front end on device buffers, queued on the caller's stream."""

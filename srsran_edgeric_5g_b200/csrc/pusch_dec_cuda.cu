@@ -8,6 +8,7 @@
 #include "ldpc_decode_h2.cuh"
 #include "tb_assemble.cuh"
 #include "ulsch_demux.cuh"
+#include "demod.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -39,8 +40,30 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess)
     }                                                                                                                  \
   } while (0)
 
+// Soft demapper stage (grow-only buffers; the call / tile table is staged through a ring of pinned buffers like the
+// front-end plan).
+struct DemodStage {
+  float2*              d_sym = nullptr;
+  size_t               sym_cap = 0;
+  float*               d_nv = nullptr;
+  size_t               nv_cap = 0;
+  unsigned char*       d_tab = nullptr;
+  size_t               tab_cap = 0;
+  static constexpr int RING = 4;
+  unsigned char*       h_tab[RING]     = {nullptr, nullptr, nullptr, nullptr};
+  size_t               h_tab_cap[RING] = {0, 0, 0, 0};
+  cudaEvent_t          tab_ev[RING]    = {nullptr, nullptr, nullptr, nullptr};
+  int                  ring_pos = 0;
+  std::vector<pdc::DemodCall> calls;
+  std::vector<pdc::DemodTile> tiles;
+  pdc::DemodArgs       args = {};
+  uint32_t             n_tiles = 0;
+  bool                 kernel_pending = false;
+};
+
 // Buffers of the codeword front end (grow-only; the plan is staged in pinned memory).
 struct FrontEnd {
+  DemodStage           dm;
   pdc::UlschPlan       plan;
   int8_t*              d_raw = nullptr;
   size_t               raw_cap = 0;
@@ -410,6 +433,7 @@ void pdc_default_config(pdc_config* cfg)
   cfg->scale_mode         = PDC_SCALE_X86;
   cfg->combine_simd_width = 64;
   cfg->nof_streams        = 2;
+  cfg->demod_mode         = PDC_DEMOD_X86;
 }
 
 const char* pdc_last_error(void)
@@ -420,7 +444,8 @@ const char* pdc_last_error(void)
 int pdc_create(const pdc_config* cfg, pdc_ctx** out)
 {
   if (!cfg || !out || cfg->max_cbs == 0 || cfg->harq_entries == 0 || cfg->nof_streams == 0 ||
-      cfg->scale_mode < PDC_SCALE_X86 || cfg->scale_mode > PDC_SCALE_NEON) {
+      cfg->scale_mode < PDC_SCALE_X86 || cfg->scale_mode > PDC_SCALE_NEON ||
+      (cfg->demod_mode != PDC_DEMOD_X86 && cfg->demod_mode != PDC_DEMOD_SCALAR)) {
     return fail(PDC_ERR_INVALID, "pdc_create: invalid configuration");
   }
   int n_dev = 0;
@@ -497,6 +522,15 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
 
 static void free_front_end(FrontEnd& fe)
 {
+  cudaFree(fe.dm.d_sym);
+  cudaFree(fe.dm.d_nv);
+  cudaFree(fe.dm.d_tab);
+  for (int k = 0; k != DemodStage::RING; ++k) {
+    cudaFreeHost(fe.dm.h_tab[k]);
+    if (fe.dm.tab_ev[k]) {
+      cudaEventDestroy(fe.dm.tab_ev[k]);
+    }
+  }
   cudaFree(fe.d_raw);
   cudaFree(fe.d_seq);
   cudaFree(fe.d_uci);
@@ -595,6 +629,7 @@ void pdc_host_free(void* p)
 }
 
 static int front_end_kernels(pdc_ctx* ctx, FrontEnd& fe, cudaStream_t s);
+static int demod_kernel_launch(pdc_ctx* ctx, DemodStage& dm, cudaStream_t s);
 
 // Page-locked host memory (pdc_host_alloc, cudaHostAlloc, cudaHostRegister) can be the target of an asynchronous copy.
 static bool is_pinned_host(const void* p)
@@ -715,6 +750,13 @@ static int front_end_kernels(pdc_ctx* ctx, FrontEnd& fe, cudaStream_t s)
     return PDC_OK;
   }
   fe.kernels_pending       = false;
+  if (fe.dm.kernel_pending) {
+    // The codewords come from the soft demapper (pdc_submit_symbols).
+    int rc = demod_kernel_launch(ctx, fe.dm, s);
+    if (rc != PDC_OK) {
+      return rc;
+    }
+  }
   const pdc::UlschArgs& a  = fe.args;
   const uint32_t        n_cw = fe.k_n_cw;
   if (fe.k_generate_seq) {
@@ -906,6 +948,230 @@ int pdc_submit_codewords(pdc_ctx*           ctx,
     q.fe.u_uci        = direct ? nullptr : uci_out;
   }
   q.fe.pending = true;
+  return PDC_OK;
+}
+
+// ---- soft demapper -----------------------------------------------------------------------------------------------------
+
+static int demod_kernel_launch(pdc_ctx* ctx, DemodStage& dm, cudaStream_t s)
+{
+  dm.kernel_pending = false;
+  if (dm.n_tiles == 0) {
+    return PDC_OK;
+  }
+  pdc::demod_kernel<<<dm.n_tiles, pdc::DEMOD_THREADS, 0, s>>>(dm.args);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return PDC_OK;
+}
+
+// Validates dm.calls, cuts them into tiles, uploads the table on stream s and prepares (or queues) the kernel:
+//   d_sym / d_nv (n_sym symbols, on the device) -> d_llrs.
+static int demod_prepare(pdc_ctx*      ctx,
+                         DemodStage&   dm,
+                         const float2* d_sym,
+                         const float*  d_nv,
+                         size_t        n_sym,
+                         int8_t*       d_llrs,
+                         size_t        llr_capacity,
+                         cudaStream_t  s,
+                         bool          launch_now)
+{
+  dm.tiles.clear();
+  for (size_t c = 0; c != dm.calls.size(); ++c) {
+    const pdc::DemodCall& call = dm.calls[c];
+    const uint32_t        m    = call.mod;
+    if (!(m == PDC_MOD_PI_2_BPSK || m == PDC_MOD_BPSK || m == PDC_MOD_QPSK || m == PDC_MOD_QAM16 ||
+          m == PDC_MOD_QAM64 || m == PDC_MOD_QAM256)) {
+      return fail(PDC_ERR_INVALID, "soft demapper: invalid modulation");
+    }
+    const size_t qm = (m == PDC_MOD_PI_2_BPSK) ? 1 : m;
+    if ((size_t)call.sym_off + call.n_sym > n_sym || (size_t)call.llr_off + (size_t)call.n_sym * qm > llr_capacity) {
+      return fail(PDC_ERR_INVALID, "soft demapper: call outside the symbol or soft-bit buffer");
+    }
+    for (uint32_t first = 0; first < call.n_sym; first += pdc::DEMOD_TILE) {
+      dm.tiles.push_back(pdc::DemodTile{(uint32_t)c, first});
+    }
+  }
+  dm.n_tiles = (uint32_t)dm.tiles.size();
+  if (dm.n_tiles == 0) {
+    dm.kernel_pending = false;
+    return PDC_OK;
+  }
+  const size_t b_calls = dm.calls.size() * sizeof(pdc::DemodCall);
+  const size_t bytes   = b_calls + dm.tiles.size() * sizeof(pdc::DemodTile);
+  PDC_CUDA(grow_device(&dm.d_tab, &dm.tab_cap, bytes));
+  const int slot = dm.ring_pos;
+  dm.ring_pos    = (dm.ring_pos + 1) % DemodStage::RING;
+  if (dm.tab_ev[slot] == nullptr) {
+    PDC_CUDA(cudaEventCreateWithFlags(&dm.tab_ev[slot], cudaEventDisableTiming));
+  } else {
+    PDC_CUDA(cudaEventSynchronize(dm.tab_ev[slot]));
+  }
+  if (bytes > dm.h_tab_cap[slot]) {
+    cudaFreeHost(dm.h_tab[slot]);
+    dm.h_tab[slot]     = nullptr;
+    dm.h_tab_cap[slot] = 0;
+    PDC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&dm.h_tab[slot]), bytes + bytes / 4 + 64));
+    dm.h_tab_cap[slot] = bytes + bytes / 4 + 64;
+  }
+  memcpy(dm.h_tab[slot], dm.calls.data(), b_calls);
+  memcpy(dm.h_tab[slot] + b_calls, dm.tiles.data(), bytes - b_calls);
+  PDC_CUDA(cudaMemcpyAsync(dm.d_tab, dm.h_tab[slot], bytes, cudaMemcpyHostToDevice, s));
+  PDC_CUDA(cudaEventRecord(dm.tab_ev[slot], s));
+  dm.args.calls      = reinterpret_cast<const pdc::DemodCall*>(dm.d_tab);
+  dm.args.tiles      = reinterpret_cast<const pdc::DemodTile*>(dm.d_tab + b_calls);
+  dm.args.symbols    = d_sym;
+  dm.args.noise_vars = d_nv;
+  dm.args.llrs       = d_llrs;
+  dm.args.flags      = (ctx->cfg.demod_mode == PDC_DEMOD_SCALAR) ? pdc::DEMOD_SCALAR_ONLY : 0u;
+  dm.kernel_pending  = true;
+  return launch_now ? demod_kernel_launch(ctx, dm, s) : PDC_OK;
+}
+
+// Soft bits of a codeword: the resource elements of its OFDM symbols times the bits per element
+// (pusch_demodulator_impl.cpp:143-174). 0 for a description the plan will reject.
+static size_t codeword_soft_bits(const pdc_cw_desc& d)
+{
+  if (d.nof_symbols == 0 || d.start_symbol_index + d.nof_symbols > 14 || (d.dmrs_type != 1 && d.dmrs_type != 2)) {
+    return 0;
+  }
+  const int per_prb_dmrs = d.nof_cdm_groups_without_data * ((d.dmrs_type == 1) ? 6 : 4);
+  if (per_prb_dmrs > 12) {
+    return 0;
+  }
+  size_t n_re = 0;
+  for (unsigned l = d.start_symbol_index; l != (unsigned)d.start_symbol_index + d.nof_symbols; ++l) {
+    n_re += (size_t)d.nof_prb * (((d.dmrs_symbol_mask >> l) & 1u) ? (12 - per_prb_dmrs) : 12);
+  }
+  return n_re * d.qm * d.nof_layers;
+}
+
+int pdc_submit_symbols(pdc_ctx*           ctx,
+                       uint32_t           stream,
+                       const pdc_cw_desc* cws,
+                       uint32_t           n_cw,
+                       const uint32_t*    sym_offsets,
+                       const float*       symbols,
+                       const float*       noise_vars,
+                       size_t             n_sym,
+                       int8_t*            uci_out,
+                       size_t             uci_capacity,
+                       pdc_cw_result*     results)
+{
+  if (!ctx || stream >= ctx->queues.size() || !cws || n_cw == 0 || n_cw > 65535u || !sym_offsets || !symbols ||
+      !noise_vars || n_sym == 0 || n_sym > 0xffffffffu || !results) {
+    return fail(PDC_ERR_INVALID, "pdc_submit_symbols: invalid argument");
+  }
+  Queue& q = ctx->queues[stream];
+  if (q.busy || q.fe.pending) {
+    return fail(PDC_ERR_CAPACITY, "pdc_submit_symbols: queue busy (call pdc_wait first)");
+  }
+  size_t n_raw = 0;
+  for (uint32_t i = 0; i != n_cw; ++i) {
+    if (!(cws[i].flags & PDC_CW_SCRAMBLED)) {
+      return fail(PDC_ERR_INVALID, "pdc_submit_symbols: the demapper's soft bits are scrambled (PDC_CW_SCRAMBLED)");
+    }
+    n_raw = std::max(n_raw, (size_t)cws[i].in_offset + codeword_soft_bits(cws[i]));
+  }
+  if (n_raw > 0xfffffff0u) {
+    return fail(PDC_ERR_CAPACITY, "pdc_submit_symbols: too many soft bits");
+  }
+  FrontEnd& fe = q.fe;
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  PDC_CUDA(grow_device(&fe.d_raw, &fe.raw_cap, n_raw + 16));
+  PDC_CUDA(grow_device(&fe.dm.d_sym, &fe.dm.sym_cap, n_sym));
+  PDC_CUDA(grow_device(&fe.dm.d_nv, &fe.dm.nv_cap, n_sym));
+  PDC_CUDA(cudaMemcpyAsync(fe.dm.d_sym, symbols, n_sym * sizeof(float2), cudaMemcpyHostToDevice, q.stream));
+  PDC_CUDA(cudaMemcpyAsync(fe.dm.d_nv, noise_vars, n_sym * sizeof(float), cudaMemcpyHostToDevice, q.stream));
+  int rc = front_end_launch(ctx, fe, cws, n_cw, n_raw, fe.d_raw, q.d_llrs, ctx->cfg.max_llrs,
+                            uci_out ? uci_capacity : (size_t)-1, nullptr, results, q.stream, nullptr, false);
+  if (rc != PDC_OK) {
+    fe.kernels_pending = false;
+    return rc;
+  }
+  // One demodulate_soft call per OFDM symbol of each codeword (pusch_demodulator_impl.cpp:231-247).
+  fe.dm.calls.clear();
+  for (uint32_t i = 0; i != n_cw; ++i) {
+    const pdc::UlschCodeword& cw = fe.plan.cws[i];
+    const uint32_t            qm = cw.qm;
+    const uint32_t            mod =
+        (qm == 1) ? ((cws[i].flags & PDC_CW_PLAIN_BPSK) ? PDC_MOD_BPSK : PDC_MOD_PI_2_BPSK) : qm;
+    for (uint32_t k = 0; k != cw.n_sym; ++k) {
+      const pdc::UlschSymbol& sy   = fe.plan.syms[cw.sym_first + k];
+      const uint32_t          next = (k + 1 != cw.n_sym) ? fe.plan.syms[cw.sym_first + k + 1].in_off : cw.n_in;
+      fe.dm.calls.push_back(
+          pdc::DemodCall{sym_offsets[i] + sy.in_off / qm, (next - sy.in_off) / qm, cw.in_off + sy.in_off, mod});
+    }
+  }
+  rc = demod_prepare(ctx, fe.dm, fe.dm.d_sym, fe.dm.d_nv, n_sym, fe.d_raw, n_raw, q.stream, false);
+  if (rc != PDC_OK) {
+    fe.kernels_pending = false;
+    return rc;
+  }
+  fe.u_uci        = nullptr;
+  fe.uci_copy_dst = nullptr;
+  if (uci_out && fe.uci_bytes != 0) {
+    const bool direct = is_pinned_host(uci_out);
+    fe.uci_copy_dst   = direct ? uci_out : fe.h_uci;
+    fe.u_uci          = direct ? nullptr : uci_out;
+  }
+  fe.pending = true;
+  return PDC_OK;
+}
+
+int pdc_launch_demod_device(pdc_ctx*              ctx,
+                            const pdc_demod_call* calls,
+                            uint32_t              n_calls,
+                            const void*           d_symbols,
+                            const void*           d_noise_vars,
+                            size_t                n_sym,
+                            void*                 d_llrs,
+                            size_t                llr_capacity,
+                            void*                 cuda_stream)
+{
+  if (!ctx || !calls || n_calls == 0 || !d_symbols || !d_noise_vars || !d_llrs) {
+    return fail(PDC_ERR_INVALID, "pdc_launch_demod_device: invalid argument");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  DemodStage& dm = ctx->fe_sync.dm;
+  dm.calls.clear();
+  for (uint32_t i = 0; i != n_calls; ++i) {
+    dm.calls.push_back(pdc::DemodCall{calls[i].sym_offset, calls[i].n_sym, calls[i].llr_offset, calls[i].modulation});
+  }
+  return demod_prepare(ctx, dm, static_cast<const float2*>(d_symbols), static_cast<const float*>(d_noise_vars), n_sym,
+                       static_cast<int8_t*>(d_llrs), llr_capacity, static_cast<cudaStream_t>(cuda_stream), true);
+}
+
+int pdc_demodulate_soft(pdc_ctx*     ctx,
+                        int8_t*      llrs,
+                        const float* symbols,
+                        const float* noise_vars,
+                        uint32_t     n,
+                        int          modulation)
+{
+  if (!ctx || !llrs || !symbols || !noise_vars) {
+    return fail(PDC_ERR_INVALID, "pdc_demodulate_soft: invalid argument");
+  }
+  if (n == 0) {
+    return PDC_OK;
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  FrontEnd&    fe = ctx->fe_sync;
+  const size_t qm = (modulation == PDC_MOD_PI_2_BPSK) ? 1 : (size_t)modulation;
+  PDC_CUDA(grow_device(&fe.d_raw, &fe.raw_cap, (size_t)n * 8 + 16));
+  PDC_CUDA(grow_device(&fe.dm.d_sym, &fe.dm.sym_cap, (size_t)n));
+  PDC_CUDA(grow_device(&fe.dm.d_nv, &fe.dm.nv_cap, (size_t)n));
+  PDC_CUDA(cudaMemcpyAsync(fe.dm.d_sym, symbols, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, nullptr));
+  PDC_CUDA(cudaMemcpyAsync(fe.dm.d_nv, noise_vars, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, nullptr));
+  fe.dm.calls.assign(1, pdc::DemodCall{0u, n, 0u, (uint32_t)modulation});
+  int rc = demod_prepare(ctx, fe.dm, fe.dm.d_sym, fe.dm.d_nv, n, fe.d_raw, (size_t)n * 8, nullptr, true);
+  if (rc != PDC_OK) {
+    cudaStreamSynchronize(nullptr);
+    return rc;
+  }
+  PDC_CUDA(cudaMemcpyAsync(llrs, fe.d_raw, (size_t)n * qm, cudaMemcpyDeviceToHost, nullptr));
+  PDC_CUDA(cudaStreamSynchronize(nullptr));
   return PDC_OK;
 }
 

@@ -199,13 +199,37 @@ def gen_frontend(orc):
                         outs=np.concatenate(outs), lens=np.array(lens, np.int64))
 
 
+def gen_demod():
+    """demodulation_mapper_impl::demodulate_soft of the compiled reference (x86 build: AVX2 blocks + scalar remainder) on
+    every modulation, call sizes with and without a remainder, and the four input families of tests.vectors.demod_inputs."""
+    from tests.vectors import DEMOD_MODS, demod_inputs
+    ref = po.Reference()
+    rng = np.random.default_rng(2024)
+    cases, syms, nvs, outs = [], [], [], []
+    for mod in DEMOD_MODS:
+        for kind in range(4):
+            for n in (1, 3, 4, 7, 16, 24, 36, 45, 132, 300):
+                s, nv = demod_inputs(rng, n, mod, kind)
+                o = ref.demodulate_soft(s, nv, mod)
+                cases.append((mod, kind, n))
+                syms.append(s)
+                nvs.append(nv)
+                outs.append(o)
+    np.savez_compressed(OUT / "ref_demod.npz", cases=np.array(cases, np.int32), symbols=np.concatenate(syms),
+                        noise_vars=np.concatenate(nvs), llrs=np.concatenate(outs))
+
+
 if __name__ == "__main__":
     orc = po.Oracle()
+    if "--demod-only" in sys.argv:
+        gen_demod()
+        sys.exit(0)
     if "--frontend-only" in sys.argv:
         gen_frontend(orc)
         sys.exit(0)
     gen_examples()
     gen_frontend(orc)
+    gen_demod()
     gen_decoder(orc)
     gen_dematcher()
     gen_pusch(orc)

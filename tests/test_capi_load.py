@@ -34,7 +34,8 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(capi.CbResult) == 4 and capi.CB_RESULT_DTYPE.itemsize == 4
     assert ctypes.sizeof(capi.TbDesc) == 20 and capi.TB_DESC_DTYPE.itemsize == 20
     assert ctypes.sizeof(capi.TbResult) == 4 and capi.TB_RESULT_DTYPE.itemsize == 4
-    assert ctypes.sizeof(capi.Config) == 36
+    assert ctypes.sizeof(capi.Config) == 40
+    assert capi.DEMOD_CALL_DTYPE.itemsize == 16
     for f, _ in capi.CbDesc._fields_:
         assert capi.CB_DESC_DTYPE.fields[f][1] == getattr(capi.CbDesc, f).offset
 

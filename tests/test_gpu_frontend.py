@@ -198,6 +198,9 @@ def test_deferred_descrambling_in_the_dematcher(ctx, orc, qm, nl, nprb, rate):
         state.append(dict(cfg=cfg, n=n, src=src, n_sch=n_sch, tbs_bits=tbs_bits, C=C, tb=tb,
                           c_init=int(rng.integers(0, 1 << 31))))
     first_id = {0: 300, 1: 700}  # HARQ entries of the chain / of the direct decode
+    for base in first_id.values():  # both sets start from the same (empty) soft buffers whatever ran before
+        for i in range(sum(st["C"] for st in state)):
+            ctx.harq_write(base + i, np.zeros(capi.PDC_MAX_CB_SOFT, np.int8))
     for tx, rv in enumerate([0, 2]):
         raws, schs, cws, cb_chain, cb_direct = [], [], [], [], []
         in_off = sch_off = uci_off = cb_pos = 0

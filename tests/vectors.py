@@ -161,3 +161,79 @@ def ulsch_case(orc, rng, max_prb=40):
         rc, outs = orc.ulsch_demux(cfg, llr, seq)
         if rc == 0:
             return cfg, llr, seq, outs
+
+
+# ---- soft demapper ------------------------------------------------------------------------------------------------------
+
+DEMOD_MODS = (0, 1, 2, 4, 6, 8)  # pi/2-BPSK, BPSK, QPSK, 16QAM, 64QAM, 256QAM
+_QAM_UNIT = {0: 1.0, 1: 1.0, 2: 1.0, 4: 1 / np.sqrt(10), 6: 1 / np.sqrt(42), 8: 1 / np.sqrt(170)}
+
+
+def demod_inputs(rng, n, mod, kind):
+    """Symbols and noise variances of one demodulate_soft call. kind 0: plausible equaliser output; 1: magnitudes over
+    nine decades; 2: values on (and one or two ulps around) the interval boundaries of the piecewise-linear LLR
+    functions with noise variances that make rounding ties; 3: zeros, denormals, near-zero thresholds, infinities, NaNs,
+    negative / zero / infinite / NaN noise variances."""
+    if kind == 0:
+        s = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.8
+        nv = np.abs(rng.standard_normal(n)) * 0.05 + 1e-3
+    elif kind == 1:
+        s = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 10.0 ** rng.uniform(-6, 3, n)
+        nv = 10.0 ** rng.uniform(-4, 2, n)
+    elif kind == 2:
+        s = ((rng.integers(-20, 21, n) + 1j * rng.integers(-20, 21, n)) * np.float32(_QAM_UNIT[mod])).astype(np.complex64)
+        re = s.real.copy().view(np.int32)
+        re += rng.integers(-2, 3, n).astype(np.int32)
+        im = s.imag.copy()
+        s = np.empty(n, np.complex64)
+        s.real, s.imag = re.view(np.float32), im
+        nv = rng.choice(np.array([0.5, 1, 0.25, 0.1, 1 / 3., 0.7, 2.0], np.float32), n)
+    else:
+        pool = np.array([0, -0.0, 1e-10, -1e-10, 1e-9, 2e-5, 3.2e-5, 3.1e-5, np.inf, -np.inf, np.nan, 1e30, -1e30, 3e9,
+                         -3e9, 2147483520.0, 0.3, -0.7, 1e-38, 1e-45], np.float32)
+        s = np.empty(n, np.complex64)
+        s.real, s.imag = rng.choice(pool, n), rng.choice(pool, n)
+        nv = rng.choice(np.array([0, -1, np.nan, np.inf, 1e-30, 1e30, 0.1, 1, 1e-45, -0.0], np.float32), n)
+    with np.errstate(all="ignore"):
+        return np.ascontiguousarray(s, np.complex64), np.ascontiguousarray(nv, np.float32)
+
+
+def ofdm_symbol_sizes(cfg):
+    """Modulation symbols of every OFDM symbol of a codeword that carries data = sizes of the demodulate_soft calls of
+    pusch_demodulator_impl.cpp:160-247 (resource elements x layers)."""
+    per_dmrs = 12 - cfg["nof_cdm_groups_without_data"] * (6 if cfg["dmrs_type"] == 1 else 4)
+    sizes = []
+    for l in range(cfg["start_symbol_index"], cfg["start_symbol_index"] + cfg["nof_symbols"]):
+        n_re = (per_dmrs if (cfg["dmrs_symbol_mask"] >> l) & 1 else 12) * cfg["nof_prb"]
+        if n_re:
+            sizes.append(n_re * cfg["nof_layers"])
+    return sizes
+
+
+def demod_codeword(orc, cfg, symbols, noise_vars, mod=None, simd=True):
+    """The soft bits pusch_demodulator_impl obtains for a codeword: one oracle demodulate_soft call per OFDM symbol."""
+    mod = cfg["qm"] if mod is None else mod
+    out, pos = [], 0
+    for n in ofdm_symbol_sizes(cfg):
+        out.append(orc.demodulate_soft(symbols[pos:pos + n], noise_vars[pos:pos + n], mod, simd))
+        pos += n
+    assert pos == symbols.size
+    return np.concatenate(out)
+
+
+def modulate(bits, qm, rng=None):
+    """TS 38.211 5.1 modulation mapper (QPSK .. 256QAM), written from the standard's formulas."""
+    b = bits.reshape(-1, qm).astype(np.float64)
+    s = 1 - 2 * b
+    if qm == 2:
+        re, im, norm = s[:, 0], s[:, 1], np.sqrt(2)
+    elif qm == 4:
+        re, im, norm = s[:, 0] * (2 - s[:, 2]), s[:, 1] * (2 - s[:, 3]), np.sqrt(10)
+    elif qm == 6:
+        re, im = s[:, 0] * (4 - s[:, 2] * (2 - s[:, 4])), s[:, 1] * (4 - s[:, 3] * (2 - s[:, 5]))
+        norm = np.sqrt(42)
+    else:
+        re = s[:, 0] * (8 - s[:, 2] * (4 - s[:, 4] * (2 - s[:, 6])))
+        im = s[:, 1] * (8 - s[:, 3] * (4 - s[:, 5] * (2 - s[:, 7])))
+        norm = np.sqrt(170)
+    return ((re + 1j * im) / norm).astype(np.complex64)
