@@ -448,3 +448,70 @@ std::unique_ptr<ulsch_demultiplex> srsran::cuda::create_ulsch_demultiplex_cuda(s
   }
   return std::make_unique<ulsch_demultiplex_cuda>(std::move(ctx));
 }
+
+// ---- soft demapper ---------------------------------------------------------------------------------------------------
+
+void demodulation_mapper_cuda::demodulate_soft(span<log_likelihood_ratio> llrs,
+                                               span<const cf_t>           symbols,
+                                               span<const float>          noise_vars,
+                                               modulation_scheme          mod)
+{
+  srsran_assert(symbols.size() == noise_vars.size(), "Inputs symbols and noise_vars must have the same length.");
+  srsran_assert(symbols.size() * get_bits_per_symbol(mod) == llrs.size(), "Input and output lengths are incompatible.");
+  int m = PDC_MOD_QAM256;
+  switch (mod) {
+    case modulation_scheme::PI_2_BPSK:
+      m = PDC_MOD_PI_2_BPSK;
+      break;
+    case modulation_scheme::BPSK:
+      m = PDC_MOD_BPSK;
+      break;
+    case modulation_scheme::QPSK:
+      m = PDC_MOD_QPSK;
+      break;
+    case modulation_scheme::QAM16:
+      m = PDC_MOD_QAM16;
+      break;
+    case modulation_scheme::QAM64:
+      m = PDC_MOD_QAM64;
+      break;
+    default:
+      break;
+  }
+  // log_likelihood_ratio is a one-byte wrapper of int8_t and cf_t is two floats: the spans are passed as they are.
+  static_assert(sizeof(log_likelihood_ratio) == 1 && sizeof(cf_t) == 8, "unexpected layout");
+  int rc = pdc_demodulate_soft(ctx->get(),
+                               reinterpret_cast<int8_t*>(llrs.data()),
+                               reinterpret_cast<const float*>(symbols.data()),
+                               noise_vars.data(),
+                               static_cast<uint32_t>(symbols.size()),
+                               m);
+  srsran_assert(rc == PDC_OK, "pdc_demodulate_soft failed: {}", pdc_last_error());
+  (void)rc;
+}
+
+namespace {
+class channel_modulation_factory_cuda : public channel_modulation_factory
+{
+public:
+  explicit channel_modulation_factory_cuda(std::shared_ptr<context> c) :
+    ctx(std::move(c)), sw(create_channel_modulation_sw_factory())
+  {
+  }
+  std::unique_ptr<modulation_mapper>   create_modulation_mapper() override { return sw->create_modulation_mapper(); }
+  std::unique_ptr<demodulation_mapper> create_demodulation_mapper() override
+  {
+    return std::make_unique<demodulation_mapper_cuda>(ctx);
+  }
+  std::unique_ptr<evm_calculator> create_evm_calculator() override { return sw->create_evm_calculator(); }
+
+private:
+  std::shared_ptr<context>                    ctx;
+  std::shared_ptr<channel_modulation_factory> sw;
+};
+} // namespace
+
+std::shared_ptr<channel_modulation_factory> srsran::cuda::create_channel_modulation_cuda_factory(std::shared_ptr<context> ctx)
+{
+  return std::make_shared<channel_modulation_factory_cuda>(std::move(ctx));
+}

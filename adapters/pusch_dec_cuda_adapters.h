@@ -11,6 +11,9 @@
 ///   ulsch_demultiplex_cuda        : srsran::ulsch_demultiplex + pusch_codeword_buffer
 ///                                   (phy/upper/channel_processors/pusch/ulsch_demultiplex.h:41-103,
 ///                                   pusch_codeword_buffer.h), the step that feeds pusch_decoder_buffer::on_new_softbits.
+///   demodulation_mapper_cuda      : srsran::demodulation_mapper     (phy/upper/channel_modulation/demodulation_mapper.h:41-69),
+///                                   created by create_channel_modulation_cuda_factory() in the place of
+///                                   create_channel_modulation_sw_factory() (channel_modulation_factories.h:32-41).
 /// and the factories a "cuda" branch of create_ldpc_decoder_factory_sw / create_ldpc_rate_dematcher_factory_sw /
 /// create_crc_calculator_factory_sw / create_hw_accelerator_pusch_dec_factory returns.
 #pragma once
@@ -19,6 +22,7 @@
 #include "srsran/hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec.h"
 #include "srsran/hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec_factory.h"
 #include "srsran/phy/upper/channel_coding/channel_coding_factories.h"
+#include "srsran/phy/upper/channel_modulation/channel_modulation_factories.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_codeword_buffer.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_buffer.h"
 #include "srsran/phy/upper/channel_processors/pusch/ulsch_demultiplex.h"
@@ -164,6 +168,25 @@ private:
   std::vector<int8_t>               out_sch, out_uci;
   size_t                            count = 0;
 };
+
+/// \brief Soft demapper in the demodulation_mapper slot: one demodulate_soft call = one pdc_demodulate_soft call (bit-exact
+/// with the x86 build of demodulation_mapper_impl, SIMD blocks and scalar remainder of the call included).
+class demodulation_mapper_cuda : public demodulation_mapper
+{
+public:
+  explicit demodulation_mapper_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  void demodulate_soft(span<log_likelihood_ratio> llrs,
+                       span<const cf_t>           symbols,
+                       span<const float>          noise_vars,
+                       modulation_scheme          mod) override;
+
+private:
+  std::shared_ptr<context> ctx;
+};
+
+/// Channel-modulation factory whose demodulation mapper runs on the GPU; the modulation mapper and the EVM calculator are
+/// the software ones (they are not on the uplink decode path).
+std::shared_ptr<channel_modulation_factory> create_channel_modulation_cuda_factory(std::shared_ptr<context> ctx);
 
 std::shared_ptr<ldpc_decoder_factory>        create_ldpc_decoder_factory_cuda(std::shared_ptr<context> ctx);
 std::shared_ptr<ldpc_rate_dematcher_factory> create_ldpc_rate_dematcher_factory_cuda(std::shared_ptr<context> ctx);

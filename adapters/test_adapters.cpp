@@ -417,6 +417,42 @@ int main()
     std::printf("ulsch_demultiplex_cuda: %u configurations compared with ulsch_demultiplex_impl\n", checked);
     CHECK(checked >= 30, "too few UL-SCH demultiplexing configurations were checked");
   }
+  // ---- soft demapper: demodulation_mapper_cuda vs demodulation_mapper_impl ------------------------------------------------
+  {
+    auto dm_sw  = create_channel_modulation_sw_factory()->create_demodulation_mapper();
+    auto dm_gpu = cuda::create_channel_modulation_cuda_factory(ctx)->create_demodulation_mapper();
+    const modulation_scheme mods[] = {modulation_scheme::PI_2_BPSK, modulation_scheme::BPSK, modulation_scheme::QPSK,
+                                      modulation_scheme::QAM16, modulation_scheme::QAM64, modulation_scheme::QAM256};
+    std::normal_distribution<float>       gauss(0.0F, 0.8F);
+    std::uniform_real_distribution<float> uni(0.0F, 1.0F);
+    unsigned                              checked = 0;
+    for (int trial = 0; trial != 120; ++trial) {
+      modulation_scheme mod = mods[trial % 6];
+      unsigned          n   = 1 + rng() % 4000;
+      unsigned          qm  = get_bits_per_symbol(mod);
+      std::vector<cf_t>  sym(n);
+      std::vector<float> nv(n);
+      for (unsigned i = 0; i != n; ++i) {
+        sym[i] = cf_t(gauss(rng), gauss(rng));
+        nv[i]  = 0.001F + 0.1F * uni(rng);
+        if (trial % 5 == 4 && rng() % 16 == 0) {
+          // ill-formed inputs: zero / negative / NaN / infinite noise variances, tiny and huge symbols
+          const float bad[] = {0.0F, -1.0F, NAN, INFINITY, 1e-30F};
+          nv[i]             = bad[rng() % 5];
+          if (rng() % 2) {
+            sym[i] = cf_t(1e-10F * gauss(rng), (rng() % 2) ? 1e20F : 0.0F);
+          }
+        }
+      }
+      std::vector<log_likelihood_ratio> a(n * qm), b(n * qm);
+      dm_sw->demodulate_soft(a, sym, nv, mod);
+      dm_gpu->demodulate_soft(b, sym, nv, mod);
+      CHECK(std::equal(a.begin(), a.end(), b.begin()), "demodulation mapper: soft bits differ (trial %d, %s, %u symbols)",
+            trial, to_string(mod).c_str(), n);
+      ++checked;
+    }
+    std::printf("demodulation_mapper_cuda: %u demodulate_soft calls compared with demodulation_mapper_impl\n", checked);
+  }
   std::printf(failures ? "FAILED: %d checks\n" : "PASS (%d failures)\n", failures);
   return failures ? 1 : 0;
 }
