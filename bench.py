@@ -359,6 +359,163 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
     return out
 
 
+def symbol_legs(ctx, orc, capi, torch, stream, args):
+    """Configs 3 and 4 entered at the channel equaliser's output: equalised 256QAM symbols + noise
+    variances -> soft demapper -> (deferred) descrambling -> rate dematcher -> LDPC -> TB, all on the device. Reports the
+    demapper kernel against the HBM roofline (12 B read + 8 B written per 256QAM symbol), the slot with the demapper in
+    the chain, and the slot end to end from HOST symbol buffers through pdc_submit_symbols + pdc_submit."""
+    from srsran_edgeric_5g_b200 import ldpc
+    from tests.vectors import modulate, ofdm_symbol_sizes
+    rng = np.random.default_rng(5)
+    tbs_bits, n_llr, qm, nl = 1277992, 1362816, 8, 4
+    n_sym = n_llr // qm
+    C = ldpc.compute_nof_codeblocks(tbs_bits, 1)
+    nref = ldpc.compute_N_ref(tbs_bits // 8, C)
+    tb = rng.integers(0, 256, tbs_bits // 8).astype(np.uint8)
+    cw_bits, _ = orc.tb_encode(tb, 1, 0, qm, nref, nl, n_llr)
+    metas = ldpc.segment_rx(tbs_bits, 1, 0, qm, nref, nl, n_llr)
+    cfg = dict(qm=qm, nof_layers=nl, nof_prb=273, start_symbol_index=0, nof_symbols=14, dmrs_type=1,
+               dmrs_symbol_mask=1 << 2, nof_cdm_groups_without_data=2)
+    sizes = ofdm_symbol_sizes(cfg)
+    assert sum(sizes) == n_sym
+    snr_db = 36.0  # the TB is rate 0.94 on 256QAM
+    sigma2 = 10 ** (-snr_db / 10)
+    pk, pk_src = peaks()
+    out = {}
+    for name, cells in (("config3_slot_1cell", 1), ("config4_slot_16cells", 16)):
+        n_cb = C * cells
+        if n_cb > ctx.cfg.max_cbs:
+            continue
+        cbs = np.zeros(n_cb, capi.CB_DESC_DTYPE)
+        tbd = np.zeros(cells, capi.TB_DESC_DTYPE)
+        flags = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA
+        tb_stride = (tbs_bits + 24 + 31) // 32 * 4
+        cws = np.zeros(cells, capi.CW_DESC_DTYPE)
+        syms, calls = [], []
+        for c in range(cells):
+            tbd[c] = (c * C, C, tbs_bits, c * tb_stride, 0)
+            for k, m in enumerate(metas):
+                cbs[c * C + k] = (c * n_llr + m.cw_offset, m.rm_length, c * C + k, nref, m.lifting_size, m.nof_filler_bits,
+                                  1, qm, 0, capi.CRC24B, MAX_ITER, flags, c)
+            c_init = (0x4601 + c) * 32768 + 17 * c
+            cws[c]["in_offset"], cws[c]["sch_offset"], cws[c]["c_init"] = c * n_llr, c * n_llr, c_init
+            cws[c]["flags"] = capi.CW_SCRAMBLED | capi.CW_DEFER_DESCRAMBLING
+            for k, v in cfg.items():
+                cws[c][k] = v
+            tx = modulate(cw_bits ^ orc.prg_bits(c_init, 0, n_llr), qm)
+            noise = (rng.standard_normal(n_sym) + 1j * rng.standard_normal(n_sym)) * np.sqrt(sigma2 / 2)
+            syms.append((tx + noise).astype(np.complex64))
+            pos = 0
+            for n in sizes:  # one demodulate_soft call per OFDM symbol (pusch_demodulator_impl.cpp:231-247)
+                calls.append((c * n_sym + pos, n, c * n_llr + pos * qm, qm))
+                pos += n
+        sym_all = np.concatenate(syms)
+        nv_all = np.full(sym_all.size, sigma2, np.float32)
+        calls = np.array(calls, capi.DEMOD_CALL_DTYPE)
+        d_sym = torch.from_numpy(sym_all.view(np.float32)).cuda()
+        d_nv = torch.from_numpy(nv_all).cuda()
+        d_raw = torch.zeros(cells * n_llr + 16, dtype=torch.int8, device="cuda")
+        d_sch = torch.zeros(cells * n_llr + 16, dtype=torch.int8, device="cuda")
+        d_cbs = torch.from_numpy(cbs.view(np.uint8)).cuda()
+        d_tbs = torch.from_numpy(tbd.view(np.uint8)).cuda()
+        d_res = torch.zeros(n_cb * 4, dtype=torch.uint8, device="cuda")
+        d_bits = torch.zeros(n_cb * capi.PDC_MAX_CB_BYTES, dtype=torch.uint8, device="cuda")
+        d_tres = torch.zeros(cells * 4, dtype=torch.uint8, device="cuda")
+        d_tb = torch.zeros(cells * tb_stride + 16, dtype=torch.uint8, device="cuda")
+
+        def demod():
+            ctx.launch_demod_device(calls, d_sym.data_ptr(), d_nv.data_ptr(), sym_all.size, d_raw.data_ptr(),
+                                    cells * n_llr, cuda_stream=stream.cuda_stream)
+
+        def chain():
+            demod()
+            ctx.launch_codewords_device(cws, d_raw.data_ptr(), cells * n_llr, d_sch.data_ptr(), cells * n_llr,
+                                        cuda_stream=stream.cuda_stream)
+            ctx.launch_device(d_cbs.data_ptr(), n_cb, d_sch.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), 384, flags,
+                              True, cuda_stream=stream.cuda_stream, d_tbs=d_tbs.data_ptr(), n_tb=cells,
+                              d_tb_results=d_tres.data_ptr(), d_tb_bytes=d_tb.data_ptr())
+
+        times = {}
+        reps = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for label, fn in (("demod", demod), ("chain", chain)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            times[label] = e0.elapsed_time(e1) / reps * 1e3
+        tres = d_tres.cpu().numpy().view(capi.TB_RESULT_DTYPE)
+        tb_ok = bool(tres["tb_crc_ok"].all()) and bool((d_tb.cpu().numpy()[:tbs_bits // 8] == tb).all())
+        # spot check of the demapper against the oracle: the first and the last OFDM symbol of cell 0
+        raw0 = d_raw[:n_llr].cpu().numpy()
+        want_first = orc.demodulate_soft(sym_all[:sizes[0]], nv_all[:sizes[0]], qm)
+        want_last = orc.demodulate_soft(sym_all[n_sym - sizes[-1]:n_sym], nv_all[:sizes[-1]], qm)
+        demod_ok = bool((raw0[:want_first.size] == want_first).all() and (raw0[-want_last.size:] == want_last).all())
+        demod_bytes = sym_all.size * (12 + qm)
+        # ---- end to end with HOST buffers: symbols + noise variances in page-locked memory -> TB bytes ------------------
+        NQ = 3
+        ctx3 = capi.Context(device=torch.cuda.current_device(), max_cbs=n_cb, max_llrs=cells * n_llr + 64,
+                            harq_entries=NQ * n_cb, max_tbs=cells, max_tb_bytes=cells * tb_stride + 64, nof_streams=NQ)
+        sym_pin = [capi.PinnedBuffer(sym_all.size * 8, np.complex64) for _ in range(NQ)]
+        nv_pin = [capi.PinnedBuffer(sym_all.size * 4, np.float32) for _ in range(NQ)]
+        bits_pin = [capi.PinnedBuffer(n_cb * capi.PDC_MAX_CB_BYTES, np.uint8) for _ in range(NQ)]
+        tb_pin = [capi.PinnedBuffer(cells * tb_stride + 64, np.uint8) for _ in range(NQ)]
+        for q in range(NQ):
+            sym_pin[q].array[:] = sym_all
+            nv_pin[q].array[:] = nv_all
+        sym_offsets = (np.arange(cells) * n_sym).astype(np.uint32)
+        cbs_q = []
+        for q in range(NQ):
+            c2 = cbs.copy()
+            c2["harq_id"] += q * n_cb
+            cbs_q.append(c2)
+
+        def slot(i):
+            q = i % NQ
+            ctx3.submit_symbols(cws, sym_offsets, sym_pin[q].array, nv_pin[q].array, stream=q)
+            return ctx3.submit(cbs_q[q], None, tbd, stream=q, out_bits=bits_pin[q].array, out_tb=tb_pin[q].array)
+
+        def run(n):
+            last = None
+            for i in range(n):
+                if i >= NQ:
+                    ctx3.wait(i % NQ)
+                slot(i)
+            for i in range(n, n + NQ):
+                r = ctx3.wait(i % NQ)
+                last = r if r is not None else last
+            return last
+
+        run(2 * NQ + 4)
+        n_slots = 40
+        t0 = time.perf_counter()
+        last = run(n_slots)
+        t1 = time.perf_counter()
+        us_e2e = (t1 - t0) / n_slots * 1e6
+        e2e = {"us_per_slot": us_e2e, "value": cells * tbs_bits / (us_e2e * 1e-6) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_slot": sym_all.size * 12 + n_cb * 28 + cells * 60,
+               "d2h_bytes_per_slot": n_cb * (capi.PDC_MAX_CB_BYTES + 4) + cells * tb_stride, "slots_in_flight": NQ,
+               "tb_crc_ok": bool(last["tb_results"]["tb_crc_ok"].all()),
+               "tb_bytes_match": bool((last["tb_bytes"][:tbs_bits // 8] == tb).all())}
+        ctx3.close()
+        out[f"{name}_from_symbols"] = {
+            "us_demod": times["demod"], "us_per_slot_with_demod": times["chain"], "symbols": int(sym_all.size),
+            "demod_calls": int(calls.size), "demod_equals_oracle": demod_ok, "tb_crc_ok_and_bytes_match": tb_ok,
+            "snr_db": snr_db, "value": cells * tbs_bits / (times["chain"] * 1e-6) / 1e9, "unit": UNIT,
+            "roofline_demod": {"kernel": "demod_kernel", "bound": "hbm", "achieved": demod_bytes / (times["demod"] * 1e-6) / 1e9,
+                               "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": demod_bytes / (times["demod"] * 1e-6) / 1e9 / pk["hbm_gbs"],
+                               "bytes_per_launch": demod_bytes, "traffic": profiled_traffic("demod_kernel"),
+                               "peak_source": pk_src,
+                               "note": "incl. the upload of the call table and the launch; 12 B read + 8 B written per symbol"},
+            "e2e_host_buffers": e2e}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,7 +553,9 @@ def main():
     if args.only_slots:
         ctx2 = capi.Context(device=local_rank, max_cbs=2432, max_llrs=1 << 20, harq_entries=2432, max_tbs=16,
                             max_tb_bytes=16 * 160000, nof_streams=1)
-        print(json.dumps(slot_legs(ctx2, orc, capi, torch, torch.cuda.current_stream(), args)))
+        legs = slot_legs(ctx2, orc, capi, torch, torch.cuda.current_stream(), args)
+        legs.update(symbol_legs(ctx2, orc, capi, torch, torch.cuda.current_stream(), args))
+        print(json.dumps(legs))
         ctx2.close()
         return
     n_cb = args.n_cb
@@ -587,6 +746,7 @@ def main():
             ctx2 = capi.Context(device=local_rank, max_cbs=2432, max_llrs=1 << 20, harq_entries=2432, max_tbs=16,
                                 max_tb_bytes=16 * 160000, nof_streams=1)
             line["extra"].update(slot_legs(ctx2, orc, capi, torch, stream, args))
+            line["extra"].update(symbol_legs(ctx2, orc, capi, torch, stream, args))
             ctx2.close()
             # ---- CPU baseline: the reference's own SIMD code on the host cores, bounded sample ---------------------------
             line["cpu_baseline"] = cpu_reference_rate(llrs_np[:2048], False, 12.0, os.cpu_count() or 1)

@@ -12,8 +12,10 @@
 // "0.8 - gain * |x|" in the scalar loop) into one FMA; every other operation is a separate IEEE single-precision
 // operation, written with the _rn intrinsics so that nvcc cannot contract anything else.
 //
-// HBM-bound: 12 bytes read and Qm bytes written per symbol. One CTA per tile of DEMOD_TILE symbols of one call; soft bits
-// are staged in shared memory and leave in 16-byte words.
+// 12 bytes read and Qm bytes written per symbol. One CTA per tile of DEMOD_TILE symbols of one call, four symbols per
+// thread (all loads of a tile first; persistent CTAs striding over smaller tiles, with or without a one-tile look-ahead, measured slower: 26-28 us against 19.5 us per 16-cell slot); soft bits are staged in shared memory and leave in 16-byte words. The call table travels
+// in the kernel parameters, the piecewise-linear tables are computed once per context. At ~115 instructions per 256QAM
+// symbol the kernel sits between the issue and the HBM rooflines.
 #pragma once
 
 #include "pdc_device.cuh"
@@ -21,7 +23,9 @@
 namespace pdc {
 
 constexpr int      DEMOD_THREADS = 256;
-constexpr int      DEMOD_TILE    = 1024;
+constexpr int      DEMOD_TILE    = 1024; // symbols per tile (one tile per CTA), four per thread
+constexpr int      DEMOD_PER_THREAD = DEMOD_TILE / DEMOD_THREADS;
+constexpr int      DEMOD_MAX_CALLS = 224; // calls per launch: the call table travels in the kernel parameters
 constexpr uint32_t DEMOD_SCALAR_ONLY = 1u; // flags: the portable build of the reference (no SIMD blocks)
 
 struct DemodCall {
@@ -31,18 +35,17 @@ struct DemodCall {
   uint32_t mod;     // PDC_MOD_*
 };
 
-struct DemodTile {
-  uint32_t call;
-  uint32_t first; // first symbol of the tile inside its call
-};
-
+// Kernel parameters: the calls of this launch and the first tile (CTA) of each; no table in device memory, hence no
+// upload in front of the kernel.
 struct DemodArgs {
-  const DemodCall* calls;
-  const DemodTile* tiles;
-  const float2*    symbols;
-  const float*     noise_vars;
-  int8_t*          llrs;
-  uint32_t         flags;
+  DemodCall     calls[DEMOD_MAX_CALLS];
+  uint32_t      tile_start[DEMOD_MAX_CALLS + 1];
+  const float*  tables; // SmemTables image computed once per context (demod_tables_kernel)
+  uint32_t      n_calls;
+  uint32_t      flags;
+  const float2* symbols;
+  const float*  noise_vars;
+  int8_t*       llrs;
 };
 
 namespace demod {
@@ -73,26 +76,37 @@ __constant__ TableDef c_demod_tab[7] = {
     {8, 4, {4, -4, 4, -4, 4, -4, 4, -4}, {28, -20, 12, -4, -4, 12, -20, 28}},
 };
 
-// The tables in shared memory: per table 16 slopes, 16 intercepts, then {width, 1 / width}.
+// The tables in shared memory: per table 16 {slope, intercept} pairs, then {width, 1 / width}.
 struct SmemTables {
-  float slope[7][16];
-  float icpt[7][16];
-  float width[7];
-  float inv_width[7];
+  float2 si[7][16];
+  float  width[7];
+  float  inv_width[7];
 };
 
-__device__ __forceinline__ void build_tables(SmemTables& t, int tid)
+constexpr int TABLE_FLOATS = sizeof(SmemTables) / sizeof(float);
+
+// The tables, computed on the device with the reference's single-precision operations; run once per context.
+__global__ void demod_tables_kernel(float* image)
 {
+  SmemTables& t   = *reinterpret_cast<SmemTables*>(image);
+  const int   tid = threadIdx.x;
   if (tid < 7 * 16) {
     const int   g = tid >> 4, i = tid & 15;
     const float unit = (g < 3) ? U42 : U170, den = (g < 3) ? 21.0f : 85.0f;
-    t.slope[g][i] = __fmul_rn((float)c_demod_tab[g].slope_k[i], unit);
-    t.icpt[g][i]  = __fdiv_rn((float)c_demod_tab[g].icpt_num[i], den);
+    t.si[g][i] = make_float2(__fmul_rn((float)c_demod_tab[g].slope_k[i], unit),
+                             __fdiv_rn((float)c_demod_tab[g].icpt_num[i], den));
     if (i == 0) {
       const float w  = __fmul_rn((float)c_demod_tab[g].width_units, unit);
       t.width[g]     = w;
       t.inv_width[g] = __fdiv_rn(1.0f, w);
     }
+  }
+}
+
+__device__ __forceinline__ void load_tables(SmemTables& t, const float* image, int tid)
+{
+  if (tid < TABLE_FLOATS) {
+    reinterpret_cast<float*>(&t)[tid] = __ldg(image + tid);
   }
 }
 
@@ -114,21 +128,6 @@ __device__ __forceinline__ uint32_t quantize_scalar(float value, float range_lim
   return x86_f2i(roundf(q)) & 0xffu;
 }
 
-// mm256::quantize_ps (avx2_helpers.h:121-166), one element; scale = 120 / range_limit (6 or 5, exact).
-__device__ __forceinline__ uint32_t quantize_simd(float value, float scale)
-{
-  float v = __fmul_rn(value, scale);
-  if (v > 120.0f) {
-    v = 120.0f;
-  }
-  if (v < -120.0f) {
-    v = -120.0f;
-  }
-  v = rintf(v);
-  const int32_t i = (int32_t)x86_f2i(v);
-  return (i > 120 || i < -120) ? 0u : ((uint32_t)i & 0xffu);
-}
-
 __device__ __forceinline__ int interval_index(float q, int n)
 {
   const int32_t idx = (int32_t)(x86_f2i(floorf(q)) + (uint32_t)(n >> 1));
@@ -138,19 +137,95 @@ __device__ __forceinline__ int interval_index(float q, int n)
 // interval_function (demodulation_mapper_intervals.h:31-63).
 __device__ __forceinline__ float interval_scalar(const SmemTables& t, int g, int n, float value, float rcp_noise)
 {
-  const int k = interval_index(__fdiv_rn(value, t.width[g]), n);
-  return __fmul_rn(__fmaf_rn(t.slope[g][k], value, t.icpt[g][k]), rcp_noise);
+  const int    k  = interval_index(__fdiv_rn(value, t.width[g]), n);
+  const float2 si = t.si[g][k];
+  return __fmul_rn(__fmaf_rn(si.x, value, si.y), rcp_noise);
 }
 
-// mm256::interval_function (avx2_helpers.h:234-254).
-__device__ __forceinline__ float interval_simd(const SmemTables& t, int g, int n, float value, float rcp_noise)
+// ---- SIMD-block semantics, written for instruction count (this path takes all but the last few symbols of a call) ----
+
+__device__ __forceinline__ float max_nan(float a, float b)
 {
-  const int k = interval_index(__fmul_rn(value, t.inv_width[g]), n);
-  float     l = __fmul_rn(__fmaf_rn(t.slope[g][k], value, t.icpt[g][k]), rcp_noise);
-  if (fabsf(value) <= 1e-9f) {
-    l = 0.0f;
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float min_nan(float a, float b)
+{
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+// mm256::quantize_ps, one element: scale, clip to +-120 with a NaN passing through (the NaN-propagating min / max),
+// round to nearest even and convert - cvt.rni turns the NaN into the 0 that check_bounds_epi32 makes of it.
+__device__ __forceinline__ uint32_t quantize_fast(float value, float scale)
+{
+  return (uint32_t)__float2int_rn(min_nan(max_nan(__fmul_rn(value, scale), -120.0f), 120.0f));
+}
+
+// compute_interval_idx (avx2_helpers.h:174-193): clamp(int(floor(value / width)) + n / 2, 0, n - 1), where the x86
+// conversion of a floor at or beyond +-2^31 gives 0x80000000 and so lands in interval 0. cvt.rmi saturates instead
+// (+2^31 -> INT_MAX), but INT_MAX + n / 2 wraps negative as well and is clamped to the same interval 0; a NaN converts
+// to 0 here and to 0x80000000 there, which is immaterial because slope * NaN + intercept is NaN for every interval.
+__device__ __forceinline__ int interval_index_fast(float q, int half_n, int n_minus_1)
+{
+  return min(__viaddmax_s32(__float2int_rd(q), half_n, 0), n_minus_1);
+}
+
+// Four soft bits {a, b, c, d} -> one little-endian word.
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+// One symbol through the AVX2-kernel arithmetic (demodulation_mapper_qpsk.cpp:39-78, _qam16.cpp:41-116,
+// _qam64.cpp:185-283, _qam256.cpp:228-273). The "force zero where |value| <= 1e-9" blend of interval_function is applied
+// as a zero reciprocal of that component (a finite value times zero quantises to the same 0).
+template <uint32_t MOD>
+__device__ __forceinline__ uint64_t demod_symbol_simd(const SmemTables& t, float re, float im, float nv)
+{
+  const float rcp  = (nv > 0.0f) ? __frcp_rn(nv) : 0.0f; // safe_div(1, noise) (avx2_helpers.h:259-271); IEEE 1 / x
+  const float c[2] = {re, im};
+  if (MOD == PDC_MOD_QPSK) {
+    const uint32_t a = quantize_fast(__fmul_rn(__fmul_rn(GAIN_QPSK, re), rcp), 5.0f);
+    const uint32_t b = quantize_fast(__fmul_rn(__fmul_rn(GAIN_QPSK, im), rcp), 5.0f);
+    return __byte_perm(a, b, 0x0040) & 0xffffu;
   }
-  return l;
+  if (MOD == PDC_MOD_QAM16) {
+    const float gain = __fmul_rn(4.0f, U10), thr = __fmul_rn(2.0f, U10);
+    uint32_t    q[4];
+#pragma unroll
+    for (int k = 0; k != 2; ++k) {
+      const float first  = __fmul_rn(gain, c[k]);
+      const float second = __fsub_rn(__fmul_rn(2.0f, first), copysignf(0.8f, c[k]));
+      const float rc     = (fabsf(c[k]) <= 1e-9f) ? 0.0f : rcp;
+      const float l01    = (fabsf(c[k]) > thr) ? second : first;
+      const float l23    = __fsub_rn(0.8f, fabsf(first));
+      // |value| <= 1e-9: both values are finite, so the zero reciprocal gives the blended zero
+      q[k]     = quantize_fast(__fmul_rn(l01, rc), 6.0f);
+      q[2 + k] = quantize_fast(__fmul_rn(l23, rc), 6.0f);
+    }
+    return pack4(q[0], q[1], q[2], q[3]);
+  }
+  // 64QAM / 256QAM: the groups of width 2 units share their interval index, the last group has width 4 units.
+  constexpr bool Q256 = (MOD == PDC_MOD_QAM256);
+  constexpr int  G0 = Q256 ? 3 : 0, NG = Q256 ? 4 : 3, HALF_A = Q256 ? 8 : 4, HALF_B = Q256 ? 4 : 2;
+  const float    inv_a = t.inv_width[G0], inv_b = t.inv_width[G0 + NG - 1];
+  uint32_t       q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k != 2; ++k) {
+    const float v  = c[k];
+    const float rc = (fabsf(v) <= 1e-9f) ? 0.0f : rcp;
+    const int   ka = interval_index_fast(__fmul_rn(v, inv_a), HALF_A, 2 * HALF_A - 1);
+    const int   kb = interval_index_fast(__fmul_rn(v, inv_b), HALF_B, 2 * HALF_B - 1);
+#pragma unroll
+    for (int g = 0; g != NG; ++g) {
+      const float2 si = t.si[G0 + g][(g == NG - 1) ? kb : ka];
+      q[2 * g + k]    = quantize_fast(__fmul_rn(__fmaf_rn(si.x, v, si.y), rc), 6.0f);
+    }
+  }
+  return (uint64_t)pack4(q[0], q[1], q[2], q[3]) | ((uint64_t)pack4(q[4], q[5], q[6], q[7]) << 32);
 }
 
 // Soft bits of one symbol, byte k of the result = soft bit k. i_call = index of the symbol inside its call.
@@ -167,43 +242,13 @@ __device__ __forceinline__ uint64_t demod_symbol(const SmemTables& t, float re, 
     }
     return out;
   }
-  const float c[2] = {re, im};
   if (simd) {
-    const float rcp = (nv > 0.0f) ? __fdiv_rn(1.0f, nv) : 0.0f; // safe_div (avx2_helpers.h:259-271)
-    if (mod == PDC_MOD_QPSK) {
-#pragma unroll
-      for (int k = 0; k != 2; ++k) {
-        out |= (uint64_t)quantize_simd(__fmul_rn(__fmul_rn(GAIN_QPSK, c[k]), rcp), 5.0f) << (8 * k);
-      }
-    } else if (mod == PDC_MOD_QAM16) {
-      const float gain = __fmul_rn(4.0f, U10), thr = __fmul_rn(2.0f, U10);
-#pragma unroll
-      for (int k = 0; k != 2; ++k) {
-        const float first  = __fmul_rn(gain, c[k]);
-        const float second = __fsub_rn(__fmul_rn(2.0f, first), copysignf(0.8f, c[k]));
-        float       l01    = (fabsf(c[k]) > thr) ? second : first;
-        float       l23    = __fsub_rn(0.8f, fabsf(first));
-        l01                = __fmul_rn(l01, rcp);
-        l23                = __fmul_rn(l23, rcp);
-        if (fabsf(c[k]) <= 1e-9f) {
-          l01 = 0.0f;
-          l23 = 0.0f;
-        }
-        out |= (uint64_t)quantize_simd(l01, 6.0f) << (8 * k);
-        out |= (uint64_t)quantize_simd(l23, 6.0f) << (8 * (2 + k));
-      }
-    } else {
-      const int g0 = (mod == PDC_MOD_QAM64) ? 0 : 3, ng = (int)mod >> 1;
-      for (int g = 0; g != ng; ++g) {
-        const int n = c_demod_tab[g0 + g].n;
-#pragma unroll
-        for (int k = 0; k != 2; ++k) {
-          out |= (uint64_t)quantize_simd(interval_simd(t, g0 + g, n, c[k], rcp), 6.0f) << (8 * (2 * g + k));
-        }
-      }
-    }
-    return out;
+    return (mod == PDC_MOD_QAM256)  ? demod_symbol_simd<PDC_MOD_QAM256>(t, re, im, nv)
+           : (mod == PDC_MOD_QAM64) ? demod_symbol_simd<PDC_MOD_QAM64>(t, re, im, nv)
+           : (mod == PDC_MOD_QAM16) ? demod_symbol_simd<PDC_MOD_QAM16>(t, re, im, nv)
+                                    : demod_symbol_simd<PDC_MOD_QPSK>(t, re, im, nv);
   }
+  const float c[2] = {re, im};
   // Scalar remainder loops.
   if (mod == PDC_MOD_QPSK) {
     // demod_QPSK_symbol (demodulation_mapper_qpsk.cpp:121-129).
@@ -248,48 +293,103 @@ __device__ __forceinline__ uint64_t demod_symbol(const SmemTables& t, float re, 
   return out;
 }
 
+// Stores the qm soft bits of one symbol (byte k of v = soft bit k) into the staging area.
+__device__ __forceinline__ void stage_symbol(unsigned char* p, uint64_t v, uint32_t qm)
+{
+  if (qm == 8) {
+    *reinterpret_cast<uint2*>(p) = make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+  } else if (qm == 6) {
+    reinterpret_cast<uint16_t*>(p)[0] = (uint16_t)v;
+    reinterpret_cast<uint16_t*>(p)[1] = (uint16_t)(v >> 16);
+    reinterpret_cast<uint16_t*>(p)[2] = (uint16_t)(v >> 32);
+  } else if (qm == 4) {
+    *reinterpret_cast<uint32_t*>(p) = (uint32_t)v;
+  } else if (qm == 2) {
+    *reinterpret_cast<uint16_t*>(p) = (uint16_t)v;
+  } else {
+    *p = (unsigned char)v;
+  }
+}
+
+// A tile whose symbols all take the SIMD-block arithmetic: all loads before any arithmetic.
+template <uint32_t MOD>
+__device__ __forceinline__ void tile_simd(const SmemTables& tab, const DemodArgs& a, const DemodCall& call, uint32_t first,
+                                          uint32_t end, unsigned char* stage, int tid)
+{
+  float2 z[DEMOD_PER_THREAD];
+  float  nv[DEMOD_PER_THREAD];
+#pragma unroll
+  for (int r = 0; r != DEMOD_PER_THREAD; ++r) {
+    const uint32_t i = first + r * DEMOD_THREADS + tid;
+    if (i < end) {
+      z[r]  = __ldg(a.symbols + call.sym_off + i);
+      nv[r] = __ldg(a.noise_vars + call.sym_off + i);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r != DEMOD_PER_THREAD; ++r) {
+    const uint32_t i = first + r * DEMOD_THREADS + tid;
+    if (i < end) {
+      stage_symbol(stage + (size_t)(i - first) * MOD, demod_symbol_simd<MOD>(tab, z[r].x, z[r].y, nv[r]), MOD);
+    }
+  }
+}
+
 } // namespace demod
 
-__global__ void __launch_bounds__(DEMOD_THREADS) demod_kernel(DemodArgs a)
+__global__ void __launch_bounds__(DEMOD_THREADS, 8) demod_kernel(const __grid_constant__ DemodArgs a)
 {
   __shared__ demod::SmemTables tab;
-  __shared__ __align__(16) unsigned char stage[DEMOD_THREADS * 8];
+  __shared__ __align__(16) unsigned char stage[DEMOD_TILE * 8];
   const int tid = threadIdx.x;
-  demod::build_tables(tab, tid);
-  const DemodTile tile = a.tiles[blockIdx.x];
-  const DemodCall call = a.calls[tile.call];
-  const uint32_t  qm   = (call.mod == PDC_MOD_PI_2_BPSK) ? 1u : call.mod;
-  const uint32_t  block =
-      (call.mod == PDC_MOD_QPSK || call.mod == PDC_MOD_QAM64) ? 16u : (call.mod == PDC_MOD_QAM16) ? 8u : 4u;
-  const uint32_t n_simd =
-      ((a.flags & DEMOD_SCALAR_ONLY) || call.mod <= PDC_MOD_BPSK) ? 0u : (call.n_sym / block) * block;
-  const uint32_t end = min(call.n_sym, tile.first + (uint32_t)DEMOD_TILE);
+  demod::load_tables(tab, a.tables, tid);
   __syncthreads();
-  for (uint32_t base = tile.first; base < end; base += DEMOD_THREADS) {
-    const uint32_t i = base + tid;
-    if (i < end) {
-      const float2   z  = __ldg(a.symbols + call.sym_off + i);
-      const float    nv = __ldg(a.noise_vars + call.sym_off + i);
-      const uint64_t v  = demod::demod_symbol(tab, z.x, z.y, nv, call.mod, i < n_simd, i);
-      unsigned char* p  = stage + tid * qm;
-      if (qm == 8) {
-        *reinterpret_cast<uint2*>(p) = make_uint2((uint32_t)v, (uint32_t)(v >> 32));
-      } else if (qm == 6) {
-        reinterpret_cast<uint16_t*>(p)[0] = (uint16_t)v;
-        reinterpret_cast<uint16_t*>(p)[1] = (uint16_t)(v >> 16);
-        reinterpret_cast<uint16_t*>(p)[2] = (uint16_t)(v >> 32);
-      } else if (qm == 4) {
-        *reinterpret_cast<uint32_t*>(p) = (uint32_t)v;
-      } else if (qm == 2) {
-        *reinterpret_cast<uint16_t*>(p) = (uint16_t)v;
+  {
+    const uint32_t tile = blockIdx.x;
+    // The call of this tile: last call whose first tile is not beyond it.
+    uint32_t lo = 0, hi = a.n_calls;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (a.tile_start[mid] <= tile) {
+        lo = mid;
       } else {
-        *p = (unsigned char)v;
+        hi = mid;
+      }
+    }
+    const DemodCall call  = a.calls[lo];
+    const uint32_t  first = (tile - a.tile_start[lo]) * DEMOD_TILE;
+    const uint32_t  qm    = (call.mod == PDC_MOD_PI_2_BPSK) ? 1u : call.mod;
+    const uint32_t  block =
+        (call.mod == PDC_MOD_QPSK || call.mod == PDC_MOD_QAM64) ? 16u : (call.mod == PDC_MOD_QAM16) ? 8u : 4u;
+    const uint32_t n_simd =
+        ((a.flags & DEMOD_SCALAR_ONLY) || call.mod <= PDC_MOD_BPSK) ? 0u : (call.n_sym / block) * block;
+    const uint32_t end = min(call.n_sym, first + (uint32_t)DEMOD_TILE);
+    if (end <= n_simd) {
+      // Every symbol of the tile lies in the SIMD blocks of its call (all tiles but the last of a call, and the last too
+      // unless the call has a remainder): straight-line code for the modulation.
+      if (call.mod == PDC_MOD_QAM256) {
+        demod::tile_simd<PDC_MOD_QAM256>(tab, a, call, first, end, stage, tid);
+      } else if (call.mod == PDC_MOD_QAM64) {
+        demod::tile_simd<PDC_MOD_QAM64>(tab, a, call, first, end, stage, tid);
+      } else if (call.mod == PDC_MOD_QAM16) {
+        demod::tile_simd<PDC_MOD_QAM16>(tab, a, call, first, end, stage, tid);
+      } else {
+        demod::tile_simd<PDC_MOD_QPSK>(tab, a, call, first, end, stage, tid);
+      }
+    } else {
+      // Tiles with symbols of the scalar remainder (and BPSK, which has no SIMD kernel): symbol by symbol.
+#pragma unroll 1
+      for (uint32_t i = first + tid; i < end; i += DEMOD_THREADS) {
+        const float2 z  = __ldg(a.symbols + call.sym_off + i);
+        const float  nv = __ldg(a.noise_vars + call.sym_off + i);
+        demod::stage_symbol(stage + (size_t)(i - first) * qm,
+                            demod::demod_symbol(tab, z.x, z.y, nv, call.mod, i < n_simd, i), qm);
       }
     }
     __syncthreads();
-    // Staged soft bits of this step leave in 16-byte words where the destination allows it.
-    const uint32_t nbytes = min((uint32_t)DEMOD_THREADS, end - base) * qm;
-    int8_t*        dst    = a.llrs + (size_t)call.llr_off + (size_t)base * qm;
+    // The soft bits of the tile leave in 16-byte words where the destination allows it.
+    const uint32_t nbytes = (end - first) * qm;
+    int8_t*        dst    = a.llrs + (size_t)call.llr_off + (size_t)first * qm;
     if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
       const uint32_t n16 = nbytes >> 4;
       for (uint32_t w = tid; w < n16; w += DEMOD_THREADS) {
@@ -303,7 +403,6 @@ __global__ void __launch_bounds__(DEMOD_THREADS) demod_kernel(DemodArgs a)
         dst[b] = (int8_t)stage[b];
       }
     }
-    __syncthreads();
   }
 }
 

@@ -40,24 +40,16 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess)
     }                                                                                                                  \
   } while (0)
 
-// Soft demapper stage (grow-only buffers; the call / tile table is staged through a ring of pinned buffers like the
-// front-end plan).
+// Soft demapper stage (grow-only buffers). The call table travels in the kernel parameters: nothing to upload.
 struct DemodStage {
   float2*              d_sym = nullptr;
   size_t               sym_cap = 0;
   float*               d_nv = nullptr;
   size_t               nv_cap = 0;
-  unsigned char*       d_tab = nullptr;
-  size_t               tab_cap = 0;
-  static constexpr int RING = 4;
-  unsigned char*       h_tab[RING]     = {nullptr, nullptr, nullptr, nullptr};
-  size_t               h_tab_cap[RING] = {0, 0, 0, 0};
-  cudaEvent_t          tab_ev[RING]    = {nullptr, nullptr, nullptr, nullptr};
-  int                  ring_pos = 0;
   std::vector<pdc::DemodCall> calls;
-  std::vector<pdc::DemodTile> tiles;
-  pdc::DemodArgs       args = {};
-  uint32_t             n_tiles = 0;
+  const float2*        k_sym = nullptr;
+  const float*         k_nv = nullptr;
+  int8_t*              k_llrs = nullptr;
   bool                 kernel_pending = false;
 };
 
@@ -145,6 +137,7 @@ struct pdc_ctx {
   int32_t*             d_harq_last = nullptr; // (harq_entries + 1) x DM_MAX_PARTS: last non-zero soft bit (+1), -1 unknown
   int8_t*              d_scratch_llr = nullptr;
   size_t               scratch_llr_bytes = 0;
+  float*               d_demod_tables = nullptr;  // piecewise-linear LLR tables of the soft demapper
   std::vector<Queue>   queues;
   std::atomic<uint64_t> launches{0};
   bool                 force_scalar = false;      // PDC_FORCE_SCALAR=1: use the general kernel for every batch
@@ -494,6 +487,9 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
   PDC_CREATE(cudaMemset(ctx->d_tb_sync, 0, 2 * (size_t)ctx->tb_sync_entries * sizeof(uint32_t)));
   PDC_CREATE(dev_alloc(&ctx->d_harq_last, entries * pdc::DM_MAX_PARTS));
   PDC_CREATE(cudaMemset(ctx->d_harq_last, 0, entries * pdc::DM_MAX_PARTS * sizeof(int32_t))); // all-zero entries
+  PDC_CREATE(dev_alloc(&ctx->d_demod_tables, (size_t)pdc::demod::TABLE_FLOATS));
+  pdc::demod::demod_tables_kernel<<<1, 128>>>(ctx->d_demod_tables);
+  PDC_CREATE(cudaGetLastError());
   ctx->scratch_llr_bytes = 35u * PDC_MAX_CB_BYTES * 8u; // MAX_CODEBLOCK_RM_SIZE (ldpc.h:122)
   PDC_CREATE(dev_alloc(&ctx->d_scratch_llr, ctx->scratch_llr_bytes));
   ctx->queues.resize(cfg->nof_streams);
@@ -524,13 +520,6 @@ static void free_front_end(FrontEnd& fe)
 {
   cudaFree(fe.dm.d_sym);
   cudaFree(fe.dm.d_nv);
-  cudaFree(fe.dm.d_tab);
-  for (int k = 0; k != DemodStage::RING; ++k) {
-    cudaFreeHost(fe.dm.h_tab[k]);
-    if (fe.dm.tab_ev[k]) {
-      cudaEventDestroy(fe.dm.tab_ev[k]);
-    }
-  }
   cudaFree(fe.d_raw);
   cudaFree(fe.d_seq);
   cudaFree(fe.d_uci);
@@ -583,6 +572,7 @@ void pdc_destroy(pdc_ctx* ctx)
   cudaFree(ctx->d_harq_last);
   cudaFree(ctx->d_tb_sync);
   cudaFree(ctx->d_scratch_llr);
+  cudaFree(ctx->d_demod_tables);
   for (pdc_ctx::DecodeScratch& c : ctx->decode_scratch) {
     cudaFree(c.d_state);
     cudaFree(c.d_counter);
@@ -956,17 +946,34 @@ int pdc_submit_codewords(pdc_ctx*           ctx,
 static int demod_kernel_launch(pdc_ctx* ctx, DemodStage& dm, cudaStream_t s)
 {
   dm.kernel_pending = false;
-  if (dm.n_tiles == 0) {
-    return PDC_OK;
+  // Up to DEMOD_MAX_CALLS calls per launch (a 16-cell slot has 16 x 13).
+  static thread_local pdc::DemodArgs args;
+  args.tables     = ctx->d_demod_tables;
+  args.symbols    = dm.k_sym;
+  args.noise_vars = dm.k_nv;
+  args.llrs       = dm.k_llrs;
+  args.flags      = (ctx->cfg.demod_mode == PDC_DEMOD_SCALAR) ? pdc::DEMOD_SCALAR_ONLY : 0u;
+  for (size_t c0 = 0; c0 < dm.calls.size(); c0 += pdc::DEMOD_MAX_CALLS) {
+    const uint32_t n = (uint32_t)std::min<size_t>(pdc::DEMOD_MAX_CALLS, dm.calls.size() - c0);
+    uint32_t       tiles = 0;
+    for (uint32_t c = 0; c != n; ++c) {
+      args.calls[c]      = dm.calls[c0 + c];
+      args.tile_start[c] = tiles;
+      tiles += (args.calls[c].n_sym + pdc::DEMOD_TILE - 1) / pdc::DEMOD_TILE;
+    }
+    args.tile_start[n] = tiles;
+    args.n_calls       = n;
+    if (tiles == 0) {
+      continue;
+    }
+    pdc::demod_kernel<<<tiles, pdc::DEMOD_THREADS, 0, s>>>(args);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
   }
-  pdc::demod_kernel<<<dm.n_tiles, pdc::DEMOD_THREADS, 0, s>>>(dm.args);
-  PDC_CUDA(cudaGetLastError());
-  ctx->launches++;
   return PDC_OK;
 }
 
-// Validates dm.calls, cuts them into tiles, uploads the table on stream s and prepares (or queues) the kernel:
-//   d_sym / d_nv (n_sym symbols, on the device) -> d_llrs.
+// Validates dm.calls and prepares (or queues) the kernel: d_sym / d_nv (n_sym symbols, on the device) -> d_llrs.
 static int demod_prepare(pdc_ctx*      ctx,
                          DemodStage&   dm,
                          const float2* d_sym,
@@ -977,10 +984,8 @@ static int demod_prepare(pdc_ctx*      ctx,
                          cudaStream_t  s,
                          bool          launch_now)
 {
-  dm.tiles.clear();
-  for (size_t c = 0; c != dm.calls.size(); ++c) {
-    const pdc::DemodCall& call = dm.calls[c];
-    const uint32_t        m    = call.mod;
+  for (const pdc::DemodCall& call : dm.calls) {
+    const uint32_t m = call.mod;
     if (!(m == PDC_MOD_PI_2_BPSK || m == PDC_MOD_BPSK || m == PDC_MOD_QPSK || m == PDC_MOD_QAM16 ||
           m == PDC_MOD_QAM64 || m == PDC_MOD_QAM256)) {
       return fail(PDC_ERR_INVALID, "soft demapper: invalid modulation");
@@ -989,43 +994,11 @@ static int demod_prepare(pdc_ctx*      ctx,
     if ((size_t)call.sym_off + call.n_sym > n_sym || (size_t)call.llr_off + (size_t)call.n_sym * qm > llr_capacity) {
       return fail(PDC_ERR_INVALID, "soft demapper: call outside the symbol or soft-bit buffer");
     }
-    for (uint32_t first = 0; first < call.n_sym; first += pdc::DEMOD_TILE) {
-      dm.tiles.push_back(pdc::DemodTile{(uint32_t)c, first});
-    }
   }
-  dm.n_tiles = (uint32_t)dm.tiles.size();
-  if (dm.n_tiles == 0) {
-    dm.kernel_pending = false;
-    return PDC_OK;
-  }
-  const size_t b_calls = dm.calls.size() * sizeof(pdc::DemodCall);
-  const size_t bytes   = b_calls + dm.tiles.size() * sizeof(pdc::DemodTile);
-  PDC_CUDA(grow_device(&dm.d_tab, &dm.tab_cap, bytes));
-  const int slot = dm.ring_pos;
-  dm.ring_pos    = (dm.ring_pos + 1) % DemodStage::RING;
-  if (dm.tab_ev[slot] == nullptr) {
-    PDC_CUDA(cudaEventCreateWithFlags(&dm.tab_ev[slot], cudaEventDisableTiming));
-  } else {
-    PDC_CUDA(cudaEventSynchronize(dm.tab_ev[slot]));
-  }
-  if (bytes > dm.h_tab_cap[slot]) {
-    cudaFreeHost(dm.h_tab[slot]);
-    dm.h_tab[slot]     = nullptr;
-    dm.h_tab_cap[slot] = 0;
-    PDC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&dm.h_tab[slot]), bytes + bytes / 4 + 64));
-    dm.h_tab_cap[slot] = bytes + bytes / 4 + 64;
-  }
-  memcpy(dm.h_tab[slot], dm.calls.data(), b_calls);
-  memcpy(dm.h_tab[slot] + b_calls, dm.tiles.data(), bytes - b_calls);
-  PDC_CUDA(cudaMemcpyAsync(dm.d_tab, dm.h_tab[slot], bytes, cudaMemcpyHostToDevice, s));
-  PDC_CUDA(cudaEventRecord(dm.tab_ev[slot], s));
-  dm.args.calls      = reinterpret_cast<const pdc::DemodCall*>(dm.d_tab);
-  dm.args.tiles      = reinterpret_cast<const pdc::DemodTile*>(dm.d_tab + b_calls);
-  dm.args.symbols    = d_sym;
-  dm.args.noise_vars = d_nv;
-  dm.args.llrs       = d_llrs;
-  dm.args.flags      = (ctx->cfg.demod_mode == PDC_DEMOD_SCALAR) ? pdc::DEMOD_SCALAR_ONLY : 0u;
-  dm.kernel_pending  = true;
+  dm.k_sym          = d_sym;
+  dm.k_nv           = d_nv;
+  dm.k_llrs         = d_llrs;
+  dm.kernel_pending = true;
   return launch_now ? demod_kernel_launch(ctx, dm, s) : PDC_OK;
 }
 
