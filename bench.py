@@ -511,7 +511,8 @@ def symbol_legs(ctx, orc, capi, torch, stream, args):
                                "frac": demod_bytes / (times["demod"] * 1e-6) / 1e9 / pk["hbm_gbs"],
                                "bytes_per_launch": demod_bytes, "traffic": profiled_traffic("demod_kernel"),
                                "peak_source": pk_src,
-                               "note": "incl. the upload of the call table and the launch; 12 B read + 8 B written per symbol"},
+                               "note": "timed with CUDA events over back-to-back launches (launch overhead included); "
+                                       "12 B read + 8 B written per symbol"},
             "e2e_host_buffers": e2e}
     return out
 
