@@ -349,6 +349,19 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
                        "d2h_bytes_per_slot": n_cb * (capi.PDC_MAX_CB_BYTES + 4) + cells * tb_stride,
                        "slots_in_flight": NQ, "tb_crc_ok": bool(last["tb_results"]["tb_crc_ok"].all()),
                        "tb_bytes_match": bool((last["tb_bytes"][:tbs_bits // 8] == tb).all())}
+                # ---- latency: one slot at a time, from "scrambled soft bits in page-locked host memory" to
+                # "TB bytes and CRC flags back in host memory" (when on_sch_data could be called), host clock, p50 / p99.
+                n_lat = 1000 if cells == 1 else 300
+                lat = np.zeros(n_lat)
+                for i in range(n_lat + 20):
+                    t0 = time.perf_counter()
+                    slot(0)
+                    ctx3.wait(0)
+                    if i >= 20:
+                        lat[i - 20] = (time.perf_counter() - t0) * 1e6
+                e2e["latency_us"] = {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                                     "mean": float(lat.mean()), "slots": n_lat, "in_flight": 1,
+                                     "path": "pdc_submit_codewords + pdc_submit + pdc_wait, host buffers"}
                 ctx3.close()
             out[f"{name}_front_end"] = {
                 "us_front_end": times["front_end"], "us_per_slot_with_front_end": times["chain"],

@@ -144,6 +144,19 @@ struct GraphSmem {
 };
 
 
+// Global-memory images of what a CTA needs per (base graph, lifting size), built once on the host (upload_h2_images):
+// the per-edge table in the layout of GraphSmem (column bases relative to the soft-bit array), the row table and the CRC
+// word weights. A CTA copies them with coalesced loads instead of deriving them from the constant-memory base graph
+// with one (serialised) constant access per thread, and only when the shape differs from that of its previous pair.
+#ifndef H2_NO_REUSE
+#define H2_NO_REUSE 0
+#endif
+constexpr int H2_Z_SLOTS = 51;
+__device__ uint2    g_h2_einfo[2][H2_Z_SLOTS][MAX_EDGES + MAX_ROWS];
+__device__ uint32_t g_h2_row_info[2][MAX_ROWS];
+__device__ uint32_t g_h2_xpow32[3][XPOW_ENTRIES];
+__device__ uint8_t  g_h2_z_slot[MAX_Z + 1];
+
 // CTA barrier that threads of one warp may reach from different places (partial last warp of a lifting size that is not
 // a multiple of 32): the non-aligned form.
 __device__ __forceinline__ void row_barrier()
@@ -351,6 +364,11 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
   __shared__ pdc_cb_result      sh_result[2];
   __shared__ int      sh_defer_b; // codeblock B could not be decoded together with A: it gets its own pass
   __shared__ uint32_t sh_next_pair;
+  __shared__ __align__(16) uint32_t sh_desc[2][8];                       // the two descriptors of the pair
+  // Hard decisions of the last check, packed during the sweep (the 384-thread variant; the 192-thread variant runs four
+  // CTAs per SM and has no shared memory to spare for them).
+  constexpr bool PACK_IN_SWEEP = MAX_THREADS > 192;
+  __shared__ __align__(16) uint32_t sh_bits[2][PACK_IN_SWEEP ? (22 * MAX_Z + 31) / 32 : 1];
 
   const int tid  = threadIdx.x;
   const int nthr = blockDim.x;
@@ -360,9 +378,21 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
   // The first pair of a CTA is its index; further pairs come from a counter, so that CTAs whose codeblocks stopped early
   // take over work from those still iterating.
   const uint32_t n_pairs = (prm.n_cb + 1) / 2;
+  // Shape of the tables currently in shared memory (a CTA usually decodes pairs of one shape back to back).
+  int      cur_bg = 0, cur_Z = 0;
+  uint32_t cur_wkey0 = 0xffffffffu, cur_wkey1 = 0xffffffffu;
   for (uint32_t pair = blockIdx.x; pair < n_pairs;) {
     for (int pass = 0; pass != 2; ++pass) {
       const uint32_t cb0 = 2 * pair;
+      __syncthreads();
+      // Both descriptors (7 words each) in one round trip.
+      static_assert(sizeof(pdc_cb_desc) == 28, "descriptor layout");
+      if (tid < 14) {
+        const uint32_t h = tid / 7u, wd = tid % 7u;
+        if (cb0 + h < prm.n_cb) {
+          sh_desc[h][wd] = __ldg(reinterpret_cast<const uint32_t*>(prm.cbs + cb0 + h) + wd);
+        }
+      }
       __syncthreads();
       if (tid == 0) {
         const pdc_cb_desc* d[2];
@@ -372,7 +402,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           ok[h]       = false;
           d[h]        = nullptr;
           if (cb < prm.n_cb) {
-            d[h]  = &prm.cbs[cb];
+            d[h]  = reinterpret_cast<const pdc_cb_desc*>(sh_desc[h]);
             ok[h] = (d[h]->flags & PDC_CB_DECODE) != 0;
             if (ok[h]) {
               const int bg = d[h]->base_graph, Z = d[h]->lifting_size;
@@ -413,17 +443,17 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         continue;
       }
       const int          lead    = lane[0].valid ? 0 : 1;
-      const pdc_cb_desc& dl      = prm.cbs[lane[lead].cb];
+      const pdc_cb_desc& dl      = *reinterpret_cast<const pdc_cb_desc*>(sh_desc[lead]);
+      const pdc_cb_desc* const dsc[2] = {reinterpret_cast<const pdc_cb_desc*>(sh_desc[0]),
+                                         reinterpret_cast<const pdc_cb_desc*>(sh_desc[1])};
       const int          bg      = dl.base_graph;
       const int          Z       = dl.lifting_size;
       const int          b       = bg - 1;
       const int          kb      = (bg == 1) ? 22 : 10;
       const int          n_full  = (bg == 1) ? 68 : 52;
       const int          rows    = (bg == 1) ? 46 : 42;
-      const int          n_edges = (bg == 1) ? BG1_EDGES_N : BG2_EDGES_N;
       const int          K       = kb * Z;
       const int          N       = (n_full - 2) * Z;
-      const int          set     = c_tab.set_index[Z];
       const int          n_words = (K + 31) / 32;
 
       // Carve shared memory.
@@ -440,13 +470,31 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       const uint32_t st_stride = (uint32_t)((Z + 31) & ~31);
       const uint32_t soft_s    = (uint32_t)__cvta_generic_to_shared(smem_raw);
 
-      for (int i = tid; i < n_edges; i += nthr) {
-        const int m  = c_tab.row[b][i];
-        const int pi = c_tab.row_pstart[b][m] + (i - c_tab.row_start[b][m]);
-        g.einfo[pi]  = make_uint2((uint32_t)(4 * (c_tab.v[b][set][i] % Z)), // ldpc_luts_impl.cpp:4536-4541
-                                  soft_s + (uint32_t)(c_tab.col[b][i] * Z * 4));
+      // Last non-zero input of each codeblock (ldpc_decoder_impl.cpp:86-99), recorded by the rate dematcher: the loads
+      // are issued here and consumed after the tables are in place.
+      const int8_t* in[2];
+      int4          slots[2];
+      for (int h = 0; h != 2; ++h) {
+        in[h]    = lane[h].valid ? prm.harq + (size_t)dsc[h]->harq_id * PDC_MAX_CB_SOFT : nullptr;
+        slots[h] = lane[h].valid ? __ldg(reinterpret_cast<const int4*>(prm.harq_last) + dsc[h]->harq_id)
+                                 : make_int4(0, 0, 0, 0);
       }
-      // CRC word weights: x^(32 (T-1-t)) mod P for the T words of the K - F checked bits, zero beyond.
+      if (H2_NO_REUSE || bg != cur_bg || Z != cur_Z) {
+        const uint2* img = g_h2_einfo[b][g_h2_z_slot[Z]];
+        for (int i = tid; i < MAX_EDGES + MAX_ROWS; i += nthr) {
+          uint2 e = img[i];
+          e.y += soft_s; // the image holds column bases relative to the soft-bit array
+          g.einfo[i] = e;
+        }
+        for (int m = tid; m < rows; m += nthr) {
+          g.row_info[m] = g_h2_row_info[b][m];
+        }
+        cur_bg    = bg;
+        cur_Z     = Z;
+        cur_wkey0 = 0xffffffffu; // the weights live behind the soft bits: a new shape moves them
+      }
+      // CRC word weights: x^(32 (T-1-t)) mod P for the T words of the K - F checked bits, zero beyond; and
+      // x^(order + k) mod P for the final reduction.
       {
         int kind[2], T[2];
         for (int h = 0; h != 2; ++h) {
@@ -454,45 +502,42 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           kind[h]             = with_crc ? lane[h].crc_kind - 1 : 0;
           T[h]                = with_crc ? (K - lane[h].F + 31) / 32 : 0;
         }
-        for (int t = tid; t < n_words; t += nthr) {
-          wgt[t] = make_uint2((t < T[0]) ? c_tab.xpow32[kind[0]][T[0] - 1 - t] : 0u,
-                              (t < T[1]) ? c_tab.xpow32[kind[1]][T[1] - 1 - t] : 0u);
-        }
-      }
-      for (int idx = tid; idx < 64; idx += nthr) {
-        const int h = idx >> 5, k = idx & 31;
-        uint32_t  r = 0;
-        if (lane[h].valid && lane[h].crc_kind != PDC_CRC_NONE) {
-          const uint32_t poly = crc_poly(lane[h].crc_kind), top = 1u << crc_order(lane[h].crc_kind);
-          r = poly ^ top; // x^order mod P
-          for (int i = 0; i != k; ++i) {
-            r <<= 1;
-            if (r & top) {
-              r ^= poly;
-            }
+        const uint32_t wkey0 = (uint32_t)kind[0] | ((uint32_t)T[0] << 8) | ((uint32_t)n_words << 20);
+        const uint32_t wkey1 = (uint32_t)kind[1] | ((uint32_t)T[1] << 8) | ((uint32_t)n_words << 20);
+        if (H2_NO_REUSE || wkey0 != cur_wkey0 || wkey1 != cur_wkey1) {
+          for (int t = tid; t < n_words; t += nthr) {
+            wgt[t] = make_uint2((t < T[0]) ? g_h2_xpow32[kind[0]][T[0] - 1 - t] : 0u,
+                                (t < T[1]) ? g_h2_xpow32[kind[1]][T[1] - 1 - t] : 0u);
           }
+          for (int idx = tid; idx < 64; idx += nthr) {
+            const int h = idx >> 5, k = idx & 31;
+            uint32_t  r = 0;
+            if (T[h] != 0) {
+              const uint32_t poly = crc_poly(kind[h] + 1), top = 1u << crc_order(kind[h] + 1);
+              r = poly ^ top; // x^order mod P
+              for (int i = 0; i != k; ++i) {
+                r <<= 1;
+                if (r & top) {
+                  r ^= poly;
+                }
+              }
+            }
+            sh_red[h][k] = r;
+          }
+          cur_wkey0 = wkey0;
+          cur_wkey1 = wkey1;
         }
-        sh_red[h][k] = r;
-      }
-      for (int m = tid; m < rows; m += nthr) {
-        g.row_info[m] = ((uint32_t)c_tab.row_free[b][m] << 31) | (uint32_t)c_tab.row_pstart[b][m] |
-                        ((uint32_t)(c_tab.row_start[b][m + 1] - c_tab.row_start[b][m]) << 16);
       }
       // Last non-zero input of each codeblock (ldpc_decoder_impl.cpp:86-99): recorded by the rate dematcher for the
       // entries it wrote; entries of unknown content are scanned.
-      const int8_t* in[2];
-      for (int h = 0; h != 2; ++h) {
-        in[h] = lane[h].valid ? prm.harq + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_SOFT : nullptr;
-      }
       const uint64_t pol_stream = l2_policy_evict_first();
 #pragma unroll
       for (int h = 0; h != 2; ++h) {
         if (in[h] == nullptr) {
           continue;
         }
-        const int4 slots = reinterpret_cast<const int4*>(prm.harq_last)[prm.cbs[lane[h].cb].harq_id];
-        const int  known = max(max(slots.x, slots.y), max(slots.z, slots.w));
-        if (min(min(slots.x, slots.y), min(slots.z, slots.w)) >= 0) {
+        const int known = max(max(slots[h].x, slots[h].y), max(slots[h].z, slots[h].w));
+        if (min(min(slots[h].x, slots[h].y), min(slots[h].z, slots[h].w)) >= 0) {
           if (tid == 0) {
             sh_last[h] = min(known, N);
           }
@@ -555,20 +600,32 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           src[h] = lane[h].valid ? reinterpret_cast<const uint32_t*>(in[h]) : nullptr;
         }
         const __half2 h64 = H(0x54005400u), hn64 = H(0xD400D400u), hn1152 = H(0xE480E480u);
-#pragma unroll 2
-        for (int q = tid; q < ((n_load + 3) >> 2); q += nthr) {
-          const uint32_t wa = src[0] ? ld_stream_u32(src[0] + q, pol_stream) : 0u;
-          const uint32_t wb = src[1] ? ld_stream_u32(src[1] + q, pol_stream) : 0u;
+        // Four words of each codeblock in flight per thread (the loop is latency bound: one CTA, streaming loads).
+        const int n_q = (n_load + 3) >> 2;
+        for (int q0 = tid; q0 < n_q; q0 += 4 * nthr) {
+          uint32_t wa[4], wb[4];
 #pragma unroll
-          for (int k = 0; k != 4; ++k) {
-            // bytes {A_k, A_k, B_k, B_k} -> halves {0x64 : A_k ^ 0x80, 0x64 : B_k ^ 0x80}
-            uint32_t t = __byte_perm(wa, wb, (uint32_t)(k | (k << 4) | ((4 + k) << 8) | ((4 + k) << 12)));
-            uint32_t u;
-            asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(u) : "r"(t), "r"(0x00ff00ffu), "r"(0x64806480u));
-            __half2 v = __hadd2(H(u), hn1152);
-            v         = __hmax2(__hmin2(v, h64), hn64);
-            if (4 * q + k < n_load) {
-              soft[2 * Z + 4 * q + k] = U(v);
+          for (int u = 0; u != 4; ++u) {
+            const int q = q0 + u * nthr;
+            wa[u]       = (src[0] && q < n_q) ? ld_stream_u32(src[0] + q, pol_stream) : 0u;
+            wb[u]       = (src[1] && q < n_q) ? ld_stream_u32(src[1] + q, pol_stream) : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u != 4; ++u) {
+            const int q = q0 + u * nthr;
+            if (q < n_q) {
+#pragma unroll
+              for (int k = 0; k != 4; ++k) {
+                // bytes {A_k, A_k, B_k, B_k} -> halves {0x64 : A_k ^ 0x80, 0x64 : B_k ^ 0x80}
+                uint32_t t = __byte_perm(wa[u], wb[u], (uint32_t)(k | (k << 4) | ((4 + k) << 8) | ((4 + k) << 12)));
+                uint32_t x;
+                asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(x) : "r"(t), "r"(0x00ff00ffu), "r"(0x64806480u));
+                __half2 v = __hadd2(H(x), hn1152);
+                v         = __hmax2(__hmin2(v, h64), hn64);
+                if (4 * q + k < n_load) {
+                  soft[2 * Z + 4 * q + k] = U(v);
+                }
+              }
             }
           }
         }
@@ -649,6 +706,15 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
                 m1 = (i < nb1) ? m1 : 0u;
               }
               const uint2 wg = wgt[w];
+              // Hard decisions of the word, packed MSB first in memory order, kept for the publication below.
+              if (PACK_IN_SWEEP) {
+                const uint32_t b0 = __ballot_sync(0xffffffffu, (hm & 0xffffu) != 0);
+                const uint32_t b1 = __ballot_sync(0xffffffffu, (hm >> 16) != 0);
+                if (lane_id == 0) {
+                  sh_bits[0][w] = __byte_perm(__brev(b0), 0, 0x0123);
+                  sh_bits[1][w] = __byte_perm(__brev(b1), 0, 0x0123);
+                }
+              }
               zacc |= zm;
               a0l = lop_xor_and(a0l, wg.x << shl, m0);
               a0h = lop_xor_and(a0h, __funnelshift_l(wg.x, 0u, shl), m0);
@@ -663,36 +729,33 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
             for (; w < n_words; w += n_warps) {
               sweep(w, true);
             }
-            uint64_t acc0 = ((uint64_t)a0h << 32) | a0l, acc1 = ((uint64_t)a1h << 32) | a1l;
+            // Warp-wide XOR / OR reductions in one instruction each (redux.sync).
             const int za = __any_sync(0xffffffffu, (zacc & 0xffffu) != 0);
             const int zb = __any_sync(0xffffffffu, (zacc >> 16) != 0);
-            for (int o = 16; o > 0; o >>= 1) {
-              acc0 ^= __shfl_xor_sync(0xffffffffu, acc0, o);
-              acc1 ^= __shfl_xor_sync(0xffffffffu, acc1, o);
-            }
+            a0l = __reduce_xor_sync(0xffffffffu, a0l);
+            a0h = __reduce_xor_sync(0xffffffffu, a0h);
+            a1l = __reduce_xor_sync(0xffffffffu, a1l);
+            a1h = __reduce_xor_sync(0xffffffffu, a1h);
             if (lane_id == 0) {
-              sh_part[0][warp] = acc0;
-              sh_part[1][warp] = acc1;
+              sh_part[0][warp] = ((uint64_t)a0h << 32) | a0l;
+              sh_part[1][warp] = ((uint64_t)a1h << 32) | a1l;
               sh_zpart[warp]   = (za ? 1 : 0) | (zb ? 2 : 0);
             }
             __syncthreads();
             if (warp == 0) {
-              uint64_t v0 = (lane_id < n_warps) ? sh_part[0][lane_id] : 0ull;
-              uint64_t v1 = (lane_id < n_warps) ? sh_part[1][lane_id] : 0ull;
-              int      zz = (lane_id < n_warps) ? sh_zpart[lane_id] : 0;
-              for (int o = 16; o > 0; o >>= 1) {
-                v0 ^= __shfl_xor_sync(0xffffffffu, v0, o);
-                v1 ^= __shfl_xor_sync(0xffffffffu, v1, o);
-                zz |= __shfl_xor_sync(0xffffffffu, zz, o);
-              }
+              const uint64_t p0 = (lane_id < n_warps) ? sh_part[0][lane_id] : 0ull;
+              const uint64_t p1 = (lane_id < n_warps) ? sh_part[1][lane_id] : 0ull;
+              const uint64_t v0 = ((uint64_t)__reduce_xor_sync(0xffffffffu, (uint32_t)(p0 >> 32)) << 32) |
+                                  __reduce_xor_sync(0xffffffffu, (uint32_t)p0);
+              const uint64_t v1 = ((uint64_t)__reduce_xor_sync(0xffffffffu, (uint32_t)(p1 >> 32)) << 32) |
+                                  __reduce_xor_sync(0xffffffffu, (uint32_t)p1);
+              const int zz = (int)__reduce_or_sync(0xffffffffu, (uint32_t)((lane_id < n_warps) ? sh_zpart[lane_id] : 0));
               for (int h = 0; h != 2; ++h) {
                 const uint64_t v     = h ? v1 : v0;
                 const int      kind  = lane[h].crc_kind;
                 const int      order = crc_order(kind);
-                uint32_t       part  = ((v >> (order + lane_id)) & 1ull) ? sh_red[h][lane_id] : 0u;
-                for (int o = 16; o > 0; o >>= 1) {
-                  part ^= __shfl_xor_sync(0xffffffffu, part, o);
-                }
+                const uint32_t part  =
+                    __reduce_xor_sync(0xffffffffu, ((v >> (order + lane_id)) & 1ull) ? sh_red[h][lane_id] : 0u);
                 const uint32_t crc = part ^ ((uint32_t)v & ((1u << order) - 1u));
                 if (lane_id == 0) {
                   const bool active   = lane[h].valid && !lane[h].done && (lane[h].early || last_it);
@@ -713,15 +776,40 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
             }
             __syncthreads();
           }
-          // Publish finished codeblocks: hard decisions packed MSB first, one 32-bit word per warp step.
-          if (sh_publish[0] || sh_publish[1]) {
+          // Publish finished codeblocks: the packed hard decisions of the sweep above, copied word by word.
+          if (PACK_IN_SWEEP && (sh_publish[0] || sh_publish[1])) {
+            const int nbytes = (K + 7) / 8, n_full_words = nbytes >> 2;
+#pragma unroll
+            for (int h = 0; h != 2; ++h) {
+              if (!sh_publish[h]) {
+                continue;
+              }
+              uint8_t* out   = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
+              uint8_t* out_h = prm.harq_data + (size_t)dsc[h]->harq_id * PDC_MAX_CB_BYTES;
+              for (int w = tid; w < n_full_words; w += nthr) {
+                const uint32_t le                      = sh_bits[h][w];
+                reinterpret_cast<uint32_t*>(out)[w]   = le;
+                reinterpret_cast<uint32_t*>(out_h)[w] = le;
+              }
+              if (tid == 0) {
+                for (int k = 4 * n_full_words; k < nbytes; ++k) {
+                  const uint8_t v = (uint8_t)(sh_bits[h][k >> 2] >> (8 * (k & 3)));
+                  out[k]   = v;
+                  out_h[k] = v;
+                }
+                prm.results[lane[h].cb] = sh_result[h];
+              }
+            }
+          }
+          // The small variant (four CTAs per SM, no room for the packed words) packs them here, one word per warp step.
+          if (!PACK_IN_SWEEP && (sh_publish[0] || sh_publish[1])) {
             const int lane_id = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
             const int nbytes  = (K + 7) / 8;
             uint8_t*  out[2];
             uint8_t*  out_h[2];
             for (int h = 0; h != 2; ++h) {
               out[h]   = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
-              out_h[h] = sh_publish[h] ? prm.harq_data + (size_t)prm.cbs[lane[h].cb].harq_id * PDC_MAX_CB_BYTES : nullptr;
+              out_h[h] = sh_publish[h] ? prm.harq_data + (size_t)dsc[h]->harq_id * PDC_MAX_CB_BYTES : nullptr;
             }
             for (int w = warp; w < n_words; w += n_warps) {
               const int      i  = 32 * w + lane_id;
@@ -773,6 +861,47 @@ struct H2Plan {
   size_t scratch_words_per_cta;
   bool   big; // the 384-thread instantiation (two CTAs per SM)
 };
+
+// Builds the per-(base graph, lifting size) images the kernel copies (after upload_tables, once per context).
+inline cudaError_t upload_h2_images()
+{
+  const BgTables& h = host_tables();
+  static uint2    einfo[2][h2::H2_Z_SLOTS][MAX_EDGES + MAX_ROWS];
+  static uint32_t row_info[2][MAX_ROWS];
+  static uint8_t  z_slot[MAX_Z + 1];
+  static_assert(NR_LDPC_NOF_LIFTING_SIZES == h2::H2_Z_SLOTS, "lifting size table");
+  memset(einfo, 0, sizeof(einfo));
+  memset(row_info, 0, sizeof(row_info));
+  memset(z_slot, 0, sizeof(z_slot));
+  for (int bg = 0; bg != 2; ++bg) {
+    const int rows = bg ? 42 : 46, n_edges = bg ? BG2_NOF_EDGES : BG1_NOF_EDGES;
+    for (int zi = 0; zi != h2::H2_Z_SLOTS; ++zi) {
+      const int Z = NR_LDPC_LIFTING_SIZES[zi], set = NR_LDPC_SET_INDEX[zi];
+      z_slot[Z]   = (uint8_t)zi;
+      for (int i = 0; i != n_edges; ++i) {
+        const int m  = h.row[bg][i];
+        const int pi = h.row_pstart[bg][m] + (i - h.row_start[bg][m]);
+        // {circulant shift in bytes (ldpc_luts_impl.cpp:4536-4541), column base relative to the soft-bit array}
+        einfo[bg][zi][pi] = make_uint2((uint32_t)(4 * (h.v[bg][set][i] % Z)), (uint32_t)(h.col[bg][i] * Z * 4));
+      }
+    }
+    for (int m = 0; m != rows; ++m) {
+      row_info[bg][m] = ((uint32_t)h.row_free[bg][m] << 31) | (uint32_t)h.row_pstart[bg][m] |
+                        ((uint32_t)(h.row_start[bg][m + 1] - h.row_start[bg][m]) << 16);
+    }
+  }
+  cudaError_t e = cudaMemcpyToSymbol(h2::g_h2_einfo, einfo, sizeof(einfo));
+  if (e == cudaSuccess) {
+    e = cudaMemcpyToSymbol(h2::g_h2_row_info, row_info, sizeof(row_info));
+  }
+  if (e == cudaSuccess) {
+    e = cudaMemcpyToSymbol(h2::g_h2_z_slot, z_slot, sizeof(z_slot));
+  }
+  if (e == cudaSuccess) {
+    e = cudaMemcpyToSymbol(h2::g_h2_xpow32, h.xpow32, sizeof(h.xpow32));
+  }
+  return e;
+}
 
 typedef void (*h2_kernel_t)(BatchParams, uint32_t*, uint32_t, uint32_t*);
 

@@ -474,6 +474,7 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
     }                                                                                                                  \
   } while (0)
   PDC_CREATE(pdc::upload_tables());
+  PDC_CREATE(pdc::upload_h2_images());
   PDC_CREATE(pdc::upload_tb_tables());
   PDC_CREATE(pdc::upload_prg_tables());
   PDC_CREATE(upload_crc_tables());

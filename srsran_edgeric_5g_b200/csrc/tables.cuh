@@ -10,9 +10,16 @@ namespace pdc {
 
 __constant__ BgTables c_tab;
 
-inline cudaError_t upload_tables()
+// Host copy of the tables (filled by upload_tables; the decoder's per-shape images are derived from it).
+inline BgTables& host_tables()
 {
   static BgTables h;
+  return h;
+}
+
+inline cudaError_t upload_tables()
+{
+  BgTables& h = host_tables();
   memset(&h, 0, sizeof(h));
   for (int bg = 0; bg != 2; ++bg) {
     int n                        = bg ? BG2_NOF_EDGES : BG1_NOF_EDGES;

@@ -157,6 +157,8 @@ def test_front_end_feeds_the_decoder(ctx, orc, ack_bits):
     tbd = np.zeros(1, capi.TB_DESC_DTYPE)
     tbd[0] = (0, C, tbs_bits, 0, 0)
     d = cw_desc(cfg, c_init=c_init, flags=capi.CW_SCRAMBLED)
+    for k in range(C):  # entries other tests may have used: start from empty soft buffers like a fresh rx_buffer
+        ctx.harq_write(100 + k, np.zeros(capi.PDC_MAX_CB_SOFT, np.int8))
     ctx.submit_codewords(np.array([d]), raw.array, stream=0)
     ctx.submit(cbs, None, tbd, stream=0)
     out = ctx.wait(0)
@@ -169,7 +171,7 @@ def test_front_end_feeds_the_decoder(ctx, orc, ack_bits):
     direct = ctx.wait(1)
     assert (out["cb_results"] == direct["cb_results"]).all()
     assert (out["cb_bits"] == direct["cb_bits"]).all()
-    assert out["tb_results"][0]["tb_crc_ok"] == 1
+    assert out["tb_results"][0]["tb_crc_ok"] == 1, out["cb_results"]
     assert (out["tb_bytes"][:tbs_bits // 8] == tb).all()
 
 
