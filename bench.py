@@ -362,6 +362,42 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
                 e2e["latency_us"] = {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                                      "mean": float(lat.mean()), "slots": n_lat, "in_flight": 1,
                                      "path": "pdc_submit_codewords + pdc_submit + pdc_wait, host buffers"}
+                if cells >= 4:
+                    # The same slot as G batches of cells / G cells on G queues: the copy in of batch g + 1 runs while the
+                    # kernels of batch g do, so the slot completes one batch of kernels after its last byte arrived.
+                    G = 4
+                    per, cb_per = cells // G, n_cb // G
+                    grp = []
+                    for g in range(G):
+                        cw_g = cws_def[g * per:(g + 1) * per].copy()
+                        cw_g["in_offset"] -= g * per * n_llr
+                        cw_g["sch_offset"] -= g * per * n_llr
+                        cb_g = cbs[g * cb_per:(g + 1) * cb_per].copy()
+                        cb_g["llr_offset"] -= g * per * n_llr
+                        cb_g["tb_index"] -= g * per
+                        tb_g = tbd[g * per:(g + 1) * per].copy()
+                        tb_g["first_cb"] -= g * cb_per
+                        tb_g["out_offset"] -= g * per * tb_stride
+                        grp.append((cw_g, cb_g, tb_g))
+                    ctx4 = capi.Context(device=torch.cuda.current_device(), max_cbs=cb_per, max_llrs=per * n_llr + 64,
+                                        harq_entries=n_cb, max_tbs=per, max_tb_bytes=per * tb_stride + 64, nof_streams=G)
+                    lat4 = np.zeros(n_lat)
+                    ok4 = True
+                    for i in range(n_lat + 20):
+                        t0 = time.perf_counter()
+                        for g, (cw_g, cb_g, tb_g) in enumerate(grp):
+                            ctx4.submit_codewords(cw_g, raw_pin[0].array[g * per * n_llr:(g + 1) * per * n_llr], stream=g)
+                            ctx4.submit(cb_g, None, tb_g, stream=g,
+                                        out_bits=bits_pin[0].array[g * cb_per * capi.PDC_MAX_CB_BYTES:],
+                                        out_tb=tb_pin[0].array[g * per * tb_stride:])
+                        res4 = [ctx4.wait(g) for g in range(G)]
+                        if i >= 20:
+                            lat4[i - 20] = (time.perf_counter() - t0) * 1e6
+                        ok4 = ok4 and all(bool(r["tb_results"]["tb_crc_ok"].all()) for r in res4)
+                    e2e["latency_us_4_queues"] = {"p50": float(np.percentile(lat4, 50)), "p99": float(np.percentile(lat4, 99)),
+                                                  "mean": float(lat4.mean()), "slots": n_lat, "batches_per_slot": G,
+                                                  "tb_crc_ok": ok4}
+                    ctx4.close()
                 ctx3.close()
             out[f"{name}_front_end"] = {
                 "us_front_end": times["front_end"], "us_per_slot_with_front_end": times["chain"],

@@ -332,6 +332,105 @@ __device__ __forceinline__ void dispatch_row(int deg, uint32_t e_info, uint32_t 
   }
 }
 
+// ---- hard decisions, "a message soft bit is zero" flags and CRC of both codeblocks ---------------------------------------
+//
+// acc[0..3] = unreduced CRC remainders {A low, A high, B low, B high}, acc[4] = zero flags (one 16-bit half per
+// codeblock). out[2h], out[2h + 1]: where the packed hard decisions of codeblock h go (batch output, HARQ entry), or null.
+
+// 128 consecutive positions per warp step, four per lane (one 128-bit shared load); only for steps whose positions are
+// all inside the checked bits of every codeblock present. Eight lanes make one 32-bit word of hard decisions.
+template <bool CRC, bool PACK>
+__device__ __forceinline__ void sweep128(const hh* soft, const uint2* wgt, int n_steps, int warp, int n_warps, int lane_id,
+                                         uint32_t (&acc)[5], uint8_t* const (&out)[4])
+{
+  const int      l8  = lane_id & 7, grp = lane_id >> 3;
+  const uint32_t sh3 = 28u - 4u * (uint32_t)l8;                         // shift of the lane's LAST bit: 31 - (4 l8 + 3)
+  const uint32_t bitpos = 8u * (uint32_t)(l8 >> 1) + ((l8 & 1) ? 0u : 4u); // of the lane's nibble in the little-endian word
+  const uint32_t gmask  = 0xffu << (8 * grp);
+  for (int s = warp; s < n_steps; s += n_warps) {
+    const uint4 v4 = *reinterpret_cast<const uint4*>(soft + 128 * s + 4 * lane_id);
+    const int   t  = 4 * s + grp;
+    const hh    sv[4] = {v4.x, v4.y, v4.z, v4.w};
+    uint32_t    hm[4];
+#pragma unroll
+    for (int k = 0; k != 4; ++k) {
+      hm[k] = __hle2_mask(H(sv[k]), H(H_ZERO)); // 0xffff per half: hard bit 1 (soft <= 0)
+    }
+    if (CRC) {
+      const uint2 wg = wgt[t];
+#pragma unroll
+      for (int k = 0; k != 4; ++k) {
+        acc[4] |= __heq2_mask(H(sv[k]), H(H_ZERO));
+        const uint32_t m0 = __byte_perm(hm[k], 0, 0x1010), m1 = __byte_perm(hm[k], 0, 0x3232);
+        const uint32_t sh = sh3 + 3u - (uint32_t)k;
+        acc[0] = lop_xor_and(acc[0], wg.x << sh, m0);
+        acc[1] = lop_xor_and(acc[1], __funnelshift_l(wg.x, 0u, sh), m0);
+        acc[2] = lop_xor_and(acc[2], wg.y << sh, m1);
+        acc[3] = lop_xor_and(acc[3], __funnelshift_l(wg.y, 0u, sh), m1);
+      }
+    }
+    if (PACK) {
+      // nibbles {A: bits 0-3, B: bits 16-19}, first position in the most significant bit
+      const uint32_t one = 0x00010001u;
+      const uint32_t nib = ((hm[0] & one) << 3) | ((hm[1] & one) << 2) | ((hm[2] & one) << 1) | (hm[3] & one);
+      const uint32_t wa  = __reduce_or_sync(gmask, (nib & 0xfu) << bitpos);
+      const uint32_t wb  = __reduce_or_sync(gmask, ((nib >> 16) & 0xfu) << bitpos);
+      if (l8 == 0) {
+        if (out[0] != nullptr) {
+          reinterpret_cast<uint32_t*>(out[0])[t] = wa;
+          reinterpret_cast<uint32_t*>(out[1])[t] = wa;
+        }
+        if (out[2] != nullptr) {
+          reinterpret_cast<uint32_t*>(out[2])[t] = wb;
+          reinterpret_cast<uint32_t*>(out[3])[t] = wb;
+        }
+      }
+    }
+  }
+}
+
+// One 32-bit word (lane = bit) with bound tests: the words around the end of the checked bits and of the message.
+template <bool CRC>
+__device__ __forceinline__ void sweep_word(const hh* soft, const uint2* wgt, int w, int K, int nb0, int nb1, int lane_id,
+                                           uint32_t (&acc)[5], uint8_t* const (&out)[4])
+{
+  const int      i  = 32 * w + lane_id;
+  const __half2  sw = H((i < K) ? soft[i] : H_ONE);
+  const uint32_t hm = __hle2_mask(sw, H(H_ZERO));
+  if (CRC) {
+    const uint32_t shl = 31u - (uint32_t)lane_id;
+    const uint32_t m0  = (i < nb0) ? __byte_perm(hm, 0, 0x1010) : 0u;
+    const uint32_t m1  = (i < nb1) ? __byte_perm(hm, 0, 0x3232) : 0u;
+    const uint2    wg  = wgt[w];
+    acc[4] |= __heq2_mask(sw, H(H_ZERO));
+    acc[0] = lop_xor_and(acc[0], wg.x << shl, m0);
+    acc[1] = lop_xor_and(acc[1], __funnelshift_l(wg.x, 0u, shl), m0);
+    acc[2] = lop_xor_and(acc[2], wg.y << shl, m1);
+    acc[3] = lop_xor_and(acc[3], __funnelshift_l(wg.y, 0u, shl), m1);
+  }
+  if (out[0] != nullptr || out[2] != nullptr) {
+    // Lane k holds bit k of the ballot = bit 31-k of the MSB-first word: reversing the bits of each byte gives the byte
+    // string in memory order.
+    const uint32_t b0 = __ballot_sync(0xffffffffu, (hm & 0xffffu) != 0);
+    const uint32_t b1 = __ballot_sync(0xffffffffu, (hm >> 16) != 0);
+    const int      nbytes = (K + 7) / 8;
+    uint8_t* const o0 = lane_id ? out[2] : out[0];
+    uint8_t* const o1 = lane_id ? out[3] : out[1];
+    if (lane_id < 2 && o0 != nullptr) {
+      const uint32_t le = __byte_perm(__brev(lane_id ? b1 : b0), 0, 0x0123);
+      if (4 * w + 4 <= nbytes) {
+        reinterpret_cast<uint32_t*>(o0)[w] = le;
+        reinterpret_cast<uint32_t*>(o1)[w] = le;
+      } else {
+        for (int k = 0; 4 * w + k < nbytes; ++k) {
+          o0[4 * w + k] = (uint8_t)(le >> (8 * k));
+          o1[4 * w + k] = (uint8_t)(le >> (8 * k));
+        }
+      }
+    }
+  }
+}
+
 // Per-codeblock bookkeeping of the pair.
 struct LaneInfo {
   int valid; // a codeblock is decoded in this half during the current pass
@@ -365,10 +464,6 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
   __shared__ int      sh_defer_b; // codeblock B could not be decoded together with A: it gets its own pass
   __shared__ uint32_t sh_next_pair;
   __shared__ __align__(16) uint32_t sh_desc[2][8];                       // the two descriptors of the pair
-  // Hard decisions of the last check, packed during the sweep (the 384-thread variant; the 192-thread variant runs four
-  // CTAs per SM and has no shared memory to spare for them).
-  constexpr bool PACK_IN_SWEEP = MAX_THREADS > 192;
-  __shared__ __align__(16) uint32_t sh_bits[2][PACK_IN_SWEEP ? (22 * MAX_Z + 31) / 32 : 1];
 
   const int tid  = threadIdx.x;
   const int nthr = blockDim.x;
@@ -688,57 +783,40 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           // bits blocks the early stop. The CRC is computed in the same sweep as M(x) mod P == 0 with
           // M(x) = sum_t W_t(x) x^(32 (T-1-t)): the lane holding bit b of word t adds the UNREDUCED product
           // wgt[t] x^(31-b); the sum is reduced modulo P once, one bit per lane, by the first warp.
+          // On the last iteration every codeblock still active is published whatever its CRC says, so the same sweep
+          // writes its packed hard decisions; a codeblock that stops earlier gets a pack-only sweep below.
+          const int lane_id = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
           {
-            const int lane_id = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
             const int nb0 = lane[0].valid ? K - lane[0].F : 0, nb1 = lane[1].valid ? K - lane[1].F : 0;
-            const int shl = 31 - lane_id;
-            // Words entirely inside the checked bits of both codeblocks need no bound test.
-            const int w_safe = min(nb0, nb1) >> 5;
-            uint32_t  a0l = 0, a0h = 0, a1l = 0, a1h = 0, zacc = 0;
-            auto      sweep = [&](int w, bool bounded) {
-              const int      i  = 32 * w + lane_id;
-              const __half2  sw = H((i < K) ? soft[i] : H_ONE);
-              const uint32_t zm = __heq2_mask(sw, H(H_ZERO)); // 0xffff per half: the soft bit is zero
-              const uint32_t hm = __hle2_mask(sw, H(H_ZERO)); // 0xffff per half: hard bit 1 (soft <= 0)
-              uint32_t       m0 = __byte_perm(hm, 0, 0x1010), m1 = __byte_perm(hm, 0, 0x3232);
-              if (bounded) {
-                m0 = (i < nb0) ? m0 : 0u;
-                m1 = (i < nb1) ? m1 : 0u;
-              }
-              const uint2 wg = wgt[w];
-              // Hard decisions of the word, packed MSB first in memory order, kept for the publication below.
-              if (PACK_IN_SWEEP) {
-                const uint32_t b0 = __ballot_sync(0xffffffffu, (hm & 0xffffu) != 0);
-                const uint32_t b1 = __ballot_sync(0xffffffffu, (hm >> 16) != 0);
-                if (lane_id == 0) {
-                  sh_bits[0][w] = __byte_perm(__brev(b0), 0, 0x0123);
-                  sh_bits[1][w] = __byte_perm(__brev(b1), 0, 0x0123);
+            // Positions inside the checked bits of every codeblock present need no bound test: whole 128-position steps
+            // (four words) of them take the vector path, the rest goes word by word.
+            const int n_steps = min(lane[0].valid ? nb0 : K, lane[1].valid ? nb1 : K) >> 7;
+            uint32_t  acc[5]  = {0, 0, 0, 0, 0}; // a0l, a0h, a1l, a1h, zero flags
+            uint8_t*  out[4]  = {nullptr, nullptr, nullptr, nullptr};
+            if (last_it) {
+              for (int h = 0; h != 2; ++h) {
+                if (lane[h].valid && !lane[h].done) {
+                  out[2 * h]     = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
+                  out[2 * h + 1] = prm.harq_data + (size_t)dsc[h]->harq_id * PDC_MAX_CB_BYTES;
                 }
               }
-              zacc |= zm;
-              a0l = lop_xor_and(a0l, wg.x << shl, m0);
-              a0h = lop_xor_and(a0h, __funnelshift_l(wg.x, 0u, shl), m0);
-              a1l = lop_xor_and(a1l, wg.y << shl, m1);
-              a1h = lop_xor_and(a1h, __funnelshift_l(wg.y, 0u, shl), m1);
-            };
-            int w = warp;
-#pragma unroll 2
-            for (; w < w_safe; w += n_warps) {
-              sweep(w, false);
+              sweep128<true, true>(soft, wgt, n_steps, warp, n_warps, lane_id, acc, out);
+            } else {
+              sweep128<true, false>(soft, wgt, n_steps, warp, n_warps, lane_id, acc, out);
             }
-            for (; w < n_words; w += n_warps) {
-              sweep(w, true);
+            for (int w = 4 * n_steps + warp; w < n_words; w += n_warps) {
+              sweep_word<true>(soft, wgt, w, K, nb0, nb1, lane_id, acc, out);
             }
             // Warp-wide XOR / OR reductions in one instruction each (redux.sync).
-            const int za = __any_sync(0xffffffffu, (zacc & 0xffffu) != 0);
-            const int zb = __any_sync(0xffffffffu, (zacc >> 16) != 0);
-            a0l = __reduce_xor_sync(0xffffffffu, a0l);
-            a0h = __reduce_xor_sync(0xffffffffu, a0h);
-            a1l = __reduce_xor_sync(0xffffffffu, a1l);
-            a1h = __reduce_xor_sync(0xffffffffu, a1h);
+            const int za = __any_sync(0xffffffffu, (acc[4] & 0xffffu) != 0);
+            const int zb = __any_sync(0xffffffffu, (acc[4] >> 16) != 0);
+#pragma unroll
+            for (int k = 0; k != 4; ++k) {
+              acc[k] = __reduce_xor_sync(0xffffffffu, acc[k]);
+            }
             if (lane_id == 0) {
-              sh_part[0][warp] = ((uint64_t)a0h << 32) | a0l;
-              sh_part[1][warp] = ((uint64_t)a1h << 32) | a1l;
+              sh_part[0][warp] = ((uint64_t)acc[1] << 32) | acc[0];
+              sh_part[1][warp] = ((uint64_t)acc[3] << 32) | acc[2];
               sh_zpart[warp]   = (za ? 1 : 0) | (zb ? 2 : 0);
             }
             __syncthreads();
@@ -776,59 +854,22 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
             }
             __syncthreads();
           }
-          // Publish finished codeblocks: the packed hard decisions of the sweep above, copied word by word.
-          if (PACK_IN_SWEEP && (sh_publish[0] || sh_publish[1])) {
-            const int nbytes = (K + 7) / 8, n_full_words = nbytes >> 2;
-#pragma unroll
-            for (int h = 0; h != 2; ++h) {
-              if (!sh_publish[h]) {
-                continue;
-              }
-              uint8_t* out   = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
-              uint8_t* out_h = prm.harq_data + (size_t)dsc[h]->harq_id * PDC_MAX_CB_BYTES;
-              for (int w = tid; w < n_full_words; w += nthr) {
-                const uint32_t le                      = sh_bits[h][w];
-                reinterpret_cast<uint32_t*>(out)[w]   = le;
-                reinterpret_cast<uint32_t*>(out_h)[w] = le;
-              }
-              if (tid == 0) {
-                for (int k = 4 * n_full_words; k < nbytes; ++k) {
-                  const uint8_t v = (uint8_t)(sh_bits[h][k >> 2] >> (8 * (k & 3)));
-                  out[k]   = v;
-                  out_h[k] = v;
+          // Publish finished codeblocks. On the last iteration their hard decisions are already out; a codeblock that
+          // stopped before gets a pack-only sweep now.
+          if (sh_publish[0] || sh_publish[1]) {
+            if (!last_it) {
+              uint8_t* out[4] = {nullptr, nullptr, nullptr, nullptr};
+              for (int h = 0; h != 2; ++h) {
+                if (sh_publish[h]) {
+                  out[2 * h]     = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
+                  out[2 * h + 1] = prm.harq_data + (size_t)dsc[h]->harq_id * PDC_MAX_CB_BYTES;
                 }
-                prm.results[lane[h].cb] = sh_result[h];
               }
-            }
-          }
-          // The small variant (four CTAs per SM, no room for the packed words) packs them here, one word per warp step.
-          if (!PACK_IN_SWEEP && (sh_publish[0] || sh_publish[1])) {
-            const int lane_id = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
-            const int nbytes  = (K + 7) / 8;
-            uint8_t*  out[2];
-            uint8_t*  out_h[2];
-            for (int h = 0; h != 2; ++h) {
-              out[h]   = prm.cb_bits + (size_t)lane[h].cb * PDC_MAX_CB_BYTES;
-              out_h[h] = sh_publish[h] ? prm.harq_data + (size_t)dsc[h]->harq_id * PDC_MAX_CB_BYTES : nullptr;
-            }
-            for (int w = warp; w < n_words; w += n_warps) {
-              const int      i  = 32 * w + lane_id;
-              const uint32_t hm = __hle2_mask(H((i < K) ? soft[i] : H_ONE), H(H_ZERO));
-              const uint32_t b0 = __ballot_sync(0xffffffffu, (hm & 0xffffu) != 0);
-              const uint32_t b1 = __ballot_sync(0xffffffffu, (hm >> 16) != 0);
-              if (lane_id < 2 && sh_publish[lane_id]) {
-                // Lane k holds bit k of the ballot = bit 31-k of the MSB-first word: reversing the bits of each byte
-                // gives the byte string in memory order.
-                const uint32_t le = __byte_perm(__brev(lane_id ? b1 : b0), 0, 0x0123);
-                if (4 * w + 4 <= nbytes) {
-                  reinterpret_cast<uint32_t*>(out[lane_id])[w]   = le;
-                  reinterpret_cast<uint32_t*>(out_h[lane_id])[w] = le;
-                } else {
-                  for (int k = 0; 4 * w + k < nbytes; ++k) {
-                    out[lane_id][4 * w + k]   = (uint8_t)(le >> (8 * k));
-                    out_h[lane_id][4 * w + k] = (uint8_t)(le >> (8 * k));
-                  }
-                }
+              uint32_t  acc[5] = {0, 0, 0, 0, 0};
+              const int n_steps = K >> 7;
+              sweep128<false, true>(soft, wgt, n_steps, warp, n_warps, lane_id, acc, out);
+              for (int w = 4 * n_steps + warp; w < n_words; w += n_warps) {
+                sweep_word<false>(soft, wgt, w, K, 0, 0, lane_id, acc, out);
               }
             }
             if (tid < 2 && sh_publish[tid]) {
