@@ -155,7 +155,7 @@ constexpr int H2_Z_SLOTS = 51;
 __device__ uint2    g_h2_einfo[2][H2_Z_SLOTS][MAX_EDGES + MAX_ROWS];
 __device__ uint32_t g_h2_row_info[2][MAX_ROWS];
 __device__ uint32_t g_h2_xpow32[3][XPOW_ENTRIES];
-__device__ uint8_t  g_h2_z_slot[MAX_Z + 1];
+__constant__ uint8_t c_h2_z_slot[MAX_Z + 1]; // uniform index: one constant-cache access
 
 // CTA barrier that threads of one warp may reach from different places (partial last warp of a lifting size that is not
 // a multiple of 32): the non-aligned form.
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
                                  : make_int4(0, 0, 0, 0);
       }
       if (H2_NO_REUSE || bg != cur_bg || Z != cur_Z) {
-        const uint2* img = g_h2_einfo[b][g_h2_z_slot[Z]];
+        const uint2* img = g_h2_einfo[b][c_h2_z_slot[Z]];
         for (int i = tid; i < MAX_EDGES + MAX_ROWS; i += nthr) {
           uint2 e = img[i];
           e.y += soft_s; // the image holds column bases relative to the soft-bit array
@@ -695,18 +695,20 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           src[h] = lane[h].valid ? reinterpret_cast<const uint32_t*>(in[h]) : nullptr;
         }
         const __half2 h64 = H(0x54005400u), hn64 = H(0xD400D400u), hn1152 = H(0xE480E480u);
-        // Four words of each codeblock in flight per thread (the loop is latency bound: one CTA, streaming loads).
-        const int n_q = (n_load + 3) >> 2;
-        for (int q0 = tid; q0 < n_q; q0 += 4 * nthr) {
-          uint32_t wa[4], wb[4];
+        // Six words of each codeblock in flight per thread (the loop is latency bound: one CTA, streaming loads; six
+        // cover the four-row codeblocks of a high-rate slot in one round trip).
+        constexpr int IN_FLIGHT = 6;
+        const int     n_q       = (n_load + 3) >> 2;
+        for (int q0 = tid; q0 < n_q; q0 += IN_FLIGHT * nthr) {
+          uint32_t wa[IN_FLIGHT], wb[IN_FLIGHT];
 #pragma unroll
-          for (int u = 0; u != 4; ++u) {
+          for (int u = 0; u != IN_FLIGHT; ++u) {
             const int q = q0 + u * nthr;
             wa[u]       = (src[0] && q < n_q) ? ld_stream_u32(src[0] + q, pol_stream) : 0u;
             wb[u]       = (src[1] && q < n_q) ? ld_stream_u32(src[1] + q, pol_stream) : 0u;
           }
 #pragma unroll
-          for (int u = 0; u != 4; ++u) {
+          for (int u = 0; u != IN_FLIGHT; ++u) {
             const int q = q0 + u * nthr;
             if (q < n_q) {
 #pragma unroll
@@ -936,7 +938,7 @@ inline cudaError_t upload_h2_images()
     e = cudaMemcpyToSymbol(h2::g_h2_row_info, row_info, sizeof(row_info));
   }
   if (e == cudaSuccess) {
-    e = cudaMemcpyToSymbol(h2::g_h2_z_slot, z_slot, sizeof(z_slot));
+    e = cudaMemcpyToSymbol(h2::c_h2_z_slot, z_slot, sizeof(z_slot));
   }
   if (e == cudaSuccess) {
     e = cudaMemcpyToSymbol(h2::g_h2_xpow32, h.xpow32, sizeof(h.xpow32));
