@@ -451,7 +451,8 @@ __host__ __device__ inline size_t h2_smem_bytes(int bg, int Z)
 
 template <int MAX_THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
-    ldpc_decode_h2_kernel(BatchParams prm, hh* state_scratch, uint32_t scratch_stride_words, uint32_t* work_counter)
+    ldpc_decode_h2_kernel(BatchParams prm, hh* state_scratch, uint32_t scratch_stride_words, uint32_t* work_counter,
+                          uint32_t counter_base)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ LaneInfo lane[2];
@@ -565,6 +566,10 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       const uint32_t st_stride = (uint32_t)((Z + 31) & ~31);
       const uint32_t soft_s    = (uint32_t)__cvta_generic_to_shared(smem_raw);
 
+      // Programmatic dependent launch: this kernel may have started while the rate dematcher of the same batch was still
+      // draining. Everything above reads only what was complete before the dematcher started (descriptors); what follows
+      // reads what it wrote (soft bits, last non-zero positions).
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       // Last non-zero input of each codeblock (ldpc_decoder_impl.cpp:86-99), recorded by the rate dematcher: the loads
       // are issued here and consumed after the tables are in place.
       const int8_t* in[2];
@@ -887,7 +892,9 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
     }
     __syncthreads();
     if (tid == 0) {
-      sh_next_pair = gridDim.x + atomicAdd(work_counter, 1u);
+      // The counter is never reset: every decoded pair takes exactly one ticket, so a launch advances it by its number
+      // of pairs and the host passes the value it had before the launch.
+      sh_next_pair = gridDim.x + (atomicAdd(work_counter, 1u) - counter_base);
     }
     __syncthreads();
     pair = sh_next_pair;
@@ -946,7 +953,7 @@ inline cudaError_t upload_h2_images()
   return e;
 }
 
-typedef void (*h2_kernel_t)(BatchParams, uint32_t*, uint32_t, uint32_t*);
+typedef void (*h2_kernel_t)(BatchParams, uint32_t*, uint32_t, uint32_t*, uint32_t);
 
 inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count, H2Plan& plan)
 {
@@ -979,18 +986,27 @@ inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count,
   return cudaSuccess;
 }
 
-// work_counter: one zeroed uint32 per launch (pairs beyond the first of every CTA are handed out through it).
+// work_counter: a uint32 that only ever grows; counter_base = its value before this launch (the launch adds one per
+// pair). The kernel is launched with programmatic stream serialization: it may begin while the previous kernel of the
+// stream (the rate dematcher) drains, and waits (griddepcontrol.wait) before touching what that kernel wrote.
 inline cudaError_t launch_ldpc_decode_h2(const BatchParams& p, const H2Plan& plan, uint32_t* scratch,
-                                         uint32_t* work_counter, cudaStream_t s)
+                                         uint32_t* work_counter, uint32_t counter_base, cudaStream_t s)
 {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim            = dim3((unsigned)plan.grid);
+  cfg.blockDim           = dim3((unsigned)plan.threads);
+  cfg.dynamicSmemBytes   = plan.smem;
+  cfg.stream             = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs                                          = attr;
+  cfg.numAttrs                                       = 1;
+  const uint32_t stride = (uint32_t)plan.scratch_words_per_cta;
   if (plan.big) {
-    h2::ldpc_decode_h2_kernel<384, 2>
-        <<<plan.grid, plan.threads, plan.smem, s>>>(p, scratch, (uint32_t)plan.scratch_words_per_cta, work_counter);
-  } else {
-    h2::ldpc_decode_h2_kernel<192, 4>
-        <<<plan.grid, plan.threads, plan.smem, s>>>(p, scratch, (uint32_t)plan.scratch_words_per_cta, work_counter);
+    return cudaLaunchKernelEx(&cfg, h2::ldpc_decode_h2_kernel<384, 2>, p, scratch, stride, work_counter, counter_base);
   }
-  return cudaGetLastError();
+  return cudaLaunchKernelEx(&cfg, h2::ldpc_decode_h2_kernel<192, 4>, p, scratch, stride, work_counter, counter_base);
 }
 
 } // namespace pdc

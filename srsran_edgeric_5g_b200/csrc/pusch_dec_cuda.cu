@@ -148,6 +148,7 @@ struct pdc_ctx {
     uint32_t*    d_state = nullptr;
     size_t       words   = 0;
     uint32_t*    d_counter = nullptr;
+    uint32_t     counter_base = 0; // value of *d_counter once the launches queued so far have run
   };
   std::vector<DecodeScratch> decode_scratch;
   FrontEnd             fe_sync;                   // buffers of the synchronous front-end calls
@@ -263,6 +264,7 @@ int launch_batch(pdc_ctx*             ctx,
         sc         = &ctx->decode_scratch.back();
         sc->stream = s;
         PDC_CUDA(cudaMalloc(reinterpret_cast<void**>(&sc->d_counter), sizeof(uint32_t)));
+        PDC_CUDA(cudaMemsetAsync(sc->d_counter, 0, sizeof(uint32_t), s));
       }
       if (need > sc->words) {
         // Grow-only; sized once per (largest lifting size) in practice. cudaMalloc synchronises the device.
@@ -275,8 +277,16 @@ int launch_batch(pdc_ctx*             ctx,
         sc->words = want;
       }
       // Pairs are handed out dynamically (codeblocks that stop early free their CTA for the next pair).
-      PDC_CUDA(cudaMemsetAsync(sc->d_counter, 0, sizeof(uint32_t), s));
-      PDC_CUDA(pdc::launch_ldpc_decode_h2(p, plan, sc->d_state, sc->d_counter, s));
+      {
+        cudaError_t e = pdc::launch_ldpc_decode_h2(p, plan, sc->d_state, sc->d_counter, sc->counter_base, s);
+        if (e != cudaSuccess) {
+          // Re-arm the ticket counter for whatever comes next.
+          cudaMemsetAsync(sc->d_counter, 0, sizeof(uint32_t), s);
+          sc->counter_base = 0;
+          return fail(PDC_ERR_CUDA, "launch_ldpc_decode_h2", e);
+        }
+        sc->counter_base += (n_cb + 1) / 2;
+      }
     } else {
       PDC_CUDA(pdc::launch_ldpc_decode(p, shape.max_Z, shape.any_bg1, direct_in, direct_n, s));
     }
