@@ -139,4 +139,27 @@ struct TbParams {
   uint8_t*           tb_bytes;
 };
 
+// Launch with programmatic stream serialization: the kernel may begin while the previous kernel of the stream drains
+// (its launch latency and prologue overlap that tail) and must execute pdl_wait() before it touches anything the
+// previous kernel wrote - or anything the previous kernel may still read, if it writes it.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim            = grid;
+  cfg.blockDim           = block;
+  cfg.dynamicSmemBytes   = smem;
+  cfg.stream             = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs                                          = attr;
+  cfg.numAttrs                                       = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 } // namespace pdc

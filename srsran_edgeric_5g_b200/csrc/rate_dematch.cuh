@@ -530,6 +530,9 @@ __global__ void __launch_bounds__(DM_THREADS, 3) rate_dematch_kernel(BatchParams
   const int                        tid = threadIdx.x;
   uint32_t                         cb  = blockIdx.x;
   const pdc_cb_desc                d   = prm.cbs[cb];
+  // Launched with programmatic serialization: the descriptor was uploaded before the previous kernel began; everything
+  // else (soft bits of the front end, the codeblock-to-codeword map, HARQ entries a decoder may still be reading) waits.
+  pdl_wait();
   if (!(d.flags & PDC_CB_DEMATCH)) {
     return;
   }
@@ -662,8 +665,7 @@ inline cudaError_t launch_rate_dematch(const BatchParams& p, int sm_count, cudaS
   while (parts < DM_MAX_PARTS && (size_t)p.n_cb * parts < (size_t)4 * sm_count) {
     parts *= 2;
   }
-  rate_dematch_kernel<<<dim3(p.n_cb, parts), DM_THREADS, 0, s>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(rate_dematch_kernel, dim3(p.n_cb, parts), dim3(DM_THREADS), 0, s, p);
 }
 
 } // namespace pdc

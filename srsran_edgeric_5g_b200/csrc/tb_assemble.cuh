@@ -45,17 +45,18 @@ __global__ void __launch_bounds__(TB_THREADS) tb_assemble_kernel(TbParams prm, c
   const pdc_tb_desc&  tb  = prm.tbs[blockIdx.x];
   const int           tid = threadIdx.x;
   int                 ok  = 1;
-  for (uint32_t i = tid; i < tb.nof_cb; i += blockDim.x) {
-    const pdc_cb_desc& d = prm.cbs[tb.first_cb + i];
-    if ((d.flags & PDC_CB_DECODE) && !prm.cb_results[tb.first_cb + i].crc_ok) {
-      ok = 0;
-    }
-  }
   if (tid < 256) {
     sh_table[tid] = c_crc24a_table[tid];
   }
   if (tid == 0) {
     sh_crc = 0;
+  }
+  pdl_wait(); // launched behind the decoder with programmatic serialization: its results are read from here on
+  for (uint32_t i = tid; i < tb.nof_cb; i += blockDim.x) {
+    const pdc_cb_desc& d = prm.cbs[tb.first_cb + i];
+    if ((d.flags & PDC_CB_DECODE) && !prm.cb_results[tb.first_cb + i].crc_ok) {
+      ok = 0;
+    }
   }
   ok = __syncthreads_and(ok);
   pdc_tb_result r;
@@ -199,8 +200,7 @@ inline cudaError_t launch_tb_assemble(const TbParams& p, const uint8_t* harq_dat
   if (p.n_tb == 0) {
     return cudaSuccess;
   }
-  tb_assemble_kernel<<<dim3(p.n_tb, TB_SPLIT), TB_THREADS, 0, s>>>(p, harq_data, sync);
-  return cudaGetLastError();
+  return launch_pdl(tb_assemble_kernel, dim3(p.n_tb, TB_SPLIT), dim3(TB_THREADS), 0, s, p, harq_data, sync);
 }
 
 } // namespace pdc
