@@ -899,6 +899,9 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
     __syncthreads();
     pair = sh_next_pair;
   }
+  // A CTA that never reached the wait above (only invalid codeblocks) must not let the grid complete ahead of the
+  // kernel it was serialized behind: the next kernel's wait relies on this one for the ordering.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 } // namespace h2

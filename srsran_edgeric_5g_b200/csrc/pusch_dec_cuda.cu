@@ -223,9 +223,8 @@ int launch_batch(pdc_ctx*             ctx,
   if (fe != nullptr && fe->deferred && shape.any_dematch && d_llrs == fe->deferred_sch) {
     // Codewords whose descrambling was deferred to this batch: map every codeblock to its codeword (one-shot).
     PDC_CUDA(grow_device(&fe->d_cb_scr, &fe->cb_scr_cap, (size_t)n_cb));
-    pdc::cb_descramble_map_kernel<<<(n_cb + 255) / 256, 256, 0, s>>>(
-        d_cbs, n_cb, reinterpret_cast<const pdc::UlschCodeword*>(fe->d_plan), fe->deferred_n_cw, fe->d_cb_scr);
-    PDC_CUDA(cudaGetLastError());
+    PDC_CUDA(pdc::launch_pdl(pdc::cb_descramble_map_kernel, dim3((n_cb + 255) / 256), dim3(256), 0, s, d_cbs, n_cb,
+                             reinterpret_cast<const pdc::UlschCodeword*>(fe->d_plan), fe->deferred_n_cw, fe->d_cb_scr));
     ctx->launches++;
     p.cb_scr     = fe->d_cb_scr;
     p.seq        = fe->d_seq;
@@ -771,13 +770,11 @@ static int front_end_kernels(pdc_ctx* ctx, FrontEnd& fe, cudaStream_t s)
     // Enough CTAs to fill the GPU a few times over; each thread steps through the chunks of its codeword.
     const uint32_t chunks = (fe.k_max_sch + 15) / 16;
     uint32_t       gx = std::max(1u, std::min((chunks + 255) / 256, (uint32_t)(8 * ctx->sm_count + n_cw - 1) / n_cw));
-    pdc::ulsch_sch_kernel<<<dim3(gx, n_cw), 256, 0, s>>>(a);
-    PDC_CUDA(cudaGetLastError());
+    PDC_CUDA(pdc::launch_pdl(pdc::ulsch_sch_kernel, dim3(gx, n_cw), dim3(256), 0, s, a));
     ctx->launches++;
   }
   if (fe.k_max_uci != 0) {
-    pdc::ulsch_uci_kernel<<<dim3((fe.k_max_uci + 255) / 256, n_cw), 256, 0, s>>>(a);
-    PDC_CUDA(cudaGetLastError());
+    PDC_CUDA(pdc::launch_pdl(pdc::ulsch_uci_kernel, dim3((fe.k_max_uci + 255) / 256, n_cw), dim3(256), 0, s, a));
     ctx->launches++;
   }
   if (fe.uci_copy_dst != nullptr && fe.uci_bytes != 0) {

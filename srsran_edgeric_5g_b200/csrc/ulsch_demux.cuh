@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(256) ulsch_sch_kernel(UlschArgs a)
 {
   __shared__ UlschCodeword cw;
   __shared__ UlschSymbol   S[ULSCH_MAX_SYMBOLS];
+  pdl_wait(); // programmatic serialization behind prg_kernel / the soft demapper
   if (threadIdx.x == 0) {
     cw = a.cws[blockIdx.y];
   }
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(256) ulsch_uci_kernel(UlschArgs a)
 {
   __shared__ UlschCodeword cw;
   __shared__ UlschSymbol   S[ULSCH_MAX_SYMBOLS];
+  pdl_wait();
   if (threadIdx.x == 0) {
     cw = a.cws[blockIdx.y];
   }
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(256) ulsch_uci_kernel(UlschArgs a)
 __global__ void cb_descramble_map_kernel(const pdc_cb_desc* __restrict__ cbs, uint32_t n_cb,
                                          const UlschCodeword* __restrict__ cws, uint32_t n_cw, uint4* __restrict__ out)
 {
+  pdl_wait();
   const uint32_t cb = blockIdx.x * blockDim.x + threadIdx.x;
   if (cb >= n_cb) {
     return;
