@@ -18,8 +18,8 @@ namespace pdc {
 // Kernel geometry. The rate-matched input of a codeblock is first staged in shared memory in DEINTERLEAVED order
 // (coalesced 64/128-bit global loads, bit planes separated with byte permutes), so the gather that follows reads
 // consecutive bytes. Inputs longer than the staging buffer are gathered from global memory instead.
-constexpr int DM_THREADS     = 512;
-constexpr int DM_STAGE_BYTES = 40960;
+constexpr int DM_THREADS     = 256;
+constexpr int DM_STAGE_BYTES = 25600; // one lap of the largest codeblock; longer inputs take the unstaged path (eight CTAs per SM matter more)
 constexpr int DM_MAX_PARTS   = 4; // CTAs per codeblock (small batches are latency bound: split the N positions)
 
 struct DematchGeom {
@@ -519,7 +519,7 @@ __device__ __forceinline__ void dm_stage(const DematchGeom& g, const int8_t* __r
 }
 
 // gridDim = (codeblocks, parts). Each CTA owns a contiguous range of the 32-bit words of the HARQ entry.
-__global__ void __launch_bounds__(DM_THREADS, 3) rate_dematch_kernel(BatchParams prm)
+__global__ void __launch_bounds__(DM_THREADS, 8) rate_dematch_kernel(BatchParams prm)
 {
   __shared__ __align__(16) uint8_t sh_in[DM_STAGE_BYTES + 16];
   __shared__ DematchGeom           g_sh;
@@ -662,7 +662,7 @@ inline cudaError_t launch_rate_dematch(const BatchParams& p, int sm_count, cudaS
   }
   // Small batches are latency bound: up to DM_MAX_PARTS CTAs per codeblock until the GPU is filled a few times over.
   int parts = 1;
-  while (parts < DM_MAX_PARTS && (size_t)p.n_cb * parts < (size_t)4 * sm_count) {
+  while (parts < DM_MAX_PARTS && (size_t)p.n_cb * parts < (size_t)8 * sm_count) {
     parts *= 2;
   }
   return launch_pdl(rate_dematch_kernel, dim3(p.n_cb, parts), dim3(DM_THREADS), 0, s, p);
