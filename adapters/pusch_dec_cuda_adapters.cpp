@@ -515,3 +515,211 @@ std::shared_ptr<channel_modulation_factory> srsran::cuda::create_channel_modulat
 {
   return std::make_shared<channel_modulation_factory_cuda>(std::move(ctx));
 }
+
+// ---- batched PUSCH decoder -------------------------------------------------------------------------------------------
+
+pusch_decoder_batch_cuda::pusch_decoder_batch_cuda(std::shared_ptr<context>           c,
+                                                   unsigned                           queue,
+                                                   std::unique_ptr<ldpc_segmenter_rx> seg) :
+  ctx(std::move(c)), queue_id(queue), segmenter(std::move(seg))
+{
+}
+
+pusch_decoder_batch_cuda::~pusch_decoder_batch_cuda()
+{
+  pdc_wait(ctx->get(), queue_id);
+  pdc_host_free(llr_staging);
+  pdc_host_free(tb_staging);
+}
+
+std::unique_ptr<pusch_decoder> pusch_decoder_batch_cuda::create()
+{
+  return std::make_unique<pusch_decoder_cuda>(*this);
+}
+
+pusch_decoder_buffer& pusch_decoder_cuda::new_data(span<uint8_t>           transport_block,
+                                                   unique_rx_buffer        rm_buffer,
+                                                   pusch_decoder_notifier& notifier,
+                                                   const configuration&    cfg)
+{
+  srsran_assert(st == state::idle, "Invalid state: the decoder is busy.");
+  const unsigned nof_cb = ldpc::compute_nof_codeblocks(units::bytes(transport_block.size()).to_bits(), cfg.base_graph);
+  srsran_assert(nof_cb == rm_buffer.get().get_nof_codeblocks(),
+                "Wrong number of codeblocks {} (expected {}).",
+                rm_buffer.get().get_nof_codeblocks(),
+                nof_cb);
+  current.decoder         = this;
+  current.transport_block = transport_block;
+  current.rm_buffer       = std::move(rm_buffer);
+  current.notifier        = &notifier;
+  current.cfg             = cfg;
+  current.llrs.clear();
+  expected_softbits.reset();
+  if (cfg.new_data) {
+    current.rm_buffer.get().reset_codeblocks_crc(); // pusch_decoder_impl.cpp:125-127
+  }
+  st = state::collecting;
+  return *this;
+}
+
+void pusch_decoder_cuda::set_nof_softbits(units::bits nof_softbits)
+{
+  // The batch starts at flush(); like pusch_decoder_hw_impl::set_nof_softbits this only records the expectation.
+  expected_softbits = nof_softbits.value();
+}
+
+span<log_likelihood_ratio> pusch_decoder_cuda::get_next_block_view(unsigned block_size)
+{
+  srsran_assert(st == state::collecting, "Invalid state.");
+  view.resize(block_size);
+  return view;
+}
+
+void pusch_decoder_cuda::on_new_softbits(span<const log_likelihood_ratio> softbits)
+{
+  srsran_assert(st == state::collecting, "Invalid state.");
+  current.llrs.insert(current.llrs.end(), softbits.begin(), softbits.end());
+}
+
+void pusch_decoder_cuda::on_end_softbits()
+{
+  srsran_assert(st == state::collecting, "Invalid state.");
+  srsran_assert(!expected_softbits.has_value() || *expected_softbits == current.llrs.size(),
+                "The number of UL-SCH softbits does not match the expected value.");
+  srsran_assert(current.llrs.size() % get_bits_per_symbol(current.cfg.mod) == 0,
+                "The number of soft bits must be multiple of the modulation order.");
+  st = state::decoding;
+  batch.queue(std::move(current));
+}
+
+bool pusch_decoder_batch_cuda::flush()
+{
+  if (queued.empty()) {
+    return true;
+  }
+  std::vector<queued_tb> work;
+  work.swap(queued);
+  cbs.clear();
+  tbs.clear();
+  decode_mask.clear();
+  size_t n_llr = 0, tb_bytes = 0;
+  for (const queued_tb& q : work) {
+    n_llr += q.llrs.size();
+    tb_bytes += (q.transport_block.size() * 8 + 24 + 31) / 32 * 4;
+  }
+  if (n_llr > llr_capacity) {
+    pdc_host_free(llr_staging);
+    llr_capacity = n_llr + n_llr / 4 + 64;
+    llr_staging  = static_cast<int8_t*>(pdc_host_alloc(llr_capacity));
+  }
+  if (tb_bytes > tb_capacity) {
+    pdc_host_free(tb_staging);
+    tb_capacity = tb_bytes + tb_bytes / 4 + 64;
+    tb_staging  = static_cast<uint8_t*>(pdc_host_alloc(tb_capacity));
+  }
+  srsran_assert(llr_staging != nullptr && tb_staging != nullptr, "pdc_host_alloc failed: {}", pdc_last_error());
+  size_t llr_off = 0, tb_off = 0;
+  for (size_t i_tb = 0; i_tb != work.size(); ++i_tb) {
+    queued_tb&     q        = work[i_tb];
+    const unsigned tbs_bits = static_cast<unsigned>(q.transport_block.size() * 8);
+    // Segmentation by the reference's own segmenter (ldpc_segmenter_rx_impl), as in pusch_decoder_impl::on_end_softbits.
+    segmenter_config seg_cfg;
+    seg_cfg.base_graph     = q.cfg.base_graph;
+    seg_cfg.rv             = q.cfg.rv;
+    seg_cfg.mod            = q.cfg.mod;
+    seg_cfg.Nref           = q.cfg.Nref;
+    seg_cfg.nof_layers     = q.cfg.nof_layers;
+    seg_cfg.nof_ch_symbols = static_cast<unsigned>(q.llrs.size()) / get_bits_per_symbol(q.cfg.mod);
+    static_vector<described_rx_codeblock, MAX_NOF_SEGMENTS> blocks;
+    segmenter->segment(blocks, q.llrs, tbs_bits, seg_cfg);
+    const unsigned C = static_cast<unsigned>(blocks.size());
+    // A lone codeblock carries the transport-block CRC (CRC16 up to 3824 bits, CRC24A above), the others CRC24B.
+    const int  crc_kind = (C > 1) ? PDC_CRC24B : (tbs_bits > 3824 ? PDC_CRC24A : PDC_CRC16);
+    span<bool> crcs     = q.rm_buffer.get().get_codeblocks_crc();
+    memcpy(llr_staging + llr_off, q.llrs.data(), q.llrs.size());
+    pdc_tb_desc t   = {};
+    t.first_cb      = static_cast<uint32_t>(cbs.size());
+    t.nof_cb        = C;
+    t.tbs_bits      = tbs_bits;
+    t.out_offset    = static_cast<uint32_t>(tb_off);
+    tbs.push_back(t);
+    tb_off += (tbs_bits + 24 + 31) / 32 * 4;
+    for (unsigned k = 0; k != C; ++k) {
+      const codeblock_metadata& m = blocks[k].second;
+      pdc_cb_desc               d = {};
+      d.llr_offset                = static_cast<uint32_t>(llr_off + m.cb_specific.cw_offset);
+      d.rm_length                 = m.cb_specific.rm_length;
+      d.harq_id                   = q.rm_buffer.get().get_absolute_codeblock_id(k);
+      d.nref                      = m.tb_common.Nref;
+      d.lifting_size              = static_cast<uint16_t>(m.tb_common.lifting_size);
+      d.nof_filler                = static_cast<uint16_t>(m.cb_specific.nof_filler_bits);
+      d.base_graph                = (m.tb_common.base_graph == ldpc_base_graph_type::BG1) ? 1 : 2;
+      d.qm                        = static_cast<uint8_t>(get_bits_per_symbol(m.tb_common.mod));
+      d.rv                        = static_cast<uint8_t>(m.tb_common.rv);
+      d.crc_kind                  = static_cast<uint8_t>(crc_kind);
+      d.max_iter                  = static_cast<uint8_t>(q.cfg.nof_ldpc_iterations);
+      // Codeblocks whose CRC already passed are only combined, not decoded again (pusch_decoder_impl.cpp:335-345).
+      const bool decode = !crcs[k];
+      d.flags           = static_cast<uint8_t>(PDC_CB_DEMATCH | (q.cfg.new_data ? PDC_CB_NEW_DATA : 0) |
+                                     (q.cfg.use_early_stop ? PDC_CB_EARLY_STOP : 0) | (decode ? PDC_CB_DECODE : 0));
+      d.tb_index        = static_cast<uint16_t>(i_tb);
+      cbs.push_back(d);
+      decode_mask.push_back(decode ? 1 : 0);
+    }
+    llr_off += q.llrs.size();
+  }
+  cb_results.assign(cbs.size(), pdc_cb_result{});
+  tb_results.assign(tbs.size(), pdc_tb_result{});
+  int rc = pdc_submit(ctx->get(), queue_id, cbs.data(), static_cast<uint32_t>(cbs.size()), llr_staging, n_llr, tbs.data(),
+                      static_cast<uint32_t>(tbs.size()), cb_results.data(), nullptr, tb_results.data(), tb_staging);
+  if (rc == PDC_OK) {
+    rc = pdc_wait(ctx->get(), queue_id);
+  }
+  const bool ok = (rc == PDC_OK);
+  for (size_t i_tb = 0; i_tb != work.size(); ++i_tb) {
+    queued_tb&           q = work[i_tb];
+    const pdc_tb_desc&   t = tbs[i_tb];
+    span<bool>           crcs = q.rm_buffer.get().get_codeblocks_crc();
+    pusch_decoder_result result;
+    result.tb_crc_ok            = false;
+    result.nof_codeblocks_total = t.nof_cb;
+    if (ok) {
+      for (unsigned k = 0; k != t.nof_cb; ++k) {
+        if (!decode_mask[t.first_cb + k]) {
+          continue;
+        }
+        const pdc_cb_result& r = cb_results[t.first_cb + k];
+        if (r.crc_ok) {
+          crcs[k] = true;
+          result.ldpc_decoder_stats.update(r.iters);
+        } else {
+          result.ldpc_decoder_stats.update(q.cfg.nof_ldpc_iterations);
+        }
+      }
+      const bool all_ok = std::all_of(crcs.begin(), crcs.end(), [](bool b) { return b; });
+      if (t.nof_cb == 1) {
+        // The codeblock CRC is the transport-block CRC (pusch_decoder_impl.cpp:404-412).
+        result.tb_crc_ok = crcs[0];
+        if (result.tb_crc_ok) {
+          memcpy(q.transport_block.data(), tb_staging + t.out_offset, q.transport_block.size());
+        }
+      } else if (all_ok) {
+        memcpy(q.transport_block.data(), tb_staging + t.out_offset, q.transport_block.size());
+        if (tb_results[i_tb].tb_crc_ok) {
+          result.tb_crc_ok = true;
+        } else {
+          // All codeblocks pass but the transport block does not: start over (pusch_decoder_impl.cpp:428-433).
+          q.rm_buffer.get().reset_codeblocks_crc();
+        }
+      }
+    }
+    if (result.tb_crc_ok) {
+      q.rm_buffer.release();
+    } else {
+      q.rm_buffer.unlock();
+    }
+    q.decoder->st = pusch_decoder_cuda::state::idle;
+    q.notifier->on_sch_data(result);
+  }
+  return ok;
+}

@@ -14,6 +14,11 @@
 ///   demodulation_mapper_cuda      : srsran::demodulation_mapper     (phy/upper/channel_modulation/demodulation_mapper.h:41-69),
 ///                                   created by create_channel_modulation_cuda_factory() in the place of
 ///                                   create_channel_modulation_sw_factory() (channel_modulation_factories.h:32-41).
+///   pusch_decoder_cuda / pusch_decoder_batch_cuda : srsran::pusch_decoder (phy/upper/channel_processors/pusch/
+///                                   pusch_decoder.h:54-99), the BATCHED decoder: every decoder created from one batch
+///                                   object queues its transport block at on_end_softbits; flush() decodes all of them
+///                                   (every UE and cell of the slot) with ONE pdc_submit, TB concatenation and TB CRC on
+///                                   the device, and then fires the notifiers.
 /// and the factories a "cuda" branch of create_ldpc_decoder_factory_sw / create_ldpc_rate_dematcher_factory_sw /
 /// create_crc_calculator_factory_sw / create_hw_accelerator_pusch_dec_factory returns.
 #pragma once
@@ -24,9 +29,15 @@
 #include "srsran/phy/upper/channel_coding/channel_coding_factories.h"
 #include "srsran/phy/upper/channel_modulation/channel_modulation_factories.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_codeword_buffer.h"
+#include "srsran/phy/upper/channel_coding/ldpc/ldpc_segmenter_rx.h"
+#include "srsran/phy/upper/channel_processors/pusch/pusch_decoder.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_buffer.h"
+#include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_notifier.h"
+#include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_result.h"
+#include "srsran/phy/upper/unique_rx_buffer.h"
 #include "srsran/phy/upper/channel_processors/pusch/ulsch_demultiplex.h"
 #include <memory>
+#include <optional>
 #include <vector>
 
 namespace srsran {
@@ -187,6 +198,83 @@ private:
 /// Channel-modulation factory whose demodulation mapper runs on the GPU; the modulation mapper and the EVM calculator are
 /// the software ones (they are not on the uplink decode path).
 std::shared_ptr<channel_modulation_factory> create_channel_modulation_cuda_factory(std::shared_ptr<context> ctx);
+
+class pusch_decoder_cuda;
+
+/// \brief Slot batch of the batched PUSCH decoder (the throughput path of INTEGRATION.md 3).
+///
+/// Owns one accelerator queue. pusch_decoder_cuda instances created from it behave like pusch_decoder_impl up to
+/// on_end_softbits, which queues the transport block instead of decoding it; flush() - called once the PUSCH processors
+/// of the slot have delivered their soft bits - builds the codeblock and transport-block descriptors with the
+/// reference's own ldpc_segmenter_rx, submits them as one batch and reports every transport block through its
+/// notifier exactly as pusch_decoder_impl::join_and_notify does (pusch_decoder_impl.cpp:384-450): codeblock CRC flags
+/// in the rx buffer, iteration statistics, TB bytes, TB CRC, buffer release / unlock. Deferring on_sch_data is what the
+/// interface allows (the software decoder also completes on another thread, pusch_decoder_impl.cpp:365-367).
+class pusch_decoder_batch_cuda
+{
+public:
+  /// \param queue Queue ("stream") of the context this batch submits on.
+  pusch_decoder_batch_cuda(std::shared_ptr<context> ctx, unsigned queue, std::unique_ptr<ldpc_segmenter_rx> segmenter);
+  ~pusch_decoder_batch_cuda();
+  /// pusch_decoder_factory::create(): a decoder bound to this batch (one per PUSCH processor).
+  std::unique_ptr<pusch_decoder> create();
+  /// Number of transport blocks waiting for flush().
+  unsigned pending() const { return static_cast<unsigned>(queued.size()); }
+  /// Decodes everything queued with one GPU submission and notifies. Returns false if the submission failed (every
+  /// queued transport block is then reported with tb_crc_ok = false).
+  bool flush();
+
+private:
+  friend class pusch_decoder_cuda;
+  struct queued_tb {
+    pusch_decoder_cuda*               decoder;
+    span<uint8_t>                     transport_block;
+    unique_rx_buffer                  rm_buffer;
+    pusch_decoder_notifier*           notifier;
+    pusch_decoder::configuration      cfg;
+    std::vector<log_likelihood_ratio> llrs;
+  };
+  void queue(queued_tb&& tb) { queued.push_back(std::move(tb)); }
+
+  std::shared_ptr<context>           ctx;
+  unsigned                           queue_id;
+  std::unique_ptr<ldpc_segmenter_rx> segmenter;
+  std::vector<queued_tb>             queued;
+  std::vector<pdc_cb_desc>           cbs;
+  std::vector<pdc_tb_desc>           tbs;
+  std::vector<pdc_cb_result>         cb_results;
+  std::vector<pdc_tb_result>         tb_results;
+  std::vector<uint8_t>               decode_mask;
+  int8_t*                            llr_staging  = nullptr; // page-locked
+  size_t                             llr_capacity = 0;
+  uint8_t*                           tb_staging   = nullptr; // page-locked
+  size_t                             tb_capacity  = 0;
+};
+
+/// One PUSCH decoder bound to a pusch_decoder_batch_cuda; the pusch_decoder_buffer it hands out is itself.
+class pusch_decoder_cuda : public pusch_decoder, private pusch_decoder_buffer
+{
+public:
+  explicit pusch_decoder_cuda(pusch_decoder_batch_cuda& b) : batch(b) {}
+  pusch_decoder_buffer& new_data(span<uint8_t>           transport_block,
+                                 unique_rx_buffer        rm_buffer,
+                                 pusch_decoder_notifier& notifier,
+                                 const configuration&    cfg) override;
+  void                  set_nof_softbits(units::bits nof_softbits) override;
+
+private:
+  friend class pusch_decoder_batch_cuda;
+  span<log_likelihood_ratio> get_next_block_view(unsigned block_size) override;
+  void                       on_new_softbits(span<const log_likelihood_ratio> softbits) override;
+  void                       on_end_softbits() override;
+
+  enum class state { idle, collecting, decoding };
+  pusch_decoder_batch_cuda&          batch;
+  state                              st = state::idle;
+  pusch_decoder_batch_cuda::queued_tb current;
+  std::vector<log_likelihood_ratio>  view;
+  std::optional<unsigned>            expected_softbits;
+};
 
 std::shared_ptr<ldpc_decoder_factory>        create_ldpc_decoder_factory_cuda(std::shared_ptr<context> ctx);
 std::shared_ptr<ldpc_rate_dematcher_factory> create_ldpc_rate_dematcher_factory_cuda(std::shared_ptr<context> ctx);

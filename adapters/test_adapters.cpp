@@ -327,6 +327,144 @@ int main()
     }
   }
 
+  // ---- batched PUSCH decoder: several UEs per slot in ONE submission vs the software decoder, over HARQ retransmissions ---
+  {
+    struct ue_t {
+      int                  bg, qm, nl, tb_bytes, nsym, n_llr;
+      unsigned             C, nref, max_it;
+      bool                 early, done = false;
+      double               sigma2;
+      std::vector<uint8_t> tb;
+      std::unique_ptr<test_rx_buffer> buf_sw, buf_gpu;
+      std::unique_ptr<pusch_decoder_impl> sw;
+      std::unique_ptr<pusch_decoder>      gpu;
+    };
+    cuda::pusch_decoder_batch_cuda batch(ctx, 1, create_ldpc_segmenter_rx_factory_sw()->create());
+    std::vector<ue_t>              ues(7);
+    unsigned                       next_id = 1200;
+    for (size_t u = 0; u != ues.size(); ++u) {
+      ue_t& e    = ues[u];
+      e.bg       = (u % 3 == 2) ? 2 : 1;
+      e.qm       = 2 + 2 * static_cast<int>(u % 4);
+      e.nl       = 1 + static_cast<int>(u % 2);
+      e.tb_bytes = (e.bg == 1) ? 600 + 2100 * static_cast<int>(u) : 40 + 90 * static_cast<int>(u);
+      double rate = (e.bg == 1) ? 0.62 + 0.04 * (u % 5) : 0.3 + 0.04 * (u % 5);
+      e.nsym      = static_cast<int>(std::ceil(e.tb_bytes * 8 / rate / e.qm / e.nl)) * e.nl;
+      e.n_llr     = e.nsym * e.qm;
+      e.C         = ldpc::compute_nof_codeblocks(units::bits(e.tb_bytes * 8),
+                                         e.bg == 1 ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2);
+      e.nref      = (u % 2) ? ldpc::compute_N_ref(units::bytes(e.tb_bytes + 40), e.C).value() : 0;
+      e.early     = u % 2;
+      e.max_it    = 3 + u % 4;
+      double snr  = ((e.bg == 1) ? 8.0 : 3.0) * rate / 0.8 - 1.6 - 0.6 * (u % 4);
+      e.sigma2    = std::pow(10.0, -snr / 10.0);
+      e.tb.resize(e.tb_bytes);
+      for (auto& v : e.tb) {
+        v = rng() & 0xff;
+      }
+      e.buf_sw  = std::make_unique<test_rx_buffer>(e.C, 0);
+      e.buf_gpu = std::make_unique<test_rx_buffer>(e.C, next_id);
+      next_id += e.C;
+      std::vector<std::unique_ptr<pusch_codeblock_decoder>> cbd(1);
+      pusch_codeblock_decoder::sch_crc c1{crc_f->create(crc_generator_poly::CRC16),
+                                          crc_f->create(crc_generator_poly::CRC24A),
+                                          crc_f->create(crc_generator_poly::CRC24B)};
+      cbd[0]    = std::make_unique<pusch_codeblock_decoder>(create_ldpc_rate_dematcher_factory_sw("auto")->create(),
+                                                         create_ldpc_decoder_factory_sw("auto")->create(),
+                                                         c1);
+      auto pool = std::make_shared<pusch_decoder_impl::codeblock_decoder_pool>(std::move(cbd));
+      pusch_decoder_impl::sch_crc c2{crc_f->create(crc_generator_poly::CRC16),
+                                     crc_f->create(crc_generator_poly::CRC24A),
+                                     crc_f->create(crc_generator_poly::CRC24B)};
+      e.sw  = std::make_unique<pusch_decoder_impl>(create_ldpc_segmenter_rx_factory_sw()->create(), pool, std::move(c2),
+                                                  nullptr, MAX_RB, 4);
+      e.gpu = batch.create();
+    }
+    const int rvs[4]     = {0, 2, 3, 1};
+    unsigned  slots_done = 0, tbs_compared = 0;
+    for (int t = 0; t != 4; ++t) {
+      std::vector<std::vector<uint8_t>> out_sw(ues.size()), out_gpu(ues.size());
+      std::vector<spy>                  n_sw(ues.size()), n_gpu(ues.size());
+      std::vector<size_t>               active;
+      for (size_t u = 0; u != ues.size(); ++u) {
+        ue_t& e = ues[u];
+        if (e.done) {
+          continue;
+        }
+        active.push_back(u);
+        std::vector<uint8_t> cw(e.n_llr);
+        ref_tb_encode(e.tb.data(), e.tb_bytes, e.bg, rvs[t], e.qm, e.nref, e.nl, e.nsym, cw.data());
+        std::vector<log_likelihood_ratio> llrs(e.n_llr);
+        std::normal_distribution<double>  noise(0.0, std::sqrt(e.sigma2));
+        for (int i = 0; i != e.n_llr; ++i) {
+          double y = (1.0 - 2.0 * cw[i]) + noise(rng);
+          double l = std::round(12.0 * y / e.sigma2);
+          llrs[i]  = static_cast<int>(std::max(-120.0, std::min(120.0, l)));
+        }
+        pusch_decoder::configuration cfg;
+        cfg.base_graph          = e.bg == 1 ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2;
+        cfg.rv                  = rvs[t];
+        cfg.mod                 = to_mod(e.qm);
+        cfg.Nref                = e.nref;
+        cfg.nof_layers          = e.nl;
+        cfg.nof_ldpc_iterations = e.max_it;
+        cfg.use_early_stop      = e.early;
+        cfg.new_data            = (t == 0);
+        out_sw[u].assign(e.tb_bytes, 0);
+        out_gpu[u].assign(e.tb_bytes, 0);
+        {
+          pusch_decoder_buffer& b = e.sw->new_data(out_sw[u], unique_rx_buffer(*e.buf_sw), n_sw[u], cfg);
+          b.on_new_softbits(llrs);
+          b.on_end_softbits();
+        }
+        {
+          // Soft bits arrive in two blocks through the view the decoder hands out, like from the demodulator.
+          pusch_decoder_buffer& b = e.gpu->new_data(out_gpu[u], unique_rx_buffer(*e.buf_gpu), n_gpu[u], cfg);
+          e.gpu->set_nof_softbits(units::bits(e.n_llr));
+          const unsigned             first = (e.n_llr / 2 / e.qm) * e.qm;
+          span<log_likelihood_ratio> v     = b.get_next_block_view(first);
+          std::copy(llrs.begin(), llrs.begin() + first, v.begin());
+          b.on_new_softbits(v);
+          b.on_new_softbits(span<const log_likelihood_ratio>(llrs).last(e.n_llr - first));
+          b.on_end_softbits();
+        }
+      }
+      if (active.empty()) {
+        break;
+      }
+      CHECK(batch.pending() == active.size(), "batched decoder: %u transport blocks queued, %zu expected", batch.pending(),
+            active.size());
+      CHECK(batch.flush(), "batched decoder: flush failed: %s", pdc_last_error());
+      ++slots_done;
+      for (size_t u : active) {
+        ue_t&                       e = ues[u];
+        const pusch_decoder_result &a = n_sw[u].result, &b = n_gpu[u].result;
+        CHECK(a.tb_crc_ok == b.tb_crc_ok, "batched decoder: tb_crc_ok differs (ue %zu tx %d)", u, t);
+        CHECK(a.nof_codeblocks_total == b.nof_codeblocks_total, "batched decoder: nof_codeblocks differs (ue %zu)", u);
+        CHECK(a.ldpc_decoder_stats.get_nof_observations() == b.ldpc_decoder_stats.get_nof_observations(),
+              "batched decoder: observations differ (ue %zu tx %d)", u, t);
+        if (a.ldpc_decoder_stats.get_nof_observations() && b.ldpc_decoder_stats.get_nof_observations()) {
+          CHECK(a.ldpc_decoder_stats.get_min() == b.ldpc_decoder_stats.get_min() &&
+                    a.ldpc_decoder_stats.get_max() == b.ldpc_decoder_stats.get_max() &&
+                    a.ldpc_decoder_stats.get_mean() == b.ldpc_decoder_stats.get_mean(),
+                "batched decoder: iteration statistics differ (ue %zu tx %d)", u, t);
+        }
+        for (unsigned cb = 0; cb != e.C; ++cb) {
+          CHECK(e.buf_sw->crcs[cb] == e.buf_gpu->crcs[cb], "batched decoder: CB CRC flag differs (ue %zu tx %d cb %u)", u,
+                t, cb);
+        }
+        if (a.tb_crc_ok) {
+          CHECK(out_sw[u] == out_gpu[u] && out_sw[u] == e.tb, "batched decoder: TB bytes differ (ue %zu tx %d)", u, t);
+          e.done = true;
+        }
+        ++tbs_compared;
+      }
+    }
+    std::printf("pusch_decoder_batch_cuda: %u slots, %u transport blocks compared with pusch_decoder_impl\n", slots_done,
+                tbs_compared);
+    CHECK(tbs_compared >= 7 && slots_done >= 2, "batched decoder: too little was compared");
+  }
+
   // ---- ulsch_demultiplex_cuda vs the reference's ulsch_demultiplex_impl ---------------------------------------------------
   {
     auto     demux_gpu = cuda::create_ulsch_demultiplex_cuda(ctx);
