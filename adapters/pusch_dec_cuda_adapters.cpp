@@ -723,3 +723,21 @@ bool pusch_decoder_batch_cuda::flush()
   }
   return ok;
 }
+
+namespace {
+class pusch_decoder_factory_cuda : public pusch_decoder_factory
+{
+public:
+  explicit pusch_decoder_factory_cuda(std::shared_ptr<pusch_decoder_batch_cuda> b) : batch(std::move(b)) {}
+  std::unique_ptr<pusch_decoder> create() override { return batch->create(); }
+
+private:
+  std::shared_ptr<pusch_decoder_batch_cuda> batch;
+};
+} // namespace
+
+std::shared_ptr<pusch_decoder_factory>
+srsran::cuda::create_pusch_decoder_factory_cuda(std::shared_ptr<pusch_decoder_batch_cuda> batch)
+{
+  return std::make_shared<pusch_decoder_factory_cuda>(std::move(batch));
+}

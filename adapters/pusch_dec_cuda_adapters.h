@@ -30,6 +30,7 @@
 #include "srsran/phy/upper/channel_modulation/channel_modulation_factories.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_codeword_buffer.h"
 #include "srsran/phy/upper/channel_coding/ldpc/ldpc_segmenter_rx.h"
+#include "srsran/phy/upper/channel_processors/pusch/factories.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_buffer.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_notifier.h"
@@ -275,6 +276,10 @@ private:
   std::vector<log_likelihood_ratio>  view;
   std::optional<unsigned>            expected_softbits;
 };
+
+/// What a "cuda" choice in place of create_pusch_decoder_factory_sw / _hw (phy/upper/channel_processors/pusch/
+/// factories.h:56-99) returns: every create() yields a decoder bound to the given slot batch.
+std::shared_ptr<pusch_decoder_factory> create_pusch_decoder_factory_cuda(std::shared_ptr<pusch_decoder_batch_cuda> batch);
 
 std::shared_ptr<ldpc_decoder_factory>        create_ldpc_decoder_factory_cuda(std::shared_ptr<context> ctx);
 std::shared_ptr<ldpc_rate_dematcher_factory> create_ldpc_rate_dematcher_factory_cuda(std::shared_ptr<context> ctx);

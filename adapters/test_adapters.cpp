@@ -339,7 +339,9 @@ int main()
       std::unique_ptr<pusch_decoder_impl> sw;
       std::unique_ptr<pusch_decoder>      gpu;
     };
-    cuda::pusch_decoder_batch_cuda batch(ctx, 1, create_ldpc_segmenter_rx_factory_sw()->create());
+    auto batch_ptr = std::make_shared<cuda::pusch_decoder_batch_cuda>(ctx, 1, create_ldpc_segmenter_rx_factory_sw()->create());
+    cuda::pusch_decoder_batch_cuda& batch = *batch_ptr;
+    auto dec_factory = cuda::create_pusch_decoder_factory_cuda(batch_ptr);
     std::vector<ue_t>              ues(7);
     unsigned                       next_id = 1200;
     for (size_t u = 0; u != ues.size(); ++u) {
@@ -378,7 +380,7 @@ int main()
                                      crc_f->create(crc_generator_poly::CRC24B)};
       e.sw  = std::make_unique<pusch_decoder_impl>(create_ldpc_segmenter_rx_factory_sw()->create(), pool, std::move(c2),
                                                   nullptr, MAX_RB, 4);
-      e.gpu = batch.create();
+      e.gpu = dec_factory->create();
     }
     const int rvs[4]     = {0, 2, 3, 1};
     unsigned  slots_done = 0, tbs_compared = 0;

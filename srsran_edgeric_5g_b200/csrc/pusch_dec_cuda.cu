@@ -760,9 +760,17 @@ static int front_end_kernels(pdc_ctx* ctx, FrontEnd& fe, cudaStream_t s)
   const pdc::UlschArgs& a  = fe.args;
   const uint32_t        n_cw = fe.k_n_cw;
   if (fe.k_generate_seq) {
-    const uint32_t per_cta = 128 * pdc::PRG_WORDS_PER_THREAD;
-    dim3           grid(((fe.k_max_in + 31) / 32 + per_cta - 1) / per_cta, n_cw);
-    pdc::prg_kernel<<<grid, 128, 0, s>>>(a.cws, fe.d_seq);
+    // One polynomial jump per thread: few sequence words per thread while the batch cannot fill the GPU (the kernel is
+    // then bound by the latency of one thread's chain), more once it can (the jumps are then what costs).
+    const uint32_t words = (fe.k_max_in + 31) / 32;
+    const bool     small = (size_t)words * n_cw / pdc::PRG_WORDS_PER_THREAD < (size_t)256 * ctx->sm_count;
+    const uint32_t per_cta = 128 * (small ? pdc::PRG_WORDS_PER_THREAD_SMALL : pdc::PRG_WORDS_PER_THREAD);
+    dim3           grid((words + per_cta - 1) / per_cta, n_cw);
+    if (small) {
+      pdc::prg_kernel<pdc::PRG_WORDS_PER_THREAD_SMALL><<<grid, 128, 0, s>>>(a.cws, fe.d_seq);
+    } else {
+      pdc::prg_kernel<pdc::PRG_WORDS_PER_THREAD><<<grid, 128, 0, s>>>(a.cws, fe.d_seq);
+    }
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -1522,7 +1530,7 @@ int pdc_scrambling_sequence(pdc_ctx* ctx, uint32_t c_init, uint32_t offset, uint
   PDC_CUDA(grow_device(&fe.d_plan, &fe.plan_cap, sizeof(cw)));
   PDC_CUDA(cudaMemcpyAsync(fe.d_plan, &cw, sizeof(cw), cudaMemcpyHostToDevice, nullptr));
   const uint32_t per_cta = 128 * pdc::PRG_WORDS_PER_THREAD;
-  pdc::prg_kernel<<<dim3(((n + 31) / 32 + per_cta - 1) / per_cta, 1), 128>>>(
+  pdc::prg_kernel<pdc::PRG_WORDS_PER_THREAD><<<dim3(((n + 31) / 32 + per_cta - 1) / per_cta, 1), 128>>>(
       reinterpret_cast<const pdc::UlschCodeword*>(fe.d_plan), fe.d_seq);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;

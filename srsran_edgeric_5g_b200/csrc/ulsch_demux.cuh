@@ -23,7 +23,8 @@ namespace pdc {
 constexpr uint32_t PRG_NC    = 1600;
 constexpr uint32_t PRG_TAPS1 = 0x9u; // x1: x^31 + x^3 + 1
 constexpr uint32_t PRG_TAPS2 = 0xfu; // x2: x^31 + x^3 + x^2 + x + 1
-constexpr int      PRG_WORDS_PER_THREAD = 16;
+constexpr int      PRG_WORDS_PER_THREAD = 16; // large batches; small ones use PRG_WORDS_PER_THREAD_SMALL (latency bound)
+constexpr int      PRG_WORDS_PER_THREAD_SMALL = 4;
 
 // x^(c * 128^level) mod g of both generators, c < 128, level < 3 (sequence positions below 2^21).
 __device__ uint32_t g_prg_jump[2][3][128];
@@ -92,11 +93,12 @@ __device__ __forceinline__ uint32_t prg_step16(uint32_t& x1, uint32_t& x2)
 }
 
 // seq[cw.seq_word_off + j] = elements cw.prg_offset + 32 j .. + 31 of c(n) for cw.c_init, element k in bit k.
+template <int WPT>
 __global__ void __launch_bounds__(128) prg_kernel(const UlschCodeword* __restrict__ cws, uint32_t* __restrict__ seq)
 {
   const UlschCodeword& cw      = cws[blockIdx.y];
   const uint32_t       n_words = (cw.n_in + 31u) / 32u;
-  const uint32_t       w0      = (blockIdx.x * blockDim.x + threadIdx.x) * PRG_WORDS_PER_THREAD;
+  const uint32_t       w0      = (blockIdx.x * blockDim.x + threadIdx.x) * WPT;
   if (w0 >= n_words) {
     return;
   }
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(128) prg_kernel(const UlschCodeword* __restric
   uint32_t       x2 = prg_state_at(prg_xpow(1, n, PRG_TAPS2), prg_prefix(cw.c_init, PRG_TAPS2));
   uint32_t*      out = seq + cw.seq_word_off + w0;
 #pragma unroll
-  for (int k = 0; k != PRG_WORDS_PER_THREAD; ++k) {
+  for (int k = 0; k != WPT; ++k) {
     const uint32_t lo = prg_step16(x1, x2);
     const uint32_t hi = prg_step16(x1, x2);
     out[k]            = lo | (hi << 16);
