@@ -262,6 +262,8 @@ class Reference:
         L.ref_prg_bits.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, _vp]
         L.ref_ulsch_demux.restype = _c_int
         L.ref_ulsch_demux.argtypes = [_vp, _vp, _vp, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _vp, _vp]
+        L.ref_pusch_tbs.restype = None
+        L.ref_pusch_tbs.argtypes = [_c_int] * 7 + [_vp]
         L.ref_demodulate_soft.restype = None
         L.ref_demodulate_soft.argtypes = [_vp, _vp, _vp, ctypes.c_uint, _c_int]
         L.ref_pusch_create.restype = _vp
@@ -336,6 +338,14 @@ class Reference:
         bits = np.zeros(n, np.uint8)
         self.L.ref_prg_bits(c_init, offset, n, _ptr(bits))
         return bits
+
+    def pusch_tbs(self, table, mcs, nof_symb_sh, nof_dmrs_prb, nof_oh_prb, nof_layers, n_prb):
+        """(tbs bits, base graph, bits per symbol, target code rate x 1024) from the reference's pusch_mcs_get_config,
+        tbs_calculator_calculate and get_ldpc_base_graph. table: "qam64" / "qam256"."""
+        out = np.zeros(4, np.int32)
+        self.L.ref_pusch_tbs(0 if table == "qam64" else 1, mcs, nof_symb_sh, nof_dmrs_prb, nof_oh_prb, nof_layers, n_prb,
+                             _ptr(out))
+        return int(out[0]), int(out[1]), int(out[2]), out[3] / 2.0
 
     def demodulate_soft(self, symbols, noise_vars, mod):
         """demodulation_mapper_impl::demodulate_soft of the compiled reference (one call)."""

@@ -22,6 +22,9 @@
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_notifier.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_result.h"
 #include "srsran/phy/upper/unique_rx_buffer.h"
+#include "srsran/ran/pusch/pusch_mcs.h"
+#include "srsran/ran/sch/ldpc_base_graph.h"
+#include "srsran/ran/sch/tbs_calculator.h"
 #include "srsran/srsvec/bit.h"
 #include "srsran/support/cpu_features.h"
 #include <atomic>
@@ -564,6 +567,28 @@ void ref_prg_bits(unsigned c_init, unsigned offset, unsigned n, uint8_t* bits)
   for (unsigned i = 0; i != n; ++i) {
     bits[i] = seq.extract(i, 1);
   }
+}
+
+/// tbs_calculator_calculate (lib/ran/sch/tbs_calculator.cpp:166-188) for a PUSCH MCS (pusch_mcs_get_config, table 0 = qam64,
+/// 1 = qam256, no transform precoding) and get_ldpc_base_graph. out = {tbs bits, base graph (1 / 2), bits per symbol,
+/// target code rate x 1024 x 2}.
+void ref_pusch_tbs(int table, int mcs, int nof_symb_sh, int nof_dmrs_prb, int nof_oh_prb, int nof_layers, int n_prb, int* out)
+{
+  sch_mcs_description d =
+      pusch_mcs_get_config(table == 0 ? pusch_mcs_table::qam64 : pusch_mcs_table::qam256, sch_mcs_index(mcs), false);
+  tbs_calculator_configuration c = {};
+  c.nof_symb_sh                  = nof_symb_sh;
+  c.nof_dmrs_prb                 = nof_dmrs_prb;
+  c.nof_oh_prb                   = nof_oh_prb;
+  c.mcs_descr                    = d;
+  c.nof_layers                   = nof_layers;
+  c.tb_scaling_field             = 0;
+  c.n_prb                        = n_prb;
+  unsigned tbs                   = tbs_calculator_calculate(c);
+  out[0]                         = static_cast<int>(tbs);
+  out[1] = (get_ldpc_base_graph(d.get_normalised_target_code_rate(), units::bits(tbs)) == ldpc_base_graph_type::BG1) ? 1 : 2;
+  out[2] = static_cast<int>(get_bits_per_symbol(d.modulation));
+  out[3] = static_cast<int>(d.target_code_rate * 2.0F);
 }
 
 /// One demodulation_mapper::demodulate_soft call (include/srsran/phy/upper/channel_modulation/demodulation_mapper.h:62)

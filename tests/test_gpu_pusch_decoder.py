@@ -111,3 +111,39 @@ def test_config3_slot_273prb_256qam_4layers(ctx, orc):
     ue = dict(tb=rng.integers(0, 256, tb_bytes).astype(np.uint8), bg=1, qm=8, nl=4, n_llr=n_llr, nref=nref, snr=7.9)
     done = _run_tb_sequence(ctx, orc, pool, batch, [ue], [0, 2, 3, 1], 6, True, rng, fill=3)
     assert done[0]
+
+
+@pytest.mark.parametrize("bw_prb,table", [(52, "qam64"), (106, "qam64"), (106, "qam256")])
+def test_config5_edgeric_multi_ue_slots(ctx, orc, bw_prb, table):
+    """BASELINE config 5 (5G/configs/zmq-mode-multi-ue.yml: 10 MHz = 52 PRB, 20 MHz = 106 PRB at 15 kHz, one layer, 2-4
+    UEs sharing the carrier): transport block sizes from the MCS tables and TS 38.214 5.1.3.2 (sch.py), base graph by
+    TS 38.212 6.2.2, 1-7 codeblocks per UE, BG1 / BG2 mix, all UEs of a slot in ONE batch, HARQ over rv 0-2-3-1, gNB-style
+    limited buffer. Every result, CRC flag and HARQ soft bit against the oracle."""
+    from srsran_edgeric_5g_b200 import sch
+    rng = np.random.default_rng(500 + bw_prb + len(table))
+    pool = rx_buffer_pool(ctx, first_entry=1536, nof_entries=512)
+    batch = PuschDecoderBatch(ctx)
+    seen_bg, seen_cb = set(), set()
+    for slot in range(6):
+        n_ue = int(rng.integers(2, 5))
+        cuts = np.sort(rng.choice(np.arange(1, bw_prb), n_ue - 1, replace=False))
+        shares = np.diff(np.concatenate([[0], cuts, [bw_prb]]))
+        ues = []
+        for n_prb in shares:
+            n_mcs = len(sch.MCS_TABLE_QAM64 if table == "qam64" else sch.MCS_TABLE_QAM256)
+            a = sch.pusch_allocation(table, int(rng.integers(0, n_mcs)), int(n_prb), nof_dmrs_symbols=int(rng.integers(1, 4)))
+            C = compute_nof_codeblocks(a["tbs_bits"], a["base_graph"])
+            nref = compute_N_ref(a["tbs_bits"] // 8, C)  # TBS_LBRM of the UE = this transport block
+            # per-soft-bit SNR around the decoding threshold of the code rate, so that some UEs need retransmissions
+            snr = (8 if a["base_graph"] == 1 else 3) * a["rate"] / 0.8 + rng.uniform(-4, 0)
+            ues.append(dict(tb=rng.integers(0, 256, a["tbs_bits"] // 8).astype(np.uint8), bg=a["base_graph"], qm=a["qm"],
+                            nl=1, n_llr=a["n_llr"], nref=nref, snr=float(snr)))
+            seen_bg.add(a["base_graph"])
+            seen_cb.add(C)
+        _run_tb_sequence(ctx, orc, pool, batch, ues, [0, 2, 3, 1], 6, True, rng, fill=0)
+        for i in range(len(ues)):  # end of the HARQ processes: hand the entries back
+            b = pool._buffers.get(("ue", i))
+            if b is not None:
+                b.release()
+    assert seen_bg == {1, 2} or bw_prb == 106
+    assert max(seen_cb) >= 2

@@ -160,3 +160,44 @@ def test_ulsch_plan_rejects_inconsistent_descriptions():
     assert L.plan_demux_cpu(d.ctypes.data_as(vp), *args) == -1
     d[0]["qm"] = 3                                                          # not a modulation order
     assert L.plan_demux_cpu(d.ctypes.data_as(vp), *args) == -1
+
+
+def test_tbs_and_base_graph_known_answers():
+    """TS 38.214 5.1.3.2 / TS 38.212 6.2.2 through sch.py: the largest NR transport block (what BASELINE config 3 decodes:
+    273 PRB, 4 layers, 256QAM MCS 27 -> 1 277 992 bits = MAX_TBS, ldpc_segmenter_impl.cpp:38) and the table end points."""
+    from srsran_edgeric_5g_b200 import sch
+    a = sch.pusch_allocation("qam256", 27, 273, nof_layers=4)
+    assert a["tbs_bits"] == 1277992 and a["base_graph"] == 1 and a["n_llr"] == 1362816 and a["qm"] == 8
+    assert sch.tbs_calculate(14, 12, 0, 2, 120, 1, 1) == 32          # one PRB at the lowest MCS
+    assert sch.get_ldpc_base_graph(0.9, 292) == 2 and sch.get_ldpc_base_graph(0.9, 296) == 1
+    assert sch.get_ldpc_base_graph(0.67, 3824) == 2 and sch.get_ldpc_base_graph(0.68, 3824) == 1
+    assert sch.get_ldpc_base_graph(0.25, 100000) == 2 and sch.get_ldpc_base_graph(0.26, 100000) == 1
+    # every size is byte aligned and above 3824 bits leaves equal codeblocks (step 4 of the procedure)
+    for mcs in range(29):
+        for nprb in (1, 6, 25, 52, 106, 273):
+            t = sch.pusch_allocation("qam64", mcs, nprb)["tbs_bits"]
+            assert t % 8 == 0 and t >= 24
+            if t > 3824:
+                C = ldpc.compute_nof_codeblocks(t, sch.pusch_allocation("qam64", mcs, nprb)["base_graph"])
+                assert (t + 24) % C == 0
+
+
+def test_tbs_matches_the_reference(ref_available):
+    """sch.py against pusch_mcs_get_config + tbs_calculator_calculate + get_ldpc_base_graph of the compiled reference."""
+    if not ref_available:
+        pytest.skip("compiled reference not present")
+    from oracle import pyoracle as po
+    from srsran_edgeric_5g_b200 import sch
+    ref = po.Reference()
+    n = 0
+    for table, T in (("qam64", sch.MCS_TABLE_QAM64), ("qam256", sch.MCS_TABLE_QAM256)):
+        for mcs in range(len(T)):
+            for nprb in (1, 2, 3, 5, 11, 24, 25, 26, 51, 52, 53, 79, 106, 133, 217, 273):
+                for nsym, dmrs in ((14, 12), (14, 36), (12, 24), (7, 6)):
+                    for nl in (1, 2, 4):
+                        qm, r1024 = sch.pusch_mcs_get_config(table, mcs)
+                        tbs = sch.tbs_calculate(nsym, dmrs, 0, qm, r1024, nl, nprb)
+                        got = (tbs, sch.get_ldpc_base_graph(r1024 / 1024.0, tbs), qm, float(r1024))
+                        assert got == ref.pusch_tbs(table, mcs, nsym, dmrs, 0, nl, nprb), (table, mcs, nprb, nsym, nl)
+                        n += 1
+    assert n > 10000
