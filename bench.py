@@ -566,6 +566,103 @@ def symbol_legs(ctx, orc, capi, torch, stream, args):
     return out
 
 
+def config5_leg(ctx, orc, capi, torch, stream, args):
+    """BASELINE config 5 (EdgeRIC zmq-mode multi-UE cell: 20 MHz = 106 PRB at 15 kHz, one layer, four UEs sharing the
+    carrier at 64QAM MCS 20, transport block sizes by TS 38.214): one slot = 4 transport blocks of 2 codeblocks. A batch
+    this small is pure latency: reported device resident, end to end from host buffers (p50 / p99 of single slots), and
+    beside the reference's own pusch_decoder_impl (one thread, AVX2/AVX512 as "auto" picks) on the same soft bits."""
+    from oracle.pyoracle import Reference, ReferencePusch
+    from srsran_edgeric_5g_b200 import ldpc, sch
+    from tests.vectors import make_tb_llrs
+    rng = np.random.default_rng(55)
+    shares, mcs = [27, 27, 26, 26], 20
+    cbs_l, tbd_l, llr_l, tbs_l = [], [], [], []
+    llr_off = cb_off = tb_off = 0
+    flags = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA | capi.CB_EARLY_STOP
+    ues = []
+    for u, n_prb in enumerate(shares):
+        a = sch.pusch_allocation("qam64", mcs, n_prb)
+        C = ldpc.compute_nof_codeblocks(a["tbs_bits"], a["base_graph"])
+        nref = ldpc.compute_N_ref(a["tbs_bits"] // 8, C)
+        tb = rng.integers(0, 256, a["tbs_bits"] // 8).astype(np.uint8)
+        llrs, _ = make_tb_llrs(orc, tb, a["base_graph"], 0, a["qm"], nref, 1, a["n_llr"], 6.5, rng)
+        crc_kind = capi.CRC24B if C > 1 else (capi.CRC24A if a["tbs_bits"] > 3824 else capi.CRC16)
+        for m in ldpc.segment_rx(a["tbs_bits"], a["base_graph"], 0, a["qm"], nref, 1, a["n_llr"]):
+            cbs_l.append((llr_off + m.cw_offset, m.rm_length, cb_off, nref, m.lifting_size, m.nof_filler_bits,
+                          a["base_graph"], a["qm"], 0, crc_kind, MAX_ITER, flags, u))
+            cb_off += 1
+        tbd_l.append((cb_off - C, C, a["tbs_bits"], tb_off, 0))
+        tb_off += (a["tbs_bits"] + 24 + 31) // 32 * 4
+        llr_off += llrs.size
+        llr_l.append(llrs)
+        tbs_l.append(tb)
+        ues.append(dict(a, nref=nref, C=C))
+    cbs = np.array(cbs_l, capi.CB_DESC_DTYPE)
+    tbd = np.array(tbd_l, capi.TB_DESC_DTYPE)
+    llr_all = np.concatenate(llr_l)
+    n_cb, n_tb, info_bits = cbs.size, tbd.size, sum(u["tbs_bits"] for u in ues)
+    d_cbs = torch.from_numpy(cbs.view(np.uint8)).cuda()
+    d_tbs = torch.from_numpy(tbd.view(np.uint8)).cuda()
+    d_llr = torch.from_numpy(llr_all).cuda()
+    d_res = torch.zeros(n_cb * 4, dtype=torch.uint8, device="cuda")
+    d_bits = torch.zeros(n_cb * capi.PDC_MAX_CB_BYTES, dtype=torch.uint8, device="cuda")
+    d_tres = torch.zeros(n_tb * 4, dtype=torch.uint8, device="cuda")
+    d_tb = torch.zeros(tb_off + 16, dtype=torch.uint8, device="cuda")
+    max_z = int(cbs["lifting_size"].max())
+
+    def step():
+        ctx.launch_device(d_cbs.data_ptr(), n_cb, d_llr.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), max_z, flags,
+                          bool((cbs["base_graph"] == 1).any()), cuda_stream=stream.cuda_stream, d_tbs=d_tbs.data_ptr(),
+                          n_tb=n_tb, d_tb_results=d_tres.data_ptr(), d_tb_bytes=d_tb.data_ptr())
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    e0.record(stream)
+    for _ in range(reps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    res = d_res.cpu().numpy().view(capi.CB_RESULT_DTYPE)
+    tb_ok = bool(d_tres.cpu().numpy().view(capi.TB_RESULT_DTYPE)["tb_crc_ok"].all())
+    # end to end, one slot at a time, host buffers
+    ctx5 = capi.Context(device=torch.cuda.current_device(), max_cbs=n_cb, max_llrs=llr_all.size + 64, harq_entries=n_cb,
+                        max_tbs=n_tb, max_tb_bytes=tb_off + 64, nof_streams=1)
+    pin = capi.PinnedBuffer(llr_all.size)
+    pin.array[:] = llr_all
+    tb_pin = capi.PinnedBuffer(tb_off + 64, np.uint8)
+    lat = np.zeros(1000)
+    for i in range(1020):
+        t0 = time.perf_counter()
+        ctx5.submit(cbs, pin.array, tbd, stream=0, want_bits=False, out_tb=tb_pin.array)
+        out = ctx5.wait(0)
+        if i >= 20:
+            lat[i - 20] = (time.perf_counter() - t0) * 1e6
+    match = all(bool((out["tb_bytes"][int(t["out_offset"]):int(t["out_offset"]) + tb.size] == tb).all())
+                for t, tb in zip(tbd, tbs_l))
+    ctx5.close()
+    leg = {"us_per_slot": us, "value": info_bits / (us * 1e-6) / 1e9, "unit": UNIT, "ues": len(shares), "prb": sum(shares),
+           "mcs": mcs, "codeblocks": int(n_cb), "tbs_bits": [int(u["tbs_bits"]) for u in ues],
+           "lifting_sizes": sorted(set(int(z) for z in cbs["lifting_size"])), "mean_iters": float(res["iters"].mean()),
+           "tb_crc_ok": tb_ok, "tb_bytes_match": match,
+           "latency_us_host_buffers": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                                       "slots": 1000, "path": "pdc_submit + pdc_wait"}}
+    if Reference.available():
+        # the reference's own software decoder on the same slot, one thread (what a zmq-mode gNB spends per slot)
+        t_ref = []
+        rps = [ReferencePusch(u["C"]) for u in ues]
+        for rep in range(6):
+            t0 = time.perf_counter()
+            for rp, u, llrs, tb in zip(rps, ues, llr_l, tbs_l):
+                rp.decode(llrs, tb.size, u["base_graph"], 0, u["qm"], u["nref"], 1, MAX_ITER, True, True, reset_crcs=True)
+            t_ref.append((time.perf_counter() - t0) * 1e6)
+        leg["reference_pusch_decoder_impl_us_per_slot"] = float(min(t_ref))
+    return {"config5_zmq_20mhz_4ue_slot": leg}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -575,7 +672,8 @@ def main():
     ap.add_argument("--n-cb", type=int, default=8192, help="codeblocks per GPU per step")
     ap.add_argument("--snr", type=float, default=-1.0, help="AWGN SNR (dB) of the synthetic LLRs")
     ap.add_argument("--no-extras", action="store_true", help="skip the early-stop / config-3 / cpu legs")
-    ap.add_argument("--only-slots", action="store_true", help="profiling aid: run only the config-3/4 slot legs")
+    ap.add_argument("--only-slots", action="store_true", help="profiling aid: run only the config-3/4/5 slot legs")
+    ap.add_argument("--only-config5", action="store_true", help="profiling aid: run only the config-5 slot leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
 
@@ -600,11 +698,18 @@ def main():
     from srsran_edgeric_5g_b200 import capi
 
     orc = Oracle()
+    if args.only_config5:
+        ctx2 = capi.Context(device=local_rank, max_cbs=64, max_llrs=1 << 20, harq_entries=64, max_tbs=16,
+                            max_tb_bytes=1 << 20, nof_streams=1)
+        print(json.dumps(config5_leg(ctx2, orc, capi, torch, torch.cuda.current_stream(), args)))
+        ctx2.close()
+        return
     if args.only_slots:
         ctx2 = capi.Context(device=local_rank, max_cbs=2432, max_llrs=1 << 20, harq_entries=2432, max_tbs=16,
                             max_tb_bytes=16 * 160000, nof_streams=1)
         legs = slot_legs(ctx2, orc, capi, torch, torch.cuda.current_stream(), args)
         legs.update(symbol_legs(ctx2, orc, capi, torch, torch.cuda.current_stream(), args))
+        legs.update(config5_leg(ctx2, orc, capi, torch, torch.cuda.current_stream(), args))
         print(json.dumps(legs))
         ctx2.close()
         return
@@ -797,6 +902,7 @@ def main():
                                 max_tb_bytes=16 * 160000, nof_streams=1)
             line["extra"].update(slot_legs(ctx2, orc, capi, torch, stream, args))
             line["extra"].update(symbol_legs(ctx2, orc, capi, torch, stream, args))
+            line["extra"].update(config5_leg(ctx2, orc, capi, torch, stream, args))
             ctx2.close()
             # ---- CPU baseline: the reference's own SIMD code on the host cores, bounded sample ---------------------------
             line["cpu_baseline"] = cpu_reference_rate(llrs_np[:2048], False, 12.0, os.cpu_count() or 1)
