@@ -19,6 +19,8 @@
  *                                         include/srsran/phy/upper/channel_processors/pusch/ulsch_demultiplex.h:41-103,
  *                                         include/srsran/phy/upper/channel_processors/pusch/pusch_codeword_buffer.h
  *   pseudo_random_generator::generate     include/srsran/phy/upper/sequence_generators/pseudo_random_generator.h
+ *   ldpc_encoder::encode                  include/srsran/phy/upper/channel_coding/ldpc/ldpc_encoder.h:37-38 (downlink twin)
+ *   ldpc_rate_matcher::rate_match         include/srsran/phy/upper/channel_coding/ldpc/ldpc_rate_matcher.h:37
  *   demodulation_mapper::demodulate_soft  include/srsran/phy/upper/channel_modulation/demodulation_mapper.h:62-65
  *                                         (factory: channel_modulation_factories.h:32-41)
  *
@@ -190,6 +192,23 @@ typedef struct {
   uint32_t llr_offset; /* first soft bit of the call in the output                                                     */
   uint32_t modulation; /* PDC_MOD_*                                                                                    */
 } pdc_demod_call;
+
+/*
+ * Downlink twin: one codeblock to encode and rate match. Carries the fields of codeblock_metadata
+ * (include/srsran/phy/upper/codeblock_metadata.h:42-80) the encoder and the rate matcher read.
+ */
+typedef struct {
+  uint32_t msg_offset;   /* byte offset of the codeblock's K message bits (packed MSB first, filler bits as zeros)      */
+  uint32_t out_offset;   /* where its rate-matched bits start in the output (one bit per byte)                          */
+  uint32_t rm_length;    /* E: number of rate-matched bits (multiple of qm)                                             */
+  uint32_t nref;         /* limited-buffer length N_ref, 0 = unlimited                                                  */
+  uint16_t lifting_size; /* Z                                                                                           */
+  uint16_t nof_filler;   /* F                                                                                           */
+  uint8_t  base_graph;   /* 1 or 2                                                                                      */
+  uint8_t  qm;           /* bits per symbol of the bit interleaver: 1, 2, 4, 6, 8                                       */
+  uint8_t  rv;           /* redundancy version 0..3                                                                     */
+  uint8_t  reserved;
+} pdc_enc_desc;
 
 typedef struct {
   int32_t  device;          /* CUDA device ordinal                                                                     */
@@ -430,6 +449,35 @@ int pdc_launch_demod_device(pdc_ctx*              ctx,
 int pdc_scrambling_sequence(pdc_ctx* ctx, uint32_t c_init, uint32_t offset, uint32_t n, uint8_t* packed);
 
 int pdc_crc(pdc_ctx* ctx, int crc_kind, const uint8_t* packed, uint32_t nbits, uint32_t* checksum);
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Downlink twin: LDPC encoding + rate matching (ldpc_encoder::encode followed by ldpc_rate_matcher::rate_match, as     */
+/* pdsch_encoder_impl.cpp:52-70 chains them for every codeblock), one kernel for a batch of codeblocks.                 */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+/*
+ * Synchronous, host buffers: msgs = the codeblocks' message bits (packed), out = the rate-matched bits of all codeblocks,
+ * one bit per byte, each codeblock at its out_offset (concatenating them gives the codeword the modulator consumes).
+ */
+int pdc_encode(pdc_ctx*            ctx,
+               const pdc_enc_desc* cbs,
+               uint32_t            n_cb,
+               const uint8_t*      msgs,
+               size_t              msg_bytes,
+               uint8_t*            out,
+               size_t              out_capacity);
+/* Device-resident variant on the caller's CUDA stream (descriptors on the device too; the caller vouches for them). */
+int pdc_launch_encode_device(pdc_ctx*    ctx,
+                             const void* d_cbs,
+                             uint32_t    n_cb,
+                             const void* d_msgs,
+                             void*       d_out,
+                             size_t      out_capacity,
+                             uint32_t    max_lifting_size,
+                             int         any_bg1,
+                             void*       cuda_stream);
+/* ldpc_encoder::encode alone: K message bits (packed) -> the N = 66 Z or 50 Z bits of the codeblock, one bit per byte. */
+int pdc_ldpc_encode(pdc_ctx* ctx, int base_graph, int lifting_size, const uint8_t* msg_packed, uint8_t* codeblock_bits);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,10 @@ CW_PLAIN_BPSK = 16
 # soft demapper: modulation codes (bits per symbol, 0 = pi/2-BPSK), reference build reproduced, pdc_demod_call
 MOD_PI_2_BPSK, MOD_BPSK, MOD_QPSK, MOD_QAM16, MOD_QAM64, MOD_QAM256 = 0, 1, 2, 4, 6, 8
 DEMOD_X86, DEMOD_SCALAR = 0, 1
+# pdc_enc_desc (downlink twin: LDPC encoding + rate matching)
+ENC_DESC_DTYPE = np.dtype([("msg_offset", "<u4"), ("out_offset", "<u4"), ("rm_length", "<u4"), ("nref", "<u4"),
+                           ("lifting_size", "<u2"), ("nof_filler", "<u2"), ("base_graph", "u1"), ("qm", "u1"),
+                           ("rv", "u1"), ("reserved", "u1")])
 DEMOD_CALL_DTYPE = np.dtype([("sym_offset", "<u4"), ("n_sym", "<u4"), ("llr_offset", "<u4"), ("modulation", "<u4")])
 # pdc_cw_desc / pdc_cw_result (codeword front end)
 CW_DESC_DTYPE = np.dtype([("in_offset", "<u4"), ("sch_offset", "<u4"), ("uci_offset", "<u4"), ("c_init", "<u4"),
@@ -71,7 +75,7 @@ CW_DESC_DTYPE = np.dtype([("in_offset", "<u4"), ("sch_offset", "<u4"), ("uci_off
                           ("nof_csi_part1_bits", "<u4"), ("nof_enc_csi_part1_bits", "<u4"),
                           ("nof_csi_part2_bits", "<u4"), ("nof_enc_csi_part2_bits", "<u4")])
 CW_RESULT_DTYPE = np.dtype([("n_sch", "<u4"), ("n_harq_ack", "<u4"), ("n_csi_part1", "<u4"), ("n_csi_part2", "<u4")])
-assert CW_DESC_DTYPE.itemsize == 60 and CW_RESULT_DTYPE.itemsize == 16
+assert CW_DESC_DTYPE.itemsize == 60 and CW_RESULT_DTYPE.itemsize == 16 and ENC_DESC_DTYPE.itemsize == 24
 assert CB_DESC_DTYPE.itemsize == ctypes.sizeof(CbDesc) == 28
 assert TB_DESC_DTYPE.itemsize == ctypes.sizeof(TbDesc) == 20
 
@@ -79,7 +83,8 @@ EXPORTS = ["pdc_default_config", "pdc_create", "pdc_destroy", "pdc_last_error", 
            "pdc_measure_int_peak", "pdc_host_alloc", "pdc_host_free", "pdc_submit", "pdc_wait", "pdc_poll", "pdc_launch_device",
            "pdc_harq_read", "pdc_harq_write", "pdc_harq_free", "pdc_harq_device_ptr", "pdc_ldpc_decode",
            "pdc_rate_dematch", "pdc_crc", "pdc_submit_codewords", "pdc_ulsch_demux", "pdc_scrambling_sequence",
-           "pdc_launch_codewords_device", "pdc_submit_symbols", "pdc_demodulate_soft", "pdc_launch_demod_device"]
+           "pdc_launch_codewords_device", "pdc_submit_symbols", "pdc_demodulate_soft", "pdc_launch_demod_device",
+           "pdc_encode", "pdc_launch_encode_device", "pdc_ldpc_encode"]
 
 _lib = None
 
@@ -138,6 +143,9 @@ def load():
     L.pdc_submit_symbols.argtypes = [_vp, _u32, _vp, _u32, _vp, _vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp]
     L.pdc_demodulate_soft.argtypes = [_vp, _vp, _vp, _vp, _u32, ctypes.c_int]
     L.pdc_launch_demod_device.argtypes = [_vp, _vp, _u32, _vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp]
+    L.pdc_encode.argtypes = [_vp, _vp, _u32, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t]
+    L.pdc_launch_encode_device.argtypes = [_vp, _vp, _u32, _vp, _vp, ctypes.c_size_t, _u32, ctypes.c_int, _vp]
+    L.pdc_ldpc_encode.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp]
     _lib = L
     return L
 
@@ -385,6 +393,30 @@ class Context:
         check(self._L.pdc_rate_dematch(self.h, _ptr(buffer), buffer.size, _ptr(llrs), llrs.size, int(new_data), rv, qm,
                                        nref, nof_filler))
         return buffer
+
+    # -- downlink twin ------------------------------------------------------------------------------------------------
+    def encode(self, cbs, msgs_packed, out_capacity=None):
+        """pdc_encode: LDPC encoding + rate matching of a batch of codeblocks. cbs: ENC_DESC_DTYPE array; msgs_packed: the
+        message bits (packed, each codeblock at its msg_offset). Returns the rate-matched bits, one per byte."""
+        cbs = np.ascontiguousarray(cbs, ENC_DESC_DTYPE)
+        msgs_packed = np.ascontiguousarray(msgs_packed, np.uint8)
+        if out_capacity is None:
+            out_capacity = int((cbs["out_offset"].astype(np.int64) + cbs["rm_length"]).max())
+        out = np.zeros(out_capacity, np.uint8)
+        check(self._L.pdc_encode(self.h, _ptr(cbs), cbs.size, _ptr(msgs_packed), msgs_packed.size, _ptr(out), out.size))
+        return out
+
+    def launch_encode_device(self, d_cbs, n_cb, d_msgs, d_out, out_capacity, max_lifting_size, any_bg1, cuda_stream=0):
+        check(self._L.pdc_launch_encode_device(self.h, d_cbs, n_cb, d_msgs, d_out, out_capacity, max_lifting_size,
+                                               int(any_bg1), cuda_stream or None))
+
+    def ldpc_encode(self, bg, Z, msg_bits):
+        """pdc_ldpc_encode: ldpc_encoder::encode of one codeblock. msg_bits: K bits (one per element). Returns the
+        N = 66 Z / 50 Z codeblock bits, one per byte."""
+        packed = np.packbits(np.ascontiguousarray(msg_bits, np.uint8))
+        out = np.zeros((66 if bg == 1 else 50) * Z, np.uint8)
+        check(self._L.pdc_ldpc_encode(self.h, bg, Z, _ptr(packed), _ptr(out)))
+        return out
 
     def crc(self, crc_kind, packed, nbits):
         packed = np.ascontiguousarray(packed, np.uint8)

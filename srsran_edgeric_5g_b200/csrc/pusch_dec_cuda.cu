@@ -9,6 +9,7 @@
 #include "tb_assemble.cuh"
 #include "ulsch_demux.cuh"
 #include "demod.cuh"
+#include "ldpc_encode.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -152,6 +153,13 @@ struct pdc_ctx {
   };
   std::vector<DecodeScratch> decode_scratch;
   FrontEnd             fe_sync;                   // buffers of the synchronous front-end calls
+  // Downlink twin (synchronous calls): grow-only device staging.
+  unsigned char*       d_enc_cbs = nullptr;
+  size_t               enc_cbs_cap = 0;
+  unsigned char*       d_enc_msgs = nullptr;
+  size_t               enc_msgs_cap = 0;
+  unsigned char*       d_enc_out = nullptr;
+  size_t               enc_out_cap = 0;
   int8_t*              d_sch_sync = nullptr;
   size_t               sch_sync_cap = 0;
 };
@@ -583,6 +591,9 @@ void pdc_destroy(pdc_ctx* ctx)
   cudaFree(ctx->d_tb_sync);
   cudaFree(ctx->d_scratch_llr);
   cudaFree(ctx->d_demod_tables);
+  cudaFree(ctx->d_enc_cbs);
+  cudaFree(ctx->d_enc_msgs);
+  cudaFree(ctx->d_enc_out);
   for (pdc_ctx::DecodeScratch& c : ctx->decode_scratch) {
     cudaFree(c.d_state);
     cudaFree(c.d_counter);
@@ -1571,3 +1582,140 @@ int pdc_crc(pdc_ctx* ctx, int crc_kind, const uint8_t* packed, uint32_t nbits, u
 }
 
 } // extern "C"
+
+// ---- downlink twin: LDPC encoding + rate matching ------------------------------------------------------------------
+
+static int launch_encode(pdc_ctx* ctx, const pdc::EncodeParams& p, int max_Z, bool any_bg1, int mode, cudaStream_t s)
+{
+  const size_t  smem = pdc::enc_smem_bytes(any_bg1 ? 1 : 2, max_Z);
+  static size_t configured = 0;
+  if (smem > configured && smem > 48 * 1024) {
+    PDC_CUDA(cudaFuncSetAttribute(pdc::ldpc_encode_rm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int threads = std::min(pdc::ENC_MAX_THREADS, ((max_Z + 31) / 32) * 32);
+  pdc::ldpc_encode_rm_kernel<<<p.n_cb, threads, smem, s>>>(p, mode);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return PDC_OK;
+}
+
+static bool enc_desc_valid(const pdc_enc_desc& d, int mode, size_t msg_bytes, size_t out_capacity)
+{
+  const int bg = d.base_graph, Z = d.lifting_size;
+  if ((bg != 1 && bg != 2) || Z < 2 || Z > pdc::MAX_Z || pdc::host_tables().set_index[Z] == 0xff) {
+    return false;
+  }
+  const int kb = (bg == 1) ? 22 : 10, N = ((bg == 1) ? 66 : 50) * Z, K = kb * Z, K_sys = (kb - 2) * Z;
+  if ((size_t)d.msg_offset + (size_t)(K + 7) / 8 > msg_bytes || d.nof_filler >= K || d.rv > 3) {
+    return false;
+  }
+  if (mode == 1) {
+    return (size_t)d.out_offset + (size_t)N <= out_capacity;
+  }
+  const int qm  = d.qm;
+  const int Ncb = (d.nref > 0) ? std::min<int>((int)d.nref, N) : N;
+  if (!(qm == 1 || qm == 2 || qm == 4 || qm == 6 || qm == 8) || d.rm_length % qm != 0 ||
+      (size_t)d.out_offset + d.rm_length > out_capacity) {
+    return false;
+  }
+  // A circular buffer that ends inside or before the filler bits is not a configuration the standard produces.
+  return !(d.nof_filler != 0 && Ncb < K_sys) && Ncb > (int)d.nof_filler;
+}
+
+static int encode_sync(pdc_ctx*            ctx,
+                       const pdc_enc_desc* cbs,
+                       uint32_t            n_cb,
+                       const uint8_t*      msgs,
+                       size_t              msg_bytes,
+                       uint8_t*            out,
+                       size_t              out_capacity,
+                       int                 mode)
+{
+  int  max_Z = 0;
+  bool any_bg1 = false;
+  for (uint32_t i = 0; i != n_cb; ++i) {
+    if (!enc_desc_valid(cbs[i], mode, msg_bytes, out_capacity)) {
+      return fail(PDC_ERR_INVALID, "pdc_encode: invalid codeblock descriptor");
+    }
+    max_Z   = std::max<int>(max_Z, cbs[i].lifting_size);
+    any_bg1 = any_bg1 || cbs[i].base_graph == 1;
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  PDC_CUDA(grow_device(&ctx->d_enc_cbs, &ctx->enc_cbs_cap, sizeof(pdc_enc_desc) * n_cb));
+  PDC_CUDA(grow_device(&ctx->d_enc_msgs, &ctx->enc_msgs_cap, msg_bytes + 16));
+  PDC_CUDA(grow_device(&ctx->d_enc_out, &ctx->enc_out_cap, out_capacity + 16));
+  PDC_CUDA(cudaMemcpyAsync(ctx->d_enc_cbs, cbs, sizeof(pdc_enc_desc) * n_cb, cudaMemcpyHostToDevice, nullptr));
+  PDC_CUDA(cudaMemcpyAsync(ctx->d_enc_msgs, msgs, msg_bytes, cudaMemcpyHostToDevice, nullptr));
+  pdc::EncodeParams p;
+  p.cbs          = reinterpret_cast<const pdc_enc_desc*>(ctx->d_enc_cbs);
+  p.n_cb         = n_cb;
+  p.msgs         = ctx->d_enc_msgs;
+  p.out          = ctx->d_enc_out;
+  p.out_capacity = (uint32_t)out_capacity;
+  int rc = launch_encode(ctx, p, max_Z, any_bg1, mode, nullptr);
+  if (rc != PDC_OK) {
+    return rc;
+  }
+  // Only the codeblocks' own ranges are written back.
+  for (uint32_t i = 0; i != n_cb; ++i) {
+    const size_t n = (mode == 1) ? (size_t)((cbs[i].base_graph == 1) ? 66 : 50) * cbs[i].lifting_size : cbs[i].rm_length;
+    if (n != 0) {
+      PDC_CUDA(cudaMemcpyAsync(out + cbs[i].out_offset, ctx->d_enc_out + cbs[i].out_offset, n, cudaMemcpyDeviceToHost,
+                               nullptr));
+    }
+  }
+  PDC_CUDA(cudaStreamSynchronize(nullptr));
+  return PDC_OK;
+}
+
+int pdc_encode(pdc_ctx*            ctx,
+               const pdc_enc_desc* cbs,
+               uint32_t            n_cb,
+               const uint8_t*      msgs,
+               size_t              msg_bytes,
+               uint8_t*            out,
+               size_t              out_capacity)
+{
+  if (!ctx || !cbs || n_cb == 0 || !msgs || !out || out_capacity > 0xfffffff0u) {
+    return fail(PDC_ERR_INVALID, "pdc_encode: invalid argument");
+  }
+  return encode_sync(ctx, cbs, n_cb, msgs, msg_bytes, out, out_capacity, 0);
+}
+
+int pdc_ldpc_encode(pdc_ctx* ctx, int base_graph, int lifting_size, const uint8_t* msg_packed, uint8_t* codeblock_bits)
+{
+  if (!ctx || !msg_packed || !codeblock_bits || (base_graph != 1 && base_graph != 2) || lifting_size < 2 ||
+      lifting_size > pdc::MAX_Z) {
+    return fail(PDC_ERR_INVALID, "pdc_ldpc_encode: invalid argument");
+  }
+  pdc_enc_desc d = {};
+  d.base_graph   = (uint8_t)base_graph;
+  d.lifting_size = (uint16_t)lifting_size;
+  d.qm           = 1;
+  const size_t K = (size_t)((base_graph == 1) ? 22 : 10) * lifting_size, N = (size_t)((base_graph == 1) ? 66 : 50) * lifting_size;
+  return encode_sync(ctx, &d, 1, msg_packed, (K + 7) / 8, codeblock_bits, N, 1);
+}
+
+int pdc_launch_encode_device(pdc_ctx*    ctx,
+                             const void* d_cbs,
+                             uint32_t    n_cb,
+                             const void* d_msgs,
+                             void*       d_out,
+                             size_t      out_capacity,
+                             uint32_t    max_lifting_size,
+                             int         any_bg1,
+                             void*       cuda_stream)
+{
+  if (!ctx || !d_cbs || n_cb == 0 || !d_msgs || !d_out || max_lifting_size < 2 || max_lifting_size > (uint32_t)pdc::MAX_Z) {
+    return fail(PDC_ERR_INVALID, "pdc_launch_encode_device: invalid argument");
+  }
+  PDC_CUDA(cudaSetDevice(ctx->cfg.device));
+  pdc::EncodeParams p;
+  p.cbs          = static_cast<const pdc_enc_desc*>(d_cbs);
+  p.n_cb         = n_cb;
+  p.msgs         = static_cast<const uint8_t*>(d_msgs);
+  p.out          = static_cast<uint8_t*>(d_out);
+  p.out_capacity = (uint32_t)out_capacity;
+  return launch_encode(ctx, p, (int)max_lifting_size, any_bg1 != 0, 0, static_cast<cudaStream_t>(cuda_stream));
+}

@@ -87,3 +87,34 @@ def segment_rx(tbs_bits, base_graph, rv, mod, Nref, nof_layers, nof_cw_llrs):
         offset += rm
     assert offset == nof_cw_llrs
     return out
+
+
+def segment_tx(ctx, transport_block, base_graph):
+    """ldpc_segmenter_tx::segment (lib/phy/upper/channel_coding/ldpc/ldpc_segmenter_tx_impl.cpp; TS 38.212 5.2.2, 7.2.3):
+    transport-block CRC attachment, segmentation, codeblock CRC attachment and filler bits. Returns one array of K bits
+    per codeblock (filler bits as zeros: the rate matcher skips them by position). CRCs come from the device's CRC
+    calculator (ctx.crc = pdc_crc)."""
+    import numpy as np
+    from . import capi
+    tb = np.ascontiguousarray(transport_block, np.uint8)
+    tbs_bits = tb.size * 8
+    tcrc = compute_tb_crc_size(tbs_bits)
+    chk = ctx.crc(capi.CRC16 if tcrc == 16 else capi.CRC24A, tb, tbs_bits)
+    bits = np.concatenate([np.unpackbits(tb), np.array([(chk >> (tcrc - 1 - i)) & 1 for i in range(tcrc)], np.uint8)])
+    C = compute_nof_codeblocks(tbs_bits, base_graph)
+    Z = compute_lifting_size(tbs_bits, base_graph, C)
+    K = compute_codeblock_size(base_graph, Z)
+    cb_crc = 24 if C > 1 else 0
+    b_out = bits.size + cb_crc * C
+    info = -(-b_out // C) - cb_crc  # information bits per codeblock; the last one is zero padded
+    segments, off = [], 0
+    for _ in range(C):
+        seg = np.zeros(K, np.uint8)
+        take = min(info, bits.size - off)
+        seg[:take] = bits[off:off + take]
+        off += take
+        if cb_crc:
+            c = ctx.crc(capi.CRC24B, np.packbits(seg[:info]), info)
+            seg[info:info + 24] = [(c >> (23 - i)) & 1 for i in range(24)]
+        segments.append(seg)
+    return segments
