@@ -741,3 +741,46 @@ srsran::cuda::create_pusch_decoder_factory_cuda(std::shared_ptr<pusch_decoder_ba
 {
   return std::make_shared<pusch_decoder_factory_cuda>(std::move(batch));
 }
+
+// ---- downlink twin: LDPC encoder ---------------------------------------------------------------------------------------
+
+void ldpc_encoder_cuda::encode(bit_buffer& output, const bit_buffer& input, const codeblock_metadata::tb_common_metadata& cfg)
+{
+  const unsigned bg = (cfg.base_graph == ldpc_base_graph_type::BG1) ? 1 : 2;
+  const unsigned Z  = static_cast<unsigned>(cfg.lifting_size);
+  const unsigned K = (bg == 1 ? 22 : 10) * Z, N = (bg == 1 ? 66 : 50) * Z;
+  srsran_assert(input.size() == K, "Input size {} does not match the codeblock size {}.", input.size(), K);
+  srsran_assert(output.size() <= N, "Output size {} exceeds the full codeblock size {}.", output.size(), N);
+  // bit_buffer stores bits packed MSB first: the message goes as it is (filler bits read as zeros, like in the
+  // reference's encoders, ldpc_encoder_impl.cpp:52-60).
+  std::vector<uint8_t> msg((K + 7) / 8, 0);
+  for (unsigned i = 0; i != K; ++i) {
+    const uint8_t b = input.extract(i, 1);
+    msg[i >> 3] |= static_cast<uint8_t>((b & 1u) << (7 - (i & 7)));
+  }
+  bits.resize(N);
+  int rc = pdc_ldpc_encode(ctx->get(), static_cast<int>(bg), static_cast<int>(Z), msg.data(), bits.data());
+  srsran_assert(rc == PDC_OK, "pdc_ldpc_encode failed: {}", pdc_last_error());
+  (void)rc;
+  // The caller may ask for a prefix of the codeblock only (ldpc_encoder.h:47-50).
+  for (unsigned i = 0, n = output.size(); i != n; ++i) {
+    output.insert(bits[i], i, 1);
+  }
+}
+
+namespace {
+class ldpc_encoder_factory_cuda : public ldpc_encoder_factory
+{
+public:
+  explicit ldpc_encoder_factory_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  std::unique_ptr<ldpc_encoder> create() override { return std::make_unique<ldpc_encoder_cuda>(ctx); }
+
+private:
+  std::shared_ptr<context> ctx;
+};
+} // namespace
+
+std::shared_ptr<ldpc_encoder_factory> srsran::cuda::create_ldpc_encoder_factory_cuda(std::shared_ptr<context> ctx)
+{
+  return std::make_shared<ldpc_encoder_factory_cuda>(std::move(ctx));
+}

@@ -19,6 +19,8 @@
 ///                                   object queues its transport block at on_end_softbits; flush() decodes all of them
 ///                                   (every UE and cell of the slot) with ONE pdc_submit, TB concatenation and TB CRC on
 ///                                   the device, and then fires the notifiers.
+///   ldpc_encoder_cuda             : srsran::ldpc_encoder (phy/upper/channel_coding/ldpc/ldpc_encoder.h:37-38), the downlink
+///                                   twin; pdc_encode additionally fuses the rate matcher for whole batches.
 /// and the factories a "cuda" branch of create_ldpc_decoder_factory_sw / create_ldpc_rate_dematcher_factory_sw /
 /// create_crc_calculator_factory_sw / create_hw_accelerator_pusch_dec_factory returns.
 #pragma once
@@ -29,6 +31,7 @@
 #include "srsran/phy/upper/channel_coding/channel_coding_factories.h"
 #include "srsran/phy/upper/channel_modulation/channel_modulation_factories.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_codeword_buffer.h"
+#include "srsran/phy/upper/channel_coding/ldpc/ldpc_encoder.h"
 #include "srsran/phy/upper/channel_coding/ldpc/ldpc_segmenter_rx.h"
 #include "srsran/phy/upper/channel_processors/pusch/factories.h"
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder.h"
@@ -280,6 +283,21 @@ private:
 /// What a "cuda" choice in place of create_pusch_decoder_factory_sw / _hw (phy/upper/channel_processors/pusch/
 /// factories.h:56-99) returns: every create() yields a decoder bound to the given slot batch.
 std::shared_ptr<pusch_decoder_factory> create_pusch_decoder_factory_cuda(std::shared_ptr<pusch_decoder_batch_cuda> batch);
+
+/// LDPC encoder, single-codeblock synchronous call (the throughput interface is pdc_encode: encoder + rate matcher for a
+/// batch of codeblocks in one kernel).
+class ldpc_encoder_cuda : public ldpc_encoder
+{
+public:
+  explicit ldpc_encoder_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  void encode(bit_buffer& output, const bit_buffer& input, const codeblock_metadata::tb_common_metadata& cfg) override;
+
+private:
+  std::shared_ptr<context> ctx;
+  std::vector<uint8_t>     bits;
+};
+/// What a "cuda" branch of create_ldpc_encoder_factory_sw (channel_coding_factories.h:68) returns.
+std::shared_ptr<ldpc_encoder_factory> create_ldpc_encoder_factory_cuda(std::shared_ptr<context> ctx);
 
 std::shared_ptr<ldpc_decoder_factory>        create_ldpc_decoder_factory_cuda(std::shared_ptr<context> ctx);
 std::shared_ptr<ldpc_rate_dematcher_factory> create_ldpc_rate_dematcher_factory_cuda(std::shared_ptr<context> ctx);

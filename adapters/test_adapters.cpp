@@ -593,6 +593,67 @@ int main()
     }
     std::printf("demodulation_mapper_cuda: %u demodulate_soft calls compared with demodulation_mapper_impl\n", checked);
   }
+  // ---- downlink twin: ldpc_encoder_cuda vs the reference's encoder, and pdc_encode vs encoder + rate matcher -----------------
+  {
+    auto enc_sw  = create_ldpc_encoder_factory_sw("auto")->create();
+    auto enc_gpu = cuda::create_ldpc_encoder_factory_cuda(ctx)->create();
+    auto rm_sw   = create_ldpc_rate_matcher_factory_sw()->create();
+    unsigned checked = 0;
+    for (int trial = 0; trial != 40; ++trial) {
+      const unsigned Zs[] = {384, 352, 208, 96, 52, 30, 13, 7, 2, 256};
+      const unsigned Z = Zs[trial % 10], bg = 1 + (trial % 2);
+      const unsigned K = (bg == 1 ? 22 : 10) * Z, N = (bg == 1 ? 66 : 50) * Z;
+      const unsigned F = (trial % 3 == 0) ? rng() % Z : 0;
+      const unsigned qm = 2 * (1 + trial % 4);
+      codeblock_metadata m;
+      m.tb_common.base_graph        = bg == 1 ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2;
+      m.tb_common.lifting_size      = static_cast<ldpc::lifting_size_t>(Z);
+      m.tb_common.rv                = trial % 4;
+      m.tb_common.mod               = to_mod(qm);
+      m.tb_common.Nref              = (trial % 5 == 0) ? (N - rng() % (N / 4)) : 0;
+      m.cb_specific.full_length     = N;
+      m.cb_specific.rm_length       = ((N / 3 + rng() % (2 * N)) / qm) * qm;
+      m.cb_specific.nof_filler_bits = F;
+      dynamic_bit_buffer msg(K), cw_sw(N), cw_gpu(N);
+      std::vector<uint8_t> packed((K + 7) / 8, 0);
+      for (unsigned i = 0; i != K; ++i) {
+        const uint8_t b = (i < K - F) ? (rng() & 1) : 0;
+        msg.insert(b, i, 1);
+        packed[i >> 3] |= static_cast<uint8_t>(b << (7 - (i & 7)));
+      }
+      enc_sw->encode(cw_sw, msg, m.tb_common);
+      enc_gpu->encode(cw_gpu, msg, m.tb_common);
+      bool same = true;
+      for (unsigned i = 0; i != N; ++i) {
+        // filler positions of the systematic part are "filler bit" markers in the reference; compare what is transmitted
+        if (i >= K - 2 * Z - F && i < K - 2 * Z) {
+          continue;
+        }
+        same = same && (cw_sw.extract(i, 1) == cw_gpu.extract(i, 1));
+      }
+      CHECK(same, "ldpc encoder: codeblock differs (trial %d bg%u Z=%u)", trial, bg, Z);
+      // encoder + rate matcher of the reference vs the fused device kernel
+      const unsigned     E = m.cb_specific.rm_length;
+      dynamic_bit_buffer rm_out(E);
+      rm_sw->rate_match(rm_out, cw_sw, m);
+      pdc_enc_desc d = {};
+      d.rm_length = E, d.nref = m.tb_common.Nref, d.lifting_size = static_cast<uint16_t>(Z);
+      d.nof_filler = static_cast<uint16_t>(F), d.base_graph = static_cast<uint8_t>(bg), d.qm = static_cast<uint8_t>(qm);
+      d.rv = static_cast<uint8_t>(m.tb_common.rv);
+      std::vector<uint8_t> out(E);
+      CHECK(pdc_encode(ctx->get(), &d, 1, packed.data(), packed.size(), out.data(), out.size()) == PDC_OK,
+            "pdc_encode failed: %s", pdc_last_error());
+      bool same_rm = true;
+      for (unsigned i = 0; i != E; ++i) {
+        same_rm = same_rm && (rm_out.extract(i, 1) == out[i]);
+      }
+      CHECK(same_rm, "encoder + rate matcher: bits differ (trial %d bg%u Z=%u E=%u rv=%u qm=%u F=%u)", trial, bg, Z, E,
+            m.tb_common.rv, qm, F);
+      ++checked;
+    }
+    std::printf("ldpc_encoder_cuda / pdc_encode: %u codeblocks compared with the reference's encoder and rate matcher\n",
+                checked);
+  }
   std::printf(failures ? "FAILED: %d checks\n" : "PASS (%d failures)\n", failures);
   return failures ? 1 : 0;
 }
