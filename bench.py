@@ -663,6 +663,63 @@ def config5_leg(ctx, orc, capi, torch, stream, args):
     return {"config5_zmq_20mhz_4ue_slot": leg}
 
 
+def encode_leg(ctx, orc, capi, torch, stream, args):
+    """Downlink twin: LDPC encoding + rate matching of config-3 shaped transport blocks (152 codeblocks,
+    Z = 384, E = 8960 / 8992, rv 0) on the device, one and sixteen blocks per launch; the reference's encoder + rate matcher
+    on one host core beside it."""
+    from oracle.pyoracle import Reference
+    from srsran_edgeric_5g_b200 import ldpc
+    rng = np.random.default_rng(77)
+    tbs_bits, n_llr, qm, nl = 1277992, 1362816, 8, 4
+    C = ldpc.compute_nof_codeblocks(tbs_bits, 1)
+    nref = ldpc.compute_N_ref(tbs_bits // 8, C)
+    tb = rng.integers(0, 256, tbs_bits // 8).astype(np.uint8)
+    metas = ldpc.segment_rx(tbs_bits, 1, 0, qm, nref, nl, n_llr)
+    segs = ldpc.segment_tx(ctx, tb, 1)
+    want, _ = orc.tb_encode(tb, 1, 0, qm, nref, nl, n_llr)
+    out = {}
+    for cells in (1, 16):
+        cbs = np.zeros(C * cells, capi.ENC_DESC_DTYPE)
+        msgs, off = [], 0
+        for c in range(cells):
+            for k, (m, seg) in enumerate(zip(metas, segs)):
+                packed = np.packbits(seg)
+                cbs[c * C + k] = (off, c * n_llr + m.cw_offset, m.rm_length, nref, m.lifting_size, m.nof_filler_bits, 1, qm,
+                                  0, 0)
+                msgs.append(packed)
+                off += packed.size
+        d_cbs = torch.from_numpy(cbs.view(np.uint8)).cuda()
+        d_msgs = torch.from_numpy(np.concatenate(msgs)).cuda()
+        d_out = torch.zeros(cells * n_llr + 16, dtype=torch.uint8, device="cuda")
+
+        def step():
+            ctx.launch_encode_device(d_cbs.data_ptr(), cbs.size, d_msgs.data_ptr(), d_out.data_ptr(), cells * n_llr, 384,
+                                     True, cuda_stream=stream.cuda_stream)
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record(stream)
+        for _ in range(reps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / reps * 1e3
+        got = d_out.cpu().numpy()
+        ok = all(bool((got[c * n_llr:(c + 1) * n_llr] == want).all()) for c in range(cells))
+        out[f"{cells}_tb"] = {"us": us, "info_gbps": cells * tbs_bits / (us * 1e-6) / 1e9,
+                              "coded_gbps": cells * n_llr / (us * 1e-6) / 1e9, "codeblocks": int(cbs.size),
+                              "equals_oracle": ok}
+    if Reference.available():
+        ref = Reference()
+        t0 = time.perf_counter()
+        ref.tb_encode(tb, 1, 0, qm, nref, nl, n_llr)
+        out["reference_one_core_us_per_tb"] = (time.perf_counter() - t0) * 1e6
+    return {"downlink_twin_encode_config3_tb": out}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -710,6 +767,7 @@ def main():
         legs = slot_legs(ctx2, orc, capi, torch, torch.cuda.current_stream(), args)
         legs.update(symbol_legs(ctx2, orc, capi, torch, torch.cuda.current_stream(), args))
         legs.update(config5_leg(ctx2, orc, capi, torch, torch.cuda.current_stream(), args))
+        legs.update(encode_leg(ctx2, orc, capi, torch, torch.cuda.current_stream(), args))
         print(json.dumps(legs))
         ctx2.close()
         return
@@ -903,6 +961,7 @@ def main():
             line["extra"].update(slot_legs(ctx2, orc, capi, torch, stream, args))
             line["extra"].update(symbol_legs(ctx2, orc, capi, torch, stream, args))
             line["extra"].update(config5_leg(ctx2, orc, capi, torch, stream, args))
+            line["extra"].update(encode_leg(ctx2, orc, capi, torch, stream, args))
             ctx2.close()
             # ---- CPU baseline: the reference's own SIMD code on the host cores, bounded sample ---------------------------
             line["cpu_baseline"] = cpu_reference_rate(llrs_np[:2048], False, 12.0, os.cpu_count() or 1)
