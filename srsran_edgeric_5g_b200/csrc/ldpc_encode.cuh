@@ -11,11 +11,14 @@
 // rotation of the first, the others follow by back-substitution); every extension row is then independent of the others
 // and only the rows the rate matcher will read are computed. The rate matcher is a gather: output bit o of the
 // interleaved sequence finds its position in the circular buffer in closed form (the filler bits are a gap in it).
+// The base graph is walked in constant memory with uniform indices (one broadcast per edge); taking the edges from the
+// decoder's per-shape images instead (shifts already reduced modulo Z), from global or staged in shared memory, measured
+// slower: the kernel then needs 39-54 registers instead of 32 and loses a resident CTA per SM (16 transport blocks:
+// 271 -> 343-382 us).
 #pragma once
 
 #include "pdc_device.cuh"
 #include "tables.cuh"
-#include "ldpc_decode_h2.cuh" // per-(base graph, lifting size) edge images: shifts already reduced modulo Z
 
 namespace pdc {
 
@@ -51,9 +54,7 @@ __global__ void __launch_bounds__(ENC_MAX_THREADS) ldpc_encode_rm_kernel(EncodeP
     return; // the host validated the descriptors; nothing is written for an invalid one
   }
   const int kb = (bg == 1) ? 22 : 10, n_full = (bg == 1) ? 68 : 52, rows = (bg == 1) ? 46 : 42;
-  const int K = kb * Z, N = (n_full - 2) * Z;
-  // Edge i of row m sits at padded position row_pstart[m] + (i - row_start[m]) of the image: {4 * (shift mod Z), 4 * col * Z}.
-  const uint2* img = h2::g_h2_einfo[b][h2::c_h2_z_slot[Z]];
+  const int K = kb * Z, N = (n_full - 2) * Z, set = c_tab.set_index[Z];
   uint8_t*  c   = enc_smem;                 // n_full * Z bits
   uint8_t*  lam = enc_smem + n_full * Z;    // 4 * Z: information part of the four core rows
 
@@ -79,33 +80,8 @@ __global__ void __launch_bounds__(ENC_MAX_THREADS) ldpc_encode_rm_kernel(EncodeP
 
   // Message bits (fillers are zeros in the input), parity nodes cleared.
   const uint8_t* msg = prm.msgs + d.msg_offset;
-  for (int w = tid; w < (K + 31) / 32; w += nthr) {
-    // four message bytes -> 32 bits, one per byte
-    uint32_t v = 0;
-    for (int k = 0; k != 4; ++k) {
-      const int byte = 4 * w + k;
-      v |= (uint32_t)((byte < (K + 7) / 8) ? msg[byte] : 0u) << (8 * k);
-    }
-#pragma unroll
-    for (int q = 0; q != 8; ++q) {
-      // bits 4q .. 4q+3 of the word (MSB first inside each byte)
-      uint32_t o = 0;
-#pragma unroll
-      for (int r = 0; r != 4; ++r) {
-        const int bit = 4 * q + r;
-        o |= ((v >> (8 * (bit >> 3) + 7 - (bit & 7))) & 1u) << (8 * r);
-      }
-      const int pos = 32 * w + 4 * q;
-      if (pos + 4 <= K) {
-        *reinterpret_cast<uint32_t*>(c + pos) = o;
-      } else {
-        for (int r = 0; r != 4; ++r) {
-          if (pos + r < K) {
-            c[pos + r] = (uint8_t)(o >> (8 * r));
-          }
-        }
-      }
-    }
+  for (int i = tid; i < K; i += nthr) {
+    c[i] = (uint8_t)((msg[i >> 3] >> (7 - (i & 7))) & 1u);
   }
   for (int i = K + tid; i < (kb + rows_needed) * Z; i += nthr) {
     c[i] = 0;
@@ -118,11 +94,10 @@ __global__ void __launch_bounds__(ENC_MAX_THREADS) ldpc_encode_rm_kernel(EncodeP
   if (active) {
     for (int m = 0; m != 4; ++m) {
       uint8_t acc = 0;
-      const int deg = c_tab.row_start[b][m + 1] - c_tab.row_start[b][m], p0 = c_tab.row_pstart[b][m];
-      for (int e = 0; e != deg; ++e) {
-        const uint2 ed = img[p0 + e];
-        if ((int)(ed.y >> 2) < K) { // information column
-          acc ^= c[(ed.y >> 2) + enc_wrap(j + (int)(ed.x >> 2), Z)];
+      for (int i = c_tab.row_start[b][m]; i != c_tab.row_start[b][m + 1]; ++i) {
+        const int col = c_tab.col[b][i];
+        if (col < kb) {
+          acc ^= c[col * Z + enc_wrap(j + c_tab.v[b][set][i] % Z, Z)];
         }
       }
       lam[m * Z + j] = acc;
@@ -133,13 +108,9 @@ __global__ void __launch_bounds__(ENC_MAX_THREADS) ldpc_encode_rm_kernel(EncodeP
   // rows is one rotation of it.
   {
     int sh[3] = {0, 0, 0}, n_sh = 0;
-    for (int m = 0; m != 4; ++m) {
-      const int deg = c_tab.row_start[b][m + 1] - c_tab.row_start[b][m], p0 = c_tab.row_pstart[b][m];
-      for (int e = 0; e != deg; ++e) {
-        const uint2 ed = img[p0 + e];
-        if ((int)(ed.y >> 2) == kb * Z && n_sh < 3) {
-          sh[n_sh++] = (int)(ed.x >> 2);
-        }
+    for (int i = c_tab.row_start[b][0]; i != c_tab.row_start[b][4]; ++i) {
+      if (c_tab.col[b][i] == kb && n_sh < 3) {
+        sh[n_sh++] = c_tab.v[b][set][i] % Z;
       }
     }
     const int dsh = (sh[0] == sh[1]) ? sh[2] : ((sh[0] == sh[2]) ? sh[1] : sh[0]);
@@ -154,14 +125,12 @@ __global__ void __launch_bounds__(ENC_MAX_THREADS) ldpc_encode_rm_kernel(EncodeP
     for (int round = 0; round != 3; ++round) {
       int solved = 0;
       for (int m = 0; m != 4; ++m) {
-        int       unknown = -1, n_unknown = 0, unknown_shift = 0;
-        const int deg = c_tab.row_start[b][m + 1] - c_tab.row_start[b][m], p0 = c_tab.row_pstart[b][m];
-        for (int e = 0; e != deg; ++e) {
-          const uint2 ed  = img[p0 + e];
-          const int   col = (int)(ed.y >> 2) / Z;
+        int unknown = -1, n_unknown = 0, unknown_shift = 0;
+        for (int i = c_tab.row_start[b][m]; i != c_tab.row_start[b][m + 1]; ++i) {
+          const int col = c_tab.col[b][i];
           if (col >= kb && col < kb + 4 && !((known >> (col - kb)) & 1)) {
             unknown       = col;
-            unknown_shift = (int)(ed.x >> 2);
+            unknown_shift = c_tab.v[b][set][i] % Z;
             ++n_unknown;
           }
         }
@@ -170,11 +139,10 @@ __global__ void __launch_bounds__(ENC_MAX_THREADS) ldpc_encode_rm_kernel(EncodeP
         }
         if (active) {
           uint8_t acc = lam[m * Z + j];
-          for (int e = 0; e != deg; ++e) {
-            const uint2 ed  = img[p0 + e];
-            const int   col = (int)(ed.y >> 2) / Z;
+          for (int i = c_tab.row_start[b][m]; i != c_tab.row_start[b][m + 1]; ++i) {
+            const int col = c_tab.col[b][i];
             if (col >= kb && col < kb + 4 && ((known >> (col - kb)) & 1)) {
-              acc ^= c[(ed.y >> 2) + enc_wrap(j + (int)(ed.x >> 2), Z)];
+              acc ^= c[col * Z + enc_wrap(j + c_tab.v[b][set][i] % Z, Z)];
             }
           }
           c[unknown * Z + enc_wrap(j + unknown_shift, Z)] = acc;
@@ -191,12 +159,11 @@ __global__ void __launch_bounds__(ENC_MAX_THREADS) ldpc_encode_rm_kernel(EncodeP
   // Extension rows: a single identity column kb + m each.
   if (active) {
     for (int m = 4; m < rows_needed; ++m) {
-      uint8_t   acc = 0;
-      const int deg = c_tab.row_start[b][m + 1] - c_tab.row_start[b][m], p0 = c_tab.row_pstart[b][m];
-      for (int e = 0; e != deg; ++e) {
-        const uint2 ed = img[p0 + e];
-        if ((int)(ed.y >> 2) != (kb + m) * Z) {
-          acc ^= c[(ed.y >> 2) + enc_wrap(j + (int)(ed.x >> 2), Z)];
+      uint8_t acc = 0;
+      for (int i = c_tab.row_start[b][m]; i != c_tab.row_start[b][m + 1]; ++i) {
+        const int col = c_tab.col[b][i];
+        if (col != kb + m) {
+          acc ^= c[col * Z + enc_wrap(j + c_tab.v[b][set][i] % Z, Z)];
         }
       }
       c[(kb + m) * Z + j] = acc;
