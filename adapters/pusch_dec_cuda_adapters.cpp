@@ -784,3 +784,108 @@ std::shared_ptr<ldpc_encoder_factory> srsran::cuda::create_ldpc_encoder_factory_
 {
   return std::make_shared<ldpc_encoder_factory_cuda>(std::move(ctx));
 }
+
+// ---- downlink twin: PDSCH encoder accelerator (codeblock mode) --------------------------------------------------------
+
+void hw_accelerator_pdsch_enc_cuda::reserve_queue()
+{
+  descs.clear();
+  enqueued.clear();
+  msgs.clear();
+  out.clear();
+  encoded = false;
+}
+
+void hw_accelerator_pdsch_enc_cuda::configure_operation(const hal::hw_pdsch_encoder_configuration& cfg, unsigned cb_index)
+{
+  if (descs.size() <= cb_index) {
+    descs.resize(cb_index + 1);
+    enqueued.resize(cb_index + 1, 0);
+  }
+  pdc_enc_desc& d = descs[cb_index];
+  d               = {};
+  d.rm_length     = cfg.rm_length;
+  d.nref          = cfg.Nref;
+  d.lifting_size  = static_cast<uint16_t>(cfg.lifting_size);
+  d.nof_filler    = static_cast<uint16_t>(cfg.nof_filler_bits);
+  d.base_graph    = (cfg.base_graph_index == ldpc_base_graph_type::BG1) ? 1 : 2;
+  d.qm            = static_cast<uint8_t>(get_bits_per_symbol(cfg.modulation));
+  d.rv            = static_cast<uint8_t>(cfg.rv);
+}
+
+bool hw_accelerator_pdsch_enc_cuda::enqueue_operation(span<const uint8_t> data, span<const uint8_t>, unsigned cb_index)
+{
+  srsran_assert(cb_index < descs.size(), "Codeblock {} was not configured.", cb_index);
+  pdc_enc_desc&  d = descs[cb_index];
+  const unsigned K = ((d.base_graph == 1) ? 22u : 10u) * d.lifting_size;
+  // The segment arrives without its filler bits (pdsch_encoder_hw_impl.cpp:92-95): they are zeros behind it.
+  d.msg_offset = static_cast<uint32_t>(msgs.size());
+  msgs.resize(msgs.size() + (K + 7) / 8, 0);
+  const unsigned n_bits = K - d.nof_filler;
+  memcpy(msgs.data() + d.msg_offset, data.data(), std::min<size_t>(data.size(), (n_bits + 7) / 8));
+  if (n_bits % 8) {
+    msgs[d.msg_offset + n_bits / 8] &= static_cast<uint8_t>(0xff00u >> (n_bits % 8));
+  }
+  enqueued[cb_index] = 1;
+  encoded            = false;
+  return true;
+}
+
+bool hw_accelerator_pdsch_enc_cuda::dequeue_operation(span<uint8_t> data, span<uint8_t> aux_data, unsigned segment_index)
+{
+  if (segment_index >= descs.size() || !enqueued[segment_index]) {
+    return false;
+  }
+  if (!encoded) {
+    // Everything enqueued so far in one batch.
+    std::vector<pdc_enc_desc> batch;
+    uint32_t                  off = 0;
+    for (size_t i = 0; i != descs.size(); ++i) {
+      if (enqueued[i]) {
+        descs[i].out_offset = off;
+        off += descs[i].rm_length;
+        batch.push_back(descs[i]);
+      }
+    }
+    out.assign(off + 8, 0);
+    int rc = pdc_encode(ctx->get(), batch.data(), static_cast<uint32_t>(batch.size()), msgs.data(), msgs.size(), out.data(),
+                        out.size());
+    srsran_assert(rc == PDC_OK, "pdc_encode failed: {}", pdc_last_error());
+    if (rc != PDC_OK) {
+      return false;
+    }
+    encoded = true;
+  }
+  const pdc_enc_desc& d = descs[segment_index];
+  srsran_assert(data.size() == d.rm_length, "Wrong codeblock length.");
+  memcpy(data.data(), out.data() + d.out_offset, d.rm_length);
+  for (size_t i = 0, n = std::min<size_t>(aux_data.size(), (d.rm_length + 7) / 8); i != n; ++i) {
+    uint8_t v = 0;
+    for (unsigned b = 0; b != 8 && 8 * i + b < d.rm_length; ++b) {
+      v |= static_cast<uint8_t>((out[d.out_offset + 8 * i + b] & 1u) << (7 - b));
+    }
+    aux_data[i] = v;
+  }
+  return true;
+}
+
+namespace {
+class hw_accelerator_pdsch_enc_factory_cuda : public hal::hw_accelerator_pdsch_enc_factory
+{
+public:
+  explicit hw_accelerator_pdsch_enc_factory_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  std::unique_ptr<hal::hw_accelerator_pdsch_enc> create() override
+  {
+    return std::make_unique<hw_accelerator_pdsch_enc_cuda>(ctx);
+  }
+
+private:
+  std::shared_ptr<context> ctx;
+};
+} // namespace
+
+std::shared_ptr<hal::hw_accelerator_pdsch_enc_factory>
+srsran::cuda::create_hw_accelerator_pdsch_enc_factory_cuda(std::shared_ptr<context> ctx)
+{
+  return std::make_shared<hw_accelerator_pdsch_enc_factory_cuda>(std::move(ctx));
+}

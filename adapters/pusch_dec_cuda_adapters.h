@@ -27,6 +27,8 @@
 
 #include "pusch_dec_cuda.h"
 #include "srsran/hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec.h"
+#include "srsran/hal/phy/upper/channel_processors/hw_accelerator_pdsch_enc.h"
+#include "srsran/hal/phy/upper/channel_processors/hw_accelerator_pdsch_enc_factory.h"
 #include "srsran/hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec_factory.h"
 #include "srsran/phy/upper/channel_coding/channel_coding_factories.h"
 #include "srsran/phy/upper/channel_modulation/channel_modulation_factories.h"
@@ -296,6 +298,32 @@ private:
   std::shared_ptr<context> ctx;
   std::vector<uint8_t>     bits;
 };
+/// \brief PDSCH encoder accelerator in the hal::hw_accelerator_pdsch_enc slot (hal/phy/upper/channel_processors/
+/// hw_accelerator_pdsch_enc.h:77-105), codeblock mode: pdsch_encoder_hw_impl (lib/phy/upper/channel_processors/
+/// pdsch_encoder_hw_impl.cpp:35-200), unchanged, segments the transport block and attaches the CRCs, enqueues every
+/// segment and dequeues the rate-matched codeblocks; the first dequeue encodes and rate-matches all enqueued segments as
+/// ONE pdc_encode batch.
+class hw_accelerator_pdsch_enc_cuda : public hal::hw_accelerator_pdsch_enc
+{
+public:
+  explicit hw_accelerator_pdsch_enc_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
+  void reserve_queue() override;
+  void free_queue() override {}
+  bool enqueue_operation(span<const uint8_t> data, span<const uint8_t> aux_data = {}, unsigned cb_index = 0) override;
+  bool dequeue_operation(span<uint8_t> data, span<uint8_t> aux_data = {}, unsigned segment_index = 0) override;
+  void configure_operation(const hal::hw_pdsch_encoder_configuration& config, unsigned cb_index = 0) override;
+  bool get_cb_mode() const override { return true; }
+  unsigned get_max_tb_size() const override { return 0; }
+
+private:
+  std::shared_ptr<context>  ctx;
+  std::vector<pdc_enc_desc> descs;    // by codeblock index
+  std::vector<uint8_t>      enqueued; // by codeblock index
+  std::vector<uint8_t>      msgs, out;
+  bool                      encoded = false;
+};
+std::shared_ptr<hal::hw_accelerator_pdsch_enc_factory> create_hw_accelerator_pdsch_enc_factory_cuda(std::shared_ptr<context> ctx);
+
 /// What a "cuda" branch of create_ldpc_encoder_factory_sw (channel_coding_factories.h:68) returns.
 std::shared_ptr<ldpc_encoder_factory> create_ldpc_encoder_factory_cuda(std::shared_ptr<context> ctx);
 

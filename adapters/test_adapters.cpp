@@ -2,6 +2,8 @@
 // own classes: the UNMODIFIED pusch_decoder_hw_impl (lib/phy/upper/channel_processors/pusch/pusch_decoder_hw_impl.cpp)
 // runs on top of hw_accelerator_pusch_dec_cuda and is compared with the reference's software pusch_decoder_impl on the
 // same LLRs, over HARQ retransmissions. Test infrastructure: links oracle/_ref/libsrsref.so (the compiled reference).
+#include "lib/phy/upper/channel_processors/pdsch_encoder_hw_impl.h"
+#include "lib/phy/upper/channel_processors/pdsch_encoder_impl.h"
 #include "lib/phy/upper/channel_processors/pusch/pusch_codeblock_decoder.h"
 #include "lib/phy/upper/channel_processors/pusch/pusch_decoder_hw_impl.h"
 #include "lib/phy/upper/channel_processors/pusch/pusch_decoder_impl.h"
@@ -653,6 +655,44 @@ int main()
     }
     std::printf("ldpc_encoder_cuda / pdc_encode: %u codeblocks compared with the reference's encoder and rate matcher\n",
                 checked);
+  }
+  // ---- downlink twin: the reference's pdsch_encoder_hw_impl, unchanged, on the CUDA accelerator vs pdsch_encoder_impl --------
+  {
+    pdsch_encoder_impl sw(create_ldpc_segmenter_tx_factory_sw(crc_f)->create(),
+                          create_ldpc_encoder_factory_sw("auto")->create(),
+                          create_ldpc_rate_matcher_factory_sw()->create());
+    pdsch_encoder_hw_impl::sch_crc c4{crc_f->create(crc_generator_poly::CRC16), crc_f->create(crc_generator_poly::CRC24A),
+                                      crc_f->create(crc_generator_poly::CRC24B)};
+    pdsch_encoder_hw_impl hw(c4, create_ldpc_segmenter_tx_factory_sw(crc_f)->create(),
+                             cuda::create_hw_accelerator_pdsch_enc_factory_cuda(ctx)->create());
+    unsigned checked = 0;
+    for (int trial = 0; trial != 24; ++trial) {
+      const int      bg       = (trial % 3 == 2) ? 2 : 1;
+      const unsigned qm       = 2 * (1 + trial % 4), nl = 1 + trial % 4;
+      const unsigned tb_bytes = (bg == 1) ? 500 + 3700 * (trial % 7) : 30 + 60 * (trial % 7);
+      const double   rate     = (bg == 1) ? 0.5 + 0.04 * (trial % 10) : 0.2 + 0.04 * (trial % 10);
+      const unsigned nsym     = static_cast<unsigned>(std::ceil(tb_bytes * 8 / rate / qm / nl)) * nl;
+      const unsigned C        = ldpc::compute_nof_codeblocks(units::bits(tb_bytes * 8),
+                                                      bg == 1 ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2);
+      pdsch_encoder::configuration cfg;
+      cfg.base_graph     = bg == 1 ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2;
+      cfg.rv             = trial % 4;
+      cfg.mod            = to_mod(qm);
+      cfg.Nref           = (trial % 2) ? ldpc::compute_N_ref(units::bytes(tb_bytes + 50), C).value() : 0;
+      cfg.nof_layers     = nl;
+      cfg.nof_ch_symbols = nsym;
+      std::vector<uint8_t> tb(tb_bytes), cw_sw(nsym * qm), cw_hw(nsym * qm);
+      for (auto& v : tb) {
+        v = rng() & 0xff;
+      }
+      sw.encode(cw_sw, tb, cfg);
+      hw.encode(cw_hw, tb, cfg);
+      CHECK(cw_sw == cw_hw, "pdsch encoder: codeword differs (trial %d bg%d tbs=%u C=%u qm=%u nl=%u rv=%u)", trial, bg,
+            tb_bytes * 8, C, qm, nl, cfg.rv);
+      ++checked;
+    }
+    std::printf("hw_accelerator_pdsch_enc_cuda: %u transport blocks through pdsch_encoder_hw_impl compared with "
+                "pdsch_encoder_impl\n", checked);
   }
   std::printf(failures ? "FAILED: %d checks\n" : "PASS (%d failures)\n", failures);
   return failures ? 1 : 0;
