@@ -28,6 +28,8 @@ PATCHES = {
     "lib/phy/upper/channel_coding/channel_coding_factories.cpp": [
         ("std::shared_ptr<ldpc_decoder_factory> srsran::create_ldpc_decoder_factory_sw(",
          '  if (dec_type == "cuda") {\n    return srsran::cuda::create_ldpc_decoder_factory_cuda(cuda_context());\n  }\n'),
+        ("std::shared_ptr<ldpc_encoder_factory> srsran::create_ldpc_encoder_factory_sw(",
+         '  if (enc_type == "cuda") {\n    return srsran::cuda::create_ldpc_encoder_factory_cuda(cuda_context());\n  }\n'),
         ("srsran::create_ldpc_rate_dematcher_factory_sw(",
          '  if (dematcher_type == "cuda") {\n'
          '    return srsran::cuda::create_ldpc_rate_dematcher_factory_cuda(cuda_context());\n  }\n'),

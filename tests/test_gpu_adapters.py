@@ -47,3 +47,15 @@ def test_reference_ldpc_decoder_benchmark_with_cuda_factory():
                          timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "LDPC decoder cuda" in out.stdout and "BG=2 LS=96" in out.stdout
+
+
+def test_reference_ldpc_encoder_benchmark_with_cuda_factory():
+    """tests/benchmarks/phy/upper/channel_coding/ldpc/ldpc_encoder_benchmark.cpp of the reference, unmodified,
+    `-T cuda`: create_ldpc_encoder_factory_sw("cuda") hands out the GPU encoder (downlink twin) and the benchmark runs to
+    completion over both base graphs and all lifting sizes."""
+    exe = HARNESS / "ldpc_encoder_benchmark"
+    if not exe.exists():
+        pytest.skip("integration/_build not built (needs /root/reference at build time)")
+    out = subprocess.run([str(exe), "-T", "cuda", "-R", "5"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "LDPC encoder cuda" in out.stdout
