@@ -85,6 +85,59 @@ def test_batch_of_calls_on_device_buffers(ctx, orc):
     assert (got[~covered] == 77).all()  # nothing written outside the calls
 
 
+def test_more_calls_than_one_launch_carries_and_empty_calls(ctx, orc):
+    """The call table travels in the kernel parameters, 224 calls per launch: a batch of 500 calls (some of them empty)
+    goes out as three launches; an empty demodulate_soft call is a no-op."""
+    import torch
+    rng = np.random.default_rng(35)
+    calls, syms, nvs, want = [], [], [], []
+    sym_pos = llr_pos = 0
+    for k in range(500):
+        mod = int(rng.choice(DEMOD_MODS))
+        n = 0 if k % 37 == 5 else int(rng.integers(1, 70))
+        s, nv = demod_inputs(rng, n, mod, k % 3) if n else (np.zeros(0, np.complex64), np.zeros(0, np.float32))
+        calls.append((sym_pos, n, llr_pos, mod))
+        want.append(orc.demodulate_soft(s, nv, mod) if n else np.zeros(0, np.int8))
+        syms.append(s)
+        nvs.append(nv)
+        sym_pos += n
+        llr_pos += n * max(mod, 1)
+    d_sym = torch.from_numpy(np.concatenate(syms).view(np.float32)).cuda()
+    d_nv = torch.from_numpy(np.concatenate(nvs)).cuda()
+    d_llr = torch.zeros(llr_pos + 16, dtype=torch.int8, device="cuda")
+    before = ctx.launch_count()
+    ctx.launch_demod_device(np.array(calls, capi.DEMOD_CALL_DTYPE), d_sym.data_ptr(), d_nv.data_ptr(), sym_pos,
+                            d_llr.data_ptr(), llr_pos, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert ctx.launch_count() - before == 3
+    assert (d_llr.cpu().numpy()[:llr_pos] == np.concatenate(want)).all()
+    assert ctx.demodulate_soft(np.zeros(0, np.complex64), np.zeros(0, np.float32), 4).size == 0
+
+
+def test_symbols_bpsk_flag(ctx, orc):
+    """qm = 1 through pdc_submit_symbols: pi/2-BPSK unless the codeword says plain BPSK (PDC_CW_PLAIN_BPSK)."""
+    rng = np.random.default_rng(36)
+    cfg = dict(qm=1, nof_layers=1, nof_prb=7, start_symbol_index=0, nof_symbols=14, dmrs_type=1, dmrs_symbol_mask=1 << 3,
+               nof_cdm_groups_without_data=2)
+    n = orc.ulsch_codeword_length(cfg)
+    s, nv = demod_inputs(rng, n, 0, 0)
+    c_init = 4242
+    seq = orc.prg_bits(c_init, 0, n)
+    for flag, mod in ((0, 0), (capi.CW_PLAIN_BPSK, 1)):
+        raw = demod_codeword(orc, cfg, s, nv, mod=mod)
+        want = orc.revert_scrambling(raw, seq)
+        d = cw_desc(cfg, c_init=c_init, flags=capi.CW_SCRAMBLED | flag)
+        ctx.harq_write(520, np.zeros(capi.PDC_MAX_CB_SOFT, np.int8))
+        ctx.submit_symbols(np.array([d]), np.zeros(1, np.uint32), s, nv, stream=0)
+        cbs = np.zeros(1, capi.CB_DESC_DTYPE)
+        cbs[0] = (0, n, 520, 0, 384, 0, 1, 1, 0, capi.CRC24B, 1, capi.CB_DEMATCH | capi.CB_NEW_DATA, 0xffff)
+        ctx.submit(cbs, None, None, stream=0, want_bits=False)
+        ctx.wait(0)
+        buf = np.zeros(66 * 384, np.int8)
+        orc.rate_dematch(buf, want, True, 0, 1)
+        assert (ctx.harq_read(520) == buf).all(), mod
+
+
 def test_invalid_calls_are_rejected(ctx):
     s = np.zeros(8, np.complex64)
     nv = np.ones(8, np.float32)
