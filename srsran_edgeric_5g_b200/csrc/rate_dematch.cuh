@@ -337,21 +337,60 @@ __device__ __forceinline__ void dm_segment_words(const DematchGeom& g, const int
                                                  uint32_t* out, int action, int ioff, int wa, int wb, DmLast& last)
 {
   const int tid = threadIdx.x, T = blockDim.x;
+  // The write-only actions go out in 16-byte stores: words [wa, va) and [vb, wb) one by one, [va, vb) four at a time
+  // (the HARQ entry is 16-byte aligned). These loops are what the kernel spends its issue slots on.
+  const int va = min(wb, (wa + 3) & ~3), vb = max(va, wb & ~3);
+  uint4*    out4 = reinterpret_cast<uint4*>(out);
   switch (action) {
     case DM_ZERO:
-      for (int w = wa + tid; w < wb; w += T) {
+      for (int w = wa + tid; w < va; w += T) {
+        out[w] = 0u;
+      }
+      for (int q = (va >> 2) + tid; q < (vb >> 2); q += T) {
+        out4[q] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      for (int w = vb + tid; w < wb; w += T) {
         out[w] = 0u;
       }
       break;
     case DM_FILL:
-      for (int w = wa + tid; w < wb; w += T) {
+      for (int w = wa + tid; w < va; w += T) {
+        out[w] = 0x7f7f7f7fu;
+        last.note(w, 0x7f7f7f7fu);
+      }
+      for (int q = (va >> 2) + tid; q < (vb >> 2); q += T) {
+        out4[q] = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+        last.note(4 * q + 3, 0x7f7f7f7fu);
+      }
+      for (int w = vb + tid; w < wb; w += T) {
         out[w] = 0x7f7f7f7fu;
         last.note(w, 0x7f7f7f7fu);
       }
       break;
     case DM_COPY:
-#pragma unroll 2
-      for (int w = wa + tid; w < wb; w += T) {
+      for (int w = wa + tid; w < va; w += T) {
+        const uint32_t r = dm_lds_u32_unaligned(sh, 4 * w + ioff);
+        out[w]           = r;
+        last.note(w, r);
+      }
+      for (int q = (va >> 2) + tid; q < (vb >> 2); q += T) {
+        // sixteen staged bytes from an arbitrary byte offset: five aligned words, four funnel shifts
+        const int       a   = 16 * q + ioff;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(sh + (a & ~3));
+        const uint32_t  sh8 = 8u * (uint32_t)(a & 3);
+        const uint32_t  s0 = src[0], s1 = src[1], s2 = src[2], s3 = src[3], s4 = src[4];
+        uint4           r;
+        r.x = __funnelshift_r(s0, s1, sh8);
+        r.y = __funnelshift_r(s1, s2, sh8);
+        r.z = __funnelshift_r(s2, s3, sh8);
+        r.w = __funnelshift_r(s3, s4, sh8);
+        out4[q] = r;
+        last.note(4 * q, r.x);
+        last.note(4 * q + 1, r.y);
+        last.note(4 * q + 2, r.z);
+        last.note(4 * q + 3, r.w);
+      }
+      for (int w = vb + tid; w < wb; w += T) {
         const uint32_t r = dm_lds_u32_unaligned(sh, 4 * w + ioff);
         out[w]           = r;
         last.note(w, r);
