@@ -224,3 +224,53 @@ def test_general_kernel_forced(orc, monkeypatch):
         b = make_cb_batch(orc, bg, Z, n_cb=5, E=E - E % 2, qm=2, rv=0, snr_db=3.0, seed=Z)
         _assert_same(b.run_gpu(c, 6, True), b.run_oracle(orc, 6, True), f"general kernel BG{bg} Z={Z}")
     c.close()
+
+
+def test_persistent_ctas_across_changing_shapes(ctx, orc):
+    """More codeblock pairs than resident CTAs, shapes changing from pair to pair: a persistent CTA keeps the lifted
+    graph and the CRC weights of its previous pair in shared memory when the shape repeats and must rebuild exactly
+    what changed (base graph / lifting size; filler bits or CRC polynomial only; iteration count). One Z = 384 codeblock
+    puts the batch on the 384-thread kernel (296 CTAs); 720 codeblocks give every CTA at least one more pair."""
+    from srsran_edgeric_5g_b200 import capi
+    rng = np.random.default_rng(4242)
+    kinds = [(1, 384, po.CRC24B, 0)]
+    for _ in range(40):
+        bg = int(rng.integers(1, 3))
+        Z = int(rng.choice([4, 7, 10, 16, 24, 36, 52, 64]))
+        kinds.append((bg, Z, [po.CRC16, po.CRC24A, po.CRC24B][int(rng.integers(0, 3))] if Z > 3 else po.CRC16,
+                      int(rng.integers(0, Z))))
+    protos = []
+    for i, (bg, Z, crc, F) in enumerate(kinds):
+        n_short = 66 if bg == 1 else 50
+        E = int(rng.integers(28 if bg == 1 else 14, n_short + 1)) * Z
+        E -= E % 2
+        protos.append(make_cb_batch(orc, bg, Z, 1, E, 2, 0, float(rng.uniform(0.5, 6)), 9000 + i, crc_kind=crc, nof_filler=F))
+    n = 720
+    pick = np.concatenate([[0], rng.integers(1, len(protos), n - 1)])
+    # pairs repeat their shape now and then (reuse path) and otherwise change it (rebuild path)
+    for i in range(2, n, 2):
+        if rng.random() < 0.3:
+            pick[i], pick[i + 1] = pick[i - 2], pick[i - 1]
+        elif rng.random() < 0.5:
+            pick[i + 1] = pick[i]
+    cbs = np.zeros(n, capi.CB_DESC_DTYPE)
+    llrs, off = [], 0
+    iters = rng.integers(1, 7, n)
+    for i, p in enumerate(pick):
+        b = protos[p]
+        flags = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA | (capi.CB_EARLY_STOP if i % 3 else 0)
+        cbs[i] = (off, b.E, 1000 + i, 0, b.Z, b.nof_filler, b.bg, 2, 0, b.crc_kind, int(iters[i]), flags, 0xffff)
+        llrs.append(b.llrs[0])
+        off += b.E
+    for i in range(n):
+        ctx.harq_write(1000 + i, np.zeros(capi.PDC_MAX_CB_SOFT, np.int8))
+    ctx.submit(cbs, np.concatenate(llrs), None, stream=0, want_bits=True)
+    out = ctx.wait(0)
+    cache = {}
+    for i, p in enumerate(pick):
+        key = (int(p), int(iters[i]), bool(i % 3))
+        if key not in cache:
+            cache[key] = protos[p].run_oracle(orc, int(iters[i]), bool(i % 3))
+        ref, b, r = cache[key], protos[p], out["cb_results"][i]
+        assert bool(r["crc_ok"]) == bool(ref["crc_ok"][0]) and r["iters"] == ref["iters"][0], (i, kinds[p], r, ref["iters"])
+        assert (out["cb_bits"][i, :(b.K + 7) // 8] == ref["bits"][0]).all(), (i, kinds[p])
