@@ -643,6 +643,24 @@ __global__ void __launch_bounds__(DM_THREADS, 8) rate_dematch_kernel(BatchParams
   const int  w_hi = min(nw, w_lo + per);
   DmLast last;
   if (fast) {
+    // Words cut by a breakpoint (and the incomplete last word): one thread per soft bit, the four of a word side by
+    // side; the HARQ word is requested before the segment loops and used after them.
+    const bool cut_thread = tid < 4 * DM_MAX_BP;
+    bool       cut_mine   = false;
+    int        cut_w      = 0;
+    uint32_t   cut_old    = 0;
+    if (cut_thread) {
+      const int b = sh_bp[tid >> 2];
+      cut_w       = b >> 2;
+      cut_mine    = (b & 3) != 0 && cut_w >= w_lo && cut_w < w_hi;
+      if (cut_mine && tid >= 4) {
+        const int prev = sh_bp[(tid >> 2) - 1];
+        cut_mine       = !((prev & 3) != 0 && (prev >> 2) == cut_w);
+      }
+      if (cut_mine) {
+        cut_old = out[cut_w];
+      }
+    }
     for (int s = 0; s != DM_MAX_BP - 1; ++s) {
       const DmSeg sg = sh_seg[s];
       const int   wa = max((sg.p0 + 3) >> 2, w_lo);
@@ -651,17 +669,24 @@ __global__ void __launch_bounds__(DM_THREADS, 8) rate_dematch_kernel(BatchParams
         dm_segment_words(g_sh, llr, sh_in, out, sg.action, sg.ioff, wa, wb, last);
       }
     }
-    // Words cut by a breakpoint (and the incomplete last word).
-    if (tid < DM_MAX_BP) {
-      const int b = sh_bp[tid];
-      const int w = b >> 2;
-      bool      mine = (b & 3) != 0 && w >= w_lo && w < w_hi;
-      if (mine && tid > 0) {
-        const int prev = sh_bp[tid - 1];
-        mine           = !((prev & 3) != 0 && (prev >> 2) == w);
+    if (cut_thread) {
+      const int k   = tid & 3;
+      uint32_t  res = 0;
+      if (cut_mine) {
+        const int v = dm_position<true>(g_sh, llr, sh_in, 4 * cut_w + k, (int)(int8_t)(cut_old >> (8 * k)));
+        res         = (uint32_t)(uint8_t)(int8_t)v << (8 * k);
       }
-      if (mine) {
-        last.note(w, dm_word_general<true>(g_sh, llr, sh_in, out, w));
+      const uint32_t lanes = (tid < 32) ? 0xffffffffu : ((1u << (4 * DM_MAX_BP - 32)) - 1u);
+      res |= __shfl_xor_sync(lanes, res, 1);
+      res |= __shfl_xor_sync(lanes, res, 2);
+      if (cut_mine && k == 0) {
+        if (res != cut_old) {
+          out[cut_w] = res;
+        }
+        if (4 * cut_w + 3 >= g_sh.N) { // bytes beyond N keep their old value and do not count as soft bits
+          res &= 0xffffffffu >> (8 * (4 * cut_w + 4 - g_sh.N));
+        }
+        last.note(cut_w, res);
       }
     }
   } else if (staged) {
