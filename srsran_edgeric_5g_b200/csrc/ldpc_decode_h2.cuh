@@ -347,6 +347,10 @@ __device__ __forceinline__ void sweep128(const hh* soft, const uint2* wgt, int n
   const uint32_t sh3 = 28u - 4u * (uint32_t)l8;                         // shift of the lane's LAST bit: 31 - (4 l8 + 3)
   const uint32_t bitpos = 8u * (uint32_t)(l8 >> 1) + ((l8 & 1) ? 0u : 4u); // of the lane's nibble in the little-endian word
   const uint32_t gmask  = 0xffu << (8 * grp);
+  // CRC: a lane keeps its four bit positions inside a word for the whole sweep, so the shift by 31 - b is applied once
+  // at the end: per bit and step only "accumulator ^= weight & mask", on both codeblocks at once (the weights are stored
+  // as {low halves of A and B, high halves of A and B}, the masks are one 16-bit half per codeblock).
+  uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
   for (int s = warp; s < n_steps; s += n_warps) {
     const uint4 v4 = *reinterpret_cast<const uint4*>(soft + 128 * s + 4 * lane_id);
     const int   t  = 4 * s + grp;
@@ -361,12 +365,8 @@ __device__ __forceinline__ void sweep128(const hh* soft, const uint2* wgt, int n
 #pragma unroll
       for (int k = 0; k != 4; ++k) {
         acc[4] |= __heq2_mask(H(sv[k]), H(H_ZERO));
-        const uint32_t m0 = __byte_perm(hm[k], 0, 0x1010), m1 = __byte_perm(hm[k], 0, 0x3232);
-        const uint32_t sh = sh3 + 3u - (uint32_t)k;
-        acc[0] = lop_xor_and(acc[0], wg.x << sh, m0);
-        acc[1] = lop_xor_and(acc[1], __funnelshift_l(wg.x, 0u, sh), m0);
-        acc[2] = lop_xor_and(acc[2], wg.y << sh, m1);
-        acc[3] = lop_xor_and(acc[3], __funnelshift_l(wg.y, 0u, sh), m1);
+        lo[k] = lop_xor_and(lo[k], wg.x, hm[k]);
+        hi[k] = lop_xor_and(hi[k], wg.y, hm[k]);
       }
     }
     if (PACK) {
@@ -387,6 +387,17 @@ __device__ __forceinline__ void sweep128(const hh* soft, const uint2* wgt, int n
       }
     }
   }
+  if (CRC) {
+#pragma unroll
+    for (int k = 0; k != 4; ++k) {
+      const uint32_t a  = __byte_perm(lo[k], hi[k], 0x5410), b = __byte_perm(lo[k], hi[k], 0x7632);
+      const uint32_t sh = sh3 + 3u - (uint32_t)k;
+      acc[0] ^= a << sh;
+      acc[1] ^= __funnelshift_l(a, 0u, sh);
+      acc[2] ^= b << sh;
+      acc[3] ^= __funnelshift_l(b, 0u, sh);
+    }
+  }
 }
 
 // One 32-bit word (lane = bit) with bound tests: the words around the end of the checked bits and of the message.
@@ -401,7 +412,8 @@ __device__ __forceinline__ void sweep_word(const hh* soft, const uint2* wgt, int
     const uint32_t shl = 31u - (uint32_t)lane_id;
     const uint32_t m0  = (i < nb0) ? __byte_perm(hm, 0, 0x1010) : 0u;
     const uint32_t m1  = (i < nb1) ? __byte_perm(hm, 0, 0x3232) : 0u;
-    const uint2    wg  = wgt[w];
+    const uint2    wp  = wgt[w]; // {low halves of A and B, high halves}
+    const uint2    wg  = make_uint2(__byte_perm(wp.x, wp.y, 0x5410), __byte_perm(wp.x, wp.y, 0x7632));
     acc[4] |= __heq2_mask(sw, H(H_ZERO));
     acc[0] = lop_xor_and(acc[0], wg.x << shl, m0);
     acc[1] = lop_xor_and(acc[1], __funnelshift_l(wg.x, 0u, shl), m0);
@@ -556,7 +568,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       size_t off  = 0;
       hh*    soft = reinterpret_cast<hh*>(smem_raw);
       off += (size_t)n_full * Z * 4;
-      uint2* wgt = reinterpret_cast<uint2*>(smem_raw + off); // CRC word weights {codeblock A, codeblock B}
+      uint2* wgt = reinterpret_cast<uint2*>(smem_raw + off); // CRC word weights {low halves of A and B, high halves}
       off += (size_t)n_words * 8;
       off          = (off + 15) & ~(size_t)15;
       GraphSmem& g = *reinterpret_cast<GraphSmem*>(smem_raw + off);
@@ -606,8 +618,9 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         const uint32_t wkey1 = (uint32_t)kind[1] | ((uint32_t)T[1] << 8) | ((uint32_t)n_words << 20);
         if (H2_NO_REUSE || wkey0 != cur_wkey0 || wkey1 != cur_wkey1) {
           for (int t = tid; t < n_words; t += nthr) {
-            wgt[t] = make_uint2((t < T[0]) ? g_h2_xpow32[kind[0]][T[0] - 1 - t] : 0u,
-                                (t < T[1]) ? g_h2_xpow32[kind[1]][T[1] - 1 - t] : 0u);
+            const uint32_t wa = (t < T[0]) ? g_h2_xpow32[kind[0]][T[0] - 1 - t] : 0u;
+            const uint32_t wb = (t < T[1]) ? g_h2_xpow32[kind[1]][T[1] - 1 - t] : 0u;
+            wgt[t]            = make_uint2(__byte_perm(wa, wb, 0x5410), __byte_perm(wa, wb, 0x7632));
           }
           for (int idx = tid; idx < 64; idx += nthr) {
             const int h = idx >> 5, k = idx & 31;
