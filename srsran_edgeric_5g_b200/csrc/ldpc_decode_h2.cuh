@@ -345,8 +345,6 @@ __device__ __forceinline__ void sweep128(const hh* soft, const uint2* wgt, int n
 {
   const int      l8  = lane_id & 7, grp = lane_id >> 3;
   const uint32_t sh3 = 28u - 4u * (uint32_t)l8;                         // shift of the lane's LAST bit: 31 - (4 l8 + 3)
-  const uint32_t bitpos = 8u * (uint32_t)(l8 >> 1) + ((l8 & 1) ? 0u : 4u); // of the lane's nibble in the little-endian word
-  const uint32_t gmask  = 0xffu << (8 * grp);
   // CRC: a lane keeps its four bit positions inside a word for the whole sweep, so the shift by 31 - b is applied once
   // at the end: per bit and step only "accumulator ^= weight & mask", on both codeblocks at once (the weights are stored
   // as {low halves of A and B, high halves of A and B}, the masks are one 16-bit half per codeblock).
@@ -373,8 +371,16 @@ __device__ __forceinline__ void sweep128(const hh* soft, const uint2* wgt, int n
       // nibbles {A: bits 0-3, B: bits 16-19}, first position in the most significant bit
       const uint32_t one = 0x00010001u;
       const uint32_t nib = ((hm[0] & one) << 3) | ((hm[1] & one) << 2) | ((hm[2] & one) << 1) | (hm[3] & one);
-      const uint32_t wa  = __reduce_or_sync(gmask, (nib & 0xfu) << bitpos);
-      const uint32_t wb  = __reduce_or_sync(gmask, ((nib >> 16) & 0xfu) << bitpos);
+      // Eight lanes -> one word per codeblock with three full-warp exchanges (nibbles -> bytes -> halves -> words), both
+      // codeblocks travelling in one register (a group-masked redux.sync makes the four groups of a warp take turns).
+      const uint32_t n1  = __shfl_xor_sync(0xffffffffu, nib, 1);
+      const uint32_t by  = (l8 & 1) ? ((n1 << 4) | nib) : ((nib << 4) | n1);   // A: bits 0-7, B: bits 16-23
+      const uint32_t b2  = __shfl_xor_sync(0xffffffffu, by, 2);
+      const uint32_t hf  = (l8 & 2) ? (b2 | (by << 8)) : (by | (b2 << 8));     // A: bits 0-15, B: bits 16-31
+      const uint32_t h4  = __shfl_xor_sync(0xffffffffu, hf, 4);
+      const uint32_t wlo = (l8 & 4) ? h4 : hf, whi = (l8 & 4) ? hf : h4;       // bytes 0-1 and 2-3 of the word
+      const uint32_t wa  = __byte_perm(wlo, whi, 0x5410);
+      const uint32_t wb  = __byte_perm(wlo, whi, 0x7632);
       if (l8 == 0) {
         if (out[0] != nullptr) {
           reinterpret_cast<uint32_t*>(out[0])[t] = wa;
