@@ -292,12 +292,16 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
                 for _ in range(3):
                     fn()
                 torch.cuda.synchronize()
-                e0.record(stream)
-                for _ in range(reps):
-                    fn()
-                e1.record(stream)
-                torch.cuda.synchronize()
-                times[label] = e0.elapsed_time(e1) / reps * 1e3
+                best = None
+                for _ in range(3):  # tiny kernels: a busy host shows up as launch gaps; keep the best of three passes
+                    e0.record(stream)
+                    for _ in range(reps):
+                        fn()
+                    e1.record(stream)
+                    torch.cuda.synchronize()
+                    t = e0.elapsed_time(e1) / reps * 1e3
+                    best = t if best is None else min(best, t)
+                times[label] = best
             same = bool((d_sch[:cells * n_llr].cpu().numpy() == np.tile(llrs, cells)).all())
             tres = d_tres.cpu().numpy().view(capi.TB_RESULT_DTYPE)  # results of the deferred chain (ran last)
             deferred_ok = bool(tres["tb_crc_ok"].all()) and bool((d_tb.cpu().numpy()[:tbs_bits // 8] == tb).all()) and \
