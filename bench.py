@@ -716,6 +716,33 @@ def encode_leg(ctx, orc, capi, torch, stream, args):
         out[f"{cells}_tb"] = {"us": us, "info_gbps": cells * tbs_bits / (us * 1e-6) / 1e9,
                               "coded_gbps": cells * n_llr / (us * 1e-6) / 1e9, "codeblocks": int(cbs.size),
                               "equals_oracle": ok}
+        # The same batch with packed output (PDC_ENC_PACKED: eight bits per byte, each codeblock byte aligned): what a
+        # bit_buffer consumer takes, an eighth of the bytes to store and to bring back.
+        cbs_p = cbs.copy()
+        cbs_p["flags"] = capi.ENC_PACKED
+        nbytes = (cbs_p["rm_length"].astype(np.int64) + 7) // 8
+        cbs_p["out_offset"] = np.concatenate(([0], np.cumsum(nbytes)[:-1]))
+        d_cbs_p = torch.from_numpy(cbs_p.view(np.uint8)).cuda()
+        d_out_p = torch.zeros(int(nbytes.sum()) + 16, dtype=torch.uint8, device="cuda")
+
+        def step_p():
+            ctx.launch_encode_device(d_cbs_p.data_ptr(), cbs_p.size, d_msgs.data_ptr(), d_out_p.data_ptr(),
+                                     int(nbytes.sum()), 384, True, cuda_stream=stream.cuda_stream)
+
+        for _ in range(3):
+            step_p()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(reps):
+            step_p()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        got_p = d_out_p.cpu().numpy()
+        ok_p = all(bool((got_p[int(o):int(o) + int(n)] ==
+                         np.packbits(want[m.cw_offset:m.cw_offset + m.rm_length])).all())
+                   for o, n, m in zip(cbs_p["out_offset"], nbytes, metas * cells))
+        out[f"{cells}_tb"]["us_packed_output"] = e0.elapsed_time(e1) / reps * 1e3
+        out[f"{cells}_tb"]["packed_equals_oracle"] = ok_p
     if Reference.available():
         ref = Reference()
         t0 = time.perf_counter()
@@ -735,6 +762,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the early-stop / config-3 / cpu legs")
     ap.add_argument("--only-slots", action="store_true", help="profiling aid: run only the config-3/4/5 slot legs")
     ap.add_argument("--only-config5", action="store_true", help="profiling aid: run only the config-5 slot leg")
+    ap.add_argument("--only-encode", action="store_true", help="profiling aid: run only the downlink-twin leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
 
@@ -759,6 +787,12 @@ def main():
     from srsran_edgeric_5g_b200 import capi
 
     orc = Oracle()
+    if args.only_encode:
+        ctx2 = capi.Context(device=local_rank, max_cbs=64, max_llrs=1 << 20, harq_entries=64, max_tbs=16,
+                            max_tb_bytes=1 << 20, nof_streams=1)
+        print(json.dumps(encode_leg(ctx2, orc, capi, torch, torch.cuda.current_stream(), args)))
+        ctx2.close()
+        return
     if args.only_config5:
         ctx2 = capi.Context(device=local_rank, max_cbs=64, max_llrs=1 << 20, harq_entries=64, max_tbs=16,
                             max_tb_bytes=1 << 20, nof_streams=1)

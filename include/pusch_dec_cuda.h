@@ -197,9 +197,14 @@ typedef struct {
  * Downlink twin: one codeblock to encode and rate match. Carries the fields of codeblock_metadata
  * (include/srsran/phy/upper/codeblock_metadata.h:42-80) the encoder and the rate matcher read.
  */
+/* pdc_enc_desc.flags: the codeblock's output is packed, eight bits per byte, first bit in the most significant bit:    */
+/* (rm_length + 7) / 8 bytes at out_offset, the unused bits of the last byte zero (what a bit_buffer / the packed span  */
+/* of hal::hw_accelerator_pdsch_enc::dequeue_operation holds): an eighth of the bytes on the way back to the host.       */
+#define PDC_ENC_PACKED 1u
+
 typedef struct {
   uint32_t msg_offset;   /* byte offset of the codeblock's K message bits (packed MSB first, filler bits as zeros)      */
-  uint32_t out_offset;   /* where its rate-matched bits start in the output (one bit per byte)                          */
+  uint32_t out_offset;   /* where its rate-matched bits start in the output: byte offset (one bit per byte, or packed)  */
   uint32_t rm_length;    /* E: number of rate-matched bits (multiple of qm)                                             */
   uint32_t nref;         /* limited-buffer length N_ref, 0 = unlimited                                                  */
   uint16_t lifting_size; /* Z                                                                                           */
@@ -207,7 +212,7 @@ typedef struct {
   uint8_t  base_graph;   /* 1 or 2                                                                                      */
   uint8_t  qm;           /* bits per symbol of the bit interleaver: 1, 2, 4, 6, 8                                       */
   uint8_t  rv;           /* redundancy version 0..3                                                                     */
-  uint8_t  reserved;
+  uint8_t  flags;        /* PDC_ENC_*                                                                                   */
 } pdc_enc_desc;
 
 typedef struct {

@@ -64,7 +64,8 @@ DEMOD_X86, DEMOD_SCALAR = 0, 1
 # pdc_enc_desc (downlink twin: LDPC encoding + rate matching)
 ENC_DESC_DTYPE = np.dtype([("msg_offset", "<u4"), ("out_offset", "<u4"), ("rm_length", "<u4"), ("nref", "<u4"),
                            ("lifting_size", "<u2"), ("nof_filler", "<u2"), ("base_graph", "u1"), ("qm", "u1"),
-                           ("rv", "u1"), ("reserved", "u1")])
+                           ("rv", "u1"), ("flags", "u1")])
+ENC_PACKED = 1
 DEMOD_CALL_DTYPE = np.dtype([("sym_offset", "<u4"), ("n_sym", "<u4"), ("llr_offset", "<u4"), ("modulation", "<u4")])
 # pdc_cw_desc / pdc_cw_result (codeword front end)
 CW_DESC_DTYPE = np.dtype([("in_offset", "<u4"), ("sch_offset", "<u4"), ("uci_offset", "<u4"), ("c_init", "<u4"),
@@ -397,11 +398,13 @@ class Context:
     # -- downlink twin ------------------------------------------------------------------------------------------------
     def encode(self, cbs, msgs_packed, out_capacity=None):
         """pdc_encode: LDPC encoding + rate matching of a batch of codeblocks. cbs: ENC_DESC_DTYPE array; msgs_packed: the
-        message bits (packed, each codeblock at its msg_offset). Returns the rate-matched bits, one per byte."""
+        message bits (packed, each codeblock at its msg_offset). Returns the rate-matched bits, one per byte (eight per
+        byte, MSB first, for descriptors flagged ENC_PACKED)."""
         cbs = np.ascontiguousarray(cbs, ENC_DESC_DTYPE)
         msgs_packed = np.ascontiguousarray(msgs_packed, np.uint8)
         if out_capacity is None:
-            out_capacity = int((cbs["out_offset"].astype(np.int64) + cbs["rm_length"]).max())
+            n_out = np.where(cbs["flags"] & ENC_PACKED, (cbs["rm_length"].astype(np.int64) + 7) // 8, cbs["rm_length"])
+            out_capacity = int((cbs["out_offset"].astype(np.int64) + n_out).max())
         out = np.zeros(out_capacity, np.uint8)
         check(self._L.pdc_encode(self.h, _ptr(cbs), cbs.size, _ptr(msgs_packed), msgs_packed.size, _ptr(out), out.size))
         return out

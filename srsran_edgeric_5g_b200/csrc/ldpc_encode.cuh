@@ -37,7 +37,7 @@ __device__ __forceinline__ int enc_wrap(int t, int Z)
   return (t >= Z) ? t - Z : t;
 }
 
-// mode 0: encode + rate match (E bits at out_offset); mode 1: the whole codeword, N = (n_full - 2) Z bits at out_offset
+// mode 0: encode + rate match (E bits at out_offset, one per byte, or packed for PDC_ENC_PACKED); mode 1: the whole codeword, N = (n_full - 2) Z bits at out_offset
 // (ldpc_encoder::encode alone).
 __global__ void __launch_bounds__(ENC_MAX_THREADS) ldpc_encode_rm_kernel(EncodeParams prm, int mode)
 {
@@ -188,6 +188,30 @@ __global__ void __launch_bounds__(ENC_MAX_THREADS) ldpc_encode_rm_kernel(EncodeP
   }
   const int c0  = (k0e < f_lo) ? k0e : k0e - Fp; // compressed coordinate of the start
   const int per = E / qm;
+  if (d.flags & PDC_ENC_PACKED) {
+    // Eight output bits per thread step, first bit in the most significant bit; the last byte is zero padded.
+    const int nbytes = (E + 7) >> 3;
+    for (int bi = tid; bi < nbytes; bi += nthr) {
+      const int o0 = 8 * bi;
+      int       i = o0 / qm, jj = o0 - i * qm;
+      uint32_t  v = 0;
+#pragma unroll 1
+      for (int bit = 0; bit != 8; ++bit) {
+        if (o0 + bit < E) {
+          const int k   = jj * per + i;
+          const int ci  = (c0 + k) % L;
+          const int pos = (ci < f_lo) ? ci : ci + Fp;
+          v |= (uint32_t)(c[2 * Z + pos] & 1u) << (7 - bit);
+        }
+        if (++jj == qm) {
+          jj = 0;
+          ++i;
+        }
+      }
+      out[bi] = (uint8_t)v;
+    }
+    return;
+  }
   for (int o = tid; o < E; o += nthr) {
     const int i = o / qm, jj = o - i * qm;
     const int k = jj * per + i;               // index in the selected (not yet interleaved) sequence

@@ -1615,8 +1615,9 @@ static bool enc_desc_valid(const pdc_enc_desc& d, int mode, size_t msg_bytes, si
   }
   const int qm  = d.qm;
   const int Ncb = (d.nref > 0) ? std::min<int>((int)d.nref, N) : N;
-  if (!(qm == 1 || qm == 2 || qm == 4 || qm == 6 || qm == 8) || d.rm_length % qm != 0 ||
-      (size_t)d.out_offset + d.rm_length > out_capacity) {
+  const size_t out_bytes = (d.flags & PDC_ENC_PACKED) ? ((size_t)d.rm_length + 7) / 8 : (size_t)d.rm_length;
+  if (!(qm == 1 || qm == 2 || qm == 4 || qm == 6 || qm == 8) || d.rm_length % qm != 0 || (d.flags & ~PDC_ENC_PACKED) != 0 ||
+      (size_t)d.out_offset + out_bytes > out_capacity) {
     return false;
   }
   // A circular buffer that ends inside or before the filler bits is not a configuration the standard produces.
@@ -1659,7 +1660,9 @@ static int encode_sync(pdc_ctx*            ctx,
   }
   // Only the codeblocks' own ranges are written back.
   for (uint32_t i = 0; i != n_cb; ++i) {
-    const size_t n = (mode == 1) ? (size_t)((cbs[i].base_graph == 1) ? 66 : 50) * cbs[i].lifting_size : cbs[i].rm_length;
+    const size_t n = (mode == 1) ? (size_t)((cbs[i].base_graph == 1) ? 66 : 50) * cbs[i].lifting_size
+                     : (cbs[i].flags & PDC_ENC_PACKED) ? ((size_t)cbs[i].rm_length + 7) / 8
+                                                       : (size_t)cbs[i].rm_length;
     if (n != 0) {
       PDC_CUDA(cudaMemcpyAsync(out + cbs[i].out_offset, ctx->d_enc_out + cbs[i].out_offset, n, cudaMemcpyDeviceToHost,
                                nullptr));

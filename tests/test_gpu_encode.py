@@ -43,12 +43,16 @@ def test_encode_and_rate_match_random_codeblocks(ctx, orc):
             msg = rng.integers(0, 2, K).astype(np.uint8)
             msg[K - F:] = 0
             cw = orc.ldpc_encode(bg, Z, msg)
-            want.append((out_off, orc.rate_match(cw, E, rv, qm, nref, F)))
-            cbs[i] = (msg_off, out_off, E, nref, Z, F, bg, qm, rv, 0)
+            rm = orc.rate_match(cw, E, rv, qm, nref, F)
+            # Every other codeblock or so asks for packed output (eight bits per byte, MSB first, zero padded).
+            pk = capi.ENC_PACKED if rng.random() < 0.5 else 0
+            w = np.packbits(rm) if pk else rm
+            want.append((out_off, w))
+            cbs[i] = (msg_off, out_off, E, nref, Z, F, bg, qm, rv, pk)
             packed = np.packbits(msg)
             msgs.append(packed)
             msg_off += packed.size
-            out_off += E + int(rng.integers(0, 5))
+            out_off += w.size + int(rng.integers(0, 5))
         out = ctx.encode(cbs, np.concatenate(msgs), out_capacity=out_off + 8)
         for off, w in want:
             assert (out[off:off + w.size] == w).all(), trial
@@ -108,3 +112,11 @@ def test_invalid_descriptors_are_rejected(ctx):
     cbs[0] = (0, 0, 101, 0, 16, 0, 1, 2, 0, 0)  # E is not a multiple of qm
     with pytest.raises(capi.PdcError):
         ctx.encode(cbs, np.zeros(64, np.uint8), out_capacity=200)
+    cbs[0] = (0, 0, 100, 0, 16, 0, 1, 2, 0, 2)  # unknown flag
+    with pytest.raises(capi.PdcError):
+        ctx.encode(cbs, np.zeros(64, np.uint8), out_capacity=200)
+    cbs[0] = (0, 190, 100, 0, 16, 0, 1, 2, 0, capi.ENC_PACKED)  # 13 packed bytes at 190 do not fit in 200
+    with pytest.raises(capi.PdcError):
+        ctx.encode(cbs, np.zeros(64, np.uint8), out_capacity=200)
+    cbs[0] = (0, 187, 100, 0, 16, 0, 1, 2, 0, capi.ENC_PACKED)  # ... at 187 they do
+    ctx.encode(cbs, np.zeros(64, np.uint8), out_capacity=200)
