@@ -971,6 +971,10 @@ def main():
             "share_of_step": kt["ldpc_decode"] / (kt["ldpc_decode"] + kt["rate_dematch"]),
             "peak_source": "pdc_measure_int_peak on this device: %.1f (ALU pipe) / %.1f (ALU+FMA pipes) Tera 32-bit "
                            "lane-op/s; x4 int8 lanes" % (int_peak_alu / 1e12, int_peak_both / 1e12),
+            # The same kernel against the HBM roofline, to show which bound it is NOT near: N soft bits read + K bits and a
+            # result written per codeblock against the measured copy bandwidth.
+            "hbm_view": {"bound": "hbm", "achieved": n_cb * (N_SOFT + 1056 + 4) / dec_s / 1e9, "peak": pk["hbm_gbs"],
+                         "unit": "GB/s", "frac": n_cb * (N_SOFT + 1056 + 4) / dec_s / 1e9 / pk["hbm_gbs"]},
         }
         dm_bytes = n_cb * (N_SOFT + N_SOFT)  # new data: read E, write N
         dm_s = kt["rate_dematch"] * 1e-3
