@@ -40,6 +40,22 @@ def test_struct_layouts_match_the_header():
         assert capi.CB_DESC_DTYPE.fields[f][1] == getattr(capi.CbDesc, f).offset
 
 
+def test_constants_match_the_header():
+    """Every PDC_* value the header defines and the Python mirror also names (with or without the prefix) is the same."""
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    defines = {}
+    for name, value in re.findall(r"^#define\s+(PDC_[A-Z0-9_]+)\s+\(?(-?(?:0x[0-9a-fA-F]+|\d+))u?\)?\s*$", text, flags=re.M):
+        defines[name] = int(value, 0)
+    assert len(defines) >= 30
+    checked = 0
+    for name, value in defines.items():
+        for mirror in (name, name[len("PDC_"):]):
+            if hasattr(capi, mirror):
+                assert getattr(capi, mirror) == value, f"{name}: header {value}, capi.{mirror} {getattr(capi, mirror)}"
+                checked += 1
+    assert checked >= 20
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
