@@ -187,6 +187,27 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def c_abi_latency(cbs, tbd, llrs, tb_bytes, slots):
+    """Single-slot latency of pdc_submit + pdc_wait from C++ (tools/latency_probe.cpp, built by __graft_entry__.build()):
+    host clock from soft bits in page-locked memory to TB bytes and flags back, without Python between the calls. None if
+    the program was not built."""
+    import subprocess
+    import tempfile
+    exe = ROOT / "tools" / "_build" / "latency_probe"
+    if not exe.exists():
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = [os.path.join(tmp, n) for n in ("cbs.bin", "tbs.bin", "llrs.bin")]
+        for path, arr in zip(paths, (cbs, tbd, llrs)):
+            np.ascontiguousarray(arr).tofile(path)
+        try:
+            run = subprocess.run([str(exe)] + paths + [str(int(tb_bytes)), str(int(slots))], capture_output=True, text=True,
+                                 timeout=120)
+            return json.loads(run.stdout.strip().splitlines()[-1]) if run.returncode == 0 else {"error": run.stderr[-200:]}
+        except Exception as e:  # a measurement aid must not take the bench down
+            return {"error": repr(e)}
+
+
 def slot_legs(ctx, orc, capi, torch, stream, args):
     """Config 3 (one 100 MHz 273-PRB 256QAM 4-layer slot: TBS 1 277 992 bits, 152 codeblocks, E = 8960/8992, gNB-style
     Nref) and config 4 (16 such cells in one batch), resident, including TB concatenation and TB CRC on the device."""
@@ -246,6 +267,9 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
                 "us_per_slot": us, "value": cells * tbs_bits / (us * 1e-6) / 1e9, "unit": UNIT, "codeblocks": n_cb,
                 "rows_per_cb": int(res["nlayers"].max()), "mean_iters": float(res["iters"].mean()),
                 "tb_crc_ok": tb_ok, "tb_bytes_match": tb_match, "snr_db": 8.4}
+            lat = c_abi_latency(cbs, tbd, np.tile(llrs, cells), cells * tb_stride, 1000 if cells == 1 else 300)
+            if lat is not None:
+                out[f"{name}_{'early_stop' if early else 'fixed6'}"]["latency_us_c_abi"] = lat
             if early:
                 continue
             # ---- the same slot entered one step earlier: scrambled codewords as the soft demapper
@@ -654,6 +678,9 @@ def config5_leg(ctx, orc, capi, torch, stream, args):
            "tb_crc_ok": tb_ok, "tb_bytes_match": match,
            "latency_us_host_buffers": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                                        "slots": 1000, "path": "pdc_submit + pdc_wait"}}
+    lat_c = c_abi_latency(cbs, tbd, llr_all, tb_off + 64, 1000)
+    if lat_c is not None:
+        leg["latency_us_c_abi"] = lat_c
     if Reference.available():
         # the reference's own software decoder on the same slot, one thread (what a zmq-mode gNB spends per slot)
         t_ref = []
