@@ -99,6 +99,14 @@ struct Queue {
   FrontEnd     fe;
   cudaStream_t stream = nullptr;
   cudaEvent_t  done   = nullptr;
+  // Descriptors {transport blocks, codeblocks} and results {transport blocks, codeblocks} are one block each, on the
+  // device and in page-locked host memory: one copy in and one copy out per batch instead of two (a small copy costs a
+  // few microseconds of latency whatever its size). d_tbs / d_cbs / d_tb_res / d_cb_res point into the blocks.
+  uint8_t* d_desc = nullptr;
+  uint8_t* h_desc = nullptr;
+  uint8_t* d_res  = nullptr;
+  uint8_t* h_res  = nullptr;
+  size_t   tb_desc_area = 0, tb_res_area = 0; // bytes in front of the codeblock part
   // Device staging.
   pdc_cb_desc*   d_cbs     = nullptr;
   int8_t*        d_llrs    = nullptr;
@@ -514,20 +522,26 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
   for (Queue& q : ctx->queues) {
     PDC_CREATE(cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking));
     PDC_CREATE(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
-    PDC_CREATE(dev_alloc(&q.d_cbs, cfg->max_cbs));
+    q.tb_desc_area = (sizeof(pdc_tb_desc) * cfg->max_tbs + 15) & ~(size_t)15;
+    q.tb_res_area  = (sizeof(pdc_tb_result) * cfg->max_tbs + 15) & ~(size_t)15;
+    PDC_CREATE(dev_alloc(&q.d_desc, q.tb_desc_area + sizeof(pdc_cb_desc) * cfg->max_cbs));
+    PDC_CREATE(dev_alloc(&q.d_res, q.tb_res_area + sizeof(pdc_cb_result) * cfg->max_cbs));
+    q.d_tbs    = reinterpret_cast<pdc_tb_desc*>(q.d_desc);
+    q.d_cbs    = reinterpret_cast<pdc_cb_desc*>(q.d_desc + q.tb_desc_area);
+    q.d_tb_res = reinterpret_cast<pdc_tb_result*>(q.d_res);
+    q.d_cb_res = reinterpret_cast<pdc_cb_result*>(q.d_res + q.tb_res_area);
     PDC_CREATE(dev_alloc(&q.d_llrs, (size_t)cfg->max_llrs + 16));
-    PDC_CREATE(dev_alloc(&q.d_tbs, cfg->max_tbs));
-    PDC_CREATE(dev_alloc(&q.d_cb_res, cfg->max_cbs));
     PDC_CREATE(dev_alloc(&q.d_cb_bits, (size_t)cfg->max_cbs * PDC_MAX_CB_BYTES));
-    PDC_CREATE(dev_alloc(&q.d_tb_res, cfg->max_tbs));
     PDC_CREATE(dev_alloc(&q.d_tb_out, (size_t)cfg->max_tb_bytes + 16));
     PDC_CREATE(dev_alloc(&q.d_tb_sync, 2 * (size_t)ctx->tb_sync_entries));
     PDC_CREATE(cudaMemset(q.d_tb_sync, 0, 2 * (size_t)ctx->tb_sync_entries * sizeof(uint32_t)));
-    PDC_CREATE(host_alloc(&q.h_cbs, cfg->max_cbs));
-    PDC_CREATE(host_alloc(&q.h_tbs, cfg->max_tbs));
-    PDC_CREATE(host_alloc(&q.h_cb_res, cfg->max_cbs));
+    PDC_CREATE(host_alloc(&q.h_desc, q.tb_desc_area + sizeof(pdc_cb_desc) * cfg->max_cbs));
+    PDC_CREATE(host_alloc(&q.h_res, q.tb_res_area + sizeof(pdc_cb_result) * cfg->max_cbs));
+    q.h_tbs    = reinterpret_cast<pdc_tb_desc*>(q.h_desc);
+    q.h_cbs    = reinterpret_cast<pdc_cb_desc*>(q.h_desc + q.tb_desc_area);
+    q.h_tb_res = reinterpret_cast<pdc_tb_result*>(q.h_res);
+    q.h_cb_res = reinterpret_cast<pdc_cb_result*>(q.h_res + q.tb_res_area);
     PDC_CREATE(host_alloc(&q.h_cb_bits, (size_t)cfg->max_cbs * PDC_MAX_CB_BYTES));
-    PDC_CREATE(host_alloc(&q.h_tb_res, cfg->max_tbs));
     PDC_CREATE(host_alloc(&q.h_tb_out, (size_t)cfg->max_tb_bytes + 16));
   }
 #undef PDC_CREATE
@@ -569,20 +583,16 @@ void pdc_destroy(pdc_ctx* ctx)
     if (q.done) {
       cudaEventDestroy(q.done);
     }
-    cudaFree(q.d_cbs);
+    cudaFree(q.d_desc);
+    cudaFree(q.d_res);
     cudaFree(q.d_llrs);
-    cudaFree(q.d_tbs);
-    cudaFree(q.d_cb_res);
     cudaFree(q.d_cb_bits);
-    cudaFree(q.d_tb_res);
     cudaFree(q.d_tb_out);
     cudaFree(q.d_tb_sync);
     free_front_end(q.fe);
-    cudaFreeHost(q.h_cbs);
-    cudaFreeHost(q.h_tbs);
-    cudaFreeHost(q.h_cb_res);
+    cudaFreeHost(q.h_desc);
+    cudaFreeHost(q.h_res);
     cudaFreeHost(q.h_cb_bits);
-    cudaFreeHost(q.h_tb_res);
     cudaFreeHost(q.h_tb_out);
   }
   cudaFree(ctx->d_harq);
@@ -703,13 +713,16 @@ int pdc_submit(pdc_ctx*           ctx,
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   BatchShape shape = scan_batch(cbs, n_cb);
   memcpy(q.h_cbs, cbs, sizeof(pdc_cb_desc) * n_cb);
-  PDC_CUDA(cudaMemcpyAsync(q.d_cbs, q.h_cbs, sizeof(pdc_cb_desc) * n_cb, cudaMemcpyHostToDevice, q.stream));
+  if (n_tb != 0) {
+    // Transport-block and codeblock descriptors in one copy (they are one block: {TB area, codeblocks}).
+    memcpy(q.h_tbs, tbs, sizeof(pdc_tb_desc) * n_tb);
+    PDC_CUDA(cudaMemcpyAsync(q.d_desc, q.h_desc, q.tb_desc_area + sizeof(pdc_cb_desc) * n_cb, cudaMemcpyHostToDevice,
+                             q.stream));
+  } else {
+    PDC_CUDA(cudaMemcpyAsync(q.d_cbs, q.h_cbs, sizeof(pdc_cb_desc) * n_cb, cudaMemcpyHostToDevice, q.stream));
+  }
   if (n_llrs != 0 && llrs != nullptr) {
     PDC_CUDA(cudaMemcpyAsync(q.d_llrs, llrs, n_llrs, cudaMemcpyHostToDevice, q.stream));
-  }
-  if (n_tb != 0) {
-    memcpy(q.h_tbs, tbs, sizeof(pdc_tb_desc) * n_tb);
-    PDC_CUDA(cudaMemcpyAsync(q.d_tbs, q.h_tbs, sizeof(pdc_tb_desc) * n_tb, cudaMemcpyHostToDevice, q.stream));
   }
   // Codeblocks that are not decoded report "not run".
   PDC_CUDA(cudaMemsetAsync(q.d_cb_res, 0, sizeof(pdc_cb_result) * n_cb, q.stream));
@@ -724,7 +737,12 @@ int pdc_submit(pdc_ctx*           ctx,
   if (rc != PDC_OK) {
     return rc;
   }
-  PDC_CUDA(cudaMemcpyAsync(q.h_cb_res, q.d_cb_res, sizeof(pdc_cb_result) * n_cb, cudaMemcpyDeviceToHost, q.stream));
+  if (n_tb != 0) {
+    // Transport-block and codeblock results in one copy.
+    PDC_CUDA(cudaMemcpyAsync(q.h_res, q.d_res, q.tb_res_area + sizeof(pdc_cb_result) * n_cb, cudaMemcpyDeviceToHost, q.stream));
+  } else {
+    PDC_CUDA(cudaMemcpyAsync(q.h_cb_res, q.d_cb_res, sizeof(pdc_cb_result) * n_cb, cudaMemcpyDeviceToHost, q.stream));
+  }
   // Outputs go straight to page-locked caller buffers; pageable ones are filled from the pinned staging in pdc_wait.
   const bool direct_bits = cb_bits && is_pinned_host(cb_bits);
   const bool direct_tb   = tb_bytes && n_tb != 0 && is_pinned_host(tb_bytes);
@@ -733,7 +751,6 @@ int pdc_submit(pdc_ctx*           ctx,
                              cudaMemcpyDeviceToHost, q.stream));
   }
   if (n_tb != 0) {
-    PDC_CUDA(cudaMemcpyAsync(q.h_tb_res, q.d_tb_res, sizeof(pdc_tb_result) * n_tb, cudaMemcpyDeviceToHost, q.stream));
     if (tb_bytes) {
       PDC_CUDA(cudaMemcpyAsync(direct_tb ? tb_bytes : q.h_tb_out, q.d_tb_out, tb_out_bytes, cudaMemcpyDeviceToHost,
                                q.stream));
