@@ -724,8 +724,10 @@ int pdc_submit(pdc_ctx*           ctx,
   if (n_llrs != 0 && llrs != nullptr) {
     PDC_CUDA(cudaMemcpyAsync(q.d_llrs, llrs, n_llrs, cudaMemcpyHostToDevice, q.stream));
   }
-  // Codeblocks that are not decoded report "not run".
-  PDC_CUDA(cudaMemsetAsync(q.d_cb_res, 0, sizeof(pdc_cb_result) * n_cb, q.stream));
+  // Codeblocks that are not decoded report "not run": the rate dematcher clears the result array when it runs.
+  if (!shape.any_dematch) {
+    PDC_CUDA(cudaMemsetAsync(q.d_cb_res, 0, sizeof(pdc_cb_result) * n_cb, q.stream));
+  }
   if (q.fe.pending) {
     int rc_fe = front_end_kernels(ctx, q.fe, q.stream);
     if (rc_fe != PDC_OK) {

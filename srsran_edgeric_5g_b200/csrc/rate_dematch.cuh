@@ -572,6 +572,12 @@ __global__ void __launch_bounds__(DM_THREADS, 8) rate_dematch_kernel(BatchParams
   // Launched with programmatic serialization: the descriptor was uploaded before the previous kernel began; everything
   // else (soft bits of the front end, the codeblock-to-codeword map, HARQ entries a decoder may still be reading) waits.
   pdl_wait();
+  if (tid == 0 && blockIdx.y == 0 && prm.results != nullptr) {
+    // "Not run" until the decoder says otherwise: saves the batch a separate clear of the result array.
+    pdc_cb_result none;
+    none.crc_ok = 0, none.iters = 0, none.status = 0, none.nlayers = 0;
+    prm.results[cb] = none;
+  }
   if (!(d.flags & PDC_CB_DEMATCH)) {
     return;
   }
