@@ -59,3 +59,42 @@ def test_reference_ldpc_encoder_benchmark_with_cuda_factory():
     out = subprocess.run([str(exe), "-T", "cuda", "-R", "5"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "LDPC encoder cuda" in out.stdout
+
+
+def test_cpp_client_of_the_c_abi(orc, tmp_path):
+    """tools/latency_probe.cpp (pdc_create / pdc_host_alloc / pdc_submit / pdc_wait from C++, nothing but the header): a
+    two-codeblock transport block encoded by the oracle, ideal soft bits, decoded and assembled through the C ABI."""
+    import json
+    import subprocess
+    from pathlib import Path
+
+    import numpy as np
+
+    from srsran_edgeric_5g_b200 import capi, ldpc
+    exe = Path(__file__).resolve().parent.parent / "tools" / "_build" / "latency_probe"
+    if not exe.exists():
+        pytest.skip("tools/_build/latency_probe not built (__graft_entry__.build())")
+    rng = np.random.default_rng(5)
+    bg, qm, nl, tb_bytes = 1, 6, 2, 1800
+    tbs_bits = tb_bytes * 8
+    n_llr = int(np.ceil(tbs_bits / 0.6 / qm / nl)) * nl * qm
+    C = ldpc.compute_nof_codeblocks(tbs_bits, bg)
+    assert C == 2
+    nref = ldpc.compute_N_ref(tb_bytes, C)
+    tb = rng.integers(0, 256, tb_bytes).astype(np.uint8)
+    cw, _ = orc.tb_encode(tb, bg, 0, qm, nref, nl, n_llr)
+    llrs = np.where(cw == 0, 40, -40).astype(np.int8)
+    flags = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA | capi.CB_EARLY_STOP
+    cbs = np.zeros(C, capi.CB_DESC_DTYPE)
+    for k, m in enumerate(ldpc.segment_rx(tbs_bits, bg, 0, qm, nref, nl, n_llr)):
+        cbs[k] = (m.cw_offset, m.rm_length, k, nref, m.lifting_size, m.nof_filler_bits, bg, qm, 0, capi.CRC24B, 6, flags, 0)
+    tbd = np.zeros(1, capi.TB_DESC_DTYPE)
+    tbd[0] = (0, C, tbs_bits, 0, 0)
+    paths = []
+    for name, arr in (("cbs.bin", cbs), ("tbs.bin", tbd), ("llrs.bin", llrs)):
+        paths.append(str(tmp_path / name))
+        arr.tofile(paths[-1])
+    run = subprocess.run([str(exe)] + paths + [str(tb_bytes + 8), "20"], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stderr
+    res = json.loads(run.stdout.strip().splitlines()[-1])
+    assert res["tb_crc_ok"] is True and res["codeblocks"] == 2 and res["transport_blocks"] == 1 and res["p50"] > 0
