@@ -3,7 +3,10 @@
 // flags back in host memory" (SURVEY 8d). The batch (descriptors and soft bits) comes from files bench.py writes, so the
 // transport blocks are valid codewords and every stage of the chain does its full work.
 //
-//   latency_probe <cbs.bin> <tbs.bin> <llrs.bin> <tb_bytes_per_batch> <slots> [device]
+//   latency_probe <cbs.bin> <tbs.bin> <llrs.bin> <tb_bytes_per_batch> <slots> [device] [want_cb_bits]
+//
+// With transport blocks in the batch the codeblock hard bits are not brought back unless want_cb_bits is 1 (the transport
+// block is assembled on the device; a gNB only needs its bytes and the flags).
 //
 // Prints one JSON object. Only include/pusch_dec_cuda.h is needed to build it.
 #include "pusch_dec_cuda.h"
@@ -74,12 +77,13 @@ int main(int argc, char** argv)
   const pdc_cb_desc*         cbs = reinterpret_cast<const pdc_cb_desc*>(cb_raw.data());
   const pdc_tb_desc*         tbs = reinterpret_cast<const pdc_tb_desc*>(tb_raw.data());
 
+  const bool want_bits = (n_tb == 0) || (argc > 7 && atoi(argv[7]) != 0);
   std::vector<double> lat;
   lat.reserve((size_t)slots);
   bool all_ok = true;
   for (int i = 0; i != slots + 20; ++i) {
     const auto t0 = std::chrono::steady_clock::now();
-    int rc = pdc_submit(ctx, 0, cbs, n_cb, llrs, n_llr, tbs, n_tb, cb_res.data(), bits, tb_res.data(), tbo);
+    int rc = pdc_submit(ctx, 0, cbs, n_cb, llrs, n_llr, tbs, n_tb, cb_res.data(), want_bits ? bits : nullptr, tb_res.data(), tbo);
     if (rc == PDC_OK) {
       rc = pdc_wait(ctx, 0);
     }
@@ -102,9 +106,9 @@ int main(int argc, char** argv)
   }
   mean /= (double)lat.size();
   printf("{\"p50\": %.2f, \"p99\": %.2f, \"min\": %.2f, \"mean\": %.2f, \"slots\": %d, \"codeblocks\": %u, "
-         "\"transport_blocks\": %u, \"tb_crc_ok\": %s, \"path\": \"C++: pdc_submit + pdc_wait, page-locked host buffers\"}\n",
+         "\"transport_blocks\": %u, \"cb_bits_copied_back\": %s, \"tb_crc_ok\": %s, \"path\": \"C++: pdc_submit + pdc_wait, page-locked host buffers\"}\n",
          lat[lat.size() / 2], lat[std::min(lat.size() - 1, (size_t)((double)lat.size() * 0.99))], lat.front(), mean, slots, n_cb,
-         n_tb, all_ok ? "true" : "false");
+         n_tb, want_bits ? "true" : "false", all_ok ? "true" : "false");
   pdc_host_free(llrs);
   pdc_host_free(bits);
   pdc_host_free(tbo);
