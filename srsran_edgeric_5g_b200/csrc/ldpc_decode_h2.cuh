@@ -19,6 +19,7 @@
 
 #include "pdc_device.cuh"
 #include <cuda_fp16.h>
+#include <utility>
 
 namespace pdc {
 namespace h2 {
@@ -65,11 +66,16 @@ constexpr hh H_544   = 0x60406040u; // promotion slope: 121 * 544 overflows, 120
 constexpr hh H_N65280 = 0xFBF8FBF8u;
 constexpr hh H_0P8   = 0x3A663A66u; // 0.7998046875
 constexpr hh H_N0P6  = 0xB8CDB8CDu; // -0.60009765625
+constexpr hh H_1023P5 = 0x63FF63FFu; // 1023.5
+constexpr hh H_2M13  = 0x08000800u; // 2^-13
 
 // Compressed check-to-variable messages of one (row, check), both codeblocks: one 128-bit word.
-//   rows of degree <= 16: {scaled min1 (half2), scaled min2 (half2), flags of edges 0-7, flags of edges 8-15}
-//   rows of degree 19   : {scaled minima as bytes {m1 A, m1 B, m2 A, m2 B}, flags 0-7, flags 8-15, flags 16-18}
-// A flag word holds, per codeblock half, {"held the minimum" : 8 | "negative" : 8}, first edge of the group in the MSB.
+//   rows of degree <= 16: {scaled min1 (half2), scaled min2 (half2), "negative" flags, index of the minimum (half2)}
+//   rows of degree 19   : {scaled minima as bytes {m1 A, m1 B, m2 A, m2 B}, flags of edges 0-15, flags of edges 16-18,
+//                          index of the minimum}
+// A flag word holds, per codeblock half, one bit per edge: edges 0-7 of the word in bits 7..0 (first edge in bit 7),
+// edges 8-15 in bits 15..8; the bits above a single group are don't-care. The index of the edge whose message is min2
+// is kept as a small integer in half precision (compared with HSET2, selected with one LOP3).
 typedef uint4 RowState;
 
 __device__ __forceinline__ hh& st_word(RowState& s, int k)
@@ -164,26 +170,41 @@ __device__ __forceinline__ void row_barrier()
   asm volatile("barrier.sync 0;" ::: "memory");
 }
 
-// One base-graph row (layer) of degree DEG for check j of both codeblocks. Contains the barrier that orders the row after
-// the previous one.
-//   e_info : shared-window address of the row's edge table
-//   st     : in: compressed messages of this row from the previous iteration; out: those of the NEXT row (fetched from
-//            sp_next as soon as this row's are consumed). This row's new messages are stored to sp.
-template <int DEG>
-__device__ __forceinline__ void process_row(uint32_t e_info, uint32_t j4, uint32_t neg_Z4, RowState& st, uint4* sp,
-                                            const uint4* sp_next, uint64_t pol, int scale_mode, bool need_barrier)
+// Bit pattern of the half-precision number e (0 <= e < 1024), in both halves.
+__host__ __device__ constexpr hh half2_of_small_int(int e)
 {
-  RowState st_out = make_uint4(0, 0, 0, 0);
+  if (e == 0) {
+    return 0u;
+  }
+  int ex = 0;
+  while ((2 << ex) <= e) {
+    ++ex;
+  }
+  const uint32_t h = ((uint32_t)(15 + ex) << 10) | (((uint32_t)e - (1u << ex)) << (10 - ex));
+  return h * 0x00010001u;
+}
+static_assert(half2_of_small_int(1) == 0x3C003C00u && half2_of_small_int(3) == 0x42004200u &&
+                  half2_of_small_int(18) == 0x4C804C80u,
+              "half-precision encoding of small integers");
+
+// The arithmetic of one base-graph row (layer) of degree DEG for one check of both codeblocks, given the shared-window
+// addresses of the row's soft words (formed by the caller BEFORE the barrier that orders the row after the previous one:
+// they do not depend on it, so the wait overlaps useful work).
+//   st    : in: compressed messages of this row from the previous iteration; out: those of the NEXT row (fetched from
+//           sp_next as soon as this row's are consumed). This row's new messages are stored to sp.
+//   SCALE : PDC_SCALE_X86 / PDC_SCALE_GENERIC compiled in, or -1: scale_mode decides at run time.
+template <int DEG, int SCALE>
+__device__ __forceinline__ void row_math(const uint32_t (&addr)[DEG], RowState& st, uint4* sp, const uint4* sp_next,
+                                         uint64_t pol, int scale_mode)
+{
   constexpr bool PACKED_MIN = DEG > 16;
   constexpr int  F0         = PACKED_MIN ? 1 : 2; // index of the first flag word
 
-  __half2  vc[DEG]; // soft - c2v_old clamped to +-120, infinite if the soft bit was infinite
-  uint32_t addr[DEG];
+  __half2 vc[DEG]; // soft - c2v_old clamped to +-120, infinite if the soft bit was infinite
 
-  const __half2 one = H(H_ONE), neg1 = H(H_NEG1), h120 = H(H_120), hn120 = H(H_N120), hn230 = H(H_N230);
+  const __half2 one = H(H_ONE), h120 = H(H_120), hn120 = H(H_N120);
 
-  // Old scaled minima. -mag_old = z * hd - mid with z = -1 for the edge that held the minimum (its message was min2),
-  // +1 otherwise (min1).
+  // Old scaled minima: the message of an edge has magnitude min1, that of the edge which held the minimum min2.
   __half2 m1, m2;
   if (PACKED_MIN) {
     m1 = __hadd2(H(__byte_perm(st.x, 0x64646464u, 0x4140)), H(H_N1024));
@@ -192,11 +213,122 @@ __device__ __forceinline__ void process_row(uint32_t e_info, uint32_t j4, uint32
     m1 = H(st.x);
     m2 = H(st.y);
   }
-  const __half2 mid = __hmul2(__hadd2(m1, m2), H(H_HALF));
-  const __half2 hd  = __hmul2(__hsub2(m2, m1), H(H_HALF));
+  const __half2 d12 = __hsub2(m1, m2);
+  const __half2 idx_old = H(st.w);
 
-  // Soft-word addresses of the row's edges: independent of the previous row, so they are formed BEFORE the barrier that
-  // orders this row after the previous one (the wait then overlaps useful work).
+  __half2 min1 = h120, min2 = h120, a_prev = h120;
+  hh      par = 0;
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    const hh      f    = st_word(st, F0 + (e >> 4));
+    const hh      ps   = f << ((e & 8) ? (e & 7) : 8 + (e & 7)); // "negative" flag of this edge in the sign position
+    const __half2 s    = H(lds_u32(addr[e]));
+    const __half2 eq   = __heq2(idx_old, H(half2_of_small_int(e)));
+    const __half2 sg   = H(lop_and_or(ps, H_SIGN, H_ONE));
+    const __half2 nmag = __hfma2(eq, d12, __hneg2(m1)); // -min2 for the edge that held the minimum, -min1 otherwise
+    const __half2 v    = __hfma2(sg, nmag, s);          // s - c2v_old; |v| <= 222, or infinite with s
+    // Clamp to +-120 but keep infinity: v * 2^-13 is less than half a unit in the last place of the clamped value for
+    // every finite v (|v| <= 222), so the sum rounds back to it, and infinite for an infinite v.
+    const __half2 c = __hfma2(v, H(H_2M13), __hmax2(__hmin2(v, h120), hn120));
+    vc[e]           = c;
+    par ^= U(c);
+    // Two smallest magnitudes of the row, edges taken in pairs (shorter dependency chain, three-input minimum).
+    const __half2 a = __habs2(c);
+    if ((e & 1) == 0 && e != DEG - 1) {
+      a_prev = a;
+    } else if (e == 1) {
+      // first pair: the minima start at 120 (an infinite magnitude counts as 120)
+      min1 = __hmin2(__hmin2(a_prev, a), h120);
+      min2 = __hmin2(__hmax2(a_prev, a), h120);
+    } else if (e & 1) {
+      const __half2 lo = __hmin2(a_prev, a), hi = __hmax2(a_prev, a);
+      min2             = __hmin2(__hmin2(min2, hi), __hmax2(min1, lo));
+      min1             = __hmin2(min1, lo);
+    } else {
+      min2 = __hmin2(min2, __hmax2(min1, a));
+      min1 = __hmin2(min1, a);
+    }
+  }
+
+  // This row's old messages are consumed: fetch those of the next row into the same registers.
+  st = ld_state(sp_next, pol);
+
+  // Scaled minima (SURVEY 8a R10). x86: (x * 52428) >> 16 == ceil(0.8 x) - 1 for x >= 1, 0 for x = 0;
+  // generic: round(0.8 x). Both are computed exactly through round-to-nearest in the [1024, 2048) binade.
+  __half2 s1, s2;
+  if ((SCALE < 0) ? (scale_mode == PDC_SCALE_X86) : (SCALE == PDC_SCALE_X86)) {
+    // 0.7998 x + 1023.5 rounds (once, in the binade of 1024) to 1024 + ceil(0.8 x) - 1 for every x in 1..120 and stays
+    // 1023.5 for x = 0, which the relu of the subtraction turns into 0.
+    s1 = __hfma2_relu(__hfma2(min1, H(H_0P8), H(H_1023P5)), one, H(H_N1024));
+    s2 = __hfma2_relu(__hfma2(min2, H(H_0P8), H(H_1023P5)), one, H(H_N1024));
+  } else {
+    s1 = __hadd2(__hfma2(min1, H(H_0P8), H(H_1024)), H(H_N1024));
+    s2 = __hadd2(__hfma2(min2, H(H_0P8), H(H_1024)), H(H_N1024));
+  }
+  const hh par_s = lop_and_or(par, H_SIGN, H_ONE);
+
+  // Pass 2 is balanced between the two math pipes: the magnitude select and the index of the minimum are bit operations
+  // on the comparison mask (ALU pipe), the message sum, the promotion and the sign flags are packed half-precision
+  // arithmetic (FMA pipe).
+  const hh s_diff = U(s1) ^ U(s2);
+  __half2  acc_s  = H(H_ZERO);
+  hh       idx    = 0;
+  hh       grp[3] = {0, 0, 0};
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    const __half2 c    = vc[e];
+    const hh      ism  = __heq2_mask(__habs2(c), min1);       // 0xffff per half if this edge holds the minimum
+    const __half2 mag  = H(lop_xor_and(U(s1), ism, s_diff));  // min2 for the minimum edge, min1 otherwise (scaled)
+    const __half2 sgn  = H(lop_xor_and(par_s, U(c), H_SIGN)); // +-1: sign parity of the row without this edge
+    const __half2 x    = __hfma2(sgn, mag, c);
+    // Promotion (LLR.cpp:74-87): |x| > 120 -> +-infinity. pe = relu(544 |x| - 65280) is 0 up to |x| = 120 and at
+    // least 544 from 121 on, where x * pe + x exceeds the half-precision range; an infinite x stays infinite.
+    const __half2 pe = __hfma2_relu(__habs2(x), H(H_544), H(H_N65280));
+    const __half2 r  = __hfma2(x, pe, x);
+    sts_u32(addr[e], U(r));
+    acc_s = __hfma2(acc_s, H(H_TWO), sgn);                    // sum of +-2^k; turned into "negative" bits below
+    // index of an edge that holds the minimum (with several, min2 == min1 and any of them serves): (ism & e) | (~ism & idx)
+    {
+      asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(idx) : "r"(ism), "r"(half2_of_small_int(e)), "r"(idx));
+    }
+    if ((e & 7) == 7 || e == DEG - 1) {
+      // acc_s = sum over the n edges of the group of sgn * 2^(n-1-k): negative-edge bits = ((2^n - 1) - acc_s) / 2,
+      // left-aligned for a partial group and converted to an integer byte through the 1024 binade (bits 7..0 of each
+      // half; the bits above are the exponent of 1024: don't-care for a reader that shifts its flag to the sign bit).
+      const int     n_in_group = (e & 7) + 1;
+      const int     fill       = 8 - n_in_group;
+      const float   full       = (float)((1 << n_in_group) - 1) * 0.5f * (float)(1 << fill);
+      const __half2 sc         = H(0x38003800u + (uint32_t)fill * 0x04000400u); // 0.5 * 2^fill
+      if (n_in_group < 8) {
+        // full + 1024 is an integer below 2048: one fused operation
+        grp[e >> 3] = U(__hfma2(acc_s, __hneg2(sc), __float2half2_rn(full + 1024.0f)));
+      } else {
+        grp[e >> 3] = U(__hadd2(__hfma2(acc_s, __hneg2(sc), __float2half2_rn(full)), H(H_1024)));
+      }
+      acc_s                    = H(H_ZERO);
+    }
+  }
+  RowState st_out;
+  if (PACKED_MIN) {
+    st_out.x = __byte_perm(U(__hadd2(s1, H(H_1024))), U(__hadd2(s2, H(H_1024))), 0x6420);
+    st_out.y = __byte_perm(grp[0], grp[1], 0x6240);
+    st_out.z = grp[2];
+  } else {
+    st_out.x = U(s1);
+    st_out.y = U(s2);
+    st_out.z = (DEG > 8) ? __byte_perm(grp[0], grp[1], 0x6240) : grp[0];
+  }
+  st_out.w = idx;
+  st_state(sp, st_out, pol);
+}
+
+// Table-driven row: the addresses of the row's soft words come from the edge table in shared memory.
+//   e_info : shared-window address of the row's edge table
+template <int DEG>
+__device__ __forceinline__ void process_row(uint32_t e_info, uint32_t j4, uint32_t neg_Z4, RowState& st, uint4* sp,
+                                            const uint4* sp_next, uint64_t pol, int scale_mode, bool need_barrier)
+{
+  uint32_t addr[DEG];
   {
     uint4 ei = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -212,98 +344,7 @@ __device__ __forceinline__ void process_row(uint32_t e_info, uint32_t j4, uint32
   if (need_barrier) {
     row_barrier();
   }
-
-  __half2 min1 = h120, min2 = h120, a_prev = h120;
-  hh      par = 0, ps = 0, pm = 0;
-#pragma unroll
-  for (int e = 0; e != DEG; ++e) {
-    if ((e & 7) == 0) {
-      hh f = st_word(st, F0 + (e >> 3));
-      pm   = f;      // "held the minimum" flags: bit 15 of each half = edge e, then e+1, ... after each shift
-      ps   = f << 8; // sign flags
-    }
-    const __half2 s    = H(lds_u32(addr[e]));
-    const __half2 z    = H(lop_and_or(pm, H_SIGN, H_ONE));
-    const __half2 sg   = H(lop_and_or(ps, H_SIGN, H_ONE));
-    const __half2 nmag = __hfma2(z, hd, __hneg2(mid));
-    const __half2 v    = __hfma2(sg, nmag, s); // s - c2v_old; |v| <= 222, or infinite with s
-    // Clamp to +-120 but keep infinity: relu(|v| - 230) is 0 for every finite v and infinite otherwise.
-    const __half2 inf = __hfma2_relu(__habs2(v), one, hn230);
-    __half2       c   = __hmax2(__hmin2(v, h120), hn120);
-    c                 = __hfma2(c, inf, c);
-    vc[e]             = c;
-    par ^= U(c);
-    // Two smallest magnitudes of the row, edges taken in pairs (shorter dependency chain, three-input minimum).
-    const __half2 a = __habs2(c);
-    if ((e & 1) == 0 && e != DEG - 1) {
-      a_prev = a;
-    } else if (e & 1) {
-      const __half2 lo = __hmin2(a_prev, a), hi = __hmax2(a_prev, a);
-      min2             = __hmin2(__hmin2(min2, hi), __hmax2(min1, lo));
-      min1             = __hmin2(min1, lo);
-    } else {
-      min2 = __hmin2(min2, __hmax2(min1, a));
-      min1 = __hmin2(min1, a);
-    }
-    pm <<= 1;
-    ps <<= 1;
-  }
-
-  // This row's old messages are consumed: fetch those of the next row into the same registers.
-  st = ld_state(sp_next, pol);
-
-  // Scaled minima (SURVEY 8a R10). x86: (x * 52428) >> 16 == ceil(0.8 x) - 1 for x >= 1, 0 for x = 0;
-  // generic: round(0.8 x). Both are computed exactly through round-to-nearest in the [1024, 2048) binade.
-  __half2 s1, s2;
-  if (scale_mode == PDC_SCALE_X86) {
-    s1 = __hfma2_relu(__hadd2(__hfma2(min1, H(H_0P8), H(H_N0P6)), H(H_1024)), one, H(H_N1024));
-    s2 = __hfma2_relu(__hadd2(__hfma2(min2, H(H_0P8), H(H_N0P6)), H(H_1024)), one, H(H_N1024));
-  } else {
-    s1 = __hadd2(__hfma2(min1, H(H_0P8), H(H_1024)), H(H_N1024));
-    s2 = __hadd2(__hfma2(min2, H(H_0P8), H(H_1024)), H(H_N1024));
-  }
-  const hh      par_s = lop_and_or(par, H_SIGN, H_ONE);
-
-  // Pass 2 is balanced between the two math pipes: the magnitude select and the "held the minimum" flags are bit
-  // operations on the comparison mask (ALU pipe), the message sum, the promotion and the sign flags are packed
-  // half-precision arithmetic (FMA pipe).
-  const hh s_diff = U(s1) ^ U(s2);
-  __half2  acc_s  = H(H_ZERO);
-  hh       acc_m  = 0;
-#pragma unroll
-  for (int e = 0; e != DEG; ++e) {
-    const __half2 c    = vc[e];
-    const hh      ism  = __heq2_mask(__habs2(c), min1);       // 0xffff per half if this edge holds the minimum
-    const __half2 mag  = H(lop_xor_and(U(s1), ism, s_diff));  // min2 for the minimum edge, min1 otherwise (scaled)
-    const __half2 sgn  = H(lop_xor_and(par_s, U(c), H_SIGN)); // +-1: sign parity of the row without this edge
-    const __half2 x    = __hfma2(sgn, mag, c);
-    // Promotion (LLR.cpp:74-87): |x| > 120 -> +-infinity. pe = relu(544 |x| - 65280) is 0 up to |x| = 120 and at
-    // least 544 from 121 on, where x * pe + x exceeds the half-precision range; an infinite x stays infinite.
-    const __half2 pe = __hfma2_relu(__habs2(x), H(H_544), H(H_N65280));
-    const __half2 r  = __hfma2(x, pe, x);
-    sts_u32(addr[e], U(r));
-    acc_s = __hfma2(acc_s, H(H_TWO), sgn);                    // sum of +-2^k; turned into "negative" bits below
-    acc_m = lop_and_or(ism, H_SIGN >> (e & 7), acc_m);        // flag of the first edge of a group in the MSB
-    if ((e & 7) == 7 || e == DEG - 1) {
-      // acc_s = sum over the n edges of the group of sgn * 2^(n-1-k): negative-edge bits = ((2^n - 1) - acc_s) / 2,
-      // left-aligned for a partial group and converted to an integer byte through the 1024 binade.
-      const int     n_in_group = (e & 7) + 1;
-      const int     fill       = 8 - n_in_group;
-      const float   full       = (float)((1 << n_in_group) - 1) * 0.5f * (float)(1 << fill);
-      const __half2 sc         = H(0x38003800u + (uint32_t)fill * 0x04000400u); // 0.5 * 2^fill
-      acc_s                    = __hadd2(__hfma2(acc_s, __hneg2(sc), __float2half2_rn(full)), H(H_1024));
-      st_word(st_out, F0 + (e >> 3)) = lop_and_or(U(acc_s), 0x00ff00ffu, acc_m);
-      acc_s = H(H_ZERO);
-      acc_m = 0;
-    }
-  }
-  if (PACKED_MIN) {
-    st_out.x = __byte_perm(U(__hadd2(s1, H(H_1024))), U(__hadd2(s2, H(H_1024))), 0x6420);
-  } else {
-    st_out.x = U(s1);
-    st_out.y = U(s2);
-  }
-  st_state(sp, st_out, pol);
+  row_math<DEG, -1>(addr, st, sp, sp_next, pol, scale_mode);
 }
 
 __device__ __forceinline__ void dispatch_row(int deg, uint32_t e_info, uint32_t j4, uint32_t neg_Z4, RowState& st,
@@ -329,6 +370,93 @@ __device__ __forceinline__ void dispatch_row(int deg, uint32_t e_info, uint32_t 
     process_row<9>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode, need_barrier);
   } else {
     process_row<10>(e_info, j4, neg_Z4, st, sp, sp_next, pol, scale_mode, need_barrier);
+  }
+}
+
+
+// ---- compile-time row program of the hot shape ----------------------------------------------------------------------
+//
+// For the shapes listed in tools/gen_row_program.py the layered schedule of the leading rows is compiled in: every
+// edge's variable node and circulant shift is an immediate operand, the rows are unrolled, and a third of the edge
+// addresses need no instruction at all (see the generator: per-row thread offset tau_m, extension nodes stored rotated
+// by it). The arithmetic (row_math) is shared with the table-driven rows.
+//
+// How many rows: unrolled code is 16 bytes x ~29 instructions per edge, and the row loop has to stay inside the
+// instruction cache. Measured on B200 (8192 codeblocks BG1 Z = 384, 46 rows, 6 iterations; table-driven loop 4.14 ms):
+// rows 0-3 compiled in 4.13 ms, 0-7 4.03, 0-11 3.92, 0-15 3.84, 0-23 3.82, all 46 (147 KB of code) 6.24 ms. A variant
+// with per-row address stubs jumping into one shared body per degree (41 KB) measured 4.26 ms: the indirect branch per
+// row costs more than the instructions it saves.
+#include "row_programs.inc"
+
+#ifndef H2_SPEC_ROWS
+#define H2_SPEC_ROWS 28
+#endif
+
+template <int... Is, class F>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F&& f)
+{
+  (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+  static_for_impl(std::make_integer_sequence<int, N>{}, f);
+}
+
+// Shared-window address of the soft word edge E of row M reads and writes for thread t.
+//   jb  = soft_s + 4 t          (edges at shift 0 relative to the thread: address = jb + immediate)
+//   jn4 = 4 (t - Z), "negative" (adding 4 d either stays negative - no wrap, 4 Z is added back - or not: the unsigned
+//                                minimum of the two candidates is the wrapped offset)
+template <class P, int M, int E>
+__device__ __forceinline__ uint32_t spec_edge_addr(uint32_t jb, uint32_t jn4, uint32_t soft_s)
+{
+  constexpr int      d  = P::DLT[M][E];
+  constexpr uint32_t cb = (uint32_t)P::COL[M][E] * (uint32_t)P::Z * 4u;
+  if constexpr (d == 0) {
+    return jb + cb;
+  } else {
+    const uint32_t u = jn4 + 4u * (uint32_t)d;
+    return __viaddmin_u32(u, 4u * (uint32_t)P::Z, u) + (soft_s + cb);
+  }
+}
+
+template <class P, int M, int SCALE>
+__device__ __forceinline__ void spec_row(uint32_t jb, uint32_t jn4, uint32_t soft_s, RowState& st, uint4* st_thread,
+                                         int layers, uint64_t pol, int scale_mode)
+{
+  constexpr int DEG    = P::DEG[M];
+  constexpr int STRIDE = (P::Z + 31) & ~31;
+  uint32_t      addr[DEG];
+  static_for<DEG>([&](auto ec) {
+    constexpr int e = decltype(ec)::value;
+    addr[e]         = spec_edge_addr<P, M, e>(jb, jn4, soft_s);
+  });
+  if (!P::NOBAR[M]) {
+    row_barrier();
+  }
+  // The next row in use (its old messages are fetched while this row's are processed).
+  const uint4* spn;
+  if (M + 1 < 4) {
+    spn = st_thread + (M + 1) * STRIDE;
+  } else if (M + 1 == P::ROWS) {
+    spn = st_thread;
+  } else {
+    spn = (M + 1 < layers) ? st_thread + (M + 1) * STRIDE : st_thread;
+  }
+  row_math<DEG, SCALE>(addr, st, st_thread + M * STRIDE, spn, pol, scale_mode);
+}
+
+// Rows M .. END-1 of one iteration; stops after the last row in use (at least four rows are always in use).
+template <class P, int M, int END, int SCALE>
+__device__ __forceinline__ void spec_rows_from(uint32_t jb, uint32_t jn4, uint32_t soft_s, RowState& st,
+                                               uint4* st_thread, int layers, uint64_t pol, int scale_mode)
+{
+  if constexpr (M < END) {
+    if (M >= 4 && M >= layers) {
+      return;
+    }
+    spec_row<P, M, SCALE>(jb, jn4, soft_s, st, st_thread, layers, pol, scale_mode);
+    spec_rows_from<P, M + 1, END, SCALE>(jb, jn4, soft_s, st, st_thread, layers, pol, scale_mode);
   }
 }
 
@@ -467,7 +595,9 @@ __host__ __device__ inline size_t h2_smem_bytes(int bg, int Z)
   return soft + bits + sizeof(GraphSmem) + 64;
 }
 
-template <int MAX_THREADS, int MIN_BLOCKS>
+// SPEC_Z: lifting size whose BG1 row program is compiled in (0: none); pairs of any other shape take the table-driven
+// row loop of the same kernel.
+template <int MAX_THREADS, int MIN_BLOCKS, int SPEC_Z>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
     ldpc_decode_h2_kernel(BatchParams prm, hh* state_scratch, uint32_t scratch_stride_words, uint32_t* work_counter,
                           uint32_t counter_base)
@@ -569,6 +699,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       const int          K       = kb * Z;
       const int          N       = (n_full - 2) * Z;
       const int          n_words = (K + 31) / 32;
+      const bool         spec    = (SPEC_Z != 0) && bg == 1 && Z == SPEC_Z; // the compiled-in row program applies
 
       // Carve shared memory.
       size_t off  = 0;
@@ -744,7 +875,18 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
                 __half2 v = __hadd2(H(x), hn1152);
                 v         = __hmax2(__hmin2(v, h64), hn64);
                 if (4 * q + k < n_load) {
-                  soft[2 * Z + 4 * q + k] = U(v);
+                  int dst = 2 * Z + 4 * q + k;
+                  if constexpr (SPEC_Z != 0) {
+                    // Extension nodes of the compiled-in rows are stored rotated by the row's thread offset
+                    // (tools/gen_row_program.py).
+                    const int c = (4 * q) / SPEC_Z + 2;
+                    if (spec && c >= kb + 4 && c - kb < H2_SPEC_ROWS) {
+                      int pos = 4 * q + k - (c - 2) * SPEC_Z - (int)ROWPROG_1_384_TAU[c - kb];
+                      pos += (pos < 0) ? SPEC_Z : 0;
+                      dst = c * SPEC_Z + pos;
+                    }
+                  }
+                  soft[dst] = U(v);
                 }
               }
             }
@@ -784,9 +926,21 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       const uint32_t einfo_s    = (uint32_t)__cvta_generic_to_shared(g.einfo);
       const uint32_t row_info_s = (uint32_t)__cvta_generic_to_shared(g.row_info);
       RowState       st         = make_uint4(0, 0, 0, 0);
+      const uint32_t jb = soft_s + j4, jn4 = j4 - 4u * (uint32_t)Z;
       for (int it = 0; it < max_iter; ++it) {
         uint4* sp = st_thread;
-        for (int m = 0; m < layers; ++m) {
+        int    m0 = 0;
+        if constexpr (SPEC_Z != 0) {
+          if (spec) {
+            // The leading rows of the hot shape run from the compiled-in program, the rest from the tables.
+            // (the kernel with a compiled-in program is only launched for the x86 scale rule)
+            spec_rows_from<RowProgram<1, (SPEC_Z != 0 ? SPEC_Z : 384)>, 0, H2_SPEC_ROWS, PDC_SCALE_X86>(
+                jb, jn4, soft_s, st, st_thread, layers, pol_keep, scale_mode);
+            m0 = min(layers, H2_SPEC_ROWS);
+            sp = (m0 < layers) ? st_thread + (uint32_t)m0 * st_stride : st_thread;
+          }
+        }
+        for (int m = m0; m < layers; ++m) {
           if (active) {
             const uint32_t info = lds_u32(row_info_s + 4u * (uint32_t)m);
             const int      e0   = info & 0xffffu;
@@ -931,8 +1085,19 @@ struct H2Plan {
   int    grid;
   size_t smem;
   size_t scratch_words_per_cta;
-  bool   big; // the 384-thread instantiation (two CTAs per SM)
+  bool   big;  // the 384-thread instantiation (two CTAs per SM)
+  bool   spec; // ... with the BG1 Z = 384 row program compiled in
 };
+
+// PDC_NO_SPEC=1: table-driven row loop for every shape (A/B measurements, tests of the general path).
+inline bool h2_no_spec()
+{
+  static const bool v = [] {
+    const char* e = getenv("PDC_NO_SPEC");
+    return e != nullptr && e[0] == '1';
+  }();
+  return v;
+}
 
 // Builds the per-(base graph, lifting size) images the kernel copies (after upload_tables, once per context).
 inline cudaError_t upload_h2_images()
@@ -977,7 +1142,26 @@ inline cudaError_t upload_h2_images()
 
 typedef void (*h2_kernel_t)(BatchParams, uint32_t*, uint32_t, uint32_t*, uint32_t);
 
-inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count, H2Plan& plan)
+// The dynamic shared-memory limit is an attribute of a kernel PER DEVICE: set once per context (pdc_create, with the
+// context's device current) to the largest size any batch can ask for.
+inline cudaError_t h2_configure_device()
+{
+  const int   big = (int)h2::h2_smem_bytes(1, 384), small = (int)h2::h2_smem_bytes(1, 192);
+  cudaError_t e   = cudaFuncSetAttribute((h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2, 384>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) {
+    e = cudaFuncSetAttribute((h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2, 0>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  }
+  if (e == cudaSuccess) {
+    e = cudaFuncSetAttribute((h2_kernel_t)h2::ldpc_decode_h2_kernel<192, 4, 0>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+  }
+  return e;
+}
+
+inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count, H2Plan& plan,
+                           int scale_mode = PDC_SCALE_X86)
 {
   const int bg               = any_bg1 ? 1 : 2;
   plan.threads               = ((max_Z + 31) / 32) * 32;
@@ -985,16 +1169,10 @@ inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count,
   const int rows             = (bg == 1) ? 46 : 42;
   plan.scratch_words_per_cta = (size_t)rows * 4 * ((max_Z + 31) & ~31);
   plan.big                   = plan.threads > 192;
-  h2_kernel_t   k            = plan.big ? (h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2>
-                                        : (h2_kernel_t)h2::ldpc_decode_h2_kernel<192, 4>;
-  static size_t configured[2] = {0, 0};
-  if (plan.smem > configured[plan.big]) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-    if (e != cudaSuccess) {
-      return e;
-    }
-    configured[plan.big] = plan.smem;
-  }
+  plan.spec                  = plan.big && any_bg1 && max_Z == 384 && scale_mode == PDC_SCALE_X86 && !h2_no_spec();
+  h2_kernel_t   k            = plan.spec  ? (h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2, 384>
+                               : plan.big ? (h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2, 0>
+                                          : (h2_kernel_t)h2::ldpc_decode_h2_kernel<192, 4, 0>;
   int         per_sm = 0;
   cudaError_t e      = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, plan.threads, plan.smem);
   if (e != cudaSuccess) {
@@ -1025,10 +1203,15 @@ inline cudaError_t launch_ldpc_decode_h2(const BatchParams& p, const H2Plan& pla
   cfg.attrs                                          = attr;
   cfg.numAttrs                                       = 1;
   const uint32_t stride = (uint32_t)plan.scratch_words_per_cta;
-  if (plan.big) {
-    return cudaLaunchKernelEx(&cfg, h2::ldpc_decode_h2_kernel<384, 2>, p, scratch, stride, work_counter, counter_base);
+  if (plan.spec) {
+    return cudaLaunchKernelEx(&cfg, h2::ldpc_decode_h2_kernel<384, 2, 384>, p, scratch, stride, work_counter,
+                              counter_base);
   }
-  return cudaLaunchKernelEx(&cfg, h2::ldpc_decode_h2_kernel<192, 4>, p, scratch, stride, work_counter, counter_base);
+  if (plan.big) {
+    return cudaLaunchKernelEx(&cfg, h2::ldpc_decode_h2_kernel<384, 2, 0>, p, scratch, stride, work_counter,
+                              counter_base);
+  }
+  return cudaLaunchKernelEx(&cfg, h2::ldpc_decode_h2_kernel<192, 4, 0>, p, scratch, stride, work_counter, counter_base);
 }
 
 } // namespace pdc

@@ -302,6 +302,13 @@ __global__ void ldpc_decode_scalar_kernel(BatchParams prm, const int8_t* direct_
   }
 }
 
+// Per device, once per context (see h2_configure_device).
+inline cudaError_t scalar_configure_device()
+{
+  return cudaFuncSetAttribute(ldpc_decode_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)decode_smem_bytes(1, MAX_Z));
+}
+
 inline cudaError_t launch_ldpc_decode(const BatchParams& p, int max_Z, int max_bg_rows68, const int8_t* direct_in,
                                       uint32_t direct_n, cudaStream_t s)
 {
@@ -311,15 +318,6 @@ inline cudaError_t launch_ldpc_decode(const BatchParams& p, int max_Z, int max_b
   int    bg      = max_bg_rows68 ? 1 : 2;
   size_t smem    = decode_smem_bytes(bg, max_Z);
   int    threads = ((max_Z + 31) / 32) * 32;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(ldpc_decode_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      return e;
-    }
-    configured = smem;
-  }
   ldpc_decode_scalar_kernel<<<p.n_cb, threads, smem, s>>>(p, direct_in, direct_n);
   return cudaGetLastError();
 }

@@ -18,6 +18,8 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <list>
+#include <mutex>
 
 namespace {
 
@@ -159,7 +161,11 @@ struct pdc_ctx {
     uint32_t*    d_counter = nullptr;
     uint32_t     counter_base = 0; // value of *d_counter once the launches queued so far have run
   };
-  std::vector<DecodeScratch> decode_scratch;
+  // One entry per queue stream is created (and fully sized) by pdc_create, so nothing is allocated on the launch path of
+  // the queued interface; streams of pdc_launch_device callers get theirs on first use. A list: entries never move, so
+  // a launch may keep a pointer to its entry while another thread appends one; the lookup / append is under the mutex.
+  std::list<DecodeScratch> decode_scratch;
+  std::mutex               decode_scratch_mutex;
   FrontEnd             fe_sync;                   // buffers of the synchronous front-end calls
   // Downlink twin (synchronous calls): grow-only device staging.
   unsigned char*       d_enc_cbs = nullptr;
@@ -214,6 +220,63 @@ static cudaError_t grow_device(T** p, size_t* cap, size_t need)
   return e;
 }
 
+// Row-state scratch + ticket counter of the persistent decoder for stream s, holding at least `need` words. Queue
+// streams find their entry pre-sized (pdc_create); a foreign stream (pdc_launch_device) allocates on first use.
+cudaError_t decode_scratch_for(pdc_ctx* ctx, cudaStream_t s, size_t need, pdc_ctx::DecodeScratch** out)
+{
+  pdc_ctx::DecodeScratch* sc = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(ctx->decode_scratch_mutex);
+    for (pdc_ctx::DecodeScratch& c : ctx->decode_scratch) {
+      if (c.stream == s) {
+        sc = &c;
+      }
+    }
+    if (sc == nullptr) {
+      ctx->decode_scratch.emplace_back();
+      sc         = &ctx->decode_scratch.back();
+      sc->stream = s;
+    }
+  }
+  // From here on the entry belongs to the caller: a stream is driven by one thread at a time.
+  if (sc->d_counter == nullptr) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&sc->d_counter), sizeof(uint32_t));
+    if (e == cudaSuccess) {
+      e = cudaMemsetAsync(sc->d_counter, 0, sizeof(uint32_t), s);
+    }
+    if (e != cudaSuccess) {
+      return e;
+    }
+    sc->counter_base = 0;
+  }
+  if (need > sc->words) {
+    cudaFree(sc->d_state); // synchronises the device: only on the first batch of a foreign stream
+    sc->d_state   = nullptr;
+    sc->words     = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&sc->d_state), need * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+      return e;
+    }
+    sc->words = need;
+  }
+  *out = sc;
+  return cudaSuccess;
+}
+
+// Largest row-state scratch any batch can ask for on this device: the launch plan of every lifting size with all
+// resident CTAs in use.
+size_t decode_scratch_max_words(int sm_count)
+{
+  size_t words = 0;
+  for (int i = 0; i != NR_LDPC_NOF_LIFTING_SIZES; ++i) {
+    pdc::H2Plan plan;
+    if (pdc::h2_plan(pdc::NR_LDPC_LIFTING_SIZES[i], true, 0x7fffffffu, sm_count, plan) == cudaSuccess) {
+      words = std::max(words, plan.scratch_words_per_cta * (size_t)plan.grid);
+    }
+  }
+  return words;
+}
+
 // Launches the kernels of one batch on stream s. All pointers are device pointers.
 int launch_batch(pdc_ctx*             ctx,
                  const pdc_cb_desc*   d_cbs,
@@ -266,31 +329,10 @@ int launch_batch(pdc_ctx*             ctx,
     if (direct_in == nullptr && ctx->cfg.scale_mode != PDC_SCALE_NEON && !ctx->force_scalar) {
       // Throughput kernel: two codeblocks per CTA, half-precision packed arithmetic.
       pdc::H2Plan plan;
-      PDC_CUDA(pdc::h2_plan(shape.max_Z, shape.any_bg1, n_cb, ctx->sm_count, plan));
+      PDC_CUDA(pdc::h2_plan(shape.max_Z, shape.any_bg1, n_cb, ctx->sm_count, plan, ctx->cfg.scale_mode));
       size_t need = plan.scratch_words_per_cta * (size_t)plan.grid;
       pdc_ctx::DecodeScratch* sc = nullptr;
-      for (pdc_ctx::DecodeScratch& c : ctx->decode_scratch) {
-        if (c.stream == s) {
-          sc = &c;
-        }
-      }
-      if (sc == nullptr) {
-        ctx->decode_scratch.emplace_back();
-        sc         = &ctx->decode_scratch.back();
-        sc->stream = s;
-        PDC_CUDA(cudaMalloc(reinterpret_cast<void**>(&sc->d_counter), sizeof(uint32_t)));
-        PDC_CUDA(cudaMemsetAsync(sc->d_counter, 0, sizeof(uint32_t), s));
-      }
-      if (need > sc->words) {
-        // Grow-only; sized once per (largest lifting size) in practice. cudaMalloc synchronises the device.
-        size_t want = plan.scratch_words_per_cta * (size_t)ctx->sm_count * 8;
-        want        = std::max(need, std::min(want, (size_t)1 << 27));
-        PDC_CUDA(cudaFree(sc->d_state));
-        sc->d_state = nullptr;
-        sc->words   = 0;
-        PDC_CUDA(cudaMalloc(reinterpret_cast<void**>(&sc->d_state), want * sizeof(uint32_t)));
-        sc->words = want;
-      }
+      PDC_CUDA(decode_scratch_for(ctx, s, need, &sc));
       // Pairs are handed out dynamically (codeblocks that stop early free their CTA for the next pair).
       {
         cudaError_t e = pdc::launch_ldpc_decode_h2(p, plan, sc->d_state, sc->d_counter, sc->counter_base, s);
@@ -518,9 +560,28 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
   PDC_CREATE(cudaGetLastError());
   ctx->scratch_llr_bytes = 35u * PDC_MAX_CB_BYTES * 8u; // MAX_CODEBLOCK_RM_SIZE (ldpc.h:122)
   PDC_CREATE(dev_alloc(&ctx->d_scratch_llr, ctx->scratch_llr_bytes));
+  // Kernel attributes are per device.
+  PDC_CREATE(pdc::h2_configure_device());
+  PDC_CREATE(pdc::scalar_configure_device());
+  PDC_CREATE(cudaFuncSetAttribute(pdc::ldpc_encode_rm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pdc::enc_smem_bytes(1, pdc::MAX_Z)));
+  // The decoder's row state carries an evict-last policy. PDC_L2_PERSIST=1 additionally gives such lines the largest L2
+  // set-aside the device offers; measured on B200 it does not change the decoder (4.137 vs 4.139 ms per 8192
+  // codeblocks) and costs the rate dematcher a quarter of its speed (0.120 -> 0.154 ms: less L2 for its streams), so it
+  // is off by default.
+  {
+    const char* lp = getenv("PDC_L2_PERSIST");
+    if (lp && lp[0] == '1' && prop.persistingL2CacheMaxSize > 0) {
+      PDC_CREATE(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize));
+    }
+  }
   ctx->queues.resize(cfg->nof_streams);
   for (Queue& q : ctx->queues) {
     PDC_CREATE(cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking));
+    {
+      pdc_ctx::DecodeScratch* sc = nullptr;
+      PDC_CREATE(decode_scratch_for(ctx, q.stream, decode_scratch_max_words(ctx->sm_count), &sc));
+    }
     PDC_CREATE(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
     q.tb_desc_area = (sizeof(pdc_tb_desc) * cfg->max_tbs + 15) & ~(size_t)15;
     q.tb_res_area  = (sizeof(pdc_tb_result) * cfg->max_tbs + 15) & ~(size_t)15;
@@ -1607,11 +1668,6 @@ int pdc_crc(pdc_ctx* ctx, int crc_kind, const uint8_t* packed, uint32_t nbits, u
 static int launch_encode(pdc_ctx* ctx, const pdc::EncodeParams& p, int max_Z, bool any_bg1, int mode, cudaStream_t s)
 {
   const size_t  smem = pdc::enc_smem_bytes(any_bg1 ? 1 : 2, max_Z);
-  static size_t configured = 0;
-  if (smem > configured && smem > 48 * 1024) {
-    PDC_CUDA(cudaFuncSetAttribute(pdc::ldpc_encode_rm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   const int threads = std::min(pdc::ENC_MAX_THREADS, ((max_Z + 31) / 32) * 32);
   pdc::ldpc_encode_rm_kernel<<<p.n_cb, threads, smem, s>>>(p, mode);
   PDC_CUDA(cudaGetLastError());
