@@ -32,6 +32,18 @@ static int to_crc_kind(crc_generator_poly poly)
   }
 }
 
+namespace {
+/// Errors of the synchronous device calls are logged (rate limited), never fatal.
+void log_device_error(const char* what)
+{
+  static std::atomic<unsigned> count{0};
+  unsigned                     n = count.fetch_add(1, std::memory_order_relaxed);
+  if (n < 16 || (n & (n - 1)) == 0) {
+    fmt::print(stderr, "[pusch_dec_cuda] {} failed ({} so far): {}\n", what, n + 1, pdc_last_error());
+  }
+}
+} // namespace
+
 std::shared_ptr<context> context::create(const config& cfg)
 {
   pdc_config c;
@@ -41,11 +53,12 @@ std::shared_ptr<context> context::create(const config& cfg)
   c.max_llrs     = cfg.max_cbs * 12288u;
   c.harq_entries = cfg.harq_entries;
   c.scale_mode   = cfg.scale_mode;
+  c.nof_streams  = std::max(1U, cfg.nof_queues);
   pdc_ctx* h     = nullptr;
   if (pdc_create(&c, &h) != PDC_OK) {
     return nullptr;
   }
-  return std::shared_ptr<context>(new context(h));
+  return std::shared_ptr<context>(new context(h, c.nof_streams));
 }
 
 context::~context()
@@ -80,7 +93,12 @@ std::optional<unsigned> ldpc_decoder_cuda::decode(bit_buffer&                   
                            static_cast<int>(cfg.algorithm_conf.max_iterations),
                            output.get_buffer().data(),
                            &iters);
-  report_fatal_error_if_not(rc == PDC_OK, "pdc_ldpc_decode failed: {}", pdc_last_error());
+  if (rc != PDC_OK) {
+    // A failed device call is reported like a dropped accelerator operation - CRC failure, i.e. no iteration count
+    // (hw_accelerator_pusch_dec_acc100_impl.cpp:176-187, 233-247) - and logged; the gNB keeps running and HARQ recovers.
+    log_device_error("pdc_ldpc_decode");
+    return std::nullopt;
+  }
   if (iters > 0) {
     return static_cast<unsigned>(iters);
   }
@@ -102,14 +120,20 @@ void ldpc_rate_dematcher_cuda::rate_dematch(span<log_likelihood_ratio>       out
                             static_cast<int>(get_bits_per_symbol(cfg.tb_common.mod)),
                             cfg.tb_common.Nref,
                             cfg.cb_specific.nof_filler_bits);
-  report_fatal_error_if_not(rc == PDC_OK, "pdc_rate_dematch failed: {}", pdc_last_error());
+  if (rc != PDC_OK) {
+    // The soft buffer keeps what it held: the codeblock fails its CRC and is retransmitted.
+    log_device_error("pdc_rate_dematch");
+  }
 }
 
 crc_calculator_checksum_t crc_calculator_cuda::calculate_byte(span<const uint8_t> data)
 {
   uint32_t c  = 0;
   int      rc = pdc_crc(ctx->get(), to_crc_kind(poly), data.data(), data.size() * 8, &c);
-  report_fatal_error_if_not(rc == PDC_OK, "pdc_crc failed: {}", pdc_last_error());
+  if (rc != PDC_OK) {
+    log_device_error("pdc_crc");
+    return ~0U; // never the remainder of a message that carries its checksum: the check fails
+  }
   return c;
 }
 
@@ -121,7 +145,10 @@ crc_calculator_checksum_t crc_calculator_cuda::calculate_bit(span<const uint8_t>
   }
   uint32_t c  = 0;
   int      rc = pdc_crc(ctx->get(), to_crc_kind(poly), packed.data(), data.size(), &c);
-  report_fatal_error_if_not(rc == PDC_OK, "pdc_crc failed: {}", pdc_last_error());
+  if (rc != PDC_OK) {
+    log_device_error("pdc_crc");
+    return ~0U; // never the remainder of a message that carries its checksum: the check fails
+  }
   return c;
 }
 
@@ -129,7 +156,10 @@ crc_calculator_checksum_t crc_calculator_cuda::calculate(const bit_buffer& data)
 {
   uint32_t c  = 0;
   int      rc = pdc_crc(ctx->get(), to_crc_kind(poly), data.get_buffer().data(), data.size(), &c);
-  report_fatal_error_if_not(rc == PDC_OK, "pdc_crc failed: {}", pdc_last_error());
+  if (rc != PDC_OK) {
+    log_device_error("pdc_crc");
+    return ~0U; // never the remainder of a message that carries its checksum: the check fails
+  }
   return c;
 }
 
@@ -145,6 +175,7 @@ hw_accelerator_pusch_dec_cuda::hw_accelerator_pusch_dec_cuda(std::shared_ptr<con
 
 hw_accelerator_pusch_dec_cuda::~hw_accelerator_pusch_dec_cuda()
 {
+  ctx->release_queue(queue);
   pdc_host_free(llr_staging);
 }
 
@@ -294,13 +325,18 @@ public:
   explicit hw_accelerator_pusch_dec_factory_cuda(std::shared_ptr<context> c) : ctx(std::move(c)) {}
   std::unique_ptr<hal::hw_accelerator_pusch_dec> create() override
   {
-    // One stream ("hardware queue") per accelerator instance, round robin over the context's streams.
-    return std::make_unique<hw_accelerator_pusch_dec_cuda>(ctx, next_queue++ % 2);
+    // One batch queue ("hardware queue") per accelerator instance, never shared: two PUSCH processors driving one
+    // queue from two threads would find it busy. Beyond the context's queues creation fails, like a hardware
+    // accelerator that ran out of queues (the caller sizes context::config::nof_queues to its PUSCH processors).
+    unsigned q = ctx->claim_queue();
+    if (q == context::no_queue) {
+      return nullptr;
+    }
+    return std::make_unique<hw_accelerator_pusch_dec_cuda>(ctx, q);
   }
 
 private:
   std::shared_ptr<context> ctx;
-  std::atomic<unsigned>    next_queue{0};
 };
 
 } // namespace
@@ -523,11 +559,20 @@ pusch_decoder_batch_cuda::pusch_decoder_batch_cuda(std::shared_ptr<context>     
                                                    std::unique_ptr<ldpc_segmenter_rx> seg) :
   ctx(std::move(c)), queue_id(queue), segmenter(std::move(seg))
 {
+  // queue = context::no_queue: take any free one. A queue is never shared with another batch or accelerator object.
+  if (queue_id == context::no_queue) {
+    queue_id = ctx->claim_queue();
+  } else if (!ctx->claim_queue(queue_id)) {
+    queue_id = context::no_queue;
+  }
+  report_fatal_error_if_not(queue_id != context::no_queue,
+                            "pusch_decoder_batch_cuda: no free batch queue (context::config::nof_queues)");
 }
 
 pusch_decoder_batch_cuda::~pusch_decoder_batch_cuda()
 {
   pdc_wait(ctx->get(), queue_id);
+  ctx->release_queue(queue_id);
   pdc_host_free(llr_staging);
   pdc_host_free(tb_staging);
 }

@@ -42,7 +42,9 @@
 #include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_result.h"
 #include "srsran/phy/upper/unique_rx_buffer.h"
 #include "srsran/phy/upper/channel_processors/pusch/ulsch_demultiplex.h"
+#include <atomic>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <vector>
 
@@ -60,16 +62,54 @@ public:
     unsigned harq_entries = 4096;
     /// Which reference decoder is reproduced bit for bit: PDC_SCALE_X86 (avx2/avx512, "auto" on x86) or generic.
     int scale_mode = PDC_SCALE_X86;
+    /// Batch queues (CUDA streams with their staging buffers): one per hal::hw_accelerator_pusch_dec /
+    /// pusch_decoder_batch_cuda instance, i.e. per concurrent PUSCH processor.
+    unsigned nof_queues = 4;
   };
 
   /// Returns nullptr if no usable GPU is present (there is no software fallback).
   static std::shared_ptr<context> create(const config& cfg);
   ~context();
   pdc_ctx* get() const { return ctx; }
+  unsigned nof_queues() const { return queues; }
+  /// Hands out an unused batch queue, or no_queue when all are taken: queues are never shared between objects, and an
+  /// object gives its queue back when it is destroyed.
+  static constexpr unsigned no_queue = ~0U;
+  unsigned                  claim_queue()
+  {
+    std::lock_guard<std::mutex> lock(queue_mutex);
+    for (unsigned q = 0; q != queues; ++q) {
+      if (!(in_use & (1ULL << q))) {
+        in_use |= 1ULL << q;
+        return q;
+      }
+    }
+    return no_queue;
+  }
+  /// Marks a specific queue as taken (objects constructed with an explicit queue number); false if it already is.
+  bool claim_queue(unsigned q)
+  {
+    std::lock_guard<std::mutex> lock(queue_mutex);
+    if (q >= queues || (in_use & (1ULL << q))) {
+      return false;
+    }
+    in_use |= 1ULL << q;
+    return true;
+  }
+  void release_queue(unsigned q)
+  {
+    std::lock_guard<std::mutex> lock(queue_mutex);
+    if (q < queues) {
+      in_use &= ~(1ULL << q);
+    }
+  }
 
 private:
-  explicit context(pdc_ctx* c) : ctx(c) {}
-  pdc_ctx* ctx;
+  context(pdc_ctx* c, unsigned nq) : ctx(c), queues(nq > 64 ? 64 : nq) {}
+  pdc_ctx*   ctx;
+  unsigned   queues;
+  std::mutex queue_mutex;
+  uint64_t   in_use = 0;
 };
 
 /// LDPC decoder, single-codeblock synchronous call (latency path).

@@ -16,6 +16,8 @@
 #include <functional>
 #include <cstdio>
 #include <random>
+#include <thread>
+#include <atomic>
 
 using namespace srsran;
 
@@ -214,8 +216,84 @@ int main()
     }
   }
 
+  // ---- the same objects from several threads at once -------------------------------------------------------------------
+  // pusch_decoder_impl runs a pool of decoder / dematcher objects on a pool of worker threads (pusch_decoder_impl.cpp:
+  // 309-382, concurrent_thread_local_object_pool.h:41-110): eight threads, each with its own adapter objects on the ONE
+  // shared context, each comparing every result with its own reference software objects.
+  {
+    constexpr int      n_threads = 8;
+    std::atomic<int>   bad{0}, done{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t != n_threads; ++t) {
+      pool.emplace_back([&, t]() {
+        std::mt19937 trng(777 + t);
+        auto dec_sw  = create_ldpc_decoder_factory_sw("auto")->create();
+        auto dec_gpu = cuda::create_ldpc_decoder_factory_cuda(ctx)->create();
+        auto dem_sw  = create_ldpc_rate_dematcher_factory_sw("auto")->create();
+        auto dem_gpu = cuda::create_ldpc_rate_dematcher_factory_cuda(ctx)->create();
+        auto crc_sw  = crc_f->create(crc_generator_poly::CRC24B);
+        auto crc_gpu = cuda::create_crc_calculator_factory_cuda(ctx)->create(crc_generator_poly::CRC24B);
+        for (int trial = 0; trial != 12; ++trial) {
+          unsigned           Zs[] = {384, 96, 52, 13, 7, 256};
+          unsigned           Z    = Zs[(trial + t) % 6];
+          bool               bg1  = (trial + t) % 2;
+          unsigned           N = (bg1 ? 66 : 50) * Z, K = (bg1 ? 22 : 10) * Z;
+          unsigned           qm = 2 + 2 * (trial % 4);
+          unsigned           E  = ((N / 2 + trng() % N) / qm) * qm;
+          codeblock_metadata m;
+          m.tb_common.base_graph        = bg1 ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2;
+          m.tb_common.lifting_size      = static_cast<ldpc::lifting_size_t>(Z);
+          m.tb_common.rv                = trial % 4;
+          m.tb_common.mod               = to_mod(qm);
+          m.tb_common.Nref              = 0;
+          m.cb_specific.full_length     = N;
+          m.cb_specific.rm_length       = E;
+          m.cb_specific.nof_filler_bits = trng() % Z;
+          m.cb_specific.nof_crc_bits    = 24;
+          std::vector<log_likelihood_ratio> llr(E), a(N), b(N);
+          for (auto& v : llr) {
+            v = static_cast<int>(trng() % 61) - 30;
+          }
+          for (unsigned i = 0; i != N; ++i) {
+            a[i] = b[i] = static_cast<int>(trng() % 201) - 100;
+          }
+          dem_sw->rate_dematch(a, llr, trial % 3 != 0, m);
+          dem_gpu->rate_dematch(b, llr, trial % 3 != 0, m);
+          ldpc_decoder::configuration cfg;
+          cfg.block_conf                    = m;
+          cfg.algorithm_conf.max_iterations = 1 + trial % 6;
+          dynamic_bit_buffer o1(K), o2(K);
+          auto               r1 = dec_sw->decode(o1, a, trial % 2 ? crc_sw.get() : nullptr, cfg);
+          auto               r2 = dec_gpu->decode(o2, a, trial % 2 ? crc_gpu.get() : nullptr, cfg);
+          if (!std::equal(a.begin(), a.end(), b.begin()) || r1 != r2 || !(o1 == o2) ||
+              crc_sw->calculate(o1) != crc_gpu->calculate(o1)) {
+            ++bad;
+          }
+          ++done;
+        }
+      });
+    }
+    for (auto& th : pool) {
+      th.join();
+    }
+    CHECK(bad == 0 && done == n_threads * 12, "concurrent single-codeblock adapters: %d of %d calls differ", bad.load(),
+          done.load());
+  }
+
   // ---- the reference's pusch_decoder_hw_impl on the CUDA accelerator vs the reference's software pusch_decoder_impl ----
   auto hw_factory = cuda::create_hw_accelerator_pusch_dec_factory_cuda(ctx);
+  {
+    // One batch queue per accelerator object, never shared; beyond the context's queues creation fails, and a destroyed
+    // object hands its queue back.
+    std::vector<std::unique_ptr<hal::hw_accelerator_pusch_dec>> accs;
+    for (unsigned i = 0; i != ctx->nof_queues(); ++i) {
+      accs.push_back(hw_factory->create());
+      CHECK(accs.back() != nullptr, "accelerator %u of %u not created", i, ctx->nof_queues());
+    }
+    CHECK(hw_factory->create() == nullptr, "an accelerator beyond the context's queues was created");
+    accs.pop_back();
+    CHECK(hw_factory->create() != nullptr, "a released queue was not handed out again");
+  }
   for (int trial = 0; trial != 12; ++trial) {
     int      bg       = (trial % 3) ? 1 : 2;
     int      tb_bytes = 40 + static_cast<int>(rng() % (bg == 1 ? 6000 : 700));
@@ -341,7 +419,8 @@ int main()
       std::unique_ptr<pusch_decoder_impl> sw;
       std::unique_ptr<pusch_decoder>      gpu;
     };
-    auto batch_ptr = std::make_shared<cuda::pusch_decoder_batch_cuda>(ctx, 1, create_ldpc_segmenter_rx_factory_sw()->create());
+    auto batch_ptr = std::make_shared<cuda::pusch_decoder_batch_cuda>(ctx, cuda::context::no_queue,
+                                                                      create_ldpc_segmenter_rx_factory_sw()->create());
     cuda::pusch_decoder_batch_cuda& batch = *batch_ptr;
     auto dec_factory = cuda::create_pusch_decoder_factory_cuda(batch_ptr);
     std::vector<ue_t>              ues(7);

@@ -24,9 +24,15 @@
  *   demodulation_mapper::demodulate_soft  include/srsran/phy/upper/channel_modulation/demodulation_mapper.h:62-65
  *                                         (factory: channel_modulation_factories.h:32-41)
  *
- * Threading: a context serialises nothing itself. Each queue ("stream") may be driven by one thread at a time; the
- * synchronous single-object calls (pdc_ldpc_decode, pdc_rate_dematch, pdc_crc, pdc_ulsch_demux, pdc_scrambling_sequence,
- * pdc_launch_codewords_device, pdc_demodulate_soft, pdc_launch_demod_device) share queue 0 / one set of scratch buffers and must not run concurrently with each other.
+ * Threading: each batch queue ("stream") is driven by one thread at a time (pdc_submit .. pdc_wait of a queue may come
+ * from different threads one after the other; a thread that submits to a queue another thread is submitting to gets
+ * PDC_ERR_CAPACITY). Different queues are independent. The synchronous single-object calls (pdc_ldpc_decode,
+ * pdc_rate_dematch, pdc_crc, pdc_ulsch_demux, pdc_scrambling_sequence, pdc_demodulate_soft, pdc_encode,
+ * pdc_ldpc_encode) may be called from any number of threads - the reference runs pools of decoder / dematcher objects
+ * concurrently (concurrent_thread_local_object_pool.h:41-110): they share one private queue and one set of scratch
+ * buffers inside the context and serialise on a mutex there; they never use the batch queues, so they cannot collide
+ * with a batch in flight. pdc_launch_codewords_device / pdc_launch_demod_device (caller's stream, plan buffers shared
+ * with the synchronous calls) remain one call at a time per context.
  *
  * INTEGRATION.md shows the C++ adapter classes that bind these calls behind create_ldpc_decoder_factory_sw("cuda"),
  * create_ldpc_rate_dematcher_factory_sw("cuda") and the hal::hw_accelerator_pusch_dec factory.
@@ -390,7 +396,6 @@ int pdc_rate_dematch(pdc_ctx*      ctx,
                      uint32_t      nref,
                      uint32_t      nof_filler);
 
-/* crc_calculator::calculate over the first nbits (MSB first) of packed[]. */
 /*
  * The front end on buffers that are already on the device (descriptors on the host: the plan is made there), queued on
  * the caller's CUDA stream: d_raw_llrs -> d_sch (UL-SCH space, feed it to pdc_launch_device as d_llrs) and d_uci
@@ -453,6 +458,8 @@ int pdc_launch_demod_device(pdc_ctx*              ctx,
 /* TS 38.211 5.2.1 pseudo-random sequence c(offset .. offset + n - 1), packed MSB first (pseudo_random_generator::generate). */
 int pdc_scrambling_sequence(pdc_ctx* ctx, uint32_t c_init, uint32_t offset, uint32_t n, uint8_t* packed);
 
+/* crc_calculator::calculate (crc_calculator.h:62-84) over the first nbits (MSB first) of packed[]; crc_kind PDC_CRC16 ..
+ * PDC_CRC6: remainder of the message followed by `order` zero bits, no reflection, no final xor. */
 int pdc_crc(pdc_ctx* ctx, int crc_kind, const uint8_t* packed, uint32_t nbits, uint32_t* checksum);
 
 /* ------------------------------------------------------------------------------------------------------------------ */

@@ -651,7 +651,8 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
             if (ok[h]) {
               const int bg = d[h]->base_graph, Z = d[h]->lifting_size;
               if ((bg != 1 && bg != 2) || Z < 2 || Z > MAX_Z || c_tab.set_index[Z] == 0xff || d[h]->max_iter == 0 ||
-                  d[h]->harq_id >= prm.harq_entries || d[h]->crc_kind > PDC_CRC24B) {
+                  d[h]->harq_id >= prm.harq_entries || d[h]->crc_kind > PDC_CRC24B ||
+                  (int)d[h]->nof_filler >= ((bg == 1) ? 22 : 10) * Z) {
                 if (pass == 0) {
                   pdc_cb_result r;
                   r.crc_ok = 0, r.iters = d[h]->max_iter, r.status = 2, r.nlayers = 0;

@@ -56,7 +56,7 @@ __global__ void ldpc_decode_scalar_kernel(BatchParams prm, const int8_t* direct_
   const int bg = d.base_graph;
   const int Z  = d.lifting_size;
   if ((bg != 1 && bg != 2) || Z < 2 || Z > MAX_Z || c_tab.set_index[Z] == 0xff || d.max_iter == 0 ||
-      d.harq_id >= prm.harq_entries || d.crc_kind > PDC_CRC24B) {
+      d.harq_id >= prm.harq_entries || d.crc_kind > PDC_CRC24B || (int)d.nof_filler >= ((bg == 1) ? 22 : 10) * Z) {
     if (tid == 0) {
       res.status      = 2;
       prm.results[cb] = res;

@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 #include <list>
+#include <memory>
 #include <mutex>
 
 namespace {
@@ -167,6 +168,16 @@ struct pdc_ctx {
   std::list<DecodeScratch> decode_scratch;
   std::mutex               decode_scratch_mutex;
   FrontEnd             fe_sync;                   // buffers of the synchronous front-end calls
+  // The synchronous single-object calls (pdc_ldpc_decode, pdc_rate_dematch, pdc_crc, pdc_demodulate_soft,
+  // pdc_ulsch_demux, pdc_scrambling_sequence, pdc_encode, pdc_ldpc_encode) share fe_sync, d_scratch_llr, the scratch
+  // HARQ entry and this private one-codeblock queue; they may be called from any number of threads (the reference runs
+  // a pool of decoder / dematcher objects concurrently) and serialise on the mutex. They never touch the batch queues,
+  // so they cannot collide with a pdc_submit in flight.
+  Queue                sync_q;
+  std::mutex           sync_mutex;
+  // One mutex per batch queue: pdc_submit .. pdc_wait of a queue may come from different threads one after the other,
+  // and two threads that (against the contract) drive one queue at once get PDC_ERR_CAPACITY instead of corrupting it.
+  std::unique_ptr<std::mutex[]> queue_mutex;
   // Downlink twin (synchronous calls): grow-only device staging.
   unsigned char*       d_enc_cbs = nullptr;
   size_t               enc_cbs_cap = 0;
@@ -477,6 +488,49 @@ cudaError_t upload_crc_tables()
   return cudaMemcpyToSymbol(c_xpow2, h, sizeof(h));
 }
 
+// Streams, device staging and page-locked mirrors of one queue. full_scratch: pre-size the decoder's row-state scratch
+// for the largest batch (batch queues); the one-codeblock queue of the synchronous calls sizes its own on first use.
+cudaError_t create_queue(pdc_ctx* ctx, Queue& q, uint32_t max_cbs, size_t max_llrs, uint32_t max_tbs, size_t max_tb_bytes,
+                         bool full_scratch)
+{
+#define PDC_Q(expr)                                                                                                    \
+  do {                                                                                                                 \
+    cudaError_t e__ = (expr);                                                                                          \
+    if (e__ != cudaSuccess) {                                                                                          \
+      return e__;                                                                                                      \
+    }                                                                                                                  \
+  } while (0)
+  PDC_Q(cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking));
+  {
+    pdc_ctx::DecodeScratch* sc = nullptr;
+    PDC_Q(decode_scratch_for(ctx, q.stream, full_scratch ? decode_scratch_max_words(ctx->sm_count) : 0, &sc));
+  }
+  PDC_Q(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
+  q.tb_desc_area = (sizeof(pdc_tb_desc) * max_tbs + 15) & ~(size_t)15;
+  q.tb_res_area  = (sizeof(pdc_tb_result) * max_tbs + 15) & ~(size_t)15;
+  PDC_Q(dev_alloc(&q.d_desc, q.tb_desc_area + sizeof(pdc_cb_desc) * max_cbs));
+  PDC_Q(dev_alloc(&q.d_res, q.tb_res_area + sizeof(pdc_cb_result) * max_cbs));
+  q.d_tbs    = reinterpret_cast<pdc_tb_desc*>(q.d_desc);
+  q.d_cbs    = reinterpret_cast<pdc_cb_desc*>(q.d_desc + q.tb_desc_area);
+  q.d_tb_res = reinterpret_cast<pdc_tb_result*>(q.d_res);
+  q.d_cb_res = reinterpret_cast<pdc_cb_result*>(q.d_res + q.tb_res_area);
+  PDC_Q(dev_alloc(&q.d_llrs, (size_t)max_llrs + 16));
+  PDC_Q(dev_alloc(&q.d_cb_bits, (size_t)max_cbs * PDC_MAX_CB_BYTES));
+  PDC_Q(dev_alloc(&q.d_tb_out, (size_t)max_tb_bytes + 16));
+  PDC_Q(dev_alloc(&q.d_tb_sync, 2 * (size_t)ctx->tb_sync_entries));
+  PDC_Q(cudaMemset(q.d_tb_sync, 0, 2 * (size_t)ctx->tb_sync_entries * sizeof(uint32_t)));
+  PDC_Q(host_alloc(&q.h_desc, q.tb_desc_area + sizeof(pdc_cb_desc) * max_cbs));
+  PDC_Q(host_alloc(&q.h_res, q.tb_res_area + sizeof(pdc_cb_result) * max_cbs));
+  q.h_tbs    = reinterpret_cast<pdc_tb_desc*>(q.h_desc);
+  q.h_cbs    = reinterpret_cast<pdc_cb_desc*>(q.h_desc + q.tb_desc_area);
+  q.h_tb_res = reinterpret_cast<pdc_tb_result*>(q.h_res);
+  q.h_cb_res = reinterpret_cast<pdc_cb_result*>(q.h_res + q.tb_res_area);
+  PDC_Q(host_alloc(&q.h_cb_bits, (size_t)max_cbs * PDC_MAX_CB_BYTES));
+  PDC_Q(host_alloc(&q.h_tb_out, (size_t)max_tb_bytes + 16));
+#undef PDC_Q
+  return cudaSuccess;
+}
+
 } // namespace
 
 extern "C" {
@@ -565,46 +619,22 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
   PDC_CREATE(pdc::scalar_configure_device());
   PDC_CREATE(cudaFuncSetAttribute(pdc::ldpc_encode_rm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pdc::enc_smem_bytes(1, pdc::MAX_Z)));
-  // The decoder's row state carries an evict-last policy. PDC_L2_PERSIST=1 additionally gives such lines the largest L2
-  // set-aside the device offers; measured on B200 it does not change the decoder (4.137 vs 4.139 ms per 8192
-  // codeblocks) and costs the rate dematcher a quarter of its speed (0.120 -> 0.154 ms: less L2 for its streams), so it
-  // is off by default.
+  // The decoder's row state carries an evict-last policy. PDC_L2_PERSIST_MB=<n> additionally sets n MB of L2 aside for
+  // such lines (0 / unset: the limit is left alone; values above the device maximum are clamped).
   {
-    const char* lp = getenv("PDC_L2_PERSIST");
-    if (lp && lp[0] == '1' && prop.persistingL2CacheMaxSize > 0) {
-      PDC_CREATE(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize));
+    const char* lp = getenv("PDC_L2_PERSIST_MB");
+    const long  mb = lp ? atol(lp) : 0;
+    if (mb > 0 && prop.persistingL2CacheMaxSize > 0) {
+      const size_t want = std::min((size_t)mb << 20, (size_t)prop.persistingL2CacheMaxSize);
+      PDC_CREATE(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
     }
   }
   ctx->queues.resize(cfg->nof_streams);
+  ctx->queue_mutex.reset(new std::mutex[cfg->nof_streams]);
   for (Queue& q : ctx->queues) {
-    PDC_CREATE(cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking));
-    {
-      pdc_ctx::DecodeScratch* sc = nullptr;
-      PDC_CREATE(decode_scratch_for(ctx, q.stream, decode_scratch_max_words(ctx->sm_count), &sc));
-    }
-    PDC_CREATE(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
-    q.tb_desc_area = (sizeof(pdc_tb_desc) * cfg->max_tbs + 15) & ~(size_t)15;
-    q.tb_res_area  = (sizeof(pdc_tb_result) * cfg->max_tbs + 15) & ~(size_t)15;
-    PDC_CREATE(dev_alloc(&q.d_desc, q.tb_desc_area + sizeof(pdc_cb_desc) * cfg->max_cbs));
-    PDC_CREATE(dev_alloc(&q.d_res, q.tb_res_area + sizeof(pdc_cb_result) * cfg->max_cbs));
-    q.d_tbs    = reinterpret_cast<pdc_tb_desc*>(q.d_desc);
-    q.d_cbs    = reinterpret_cast<pdc_cb_desc*>(q.d_desc + q.tb_desc_area);
-    q.d_tb_res = reinterpret_cast<pdc_tb_result*>(q.d_res);
-    q.d_cb_res = reinterpret_cast<pdc_cb_result*>(q.d_res + q.tb_res_area);
-    PDC_CREATE(dev_alloc(&q.d_llrs, (size_t)cfg->max_llrs + 16));
-    PDC_CREATE(dev_alloc(&q.d_cb_bits, (size_t)cfg->max_cbs * PDC_MAX_CB_BYTES));
-    PDC_CREATE(dev_alloc(&q.d_tb_out, (size_t)cfg->max_tb_bytes + 16));
-    PDC_CREATE(dev_alloc(&q.d_tb_sync, 2 * (size_t)ctx->tb_sync_entries));
-    PDC_CREATE(cudaMemset(q.d_tb_sync, 0, 2 * (size_t)ctx->tb_sync_entries * sizeof(uint32_t)));
-    PDC_CREATE(host_alloc(&q.h_desc, q.tb_desc_area + sizeof(pdc_cb_desc) * cfg->max_cbs));
-    PDC_CREATE(host_alloc(&q.h_res, q.tb_res_area + sizeof(pdc_cb_result) * cfg->max_cbs));
-    q.h_tbs    = reinterpret_cast<pdc_tb_desc*>(q.h_desc);
-    q.h_cbs    = reinterpret_cast<pdc_cb_desc*>(q.h_desc + q.tb_desc_area);
-    q.h_tb_res = reinterpret_cast<pdc_tb_result*>(q.h_res);
-    q.h_cb_res = reinterpret_cast<pdc_cb_result*>(q.h_res + q.tb_res_area);
-    PDC_CREATE(host_alloc(&q.h_cb_bits, (size_t)cfg->max_cbs * PDC_MAX_CB_BYTES));
-    PDC_CREATE(host_alloc(&q.h_tb_out, (size_t)cfg->max_tb_bytes + 16));
+    PDC_CREATE(create_queue(ctx, q, cfg->max_cbs, cfg->max_llrs, cfg->max_tbs, cfg->max_tb_bytes, true));
   }
+  PDC_CREATE(create_queue(ctx, ctx->sync_q, 1, 16, 1, 64, false));
 #undef PDC_CREATE
   return PDC_OK;
 }
@@ -628,6 +658,28 @@ static void free_front_end(FrontEnd& fe)
   fe = FrontEnd();
 }
 
+static void destroy_queue(Queue& q)
+{
+  if (q.stream) {
+    cudaStreamSynchronize(q.stream);
+    cudaStreamDestroy(q.stream);
+  }
+  if (q.done) {
+    cudaEventDestroy(q.done);
+  }
+  cudaFree(q.d_desc);
+  cudaFree(q.d_res);
+  cudaFree(q.d_llrs);
+  cudaFree(q.d_cb_bits);
+  cudaFree(q.d_tb_out);
+  cudaFree(q.d_tb_sync);
+  free_front_end(q.fe);
+  cudaFreeHost(q.h_desc);
+  cudaFreeHost(q.h_res);
+  cudaFreeHost(q.h_cb_bits);
+  cudaFreeHost(q.h_tb_out);
+}
+
 void pdc_destroy(pdc_ctx* ctx)
 {
   if (!ctx) {
@@ -637,25 +689,9 @@ void pdc_destroy(pdc_ctx* ctx)
   free_front_end(ctx->fe_sync);
   cudaFree(ctx->d_sch_sync);
   for (Queue& q : ctx->queues) {
-    if (q.stream) {
-      cudaStreamSynchronize(q.stream);
-      cudaStreamDestroy(q.stream);
-    }
-    if (q.done) {
-      cudaEventDestroy(q.done);
-    }
-    cudaFree(q.d_desc);
-    cudaFree(q.d_res);
-    cudaFree(q.d_llrs);
-    cudaFree(q.d_cb_bits);
-    cudaFree(q.d_tb_out);
-    cudaFree(q.d_tb_sync);
-    free_front_end(q.fe);
-    cudaFreeHost(q.h_desc);
-    cudaFreeHost(q.h_res);
-    cudaFreeHost(q.h_cb_bits);
-    cudaFreeHost(q.h_tb_out);
+    destroy_queue(q);
   }
+  destroy_queue(ctx->sync_q);
   cudaFree(ctx->d_harq);
   cudaFree(ctx->d_harq_data);
   cudaFree(ctx->d_harq_last);
@@ -743,6 +779,12 @@ int pdc_submit(pdc_ctx*           ctx,
   if (n_cb > ctx->cfg.max_cbs || n_llrs > ctx->cfg.max_llrs || n_tb > ctx->cfg.max_tbs) {
     return fail(PDC_ERR_CAPACITY, "pdc_submit: batch exceeds the capacity of the context");
   }
+  // One thread at a time per queue; a second thread arriving while a submit is being queued gets an error instead of a
+  // corrupted descriptor block.
+  std::unique_lock<std::mutex> queue_lock(ctx->queue_mutex[stream], std::try_to_lock);
+  if (!queue_lock.owns_lock()) {
+    return fail(PDC_ERR_CAPACITY, "pdc_submit: queue is being used by another thread");
+  }
   Queue& q = ctx->queues[stream];
   if (q.busy) {
     return fail(PDC_ERR_CAPACITY, "pdc_submit: queue busy (call pdc_wait first)");
@@ -761,6 +803,9 @@ int pdc_submit(pdc_ctx*           ctx,
     if (cbs[i].harq_id >= ctx->cfg.harq_entries) {
       return fail(PDC_ERR_INVALID, "pdc_submit: harq_id outside the arena");
     }
+    if (cbs[i].tb_index != 0xffff && cbs[i].tb_index >= n_tb) {
+      return fail(PDC_ERR_INVALID, "pdc_submit: codeblock refers to a transport block outside the batch");
+    }
   }
   size_t tb_out_bytes = 0;
   for (uint32_t i = 0; i != n_tb; ++i) {
@@ -770,6 +815,32 @@ int pdc_submit(pdc_ctx*           ctx,
       return fail(PDC_ERR_INVALID, "pdc_submit: invalid transport block descriptor");
     }
     tb_out_bytes = std::max(tb_out_bytes, (size_t)tbs[i].out_offset + need);
+    // The assembly kernel walks the transport block in steps of n_data = K - 24 - F bits per codeblock: every
+    // codeblock of the block must have the same, valid shape and together they must hold payload + TB checksum
+    // (ldpc_segmenter_impl.cpp:254-306 produces exactly such sets).
+    const pdc_cb_desc& c0 = cbs[tbs[i].first_cb];
+    const int          Z0 = c0.lifting_size;
+    if ((c0.base_graph != 1 && c0.base_graph != 2) || Z0 < 2 || Z0 > pdc::MAX_Z ||
+        pdc::host_tables().set_index[Z0] == 0xff) {
+      return fail(PDC_ERR_INVALID, "pdc_submit: transport block with an invalid base graph / lifting size");
+    }
+    const uint32_t K0 = ((c0.base_graph == 1) ? 22u : 10u) * (uint32_t)Z0;
+    for (uint32_t k = 1; k < tbs[i].nof_cb; ++k) {
+      const pdc_cb_desc& ck = cbs[tbs[i].first_cb + k];
+      if (ck.base_graph != c0.base_graph || ck.lifting_size != c0.lifting_size || ck.nof_filler != c0.nof_filler) {
+        return fail(PDC_ERR_INVALID, "pdc_submit: the codeblocks of a transport block differ in shape");
+      }
+    }
+    if (tbs[i].nof_cb == 1) {
+      // a single codeblock carries the TB checksum as its own (CRC16 or CRC24A)
+      const uint32_t crc_bits = (c0.crc_kind == PDC_CRC16) ? 16u : 24u;
+      if ((uint32_t)c0.nof_filler + crc_bits >= K0 || tbs[i].tbs_bits + crc_bits > K0 - c0.nof_filler) {
+        return fail(PDC_ERR_INVALID, "pdc_submit: transport block larger than its codeblock");
+      }
+    } else if ((uint32_t)c0.nof_filler + 24u >= K0 ||
+               (uint64_t)tbs[i].tbs_bits + 24u > (uint64_t)tbs[i].nof_cb * (K0 - 24u - c0.nof_filler)) {
+      return fail(PDC_ERR_INVALID, "pdc_submit: transport block larger than its codeblocks");
+    }
   }
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   BatchShape shape = scan_batch(cbs, n_cb);
@@ -1236,6 +1307,7 @@ int pdc_demodulate_soft(pdc_ctx*     ctx,
   if (n == 0) {
     return PDC_OK;
   }
+  std::lock_guard<std::mutex> sync_lock(ctx->sync_mutex);
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   FrontEnd&    fe = ctx->fe_sync;
   const size_t qm = (modulation == PDC_MOD_PI_2_BPSK) ? 1 : (size_t)modulation;
@@ -1260,6 +1332,7 @@ int pdc_wait(pdc_ctx* ctx, uint32_t stream)
   if (!ctx || stream >= ctx->queues.size()) {
     return fail(PDC_ERR_INVALID, "pdc_wait: invalid argument");
   }
+  std::lock_guard<std::mutex> queue_lock(ctx->queue_mutex[stream]);
   Queue& q = ctx->queues[stream];
   if (!q.busy && !q.fe.pending) {
     return PDC_OK;
@@ -1401,10 +1474,8 @@ int pdc_ldpc_decode(pdc_ctx*      ctx,
   if (n_llrs < K + 2 * Z || n_llrs > N || nof_filler >= K) {
     return fail(PDC_ERR_INVALID, "pdc_ldpc_decode: input length outside [K + 2Z, N]");
   }
-  Queue& q = ctx->queues[0];
-  if (q.busy) {
-    return fail(PDC_ERR_CAPACITY, "pdc_ldpc_decode: queue 0 busy");
-  }
+  std::lock_guard<std::mutex> sync_lock(ctx->sync_mutex);
+  Queue&                      q = ctx->sync_q;
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   pdc_cb_desc d;
   memset(&d, 0, sizeof(d));
@@ -1468,10 +1539,8 @@ int pdc_rate_dematch(pdc_ctx*      ctx,
     return fail(PDC_ERR_INVALID, "pdc_rate_dematch: invalid buffer length");
   }
   uint32_t Z = N / ((bg == 1) ? 66u : 50u);
-  Queue&   q = ctx->queues[0];
-  if (q.busy) {
-    return fail(PDC_ERR_CAPACITY, "pdc_rate_dematch: queue 0 busy");
-  }
+  std::lock_guard<std::mutex> sync_lock(ctx->sync_mutex);
+  Queue&                      q = ctx->sync_q;
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   pdc_cb_desc d;
   memset(&d, 0, sizeof(d));
@@ -1510,7 +1579,8 @@ int pdc_measure_int_peak(pdc_ctx* ctx, int mode, double* lane_ops_per_s)
     return fail(PDC_ERR_INVALID, "pdc_measure_int_peak: invalid argument");
   }
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
-  Queue&    q      = ctx->queues[0];
+  std::lock_guard<std::mutex> sync_lock(ctx->sync_mutex);
+  Queue&    q      = ctx->sync_q;
   const int blocks = ctx->sm_count * 8, threads = 256, iters = 2000;
   uint32_t* d_out  = nullptr;
   PDC_CUDA(dev_alloc(&d_out, (size_t)blocks * threads));
@@ -1579,6 +1649,7 @@ int pdc_ulsch_demux(pdc_ctx*           ctx,
   if (!ctx || !cws || n_cw == 0 || n_cw > 65535u || !llrs || !sch_out || !results) {
     return fail(PDC_ERR_INVALID, "pdc_ulsch_demux: invalid argument");
   }
+  std::lock_guard<std::mutex> sync_lock(ctx->sync_mutex);
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   FrontEnd& fe = ctx->fe_sync;
   PDC_CUDA(grow_device(&fe.d_raw, &fe.raw_cap, n_llrs + 16));
@@ -1610,6 +1681,7 @@ int pdc_scrambling_sequence(pdc_ctx* ctx, uint32_t c_init, uint32_t offset, uint
   if (!ctx || !packed || n == 0 || (uint64_t)offset + n + pdc::PRG_NC >= (1ull << 21)) {
     return fail(PDC_ERR_INVALID, "pdc_scrambling_sequence: invalid argument (sequence positions below 2^21 - 1600)");
   }
+  std::lock_guard<std::mutex> sync_lock(ctx->sync_mutex);
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   FrontEnd&          fe = ctx->fe_sync;
   pdc::UlschCodeword cw = {};
@@ -1642,10 +1714,8 @@ int pdc_crc(pdc_ctx* ctx, int crc_kind, const uint8_t* packed, uint32_t nbits, u
       (nbits + 7) / 8 > ctx->scratch_llr_bytes) {
     return fail(PDC_ERR_INVALID, "pdc_crc: invalid argument");
   }
-  Queue& q = ctx->queues[0];
-  if (q.busy) {
-    return fail(PDC_ERR_CAPACITY, "pdc_crc: queue 0 busy");
-  }
+  std::lock_guard<std::mutex> sync_lock(ctx->sync_mutex);
+  Queue&                      q = ctx->sync_q;
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   uint8_t*  d_in  = reinterpret_cast<uint8_t*>(ctx->d_scratch_llr);
   uint32_t* d_out = reinterpret_cast<uint32_t*>(q.d_cb_res);
@@ -1717,6 +1787,7 @@ static int encode_sync(pdc_ctx*            ctx,
     max_Z   = std::max<int>(max_Z, cbs[i].lifting_size);
     any_bg1 = any_bg1 || cbs[i].base_graph == 1;
   }
+  std::lock_guard<std::mutex> sync_lock(ctx->sync_mutex);
   PDC_CUDA(cudaSetDevice(ctx->cfg.device));
   PDC_CUDA(grow_device(&ctx->d_enc_cbs, &ctx->enc_cbs_cap, sizeof(pdc_enc_desc) * n_cb));
   PDC_CUDA(grow_device(&ctx->d_enc_msgs, &ctx->enc_msgs_cap, msg_bytes + 16));

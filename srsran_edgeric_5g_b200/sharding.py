@@ -38,6 +38,24 @@ def gather_slot_results(local: Dict[int, dict], world_size: int, group=None) -> 
     return out
 
 
+def gather_slot_flags(local, world_size: int, group=None):
+    """Per-slot gather on the hot path: every rank contributes one fixed-size tensor (e.g. {cell, tb_crc_ok, checksum} per
+    owned cell, padded to the largest share) and gets the concatenation in rank order back. One small collective per slot
+    instead of the pickled objects of gather_slot_results; NCCL for GPU tensors, gloo for CPU tensors."""
+    if world_size == 1:
+        return local.clone()
+    import torch
+    import torch.distributed as dist
+    out = torch.empty((world_size,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
+    return out.view((world_size * local.shape[0],) + tuple(local.shape[1:]))
+
+
+def cells_of_rank(n_cells: int, world_size: int, rank: int) -> List[int]:
+    """Cells this rank owns (owner_of_cell), in increasing order."""
+    return [c for c in range(n_cells) if owner_of_cell(c, world_size) == rank]
+
+
 def check_partition(tbs: Sequence[dict], world_size: int, by_cell: bool = True) -> None:
     """Every transport block has exactly one owner and all HARQ processes of a UE share it."""
     owners = {}

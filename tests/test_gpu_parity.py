@@ -24,13 +24,22 @@ def test_library_is_native(ctx):
 
 @pytest.mark.parametrize("early_stop", [True, False])
 def test_config1_bg1_z384_rate13(ctx, orc, early_stop):
-    # Config 1: BG1, Z=384, full 66Z input, around the waterfall so that iteration counts vary.
-    b = make_cb_batch(orc, 1, 384, n_cb=24, E=66 * 384, qm=2, rv=0, snr_db=-3.2, seed=11)
-    out = b.run_gpu(ctx, 6, early_stop)
-    ref = b.run_oracle(orc, 6, early_stop)
-    _assert_same(out, ref, "config1")
-    assert (out["nlayers"] == 46).all()
-    assert 0 < ref["crc_ok"].sum() < b.n_cb or True
+    # Config 1: BG1, Z=384, full 66Z input, across the waterfall of the 6-iteration decoder (-0.4 dB: a few codeblocks
+    # pass, all need 6 iterations; 0 dB: all pass in 5-6; +0.6 dB: 4-5), so that CRC flags AND iteration counts vary.
+    passes, total, iters = 0, 0, set()
+    for k, snr in enumerate((-0.4, 0.0, 0.6)):
+        b = make_cb_batch(orc, 1, 384, n_cb=16, E=66 * 384, qm=2, rv=0, snr_db=snr, seed=11 + k)
+        out = b.run_gpu(ctx, 6, early_stop)
+        ref = b.run_oracle(orc, 6, early_stop)
+        _assert_same(out, ref, f"config1 at {snr} dB")
+        assert (out["nlayers"] == 46).all()
+        passes += int(ref["crc_ok"].sum())
+        total += b.n_cb
+        iters |= set(ref["iters"][ref["crc_ok"]].tolist())
+    # the vectors really straddle the waterfall (otherwise this test compares failing decodes only)
+    assert 0 < passes < total, (passes, total)
+    if early_stop:
+        assert len(iters) >= 3, iters
 
 
 @pytest.mark.parametrize("nodes,snr", [(24, 7.4), (26, 6.2), (33, 3.6), (44, 1.2)])

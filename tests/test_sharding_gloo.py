@@ -52,6 +52,15 @@ def _worker(rank, world, port, q):
     local = {i: _decode(tbs[i]) for i in mine}
     dist.barrier()
     allr = sharding.gather_slot_results(local, world)
+    # the fixed-size per-slot gather of the hot path (one row per owned transport block, padded)
+    import torch
+    rows = torch.full((len(tbs), 2), -1, dtype=torch.int64)
+    for k, i in enumerate(mine):
+        rows[k, 0], rows[k, 1] = i, int(local[i]["ok"])
+    table = sharding.gather_slot_flags(rows, world)
+    assert sorted(int(r[0]) for r in table if r[0] >= 0) == list(range(len(tbs)))
+    assert all(int(r[1]) == 1 for r in table if r[0] >= 0)
+    assert sharding.cells_of_rank(4, world, rank) == [c for c in range(4) if c % world == rank]
     if rank == 0:
         q.put((sorted(allr), [allr[i]["ok"] for i in sorted(allr)], [allr[i]["tb"] for i in sorted(allr)], len(mine)))
     dist.destroy_process_group()
