@@ -108,3 +108,71 @@ def test_two_contexts_on_two_devices(orc):
         assert (out["harq"] == ref["harq"]).all()
     for c in ctxs:
         c.close()
+
+
+def test_pipelined_submit_equals_single_piece(orc):
+    """A large pdc_submit batch is pipelined inside the library (soft bits in groups on a copy stream, kernels per group on
+    lane streams, results as they exist). Same batch through a context with PDC_NO_PIPELINE=1: every output byte equal.
+    Covers groups of whole transport blocks, one large block cut into groups (assembled after the join), codeblocks
+    outside any transport block, and pageable as well as page-locked output buffers."""
+    import os
+    from srsran_edgeric_5g_b200 import ldpc
+    rng = np.random.default_rng(77)
+
+    def make(layout):
+        """layout: list of (tbs_bytes or None for loose codeblocks, n_llr)."""
+        cbs, tbd, llrs = [], [], []
+        off = tb_off = 0
+        flags = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA | capi.CB_EARLY_STOP
+        for tb_bytes, n_llr in layout:
+            if tb_bytes is None:
+                for _ in range(3):
+                    cbs.append((off, 2000, len(cbs), 0, 96, 7, 2, 2, 0, capi.CRC16, 3, flags, 0xffff))
+                    off += 2000
+                    llrs.append(rng.integers(-40, 41, 2000).astype(np.int8))
+                continue
+            metas = ldpc.segment_rx(tb_bytes * 8, 1, 0, 4, 0, 2, n_llr)
+            tbd.append((len(cbs), len(metas), tb_bytes * 8, tb_off, 0))
+            tb_off += (tb_bytes * 8 + 24 + 31) // 32 * 4
+            kind = capi.CRC24B if len(metas) > 1 else capi.CRC24A
+            for m in metas:
+                cbs.append((off + m.cw_offset, m.rm_length, len(cbs), 0, m.lifting_size, m.nof_filler_bits, 1, 4, 0, kind,
+                            3, flags, len(tbd) - 1))
+            llrs.append(rng.integers(-60, 61, n_llr).astype(np.int8))
+            off += n_llr
+        return (np.array(cbs, capi.CB_DESC_DTYPE), np.array(tbd, capi.TB_DESC_DTYPE) if tbd else None,
+                np.concatenate(llrs))
+
+    layouts = {
+        "several transport blocks": [(30000, 400000), (12000, 200000), (None, 0), (52000, 700000), (30000, 400000),
+                                     (4000, 60000), (40000, 500000)],
+        "one large transport block": [(150000, 1600000)],
+        "codeblocks only": [(None, 0)] * 200,
+    }
+    outs = {}
+    for mode in ("pipelined", "single"):
+        os.environ["PDC_NO_PIPELINE"] = "1" if mode == "single" else "0"
+        c = capi.Context(device=0, max_cbs=1024, max_llrs=4 << 20, harq_entries=1024, max_tbs=16, max_tb_bytes=1 << 20,
+                         nof_streams=1)
+        os.environ.pop("PDC_NO_PIPELINE")
+        rng = np.random.default_rng(77)
+        for name, layout in layouts.items():
+            cbs, tbd, llrs = make(layout)
+            for pinned in (False, True):
+                src = llrs
+                if pinned:
+                    buf = capi.PinnedBuffer(llrs.size)
+                    buf.array[:] = llrs
+                    src = buf.array
+                c.submit(cbs, src, tbd, stream=0, want_bits=True)
+                o = c.wait(0)
+                harq = np.stack([c.harq_read(i, 25344) for i in range(0, cbs.size, max(1, cbs.size // 16))])
+                outs[(mode, name, pinned)] = (o["cb_results"].copy(), o["cb_bits"].copy(),
+                                              None if tbd is None else o["tb_results"].copy(),
+                                              None if tbd is None else o["tb_bytes"].copy(), harq)
+        c.close()
+    for name in layouts:
+        for pinned in (False, True):
+            a, b = outs[("pipelined", name, pinned)], outs[("single", name, pinned)]
+            for x, y, what in zip(a, b, ("codeblock results", "codeblock bits", "TB results", "TB bytes", "HARQ")):
+                assert (x is None and y is None) or (x.tobytes() == y.tobytes()), (name, pinned, what)
