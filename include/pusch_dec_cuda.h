@@ -259,6 +259,8 @@ int pdc_measure_int_peak(pdc_ctx* ctx, int mode, double* lane_ops_per_s);
 /* Pinned host memory for zero-copy-staging of LLR batches (the caller may also pass pageable memory, at a price). */
 void* pdc_host_alloc(size_t bytes);
 void  pdc_host_free(void* p);
+/* The same for INPUT staging only (soft bits the CPU writes and never reads back): write-combined, portable memory. */
+void* pdc_host_alloc_input(size_t bytes);
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* Batched codeblock interface = hal::hw_accelerator_pusch_dec (enqueue_operation / dequeue_operation) and the batched */

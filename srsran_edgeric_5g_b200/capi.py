@@ -81,7 +81,7 @@ assert CB_DESC_DTYPE.itemsize == ctypes.sizeof(CbDesc) == 28
 assert TB_DESC_DTYPE.itemsize == ctypes.sizeof(TbDesc) == 20
 
 EXPORTS = ["pdc_default_config", "pdc_create", "pdc_destroy", "pdc_last_error", "pdc_device_info", "pdc_launch_count",
-           "pdc_measure_int_peak", "pdc_host_alloc", "pdc_host_free", "pdc_submit", "pdc_wait", "pdc_poll", "pdc_launch_device",
+           "pdc_measure_int_peak", "pdc_host_alloc", "pdc_host_alloc_input", "pdc_host_free", "pdc_submit", "pdc_wait", "pdc_poll", "pdc_launch_device",
            "pdc_harq_read", "pdc_harq_write", "pdc_harq_free", "pdc_harq_device_ptr", "pdc_ldpc_decode",
            "pdc_rate_dematch", "pdc_crc", "pdc_submit_codewords", "pdc_ulsch_demux", "pdc_scrambling_sequence",
            "pdc_launch_codewords_device", "pdc_submit_symbols", "pdc_demodulate_soft", "pdc_launch_demod_device",
@@ -120,6 +120,8 @@ def load():
     L.pdc_measure_int_peak.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     L.pdc_host_alloc.argtypes = [ctypes.c_size_t]
     L.pdc_host_alloc.restype = _vp
+    L.pdc_host_alloc_input.argtypes = [ctypes.c_size_t]
+    L.pdc_host_alloc_input.restype = _vp
     L.pdc_host_free.argtypes = [_vp]
     L.pdc_host_free.restype = None
     L.pdc_submit.argtypes = [_vp, _u32, _vp, _u32, _vp, ctypes.c_size_t, _vp, _u32, _vp, _vp, _vp, _vp]
@@ -163,9 +165,10 @@ def _ptr(a):
 class PinnedBuffer:
     """Pinned host memory from pdc_host_alloc exposed as a numpy array."""
 
-    def __init__(self, nbytes, dtype=np.int8):
+    def __init__(self, nbytes, dtype=np.int8, input_only=False):
+        """input_only: write-combined memory (pdc_host_alloc_input) - fill it once, never read it on the CPU."""
         self._L = load()
-        self.ptr = self._L.pdc_host_alloc(nbytes)
+        self.ptr = (self._L.pdc_host_alloc_input if input_only else self._L.pdc_host_alloc)(nbytes)
         if not self.ptr:
             raise PdcError(PDC_ERR_CUDA, "pdc_host_alloc failed")
         n = nbytes // np.dtype(dtype).itemsize

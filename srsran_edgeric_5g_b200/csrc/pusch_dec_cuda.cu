@@ -790,6 +790,17 @@ void* pdc_host_alloc(size_t bytes)
   return p;
 }
 
+void* pdc_host_alloc_input(size_t bytes)
+{
+  // Write-combined and portable: the CPU only ever WRITES soft bits here (reads would be slow), the copy engine reads
+  // them without snooping the CPU caches, and every context of the process (one per GPU) may copy from it.
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocWriteCombined | cudaHostAllocPortable) != cudaSuccess) {
+    return nullptr;
+  }
+  return p;
+}
+
 void pdc_host_free(void* p)
 {
   if (p) {
