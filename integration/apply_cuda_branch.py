@@ -39,13 +39,41 @@ PATCHES = {
 }
 
 
-def patch(text, rules):
+# The hal registry (create_hw_accelerator_pusch_dec_factory keyed by acc_type, "acc100" today): its whole body sits under
+# ENABLE_PUSCH_HWACC, i.e. needs DPDK; the "cuda" accelerator does not, so its branch goes in front of the #ifdef.
+HAL_FILE = "lib/hal/phy/upper/channel_processors/pusch/hw_accelerator_factories.cpp"
+HAL_ANCHOR = "srsran::hal::create_hw_accelerator_pusch_dec_factory("
+HAL_BODY = ('  if (accelerator_config.acc_type == "cuda") {\n'
+            '    // B200: batched LDPC decoding + rate dematching + HARQ in device memory (external soft bits), no DPDK.\n'
+            '    return srsran::cuda::create_hw_accelerator_pusch_dec_factory_cuda(cuda_context());\n  }\n')
+PATCHES[HAL_FILE] = [(HAL_ANCHOR, HAL_BODY)]
+
+
+# The reference's pusch_decoder_hwacc_benchmark knows one accelerator name ("acc100"); a maintainer adding the CUDA
+# accelerator adds its name next to it, going through the SAME hal registry and pusch_decoder_hw_impl as ACC100 does.
+HWACC_BENCH = "tests/benchmarks/phy/upper/channel_processors/pusch/pusch_decoder_hwacc_benchmark.cpp"
+HWACC_ANCHOR = "static std::shared_ptr<pusch_decoder_factory> create_pusch_decoder_factory(std::string decoder_type)"
+HWACC_BODY = ('  if (decoder_type == "cuda") {\n'
+              '    hal::hw_accelerator_pusch_dec_configuration hw_decoder_config;\n'
+              '    hw_decoder_config.acc_type       = "cuda";\n'
+              '    hw_decoder_config.ext_softbuffer = true;\n'
+              '    pusch_decoder_factory_hw_configuration decoder_hw_factory_config;\n'
+              '    decoder_hw_factory_config.segmenter_factory  = create_ldpc_segmenter_rx_factory_sw();\n'
+              '    decoder_hw_factory_config.crc_factory        = create_crc_calculator_factory_sw("auto");\n'
+              '    decoder_hw_factory_config.hw_decoder_factory = hal::create_hw_accelerator_pusch_dec_factory(hw_decoder_config);\n'
+              '    TESTASSERT(decoder_hw_factory_config.hw_decoder_factory, "No CUDA accelerator (no GPU?).");\n'
+              '    return create_pusch_decoder_factory_hw(decoder_hw_factory_config);\n  }\n')
+NO_CONTEXT = {HWACC_BENCH}  # files that do not need the shared context / adapter include
+PATCHES[HWACC_BENCH] = [(HWACC_ANCHOR, HWACC_BODY)]
+
+
+def patch(text, rules, with_context=True):
     lines = text.splitlines(keepends=True)
     out, pending, done = [], None, 0
     first_include = min(i for i, l in enumerate(lines) if l.startswith("#include"))
     for i, line in enumerate(lines):
         out.append(line)
-        if i == first_include:
+        if i == first_include and with_context:
             out.append(INCLUDE)
             out.append(SHARED_CONTEXT)
         for anchor, body in rules:
@@ -64,7 +92,7 @@ def main():
     dst.mkdir(parents=True, exist_ok=True)
     for rel, rules in PATCHES.items():
         target = dst / rel.replace("/", "__")
-        target.write_text(patch((ref / rel).read_text(), rules))
+        target.write_text(patch((ref / rel).read_text(), rules, rel not in NO_CONTEXT))
         print("patched", rel, "->", target)
 
 

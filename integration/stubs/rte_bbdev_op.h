@@ -1,0 +1,1 @@
+#include "rte_bbdev.h"

@@ -61,6 +61,36 @@ def test_reference_ldpc_encoder_benchmark_with_cuda_factory():
     assert "LDPC encoder cuda" in out.stdout
 
 
+def test_reference_pusch_processor_benchmark_with_cuda_decoder_and_dematcher():
+    """tests/benchmarks/phy/upper/channel_processors/pusch/pusch_processor_benchmark.cpp of the reference, unmodified:
+    the whole PUSCH chain (channel estimator, equaliser, demodulator, UL-SCH demultiplexer, pusch_decoder_impl) with
+    `-D cuda -M cuda`, i.e. create_ldpc_decoder_factory_sw("cuda") / create_ldpc_rate_dematcher_factory_sw("cuda") inside
+    its own pusch_decoder_impl, on several worker threads at once. The benchmark asserts that every transport block
+    passes its CRC (pusch_processor_benchmark.cpp: TESTASSERT on the notifier's result)."""
+    exe = HARNESS / "pusch_processor_benchmark"
+    if not exe.exists():
+        pytest.skip("integration/_build not built (needs /root/reference at build time)")
+    for profile, threads in (("scs15_5MHz_qpsk_rv0_1port_1layer", 4), ("scs30_100MHz_256qam_rv0_4port_nlayer", 2)):
+        out = subprocess.run([str(exe), "-m", "throughput_total", "-R", "2", "-B", "2", "-T", str(threads), "-t", "0", "-D",
+                              "cuda", "-M", "cuda", "-P", profile], capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        assert "PUSCH RB=" in out.stdout, out.stdout[-2000:]
+
+
+def test_reference_pusch_decoder_hwacc_benchmark_with_cuda_accelerator():
+    """tests/benchmarks/phy/upper/channel_processors/pusch/pusch_decoder_hwacc_benchmark.cpp of the reference with the
+    accelerator name "cuda" added next to "acc100" (integration/apply_cuda_branch.py): generic pusch_decoder_impl against
+    the reference's pusch_decoder_hw_impl on hal::create_hw_accelerator_pusch_dec_factory({acc_type = "cuda"}) - the hal
+    registry with the "cuda" branch - for PRB {25, 52, 106, 270} x {QPSK, 16QAM, 64QAM, 256QAM}."""
+    exe = HARNESS / "pusch_decoder_hwacc_benchmark"
+    if not exe.exists():
+        pytest.skip("integration/_build not built (needs /root/reference at build time)")
+    out = subprocess.run([str(exe), "-T", "cuda", "-i", "6"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("PUSCH RB=") == 16 and "cuda" in out.stdout, out.stdout[-2000:]
+    print(out.stdout)
+
+
 def test_cpp_client_of_the_c_abi(orc, tmp_path):
     """tools/latency_probe.cpp (pdc_create / pdc_host_alloc / pdc_submit / pdc_wait from C++, nothing but the header): a
     two-codeblock transport block encoded by the oracle, ideal soft bits, decoded and assembled through the C ABI."""
