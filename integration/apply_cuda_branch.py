@@ -67,6 +67,58 @@ NO_CONTEXT = {HWACC_BENCH}  # files that do not need the shared context / adapte
 PATCHES[HWACC_BENCH] = [(HWACC_ANCHOR, HWACC_BODY)]
 
 
+# The gNB itself: the upper PHY builds its PUSCH decoder factory from the configured LDPC decoder type.
+# With "cuda" it takes the reference's hardware front end (pusch_decoder_hw_impl) on the CUDA accelerator from the hal
+# registry - nothing else of the upper PHY changes - and the rx buffer pool keeps its soft bits in the accelerator
+# (external_soft_bits), which is what du_low_config_translator.cpp has to request.
+UPPER_PHY = "lib/phy/upper/upper_phy_factories.cpp"
+UPPER_PHY_LINE = "  pusch_config.decoder_factory                      = create_pusch_decoder_factory_sw(decoder_config);"
+UPPER_PHY_NEW = ('  if (config.ldpc_decoder_type == "cuda") {\n'
+                 '    hal::hw_accelerator_pusch_dec_configuration hw_cfg;\n'
+                 '    hw_cfg.acc_type       = "cuda";\n'
+                 '    hw_cfg.ext_softbuffer = true;\n'
+                 '    pusch_decoder_factory_hw_configuration hw_decoder_config;\n'
+                 '    hw_decoder_config.segmenter_factory  = decoder_config.segmenter_factory;\n'
+                 '    hw_decoder_config.crc_factory        = crc_calc_factory;\n'
+                 '    hw_decoder_config.hw_decoder_factory = hal::create_hw_accelerator_pusch_dec_factory(hw_cfg);\n'
+                 '    report_fatal_error_if_not(hw_decoder_config.hw_decoder_factory, "No CUDA PUSCH decoder accelerator.");\n'
+                 '    pusch_config.decoder_factory = create_pusch_decoder_factory_hw(hw_decoder_config);\n'
+                 '  } else {\n'
+                 '    pusch_config.decoder_factory = create_pusch_decoder_factory_sw(decoder_config);\n'
+                 '  }\n')
+UPPER_PHY_INCLUDE = '#include "srsran/hal/phy/upper/channel_processors/pusch/hw_accelerator_factories.h"\n'
+DU_LOW = "apps/units/flexible_du/du_low/du_low_config_translator.cpp"
+DU_LOW_LINES = [
+    ("    upper_phy_cell.rx_buffer_config.external_soft_bits   = false;",
+     '    // SRSRAN_LDPC_DECODER_TYPE=cuda selects the B200 PUSCH decoder (until expert_phy grows the three type fields)\n'
+     '    const char* pdc_type = std::getenv("SRSRAN_LDPC_DECODER_TYPE");\n'
+     '    const bool  pdc_cuda = pdc_type != nullptr && std::string(pdc_type) == "cuda";\n'
+     '    upper_phy_cell.rx_buffer_config.external_soft_bits   = pdc_cuda;\n'),
+    ('    upper_phy_cell.ldpc_rate_dematcher_type              = "auto";',
+     '    upper_phy_cell.ldpc_rate_dematcher_type              = pdc_cuda ? "cuda" : "auto";\n'),
+    ('    upper_phy_cell.ldpc_decoder_type                     = "auto";',
+     '    upper_phy_cell.ldpc_decoder_type                     = pdc_cuda ? "cuda" : "auto";\n'),
+]
+
+
+def replace_lines(text, rules, extra_include=None):
+    lines = text.splitlines(keepends=True)
+    out, done = [], 0
+    first_include = min(i for i, l in enumerate(lines) if l.startswith("#include"))
+    for i, line in enumerate(lines):
+        hit = [new for old, new in rules if line.rstrip("\n") == old]
+        if hit:
+            out.append(hit[0])
+            done += 1
+        else:
+            out.append(line)
+        if i == first_include and extra_include:
+            out.append(extra_include)
+    if done != len(rules):
+        raise SystemExit("lines not found: %d of %d replaced" % (done, len(rules)))
+    return "".join(out)
+
+
 def patch(text, rules, with_context=True):
     lines = text.splitlines(keepends=True)
     out, pending, done = [], None, 0
@@ -93,6 +145,11 @@ def main():
     for rel, rules in PATCHES.items():
         target = dst / rel.replace("/", "__")
         target.write_text(patch((ref / rel).read_text(), rules, rel not in NO_CONTEXT))
+        print("patched", rel, "->", target)
+    for rel, rules, inc in ((UPPER_PHY, [(UPPER_PHY_LINE, UPPER_PHY_NEW)], UPPER_PHY_INCLUDE),
+                            (DU_LOW, DU_LOW_LINES, "#include <cstdlib>\n#include <string>\n")):
+        target = dst / rel.replace("/", "__")
+        target.write_text(replace_lines((ref / rel).read_text(), rules, inc))
         print("patched", rel, "->", target)
 
 
