@@ -256,6 +256,13 @@ uint64_t pdc_launch_count(pdc_ctx* ctx);
  */
 int pdc_measure_int_peak(pdc_ctx* ctx, int mode, double* lane_ops_per_s);
 
+/*
+ * Debug builds of the library (-DPDC_DEBUG_BOUNDS: device-side asserts on every shared-memory / global index, canary words
+ * behind every device allocation): 1 if every canary of the context's device is intact, 0 if one was overwritten.
+ * Release builds answer -1 (nothing to check).
+ */
+int pdc_debug_canaries_ok(pdc_ctx* ctx);
+
 /* Pinned host memory for zero-copy-staging of LLR batches (the caller may also pass pageable memory, at a price). */
 void* pdc_host_alloc(size_t bytes);
 void  pdc_host_free(void* p);

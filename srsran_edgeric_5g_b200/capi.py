@@ -81,7 +81,7 @@ assert CB_DESC_DTYPE.itemsize == ctypes.sizeof(CbDesc) == 28
 assert TB_DESC_DTYPE.itemsize == ctypes.sizeof(TbDesc) == 20
 
 EXPORTS = ["pdc_default_config", "pdc_create", "pdc_destroy", "pdc_last_error", "pdc_device_info", "pdc_launch_count",
-           "pdc_measure_int_peak", "pdc_host_alloc", "pdc_host_alloc_input", "pdc_host_free", "pdc_submit", "pdc_wait", "pdc_poll", "pdc_launch_device",
+           "pdc_measure_int_peak", "pdc_debug_canaries_ok", "pdc_host_alloc", "pdc_host_alloc_input", "pdc_host_free", "pdc_submit", "pdc_wait", "pdc_poll", "pdc_launch_device",
            "pdc_harq_read", "pdc_harq_write", "pdc_harq_free", "pdc_harq_device_ptr", "pdc_ldpc_decode",
            "pdc_rate_dematch", "pdc_crc", "pdc_submit_codewords", "pdc_ulsch_demux", "pdc_scrambling_sequence",
            "pdc_launch_codewords_device", "pdc_submit_symbols", "pdc_demodulate_soft", "pdc_launch_demod_device",
@@ -118,6 +118,8 @@ def load():
     L.pdc_launch_count.argtypes = [_vp]
     L.pdc_launch_count.restype = ctypes.c_uint64
     L.pdc_measure_int_peak.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    L.pdc_debug_canaries_ok.argtypes = [_vp]
+    L.pdc_debug_canaries_ok.restype = ctypes.c_int
     L.pdc_host_alloc.argtypes = [ctypes.c_size_t]
     L.pdc_host_alloc.restype = _vp
     L.pdc_host_alloc_input.argtypes = [ctypes.c_size_t]
@@ -206,8 +208,20 @@ class Context:
         self._pending = {}
         self._pending_fe = {}
 
+    def debug_canaries_ok(self):
+        """1 / 0 on a -DPDC_DEBUG_BOUNDS build of the library (canaries intact / overwritten), -1 on a release build."""
+        return int(self._L.pdc_debug_canaries_ok(self.h))
+
     def close(self):
         if getattr(self, "h", None):
+            if os.environ.get("PDC_CHECK_CANARIES") == "1":
+                # debug-bounds run of the GPU suite (tools/run_debug_bounds.sh): every context leaves with its canaries intact
+                ok = self.debug_canaries_ok()
+                self._L.pdc_destroy(self.h)
+                self.h = None
+                if ok != 1:
+                    raise PdcError(PDC_ERR_CUDA, "device canaries overwritten (or not a PDC_DEBUG_BOUNDS build): %d" % ok)
+                return
             self._L.pdc_destroy(self.h)
             self.h = None
 

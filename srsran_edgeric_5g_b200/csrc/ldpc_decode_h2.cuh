@@ -124,18 +124,33 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p, uint64_t po
 
 // Shared memory through explicit 32-bit shared-window addresses (a generic pointer makes the compiler rebuild the window
 // base from a special register in every row).
+#ifdef PDC_DEBUG_BOUNDS
+// [a, a + n) inside the kernel's dynamic shared memory?
+__device__ __forceinline__ bool smem_range_ok(uint32_t a, uint32_t n)
+{
+  extern __shared__ __align__(16) unsigned char smem_dbg_base[];
+  uint32_t size;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(size));
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_dbg_base);
+  return a >= base && a + n <= base + size && (a % n) == 0;
+}
+#endif
+
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
 {
+  PDC_ASSERT(smem_range_ok(a, 4));
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v)
 {
+  PDC_ASSERT(smem_range_ok(a, 4));
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v));
 }
 __device__ __forceinline__ uint4 lds_u128(uint32_t a)
 {
+  PDC_ASSERT(smem_range_ok(a, 16));
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
@@ -887,6 +902,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
                       dst = c * SPEC_Z + pos;
                     }
                   }
+                  PDC_ASSERT(dst >= 2 * Z && dst < n_full * Z && 4 * q + k < PDC_MAX_CB_SOFT);
                   soft[dst] = U(v);
                 }
               }
@@ -917,6 +933,9 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       // Compressed messages: one uint4 per (row, check), only ever touched by thread j. They start at zero ("no message
       // yet") and the next row is fetched while the current one is processed.
       uint4* const   st_thread = st_base + j;
+      // every (row, check) entry this thread will touch lies inside the CTA's slice of the scratch
+      PDC_ASSERT((size_t)layers * st_stride * 4 <= scratch_stride_words && (!active || (uint32_t)j < st_stride));
+      PDC_ASSERT(layers >= 4 && layers <= rows);
       const uint64_t pol_keep  = l2_policy_evict_last();
       if (active) {
         for (int m = 0; m < layers; ++m) {

@@ -5,6 +5,24 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// -DPDC_DEBUG_BOUNDS: every shared-memory / global index the kernels form is checked on the device (a violation prints
+// the site and traps: the launch fails, the test sees it), and the host puts canary words behind every device
+// allocation (pdc_debug_canaries_ok). compute-sanitizer is not available on the pool the GPU tests run on, so the GPU
+// suite is run once per round against this build instead (tools/run_debug_bounds.sh).
+#ifdef PDC_DEBUG_BOUNDS
+#include <cstdio>
+#define PDC_ASSERT(cond)                                                                                               \
+  do {                                                                                                                 \
+    if (!(cond)) {                                                                                                     \
+      printf("PDC_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x,     \
+             (int)threadIdx.x);                                                                                        \
+      __trap();                                                                                                        \
+    }                                                                                                                  \
+  } while (0)
+#else
+#define PDC_ASSERT(cond) ((void)0)
+#endif
+
 namespace pdc {
 
 constexpr int MAX_Z        = 384;

@@ -22,6 +22,82 @@
 #include <memory>
 #include <mutex>
 
+// ---- device allocations ---------------------------------------------------------------------------------------------
+#ifdef PDC_DEBUG_BOUNDS
+// Debug build: 256 canary bytes behind every device allocation; pdc_debug_canaries_ok() reads them back.
+constexpr size_t  CANARY_BYTES = 256;
+constexpr uint8_t CANARY_VALUE = 0xA5;
+struct CanaryEntry {
+  const uint8_t* base;
+  size_t         bytes;
+  int            device;
+};
+struct CanaryRegistry {
+  std::mutex               m;
+  std::vector<CanaryEntry> entries;
+};
+static CanaryRegistry& canaries()
+{
+  static CanaryRegistry r;
+  return r;
+}
+static cudaError_t canary_malloc(void** p, size_t bytes)
+{
+  cudaError_t e = cudaMalloc(p, bytes + CANARY_BYTES);
+  if (e == cudaSuccess) {
+    e = cudaMemset(static_cast<uint8_t*>(*p) + bytes, CANARY_VALUE, CANARY_BYTES);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(canaries().m);
+    canaries().entries.push_back(CanaryEntry{static_cast<const uint8_t*>(*p), bytes, dev});
+  }
+  return e;
+}
+static cudaError_t canary_free(const void* p)
+{
+  if (p != nullptr) {
+    std::lock_guard<std::mutex> lock(canaries().m);
+    auto&                       v = canaries().entries;
+    for (size_t i = 0; i != v.size(); ++i) {
+      if (v[i].base == p) {
+        v[i] = v.back();
+        v.pop_back();
+        break;
+      }
+    }
+  }
+  return cudaFree(const_cast<void*>(p));
+}
+// Number of allocations whose canary was overwritten (0 = intact), -1 on a CUDA error.
+static int canary_check(int device)
+{
+  std::lock_guard<std::mutex> lock(canaries().m);
+  int                         bad = 0;
+  std::vector<uint8_t>        h(CANARY_BYTES);
+  for (const CanaryEntry& c : canaries().entries) {
+    if (c.device != device) {
+      continue;
+    }
+    if (cudaMemcpy(h.data(), c.base + c.bytes, CANARY_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      return -1;
+    }
+    for (uint8_t b : h) {
+      if (b != CANARY_VALUE) {
+        fprintf(stderr, "[pusch_dec_cuda] canary behind a %zu-byte device allocation was overwritten\n", c.bytes);
+        ++bad;
+        break;
+      }
+    }
+  }
+  return bad;
+}
+#define PDC_MALLOC(p, bytes) canary_malloc(reinterpret_cast<void**>(p), (bytes))
+#define PDC_FREE(p) canary_free(p)
+#else
+#define PDC_MALLOC(p, bytes) cudaMalloc(reinterpret_cast<void**>(p), (bytes))
+#define PDC_FREE(p) cudaFree(p)
+#endif
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -235,11 +311,11 @@ static cudaError_t grow_device(T** p, size_t* cap, size_t need)
   if (need <= *cap) {
     return cudaSuccess;
   }
-  cudaFree(*p);
+  PDC_FREE(*p);
   *p   = nullptr;
   *cap = 0;
   size_t      want = need + need / 4 + 64;
-  cudaError_t e    = cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T));
+  cudaError_t e    = PDC_MALLOC(p, want * sizeof(T));
   if (e == cudaSuccess) {
     *cap = want;
   }
@@ -266,7 +342,7 @@ cudaError_t decode_scratch_for(pdc_ctx* ctx, cudaStream_t s, size_t need, pdc_ct
   }
   // From here on the entry belongs to the caller: a stream is driven by one thread at a time.
   if (sc->d_counter == nullptr) {
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&sc->d_counter), sizeof(uint32_t));
+    cudaError_t e = PDC_MALLOC(&sc->d_counter, sizeof(uint32_t));
     if (e == cudaSuccess) {
       e = cudaMemsetAsync(sc->d_counter, 0, sizeof(uint32_t), s);
     }
@@ -276,10 +352,10 @@ cudaError_t decode_scratch_for(pdc_ctx* ctx, cudaStream_t s, size_t need, pdc_ct
     sc->counter_base = 0;
   }
   if (need > sc->words) {
-    cudaFree(sc->d_state); // synchronises the device: only on the first batch of a foreign stream
+    PDC_FREE(sc->d_state); // synchronises the device: only on the first batch of a foreign stream
     sc->d_state   = nullptr;
     sc->words     = 0;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&sc->d_state), need * sizeof(uint32_t));
+    cudaError_t e = PDC_MALLOC(&sc->d_state, need * sizeof(uint32_t));
     if (e != cudaSuccess) {
       return e;
     }
@@ -399,7 +475,7 @@ int launch_batch(pdc_ctx*             ctx,
 template <typename T>
 cudaError_t dev_alloc(T** p, size_t n)
 {
-  return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
+  return PDC_MALLOC(p, std::max<size_t>(n, 1) * sizeof(T));
 }
 template <typename T>
 cudaError_t host_alloc(T** p, size_t n)
@@ -674,13 +750,13 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
 
 static void free_front_end(FrontEnd& fe)
 {
-  cudaFree(fe.dm.d_sym);
-  cudaFree(fe.dm.d_nv);
-  cudaFree(fe.d_raw);
-  cudaFree(fe.d_seq);
-  cudaFree(fe.d_uci);
-  cudaFree(fe.d_plan);
-  cudaFree(fe.d_cb_scr);
+  PDC_FREE(fe.dm.d_sym);
+  PDC_FREE(fe.dm.d_nv);
+  PDC_FREE(fe.d_raw);
+  PDC_FREE(fe.d_seq);
+  PDC_FREE(fe.d_uci);
+  PDC_FREE(fe.d_plan);
+  PDC_FREE(fe.d_cb_scr);
   cudaFreeHost(fe.h_uci);
   for (int k = 0; k != FrontEnd::RING; ++k) {
     cudaFreeHost(fe.h_plan[k]);
@@ -718,12 +794,12 @@ static void destroy_queue(Queue& q)
       cudaEventDestroy(q.ev_copy[g]);
     }
   }
-  cudaFree(q.d_desc);
-  cudaFree(q.d_res);
-  cudaFree(q.d_llrs);
-  cudaFree(q.d_cb_bits);
-  cudaFree(q.d_tb_out);
-  cudaFree(q.d_tb_sync);
+  PDC_FREE(q.d_desc);
+  PDC_FREE(q.d_res);
+  PDC_FREE(q.d_llrs);
+  PDC_FREE(q.d_cb_bits);
+  PDC_FREE(q.d_tb_out);
+  PDC_FREE(q.d_tb_sync);
   free_front_end(q.fe);
   cudaFreeHost(q.h_desc);
   cudaFreeHost(q.h_res);
@@ -738,23 +814,23 @@ void pdc_destroy(pdc_ctx* ctx)
   }
   cudaSetDevice(ctx->cfg.device);
   free_front_end(ctx->fe_sync);
-  cudaFree(ctx->d_sch_sync);
+  PDC_FREE(ctx->d_sch_sync);
   for (Queue& q : ctx->queues) {
     destroy_queue(q);
   }
   destroy_queue(ctx->sync_q);
-  cudaFree(ctx->d_harq);
-  cudaFree(ctx->d_harq_data);
-  cudaFree(ctx->d_harq_last);
-  cudaFree(ctx->d_tb_sync);
-  cudaFree(ctx->d_scratch_llr);
-  cudaFree(ctx->d_demod_tables);
-  cudaFree(ctx->d_enc_cbs);
-  cudaFree(ctx->d_enc_msgs);
-  cudaFree(ctx->d_enc_out);
+  PDC_FREE(ctx->d_harq);
+  PDC_FREE(ctx->d_harq_data);
+  PDC_FREE(ctx->d_harq_last);
+  PDC_FREE(ctx->d_tb_sync);
+  PDC_FREE(ctx->d_scratch_llr);
+  PDC_FREE(ctx->d_demod_tables);
+  PDC_FREE(ctx->d_enc_cbs);
+  PDC_FREE(ctx->d_enc_msgs);
+  PDC_FREE(ctx->d_enc_out);
   for (pdc_ctx::DecodeScratch& c : ctx->decode_scratch) {
-    cudaFree(c.d_state);
-    cudaFree(c.d_counter);
+    PDC_FREE(c.d_state);
+    PDC_FREE(c.d_counter);
   }
   delete ctx;
 }
@@ -779,6 +855,19 @@ int pdc_device_info(pdc_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor)
 uint64_t pdc_launch_count(pdc_ctx* ctx)
 {
   return ctx ? ctx->launches.load() : 0;
+}
+
+int pdc_debug_canaries_ok(pdc_ctx* ctx)
+{
+#ifdef PDC_DEBUG_BOUNDS
+  if (!ctx || cudaSetDevice(ctx->cfg.device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    return 0;
+  }
+  return canary_check(ctx->cfg.device) == 0 ? 1 : 0;
+#else
+  (void)ctx;
+  return -1; // not a debug build: nothing to check
+#endif
 }
 
 void* pdc_host_alloc(size_t bytes)
@@ -1903,7 +1992,7 @@ int pdc_measure_int_peak(pdc_ctx* ctx, int mode, double* lane_ops_per_s)
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  cudaFree(d_out);
+  PDC_FREE(d_out);
   // 64 statements per inner iteration, 2 integer instructions each.
   double ops      = (double)blocks * threads * (double)iters * 64.0 * 2.0;
   *lane_ops_per_s = ops / (best * 1e-3);

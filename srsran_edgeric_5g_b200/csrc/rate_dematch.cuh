@@ -128,7 +128,9 @@ __device__ __forceinline__ int dm_combine(const DematchGeom& g, int p, int i, in
 template <bool STAGED>
 __device__ __forceinline__ int dm_fetch(const DematchGeom& g, const int8_t* __restrict__ llr, const uint8_t* sh, int i)
 {
+  PDC_ASSERT(i >= 0 && i < g.E);
   if (STAGED) {
+    PDC_ASSERT(i < DM_STAGE_BYTES);
     return (int)(int8_t)sh[i];
   }
   int k = i;
@@ -137,6 +139,7 @@ __device__ __forceinline__ int dm_fetch(const DematchGeom& g, const int8_t* __re
     int sym = i - j * g.Kq;
     k       = sym * g.qm + j;
   }
+  PDC_ASSERT(k >= 0 && k < g.E);
   int v = (int)__ldg(llr + k);
   if (g.seq != nullptr && seq_bit(g.seq, g.seq_base + (uint32_t)k)) {
     v = (int)(int8_t)(uint8_t)(0u - (uint32_t)v);
@@ -206,6 +209,7 @@ template <bool STAGED>
 __device__ __noinline__ uint32_t dm_word_general(const DematchGeom& g, const int8_t* __restrict__ llr, const uint8_t* sh,
                                                  uint32_t* out, int w)
 {
+  PDC_ASSERT(w >= 0 && 4 * w < g.N && 4 * w + 4 <= PDC_MAX_CB_SOFT);
   const uint32_t old = out[w];
   uint32_t       res = 0;
 #pragma unroll
@@ -336,6 +340,7 @@ __device__ __forceinline__ uint32_t dm_lds_u32_unaligned(const uint8_t* sh, int 
 __device__ __forceinline__ void dm_segment_words(const DematchGeom& g, const int8_t* __restrict__ llr, const uint8_t* sh,
                                                  uint32_t* out, int action, int ioff, int wa, int wb, DmLast& last)
 {
+  PDC_ASSERT(wa >= 0 && wa <= wb && 4 * wb <= g.N + 3 && 4 * wb <= PDC_MAX_CB_SOFT);
   const int tid = threadIdx.x, T = blockDim.x;
   // The write-only actions go out in 16-byte stores: words [wa, va) and [vb, wb) one by one, [va, vb) four at a time
   // (the HARQ entry is 16-byte aligned). These loops are what the kernel spends its issue slots on.

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(TB_THREADS) tb_assemble_kernel(TbParams prm, c
       uint32_t cb  = q / n_data;
       uint32_t off = q - cb * n_data;
       for (uint32_t t = first; t < last; ++t) {
+        PDC_ASSERT(cb < tb.nof_cb && off < n_data && n_data <= 8448u);
         const uint8_t* src = harq_data + (size_t)prm.cbs[tb.first_cb + cb].harq_id * PDC_MAX_CB_BYTES;
         uint32_t       w   = cb_bits32(src, off);
         uint32_t       rem = n_data - off; // bits left in this codeblock
