@@ -934,7 +934,11 @@ struct PipePlan {
 static bool plan_pipeline(const pdc_cb_desc* cbs, uint32_t n_cb, size_t n_llrs, const pdc_tb_desc* tbs, uint32_t n_tb,
                           PipePlan& plan)
 {
-  if (n_llrs < PIPE_MIN_BYTES || n_cb < 4) {
+  static const size_t min_bytes = [] {
+    const char* e = getenv("PDC_PIPE_MIN_KB"); // measurement aid: smallest batch that is pipelined
+    return e ? (size_t)atol(e) << 10 : PIPE_MIN_BYTES;
+  }();
+  if (n_llrs < min_bytes || n_cb < 4) {
     return false;
   }
   // Soft bits in codeblock order without overlap (what a demodulator emits), every codeblock dematched from them.

@@ -563,7 +563,137 @@ __device__ __forceinline__ void dm_stage(const DematchGeom& g, const int8_t* __r
 }
 
 // gridDim = (codeblocks, parts). Each CTA owns a contiguous range of the 32-bit words of the HARQ entry.
-__global__ void __launch_bounds__(DM_THREADS, 8) rate_dematch_kernel(BatchParams prm)
+// ---- express path ------------------------------------------------------------------------------------------------------
+// The common new transmission - redundancy version 0, one lap of the circular buffer, everything a multiple of four
+// soft bits - needs neither the staging buffer nor the segment machinery: every output word is four consecutive symbols
+// of one bit plane (straight from a coalesced vector load of 4 symbols x QM planes, separated with byte permutes), a
+// filler word, a stale word (only inspected for the last non-zero soft bit) or zero:
+//   [0, info)            <- deinterleaved input [0, info)
+//   [info, K_sys)        <- +infinity (filler bits)
+//   [K_sys, E + F)       <- deinterleaved input [info, E)
+//   [E + F, zf_lo)       stale (limited buffer only: the reference zeroes relative to the END of the N-long buffer)
+//   [zf_lo, N)           <- 0
+// Same bytes as the general path (the parity tests compare whole HARQ entries); about a quarter of its instructions.
+// Decided by every thread from the descriptor alone (before anything is staged); implies everything dm_express needs
+// from the geometry: no offset (rv 0), one lap at most (E <= Ncb - F), input beyond the systematic part, word alignment
+// of every region boundary but the start of the final zeroing (that word is cut, see dm_express).
+__device__ __forceinline__ bool dm_express_pre(const pdc_cb_desc& d, const int8_t* llr)
+{
+  const int qm = d.qm, bg = d.base_graph, Z = d.lifting_size;
+  if (!(d.flags & PDC_CB_NEW_DATA) || d.rv != 0 || !(qm == 2 || qm == 4 || qm == 6 || qm == 8) || (bg != 1 && bg != 2) ||
+      Z < 2 || Z > MAX_Z) {
+    return false;
+  }
+  const int      N = ((bg == 1) ? 66 : 50) * Z, K_sys = ((bg == 1) ? 20 : 8) * Z, F = d.nof_filler, E = (int)d.rm_length;
+  const int      Ncb = (d.nref > 0) ? min((int)d.nref, N) : N;
+  const uint32_t vec = (qm % 4 == 0) ? 16u : 8u;
+  return (E % (4 * qm)) == 0 && (F & 3) == 0 && (N & 3) == 0 && F < K_sys && Ncb > K_sys && E > K_sys - F &&
+         E + F <= Ncb && (reinterpret_cast<uintptr_t>(llr) % vec) == 0;
+}
+__device__ __forceinline__ bool dm_express_ok(const DematchGeom& g)
+{
+  return g.new_data && !g.wrapped && g.k0 == 0 && g.E > g.info && g.E + g.F <= g.Ncb && (g.N & 3) == 0 &&
+         (g.info & 3) == 0 && g.zf_lo >= g.E + g.F && g.zf_lo <= g.N;
+}
+
+template <int QM>
+__device__ __forceinline__ void dm_express_copy(const DematchGeom& g, const int8_t* __restrict__ llr, uint32_t* out,
+                                                int t0, int nt, DmLast& last)
+{
+  const uint8_t* src      = reinterpret_cast<const uint8_t*>(llr);
+  const int      n_groups = g.Kq >> 2;
+  constexpr int  VEC      = (QM % 4 == 0) ? 16 : 8;
+  constexpr int  U        = (QM <= 2) ? 4 : (QM <= 4 ? 2 : 1); // groups in flight per thread (the loop is latency bound)
+  for (int grp0 = t0; grp0 < n_groups; grp0 += U * nt) {
+    uint32_t w[U][QM];
+#pragma unroll
+    for (int u = 0; u != U; ++u) {
+      const int      grp = grp0 + u * nt;
+      const uint8_t* p   = src + (size_t)grp * 4 * QM;
+      if (grp < n_groups) {
+        if (VEC == 16) {
+#pragma unroll
+          for (int r = 0; r != QM / 4; ++r) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + r);
+            w[u][4 * r] = v.x, w[u][4 * r + 1] = v.y, w[u][4 * r + 2] = v.z, w[u][4 * r + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r != QM / 2; ++r) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p) + r);
+            w[u][2 * r] = v.x, w[u][2 * r + 1] = v.y;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u != U; ++u) {
+      const int grp = grp0 + u * nt;
+      if (grp >= n_groups) {
+        break;
+      }
+      if (g.seq != nullptr) {
+        const uint32_t bits = seq_bits32(g.seq, g.seq_base + (uint32_t)grp * 4u * QM);
+#pragma unroll
+        for (int r = 0; r != QM; ++r) {
+          w[u][r] = negate4(w[u][r], (bits >> (4 * r)) & 0xfu);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j != QM; ++j) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int s4 = 0; s4 != 4; ++s4) {
+          const int off = s4 * QM + j;
+          o |= ((w[u][off >> 2] >> (8 * (off & 3))) & 0xffu) << (8 * s4);
+        }
+        const int i  = j * g.Kq + 4 * grp; // deinterleaved index of the word's first soft bit
+        const int pw = ((i < g.info) ? i : i + g.F) >> 2;
+        PDC_ASSERT(4 * pw + 4 <= g.E + g.F && 4 * pw + 4 <= PDC_MAX_CB_SOFT);
+        out[pw] = o;
+        last.note(pw, o);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void dm_express(const DematchGeom& g, const int8_t* __restrict__ llr, uint32_t* out, int t0,
+                                           int nt, DmLast& last)
+{
+  switch (g.qm) {
+    case 2:
+      dm_express_copy<2>(g, llr, out, t0, nt, last);
+      break;
+    case 4:
+      dm_express_copy<4>(g, llr, out, t0, nt, last);
+      break;
+    case 6:
+      dm_express_copy<6>(g, llr, out, t0, nt, last);
+      break;
+    default:
+      dm_express_copy<8>(g, llr, out, t0, nt, last);
+      break;
+  }
+  for (int w = (g.info >> 2) + t0; w < (g.K_sys >> 2); w += nt) {
+    out[w] = 0x7f7f7f7fu;
+    last.note(w, 0x7f7f7f7fu);
+  }
+  for (int w = ((g.E + g.F) >> 2) + t0; w < (g.zf_lo >> 2); w += nt) {
+    last.note(w, out[w]); // stale soft bits still count for the decoder's trimming
+  }
+  if ((g.zf_lo & 3) != 0 && t0 == 0) {
+    // the word the final zeroing starts in: its first bytes stay, the rest is zeroed
+    const int      w = g.zf_lo >> 2;
+    const uint32_t r = out[w] & (0xffffffffu >> (8 * (4 - (g.zf_lo & 3))));
+    out[w]           = r;
+    last.note(w, r);
+  }
+  for (int w = ((g.zf_lo + 3) >> 2) + t0; w < (g.N >> 2); w += nt) {
+    out[w] = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(DM_THREADS, 6) rate_dematch_kernel(BatchParams prm)
 {
   __shared__ __align__(16) uint8_t sh_in[DM_STAGE_BYTES + 16];
   __shared__ DematchGeom           g_sh;
@@ -602,8 +732,10 @@ __global__ void __launch_bounds__(DM_THREADS, 8) rate_dematch_kernel(BatchParams
   }
   uint32_t* out = reinterpret_cast<uint32_t*>(prm.harq + (size_t)min(d.harq_id, prm.harq_entries - 1) * PDC_MAX_CB_SOFT);
   const int     qm = d.qm, E = d.rm_length;
-  const bool    staged = (qm == 1 || qm == 2 || qm == 4 || qm == 6 || qm == 8) && E > 0 && (E % qm) == 0 &&
-                      E <= DM_STAGE_BYTES;
+  // Express path candidates skip the staging; the geometry (first warp) has the last word.
+  const bool    express_pre = dm_express_pre(d, llr);
+  const bool    staged = !express_pre && (qm == 1 || qm == 2 || qm == 4 || qm == 6 || qm == 8) && E > 0 &&
+                      (E % qm) == 0 && E <= DM_STAGE_BYTES;
   if (tid < 32) {
     if (tid == 0) {
       ok            = dm_geometry(d, prm.simd_width, g_sh) && (d.harq_id < prm.harq_entries);
@@ -612,7 +744,11 @@ __global__ void __launch_bounds__(DM_THREADS, 8) rate_dematch_kernel(BatchParams
       sh_last       = 0;
     }
     __syncwarp();
-    if (ok && g_sh.staged && g_sh.E <= g_sh.Dn) {
+    if (ok && express_pre) {
+      if (tid == 0) {
+        g_sh.staged = 0; // nothing was staged: whatever the express path does not take goes position by position
+      }
+    } else if (ok && g_sh.staged && g_sh.E <= g_sh.Dn) {
       // Sort the breakpoints (rank by counting) and classify the segments between them.
       const int mine = dm_breakpoint(g_sh, min(tid, DM_MAX_BP - 1));
       int       rank = 0;
@@ -653,7 +789,10 @@ __global__ void __launch_bounds__(DM_THREADS, 8) rate_dematch_kernel(BatchParams
   const int  w_lo = (int)blockIdx.y * per;
   const int  w_hi = min(nw, w_lo + per);
   DmLast last;
-  if (fast) {
+  PDC_ASSERT(!express_pre || dm_express_ok(g_sh));
+  if (express_pre && dm_express_ok(g_sh)) {
+    dm_express(g_sh, llr, out, (int)blockIdx.y * (int)blockDim.x + tid, (int)gridDim.y * (int)blockDim.x, last);
+  } else if (fast) {
     // Words cut by a breakpoint (and the incomplete last word): one thread per soft bit, the four of a word side by
     // side; the HARQ word is requested before the segment loops and used after them.
     const bool cut_thread = tid < 4 * DM_MAX_BP;
