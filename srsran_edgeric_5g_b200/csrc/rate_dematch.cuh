@@ -456,6 +456,42 @@ __device__ __forceinline__ void dm_segment_words(const DematchGeom& g, const int
   }
 }
 
+// Bit-plane separation of a group of four symbols (w[]: 4 * QM bytes, symbol after symbol): o[j] = the four soft bits of
+// plane j. Byte permutes: one per plane for QPSK, three for 16QAM / 256QAM (pairs of symbols, then the pair of pairs);
+// 64QAM (symbols of six bytes straddle words) goes byte by byte.
+template <int QM>
+__device__ __forceinline__ void dm_planes(const uint32_t (&w)[QM], uint32_t (&o)[QM])
+{
+  if (QM == 2) {
+    o[0] = __byte_perm(w[0], w[1], 0x6420);
+    o[1] = __byte_perm(w[0], w[1], 0x7531);
+  } else if (QM == 4) {
+#pragma unroll
+    for (int j = 0; j != QM; ++j) {
+      const uint32_t sel = (uint32_t)(((4 + j) << 4) | j);
+      o[j] = __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410);
+    }
+  } else if (QM == 8) {
+#pragma unroll
+    for (int j = 0; j != QM; ++j) {
+      const uint32_t sel = (uint32_t)(((4 + (j & 3)) << 4) | (j & 3));
+      const int      h   = j >> 2; // planes 4-7 sit in the second word of a symbol
+      o[j] = __byte_perm(__byte_perm(w[h], w[2 + h], sel), __byte_perm(w[4 + h], w[6 + h], sel), 0x5410);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j != QM; ++j) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int s4 = 0; s4 != 4; ++s4) {
+        const int off = s4 * QM + j;
+        v |= ((w[off >> 2] >> (8 * (off & 3))) & 0xffu) << (8 * s4);
+      }
+      o[j] = v;
+    }
+  }
+}
+
 // Stage the rate-matched input in shared memory in deinterleaved order: sh[j * Kq + sym] = llr[sym * QM + j].
 // Four symbols per thread step: coalesced vector loads, bit planes separated with byte permutes.
 template <int QM>
@@ -504,15 +540,12 @@ __device__ __forceinline__ void dm_stage_planes(const DematchGeom& g, const int8
         w[r] = negate4(w[r], (bits >> (4 * r)) & 0xfu);
       }
     }
+    uint32_t ow[QM];
+    dm_planes<QM>(w, ow);
 #pragma unroll
     for (int j = 0; j != QM; ++j) {
-      uint32_t o = 0;
-#pragma unroll
-      for (int s4 = 0; s4 != 4; ++s4) {
-        const int off = s4 * QM + j;
-        o |= ((w[off >> 2] >> (8 * (off & 3))) & 0xffu) << (8 * s4);
-      }
-      uint8_t* dst = sh + j * g.Kq + 4 * grp;
+      const uint32_t o   = ow[j];
+      uint8_t*       dst = sh + j * g.Kq + 4 * grp;
       if (word_st) {
         *reinterpret_cast<uint32_t*>(dst) = o;
       } else {
@@ -639,16 +672,13 @@ __device__ __forceinline__ void dm_express_copy(const DematchGeom& g, const int8
           w[u][r] = negate4(w[u][r], (bits >> (4 * r)) & 0xfu);
         }
       }
+      uint32_t ow[QM];
+      dm_planes<QM>(w[u], ow);
 #pragma unroll
       for (int j = 0; j != QM; ++j) {
-        uint32_t o = 0;
-#pragma unroll
-        for (int s4 = 0; s4 != 4; ++s4) {
-          const int off = s4 * QM + j;
-          o |= ((w[u][off >> 2] >> (8 * (off & 3))) & 0xffu) << (8 * s4);
-        }
-        const int i  = j * g.Kq + 4 * grp; // deinterleaved index of the word's first soft bit
-        const int pw = ((i < g.info) ? i : i + g.F) >> 2;
+        const uint32_t o = ow[j];
+        const int      i = j * g.Kq + 4 * grp; // deinterleaved index of the word's first soft bit
+        const int      pw = ((i < g.info) ? i : i + g.F) >> 2;
         PDC_ASSERT(4 * pw + 4 <= g.E + g.F && 4 * pw + 4 <= PDC_MAX_CB_SOFT);
         out[pw] = o;
         last.note(pw, o);
