@@ -601,6 +601,30 @@ struct LaneInfo {
   int done;  // 1: early stop reached, 2: all-zero input
 };
 
+// Static shared memory of the kernel (one object, see the kernel).
+template <int MAX_THREADS>
+struct PairShared {
+  __align__(16) uint32_t sh_desc[2][8];              // the two descriptors of the pair
+  unsigned long long     sh_part[2][MAX_THREADS / 32]; // per-warp unreduced CRC remainders
+  uint32_t               sh_red[2][32];              // x^(order + k) mod P of each codeblock's CRC
+  LaneInfo               lane[2];
+  int                    sh_last[2];
+  int                    sh_zpart[MAX_THREADS / 32]; // per-warp "a message soft bit is zero" flags
+  int                    sh_publish[2];
+  pdc_cb_result          sh_result[2];
+  int                    sh_defer_b; // codeblock B could not be decoded together with A: it gets its own pass
+  uint32_t               sh_next_pair;
+};
+// Shared-window address of the dynamic shared memory of a CTA that is not part of a cluster: the driver reserves the
+// first KB, the static object follows, the dynamic part starts at the next multiple of 16. With the address a compile-
+// time constant the compiled-in rows reach every soft word as [register + immediate]; the kernel compares it with the
+// real address and takes the table-driven rows if a future toolkit lays shared memory out differently.
+template <int MAX_THREADS>
+__host__ __device__ constexpr uint32_t spec_soft_base()
+{
+  return 0x400u + (((uint32_t)sizeof(PairShared<MAX_THREADS>) + 15u) & ~15u);
+}
+
 __host__ __device__ inline size_t h2_smem_bytes(int bg, int Z)
 {
   int    n_full = (bg == 1) ? 68 : 52;
@@ -618,16 +642,19 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
                           uint32_t counter_base)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ LaneInfo lane[2];
-  __shared__ int      sh_last[2];
-  __shared__ unsigned long long sh_part[2][MAX_THREADS / 32]; // per-warp unreduced CRC remainders
-  __shared__ int                sh_zpart[MAX_THREADS / 32];   // per-warp "a message soft bit is zero" flags
-  __shared__ uint32_t           sh_red[2][32];                // x^(order + k) mod P of each codeblock's CRC
-  __shared__ int                sh_publish[2];
-  __shared__ pdc_cb_result      sh_result[2];
-  __shared__ int      sh_defer_b; // codeblock B could not be decoded together with A: it gets its own pass
-  __shared__ uint32_t sh_next_pair;
-  __shared__ __align__(16) uint32_t sh_desc[2][8];                       // the two descriptors of the pair
+  // All statically allocated shared memory of the kernel is ONE object, so that its size - and with it the shared-window
+  // address at which the dynamic part (the soft bits) starts - is known at compile time (SPEC_SOFT_BASE below).
+  __shared__ PairShared<MAX_THREADS> ps;
+  LaneInfo (&lane)[2]                             = ps.lane;
+  int (&sh_last)[2]                               = ps.sh_last;
+  unsigned long long (&sh_part)[2][MAX_THREADS / 32] = ps.sh_part;
+  int (&sh_zpart)[MAX_THREADS / 32]               = ps.sh_zpart;
+  uint32_t (&sh_red)[2][32]                       = ps.sh_red;
+  int (&sh_publish)[2]                            = ps.sh_publish;
+  pdc_cb_result (&sh_result)[2]                   = ps.sh_result;
+  int&      sh_defer_b                            = ps.sh_defer_b;
+  uint32_t& sh_next_pair                          = ps.sh_next_pair;
+  uint32_t (&sh_desc)[2][8]                       = ps.sh_desc;
 
   const int tid  = threadIdx.x;
   const int nthr = blockDim.x;
@@ -715,7 +742,10 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       const int          K       = kb * Z;
       const int          N       = (n_full - 2) * Z;
       const int          n_words = (K + 31) / 32;
-      const bool         spec    = (SPEC_Z != 0) && bg == 1 && Z == SPEC_Z; // the compiled-in row program applies
+      // the compiled-in row program applies (and the soft bits are where it expects them)
+      const bool spec = (SPEC_Z != 0) && bg == 1 && Z == SPEC_Z &&
+                        (uint32_t)__cvta_generic_to_shared(smem_raw) == spec_soft_base<MAX_THREADS>();
+      PDC_ASSERT((uint32_t)__cvta_generic_to_shared(smem_raw) == spec_soft_base<MAX_THREADS>());
 
       // Carve shared memory.
       size_t off  = 0;
@@ -954,8 +984,9 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           if (spec) {
             // The leading rows of the hot shape run from the compiled-in program, the rest from the tables.
             // (the kernel with a compiled-in program is only launched for the x86 scale rule)
+            constexpr uint32_t soft_c = spec_soft_base<MAX_THREADS>(); // == soft_s (checked above)
             spec_rows_from<RowProgram<1, (SPEC_Z != 0 ? SPEC_Z : 384)>, 0, H2_SPEC_ROWS, PDC_SCALE_X86>(
-                jb, jn4, soft_s, st, st_thread, layers, pol_keep, scale_mode);
+                soft_c + j4, jn4, soft_c, st, st_thread, layers, pol_keep, scale_mode);
             m0 = min(layers, H2_SPEC_ROWS);
             sp = (m0 < layers) ? st_thread + (uint32_t)m0 * st_stride : st_thread;
           }
