@@ -208,16 +208,25 @@ static_assert(half2_of_small_int(1) == 0x3C003C00u && half2_of_small_int(3) == 0
 //   st    : in: compressed messages of this row from the previous iteration; out: those of the NEXT row (fetched from
 //           sp_next as soon as this row's are consumed). This row's new messages are stored to sp.
 //   SCALE : PDC_SCALE_X86 / PDC_SCALE_GENERIC compiled in, or -1: scale_mode decides at run time.
-template <int DEG, int SCALE>
-__device__ __forceinline__ void row_math(const uint32_t (&addr)[DEG], RowState& st, uint4* sp, const uint4* sp_next,
-                                         uint64_t pol, int scale_mode)
+// What pass 1 of a row hands to pass 2.
+template <int DEG>
+struct RowPass {
+  __half2 vc[DEG]; // soft - c2v_old clamped to +-120, infinite if the soft bit was infinite
+  __half2 min1, min2;
+  hh      par;
+};
+
+// Pass 1: variable-to-check messages of the row's edges (st: the row's compressed messages of the previous iteration),
+// their two smallest magnitudes and the sign parity.
+template <int DEG>
+__device__ __forceinline__ void row_pass1(const uint32_t (&addr)[DEG], const RowState& st, RowPass<DEG>& rp)
 {
   constexpr bool PACKED_MIN = DEG > 16;
   constexpr int  F0         = PACKED_MIN ? 1 : 2; // index of the first flag word
 
-  __half2 vc[DEG]; // soft - c2v_old clamped to +-120, infinite if the soft bit was infinite
+  __half2 (&vc)[DEG] = rp.vc;
 
-  const __half2 one = H(H_ONE), h120 = H(H_120), hn120 = H(H_N120);
+  const __half2 h120 = H(H_120), hn120 = H(H_N120);
 
   // Old scaled minima: the message of an edge has magnitude min1, that of the edge which held the minimum min2.
   __half2 m1, m2;
@@ -265,8 +274,18 @@ __device__ __forceinline__ void row_math(const uint32_t (&addr)[DEG], RowState& 
     }
   }
 
-  // This row's old messages are consumed: fetch those of the next row into the same registers.
-  st = ld_state(sp_next, pol);
+  rp.min1 = min1, rp.min2 = min2, rp.par = par;
+}
+
+// Pass 2: scaled minima, new check-to-variable messages, soft-bit update, and the row's new compressed messages to sp.
+template <int DEG, int SCALE>
+__device__ __forceinline__ void row_pass2(const uint32_t (&addr)[DEG], const RowPass<DEG>& rp, uint4* sp, uint64_t pol,
+                                          int scale_mode)
+{
+  constexpr bool PACKED_MIN = DEG > 16;
+  const __half2 (&vc)[DEG]  = rp.vc;
+  const __half2 one = H(H_ONE), min1 = rp.min1, min2 = rp.min2;
+  const hh      par = rp.par;
 
   // Scaled minima. x86: (x * 52428) >> 16 == ceil(0.8 x) - 1 for x >= 1, 0 for x = 0;
   // generic: round(0.8 x). Both are computed exactly through round-to-nearest in the [1024, 2048) binade.
@@ -337,6 +356,17 @@ __device__ __forceinline__ void row_math(const uint32_t (&addr)[DEG], RowState& 
   st_state(sp, st_out, pol);
 }
 
+// One row: pass 1, fetch of the next row's compressed messages into the registers this row's were in, pass 2.
+template <int DEG, int SCALE>
+__device__ __forceinline__ void row_math(const uint32_t (&addr)[DEG], RowState& st, uint4* sp, const uint4* sp_next,
+                                         uint64_t pol, int scale_mode)
+{
+  RowPass<DEG> rp;
+  row_pass1<DEG>(addr, st, rp);
+  st = ld_state(sp_next, pol);
+  row_pass2<DEG, SCALE>(addr, rp, sp, pol, scale_mode);
+}
+
 // Table-driven row: the addresses of the row's soft words come from the edge table in shared memory.
 //   e_info : shared-window address of the row's edge table
 template <int DEG>
@@ -397,7 +427,9 @@ __device__ __forceinline__ void dispatch_row(int deg, uint32_t e_info, uint32_t 
 // by it). The arithmetic (row_math) is shared with the table-driven rows.
 //
 // How many rows: unrolled code is 16 bytes x ~29 instructions per edge, and the row loop has to stay inside the
-// instruction cache. Measured on B200 (8192 codeblocks BG1 Z = 384, 46 rows, 6 iterations; table-driven loop 4.14 ms):
+// instruction cache. (Two consecutive rows that share no variable node as ONE block of code - both first passes, then both
+// second passes, so that the compiler has two independent instruction streams to interleave - measured 3 % SLOWER than
+// row after row: 3.56 vs 3.46 ms.) Measured on B200 (8192 codeblocks BG1 Z = 384, 46 rows, 6 iterations; table-driven loop 4.14 ms):
 // rows 0-3 compiled in 4.13 ms, 0-7 4.03, 0-11 3.92, 0-15 3.84, 0-23 3.82, all 46 (147 KB of code) 6.24 ms. A variant
 // with per-row address stubs jumping into one shared body per degree (41 KB) measured 4.26 ms: the indirect branch per
 // row costs more than the instructions it saves.
