@@ -624,6 +624,21 @@ __device__ __forceinline__ void sweep_word(const hh* soft, const uint2* wgt, int
   }
 }
 
+// -DH2_PHASE_TIMING (tools/phase_probe.py): CTA 0 records the global timer at the phase boundaries of its first pair.
+#ifdef H2_PHASE_TIMING
+__device__ unsigned long long g_h2_phase[16];
+#define H2_PHASE(k)                                                                                                    \
+  do {                                                                                                                 \
+    if (threadIdx.x == 0 && blockIdx.x == 0) {                                                                         \
+      unsigned long long t_;                                                                                           \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                           \
+      g_h2_phase[k] = t_;                                                                                              \
+    }                                                                                                                  \
+  } while (0)
+#else
+#define H2_PHASE(k) ((void)0)
+#endif
+
 // Per-codeblock bookkeeping of the pair.
 struct LaneInfo {
   int valid; // a codeblock is decoded in this half during the current pass
@@ -690,6 +705,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
 
   const int tid  = threadIdx.x;
   const int nthr = blockDim.x;
+  H2_PHASE(0);
 
   // Persistent CTAs: pair p = codeblocks 2p and 2p+1 of the batch. They are decoded together when they share the lifted
   // graph, the iteration count and the number of rows in use; otherwise one after the other.
@@ -796,7 +812,9 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       // Programmatic dependent launch: this kernel may have started while the rate dematcher of the same batch was still
       // draining. Everything above reads only what was complete before the dematcher started (descriptors); what follows
       // reads what it wrote (soft bits, last non-zero positions).
+      H2_PHASE(1);
       asm volatile("griddepcontrol.wait;" ::: "memory");
+      H2_PHASE(2);
       // Last non-zero input of each codeblock (ldpc_decoder_impl.cpp:86-99), recorded by the rate dematcher: the loads
       // are issued here and consumed after the tables are in place.
       const int8_t* in[2];
@@ -856,6 +874,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           cur_wkey1 = wkey1;
         }
       }
+      H2_PHASE(3);
       // Last non-zero input of each codeblock (ldpc_decoder_impl.cpp:86-99): recorded by the rate dematcher for the
       // entries it wrote; entries of unknown content are scanned.
       const uint64_t pol_stream = l2_policy_evict_first();
@@ -914,6 +933,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         }
       }
       __syncthreads();
+      H2_PHASE(4);
       // load_soft_bits (ldpc_decoder_impl.cpp:149-184): two punctured nodes at zero, whole nodes clamped to +-64; only
       // the variable nodes of the rows in use are needed. int8 -> half through the 1024 binade: 0x6400 | (v + 128) is
       // the half 1024 + v + 128.
@@ -973,6 +993,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         }
       }
       __syncthreads();
+      H2_PHASE(5);
       // All-zero codeblocks without a CRC calculator output all ones.
       for (int h = 0; h != 2; ++h) {
         if (lane[h].done == 2 && lane[h].crc_kind == PDC_CRC_NONE) {
@@ -1009,7 +1030,11 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       const uint32_t row_info_s = (uint32_t)__cvta_generic_to_shared(g.row_info);
       RowState       st         = make_uint4(0, 0, 0, 0);
       const uint32_t jb = soft_s + j4, jn4 = j4 - 4u * (uint32_t)Z;
+      H2_PHASE(6);
       for (int it = 0; it < max_iter; ++it) {
+        if (it == 1) {
+          H2_PHASE(7);
+        }
         uint4* sp = st_thread;
         int    m0 = 0;
         if constexpr (SPEC_Z != 0) {
@@ -1037,6 +1062,9 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
           }
         }
 
+        if (it + 1 == max_iter) {
+          H2_PHASE(8);
+        }
         const bool last_it   = (it + 1 == max_iter);
         const bool any_early = (lane[0].valid && lane[0].early && !lane[0].done) ||
                                (lane[1].valid && lane[1].early && !lane[1].done);
@@ -1147,6 +1175,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
       }
     }
     __syncthreads();
+    H2_PHASE(9);
     if (tid == 0) {
       // The counter is never reset: every decoded pair takes exactly one ticket, so a launch advances it by its number
       // of pairs and the host passes the value it had before the launch.
@@ -1158,6 +1187,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
   // A CTA that never reached the wait above (only invalid codeblocks) must not let the grid complete ahead of the
   // kernel it was serialized behind: the next kernel's wait relies on this one for the ordering.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  H2_PHASE(10);
 }
 
 } // namespace h2

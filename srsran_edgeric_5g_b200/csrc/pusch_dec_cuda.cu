@@ -2259,3 +2259,14 @@ int pdc_launch_encode_device(pdc_ctx*    ctx,
   p.out_capacity = (uint32_t)out_capacity;
   return launch_encode(ctx, p, (int)max_lifting_size, any_bg1 != 0, 0, static_cast<cudaStream_t>(cuda_stream));
 }
+
+#ifdef H2_PHASE_TIMING
+// Timing build only (tools/phase_probe.py): the global-timer stamps CTA 0 of the last decode launch left at its phase
+// boundaries.
+extern "C" int pdc_debug_read_phases(unsigned long long* out16)
+{
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out16, pdc::h2::g_h2_phase, sizeof(unsigned long long) * 16) == cudaSuccess ? PDC_OK
+                                                                                                          : PDC_ERR_CUDA;
+}
+#endif
