@@ -40,6 +40,14 @@ __device__ __forceinline__ hh lop_and_or(hh a, hh b, hh c) // (a & b) | c
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
   return r;
 }
+// min(|a|, |b|) carrying the product of the two signs (HMNMX2.XORSIGN): a clamp of a to +-|b| when b is the bound, and
+// a running minimum of magnitudes that accumulates the sign parity in its sign bit.
+__device__ __forceinline__ __half2 min_abs_xorsign(__half2 a, __half2 b)
+{
+  hh r;
+  asm("min.xorsign.abs.f16x2 %0, %1, %2;" : "=r"(r) : "r"(*reinterpret_cast<hh*>(&a)), "r"(*reinterpret_cast<hh*>(&b)));
+  return *reinterpret_cast<__half2*>(&r);
+}
 __device__ __forceinline__ hh lop_xor_and(hh a, hh b, hh c) // a ^ (b & c)
 {
   hh r;
@@ -226,7 +234,7 @@ __device__ __forceinline__ void row_pass1(const uint32_t (&addr)[DEG], const Row
 
   __half2 (&vc)[DEG] = rp.vc;
 
-  const __half2 h120 = H(H_120), hn120 = H(H_N120);
+  const __half2 h120 = H(H_120);
 
   // Old scaled minima: the message of an edge has magnitude min1, that of the edge which held the minimum min2.
   __half2 m1, m2;
@@ -240,8 +248,8 @@ __device__ __forceinline__ void row_pass1(const uint32_t (&addr)[DEG], const Row
   const __half2 d12 = __hsub2(m1, m2);
   const __half2 idx_old = H(st.w);
 
-  __half2 min1 = h120, min2 = h120, a_prev = h120;
-  hh      par = 0;
+  // min1 carries the sign parity of the edges seen so far in its sign bits (min_abs_xorsign); its magnitude is the minimum.
+  __half2 min1 = h120, min2 = h120, c_prev = h120;
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
     const hh      f    = st_word(st, F0 + (e >> 4));
@@ -253,28 +261,26 @@ __device__ __forceinline__ void row_pass1(const uint32_t (&addr)[DEG], const Row
     const __half2 v    = __hfma2(sg, nmag, s);          // s - c2v_old; |v| <= 222, or infinite with s
     // Clamp to +-120 but keep infinity: v * 2^-13 is less than half a unit in the last place of the clamped value for
     // every finite v (|v| <= 222), so the sum rounds back to it, and infinite for an infinite v.
-    const __half2 c = __hfma2(v, H(H_2M13), __hmax2(__hmin2(v, h120), hn120));
+    const __half2 c = __hfma2(v, H(H_2M13), min_abs_xorsign(v, h120));
     vc[e]           = c;
-    par ^= U(c);
     // Two smallest magnitudes of the row, edges taken in pairs (shorter dependency chain, three-input minimum).
-    const __half2 a = __habs2(c);
     if ((e & 1) == 0 && e != DEG - 1) {
-      a_prev = a;
+      c_prev = c;
     } else if (e == 1) {
       // first pair: the minima start at 120 (an infinite magnitude counts as 120)
-      min1 = __hmin2(__hmin2(a_prev, a), h120);
-      min2 = __hmin2(__hmax2(a_prev, a), h120);
+      min1 = min_abs_xorsign(min_abs_xorsign(c_prev, c), h120);
+      min2 = __hmin2(__hmax2(__habs2(c_prev), __habs2(c)), h120);
     } else if (e & 1) {
-      const __half2 lo = __hmin2(a_prev, a), hi = __hmax2(a_prev, a);
-      min2             = __hmin2(__hmin2(min2, hi), __hmax2(min1, lo));
-      min1             = __hmin2(min1, lo);
+      const __half2 lo = min_abs_xorsign(c_prev, c), hi = __hmax2(__habs2(c_prev), __habs2(c));
+      min2             = __hmin2(__hmin2(min2, hi), __hmax2(__habs2(min1), __habs2(lo)));
+      min1             = min_abs_xorsign(min1, lo);
     } else {
-      min2 = __hmin2(min2, __hmax2(min1, a));
-      min1 = __hmin2(min1, a);
+      min2 = __hmin2(min2, __hmax2(__habs2(min1), __habs2(c)));
+      min1 = min_abs_xorsign(min1, c);
     }
   }
 
-  rp.min1 = min1, rp.min2 = min2, rp.par = par;
+  rp.min1 = __habs2(min1), rp.min2 = min2, rp.par = U(min1);
 }
 
 // Pass 2: scaled minima, new check-to-variable messages, soft-bit update, and the row's new compressed messages to sp.
@@ -426,17 +432,21 @@ __device__ __forceinline__ void dispatch_row(int deg, uint32_t e_info, uint32_t 
 // addresses need no instruction at all (see the generator: per-row thread offset tau_m, extension nodes stored rotated
 // by it). The arithmetic (row_math) is shared with the table-driven rows.
 //
-// How many rows: unrolled code is 16 bytes x ~29 instructions per edge, and the row loop has to stay inside the
-// instruction cache. (Two consecutive rows that share no variable node as ONE block of code - both first passes, then both
-// second passes, so that the compiler has two independent instruction streams to interleave - measured 3 % SLOWER than
-// row after row: 3.56 vs 3.46 ms.) Measured on B200 (8192 codeblocks BG1 Z = 384, 46 rows, 6 iterations; table-driven loop 4.14 ms):
-// rows 0-3 compiled in 4.13 ms, 0-7 4.03, 0-11 3.92, 0-15 3.84, 0-23 3.82, all 46 (147 KB of code) 6.24 ms. A variant
-// with per-row address stubs jumping into one shared body per degree (41 KB) measured 4.26 ms: the indirect branch per
-// row costs more than the instructions it saves.
+// How many rows: unrolled code is 16 bytes x ~25 instructions per edge, and the row loop has a size above which the
+// instruction fetch cannot keep up. With ~29 instructions per edge (first versions of this kernel; 8192 codeblocks BG1
+// Z = 384, 46 rows, 6 iterations; table-driven loop 4.14 ms) rows 0-3 compiled in measured 4.13 ms, 0-7 4.03, 0-11 3.92,
+// 0-15 3.84, 0-23 3.82, and all 46 (147 KB of loop) 6.24 ms. With the arithmetic of today (131 KB for all 46 rows) the
+// cliff is not reached: 28 rows 3.39 ms per step, 30 3.33, 32 3.32, 34 3.28, 40 3.28, 43 3.28, all 46 3.20 ms - a
+// table-driven row costs ~200 instructions (27 of them loop control and the jump to the body of its degree) where a
+// compiled-in row of degree 5 costs ~160. Anything that grows the code per edge has to be re-measured against this.
+// (Two consecutive rows that share no variable node as ONE block of code - both first passes, then both second passes, so
+// that the compiler has two independent instruction streams to interleave - measured 3 % SLOWER than row after row. A
+// variant with per-row address stubs jumping into one shared body per degree (41 KB) measured 4.26 ms: the indirect branch
+// per row costs more than the instructions it saves.)
 #include "row_programs.inc"
 
 #ifndef H2_SPEC_ROWS
-#define H2_SPEC_ROWS 28
+#define H2_SPEC_ROWS 46
 #endif
 
 template <int... Is, class F>
@@ -479,7 +489,10 @@ __device__ __forceinline__ void spec_row(uint32_t jb, uint32_t jn4, uint32_t sof
     addr[e]         = spec_edge_addr<P, M, e>(jb, jn4, soft_s);
   });
   if (!P::NOBAR[M]) {
-    row_barrier();
+    // every thread of the CTA is active in a compiled-in shape (Z a multiple of 32) and arrives from the same place: the
+    // aligned barrier, without the divergence check the non-aligned form is compiled with
+    static_assert(P::Z % 32 == 0, "compiled-in shapes have whole warps");
+    asm volatile("barrier.sync.aligned 0;" ::: "memory");
   }
   // The next row in use (its old messages are fetched while this row's are processed).
   const uint4* spn;
