@@ -117,6 +117,22 @@ __device__ __forceinline__ uint4 ld_state(const uint4* p, uint64_t pol)
                : "l"(p), "l"(pol));
   return v;
 }
+// The same from base + off (a compile-time byte offset) if `far`, else from base: two predicated loads instead of a select
+// and a 64-bit add in front of one.
+template <uint32_t OFF>
+__device__ __forceinline__ uint4 ld_state_sel(const uint4* base, bool far, uint64_t pol)
+{
+  uint4 v;
+  asm volatile("{\n\t"
+               ".reg .pred p;\n\t"
+               "setp.ne.u32 p, %6, 0;\n\t"
+               "@p ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4+%7], %5;\n\t"
+               "@!p ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;\n\t"
+               "}"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(base), "l"(pol), "r"((uint32_t)far), "n"(OFF));
+  return v;
+}
 __device__ __forceinline__ void st_state(uint4* p, const uint4& v, uint64_t pol)
 {
   asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
@@ -326,9 +342,11 @@ __device__ __forceinline__ void row_pass2(const uint32_t (&addr)[DEG], const Row
     const __half2 pe = __hfma2_relu(__habs2(x), H(H_544), H(H_N65280));
     const __half2 r  = __hfma2(x, pe, x);
     sts_u32(addr[e], U(r));
-    acc_s = __hfma2(acc_s, H(H_TWO), sgn);                    // sum of +-2^k; turned into "negative" bits below
+    // sum of +-2^k over the edges of a group of eight; turned into "negative" bits below
+    acc_s = ((e & 7) == 0) ? sgn : __hfma2(acc_s, H(H_TWO), sgn);
     // index of an edge that holds the minimum (with several, min2 == min1 and any of them serves): (ism & e) | (~ism & idx)
-    {
+    // (edge 0 leaves the initial 0)
+    if (e != 0) {
       asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(idx) : "r"(ism), "r"(half2_of_small_int(e)), "r"(idx));
     }
     if ((e & 7) == 7 || e == DEG - 1) {
@@ -494,16 +512,17 @@ __device__ __forceinline__ void spec_row(uint32_t jb, uint32_t jn4, uint32_t sof
     static_assert(P::Z % 32 == 0, "compiled-in shapes have whole warps");
     asm volatile("barrier.sync.aligned 0;" ::: "memory");
   }
-  // The next row in use (its old messages are fetched while this row's are processed).
-  const uint4* spn;
+  // Pass 1, fetch of the old messages of the next row in use into the registers this row's were in, pass 2.
+  RowPass<DEG> rp;
+  row_pass1<DEG>(addr, st, rp);
   if (M + 1 < 4) {
-    spn = st_thread + (M + 1) * STRIDE;
+    st = ld_state(st_thread + (M + 1) * STRIDE, pol);
   } else if (M + 1 == P::ROWS) {
-    spn = st_thread;
+    st = ld_state(st_thread, pol);
   } else {
-    spn = (M + 1 < layers) ? st_thread + (M + 1) * STRIDE : st_thread;
+    st = ld_state_sel<(uint32_t)((M + 1) * STRIDE * sizeof(uint4))>(st_thread, M + 1 < layers, pol);
   }
-  row_math<DEG, SCALE>(addr, st, st_thread + M * STRIDE, spn, pol, scale_mode);
+  row_pass2<DEG, SCALE>(addr, rp, st_thread + M * STRIDE, pol, scale_mode);
 }
 
 // Rows M .. END-1 of one iteration; stops after the last row in use (at least four rows are always in use).
@@ -1050,6 +1069,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         }
         uint4* sp = st_thread;
         int    m0 = 0;
+        bool   table_rows = true;
         if constexpr (SPEC_Z != 0) {
           if (spec) {
             // The leading rows of the hot shape run from the compiled-in program, the rest from the tables.
@@ -1057,11 +1077,15 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
             constexpr uint32_t soft_c = spec_soft_base<MAX_THREADS>(); // == soft_s (checked above)
             spec_rows_from<RowProgram<1, (SPEC_Z != 0 ? SPEC_Z : 384)>, 0, H2_SPEC_ROWS, PDC_SCALE_X86>(
                 soft_c + j4, jn4, soft_c, st, st_thread, layers, pol_keep, scale_mode);
-            m0 = min(layers, H2_SPEC_ROWS);
-            sp = (m0 < layers) ? st_thread + (uint32_t)m0 * st_stride : st_thread;
+            if constexpr (H2_SPEC_ROWS >= 46) {
+              table_rows = false; // the whole schedule is compiled in: nothing left for the table-driven loop
+            } else {
+              m0 = min(layers, H2_SPEC_ROWS);
+              sp = (m0 < layers) ? st_thread + (uint32_t)m0 * st_stride : st_thread;
+            }
           }
         }
-        for (int m = m0; m < layers; ++m) {
+        for (int m = m0; table_rows && m < layers; ++m) {
           if (active) {
             const uint32_t info = lds_u32(row_info_s + 4u * (uint32_t)m);
             const int      e0   = info & 0xffffu;
