@@ -471,7 +471,8 @@ __device__ __forceinline__ void dispatch_row(int deg, uint32_t e_info, uint32_t 
 #endif
 // The first H2_SPEC_FROM rows (0 or 4: the four degree-19 rows of BG1, 21 % of the unrolled code) run from ONE
 // table-driven copy of their code instead: 48 instructions more per row for the addresses, 20 KB less code to fetch -
-// measured 2.96 vs 3.05 ms per step (instruction-cache hit rate of the all-unrolled loop: 89 %).
+// measured 2.96 vs 3.05 ms per step (instruction-cache hit rate of the all-unrolled loop: 89 %). The same for the longest
+// runs of equal degree further down (rows 28-36, degree 5; rows 16-21, degree 6) measured SLOWER: 3.01 and 3.03 vs 2.98 ms.
 #ifndef H2_SPEC_FROM
 #define H2_SPEC_FROM 4
 #endif
@@ -1088,8 +1089,10 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
             // The first rows (all of one degree in BG1, always in use) from ONE copy of the code, table-driven addresses.
 #pragma unroll 1
             for (int m = 0; m != H2_SPEC_FROM; ++m) {
-              process_row<19>(einfo_s + 8u * 20u * (uint32_t)m, j4, neg_Z4, st, st_thread + (uint32_t)m * st_stride,
-                              st_thread + (uint32_t)(m + 1) * st_stride, pol_keep, PDC_SCALE_X86, true);
+              // (a codeblock that uses only these rows wraps around to row 0 behind the last of them)
+              const uint4* spn = (m + 1 < layers) ? st_thread + (uint32_t)(m + 1) * st_stride : st_thread;
+              process_row<19>(einfo_s + 8u * 20u * (uint32_t)m, j4, neg_Z4, st, st_thread + (uint32_t)m * st_stride, spn,
+                              pol_keep, PDC_SCALE_X86, true);
             }
 #endif
             spec_rows_from<RowProgram<1, (SPEC_Z != 0 ? SPEC_Z : 384)>, H2_SPEC_FROM, H2_SPEC_ROWS, PDC_SCALE_X86>(
