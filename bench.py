@@ -263,7 +263,8 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
 
             def step():
                 ctx.launch_device(d_cbs.data_ptr(), n_cb, d_llr.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), 384,
-                                  flags, True, cuda_stream=stream.cuda_stream, d_tbs=d_tbs.data_ptr(), n_tb=cells,
+                                  flags | capi.LAUNCH_HIGH_RATE, True, cuda_stream=stream.cuda_stream,
+                                  d_tbs=d_tbs.data_ptr(), n_tb=cells,
                                   d_tb_results=d_tres.data_ptr(), d_tb_bytes=d_tb.data_ptr())
 
             for _ in range(3):
@@ -313,7 +314,8 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
             def chain():
                 front()
                 ctx.launch_device(d_cbs.data_ptr(), n_cb, d_sch.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), 384,
-                                  flags, True, cuda_stream=stream.cuda_stream, d_tbs=d_tbs.data_ptr(), n_tb=cells,
+                                  flags | capi.LAUNCH_HIGH_RATE, True, cuda_stream=stream.cuda_stream,
+                                  d_tbs=d_tbs.data_ptr(), n_tb=cells,
                                   d_tb_results=d_tres.data_ptr(), d_tb_bytes=d_tb.data_ptr())
 
             # Deferred variant: no UCI in these codewords, so the UL-SCH soft bits are not materialised at all; the rate
@@ -326,7 +328,8 @@ def slot_legs(ctx, orc, capi, torch, stream, args):
                 ctx.launch_codewords_device(cws_def, d_raw.data_ptr(), cells * n_llr, d_sch2.data_ptr(), cells * n_llr,
                                             cuda_stream=stream.cuda_stream)
                 ctx.launch_device(d_cbs.data_ptr(), n_cb, d_sch2.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), 384,
-                                  flags, True, cuda_stream=stream.cuda_stream, d_tbs=d_tbs.data_ptr(), n_tb=cells,
+                                  flags | capi.LAUNCH_HIGH_RATE, True, cuda_stream=stream.cuda_stream,
+                                  d_tbs=d_tbs.data_ptr(), n_tb=cells,
                                   d_tb_results=d_tres.data_ptr(), d_tb_bytes=d_tb.data_ptr())
 
             times = {}

@@ -344,7 +344,11 @@ int pdc_poll(pdc_ctx* ctx, uint32_t stream, int* done);
  * host copies. d_* are device pointers; cuda_stream is a cudaStream_t (0 = default stream); d_tb_* may be 0 when
  * n_tb == 0. The host does not read the descriptors, so the caller states what the batch contains:
  * max_lifting_size = largest Z, flags_union = OR of all pdc_cb_desc::flags, any_bg1 = some codeblock uses base graph 1.
+ * flags_union may also carry PDC_LAUNCH_HIGH_RATE, a hint (results never depend on it): every codeblock is a first
+ * transmission with rv 0 whose rm_length + nof_filler does not exceed 24 Z (base graph 1), i.e. only four base-graph rows are in use
+ * (a 273-PRB 256QAM slot); pdc_submit works this out from the descriptors.
  */
+#define PDC_LAUNCH_HIGH_RATE 0x200u
 int pdc_launch_device(pdc_ctx*    ctx,
                       const void* d_cbs,
                       uint32_t    n_cb,

@@ -19,6 +19,7 @@ CRC_NONE, CRC16, CRC24A, CRC24B = 0, 1, 2, 3
 CRC24C, CRC11, CRC6 = 4, 5, 6  # pdc_crc only
 SCALE_X86, SCALE_GENERIC, SCALE_NEON = 0, 1, 2
 CB_NEW_DATA, CB_EARLY_STOP, CB_DECODE, CB_DEMATCH = 1, 2, 4, 8
+LAUNCH_HIGH_RATE = 0x200  # pdc_launch_device flags_union hint: see PDC_LAUNCH_HIGH_RATE
 
 _u8, _u16, _u32, _i32 = ctypes.c_uint8, ctypes.c_uint16, ctypes.c_uint32, ctypes.c_int32
 _vp = ctypes.c_void_p

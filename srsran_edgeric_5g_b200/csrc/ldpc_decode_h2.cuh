@@ -725,7 +725,11 @@ __host__ __device__ inline size_t h2_smem_bytes(int bg, int Z)
 
 // SPEC_Z: lifting size whose BG1 row program is compiled in (0: none); pairs of any other shape take the table-driven
 // row loop of the same kernel.
-template <int MAX_THREADS, int MIN_BLOCKS, int SPEC_Z>
+// HIGH_RATE: the instantiation for batches of first transmissions whose soft bits end inside the first 24 variable nodes
+// (four rows in use - a 273-PRB 256QAM slot): it also holds a compiled-in copy of rows 0-3 for them. (In the general
+// instantiation that copy, although never executed by a 46-row codeblock, cost the 8192-codeblock step 3 % through the
+// code layout alone: 2.98 vs 2.90 ms; four-row slots lose 7 % without it.)
+template <int MAX_THREADS, int MIN_BLOCKS, int SPEC_Z, bool HIGH_RATE = false>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
     ldpc_decode_h2_kernel(BatchParams prm, hh* state_scratch, uint32_t scratch_stride_words, uint32_t* work_counter,
                           uint32_t counter_base)
@@ -1086,17 +1090,27 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
             // (the kernel with a compiled-in program is only launched for the x86 scale rule)
             constexpr uint32_t soft_c = spec_soft_base<MAX_THREADS>(); // == soft_s (checked above)
 #if H2_SPEC_FROM > 0
-            // The first rows (all of one degree in BG1, always in use) from ONE copy of the code, table-driven addresses.
+            if (!HIGH_RATE || layers != H2_SPEC_FROM) {
+              // The first rows (all of one degree in BG1, always in use) from ONE copy of the code, table-driven addresses.
 #pragma unroll 1
-            for (int m = 0; m != H2_SPEC_FROM; ++m) {
-              // (a codeblock that uses only these rows wraps around to row 0 behind the last of them)
-              const uint4* spn = (m + 1 < layers) ? st_thread + (uint32_t)(m + 1) * st_stride : st_thread;
-              process_row<19>(einfo_s + 8u * 20u * (uint32_t)m, j4, neg_Z4, st, st_thread + (uint32_t)m * st_stride, spn,
-                              pol_keep, PDC_SCALE_X86, true);
+              for (int m = 0; m != H2_SPEC_FROM; ++m) {
+                // (a codeblock that uses only these rows wraps around to row 0 behind the last of them)
+                const uint4* spn = (m + 1 < layers) ? st_thread + (uint32_t)(m + 1) * st_stride : st_thread;
+                process_row<19>(einfo_s + 8u * 20u * (uint32_t)m, j4, neg_Z4, st, st_thread + (uint32_t)m * st_stride, spn,
+                                pol_keep, PDC_SCALE_X86, true);
+              }
+              spec_rows_from<RowProgram<1, (SPEC_Z != 0 ? SPEC_Z : 384)>, H2_SPEC_FROM, H2_SPEC_ROWS, PDC_SCALE_X86>(
+                  soft_c + j4, jn4, soft_c, st, st_thread, layers, pol_keep, scale_mode);
+            } else {
+              // A high-rate codeblock uses these rows only: their compiled-in copy (a loop that small fits the
+              // instruction cache; the table-driven copy above costs it 48 instructions per row).
+              spec_rows_from<RowProgram<1, (SPEC_Z != 0 ? SPEC_Z : 384)>, 0, H2_SPEC_FROM, PDC_SCALE_X86>(
+                  soft_c + j4, jn4, soft_c, st, st_thread, layers, pol_keep, scale_mode);
             }
-#endif
+#else
             spec_rows_from<RowProgram<1, (SPEC_Z != 0 ? SPEC_Z : 384)>, H2_SPEC_FROM, H2_SPEC_ROWS, PDC_SCALE_X86>(
                 soft_c + j4, jn4, soft_c, st, st_thread, layers, pol_keep, scale_mode);
+#endif
             if constexpr (H2_SPEC_ROWS >= 46) {
               table_rows = false; // the whole schedule is compiled in: nothing left for the table-driven loop
             } else {
@@ -1257,6 +1271,7 @@ struct H2Plan {
   size_t scratch_words_per_cta;
   bool   big;  // the 384-thread instantiation (two CTAs per SM)
   bool   spec; // ... with the BG1 Z = 384 row program compiled in
+  bool   high_rate; // ... and the instantiation for four-row codeblocks (see the kernel)
 };
 
 // PDC_NO_SPEC=1: table-driven row loop for every shape (A/B measurements, tests of the general path).
@@ -1320,6 +1335,10 @@ inline cudaError_t h2_configure_device()
   cudaError_t e   = cudaFuncSetAttribute((h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2, 384>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e == cudaSuccess) {
+    e = cudaFuncSetAttribute((h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2, 384, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  }
+  if (e == cudaSuccess) {
     e = cudaFuncSetAttribute((h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2, 0>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   }
@@ -1331,7 +1350,7 @@ inline cudaError_t h2_configure_device()
 }
 
 inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count, H2Plan& plan,
-                           int scale_mode = PDC_SCALE_X86)
+                           int scale_mode = PDC_SCALE_X86, bool high_rate = false)
 {
   const int bg               = any_bg1 ? 1 : 2;
   plan.threads               = ((max_Z + 31) / 32) * 32;
@@ -1340,7 +1359,9 @@ inline cudaError_t h2_plan(int max_Z, bool any_bg1, uint32_t n_cb, int sm_count,
   plan.scratch_words_per_cta = (size_t)rows * 4 * ((max_Z + 31) & ~31);
   plan.big                   = plan.threads > 192;
   plan.spec                  = plan.big && any_bg1 && max_Z == 384 && scale_mode == PDC_SCALE_X86 && !h2_no_spec();
-  h2_kernel_t   k            = plan.spec  ? (h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2, 384>
+  plan.high_rate             = plan.spec && high_rate;
+  h2_kernel_t   k            = plan.high_rate ? (h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2, 384, true>
+                               : plan.spec    ? (h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2, 384>
                                : plan.big ? (h2_kernel_t)h2::ldpc_decode_h2_kernel<384, 2, 0>
                                           : (h2_kernel_t)h2::ldpc_decode_h2_kernel<192, 4, 0>;
   int         per_sm = 0;
@@ -1373,6 +1394,10 @@ inline cudaError_t launch_ldpc_decode_h2(const BatchParams& p, const H2Plan& pla
   cfg.attrs                                          = attr;
   cfg.numAttrs                                       = 1;
   const uint32_t stride = (uint32_t)plan.scratch_words_per_cta;
+  if (plan.high_rate) {
+    return cudaLaunchKernelEx(&cfg, h2::ldpc_decode_h2_kernel<384, 2, 384, true>, p, scratch, stride, work_counter,
+                              counter_base);
+  }
   if (plan.spec) {
     return cudaLaunchKernelEx(&cfg, h2::ldpc_decode_h2_kernel<384, 2, 384>, p, scratch, stride, work_counter,
                               counter_base);

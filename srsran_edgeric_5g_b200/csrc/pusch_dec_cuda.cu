@@ -286,11 +286,15 @@ struct BatchShape {
   int  max_Z   = 0;
   bool any_bg1 = false;
   bool any_decode = false, any_dematch = false;
+  // every codeblock is a first transmission (rv 0) whose soft bits end inside the first 24 variable nodes: four base-graph
+  // rows in use (ldpc_decoder_impl.cpp:96-114) - selects the decoder instantiation that is fastest on those
+  bool high_rate = false;
 };
 
 BatchShape scan_batch(const pdc_cb_desc* cbs, uint32_t n)
 {
   BatchShape s;
+  bool       high = true;
   for (uint32_t i = 0; i != n; ++i) {
     if (cbs[i].lifting_size <= pdc::MAX_Z) {
       s.max_Z = std::max<int>(s.max_Z, cbs[i].lifting_size);
@@ -298,7 +302,12 @@ BatchShape scan_batch(const pdc_cb_desc* cbs, uint32_t n)
     s.any_bg1 |= (cbs[i].base_graph == 1);
     s.any_decode |= (cbs[i].flags & PDC_CB_DECODE) != 0;
     s.any_dematch |= (cbs[i].flags & PDC_CB_DEMATCH) != 0;
+    const uint8_t first = PDC_CB_DECODE | PDC_CB_DEMATCH | PDC_CB_NEW_DATA;
+    high = high && (cbs[i].flags & first) == first && cbs[i].rv == 0 &&
+           (uint64_t)cbs[i].rm_length + cbs[i].nof_filler <=
+               ((cbs[i].base_graph == 1) ? 24u : 12u) * (uint64_t)cbs[i].lifting_size;
   }
+  s.high_rate = high && n != 0;
   if (s.max_Z < 2) {
     s.max_Z = 2;
   }
@@ -434,7 +443,7 @@ int launch_batch(pdc_ctx*             ctx,
     if (direct_in == nullptr && ctx->cfg.scale_mode != PDC_SCALE_NEON && !ctx->force_scalar) {
       // Throughput kernel: two codeblocks per CTA, half-precision packed arithmetic.
       pdc::H2Plan plan;
-      PDC_CUDA(pdc::h2_plan(shape.max_Z, shape.any_bg1, n_cb, ctx->sm_count, plan, ctx->cfg.scale_mode));
+      PDC_CUDA(pdc::h2_plan(shape.max_Z, shape.any_bg1, n_cb, ctx->sm_count, plan, ctx->cfg.scale_mode, shape.high_rate));
       size_t need = plan.scratch_words_per_cta * (size_t)plan.grid;
       pdc_ctx::DecodeScratch* sc = nullptr;
       PDC_CUDA(decode_scratch_for(ctx, s, need, &sc));
@@ -1801,6 +1810,7 @@ int pdc_launch_device(pdc_ctx*    ctx,
   shape.any_bg1     = any_bg1 != 0;
   shape.any_decode  = (flags_union & PDC_CB_DECODE) != 0;
   shape.any_dematch = (flags_union & PDC_CB_DEMATCH) != 0;
+  shape.high_rate   = (flags_union & PDC_LAUNCH_HIGH_RATE) != 0;
   return launch_batch(ctx, static_cast<const pdc_cb_desc*>(d_cbs), n_cb, static_cast<const int8_t*>(d_llrs),
                       static_cast<const pdc_tb_desc*>(d_tbs), n_tb, static_cast<pdc_cb_result*>(d_cb_results),
                       static_cast<uint8_t*>(d_cb_bits), static_cast<pdc_tb_result*>(d_tb_results),
