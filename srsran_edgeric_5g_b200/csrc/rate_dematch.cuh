@@ -723,12 +723,225 @@ __device__ __forceinline__ void dm_express(const DematchGeom& g, const int8_t* _
   }
 }
 
+// ---- retransmissions: express combine -----------------------------------------------------------------------------------
+//
+// A retransmission that walks the circular buffer at most once (E <= Ncb - F), with everything a multiple of four soft
+// bits, needs neither the staging buffer nor the segments either: four consecutive symbols of one bit plane (one word
+// out of the coalesced vector load, as in dm_express_copy) meet ONE aligned word of the HARQ entry,
+//   deinterleaved index i -> data position q = (d0 + i) mod (Ncb - F) -> buffer position p = q (q < info) or q + F,
+// and are combined four at a time (VIADDMNMX.S16x2; a word with a non-finite operand on either side goes position by
+// position through the general path, which knows the reference's two combine rules). The positions the walk does not
+// touch are only inspected for the last non-zero soft bit. Same bytes as the staged path; the HARQ-buffer parity tests
+// compare whole entries.
+__device__ __forceinline__ bool dm_xcomb_pre(const pdc_cb_desc& d, const int8_t* llr)
+{
+  const int qm = d.qm, bg = d.base_graph, Z = d.lifting_size;
+  if ((d.flags & PDC_CB_NEW_DATA) || d.rv > 3 || !(qm == 2 || qm == 4 || qm == 6 || qm == 8) || (bg != 1 && bg != 2) ||
+      Z < 4 || Z > MAX_Z || (Z & 3) != 0) {
+    return false;
+  }
+  const int N = ((bg == 1) ? 66 : 50) * Z, K_sys = ((bg == 1) ? 20 : 8) * Z, F = d.nof_filler, E = (int)d.rm_length;
+  const int Ncb = (d.nref > 0) ? min((int)d.nref, N) : N;
+  if ((F & 3) != 0 || F >= K_sys || Ncb <= K_sys || (E % (4 * qm)) != 0) {
+    return false;
+  }
+  const int sf1[4] = {0, 17, 33, 56};
+  const int sf2[4] = {0, 13, 25, 43};
+  const int k0 = ((((bg == 1) ? sf1[d.rv] : sf2[d.rv]) * Ncb) / N) * Z, info = K_sys - F, Dn = Ncb - F;
+  const int d0 = (k0 < info) ? k0 : ((k0 < K_sys) ? info : k0 - F);
+  const uint32_t vec = (qm % 4 == 0) ? 16u : 8u;
+  return E <= Dn && (d0 + E <= Dn || (Dn & 3) == 0) && (reinterpret_cast<uintptr_t>(llr) % vec) == 0;
+}
+__device__ __forceinline__ bool dm_xcomb_ok(const DematchGeom& g)
+{
+  return !g.new_data && g.E <= g.Dn && (g.d0 & 3) == 0 && (g.info & 3) == 0 && (g.F & 3) == 0 && (g.N & 3) == 0 &&
+         (!g.wrapped || (g.Dn & 3) == 0);
+}
+
+// Buffer word the four symbols of bit plane j, group grp meet.
+__device__ __forceinline__ int dm_xcomb_word(const DematchGeom& g, int j, int grp)
+{
+  int q = g.d0 + j * g.Kq + 4 * grp;
+  q -= (q >= g.Dn) ? g.Dn : 0;
+  return ((q < g.info) ? q : q + g.F) >> 2;
+}
+
+// `slow`: list (in the unused staging buffer) of the words with a non-finite operand, `n_slow` its length; they are left
+// untouched here and combined position by position once the sweep is over (dm_express_combine) - a call to the general
+// path inside this loop would cost every iteration its spills.
+template <int QM>
+__device__ __forceinline__ void dm_xcomb_words(const DematchGeom& g, const int8_t* __restrict__ llr, uint32_t* out, int t0,
+                                               int nt, DmLast& last, uint16_t* slow, int* n_slow)
+{
+  const uint8_t* src      = reinterpret_cast<const uint8_t*>(llr);
+  const int      n_groups = g.Kq >> 2;
+  constexpr int  VEC      = (QM % 4 == 0) ? 16 : 8;
+  constexpr int  U        = (QM <= 2) ? 2 : 1; // groups in flight per thread
+  for (int grp0 = t0; grp0 < n_groups; grp0 += U * nt) {
+    uint32_t w[U][QM], old[U][QM];
+    int      pw[U][QM];
+#pragma unroll
+    for (int u = 0; u != U; ++u) {
+      const int      grp = grp0 + u * nt;
+      const uint8_t* p   = src + (size_t)grp * 4 * QM;
+      if (grp < n_groups) {
+        if (VEC == 16) {
+#pragma unroll
+          for (int r = 0; r != QM / 4; ++r) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + r);
+            w[u][4 * r] = v.x, w[u][4 * r + 1] = v.y, w[u][4 * r + 2] = v.z, w[u][4 * r + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r != QM / 2; ++r) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p) + r);
+            w[u][2 * r] = v.x, w[u][2 * r + 1] = v.y;
+          }
+        }
+        // the HARQ words these symbols meet, requested together with them
+        int q = g.d0 + 4 * grp;
+#pragma unroll
+        for (int j = 0; j != QM; ++j) {
+          const int qq = q - ((q >= g.Dn) ? g.Dn : 0);
+          pw[u][j]     = ((qq < g.info) ? qq : qq + g.F) >> 2;
+          PDC_ASSERT(pw[u][j] >= 0 && 4 * pw[u][j] + 4 <= g.Ncb && 4 * pw[u][j] + 4 <= PDC_MAX_CB_SOFT);
+          old[u][j] = out[pw[u][j]];
+          q += g.Kq;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u != U; ++u) {
+      const int grp = grp0 + u * nt;
+      if (grp >= n_groups) {
+        break;
+      }
+      if (g.seq != nullptr) {
+        const uint32_t bits = seq_bits32(g.seq, g.seq_base + (uint32_t)grp * 4u * QM);
+#pragma unroll
+        for (int r = 0; r != QM; ++r) {
+          w[u][r] = negate4(w[u][r], (bits >> (4 * r)) & 0xfu);
+        }
+      }
+      uint32_t ow[QM];
+      dm_planes<QM>(w[u], ow);
+#pragma unroll
+      for (int j = 0; j != QM; ++j) {
+        if (dm_any_nonfinite(old[u][j]) || dm_any_nonfinite(ow[j])) {
+          slow[atomicAdd(n_slow, 1)] = (uint16_t)pw[u][j];
+        } else {
+          const uint32_t res = dm_combine4_finite(old[u][j], ow[j]);
+          out[pw[u][j]]      = res;
+          last.note(pw[u][j], res);
+        }
+      }
+    }
+  }
+}
+
+// old_last: what the entry's previous dematcher pass recorded (maximum of its slots, -1 if any is unknown); cta_last: the
+// CTA's running maximum (shared memory, zero on entry).
+__device__ __forceinline__ void dm_express_combine(const DematchGeom& g, const int8_t* __restrict__ llr, uint32_t* out,
+                                                   int t0, int nt, DmLast& last, uint16_t* slow, int* n_slow, int old_last,
+                                                   int* cta_last)
+{
+  switch (g.qm) {
+    case 2:
+      dm_xcomb_words<2>(g, llr, out, t0, nt, last, slow, n_slow);
+      break;
+    case 4:
+      dm_xcomb_words<4>(g, llr, out, t0, nt, last, slow, n_slow);
+      break;
+    case 6:
+      dm_xcomb_words<6>(g, llr, out, t0, nt, last, slow, n_slow);
+      break;
+    default:
+      dm_xcomb_words<8>(g, llr, out, t0, nt, last, slow, n_slow);
+      break;
+  }
+  // The words set aside: position by position (the reference's two rules for non-finite operands).
+  __syncthreads();
+  {
+    const int n = *n_slow;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      const int w = slow[k];
+      last.note(w, dm_word_general<false>(g, llr, nullptr, out, w));
+    }
+  }
+  // What the walk does not touch still counts for the decoder's trimming: the filler bits, what lies beyond the circular
+  // buffer, and the data positions outside [d0, d0 + E) (one interval if the walk wrapped, two if not), each of which
+  // maps to at most two stretches of the buffer (before and behind the filler bits). A word is touched as a whole or not
+  // at all and belongs to the stretch its first position is in.
+  int lo[6], hi[6];
+  lo[0] = g.info, hi[0] = g.K_sys;
+  lo[1] = g.Ncb, hi[1] = g.N;
+  {
+    int qa[2], qb[2];
+    if (g.wrapped) {
+      qa[0] = g.d0 + g.E - g.Dn, qb[0] = g.d0;
+      qa[1] = 0, qb[1] = 0;
+    } else {
+      qa[0] = 0, qb[0] = g.d0;
+      qa[1] = g.d0 + g.E, qb[1] = g.Dn;
+    }
+#pragma unroll
+    for (int k = 0; k != 2; ++k) {
+      lo[2 + 2 * k] = qa[k], hi[2 + 2 * k] = min(qb[k], g.info);
+      lo[3 + 2 * k] = max(qa[k], g.info) + g.F, hi[3 + 2 * k] = qb[k] + g.F;
+    }
+  }
+  // They are unchanged, so the entry's previous "last non-zero" (old_last = 1 + its index, -1 = unknown) usually settles
+  // it without reading them: if that soft bit is itself untouched it still is the last one among them; if not, the last
+  // untouched non-zero lies below `bound` (the end of the highest untouched stretch under old_last), and a part whose own
+  // touched words reach at least that far need not look (the decoder takes the maximum over the parts).
+  bool scan = true;
+  if (old_last >= 0) {
+    int  bound     = 0;
+    bool untouched = false;
+#pragma unroll
+    for (int k = 0; k != 6; ++k) {
+      const int l4 = (lo[k] + 3) & ~3; // first position of the first word of the stretch
+      if (l4 < hi[k] && l4 < old_last) {
+        bound     = max(bound, min(old_last, (hi[k] + 3) & ~3));
+        untouched = untouched || (old_last - 1 >= l4 && ((old_last - 1) & ~3) < hi[k]);
+      }
+    }
+    int pos = last.position();
+    for (int o = 16; o > 0; o >>= 1) {
+      pos = max(pos, __shfl_xor_sync(0xffffffffu, pos, o));
+    }
+    if ((threadIdx.x & 31) == 0 && pos > 0) {
+      atomicMax(cta_last, pos);
+    }
+    __syncthreads();
+    if (untouched) {
+      scan = false;
+      if (t0 == 0) {
+        atomicMax(cta_last, old_last);
+      }
+    } else if (*cta_last >= bound) {
+      scan = false;
+    }
+  }
+  if (scan) {
+#pragma unroll
+    for (int k = 0; k != 6; ++k) {
+      // words whose first position p = 4 w lies in [lo, hi)
+      for (int w = ((lo[k] + 3) >> 2) + t0; 4 * w < hi[k]; w += nt) {
+        PDC_ASSERT(w >= 0 && 4 * w < g.N);
+        last.note(w, out[w]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(DM_THREADS, 6) rate_dematch_kernel(BatchParams prm)
 {
   __shared__ __align__(16) uint8_t sh_in[DM_STAGE_BYTES + 16];
   __shared__ DematchGeom           g_sh;
   __shared__ int                   ok;
   __shared__ int                   sh_last;
+  __shared__ int                   sh_n_slow;
   __shared__ int                   sh_bp[DM_MAX_BP];
   __shared__ DmSeg                 sh_seg[DM_MAX_BP];
   const int                        tid = threadIdx.x;
@@ -764,7 +977,8 @@ __global__ void __launch_bounds__(DM_THREADS, 6) rate_dematch_kernel(BatchParams
   const int     qm = d.qm, E = d.rm_length;
   // Express path candidates skip the staging; the geometry (first warp) has the last word.
   const bool    express_pre = dm_express_pre(d, llr);
-  const bool    staged = !express_pre && (qm == 1 || qm == 2 || qm == 4 || qm == 6 || qm == 8) && E > 0 &&
+  const bool    xcomb_pre   = !express_pre && dm_xcomb_pre(d, llr);
+  const bool    staged = !express_pre && !xcomb_pre && (qm == 1 || qm == 2 || qm == 4 || qm == 6 || qm == 8) && E > 0 &&
                       (E % qm) == 0 && E <= DM_STAGE_BYTES;
   if (tid < 32) {
     if (tid == 0) {
@@ -772,9 +986,10 @@ __global__ void __launch_bounds__(DM_THREADS, 6) rate_dematch_kernel(BatchParams
       g_sh.seq      = seq;
       g_sh.seq_base = seq_base;
       sh_last       = 0;
+      sh_n_slow     = 0;
     }
     __syncwarp();
-    if (ok && express_pre) {
+    if (ok && (express_pre || xcomb_pre)) {
       if (tid == 0) {
         g_sh.staged = 0; // nothing was staged: whatever the express path does not take goes position by position
       }
@@ -820,8 +1035,19 @@ __global__ void __launch_bounds__(DM_THREADS, 6) rate_dematch_kernel(BatchParams
   const int  w_hi = min(nw, w_lo + per);
   DmLast last;
   PDC_ASSERT(!express_pre || dm_express_ok(g_sh));
+  PDC_ASSERT(!xcomb_pre || dm_xcomb_ok(g_sh));
   if (express_pre && dm_express_ok(g_sh)) {
     dm_express(g_sh, llr, out, (int)blockIdx.y * (int)blockDim.x + tid, (int)gridDim.y * (int)blockDim.x, last);
+  } else if (xcomb_pre && dm_xcomb_ok(g_sh)) {
+    // (a CTA meets at most N / 4 <= 6336 words: their 16-bit indices fit the staging buffer this path does not use)
+    static_assert(DM_STAGE_BYTES >= 2 * (PDC_MAX_CB_SOFT / 4), "slow-word list");
+    const int4 slots    = *reinterpret_cast<const int4*>(prm.harq_last + (size_t)d.harq_id * DM_MAX_PARTS);
+    // (with several CTAs per codeblock a fast one may have replaced its slot before a slow one reads them: no shortcut)
+    const int  old_last = (gridDim.y != 1 || min(min(slots.x, slots.y), min(slots.z, slots.w)) < 0)
+                              ? -1
+                              : max(max(slots.x, slots.y), max(slots.z, slots.w));
+    dm_express_combine(g_sh, llr, out, (int)blockIdx.y * (int)blockDim.x + tid, (int)gridDim.y * (int)blockDim.x, last,
+                       reinterpret_cast<uint16_t*>(sh_in), &sh_n_slow, old_last, &sh_last);
   } else if (fast) {
     // Words cut by a breakpoint (and the incomplete last word): one thread per soft bit, the four of a word side by
     // side; the HARQ word is requested before the segment loops and used after them.

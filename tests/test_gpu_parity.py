@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle as po
+from srsran_edgeric_5g_b200 import capi
 from tests.vectors import LIFTING_SIZES, awgn_llr, make_cb_batch, random_message
 
 pytestmark = pytest.mark.gpu
@@ -117,6 +118,101 @@ def test_rate_dematcher_random(ctx, orc):
         ctx.rate_dematch(a, llr, new_data, rv, qm, nref, F)
         orc.rate_dematch(b, llr, new_data, rv, qm, nref, F, 64)
         assert (a == b).all(), (bg, Z, qm, F, nref, E, rv, new_data, np.nonzero(a != b)[0][:8])
+
+
+def test_rate_dematcher_express_combine(ctx, orc):
+    """Retransmissions that qualify for the dematcher's express combine (one lap at most, everything a multiple of four
+    soft bits): every redundancy version, limited buffers with and without a wrap, filler bits, non-finite soft bits on
+    either side (those words take the general path), and a second retransmission on top of the first."""
+    rng = np.random.default_rng(44)
+    hits = 0
+    for trial in range(300):
+        bg = int(rng.integers(1, 3))
+        Z = int(rng.choice([z for z in LIFTING_SIZES if z % 4 == 0]))
+        kb = 22 if bg == 1 else 10
+        N = (66 if bg == 1 else 50) * Z
+        Ksys = (kb - 2) * Z
+        qm = int(rng.choice([2, 4, 6, 8]))
+        F = 4 * int(rng.integers(0, min(Ksys - 4, 2 * Z) // 4)) if rng.random() < 0.5 else 0
+        if rng.random() < 0.5:
+            nref = 0
+        else:
+            nref = int(rng.integers(Ksys + 2 * Z, N))
+            nref -= nref % 4 if rng.random() < 0.6 else 0  # a multiple of four lets the walk wrap in the express path
+        ncb = min(nref, N) if nref else N
+        dn = ncb - F
+        e_max = dn // (4 * qm)
+        if e_max < 1:
+            continue
+        E = int(rng.integers(1, e_max + 1)) * 4 * qm
+        buf0 = (rng.integers(-120, 121, N) if rng.random() < 0.7 else rng.integers(-128, 128, N)).astype(np.int8)
+        a, b = buf0.copy(), buf0.copy()
+        for rv in rng.permutation(4)[:2]:
+            llr = (rng.integers(-120, 121, E) if rng.random() < 0.8 else rng.integers(-128, 128, E)).astype(np.int8)
+            ctx.rate_dematch(a, llr, False, int(rv), qm, nref, F)
+            orc.rate_dematch(b, llr, False, int(rv), qm, nref, F, 64)
+            assert (a == b).all(), (bg, Z, qm, F, nref, E, int(rv), np.nonzero(a != b)[0][:8])
+            hits += 1
+    assert hits > 400
+
+
+def test_express_combine_batch_and_rows_in_use(ctx, orc):
+    """A batch large enough for one dematcher CTA per codeblock (where a retransmission takes the entry's previous
+    "last non-zero soft bit" instead of reading what it does not touch): sparse soft bits so that the last non-zero
+    position moves around - including back down when a retransmission cancels it; whole HARQ entries against the oracle
+    and the decoder's number of rows in use (ldpc_decoder_impl.cpp:86-114) against the entry's contents."""
+    rng = np.random.default_rng(91)
+    n_cb = 1300
+    shapes = []
+    for i in range(n_cb):
+        bg = int(rng.integers(1, 3))
+        Z = int(rng.choice([8, 12, 16, 20, 24, 28, 32, 36, 40]))
+        kb = 22 if bg == 1 else 10
+        N = (66 if bg == 1 else 50) * Z
+        Ksys = (kb - 2) * Z
+        qm = int(rng.choice([2, 4, 6, 8]))
+        F = 4 * int(rng.integers(0, Z // 4)) if rng.random() < 0.4 else 0
+        nref = 0 if rng.random() < 0.6 else (int(rng.integers(Ksys + 2 * Z, N)) & ~3)
+        shapes.append((bg, Z, kb, N, Ksys, qm, F, nref))
+    # (the reference leaves parts of a limited buffer stale on a new transmission: start from what the arena holds)
+    bufs = [ctx.harq_read(i, s[3]) for i, s in enumerate(shapes)]
+    for rnd in range(4):
+        cbs = np.zeros(n_cb, capi.CB_DESC_DTYPE)
+        llrs, off = [], 0
+        for i, (bg, Z, kb, N, Ksys, qm, F, nref) in enumerate(shapes):
+            ncb = nref if nref else N
+            e_max = (ncb - F) // (4 * qm)
+            new = rnd == 0
+            E = int(rng.integers(max(1, (Ksys - F) // (4 * qm) + 1), e_max + 1)) * 4 * qm if new else \
+                int(rng.integers(1, e_max + 1)) * 4 * qm
+            rv = 0 if new else int(rng.integers(0, 4))
+            mode = rng.random()
+            if mode < 0.4:
+                l = rng.integers(-1, 2, E).astype(np.int8)
+            elif mode < 0.6:
+                l = np.zeros(E, np.int8)
+                l[:int(rng.integers(0, E))] = rng.integers(-3, 4, 1)[0]
+            else:
+                l = rng.integers(-120, 121, E).astype(np.int8) * (rng.random(E) < 0.3)
+                l = l.astype(np.int8)
+            flags = capi.CB_DEMATCH | capi.CB_DECODE | (capi.CB_NEW_DATA if new else 0)
+            cbs[i] = (off, E, i, nref, Z, F, bg, qm, rv, capi.CRC16, 1, flags, 0xffff)
+            llrs.append(l)
+            off += E
+            orc.rate_dematch(bufs[i], l, new, rv, qm, nref, F, 64)
+        ctx.submit(cbs, np.concatenate(llrs), None, stream=0, want_bits=False)
+        out = ctx.wait(0)
+        for i, (bg, Z, kb, N, Ksys, qm, F, nref) in enumerate(shapes):
+            got = ctx.harq_read(i, N)
+            assert (got == bufs[i]).all(), (rnd, i, shapes[i], np.nonzero(got != bufs[i])[0][:8])
+            nz = np.nonzero(bufs[i])[0]
+            res = out["cb_results"][i]
+            if nz.size == 0:
+                assert res["status"] == 1
+                continue
+            cb_len = max(int(nz[-1]) + 1 + 2 * Z, (kb + 4) * Z)
+            cb_len = (cb_len + Z - 1) // Z * Z
+            assert res["nlayers"] == cb_len // Z - kb, (rnd, i, shapes[i], int(nz[-1]), res)
 
 
 def test_crc(ctx, orc):
