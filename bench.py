@@ -1216,6 +1216,30 @@ def main():
             "unit": "GB/s", "frac": dm_bytes / dm_s / 1e9 / pk["hbm_gbs"], "traffic": profiled_traffic("rate_dematch"),
             "ms_per_launch": kt["rate_dematch"], "peak_source": pk_src,
         }
+        # The retransmission side of the same kernel: the step's soft bits combined into the entries as redundancy version 2
+        # (read E soft bits, read and write the min(E, Ncb) positions they meet).
+        d_retx = descs(False)
+        d_retx["flags"] = capi.CB_DEMATCH
+        d_retx["rv"] = 2
+        d_retx_dev = torch.from_numpy(d_retx.view(np.uint8)).cuda()
+
+        def retx_step():
+            ctx.launch_device(d_retx_dev.data_ptr(), n_cb, d_llrs.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), Z,
+                              capi.CB_DEMATCH, True, cuda_stream=stream.cuda_stream)
+        for _ in range(2):
+            retx_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(max(3, args.steps // 2)):
+            retx_step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        retx_ms = e0.elapsed_time(e1) / max(3, args.steps // 2)
+        line["roofline_hbm"]["retransmission"] = {
+            "achieved": n_cb * 3 * N_SOFT / (retx_ms * 1e-3) / 1e9, "unit": "GB/s",
+            "frac": n_cb * 3 * N_SOFT / (retx_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "ms_per_launch": retx_ms,
+            "bytes_per_codeblock": 3 * N_SOFT, "what": "rv 2 combined into entries holding earlier transmissions"}
         if sharded is not None:
             line.setdefault("extra", {}).update(sharded)
         if not args.no_extras:
