@@ -12,6 +12,7 @@
 #include "ldpc_encode.cuh"
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -192,6 +193,12 @@ struct Queue {
   cudaStream_t lane[PIPE_LANES] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t  ev_copy[PIPE_MAX_GROUPS] = {};
   cudaEvent_t  ev_lane[PIPE_LANES] = {};
+  // PDC_PIPE_TRACE=1 (measurement aid): device timestamps of the pipelined submission - start, end of every group's copy,
+  // end of every group's kernels and copies out, end of the batch - printed by pdc_wait.
+  cudaEvent_t  tr_start = nullptr, tr_done = nullptr, tr_copy[PIPE_MAX_GROUPS] = {}, tr_group[PIPE_MAX_GROUPS] = {},
+               tr_kern[PIPE_MAX_GROUPS] = {};
+  int          tr_groups = 0;
+  double       tr_host_us = 0;
   // Descriptors {transport blocks, codeblocks} and results {transport blocks, codeblocks} are one block each, on the
   // device and in page-locked host memory: one copy in and one copy out per batch instead of two (a small copy costs a
   // few microseconds of latency whatever its size). d_tbs / d_cbs / d_tb_res / d_cb_res point into the blocks.
@@ -1058,10 +1065,30 @@ static int submit_pipelined(pdc_ctx*           ctx,
   uint8_t*   tb_dst      = (tb_bytes && n_tb != 0) ? (direct_tb ? tb_bytes : q.h_tb_out) : nullptr;
   // All copies first (the copy engine then runs without gaps while the host queues the kernels of the groups behind
   // them: a launch costs a few microseconds of host time, a group's copy tens).
+  static const bool trace = [] {
+    const char* e = getenv("PDC_PIPE_TRACE");
+    return e != nullptr && e[0] == '1';
+  }();
+  const auto host_t0 = std::chrono::steady_clock::now();
+  if (trace) {
+    if (q.tr_start == nullptr) {
+      cudaEventCreate(&q.tr_start);
+      cudaEventCreate(&q.tr_done);
+      for (int k = 0; k != PIPE_MAX_GROUPS; ++k) {
+        cudaEventCreate(&q.tr_copy[k]);
+        cudaEventCreate(&q.tr_group[k]);
+        cudaEventCreate(&q.tr_kern[k]);
+      }
+    }
+    cudaEventRecord(q.tr_start, cs);
+  }
   for (int k = 0; k != plan.n_groups; ++k) {
     const PipeGroup& g = plan.g[k];
     PDC_CUDA(cudaMemcpyAsync(q.d_llrs + g.lo, llrs + g.lo, g.hi - g.lo, cudaMemcpyHostToDevice, cs));
     PDC_CUDA(cudaEventRecord(q.ev_copy[k], cs));
+    if (trace) {
+      cudaEventRecord(q.tr_copy[k], cs);
+    }
   }
   for (int k = 0; k != plan.n_groups; ++k) {
     const PipeGroup& g = plan.g[k];
@@ -1075,6 +1102,9 @@ static int submit_pipelined(pdc_ctx*           ctx,
     if (rc != PDC_OK) {
       cudaDeviceSynchronize();
       return rc;
+    }
+    if (trace) {
+      cudaEventRecord(q.tr_kern[k], ls);
     }
     // What the group produced leaves right away.
     PDC_CUDA(cudaMemcpyAsync(q.h_cb_res + g.cb0, q.d_cb_res + g.cb0, sizeof(pdc_cb_result) * n_g, cudaMemcpyDeviceToHost,
@@ -1090,6 +1120,9 @@ static int submit_pipelined(pdc_ctx*           ctx,
         hi = std::max(hi, (size_t)tbs[t].out_offset + ((size_t)tbs[t].tbs_bits + 24 + 31) / 32 * 4);
       }
       PDC_CUDA(cudaMemcpyAsync(tb_dst + lo, q.d_tb_out + lo, hi - lo, cudaMemcpyDeviceToHost, ls));
+    }
+    if (trace) {
+      cudaEventRecord(q.tr_group[k], ls);
     }
   }
   // Join: the queue's own stream continues when every lane is through.
@@ -1138,6 +1171,11 @@ static int submit_pipelined(pdc_ctx*           ctx,
     }
   }
   PDC_CUDA(cudaEventRecord(q.done, q.stream));
+  if (trace) {
+    cudaEventRecord(q.tr_done, q.stream);
+    q.tr_groups  = plan.n_groups;
+    q.tr_host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
+  }
   q.busy         = true;
   q.n_cb         = n_cb;
   q.n_tb         = n_tb;
@@ -1743,6 +1781,24 @@ int pdc_wait(pdc_ctx* ctx, uint32_t stream)
     front_end_kernels(ctx, q.fe, q.stream);
   }
   cudaError_t e = q.busy ? cudaEventSynchronize(q.done) : cudaStreamSynchronize(q.stream);
+  if (q.busy && q.tr_groups != 0 && e == cudaSuccess) {
+    // PDC_PIPE_TRACE: where the device time of the pipelined batch went (us from the start of the first copy).
+    static int printed = 0;
+    if (printed++ % 50 == 49) {
+      float t = 0;
+      fprintf(stderr, "pipe trace: host enqueue %.0f us;", q.tr_host_us);
+      for (int k = 0; k != q.tr_groups; ++k) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, q.tr_start, q.tr_copy[k]);
+        cudaEventElapsedTime(&b, q.tr_start, q.tr_group[k]);
+        cudaEventElapsedTime(&c, q.tr_start, q.tr_kern[k]);
+        fprintf(stderr, " g%d in %.0f kernels %.0f out %.0f;", k, a * 1e3f, c * 1e3f, b * 1e3f);
+      }
+      cudaEventElapsedTime(&t, q.tr_start, q.tr_done);
+      fprintf(stderr, " batch %.0f us\n", t * 1e3f);
+    }
+    q.tr_groups = 0;
+  }
   if (q.fe.pending) {
     q.fe.pending = false;
     if (e == cudaSuccess && q.fe.u_uci != nullptr) {
