@@ -973,9 +973,33 @@ static bool plan_pipeline(const pdc_cb_desc* cbs, uint32_t n_cb, size_t n_llrs, 
     }
     next_cb = tbs[t].first_cb + tbs[t].nof_cb;
   }
-  // Group sizes fall towards the end of the batch (3 3 3 2 2 1 1 1 sixteenths): what is left to do when the last byte
-  // has arrived is the kernel chain of the LAST group, so that one is the smallest.
-  static const int weight[PIPE_GROUPS] = {3, 3, 3, 2, 2, 1, 1, 1};
+  // Group sizes fall towards the end of the batch (5 4 3 2 1 1 sixteenths): what is left to do when the last byte has
+  // arrived is the kernel chain of the LAST group, so that one is the smallest; every copy costs about 10 us on top of
+  // its bytes, so there are no more groups than that takes (16-cell slot, p50: 3 3 3 2 2 1 1 1 -> 569 us, 4 4 3 2 2 1 ->
+  // 559, 5 4 3 2 1 1 -> 554, 6 5 3 1 1 -> 558, 4 4 4 3 1 -> 570, eight equal groups -> 574, 6 6 3 1 -> 586).
+  // (PDC_PIPE_WEIGHTS="5,4,3,2,1,1": measurement aid, sixteenths per group, the last one repeated.)
+  static const struct Weights {
+    int w[PIPE_GROUPS] = {5, 4, 3, 2, 1, 1, 1, 1};
+    Weights()
+    {
+      const char* e = getenv("PDC_PIPE_WEIGHTS");
+      if (e != nullptr) {
+        int k = 0, last = 1;
+        while (*e != 0 && k != PIPE_GROUPS) {
+          last   = std::max(1, atoi(e));
+          w[k++] = last;
+          while (*e != 0 && *e != ',') {
+            ++e;
+          }
+          e += (*e == ',') ? 1 : 0;
+        }
+        for (; k != PIPE_GROUPS; ++k) {
+          w[k] = last;
+        }
+      }
+    }
+  } weights;
+  const int* weight = weights.w;
   // Cut points: between transport blocks when there are several, else between codeblock pairs.
   uint32_t cb0 = 0, t_next = 0;
   size_t   lo = 0;
