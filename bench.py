@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 A step = one pass of the hot path (rate dematch + HARQ combine -> LDPC decode -> CB CRC) over one batch of synthetic
-codeblocks per GPU: --launches sub-batches of --n-cb codeblocks (16 x 8192 = 131 072 codeblocks, ~60 ms, so that K = 20
+codeblocks per GPU: --launches sub-batches of --n-cb codeblocks (24 x 8192 = 196 608 codeblocks, ~70 ms, so that K = 20
 steps time more than a second). Workload at N=1 (BASELINE.json metric shape): BG1, Z=384, rate 1/3 (E = N = 25344,
 46 layers), QPSK, rv0, 6 LDPC iterations with early stop OFF - the worst case the metric names. Inputs are AWGN LLRs of
 valid codewords at +1 dB, where the 6-iteration decoder converges (config.crc_ok_frac); every launch reads more than the
@@ -943,7 +943,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--n-cb", type=int, default=8192, help="codeblocks per GPU per launch")
-    ap.add_argument("--launches", type=int, default=16, help="launches (sub-batches of --n-cb codeblocks) per step")
+    ap.add_argument("--launches", type=int, default=24, help="launches (sub-batches of --n-cb codeblocks) per step")
     ap.add_argument("--snr", type=float, default=1.0, help="AWGN SNR (dB) of the synthetic LLRs")
     ap.add_argument("--no-extras", action="store_true", help="skip the early-stop / config-3 / cpu legs")
     ap.add_argument("--only-slots", action="store_true", help="profiling aid: run only the config-3/4/5 slot legs")
