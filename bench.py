@@ -1253,6 +1253,77 @@ def main():
                     "value": n_cb * L * INFO_BITS / (ms_es / max(3, args.steps // 2) * 1e-3) / 1e9, "unit": UNIT,
                     "snr_db": args.snr, "mean_iters": float(res["iters"].mean()),
                     "crc_ok_frac": float(res["crc_ok"].mean())}
+            # ---- the same kernels at the other end of the rate axis: 8192 codeblocks of the shape a 273-PRB 256QAM slot is
+            # made of (BG1 Z = 384, E = 8960 of a 12611-long limited buffer, 16 filler bits: rate 0.94, four rows in use),
+            # 6 forced iterations, resident; every distinct codeblock checked against the oracle.
+            if world == 1:
+                from tests.vectors import make_cb_batch
+                hb = make_cb_batch(orc, bg=1, Z=Z, n_cb=64, E=8960, qm=8, rv=0, snr_db=8.4, seed=4321,
+                                   crc_kind=capi.CRC24B, nof_filler=16, nref=12611)
+                reps = n_cb // hb.n_cb
+                d_hl = torch.from_numpy(np.tile(hb.llrs.reshape(-1), reps)).cuda()
+                hd = np.zeros(n_cb, capi.CB_DESC_DTYPE)
+                hflags = capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA
+                hd["llr_offset"] = np.arange(n_cb, dtype=np.uint64) * 8960
+                hd["rm_length"], hd["harq_id"], hd["nref"] = 8960, np.arange(n_cb), 12611
+                hd["lifting_size"], hd["nof_filler"], hd["base_graph"], hd["qm"], hd["rv"] = Z, 16, 1, 8, 0
+                hd["crc_kind"], hd["max_iter"], hd["flags"], hd["tb_index"] = capi.CRC24B, MAX_ITER, hflags, 0xffff
+                d_hd = torch.from_numpy(hd.view(np.uint8)).cuda()
+                # (a fresh context: a new transmission into a limited buffer leaves part of a reused HARQ entry stale, as
+                # the reference does, and stale soft bits of the 46-row workload would count as rows in use)
+                ctx_hr = capi.Context(device=local_rank, max_cbs=n_cb, max_llrs=n_cb * 8960, harq_entries=n_cb, max_tbs=1,
+                                      max_tb_bytes=4096, nof_streams=1)
+
+                def hr_step():
+                    ctx_hr.launch_device(d_hd.data_ptr(), n_cb, d_hl.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), Z,
+                                      hflags | capi.LAUNCH_HIGH_RATE, True, cuda_stream=stream.cuda_stream)
+                for _ in range(3):
+                    hr_step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_hr = 4 * max(3, args.steps // 2)
+                e0.record(stream)
+                for _ in range(n_hr):
+                    hr_step()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                hr_ms = e0.elapsed_time(e1) / n_hr
+                hres = d_res.cpu().numpy().view(capi.CB_RESULT_DTYPE)
+                # ... and with the CRC early stop on (the operating point of a gNB)
+                hd_es = hd.copy()
+                hd_es["flags"] = hflags | capi.CB_EARLY_STOP
+                d_hd_es = torch.from_numpy(hd_es.view(np.uint8)).cuda()
+
+                def hr_es_step():
+                    ctx_hr.launch_device(d_hd_es.data_ptr(), n_cb, d_hl.data_ptr(), d_res2.data_ptr(), d_bits.data_ptr(), Z,
+                                         hflags | capi.CB_EARLY_STOP | capi.LAUNCH_HIGH_RATE, True,
+                                         cuda_stream=stream.cuda_stream)
+                d_res2 = torch.zeros(n_cb * 4, dtype=torch.uint8, device="cuda")
+                for _ in range(3):
+                    hr_es_step()
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for _ in range(n_hr):
+                    hr_es_step()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                hr_es_ms = e0.elapsed_time(e1) / n_hr
+                hres_es = d_res2.cpu().numpy().view(capi.CB_RESULT_DTYPE)
+                hbits = d_bits.cpu().numpy().reshape(n_cb, capi.PDC_MAX_CB_BYTES)
+                href = hb.run_oracle(orc, MAX_ITER, False)
+                info_hr = K_BITS - 24 - 16
+                line["extra"]["high_rate_8192_codeblocks"] = {
+                    "value": n_cb * info_hr / (hr_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_launch": hr_ms,
+                    "info_bits_per_cb": info_hr, "rm_length": 8960, "rows_in_use": int(hres["nlayers"].max()),
+                    "iterations": MAX_ITER, "early_stop": False, "snr_db": 8.4, "crc_ok_frac": float(hres["crc_ok"].mean()),
+                    "parity_vs_oracle_all_distinct_codeblocks": bool(
+                        (hres["crc_ok"][:64].astype(bool) == href["crc_ok"]).all() and
+                        (hbits[:64, :K_BITS // 8] == href["bits"]).all()),
+                    "early_stop_on": {"value": n_cb * info_hr / (hr_es_ms * 1e-3) / 1e9, "unit": UNIT,
+                                      "ms_per_launch": hr_es_ms, "mean_iters": float(hres_es["iters"].mean()),
+                                      "crc_ok_frac": float(hres_es["crc_ok"].mean())},
+                    "what": "rate dematcher + decoder, resident, the codeblock shape of BASELINE config 3"}
+                ctx_hr.close()
             # ---- config 3 / config 4 of BASELINE.json: 273-PRB 4-layer 256QAM slots (152 codeblocks, 4 rows each) -----------
             # (a fresh context: the reference semantics leave regions of a reused HARQ entry stale)
             ctx2 = capi.Context(device=local_rank, max_cbs=2432, max_llrs=1 << 20, harq_entries=2432, max_tbs=16,
