@@ -687,8 +687,9 @@ __device__ __forceinline__ void dm_express_copy(const DematchGeom& g, const int8
   }
 }
 
+// old_last: the entry's previous record of its last non-zero soft bit (1 + index; -1 = unknown), see dm_express_combine.
 __device__ __forceinline__ void dm_express(const DematchGeom& g, const int8_t* __restrict__ llr, uint32_t* out, int t0,
-                                           int nt, DmLast& last)
+                                           int nt, DmLast& last, int old_last)
 {
   switch (g.qm) {
     case 2:
@@ -708,8 +709,20 @@ __device__ __forceinline__ void dm_express(const DematchGeom& g, const int8_t* _
     out[w] = 0x7f7f7f7fu;
     last.note(w, 0x7f7f7f7fu);
   }
-  for (int w = ((g.E + g.F) >> 2) + t0; w < (g.zf_lo >> 2); w += nt) {
-    last.note(w, out[w]); // stale soft bits still count for the decoder's trimming
+  // Stale soft bits (limited buffer) still count for the decoder's trimming. They are unchanged, so the previous record
+  // usually tells without reading them: nothing non-zero up there, or the very soft bit it points at.
+  const int s_lo = g.E + g.F, s_hi = g.zf_lo & ~3;
+  if (old_last >= 0 && old_last <= s_lo) {
+    // nothing
+  } else if (old_last >= 0 && old_last - 1 < s_hi) {
+    if (t0 == 0) {
+      const int w = (old_last - 1) >> 2;
+      last.note(w, out[w]);
+    }
+  } else {
+    for (int w = (s_lo >> 2) + t0; w < (s_hi >> 2); w += nt) {
+      last.note(w, out[w]);
+    }
   }
   if ((g.zf_lo & 3) != 0 && t0 == 0) {
     // the word the final zeroing starts in: its first bytes stay, the rest is zeroed
@@ -975,6 +988,10 @@ __global__ void __launch_bounds__(DM_THREADS, 6) rate_dematch_kernel(BatchParams
   }
   uint32_t* out = reinterpret_cast<uint32_t*>(prm.harq + (size_t)min(d.harq_id, prm.harq_entries - 1) * PDC_MAX_CB_SOFT);
   const int     qm = d.qm, E = d.rm_length;
+  // The entry's record of its last non-zero soft bit, requested now (the express paths use it long after the round trip).
+  const int4 slots = (gridDim.y == 1)
+                         ? __ldg(reinterpret_cast<const int4*>(prm.harq_last) + min(d.harq_id, prm.harq_entries - 1))
+                         : make_int4(-1, -1, -1, -1);
   // Express path candidates skip the staging; the geometry (first warp) has the last word.
   const bool    express_pre = dm_express_pre(d, llr);
   const bool    xcomb_pre   = !express_pre && dm_xcomb_pre(d, llr);
@@ -1036,16 +1053,17 @@ __global__ void __launch_bounds__(DM_THREADS, 6) rate_dematch_kernel(BatchParams
   DmLast last;
   PDC_ASSERT(!express_pre || dm_express_ok(g_sh));
   PDC_ASSERT(!xcomb_pre || dm_xcomb_ok(g_sh));
+  // The entry's previous record of its last non-zero soft bit (with several CTAs per codeblock a fast one may have
+  // replaced its slot before a slow one reads them: unknown then).
+  int old_last = -1;
+  if (gridDim.y == 1 && (express_pre || xcomb_pre) && min(min(slots.x, slots.y), min(slots.z, slots.w)) >= 0) {
+    old_last = max(max(slots.x, slots.y), max(slots.z, slots.w));
+  }
   if (express_pre && dm_express_ok(g_sh)) {
-    dm_express(g_sh, llr, out, (int)blockIdx.y * (int)blockDim.x + tid, (int)gridDim.y * (int)blockDim.x, last);
+    dm_express(g_sh, llr, out, (int)blockIdx.y * (int)blockDim.x + tid, (int)gridDim.y * (int)blockDim.x, last, old_last);
   } else if (xcomb_pre && dm_xcomb_ok(g_sh)) {
     // (a CTA meets at most N / 4 <= 6336 words: their 16-bit indices fit the staging buffer this path does not use)
     static_assert(DM_STAGE_BYTES >= 2 * (PDC_MAX_CB_SOFT / 4), "slow-word list");
-    const int4 slots    = *reinterpret_cast<const int4*>(prm.harq_last + (size_t)d.harq_id * DM_MAX_PARTS);
-    // (with several CTAs per codeblock a fast one may have replaced its slot before a slow one reads them: no shortcut)
-    const int  old_last = (gridDim.y != 1 || min(min(slots.x, slots.y), min(slots.z, slots.w)) < 0)
-                              ? -1
-                              : max(max(slots.x, slots.y), max(slots.z, slots.w));
     dm_express_combine(g_sh, llr, out, (int)blockIdx.y * (int)blockDim.x + tid, (int)gridDim.y * (int)blockDim.x, last,
                        reinterpret_cast<uint16_t*>(sh_in), &sh_n_slow, old_last, &sh_last);
   } else if (fast) {

@@ -176,13 +176,13 @@ def test_express_combine_batch_and_rows_in_use(ctx, orc):
         shapes.append((bg, Z, kb, N, Ksys, qm, F, nref))
     # (the reference leaves parts of a limited buffer stale on a new transmission: start from what the arena holds)
     bufs = [ctx.harq_read(i, s[3]) for i, s in enumerate(shapes)]
-    for rnd in range(4):
+    for rnd in range(5):
         cbs = np.zeros(n_cb, capi.CB_DESC_DTYPE)
         llrs, off = [], 0
         for i, (bg, Z, kb, N, Ksys, qm, F, nref) in enumerate(shapes):
             ncb = nref if nref else N
             e_max = (ncb - F) // (4 * qm)
-            new = rnd == 0
+            new = rnd in (0, 2)  # (round 2: a new transmission over whatever the first one left, stale stretch included)
             E = int(rng.integers(max(1, (Ksys - F) // (4 * qm) + 1), e_max + 1)) * 4 * qm if new else \
                 int(rng.integers(1, e_max + 1)) * 4 * qm
             rv = 0 if new else int(rng.integers(0, 4))
