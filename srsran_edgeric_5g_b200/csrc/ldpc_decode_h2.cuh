@@ -8,9 +8,11 @@
 //   * +-infinity ("fixed bit", the reference's +-127) with hardware-native sticky semantics: INF - c = INF,
 //   * packed add/fma/relu on the FMA pipe (HADD2/HFMA2), leaving the ALU pipe (LOP3/PRMT/HMNMX2, 64 lanes/clk/SM on
 //     B200 - the bound of this kernel) for sign logic and min/second-min only; both pipes issue in parallel.
-// Check-to-variable messages are kept compressed per (row, check) as {scaled min1, scaled min2} bytes plus one
-// "is the minimum" and one "sign" bit per edge, from which every message is exactly reconstructible; they live in a
-// per-CTA scratch that stays L2-resident (persistent CTAs) and are prefetched one row ahead.
+// Check-to-variable messages are kept compressed per (row, check) as {scaled min1, scaled min2, one "negative" bit per
+// edge, the index of the edge that held the minimum}, from which every message is exactly reconstructible; they live in a
+// per-CTA scratch in global memory (mostly L2: see DESIGN.md 4.1 for what reaches DRAM) and are prefetched one row ahead.
+// For the hot shape (BG1, Z = 384) the layered schedule is compiled in (row_programs.inc, spec_row); every other shape runs
+// the same arithmetic (row_math) from the edge tables.
 //
 // Bit-exact target: ldpc_decoder_impl::decode (lib/phy/upper/channel_coding/ldpc/ldpc_decoder_impl.cpp:60-318) with the
 // AVX2/AVX512 or generic node kernels (ldpc_decoder_avx512.cpp:81-290, ldpc_decoder_generic.cpp:30-128); see SURVEY 8a
