@@ -215,6 +215,35 @@ def test_express_combine_batch_and_rows_in_use(ctx, orc):
             assert res["nlayers"] == cb_len // Z - kb, (rnd, i, shapes[i], int(nz[-1]), res)
 
 
+def test_high_rate_hint_never_changes_results(ctx, orc):
+    """PDC_LAUNCH_HIGH_RATE only selects a decoder instantiation: a batch that does NOT fit the hint (all 46 rows in use,
+    and a mix of row counts) and one that does (four rows) decode identically with and without it, and like the oracle."""
+    import torch
+    stream = torch.cuda.current_stream()
+    for E, qm, snr, seed in ((66 * 384, 2, 0.5, 21), (30 * 384, 4, 4.0, 22), (8960, 8, 8.4, 23)):
+        b = make_cb_batch(orc, 1, 384, n_cb=10, E=E, qm=qm, rv=0, snr_db=snr, seed=seed)
+        ref = b.run_oracle(orc, 6, True)
+        cbs = b.descriptors(capi, 6, True, harq_base=100)
+        for i in range(b.n_cb):
+            ctx.harq_write(100 + i, np.zeros(b.N, np.int8))
+        d_cbs = torch.from_numpy(cbs.view(np.uint8)).cuda()
+        d_llr = torch.from_numpy(np.ascontiguousarray(b.llrs.reshape(-1))).cuda()
+        flags = int(np.bitwise_or.reduce(cbs["flags"]))
+        outs = []
+        for hint in (0, capi.LAUNCH_HIGH_RATE):
+            d_res = torch.zeros(b.n_cb * 4, dtype=torch.uint8, device="cuda")
+            d_bits = torch.zeros(b.n_cb * capi.PDC_MAX_CB_BYTES, dtype=torch.uint8, device="cuda")
+            ctx.launch_device(d_cbs.data_ptr(), b.n_cb, d_llr.data_ptr(), d_res.data_ptr(), d_bits.data_ptr(), 384,
+                              flags | hint, True, cuda_stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            res = d_res.cpu().numpy().view(capi.CB_RESULT_DTYPE)
+            bits = d_bits.cpu().numpy().reshape(b.n_cb, capi.PDC_MAX_CB_BYTES)[:, :(b.K + 7) // 8]
+            outs.append((res.copy(), bits.copy()))
+            assert (res["crc_ok"].astype(bool) == ref["crc_ok"]).all() and (bits == ref["bits"]).all(), (E, hint)
+            assert (np.where(res["crc_ok"] == 1, res["iters"], 6) == ref["iters"]).all(), (E, hint)
+        assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()
+
+
 def test_crc(ctx, orc):
     rng = np.random.default_rng(6)
     for kind in (po.CRC16, po.CRC24A, po.CRC24B, po.CRC24C, po.CRC11, po.CRC6):
