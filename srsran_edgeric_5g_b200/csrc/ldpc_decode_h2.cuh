@@ -931,10 +931,12 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         if (in[h] == nullptr) {
           continue;
         }
-        const int known = max(max(slots[h].x, slots[h].y), max(slots[h].z, slots[h].w));
-        if (min(min(slots[h].x, slots[h].y), min(slots[h].z, slots[h].w)) >= 0) {
+        // (a record that describes fewer than N positions, or whose last non-zero soft bit lies beyond this codeblock -
+        // the entry was last written for another shape - says nothing exact about [0, N): scan)
+        const int known = harq_last_known(slots[h], N);
+        if (known >= 0 && known <= N) {
           if (tid == 0) {
-            sh_last[h] = min(known, N);
+            sh_last[h] = known;
           }
           continue;
         }

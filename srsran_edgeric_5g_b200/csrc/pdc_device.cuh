@@ -126,6 +126,26 @@ __device__ __forceinline__ uint32_t negate4(uint32_t v, uint32_t bits)
 constexpr uint32_t CB_NOT_SCRAMBLED = 0xffffffffu;
 
 // Launch parameters shared by the kernels.
+// Record of the last non-zero soft bit of a HARQ entry (BatchParams::harq_last). An entry is a PDC_MAX_CB_SOFT-long slot
+// that codeblocks of different sizes use over time (the reference's buffer pool hands codeblock buffers out again without
+// clearing them, rx_buffer_pool_impl.cpp:44): a record is exact for the first `extent` positions of the entry - the N of
+// the codeblock whose rate dematcher wrote it - and says nothing about what older, longer codeblocks left behind them.
+__host__ __device__ constexpr int32_t harq_last_pack(int last, int extent)
+{
+  return (int32_t)(((uint32_t)extent << 16) | (uint32_t)last);
+}
+static_assert(PDC_MAX_CB_SOFT < 32768, "extent and position share a non-negative 32-bit word");
+// Position recorded in four slots written by one rate-dematcher launch, or -1 if any slot is unknown or the record
+// describes fewer than n leading positions.
+__device__ __forceinline__ int harq_last_known(const int4& slots, int n)
+{
+  const int mn = min(min(slots.x, slots.y), min(slots.z, slots.w));
+  if (mn < 0 || (mn >> 16) < n) {
+    return -1;
+  }
+  return max(max(slots.x, slots.y), max(slots.z, slots.w)) & 0xffff;
+}
+
 struct BatchParams {
   const pdc_cb_desc* cbs;
   uint32_t           n_cb;
@@ -135,8 +155,9 @@ struct BatchParams {
   pdc_cb_result*     results;
   uint8_t*           cb_bits;    // n_cb x PDC_MAX_CB_BYTES (device staging, always present)
   uint8_t*           harq_data;  // entries x PDC_MAX_CB_BYTES: decoded message bits kept with the HARQ entry
-  int32_t*           harq_last;  // per entry, 4 slots (one per dematcher part; take the maximum): 1 + index of the last
-                                 // non-zero soft bit, -1 = unknown (scan the entry)
+  int32_t*           harq_last;  // per entry, 4 slots (one per dematcher part; take the maximum), see harq_last_pack:
+                                 // low half = 1 + index of the last non-zero soft bit, high half = how many leading
+                                 // positions of the entry the record describes; -1 = unknown (scan the entry)
   int                scale_mode;
   int                simd_width;
   // Deferred descrambling (codewords without UCI whose UL-SCH soft bits were not materialised): per codeblock

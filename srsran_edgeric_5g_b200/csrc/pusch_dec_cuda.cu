@@ -243,7 +243,7 @@ struct pdc_ctx {
   uint8_t*             d_harq_data = nullptr; // (harq_entries + 1) x PDC_MAX_CB_BYTES
   uint32_t*            d_tb_sync = nullptr;   // per TB {CRC accumulator, arrival counter} of the TB assembly kernel
   uint32_t             tb_sync_entries = 0;
-  int32_t*             d_harq_last = nullptr; // (harq_entries + 1) x DM_MAX_PARTS: last non-zero soft bit (+1), -1 unknown
+  int32_t*             d_harq_last = nullptr; // (harq_entries + 1) x DM_MAX_PARTS: pdc::harq_last_pack records, -1 unknown
   int8_t*              d_scratch_llr = nullptr;
   size_t               scratch_llr_bytes = 0;
   float*               d_demod_tables = nullptr;  // piecewise-linear LLR tables of the soft demapper
@@ -733,7 +733,11 @@ int pdc_create(const pdc_config* cfg, pdc_ctx** out)
   PDC_CREATE(dev_alloc(&ctx->d_tb_sync, 2 * (size_t)ctx->tb_sync_entries));
   PDC_CREATE(cudaMemset(ctx->d_tb_sync, 0, 2 * (size_t)ctx->tb_sync_entries * sizeof(uint32_t)));
   PDC_CREATE(dev_alloc(&ctx->d_harq_last, entries * pdc::DM_MAX_PARTS));
-  PDC_CREATE(cudaMemset(ctx->d_harq_last, 0, entries * pdc::DM_MAX_PARTS * sizeof(int32_t))); // all-zero entries
+  {
+    // all-zero entries: nothing non-zero anywhere in the slot
+    std::vector<int32_t> fresh(entries * pdc::DM_MAX_PARTS, pdc::harq_last_pack(0, PDC_MAX_CB_SOFT));
+    PDC_CREATE(cudaMemcpy(ctx->d_harq_last, fresh.data(), fresh.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   PDC_CREATE(dev_alloc(&ctx->d_demod_tables, (size_t)pdc::demod::TABLE_FLOATS));
   pdc::demod::demod_tables_kernel<<<1, 128>>>(ctx->d_demod_tables);
   PDC_CREATE(cudaGetLastError());
@@ -2039,6 +2043,9 @@ int pdc_rate_dematch(pdc_ctx*      ctx,
   int8_t* entry  = ctx->d_harq + (size_t)ctx->cfg.harq_entries * PDC_MAX_CB_SOFT;
   PDC_CUDA(cudaMemcpyAsync(q.d_cbs, q.h_cbs, sizeof(d), cudaMemcpyHostToDevice, q.stream));
   PDC_CUDA(cudaMemcpyAsync(entry, buffer, N, cudaMemcpyHostToDevice, q.stream));
+  // (the scratch entry now holds the caller's buffer: whatever was recorded about its previous contents is void)
+  PDC_CUDA(cudaMemsetAsync(ctx->d_harq_last + (size_t)ctx->cfg.harq_entries * pdc::DM_MAX_PARTS, 0xff,
+                           pdc::DM_MAX_PARTS * sizeof(int32_t), q.stream));
   PDC_CUDA(cudaMemcpyAsync(ctx->d_scratch_llr, llrs, E, cudaMemcpyHostToDevice, q.stream));
   BatchShape shape;
   shape.max_Z       = (int)Z;

@@ -1055,9 +1055,11 @@ __global__ void __launch_bounds__(DM_THREADS, 6) rate_dematch_kernel(BatchParams
   PDC_ASSERT(!xcomb_pre || dm_xcomb_ok(g_sh));
   // The entry's previous record of its last non-zero soft bit (with several CTAs per codeblock a fast one may have
   // replaced its slot before a slow one reads them: unknown then).
+  // The record must describe all N positions of THIS codeblock: an entry last used by a shorter codeblock may still hold
+  // what a longer one left behind it.
   int old_last = -1;
-  if (gridDim.y == 1 && (express_pre || xcomb_pre) && min(min(slots.x, slots.y), min(slots.z, slots.w)) >= 0) {
-    old_last = max(max(slots.x, slots.y), max(slots.z, slots.w));
+  if (gridDim.y == 1 && (express_pre || xcomb_pre)) {
+    old_last = harq_last_known(slots, N);
   }
   if (express_pre && dm_express_ok(g_sh)) {
     dm_express(g_sh, llr, out, (int)blockIdx.y * (int)blockDim.x + tid, (int)gridDim.y * (int)blockDim.x, last, old_last);
@@ -1133,11 +1135,12 @@ __global__ void __launch_bounds__(DM_THREADS, 6) rate_dematch_kernel(BatchParams
   }
   __syncthreads();
   if (tid == 0) {
+    // (the parts together have seen or written every one of the N positions: the record is exact for [0, N))
     int32_t* slot    = prm.harq_last + (size_t)d.harq_id * DM_MAX_PARTS;
-    slot[blockIdx.y] = sh_last;
+    slot[blockIdx.y] = harq_last_pack(sh_last, N);
     if (blockIdx.y == 0) {
       for (int k = (int)gridDim.y; k < DM_MAX_PARTS; ++k) {
-        slot[k] = 0;
+        slot[k] = harq_last_pack(0, N);
       }
     }
   }

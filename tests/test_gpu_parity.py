@@ -215,6 +215,50 @@ def test_express_combine_batch_and_rows_in_use(ctx, orc):
             assert res["nlayers"] == cb_len // Z - kb, (rnd, i, shapes[i], int(nz[-1]), res)
 
 
+def test_harq_sequences_random(ctx, orc):
+    """Randomised HARQ histories through pdc_submit (tests/vectors.py: harq_sequence_rounds): few entries (several
+    dematcher CTAs per codeblock) and more than a thousand (one CTA per codeblock, where the express paths rely on the
+    entry's record of its last non-zero soft bit), the second large population taking over the entries of the first with
+    other codeblock shapes - what the reference's buffer pool does when it hands codeblock buffers out again
+    (rx_buffer_pool_impl.cpp:44: nothing is cleared)."""
+    from tests.vectors import harq_sequence_rounds
+    n = harq_sequence_rounds(ctx, orc, np.random.default_rng(2024), n_ent=40, rounds=6, harq_base=0, max_Z=384)
+    n += harq_sequence_rounds(ctx, orc, np.random.default_rng(2025), n_ent=1250, rounds=4, harq_base=0, max_Z=48)
+    n += harq_sequence_rounds(ctx, orc, np.random.default_rng(2026), n_ent=1250, rounds=4, harq_base=0, max_Z=48)
+    assert n > 8000
+
+
+def test_entry_taken_over_by_other_shapes(ctx, orc):
+    """An entry's record of its last non-zero soft bit is only good for the codeblock length it was written for: a long
+    codeblock fills the entries, a short one takes them over (its record describes 800 positions), then a codeblock with a
+    limited buffer is received whose stale stretch [1568, 1960) still holds what the FIRST one left there - the decoder
+    must see those soft bits (rows in use, ldpc_decoder_impl.cpp:86-114) like the reference, which scans the buffer."""
+    rng = np.random.default_rng(77)
+    n_cb = 1250  # one dematcher CTA per codeblock: the express paths consult the record
+    steps = ((1, 32, 0, 2112, 2), (2, 16, 500, 480, 4), (1, 32, 1960, 1568, 8))
+    bufs = [ctx.harq_read(i, 2112) for i in range(n_cb)]
+    for step, (bg, Z, nref, E, qm) in enumerate(steps):
+        N, kb = (66 if bg == 1 else 50) * Z, (22 if bg == 1 else 10)
+        cbs = np.zeros(n_cb, capi.CB_DESC_DTYPE)
+        llrs = rng.integers(-120, 121, (n_cb, E)).astype(np.int8)
+        llrs[llrs == 0] = 1
+        want = []
+        for i in range(n_cb):
+            cbs[i] = (i * E, E, i, nref, Z, 0, bg, qm, 0, capi.CRC24B, 2, capi.CB_DEMATCH | capi.CB_DECODE | capi.CB_NEW_DATA,
+                      0xffff)
+            want.append(orc.cb_decode(bufs[i][:N], llrs[i], True, 0, qm, nref, 0, po.CRC24B, False, 2))
+        ctx.submit(cbs, np.ascontiguousarray(llrs.reshape(-1)), None, stream=0, want_bits=True)
+        out = ctx.wait(0)
+        for i in range(n_cb):
+            assert (ctx.harq_read(i, 2112) == bufs[i]).all(), (step, i)
+            last = int(np.nonzero(bufs[i][:N])[0][-1])
+            cb_len = (max(last + 1 + 2 * Z, (kb + 4) * Z) + Z - 1) // Z * Z
+            assert out["cb_results"]["nlayers"][i] == cb_len // Z - kb, (step, i, last, out["cb_results"][i])
+            assert (out["cb_bits"][i, :(kb * Z + 7) // 8] == want[i][1]).all(), (step, i)
+        if step == 2:
+            assert last >= 1568  # the stale stretch did hold soft bits of the first codeblock
+
+
 def test_high_rate_hint_never_changes_results(ctx, orc):
     """PDC_LAUNCH_HIGH_RATE only selects a decoder instantiation: a batch that does NOT fit the hint (all 46 rows in use,
     and a mix of row counts) and one that does (four rows) decode identically with and without it, and like the oracle."""

@@ -237,3 +237,96 @@ def modulate(bits, qm, rng=None):
         im = s[:, 1] * (8 - s[:, 3] * (4 - s[:, 5] * (2 - s[:, 7])))
         norm = np.sqrt(170)
     return ((re + 1j * im) / norm).astype(np.complex64)
+
+
+# ---- randomised HARQ sequences through the queued batch path ------------------------------------------------------------
+
+def harq_sequence_rounds(ctx, orc, rng, n_ent, rounds, harq_base=0, stream=0, max_Z=384, debug=None):
+    """A population of HARQ entries of random shapes lives through `rounds` slots of ONE pdc_submit each: per entry and
+    slot a new transmission (new message) or a retransmission of the current one, any redundancy version, aligned and
+    unaligned lengths from a fraction of a lap to three laps, limited buffers, filler bits, AWGN soft bits of the valid
+    codeword - some thinned out or zeroed (the position of the last non-zero soft bit moves, up and down), some carrying
+    the non-finite values -128 / +-127 -, per-codeblock iteration limits and early-stop flags. After every slot: whole
+    HARQ entries (stale regions included), CRC flags, iteration counts and decoded bits against the oracle's
+    pusch_codeblock_decoder (rate dematcher + decoder on the entry it keeps: pusch_codeblock_decoder.cpp:35-71).
+    Returns the number of codeblocks compared; raises AssertionError with the case on a mismatch."""
+    from srsran_edgeric_5g_b200 import capi
+    sizes = [z for z in LIFTING_SIZES if z <= max_Z]
+    ents = []
+    for i in range(n_ent):
+        bg = int(rng.integers(1, 3))
+        Z = int(rng.choice(sizes[8:] if rng.random() < 0.7 else sizes))
+        kb = 22 if bg == 1 else 10
+        N, K, Ksys = (66 if bg == 1 else 50) * Z, kb * Z, (kb - 2) * Z
+        qm = int(rng.choice([1, 2, 4, 6, 8]))
+        crc_kind = po.CRC24B if K > 64 else po.CRC16
+        f_max = min(Ksys - 1, 2 * Z, K - 26)
+        F = int(rng.integers(0, max(1, f_max))) if rng.random() < 0.5 else 0
+        if rng.random() < 0.7:
+            F -= F % 4
+        nref = 0
+        if rng.random() < 0.4:
+            nref = int(rng.integers(Ksys + 2 * Z, N + 1))
+            if rng.random() < 0.7:
+                nref &= ~3
+        ents.append(dict(bg=bg, Z=Z, kb=kb, N=N, K=K, qm=qm, F=F, nref=nref, crc=crc_kind, cw=None,
+                         buf=ctx.harq_read(harq_base + i, N)))
+    n_cmp = 0
+    for rnd in range(rounds):
+        cbs = np.zeros(n_ent, capi.CB_DESC_DTYPE)
+        llrs, off, want, before = [], 0, [], []
+        mi_all, es_all = int(rng.integers(1, 9)), bool(rng.integers(0, 2))
+        for i, e in enumerate(ents):
+            new = e["cw"] is None or rng.random() < 0.35
+            if new:
+                e["cw"] = orc.ldpc_encode(e["bg"], e["Z"], random_message(orc, e["bg"], e["Z"], e["F"], e["crc"], rng))
+            ncb = min(e["nref"], e["N"]) if e["nref"] else e["N"]
+            qm, lap = e["qm"], ncb - e["F"]
+            mode = rng.random()
+            if mode < 0.6:     # at most one lap, a multiple of four symbols (the express paths when the rest is aligned)
+                E = int(rng.integers(1, max(2, lap // (4 * qm)) + 1)) * 4 * qm
+            elif mode < 0.85:  # any length up to one lap and a bit
+                E = int(rng.integers(1, max(2, (lap + 2 * e["Z"]) // qm))) * qm
+            else:              # several laps
+                E = int(rng.integers(max(1, lap // qm), max(2, 3 * lap // qm))) * qm
+            rv = 0 if (new and rng.random() < 0.7) else int(rng.integers(0, 4))
+            l = awgn_llr(orc.rate_match(e["cw"], E, rv, qm, e["nref"], e["F"]), float(rng.uniform(-4.0, 9.0)), rng)
+            thin = rng.random()
+            if thin < 0.15:
+                l = (l * (rng.random(E) < rng.uniform(0.02, 0.5))).astype(np.int8)
+            elif thin < 0.20:
+                l[:] = 0
+            elif thin < 0.30:
+                k = rng.integers(0, E, max(1, E // 50))
+                l[k] = rng.choice(np.array([-128, -127, 127], np.int8), k.size)
+            mi = mi_all if rng.random() < 0.8 else int(rng.integers(1, 9))
+            es = es_all if rng.random() < 0.8 else bool(rng.integers(0, 2))
+            flags = capi.CB_DEMATCH | capi.CB_DECODE | (capi.CB_NEW_DATA if new else 0) | (capi.CB_EARLY_STOP if es else 0)
+            cbs[i] = (off, E, harq_base + i, e["nref"], e["Z"], e["F"], e["bg"], qm, rv, e["crc"], mi, flags, 0xffff)
+            llrs.append(l)
+            off += E
+            if debug is not None:
+                before.append(e["buf"].copy())
+            it, bits = orc.cb_decode(e["buf"], l, new, rv, qm, e["nref"], e["F"], e["crc"], es, mi)
+            want.append((it > 0, it if it > 0 else mi, bits, (new, rv, E, mi, es)))
+        if debug is not None:
+            debug.setdefault("history", []).append(cbs.copy())
+        ctx.submit(cbs, np.concatenate(llrs), None, stream=stream, want_bits=True)
+        out = ctx.wait(stream)
+        res = out["cb_results"]
+        for i, e in enumerate(ents):
+            case = (rnd, i, {k: e[k] for k in ("bg", "Z", "qm", "F", "nref")}, want[i][3])
+            got = ctx.harq_read(harq_base + i, e["N"])
+            assert (got == e["buf"]).all(), ("HARQ entry", case, np.nonzero(got != e["buf"])[0][:8])
+            if not e["buf"].any():
+                assert res["status"][i] == 1 and res["crc_ok"][i] == 0, ("all-zero entry", case, res[i])
+                continue
+            assert res["status"][i] == 0, ("status", case, res[i])
+            assert bool(res["crc_ok"][i]) == want[i][0] and int(res["iters"][i]) == want[i][1], ("CRC / iterations", case, res[i], want[i][:2])
+            kbytes = (e["K"] + 7) // 8
+            if debug is not None and not (out["cb_bits"][i, :kbytes] == want[i][2]).all():
+                debug.update(ent=e, llr=llrs[i], desc=cbs[i].copy(), res=res[i].copy(), got=out["cb_bits"][i, :kbytes].copy(),
+                             want=want[i][2], before=before[i], cbs=cbs.copy(), index=i)
+            assert (out["cb_bits"][i, :kbytes] == want[i][2]).all(), ("decoded bits", case)
+            n_cmp += 1
+    return n_cmp

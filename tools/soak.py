@@ -2,7 +2,8 @@
 """Randomised parity soak on a GPU box: for a number of minutes, random rate-dematcher geometries (new data and
 retransmissions, all modulation orders, limited buffers, fillers, non-finite soft bits) and random decoder batches (both
 base graphs, every lifting size, 0.2-1.1 laps of soft bits, early stop on / off, 1-8 iterations) against the oracle,
-bit for bit: HARQ entries, decoded bits, CRC flags, iteration counts. Prints one JSON line; exit code 1 on a mismatch.
+bit for bit: HARQ entries, decoded bits, CRC flags, iteration counts; and randomised HARQ histories (populations of
+entries living through slots of new transmissions and retransmissions, tests/vectors.py: harq_sequence_rounds). Prints one JSON line; exit code 1 on a mismatch.
 
     python tools/soak.py [minutes] [seed]
 """
@@ -21,13 +22,35 @@ def main():
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     from oracle import pyoracle as po
     from srsran_edgeric_5g_b200 import capi
-    from tests.vectors import LIFTING_SIZES, make_cb_batch
+    from tests.vectors import LIFTING_SIZES, harq_sequence_rounds, make_cb_batch
     orc = po.Oracle()
     ctx = capi.Context(device=0, max_cbs=256, max_llrs=256 * 3 * 25344, harq_entries=256, max_tbs=4, max_tb_bytes=1 << 16)
+    # HARQ histories through the queued batch path: large populations run one dematcher CTA per codeblock
+    ctx_seq = capi.Context(device=0, max_cbs=1400, max_llrs=64 << 20, harq_entries=1400, max_tbs=4, max_tb_bytes=1 << 16)
     rng = np.random.default_rng(seed)
     t_end = time.time() + 60.0 * minutes
-    n_dm = n_dec = 0
+    n_dm = n_dec = n_seq = 0
     while time.time() < t_end:
+        # ---- HARQ histories: new transmissions and retransmissions of random geometry on entries that live on
+        n_ent, max_Z = [(1300, 64), (700, 128), (60, 384)][int(rng.integers(0, 3))]
+        prev_dbg = locals().get("dbg", {})
+        dbg = {}
+        try:
+            n_seq += harq_sequence_rounds(ctx_seq, orc, rng, n_ent=n_ent, rounds=4, max_Z=max_Z, debug=dbg)
+        except AssertionError as err:
+            info = {"mismatch": "harq sequence", "case": repr(err.args)[:2000], "seed": seed, "n_ent": n_ent}
+            if dbg:
+                e = dbg["ent"]
+                gb, wb = np.unpackbits(dbg["got"])[:e["K"]], np.unpackbits(dbg["want"])[:e["K"]]
+                diff = np.nonzero(gb != wb)[0]
+                nz = np.nonzero(e["buf"])[0]
+                info.update(result=repr(dbg["res"]), differing_bits=int(diff.size), first=diff[:16].tolist(), last=diff[-4:].tolist(),
+                            last_nonzero=int(nz[-1]), before_nonzero=np.nonzero(dbg["before"])[0][:20].tolist(),
+                            before_count=int(np.count_nonzero(dbg["before"])), after_tail=e["buf"][1560:1640].tolist(), neighbours=[repr(c) for c in dbg["cbs"][max(0, dbg["index"] - 2):dbg["index"] + 3]])
+                info["previous_population"] = [repr(h[dbg["index"]]) for h in prev_dbg.get("history", []) if dbg["index"] < h.size]
+                info["this_population"] = [repr(h[dbg["index"]]) for h in dbg.get("history", [])]
+            print(json.dumps(info))
+            return 1
         # ---- rate dematcher, single calls
         for _ in range(50):
             bg = int(rng.integers(1, 3))
@@ -80,7 +103,9 @@ def main():
                 return 1
             n_dec += n_cb
     print(json.dumps({"soak_ok": True, "minutes": minutes, "seed": seed, "rate_dematch_calls": n_dm,
-                      "codeblocks_decoded": n_dec, "canaries": ctx.debug_canaries_ok()}))
+                      "codeblocks_decoded": n_dec, "harq_sequence_codeblocks": n_seq,
+                      "canaries": min(ctx.debug_canaries_ok(), ctx_seq.debug_canaries_ok())}))
+    ctx_seq.close()
     ctx.close()
     return 0
 
