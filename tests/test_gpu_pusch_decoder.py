@@ -15,11 +15,12 @@ pytestmark = pytest.mark.gpu
 
 
 def _run_tb_sequence(ctx, orc, pool, batch, ues, rv_seq, max_iter, early_stop, rng, fill):
-    """ues: list of dicts(tb, bg, qm, nl, n_llr, nref, snr). Every (re)transmission of all UEs goes in one GPU batch."""
+    """ues: list of dicts(tb, bg, qm, nl, n_llr, nref, snr). Every (re)transmission of all UEs goes in one GPU batch.
+    fill: value the UEs' HARQ entries are set to before the first transmission; None = left as they are."""
     harqs = []
     for u in ues:
         C = compute_nof_codeblocks(u["tb"].size * 8, u["bg"])
-        harqs.append(po.Harq(C, fill))
+        harqs.append(po.Harq(C, 0 if fill is None else fill))
     done = [False] * len(ues)
     for t, rv in enumerate(rv_seq):
         spies, rx_tbs, expected = [], [], []
@@ -33,7 +34,11 @@ def _run_tb_sequence(ctx, orc, pool, batch, ues, rv_seq, max_iter, early_stop, r
             cfg = pusch_decoder_configuration(u["bg"], rv, u["qm"], u["nref"], u["nl"], max_iter, early_stop, t == 0)
             buf = pool.reserve(None, ("ue", i), C, t == 0)
             assert buf is not None
-            if t == 0:
+            if t == 0 and fill is None:
+                # the entries are taken as the previous owner left them (the reference's pool does not clear them)
+                for k in range(C):
+                    harqs[i].soft[k, :capi.PDC_MAX_CB_SOFT] = ctx.harq_read(buf.get_absolute_codeblock_id(k))
+            elif t == 0:
                 for k in range(C):
                     ctx.harq_write(buf.get_absolute_codeblock_id(k), np.full(capi.PDC_MAX_CB_SOFT, fill, np.int8))
             spy = pusch_decoder_notifier_spy()
@@ -95,6 +100,43 @@ def test_multi_ue_harq_batch(ctx, orc, early_stop, max_iter):
                         nref=nref, snr=snr))
     done = _run_tb_sequence(ctx, orc, pool, batch, ues, [0, 2, 3, 1], max_iter, early_stop, rng, fill=-7)
     assert any(done)
+
+
+def random_ues(rng, n_ue, max_tb_bytes_bg1=5000):
+    ues = []
+    for i in range(n_ue):
+        bg = 1 if i % 3 else 2
+        tb_bytes = int(rng.integers(20, 900 if bg == 2 else max_tb_bytes_bg1))
+        qm = int(rng.choice([2, 4, 6, 8]))
+        nl = int(rng.integers(1, 3))
+        rate = rng.uniform(0.55, 0.9) if bg == 1 else rng.uniform(0.25, 0.6)
+        nsym = int(np.ceil(tb_bytes * 8 / rate / qm / nl)) * nl
+        C = compute_nof_codeblocks(tb_bytes * 8, bg)
+        nref = 0 if rng.random() < 0.5 else compute_N_ref(tb_bytes + 40, C)
+        snr = (8 if bg == 1 else 3) * rate / 0.8 + rng.uniform(-4, -1)
+        ues.append(dict(tb=rng.integers(0, 256, tb_bytes).astype(np.uint8), bg=bg, qm=qm, nl=nl, n_llr=nsym * qm,
+                        nref=nref, snr=snr))
+    return ues
+
+
+def tb_generations(ctx, orc, rng, pool, n_gen, n_ue, max_tb_bytes_bg1=5000):
+    """Generations of UEs following each other on the SAME buffer-pool keys: every generation has transport blocks of
+    other sizes (codeblock count, lifting size, limited buffer or not), so the pool's entries go from codeblock shape to
+    codeblock shape without ever being cleared, as in the reference (rx_buffer_pool_impl.cpp:44). Each generation runs
+    its HARQ process (rv 0-2-3-1) with all UEs of a transmission in one batch. Returns the transport blocks decoded."""
+    batch = PuschDecoderBatch(ctx)
+    n_done = 0
+    for gen in range(n_gen):
+        ues = random_ues(rng, n_ue, max_tb_bytes_bg1)
+        early_stop, max_iter = bool(rng.integers(0, 2)), int(rng.integers(2, 9))
+        n_done += sum(_run_tb_sequence(ctx, orc, pool, batch, ues, [0, 2, 3, 1], max_iter, early_stop, rng, fill=None))
+    return n_done
+
+
+def test_generations_of_ues_on_the_same_entries(ctx, orc):
+    rng = np.random.default_rng(4242)
+    pool = rx_buffer_pool(ctx, first_entry=512, nof_entries=1024)
+    assert tb_generations(ctx, orc, rng, pool, n_gen=4, n_ue=14) > 10
 
 
 def test_config3_slot_273prb_256qam_4layers(ctx, orc):

@@ -26,11 +26,21 @@ def main():
     orc = po.Oracle()
     ctx = capi.Context(device=0, max_cbs=256, max_llrs=256 * 3 * 25344, harq_entries=256, max_tbs=4, max_tb_bytes=1 << 16)
     # HARQ histories through the queued batch path: large populations run one dematcher CTA per codeblock
-    ctx_seq = capi.Context(device=0, max_cbs=1400, max_llrs=64 << 20, harq_entries=1400, max_tbs=4, max_tb_bytes=1 << 16)
+    ctx_seq = capi.Context(device=0, max_cbs=1400, max_llrs=64 << 20, harq_entries=1400, max_tbs=64, max_tb_bytes=8 << 20)
+    from srsran_edgeric_5g_b200.pusch_decoder import rx_buffer_pool
+    from tests.test_gpu_pusch_decoder import tb_generations
+    pool_seq = rx_buffer_pool(ctx_seq, first_entry=0, nof_entries=1400)  # the same entries as the codeblock histories
     rng = np.random.default_rng(seed)
     t_end = time.time() + 60.0 * minutes
-    n_dm = n_dec = n_seq = 0
+    n_dm = n_dec = n_seq = n_tb = 0
     while time.time() < t_end:
+        # ---- transport-block level: generations of UEs with other transport block sizes on the same pool keys
+        n_ue, max_tb = [(30, 5000), (12, 60000), (40, 20000)][int(rng.integers(0, 3))]
+        try:
+            n_tb += tb_generations(ctx_seq, orc, rng, pool_seq, n_gen=2, n_ue=n_ue, max_tb_bytes_bg1=max_tb)
+        except AssertionError as err:
+            print(json.dumps({"mismatch": "transport block generations", "case": repr(err.args)[:2000], "seed": seed}))
+            return 1
         # ---- HARQ histories: new transmissions and retransmissions of random geometry on entries that live on
         n_ent, max_Z = [(1300, 64), (700, 128), (60, 384)][int(rng.integers(0, 3))]
         prev_dbg = locals().get("dbg", {})
@@ -103,7 +113,7 @@ def main():
                 return 1
             n_dec += n_cb
     print(json.dumps({"soak_ok": True, "minutes": minutes, "seed": seed, "rate_dematch_calls": n_dm,
-                      "codeblocks_decoded": n_dec, "harq_sequence_codeblocks": n_seq,
+                      "codeblocks_decoded": n_dec, "harq_sequence_codeblocks": n_seq, "transport_blocks_decoded": n_tb,
                       "canaries": min(ctx.debug_canaries_ok(), ctx_seq.debug_canaries_ok())}))
     ctx_seq.close()
     ctx.close()
