@@ -371,7 +371,11 @@ int pdc_launch_device(pdc_ctx*    ctx,
 int pdc_harq_read(pdc_ctx* ctx, uint32_t harq_id, int8_t* soft, uint32_t n);
 int pdc_harq_write(pdc_ctx* ctx, uint32_t harq_id, const int8_t* soft, uint32_t n);
 /* free_harq_context_entry: the entry may be reused; contents are left as they are (the reference pool does not clear
- * soft bits either, include/srsran/phy/upper/rx_buffer_pool.h:62-63). */
+ * soft bits either, include/srsran/phy/upper/rx_buffer_pool.h:62-63). An entry is a PDC_MAX_CB_SOFT-long slot: codeblocks
+ * of any size may follow each other on it, and what a longer codeblock left behind a shorter one is still there when a
+ * third one arrives (it shows in the stale stretch of a limited-buffer transmission, exactly as in the reference). The
+ * library's own bookkeeping about an entry (position of its last non-zero soft bit, for the decoder's trimming,
+ * ldpc_decoder_impl.cpp:86-99) is tied to the codeblock length it was taken for; pdc_harq_write voids it. */
 int pdc_harq_free(pdc_ctx* ctx, uint32_t harq_id);
 /* Device address of the arena (harq_entries x PDC_MAX_CB_SOFT int8), for device-resident pipelines. */
 void* pdc_harq_device_ptr(pdc_ctx* ctx);
