@@ -307,7 +307,7 @@ __device__ __forceinline__ void row_pass1(const uint32_t (&addr)[DEG], const Row
 // Pass 2: scaled minima, new check-to-variable messages, soft-bit update, and the row's new compressed messages to sp.
 template <int DEG, int SCALE>
 __device__ __forceinline__ void row_pass2(const uint32_t (&addr)[DEG], const RowPass<DEG>& rp, uint4* sp, uint64_t pol,
-                                          int scale_mode)
+                                          int scale_mode, bool keep = true)
 {
   constexpr bool PACKED_MIN = DEG > 16;
   const __half2 (&vc)[DEG]  = rp.vc;
@@ -382,25 +382,28 @@ __device__ __forceinline__ void row_pass2(const uint32_t (&addr)[DEG], const Row
     st_out.z = (DEG > 8) ? __byte_perm(grp[0], grp[1], 0x6240) : grp[0];
   }
   st_out.w = idx;
-  st_state(sp, st_out, pol);
+  if (keep) { // (nobody reads the messages of the last iteration)
+    st_state(sp, st_out, pol);
+  }
 }
 
 // One row: pass 1, fetch of the next row's compressed messages into the registers this row's were in, pass 2.
 template <int DEG, int SCALE>
 __device__ __forceinline__ void row_math(const uint32_t (&addr)[DEG], RowState& st, uint4* sp, const uint4* sp_next,
-                                         uint64_t pol, int scale_mode)
+                                         uint64_t pol, int scale_mode, bool keep = true)
 {
   RowPass<DEG> rp;
   row_pass1<DEG>(addr, st, rp);
   st = ld_state(sp_next, pol);
-  row_pass2<DEG, SCALE>(addr, rp, sp, pol, scale_mode);
+  row_pass2<DEG, SCALE>(addr, rp, sp, pol, scale_mode, keep);
 }
 
 // Table-driven row: the addresses of the row's soft words come from the edge table in shared memory.
 //   e_info : shared-window address of the row's edge table
 template <int DEG>
 __device__ __forceinline__ void process_row(uint32_t e_info, uint32_t j4, uint32_t neg_Z4, RowState& st, uint4* sp,
-                                            const uint4* sp_next, uint64_t pol, int scale_mode, bool need_barrier)
+                                            const uint4* sp_next, uint64_t pol, int scale_mode, bool need_barrier,
+                                            bool keep = true)
 {
   uint32_t addr[DEG];
   {
@@ -418,7 +421,7 @@ __device__ __forceinline__ void process_row(uint32_t e_info, uint32_t j4, uint32
   if (need_barrier) {
     row_barrier();
   }
-  row_math<DEG, -1>(addr, st, sp, sp_next, pol, scale_mode);
+  row_math<DEG, -1>(addr, st, sp, sp_next, pol, scale_mode, keep);
 }
 
 __device__ __forceinline__ void dispatch_row(int deg, uint32_t e_info, uint32_t j4, uint32_t neg_Z4, RowState& st,
@@ -509,7 +512,7 @@ __device__ __forceinline__ uint32_t spec_edge_addr(uint32_t jb, uint32_t jn4, ui
 
 template <class P, int M, int SCALE>
 __device__ __forceinline__ void spec_row(uint32_t jb, uint32_t jn4, uint32_t soft_s, RowState& st, uint4* st_thread,
-                                         int layers, uint64_t pol, int scale_mode)
+                                         int layers, uint64_t pol, int scale_mode, bool keep)
 {
   constexpr int DEG    = P::DEG[M];
   constexpr int STRIDE = (P::Z + 31) & ~31;
@@ -534,20 +537,20 @@ __device__ __forceinline__ void spec_row(uint32_t jb, uint32_t jn4, uint32_t sof
   } else {
     st = ld_state_sel<(uint32_t)((M + 1) * STRIDE * sizeof(uint4))>(st_thread, M + 1 < layers, pol);
   }
-  row_pass2<DEG, SCALE>(addr, rp, st_thread + M * STRIDE, pol, scale_mode);
+  row_pass2<DEG, SCALE>(addr, rp, st_thread + M * STRIDE, pol, scale_mode, keep);
 }
 
 // Rows M .. END-1 of one iteration; stops after the last row in use (at least four rows are always in use).
 template <class P, int M, int END, int SCALE>
 __device__ __forceinline__ void spec_rows_from(uint32_t jb, uint32_t jn4, uint32_t soft_s, RowState& st,
-                                               uint4* st_thread, int layers, uint64_t pol, int scale_mode)
+                                               uint4* st_thread, int layers, uint64_t pol, int scale_mode, bool keep)
 {
   if constexpr (M < END) {
     if (M >= 4 && M >= layers) {
       return;
     }
-    spec_row<P, M, SCALE>(jb, jn4, soft_s, st, st_thread, layers, pol, scale_mode);
-    spec_rows_from<P, M + 1, END, SCALE>(jb, jn4, soft_s, st, st_thread, layers, pol, scale_mode);
+    spec_row<P, M, SCALE>(jb, jn4, soft_s, st, st_thread, layers, pol, scale_mode, keep);
+    spec_rows_from<P, M + 1, END, SCALE>(jb, jn4, soft_s, st, st_thread, layers, pol, scale_mode, keep);
   }
 }
 
@@ -1088,6 +1091,9 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
         uint4* sp = st_thread;
         int    m0 = 0;
         bool   table_rows = true;
+        // The messages a row stores are read by the next iteration: the last one need not store them (a sixth of the
+        // state writes of a six-iteration decode, and dirty lines nobody will read).
+        const bool keep_state = (it + 1 != max_iter);
         if constexpr (SPEC_Z != 0) {
           if (spec) {
             // The leading rows of the hot shape run from the compiled-in program, the rest from the tables.
@@ -1101,19 +1107,19 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
                 // (a codeblock that uses only these rows wraps around to row 0 behind the last of them)
                 const uint4* spn = (m + 1 < layers) ? st_thread + (uint32_t)(m + 1) * st_stride : st_thread;
                 process_row<19>(einfo_s + 8u * 20u * (uint32_t)m, j4, neg_Z4, st, st_thread + (uint32_t)m * st_stride, spn,
-                                pol_keep, PDC_SCALE_X86, true);
+                                pol_keep, PDC_SCALE_X86, true, keep_state);
               }
               spec_rows_from<RowProgram<1, (SPEC_Z != 0 ? SPEC_Z : 384)>, H2_SPEC_FROM, H2_SPEC_ROWS, PDC_SCALE_X86>(
-                  soft_c + j4, jn4, soft_c, st, st_thread, layers, pol_keep, scale_mode);
+                  soft_c + j4, jn4, soft_c, st, st_thread, layers, pol_keep, scale_mode, keep_state);
             } else {
               // A high-rate codeblock uses these rows only: their compiled-in copy (a loop that small fits the
               // instruction cache; the table-driven copy above costs it 48 instructions per row).
               spec_rows_from<RowProgram<1, (SPEC_Z != 0 ? SPEC_Z : 384)>, 0, H2_SPEC_FROM, PDC_SCALE_X86>(
-                  soft_c + j4, jn4, soft_c, st, st_thread, layers, pol_keep, scale_mode);
+                  soft_c + j4, jn4, soft_c, st, st_thread, layers, pol_keep, scale_mode, keep_state);
             }
 #else
             spec_rows_from<RowProgram<1, (SPEC_Z != 0 ? SPEC_Z : 384)>, H2_SPEC_FROM, H2_SPEC_ROWS, PDC_SCALE_X86>(
-                soft_c + j4, jn4, soft_c, st, st_thread, layers, pol_keep, scale_mode);
+                soft_c + j4, jn4, soft_c, st, st_thread, layers, pol_keep, scale_mode, keep_state);
 #endif
             if constexpr (H2_SPEC_ROWS >= 46) {
               table_rows = false; // the whole schedule is compiled in: nothing left for the table-driven loop
