@@ -143,3 +143,40 @@ def test_pusch_decoder_harq(orc):
                 assert (s == H.soft[cb][:metas[cb].full_length]).all() and c == bool(H.crc_ok[cb])
             if so[0]:
                 break
+
+
+def test_codeblock_decoder_on_reused_buffers(orc):
+    """pusch_codeblock_decoder (rate dematcher + decoder on the buffer it keeps, pusch_codeblock_decoder.cpp:35-71) on
+    buffers that codeblocks of OTHER sizes used before and nobody cleared (rx_buffer_pool_impl.cpp:44): what an older,
+    longer codeblock left behind shows in the stale stretch of a limited-buffer transmission and decides how many rows
+    the decoder uses (ldpc_decoder_impl.cpp:86-114). The oracle against the compiled reference, buffers and results -
+    the GPU is held to the same histories in tests/test_gpu_parity.py (test_harq_sequences_random,
+    test_entry_taken_over_by_other_shapes)."""
+    from tests.vectors import awgn_llr, random_message
+    ref = po.Reference("auto")
+    rng = np.random.default_rng(8)
+    sizes = [z for z in LIFTING_SIZES if z <= 96]
+    for entry in range(12):
+        slot_r = np.zeros(po.MAX_CB_SIZE, np.int8)  # one pool entry, as the reference and as the oracle see it
+        slot_o = np.zeros(po.MAX_CB_SIZE, np.int8)
+        for owner in range(6):
+            bg = int(rng.integers(1, 3))
+            Z = int(rng.choice(sizes))
+            kb = 22 if bg == 1 else 10
+            N, K, Ksys = (66 if bg == 1 else 50) * Z, kb * Z, (kb - 2) * Z
+            qm = int(rng.choice([2, 4, 6, 8]))
+            crc = po.CRC24B if K > 64 else po.CRC16
+            F = 4 * int(rng.integers(0, max(1, min(Z // 2, (K - 26) // 4)))) if rng.random() < 0.5 else 0
+            nref = int(rng.integers(Ksys + 2 * Z, N + 1)) if rng.random() < 0.6 else 0
+            cw = orc.ldpc_encode(bg, Z, random_message(orc, bg, Z, F, crc, rng))
+            for t in range(int(rng.integers(1, 4))):
+                ncb = min(nref, N) if nref else N
+                E = int(rng.integers(max(1, (Ksys - F) // qm), max(2, (ncb - F) // qm + 1))) * qm
+                rv = 0 if t == 0 else int(rng.integers(0, 4))
+                llr = awgn_llr(orc.rate_match(cw, E, rv, qm, nref, F), float(rng.uniform(-2.0, 8.0)), rng)
+                es, mi = bool(rng.integers(0, 2)), int(rng.integers(1, 7))
+                a = ref.cb_decode(slot_r[:N], llr, t == 0, rv, qm, nref, F, crc, es, mi)
+                b = orc.cb_decode(slot_o[:N], llr, t == 0, rv, qm, nref, F, crc, es, mi)
+                case = (entry, owner, t, bg, Z, qm, F, nref, E, rv, es, mi)
+                assert (slot_r == slot_o).all(), case
+                assert a[0] == b[0] and (a[1] == b[1]).all(), case
