@@ -33,8 +33,12 @@ def _ptr(a):
 
 
 def build_oracle():
-    """Compile the C restatement (gcc only, a second)."""
-    subprocess.check_call(["make", "-s", "-C", str(HERE), "oracle"])
+    """Compile the C restatement (gcc only, a second). One process at a time: several ranks may load the oracle at once."""
+    import fcntl
+    (HERE / "_ref").mkdir(exist_ok=True)
+    with open(HERE / "_ref" / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        subprocess.check_call(["make", "-s", "-C", str(HERE), "oracle"])
 
 
 def build_reference():
