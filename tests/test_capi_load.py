@@ -71,3 +71,29 @@ def test_sm100a_code_only():
     out = subprocess.run(["cuobjdump", "-lelf", str(build.LIB)], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_cubin_is_sm100a_and_keeps_the_occupancy_the_design_counts_on():
+    """What DESIGN.md section 4 assumes about the compiled kernels, read from the library itself (cuobjdump; no GPU): only
+    sm_100a code, the throughput decoder within 80 registers (two 384-thread CTAs per SM), the rate dematcher within 40
+    (six 256-thread CTAs per SM), no local-memory arrays, and every kernel of the path present."""
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(tool).exists():
+        pytest.skip("cuobjdump not available")
+    lib = str(build.build())
+    elfs = subprocess.run([tool, "-lelf", lib], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"\.(sm_\w+)\.cubin", elfs))
+    assert archs == {"sm_100a"}, archs
+    usage = subprocess.run([tool, "-res-usage", lib], capture_output=True, text=True).stdout
+    regs = {}
+    for name, reg, local in re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) .*?LOCAL:(\d+)", usage):
+        regs[name] = int(reg)
+        assert int(local) == 0, (name, "local-memory array")
+    decoders = {k: v for k, v in regs.items() if "ldpc_decode_h2_kernelILi384ELi2E" in k}
+    assert len(decoders) >= 3 and max(decoders.values()) <= 80, decoders
+    dematcher = [v for k, v in regs.items() if "rate_dematch_kernel" in k]
+    assert dematcher and max(dematcher) <= 40, dematcher
+    for kernel in ("demod_kernel", "tb_assemble_kernel", "ulsch_sch_kernel", "ldpc_encode_rm_kernel", "prg_kernel"):
+        assert any(kernel in k for k in regs), kernel
